@@ -1,0 +1,148 @@
+/*
+ * osl_b200.h -- C ABI of libosl_b200.so: the B200-native (sm_100a) replacement for the per-frame hot path of
+ * dkotfis/Octree-SLAM (depth map -> sparse voxel octree integration, octree raycast, voxel extraction).
+ *
+ * Plain C, POD arguments, explicit stream, int status, never exit().  Each entry point names the reference
+ * interface it replaces (file:line in the reference tree).  The reference's own "extern \"C\"" functions take C++
+ * references and glm types by value and are therefore not a C ABI; the C++ shim under
+ * include/octree_slam/ re-creates those verbatim signatures on top of this header.
+ *
+ * Node pool layout (kept from the reference, common_types.h:75-79, svo.cu:130-136,269-275):
+ *   unsigned int pool[2 * n_nodes]; node i = { word0 = pool[2i], word1 = pool[2i+1] }
+ *   word0: bit 30 = has-children, bits 0-29 = index (in nodes) of the first of 8 contiguous children
+ *   word1: R | G<<8 | B<<16 | A<<24  (A = observation counter: 127 empty, +2 per observation, saturates at 255)
+ *   the root is implicit; its 8 children are nodes 0..7.
+ *
+ * All matrices are 16 floats, column-major (glm::mat4 memory layout).
+ * "d_" pointers are device pointers on the tree's device, "h_" pointers are host pointers.
+ * stream arguments are cudaStream_t passed as void* (NULL = the legacy default stream).
+ */
+#ifndef OSL_B200_H_
+#define OSL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int osl_status;
+enum {
+  OSL_OK = 0,
+  OSL_ERR_INVALID = -1,       /* bad argument */
+  OSL_ERR_CUDA = -2,          /* a CUDA runtime call failed (osl_last_cuda_error() has the code) */
+  OSL_ERR_OOM = -3,           /* device allocation failed */
+  OSL_ERR_POOL_OVERFLOW = -4, /* > 2^30 nodes: the 30-bit child index of the node layout is exhausted */
+  OSL_ERR_UNSUPPORTED = -5
+};
+
+#define OSL_MAX_DEPTH 20 /* 1 + 3*20 = 61 key bits */
+
+typedef struct osl_svo osl_svo; /* one GPU-resident octree (the reference's OctreeNode::gpu_data_/gpu_size_) */
+
+/* Per-frame counters of the last integrate call + running totals. */
+typedef struct osl_counters {
+  int64_t n_points;                     /* N  inputs of the last call */
+  int64_t n_valid;                      /* inputs with a valid key */
+  int64_t n_unique;                     /* U  distinct leaf keys */
+  int64_t n_split;                      /* S  nodes split == 8-node tiles allocated */
+  int64_t pass_sizes[OSL_MAX_DEPTH + 1];/* |codes[i]| of the reference's pass i (svo.cu:220) */
+  int64_t parents[OSL_MAX_DEPTH + 1];   /* P_l distinct touched nodes at depth l (l = 0 is the root) */
+  int64_t n_nodes;                      /* octree_size after the call (nodes) */
+  int64_t algorithmic_bytes;            /* 5N (or bytes of the point inputs) + 8U + 68S + 68*sum(P_l) */
+  int64_t frames;                       /* integrate calls so far */
+} osl_counters;
+
+typedef struct osl_raycast_params {
+  float fx, fy;     /* ray-direction focal lengths; reference hard-codes 532.57 / 531.54 (cone_tracing_kernels.cu:45-46) */
+  float start_dist; /* 0.002  (cone_tracing_kernels.cu:27) */
+  float max_range;  /* 10.0   (cone_tracing_kernels.cu:24) */
+  int mode;         /* 0 = ref_exact (accumulator reset every step, reference quirk Q8); 1 = fixed_accumulate */
+} osl_raycast_params;
+
+typedef struct osl_raycast_stats {
+  int64_t rays, steps, visits; /* visits = word0 reads in descents; bytes = 4*rays + 4*visits + 4*steps */
+} osl_raycast_stats;
+
+/* ---- lifetime -------------------------------------------------------------------------------------------- */
+
+/* Replaces: Octree::Octree + OctreeNode::pushToGPU + svo.cu:24-31 initOctree.
+ * half_edge is Octree::size_ (HALF the cube edge, octree.h:118).  reserve_nodes pre-sizes the pool (0 = default);
+ * the pool grows geometrically when needed (replacing the reference's per-frame realloc+copy, svo.cu:664-668). */
+osl_status osl_svo_create(osl_svo** out, const float center[3], float half_edge, int max_depth,
+                          size_t reserve_nodes, int device);
+void osl_svo_destroy(osl_svo* t);
+/* Drop all nodes (octree_size = 0), keep the allocations. */
+osl_status osl_svo_reset(osl_svo* t);
+/* 1 (default) reproduces reference quirk Q3 (svo.cu:123 `while (r_key >= 15)`); 0 = leaves are never split. */
+osl_status osl_svo_set_quirks(osl_svo* t, int ref_quirks);
+
+/* ---- integrate (svo.h:14-16) ------------------------------------------------------------------------------- */
+
+/* Fused main.cpp:39-44: generateVertexMap (image_kernels.cu:24-53) -> transformVertexMap (:206-215) ->
+ * svoFromPointCloud (svo.cu:642-696).  d_depth: w*h uint16 millimetres, d_rgb: w*h*3 bytes (Color256).
+ * Asynchronous on `stream` except when the pool has to grow. */
+osl_status osl_integrate_depth(osl_svo* t, const uint16_t* d_depth, const uint8_t* d_rgb, int w, int h, float fx,
+                               float fy, const float pose[16], void* stream);
+/* Same from host buffers (what OpenNIDevice::readFrame + mainLoop do, openni_device.cpp:122,144): H2D copies, the
+ * integrate, and a stream synchronize. */
+osl_status osl_integrate_depth_host(osl_svo* t, const uint16_t* h_depth, const uint8_t* h_rgb, int w, int h, float fx,
+                                    float fy, const float pose[16], void* stream);
+/* Replaces svoFromPointCloud (svo.h:16, svo.cu:642): d_xyz = n glm::vec3 (12-byte stride), d_rgb = n Color256. */
+osl_status osl_integrate_points(osl_svo* t, const float* d_xyz, const uint8_t* d_rgb, int n, void* stream);
+/* Replaces svoFromVoxelGrid (svo.h:14, svo.cu:584): n glm::vec4 centres and n glm::vec4 colours (0..1 floats). */
+osl_status osl_integrate_voxels(osl_svo* t, const float* d_centers4, const float* d_colors4, int n, void* stream);
+
+/* ---- views of the tree ------------------------------------------------------------------------------------- */
+
+/* Replaces Octree::extractSVO (octree.cpp:339-360): aliases the pool, no ownership.  Synchronizes. */
+osl_status osl_svo_view(const osl_svo* t, const uint32_t** d_pool, int* n_nodes, float center[3], float* half_edge);
+int osl_svo_size(const osl_svo* t); /* nodes; synchronizes */
+osl_status osl_svo_download(const osl_svo* t, uint32_t* h_pool, int cap_nodes);
+osl_status osl_svo_upload(osl_svo* t, const uint32_t* h_pool, int n_nodes);
+osl_status osl_get_counters(const osl_svo* t, osl_counters* out);
+
+/* ---- raycast (cone_tracing_kernels.h:16) ------------------------------------------------------------------- */
+
+/* Replaces rendering::coneTraceSVO (cone_tracing_kernels.cu:157-198).  d_out: w*h uchar4 {R,G,B,A}.
+ * prm == NULL uses the reference constants in ref_exact mode.  stats may be NULL. */
+osl_status osl_raycast(const osl_svo* t, uint8_t* d_out_rgba, int w, int h, float fov_deg, const float view[16],
+                       const osl_raycast_params* prm, void* stream);
+osl_status osl_raycast_host(const osl_svo* t, uint8_t* h_out_rgba, int w, int h, float fov_deg, const float view[16],
+                            const osl_raycast_params* prm, osl_raycast_stats* stats, void* stream);
+/* Raycast an arbitrary pool (SVO struct by value in the reference). */
+osl_status osl_raycast_pool(const uint32_t* d_pool, const float center[3], float half_edge, uint8_t* d_out_rgba, int w,
+                            int h, float fov_deg, const float view[16], const osl_raycast_params* prm,
+                            osl_raycast_stats* h_stats, void* stream);
+
+/* ---- extraction (svo.h:18) --------------------------------------------------------------------------------- */
+
+/* Replaces extractVoxelGridFromSVO (svo.cu:699-745).  Returns the voxel count in *n_out; when the d_ buffers are
+ * non-NULL and cap >= count they receive glm::vec4 centres / colours (and optionally int64 leading-1 keys). */
+osl_status osl_extract_voxels(const osl_svo* t, int max_depth, float* d_centers4, float* d_colors4, int64_t* d_keys,
+                              int64_t cap, int64_t* n_out, void* stream);
+
+/* ---- per-frame image kernels (image_kernels.h:21,24,52) ---------------------------------------------------- */
+
+osl_status osl_generate_vertex_map(const uint16_t* d_depth, float* d_xyz, int width, int height, float fx, float fy,
+                                   int img_w, int img_h, void* stream);
+osl_status osl_transform_vertex_map(float* d_xyz, const float trans[16], int n, void* stream);
+/* bbox[6] = {min xyz, max xyz}, in/out exactly like BoundingBox& in the reference (left fold seeded with the
+ * incoming box; points with non-finite x or z are skipped; a (0,0,0) accumulator is replaced). */
+osl_status osl_point_cloud_bbox(const float* d_xyz, int n, float bbox[6], void* stream);
+/* computeKeys<vec3|vec4> (svo.cu:93-106): leading-1 Morton keys, 1 for invalid points.  stride = 3 or 4 floats. */
+osl_status osl_compute_keys(const float* d_pts, int stride, int n, const float center[3], float half_edge,
+                            int max_depth, int64_t* d_keys, void* stream);
+
+/* ---- misc -------------------------------------------------------------------------------------------------- */
+const char* osl_status_string(osl_status s);
+int osl_last_cuda_error(void);
+const char* osl_version(void);
+/* number of kernels this library has launched in this process (for bench.py's gpu_launches) */
+int64_t osl_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OSL_B200_H_ */

@@ -1,0 +1,123 @@
+"""ctypes binding of libosl_b200.so (include/osl_b200.h) -- the same stub a reference maintainer would write.
+
+No torch types cross the boundary: device buffers are passed as raw pointers (torch tensors' data_ptr(), or any
+CUDA allocation), host buffers as numpy arrays.  If the CUDA library is missing this module raises: there is no CPU
+fallback in the product path.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libosl_b200.so")
+MAX_DEPTH = 20
+
+OSL_OK = 0
+STATUS = {0: "OSL_OK", -1: "OSL_ERR_INVALID", -2: "OSL_ERR_CUDA", -3: "OSL_ERR_OOM",
+          -4: "OSL_ERR_POOL_OVERFLOW", -5: "OSL_ERR_UNSUPPORTED"}
+
+EXPORTS = [
+    "osl_svo_create", "osl_svo_destroy", "osl_svo_reset", "osl_svo_set_quirks",
+    "osl_integrate_depth", "osl_integrate_depth_host", "osl_integrate_points", "osl_integrate_voxels",
+    "osl_svo_view", "osl_svo_size", "osl_svo_download", "osl_svo_upload", "osl_get_counters",
+    "osl_raycast", "osl_raycast_host", "osl_raycast_pool", "osl_extract_voxels",
+    "osl_generate_vertex_map", "osl_transform_vertex_map", "osl_point_cloud_bbox", "osl_compute_keys",
+    "osl_status_string", "osl_last_cuda_error", "osl_version", "osl_launch_count",
+]
+
+
+class OslError(RuntimeError):
+    def __init__(self, status, where):
+        self.status = status
+        super().__init__("%s failed: %s (cuda error %d)" % (where, STATUS.get(status, status),
+                                                            lib().osl_last_cuda_error()))
+
+
+class Counters(C.Structure):
+    _fields_ = [
+        ("n_points", C.c_int64), ("n_valid", C.c_int64), ("n_unique", C.c_int64), ("n_split", C.c_int64),
+        ("pass_sizes", C.c_int64 * (MAX_DEPTH + 1)), ("parents", C.c_int64 * (MAX_DEPTH + 1)),
+        ("n_nodes", C.c_int64), ("algorithmic_bytes", C.c_int64), ("frames", C.c_int64),
+    ]
+
+
+class RaycastParams(C.Structure):
+    _fields_ = [("fx", C.c_float), ("fy", C.c_float), ("start_dist", C.c_float), ("max_range", C.c_float),
+                ("mode", C.c_int)]
+
+
+class RaycastStats(C.Structure):
+    _fields_ = [("rays", C.c_int64), ("steps", C.c_int64), ("visits", C.c_int64)]
+
+
+_lib = None
+
+
+def lib():
+    """Loads the CUDA library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("libosl_b200.so is not built: run `python __graft_entry__.py build` "
+                          "(the product path has no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, f32, i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64
+    fp = C.POINTER(C.c_float)
+    sig = {
+        "osl_svo_create": (i32, [C.POINTER(vp), fp, f32, i32, C.c_size_t, i32]),
+        "osl_svo_destroy": (None, [vp]),
+        "osl_svo_reset": (i32, [vp]),
+        "osl_svo_set_quirks": (i32, [vp, i32]),
+        "osl_integrate_depth": (i32, [vp, vp, vp, i32, i32, f32, f32, fp, vp]),
+        "osl_integrate_depth_host": (i32, [vp, vp, vp, i32, i32, f32, f32, fp, vp]),
+        "osl_integrate_points": (i32, [vp, vp, vp, i32, vp]),
+        "osl_integrate_voxels": (i32, [vp, vp, vp, i32, vp]),
+        "osl_svo_view": (i32, [vp, C.POINTER(vp), C.POINTER(i32), fp, fp]),
+        "osl_svo_size": (i32, [vp]),
+        "osl_svo_download": (i32, [vp, vp, i32]),
+        "osl_svo_upload": (i32, [vp, vp, i32]),
+        "osl_get_counters": (i32, [vp, C.POINTER(Counters)]),
+        "osl_raycast": (i32, [vp, vp, i32, i32, f32, fp, C.POINTER(RaycastParams), vp]),
+        "osl_raycast_host": (i32, [vp, vp, i32, i32, f32, fp, C.POINTER(RaycastParams), C.POINTER(RaycastStats), vp]),
+        "osl_raycast_pool": (i32, [vp, fp, f32, vp, i32, i32, f32, fp, C.POINTER(RaycastParams),
+                                   C.POINTER(RaycastStats), vp]),
+        "osl_extract_voxels": (i32, [vp, i32, vp, vp, vp, i64, C.POINTER(i64), vp]),
+        "osl_generate_vertex_map": (i32, [vp, vp, i32, i32, f32, f32, i32, i32, vp]),
+        "osl_transform_vertex_map": (i32, [vp, fp, i32, vp]),
+        "osl_point_cloud_bbox": (i32, [vp, i32, fp, vp]),
+        "osl_compute_keys": (i32, [vp, i32, i32, fp, f32, i32, vp, vp]),
+        "osl_status_string": (C.c_char_p, [i32]),
+        "osl_last_cuda_error": (i32, []),
+        "osl_version": (C.c_char_p, []),
+        "osl_launch_count": (i64, []),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return _lib
+
+
+def _check(status, where):
+    if status != OSL_OK:
+        raise OslError(status, where)
+
+
+def _f(arr):
+    arr = [float(x) for x in arr]
+    return (C.c_float * len(arr))(*arr)
+
+
+def mat_colmajor(m):
+    """4x4 matrix in math convention (m[r][c]) -> 16 floats, column-major (glm::mat4 memory order)."""
+    return np.ascontiguousarray(np.asarray(m, dtype=np.float32).T).reshape(16)
+
+
+IDENTITY = np.eye(4, dtype=np.float32)
+
+
+def _hptr(a):
+    return a.ctypes.data_as(C.c_void_p)

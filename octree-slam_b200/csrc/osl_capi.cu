@@ -1,0 +1,247 @@
+// osl_capi.cu -- the C ABI of libosl_b200.so (include/osl_b200.h): object lifetime, memory, entry points.
+#include <stdio.h>
+#include <string.h>
+
+#include "osl_internal.cuh"
+
+int g_osl_last_cuda_error = 0;
+long long g_osl_launches = 0;
+
+extern "C" {
+
+const char* osl_version(void) { return "osl_b200 0.1 (sm_100a)"; }
+int osl_last_cuda_error(void) { return g_osl_last_cuda_error; }
+int64_t osl_launch_count(void) { return g_osl_launches; }
+
+const char* osl_status_string(osl_status s) {
+  switch (s) {
+    case OSL_OK: return "ok";
+    case OSL_ERR_INVALID: return "invalid argument";
+    case OSL_ERR_CUDA: return "CUDA error";
+    case OSL_ERR_OOM: return "out of device memory";
+    case OSL_ERR_POOL_OVERFLOW: return "node pool overflow (2^30 nodes)";
+    case OSL_ERR_UNSUPPORTED: return "unsupported";
+  }
+  return "unknown";
+}
+
+
+osl_status osl_svo_create(osl_svo** out, const float center[3], float half_edge, int max_depth, size_t reserve_nodes,
+                          int device) {
+  if (!out || !center || max_depth < 1 || max_depth > OSL_MAX_DEPTH || !(half_edge > 0.0f)) return OSL_ERR_INVALID;
+  *out = nullptr;
+  OSL_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  OSL_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (!prop.cooperativeLaunch) return OSL_ERR_UNSUPPORTED;
+  osl_svo* t = new osl_svo();
+  memset(t, 0, sizeof(*t));
+  t->device = device;
+  t->tp.cx = center[0]; t->tp.cy = center[1]; t->tp.cz = center[2];
+  t->tp.half = half_edge;
+  t->tp.D = max_depth;
+  t->tp.quirks = 1;
+  t->num_sms = prop.multiProcessorCount;
+  int occ = osl_sort_occupancy();
+  if (occ < 1) { delete t; return OSL_ERR_CUDA; }
+  if (occ > 4) occ = 4;
+  t->sort_grid = occ * t->num_sms;
+  osl_status rc = OSL_OK;
+  do {
+    if (cudaMalloc(&t->d_cta_hist, (size_t)t->sort_grid * 256 * sizeof(u32)) != cudaSuccess) { rc = OSL_ERR_OOM; break; }
+    if (cudaMalloc(&t->d_fs, sizeof(FrameState)) != cudaSuccess) { rc = OSL_ERR_OOM; break; }
+    if (cudaMemset(t->d_fs, 0, sizeof(FrameState)) != cudaSuccess) { rc = OSL_ERR_CUDA; break; }
+    if (cudaMallocHost(&t->h_fs, sizeof(FrameState)) != cudaSuccess) { rc = OSL_ERR_OOM; break; }
+    memset(t->h_fs, 0, sizeof(FrameState));
+    rc = osl_grow_pool(t, reserve_nodes ? reserve_nodes : ((size_t)1 << 20), 0);
+    if (rc) break;
+    if (cudaMemset(t->d_pool, 0, 64) != cudaSuccess) { rc = OSL_ERR_CUDA; break; }
+  } while (0);
+  if (rc) { osl_svo_destroy(t); return rc; }
+  *out = t;
+  return OSL_OK;
+}
+
+void osl_svo_destroy(osl_svo* t) {
+  if (!t) return;
+  cudaSetDevice(t->device);
+  cudaDeviceSynchronize();
+  cudaFree(t->d_pool);
+  cudaFree(t->d_keysA); cudaFree(t->d_keysB); cudaFree(t->d_payA); cudaFree(t->d_payB);
+  cudaFree(t->d_m); cudaFree(t->d_s); cudaFree(t->d_blockcnt); cudaFree(t->d_emit_status);
+  cudaFree(t->d_cta_hist); cudaFree(t->d_level_mem); cudaFree(t->d_fs);
+  cudaFree(t->d_depth_stage); cudaFree(t->d_rgb_stage); cudaFree(t->d_xyz_stage);
+  if (t->h_fs) cudaFreeHost(t->h_fs);
+  if (t->h_pin_depth) cudaFreeHost(t->h_pin_depth);
+  if (t->h_pin_rgb) cudaFreeHost(t->h_pin_rgb);
+  delete t;
+}
+
+osl_status osl_svo_reset(osl_svo* t) {
+  if (!t) return OSL_ERR_INVALID;
+  OSL_CUDA(cudaSetDevice(t->device));
+  OSL_CUDA(cudaDeviceSynchronize());
+  OSL_CUDA(cudaMemset(t->d_pool, 0, 64));
+  t->size = 0;
+  memset(&t->counters, 0, sizeof(t->counters));
+  return OSL_OK;
+}
+
+osl_status osl_svo_set_quirks(osl_svo* t, int ref_quirks) {
+  if (!t) return OSL_ERR_INVALID;
+  t->tp.quirks = ref_quirks ? 1 : 0;
+  return OSL_OK;
+}
+
+osl_status osl_integrate_depth(osl_svo* t, const uint16_t* d_depth, const uint8_t* d_rgb, int w, int h, float fx,
+                               float fy, const float pose[16], void* stream) {
+  if (!t || !d_depth || !d_rgb || w <= 0 || h <= 0 || !pose || (long long)w * h >= (1ll << 30)) return OSL_ERR_INVALID;
+  OSL_CUDA(cudaSetDevice(t->device));
+  EmitParams ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.depth = d_depth; ep.rgb = d_rgb; ep.w = w; ep.h = h; ep.fx = fx; ep.fy = fy;
+  memcpy(ep.M, pose, sizeof(ep.M));
+  ep.n = w * h; ep.mode = 0;
+  return osl_run_integrate(t, ep, nullptr, (cudaStream_t)stream);
+}
+
+static osl_status ensure_stage(osl_svo* t, size_t n) {
+  if (n <= t->stage_cap) return OSL_OK;
+  cudaFree(t->d_depth_stage); cudaFree(t->d_rgb_stage);
+  if (t->h_pin_depth) cudaFreeHost(t->h_pin_depth);
+  if (t->h_pin_rgb) cudaFreeHost(t->h_pin_rgb);
+  t->d_depth_stage = nullptr; t->d_rgb_stage = nullptr; t->h_pin_depth = t->h_pin_rgb = nullptr; t->stage_cap = 0;
+  OSL_CUDA(cudaMalloc(&t->d_depth_stage, n * 2));
+  OSL_CUDA(cudaMalloc(&t->d_rgb_stage, n * 3));
+  OSL_CUDA(cudaMallocHost(&t->h_pin_depth, n * 2));
+  OSL_CUDA(cudaMallocHost(&t->h_pin_rgb, n * 3));
+  t->stage_cap = n;
+  return OSL_OK;
+}
+
+osl_status osl_integrate_depth_host(osl_svo* t, const uint16_t* h_depth, const uint8_t* h_rgb, int w, int h, float fx,
+                                    float fy, const float pose[16], void* stream) {
+  if (!t || !h_depth || !h_rgb || w <= 0 || h <= 0 || !pose) return OSL_ERR_INVALID;
+  OSL_CUDA(cudaSetDevice(t->device));
+  const size_t n = (size_t)w * h;
+  osl_status rc = ensure_stage(t, n);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  // caller memory may be pageable: stage through pinned buffers so the copies are true async DMA
+  memcpy(t->h_pin_depth, h_depth, n * 2);
+  memcpy(t->h_pin_rgb, h_rgb, n * 3);
+  OSL_CUDA(cudaMemcpyAsync(t->d_depth_stage, t->h_pin_depth, n * 2, cudaMemcpyHostToDevice, st));
+  OSL_CUDA(cudaMemcpyAsync(t->d_rgb_stage, t->h_pin_rgb, n * 3, cudaMemcpyHostToDevice, st));
+  rc = osl_integrate_depth(t, t->d_depth_stage, t->d_rgb_stage, w, h, fx, fy, pose, stream);
+  if (rc) return rc;
+  OSL_CUDA(cudaStreamSynchronize(st));
+  return OSL_OK;
+}
+
+osl_status osl_integrate_points(osl_svo* t, const float* d_xyz, const uint8_t* d_rgb, int n, void* stream) {
+  if (!t || n < 0 || (n > 0 && (!d_xyz || !d_rgb))) return OSL_ERR_INVALID;
+  OSL_CUDA(cudaSetDevice(t->device));
+  EmitParams ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.pts = d_xyz; ep.stride = 3; ep.rgb = d_rgb; ep.n = n; ep.mode = 1;
+  return osl_run_integrate(t, ep, nullptr, (cudaStream_t)stream);
+}
+
+osl_status osl_integrate_voxels(osl_svo* t, const float* d_centers4, const float* d_colors4, int n, void* stream) {
+  if (!t || n < 0 || (n > 0 && (!d_centers4 || !d_colors4))) return OSL_ERR_INVALID;
+  OSL_CUDA(cudaSetDevice(t->device));
+  EmitParams ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.pts = d_centers4; ep.stride = 4; ep.n = n; ep.mode = 2;
+  return osl_run_integrate(t, ep, d_colors4, (cudaStream_t)stream);
+}
+
+osl_status osl_svo_view(const osl_svo* t, const uint32_t** d_pool, int* n_nodes, float center[3], float* half_edge) {
+  if (!t) return OSL_ERR_INVALID;
+  OSL_CUDA(cudaSetDevice(t->device));
+  OSL_CUDA(cudaDeviceSynchronize());
+  if (d_pool) *d_pool = t->d_pool;
+  if (n_nodes) *n_nodes = t->size;
+  if (center) { center[0] = t->tp.cx; center[1] = t->tp.cy; center[2] = t->tp.cz; }
+  if (half_edge) *half_edge = t->tp.half;
+  return OSL_OK;
+}
+
+int osl_svo_size(const osl_svo* t) { return t ? t->size : 0; }
+
+osl_status osl_svo_download(const osl_svo* t, uint32_t* h_pool, int cap_nodes) {
+  if (!t || !h_pool || cap_nodes < t->size) return OSL_ERR_INVALID;
+  OSL_CUDA(cudaSetDevice(t->device));
+  OSL_CUDA(cudaDeviceSynchronize());
+  if (t->size > 0) OSL_CUDA(cudaMemcpy(h_pool, t->d_pool, (size_t)t->size * 8, cudaMemcpyDeviceToHost));
+  return OSL_OK;
+}
+
+osl_status osl_svo_upload(osl_svo* t, const uint32_t* h_pool, int n_nodes) {
+  if (!t || n_nodes < 0 || (n_nodes > 0 && !h_pool)) return OSL_ERR_INVALID;
+  OSL_CUDA(cudaSetDevice(t->device));
+  OSL_CUDA(cudaDeviceSynchronize());
+  osl_status rc = osl_grow_pool(t, (size_t)(n_nodes > 8 ? n_nodes : 8), 0);
+  if (rc) return rc;
+  if (n_nodes > 0) OSL_CUDA(cudaMemcpy(t->d_pool, h_pool, (size_t)n_nodes * 8, cudaMemcpyHostToDevice));
+  else OSL_CUDA(cudaMemset(t->d_pool, 0, 64));
+  t->size = n_nodes;
+  return OSL_OK;
+}
+
+osl_status osl_get_counters(const osl_svo* t, osl_counters* out) {
+  if (!t || !out) return OSL_ERR_INVALID;
+  *out = t->counters;
+  return OSL_OK;
+}
+
+osl_status osl_raycast_pool(const uint32_t* d_pool, const float center[3], float half_edge, uint8_t* d_out_rgba, int w,
+                            int h, float fov_deg, const float view[16], const osl_raycast_params* prm,
+                            osl_raycast_stats* h_stats, void* stream) {
+  if (!d_pool || !center || !d_out_rgba || !view) return OSL_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned long long* d_stats = nullptr;
+  if (h_stats) {
+    OSL_CUDA(cudaMalloc(&d_stats, 16));
+    OSL_CUDA(cudaMemsetAsync(d_stats, 0, 16, st));
+  }
+  osl_status rc = osl_launch_raycast(d_pool, center, half_edge, d_out_rgba, w, h, fov_deg, view, prm, d_stats, st);
+  if (h_stats) {
+    unsigned long long s[2] = {0, 0};
+    cudaError_t e = cudaMemcpyAsync(s, d_stats, 16, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_stats);
+    if (rc == OSL_OK) OSL_CUDA(e);
+    h_stats->rays = (int64_t)w * h; h_stats->steps = (int64_t)s[0]; h_stats->visits = (int64_t)s[1];
+  }
+  return rc;
+}
+
+osl_status osl_raycast(const osl_svo* t, uint8_t* d_out_rgba, int w, int h, float fov_deg, const float view[16],
+                       const osl_raycast_params* prm, void* stream) {
+  if (!t || t->size == 0) return OSL_ERR_INVALID;
+  OSL_CUDA(cudaSetDevice(t->device));
+  const float c[3] = {t->tp.cx, t->tp.cy, t->tp.cz};
+  return osl_raycast_pool(t->d_pool, c, t->tp.half, d_out_rgba, w, h, fov_deg, view, prm, nullptr, stream);
+}
+
+osl_status osl_raycast_host(const osl_svo* t, uint8_t* h_out_rgba, int w, int h, float fov_deg, const float view[16],
+                            const osl_raycast_params* prm, osl_raycast_stats* stats, void* stream) {
+  if (!t || t->size == 0 || !h_out_rgba || w <= 0 || h <= 0) return OSL_ERR_INVALID;
+  OSL_CUDA(cudaSetDevice(t->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* d_out;
+  OSL_CUDA(cudaMalloc(&d_out, (size_t)w * h * 4));
+  const float c[3] = {t->tp.cx, t->tp.cy, t->tp.cz};
+  osl_status rc = osl_raycast_pool(t->d_pool, c, t->tp.half, d_out, w, h, fov_deg, view, prm, stats, stream);
+  cudaError_t e = cudaSuccess;
+  if (rc == OSL_OK) {
+    e = cudaMemcpyAsync(h_out_rgba, d_out, (size_t)w * h * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  }
+  cudaFree(d_out);
+  if (rc == OSL_OK) OSL_CUDA(e);
+  return rc;
+}
+
+}  // extern "C"

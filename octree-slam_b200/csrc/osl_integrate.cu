@@ -1,0 +1,711 @@
+// osl_integrate.cu -- depth map / point cloud / voxel grid  ->  sparse voxel octree, one frame per call.
+//
+// Replaces the reference's svoFromPointCloud / svoFromVoxelGrid (svo.cu:584-696) together with the per-frame
+// image kernels that feed it (image_kernels.cu:24-53,206-215).  Same results (node indices, node words), very
+// different structure -- see DESIGN.md section 3:
+//
+//   k_emit     back-project + pose + Morton key per input, ordered compaction of the valid ones (look-back scan)
+//   k_sort     ONE cooperative persistent kernel: LSD radix sort (8-bit digits) of (key, payload), all passes
+//   k_analyze  per sorted key: common-prefix length with its predecessor (=> which tree levels it heads), walk of the
+//              pre-frame tree to the frontier, per-block counts of level heads and of (frontier depth, depth) buckets
+//   k_scan     exclusive scan of the block counts; reproduces the reference's allocation order
+//              (pass = depth - frontier depth, then numeric key) as bucket bases; overflow check
+//   k_assign   dense per-level node lists with deterministic child-tile indices (existing or newly ranked)
+//   k_level    bottom-up, one thread per touched node: read/initialise its 64-byte child tile, blend leaves,
+//              link new tiles, mip-map (integer mean / max), write the tile back
+#include <cooperative_groups.h>
+
+#include "osl_internal.cuh"
+
+namespace cg = cooperative_groups;
+
+#define FULL 0xFFFFFFFFu
+
+// ------------------------------------------------------------------------------------------------ k_emit
+#define EMIT_THREADS 256
+#define EMIT_PPT 8
+#define EMIT_TILE (EMIT_THREADS * EMIT_PPT)
+
+__device__ __forceinline__ u32 ld_volatile_u32(const u32* p) { return *(const volatile u32*)p; }
+__device__ __forceinline__ void st_volatile_u32(u32* p, u32 v) { *(volatile u32*)p = v; }
+
+__global__ void __launch_bounds__(EMIT_THREADS)
+k_emit(EmitParams p, TreeParams tp, int vec_ok, u64* __restrict__ keys, u32* __restrict__ pay, u32* status,
+       FrameState* fs) {
+  __shared__ u32 s_warp[EMIT_THREADS / 32];
+  __shared__ u32 s_base;
+  const int tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int first = tile * EMIT_TILE + tid * EMIT_PPT;
+
+  u64 k[EMIT_PPT];
+  u32 vmask = 0;
+  if (p.mode == 0) {
+    int dv[EMIT_PPT];
+    if (vec_ok && first + EMIT_PPT <= p.n) {  // 128-bit load of 8 depth pixels
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(p.depth + first));
+      dv[0] = q.x & 0xFFFF; dv[1] = q.x >> 16; dv[2] = q.y & 0xFFFF; dv[3] = q.y >> 16;
+      dv[4] = q.z & 0xFFFF; dv[5] = q.z >> 16; dv[6] = q.w & 0xFFFF; dv[7] = q.w >> 16;
+    } else {
+#pragma unroll
+      for (int i = 0; i < EMIT_PPT; i++) dv[i] = (first + i < p.n) ? (int)__ldg(p.depth + first + i) : 0;
+    }
+    int x = first % p.w, y = first / p.w;
+#pragma unroll
+    for (int i = 0; i < EMIT_PPT; i++) {
+      float X, Y, Z;
+      osl_vertex(dv[i], x, y, p.w, p.h, p.w, p.h, p.fx, p.fy, X, Y, Z);
+      osl_transform(p.M, X, Y, Z);
+      const bool ok = osl_key(X, Y, Z, tp, k[i]) && (first + i < p.n);
+      vmask |= (u32)ok << i;
+      if (++x == p.w) { x = 0; y++; }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < EMIT_PPT; i++) {
+      const int idx = first + i;
+      bool ok = false;
+      k[i] = 0;
+      if (idx < p.n) {
+        const float* q = p.pts + (size_t)p.stride * idx;
+        ok = osl_key(__ldg(q), __ldg(q + 1), __ldg(q + 2), tp, k[i]);
+      }
+      vmask |= (u32)ok << i;
+    }
+  }
+
+  // block-wide exclusive scan of the per-thread valid counts
+  const u32 cnt = __popc(vmask);
+  u32 incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const u32 v = __shfl_up_sync(FULL, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  u32 woff = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < EMIT_THREADS / 32; w++) {
+    const u32 v = s_warp[w];
+    if (w < warp) woff += v;
+    total += v;
+  }
+
+  // ordered compaction: decoupled look-back over the tiles' valid counts, one warp, 32 predecessors per step.
+  // status word = flag(2 bits: 1 aggregate, 2 inclusive prefix) | value(30 bits)
+  if (warp == 0) {
+    u32 excl = 0;
+    if (tile == 0) {
+      if (lane == 0) st_volatile_u32(&status[0], (2u << 30) | total);
+    } else {
+      if (lane == 0) st_volatile_u32(&status[tile], (1u << 30) | total);
+      int look = tile - 1;
+      for (;;) {
+        const int idx = look - lane;
+        u32 v = (idx >= 0) ? ld_volatile_u32(&status[idx]) : (2u << 30);
+        while (__any_sync(FULL, (v >> 30) == 0)) {
+          if ((v >> 30) == 0) v = ld_volatile_u32(&status[idx]);
+        }
+        const u32 inc_mask = __ballot_sync(FULL, (v >> 30) == 2);
+        const int stop = inc_mask ? (__ffs(inc_mask) - 1) : 31;
+        u32 c = (lane <= stop) ? (v & OSL_MASK) : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
+        excl += c;
+        if (inc_mask) break;
+        look -= 32;
+      }
+      if (lane == 0) st_volatile_u32(&status[tile], (2u << 30) | (excl + total));
+    }
+    if (lane == 0) {
+      s_base = excl;
+      if (tile == gridDim.x - 1) {
+        fs->n_in = p.n;
+        fs->n_valid = (int)(excl + total);
+        fs->n_invalid_front = p.n - (int)(excl + total);
+      }
+    }
+  }
+  __syncthreads();
+
+  u32 pos = s_base + woff + (incl - cnt);
+#pragma unroll
+  for (int i = 0; i < EMIT_PPT; i++) {
+    if ((vmask >> i) & 1u) {
+      keys[pos] = k[i];
+      pay[pos] = (u32)(first + i);
+      pos++;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ k_sort
+#define SORT_THREADS 256
+#define SORT_ITEMS 8
+#define SORT_TILE (SORT_THREADS * SORT_ITEMS)
+#define SORT_WARPS (SORT_THREADS / 32)
+
+// One launch sorts (key, payload) by the low 8*passes key bits.  Stable LSD radix sort.  Each CTA owns a CONTIGUOUS
+// range of tiles, so a pass needs one grid barrier between "count" and "scatter" and the cross-CTA prefix is just a
+// sum over <= gridDim.x per-CTA histograms (no per-tile look-back chain, which serialises when all tiles are
+// co-resident as they are for one 640x480 frame).
+__global__ void __launch_bounds__(SORT_THREADS)
+k_sort(u64* kA, u32* pA, u64* kB, u32* pB, u32* cta_hist, const FrameState* fs, int passes) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ u32 s_hist[256];
+  __shared__ u32 s_whist[SORT_WARPS][256];
+  __shared__ u32 s_run[256];
+  __shared__ u32 s_base[256];
+  __shared__ u32 s_wsum[SORT_WARPS];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = fs->n_valid;
+  const int tiles = (n + SORT_TILE - 1) / SORT_TILE;
+  const int G = gridDim.x;
+  const int per = (tiles + G - 1) / G;
+  const int t0 = min(tiles, (int)blockIdx.x * per), t1 = min(tiles, t0 + per);
+  const u32 lt = lanemask_lt();
+
+  for (int pass = 0; pass < passes; pass++) {
+    const int shift = 8 * pass;
+    const u64* kin = (pass & 1) ? kB : kA;
+    const u32* pin = (pass & 1) ? pB : pA;
+    u64* kout = (pass & 1) ? kA : kB;
+    u32* pout = (pass & 1) ? pA : pB;
+
+    // phase 1: digit histogram of this CTA's tiles
+    s_hist[tid] = 0;
+    __syncthreads();
+    for (int tile = t0; tile < t1; tile++) {
+      const int base = tile * SORT_TILE;
+#pragma unroll
+      for (int i = 0; i < SORT_ITEMS; i++) {
+        const int idx = base + i * SORT_THREADS + tid;
+        if (idx < n) atomicAdd(&s_hist[(u32)(kin[idx] >> shift) & 0xFFu], 1u);
+      }
+    }
+    __syncthreads();
+    cta_hist[blockIdx.x * 256 + tid] = s_hist[tid];
+    grid.sync();
+
+    // phase 2: global base of digit `tid` for this CTA = (all smaller digits) + (same digit in earlier CTAs)
+    u32 before = 0, tot = 0;
+    for (int c = 0; c < G; c++) {
+      const u32 v = cta_hist[c * 256 + tid];
+      tot += v;
+      if (c < (int)blockIdx.x) before += v;
+    }
+    u32 incl = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const u32 v = __shfl_up_sync(FULL, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_wsum[warp] = incl;
+    __syncthreads();
+    u32 woff = 0;
+#pragma unroll
+    for (int w = 0; w < SORT_WARPS; w++)
+      if (w < warp) woff += s_wsum[w];
+    s_run[tid] = woff + (incl - tot) + before;
+    __syncthreads();
+
+    for (int tile = t0; tile < t1; tile++) {
+#pragma unroll
+      for (int w = 0; w < SORT_WARPS; w++) s_whist[w][tid] = 0;
+      __syncthreads();
+      // warp-striped load keeps (warp, item, lane) order == global index order (stability)
+      const int base = tile * SORT_TILE + warp * (32 * SORT_ITEMS);
+      u64 key[SORT_ITEMS];
+      u32 val[SORT_ITEMS], rank[SORT_ITEMS];
+#pragma unroll
+      for (int i = 0; i < SORT_ITEMS; i++) {
+        const int idx = base + i * 32 + lane;
+        const bool ok = idx < n;
+        key[i] = ok ? kin[idx] : ~0ull;
+        val[i] = ok ? pin[idx] : 0u;
+      }
+#pragma unroll
+      for (int i = 0; i < SORT_ITEMS; i++) {
+        const bool ok = (base + i * 32 + lane) < n;
+        const u32 digit = ok ? ((u32)(key[i] >> shift) & 0xFFu) : 256u;
+        const u32 peers = __match_any_sync(FULL, digit);
+        const int leader = __ffs(peers) - 1;
+        u32 old = 0;
+        if (lane == leader && ok) {
+          old = s_whist[warp][digit];
+          s_whist[warp][digit] = old + __popc(peers);
+        }
+        old = __shfl_sync(FULL, old, leader);
+        rank[i] = old + __popc(peers & lt);
+        __syncwarp();
+      }
+      __syncthreads();
+      {  // digit `tid`: exclusive scan over the warps, advance the running base
+        u32 sum = 0;
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; w++) {
+          const u32 v = s_whist[w][tid];
+          s_whist[w][tid] = sum;
+          sum += v;
+        }
+        const u32 b = s_run[tid];
+        s_base[tid] = b;
+        s_run[tid] = b + sum;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < SORT_ITEMS; i++) {
+        if ((base + i * 32 + lane) < n) {
+          const u32 digit = (u32)(key[i] >> shift) & 0xFFu;
+          const u32 pos = s_base[digit] + s_whist[warp][digit] + rank[i];
+          kout[pos] = key[i];
+          pout[pos] = val[i];
+        }
+      }
+      __syncthreads();
+    }
+    grid.sync();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ k_analyze
+#define AN_THREADS 512
+#define AN_WARPS (AN_THREADS / 32)
+#define NC_MAX OSL_NCOUNT(OSL_MAXD)
+
+__device__ __forceinline__ int key_digit(u64 key, int D, int d) { return (int)((key >> (3 * (D - d))) & 7ull); }
+
+// Walk the PRE-FRAME tree along `key` (splitKeys, svo.cu:108-142).  Returns the frontier depth s: the depth of the
+// first node on the path without the has-children flag, OSL_NONE if the path exists down to the leaf's parent.
+// Q3 (svo.cu:123 `>= 15`): when the last digit is 7 the reference also tests the LEAF and reports it for splitting.
+__device__ __forceinline__ int walk_frontier(const u32* __restrict__ pool, u64 key, int D, int quirks) {
+  u32 node = (u32)key_digit(key, D, 1);
+  for (int t = 1; t <= D - 1; t++) {
+    const u32 w0 = pool[2 * (size_t)node];
+    if (!(w0 & OSL_FLAG)) return t;
+    node = (w0 & OSL_MASK) + (u32)key_digit(key, D, t + 1);
+  }
+  if (quirks && key_digit(key, D, D) == 7) {
+    if (!(pool[2 * (size_t)node] & OSL_FLAG)) return D;
+  }
+  return OSL_NONE;
+}
+
+__global__ void __launch_bounds__(AN_THREADS)
+k_analyze(const u64* __restrict__ keys, const u32* __restrict__ pool, TreeParams tp, const FrameState* fs,
+          uint8_t* __restrict__ m8, uint8_t* __restrict__ s8, u32* __restrict__ blockcnt) {
+  __shared__ u32 s_cnt[NC_MAX];
+  const int D = tp.D, NC = OSL_NCOUNT(D);
+  const int n = fs->n_valid;
+  if ((long long)blockIdx.x * AN_THREADS >= n) return;
+  for (int c = threadIdx.x; c < NC; c += AN_THREADS) s_cnt[c] = 0;
+  __syncthreads();
+  const int j = blockIdx.x * AN_THREADS + threadIdx.x;
+  if (j < n) {
+    const u64 k = keys[j];
+    int m = 0;
+    if (j > 0) {
+      const u64 x = k ^ keys[j - 1];
+      m = x ? (D - 1 - (63 - __clzll((long long)x)) / 3) : D;
+    }
+    int s = OSL_NONE;
+    if (m < D) {
+      s = walk_frontier(pool, k, D, tp.quirks);
+      atomicAdd(&s_cnt[OSL_CLVL(D, m + 1)], 1u);  // heads every level d > m
+      if (s != OSL_NONE) {
+        const int lo = (s == D) ? D : max(m + 1, s);
+        if (s == D || lo <= D - 1) atomicAdd(&s_cnt[OSL_CBKT(D, s, lo)], 1u);
+      }
+    }
+    m8[j] = (uint8_t)m;
+    s8[j] = (uint8_t)s;
+  }
+  __syncthreads();
+  // prefix over depth turns "first level headed" histograms into per-level / per-bucket counts
+  if (threadIdx.x == 0) {
+    u32 run = 0;
+    for (int d = 1; d <= D; d++) { run += s_cnt[OSL_CLVL(D, d)]; s_cnt[OSL_CLVL(D, d)] = run; }
+  } else if ((int)threadIdx.x <= D) {
+    const int s = threadIdx.x;
+    u32 run = 0;
+    for (int d = s; d <= D; d++) {
+      run += s_cnt[OSL_CBKT(D, s, d)];
+      s_cnt[OSL_CBKT(D, s, d)] = (d == D && s != D) ? 0u : run;
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < NC; c += AN_THREADS) blockcnt[(size_t)blockIdx.x * NC + c] = s_cnt[c];
+}
+
+// ------------------------------------------------------------------------------------------------ k_scan
+__global__ void __launch_bounds__(512)
+k_scan(u32* __restrict__ blockcnt, FrameState* fs, int D) {
+  __shared__ u32 s_tot[NC_MAX];
+  const int NC = OSL_NCOUNT(D);
+  const int n = fs->n_valid;
+  const int nblocks = (n + AN_THREADS - 1) / AN_THREADS;
+  for (int c = threadIdx.x; c < NC; c += blockDim.x) {
+    u32 run = 0;
+    for (int b = 0; b < nblocks; b++) {
+      const u32 v = blockcnt[(size_t)b * NC + c];
+      blockcnt[(size_t)b * NC + c] = run;
+      run += v;
+    }
+    s_tot[c] = run;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int d = 1; d <= D; d++) fs->n_level[d] = (int)s_tot[OSL_CLVL(D, d)];
+    fs->n_level[0] = fs->n_level[1] > 0 ? 1 : 0;
+    fs->n_level[D + 1] = 0;
+    // the reference's allocation order: pass i = d - s, inside a pass numeric leading-1 key order
+    // (shallower first, then Morton) -- svo.cu:200-229, 266
+    u32 run = 0;
+    for (int i = 0; i < D; i++) {
+      u32 pc = 0;
+      for (int d = 1; d <= D; d++) {
+        const int s = d - i;
+        if (s < 1) continue;
+        if (d == D && s != D) continue;
+        fs->base[s * (D + 1) + d] = (int)run;
+        const u32 c = s_tot[OSL_CBKT(D, s, d)];
+        run += c;
+        pc += c;
+      }
+      fs->pass_count[i] = (int)pc;
+    }
+    fs->n_split = (int)run;
+    const long long after = (long long)fs->size_before + 8ll * run;
+    fs->size_after = (int)min(after, (long long)0x7FFFFFFF);
+    fs->overflow = (after > (long long)fs->capacity) ? 1 : 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ k_assign
+__global__ void __launch_bounds__(AN_THREADS)
+k_assign(const u64* __restrict__ keys, const u32* __restrict__ pay, const u32* __restrict__ pool, TreeParams tp,
+         const FrameState* __restrict__ fs, const uint8_t* __restrict__ m8, const uint8_t* __restrict__ s8,
+         const u32* __restrict__ blockbase, LevelArrays lv, int mode) {
+  __shared__ u32 s_w[AN_WARPS][NC_MAX];
+  const int D = tp.D, NC = OSL_NCOUNT(D);
+  const int n = fs->n_valid;
+  if (fs->overflow) return;
+  if ((long long)blockIdx.x * AN_THREADS >= n) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const u32 lt = lanemask_lt();
+  const int j = blockIdx.x * AN_THREADS + tid;
+
+  u64 k = 0;
+  int m = D, s = OSL_NONE;
+  if (j < n) { k = keys[j]; m = m8[j]; s = s8[j]; }
+  const bool unique = m < D;
+
+  for (int c = tid; c < AN_WARPS * NC_MAX; c += AN_THREADS) (&s_w[0][0])[c] = 0;
+  __syncthreads();
+  // pass 1: per-warp totals of every counter
+  for (int d = 1; d <= D; d++) {
+    const bool f = unique && m < d;
+    const u32 bal = __ballot_sync(FULL, f);
+    if (lane == 0) s_w[warp][OSL_CLVL(D, d)] = __popc(bal);
+    const bool sp = f && s != OSL_NONE && s <= d && (d <= D - 1 || s == D);
+    const u32 peers = __match_any_sync(FULL, sp ? s : 0);
+    if (sp && lane == __ffs(peers) - 1) s_w[warp][OSL_CBKT(D, s, d)] = __popc(peers);
+  }
+  __syncthreads();
+  // exclusive scan over the warps, plus the block's global base, plus the bucket's global rank base
+  for (int c = tid; c < NC; c += AN_THREADS) {
+    u32 run = blockbase[(size_t)blockIdx.x * NC + c];
+    if (c >= D) {
+      const int sd = c - D;  // = s*(D+1)+d
+      run += (u32)fs->base[sd];
+    }
+#pragma unroll
+    for (int w = 0; w < AN_WARPS; w++) {
+      const u32 v = s_w[w][c];
+      s_w[w][c] = run;
+      run += v;
+    }
+  }
+  __syncthreads();
+
+  // pass 2: top-down along the key; existing child tiles come from the pre-frame pool, new ones from their rank
+  const int s_eff = (s == OSL_NONE) ? D : s;
+  const u32 size0 = (u32)fs->size_before;
+  u32 node = (u32)key_digit(k, D, 1);
+  u32 prev_idx = 0;
+  for (int d = 1; d <= D; d++) {
+    const bool f = unique && m < d;
+    const u32 bal = __ballot_sync(FULL, f);
+    const bool sp = f && s != OSL_NONE && s <= d && (d <= D - 1 || s == D);
+    const u32 peers = __match_any_sync(FULL, sp ? s : 0);
+    u32 ct = 0xFFFFFFFFu;
+    if (unique) {
+      if (d < D && d < s_eff) {
+        ct = pool[2 * (size_t)node] & OSL_MASK;
+        node = ct + (u32)key_digit(k, D, d + 1);
+      } else if (sp) {
+        const u32 rank = s_w[warp][OSL_CBKT(D, s, d)] + __popc(peers & lt);
+        ct = (size0 + 8u * rank) | OSL_NEWBIT;
+      }
+    }
+    if (f) {
+      const u32 idx = s_w[warp][OSL_CLVL(D, d)] + __popc(bal & lt);
+      const size_t o = lv.off[d] + idx;
+      lv.ctile[o] = ct;
+      lv.digit[o] = (uint8_t)key_digit(k, D, d);
+      if (d == D) lv.fc[o] = (mode == 2) ? (u32)(fs->n_invalid_front + j) : pay[j];
+      if (d > 1 && m < d - 1) lv.fc[lv.off[d - 1] + prev_idx] = idx;
+      prev_idx = idx;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ k_level
+// One thread per touched node X at depth d (d = 0 is the implicit root whose "tile" is nodes 0..7).  The thread owns
+// X's 8-child tile: loads it (64 B) or starts from the split initialiser, folds in its touched children (leaf blend at
+// depth D-1, otherwise the child's mip value and -- for children split this frame -- their new child pointer),
+// writes the tile back and produces X's own mip value for its parent.
+__global__ void __launch_bounds__(256)
+k_level(u32* __restrict__ pool, LevelArrays lv, const FrameState* __restrict__ fs, int d, int D, int mode,
+        int fresh_tree, const uint8_t* __restrict__ rgb, const float* __restrict__ colors4) {
+  if (fs->overflow) return;
+  const int n_d = fs->n_level[d];
+  const int n_c = fs->n_level[d + 1];
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_d; idx += gridDim.x * blockDim.x) {
+    u32 ct, cbeg, cend;
+    if (d == 0) {
+      ct = fresh_tree ? OSL_NEWBIT : 0u;
+      cbeg = 0; cend = (u32)n_c;
+    } else {
+      const size_t o = lv.off[d] + idx;
+      ct = lv.ctile[o];
+      cbeg = lv.fc[o];
+      cend = (idx + 1 < n_d) ? lv.fc[o + 1] : (u32)n_c;
+    }
+    const u32 T = ct & OSL_MASK;
+    uint4* tile = reinterpret_cast<uint4*>(pool + 2 * (size_t)T);
+    u32 w0[8], w1[8];
+    if (ct & OSL_NEWBIT) {
+      const u32 init = (d == 0) ? 0u : OSL_EMPTY;  // svo.cu:24-31 (root tile zeroed) vs svo.cu:272-275
+#pragma unroll
+      for (int i = 0; i < 8; i++) { w0[i] = 0; w1[i] = init; }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const uint4 q = tile[i];
+        w0[2 * i] = q.x; w1[2 * i] = q.y; w0[2 * i + 1] = q.z; w1[2 * i + 1] = q.w;
+      }
+    }
+    u32 c = cbeg;
+    const size_t oc = lv.off[d + 1];
+    int cd = (c < cend) ? (int)lv.digit[oc + c] : 8;
+#pragma unroll
+    for (int slot = 0; slot < 8; slot++) {
+      if (cd == slot) {
+        const u32 cct = lv.ctile[oc + c];
+        if (d + 1 == D) {
+          const u32 src = lv.fc[oc + c];
+          if (mode == 2) {
+            const float4 col = __ldg(reinterpret_cast<const float4*>(colors4) + src);
+            w1[slot] = osl_blend_f4(w1[slot], col.x, col.y, col.z);
+          } else {
+            const uint8_t* q = rgb + 3 * (size_t)src;
+            w1[slot] = osl_blend_u8(w1[slot], __ldg(q), __ldg(q + 1), __ldg(q + 2));
+          }
+          if (cct != 0xFFFFFFFFu) {  // Q3: the leaf itself gets 8 (phantom) children
+            const u32 pt = cct & OSL_MASK;
+            w0[slot] = OSL_FLAG | pt;
+            uint4* ptile = reinterpret_cast<uint4*>(pool + 2 * (size_t)pt);
+            const uint4 e = make_uint4(0u, OSL_EMPTY, 0u, OSL_EMPTY);
+#pragma unroll
+            for (int i = 0; i < 4; i++) ptile[i] = e;
+          }
+        } else {
+          w1[slot] = lv.val[oc + c];
+          if (cct & OSL_NEWBIT) w0[slot] = OSL_FLAG | (cct & OSL_MASK);
+        }
+        c++;
+        cd = (c < cend) ? (int)lv.digit[oc + c] : 8;
+      }
+    }
+    if (d == 0) {
+      w1[0] = osl_average8(w1);  // Q6: the root average lands in node 0's value word (svo.cu:399-412,439)
+    } else {
+      lv.val[lv.off[d] + idx] = osl_average8(w1);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) tile[i] = make_uint4(w0[2 * i], w1[2 * i], w0[2 * i + 1], w1[2 * i + 1]);
+  }
+}
+
+__global__ void k_frame_begin(FrameState* fs, int size_before, int capacity) {
+  fs->size_before = size_before;
+  fs->capacity = capacity;
+  fs->overflow = 0;
+  fs->n_split = 0;
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static size_t level_cap(size_t n, int d) {
+  // n_d <= min(n, 8^d)
+  if (3 * d >= 40) return n;
+  const size_t p = (size_t)1 << (3 * d);
+  return p < n ? p : n;
+}
+
+int osl_sort_occupancy() {
+  int occ = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)k_sort, SORT_THREADS, 0);
+  if (e != cudaSuccess) { g_osl_last_cuda_error = (int)e; return 0; }
+  return occ;
+}
+
+osl_status osl_ensure_workspace(osl_svo* t, size_t n) {
+  if (n <= t->ws_cap) return OSL_OK;
+  size_t cap = t->ws_cap ? t->ws_cap : 1;
+  while (cap < n) cap *= 2;
+  if (cap < 4096) cap = 4096;
+  cudaFree(t->d_keysA); cudaFree(t->d_keysB); cudaFree(t->d_payA); cudaFree(t->d_payB);
+  cudaFree(t->d_m); cudaFree(t->d_s); cudaFree(t->d_blockcnt); cudaFree(t->d_emit_status);
+  cudaFree(t->d_level_mem);
+  t->d_keysA = t->d_keysB = nullptr; t->d_payA = t->d_payB = nullptr; t->d_m = t->d_s = nullptr;
+  t->d_blockcnt = t->d_emit_status = nullptr; t->d_level_mem = nullptr;
+  t->ws_cap = 0;
+  const int D = t->tp.D;
+  OSL_CUDA(cudaMalloc(&t->d_keysA, cap * sizeof(u64)));
+  OSL_CUDA(cudaMalloc(&t->d_keysB, cap * sizeof(u64)));
+  OSL_CUDA(cudaMalloc(&t->d_payA, cap * sizeof(u32)));
+  OSL_CUDA(cudaMalloc(&t->d_payB, cap * sizeof(u32)));
+  OSL_CUDA(cudaMalloc(&t->d_m, cap));
+  OSL_CUDA(cudaMalloc(&t->d_s, cap));
+  const size_t nblocks = (cap + AN_THREADS - 1) / AN_THREADS;
+  OSL_CUDA(cudaMalloc(&t->d_blockcnt, nblocks * OSL_NCOUNT(D) * sizeof(u32)));
+  const size_t etiles = (cap + EMIT_TILE - 1) / EMIT_TILE;
+  OSL_CUDA(cudaMalloc(&t->d_emit_status, etiles * sizeof(u32)));
+  size_t total = 0;
+  for (int d = 0; d <= D + 1; d++) {
+    t->lv.off[d] = total;
+    total += (d >= 1 && d <= D) ? level_cap(cap, d) : 0;
+  }
+  // ctile(4) + fc(4) + val(4) + digit(1) bytes per level entry
+  uint8_t* mem;
+  OSL_CUDA(cudaMalloc(&mem, total * 13 + 64));
+  t->d_level_mem = mem;
+  t->lv.ctile = reinterpret_cast<u32*>(mem);
+  t->lv.fc = t->lv.ctile + total;
+  t->lv.val = t->lv.fc + total;
+  t->lv.digit = reinterpret_cast<uint8_t*>(t->lv.val + total);
+  t->ws_cap = cap;
+  return OSL_OK;
+}
+
+osl_status osl_grow_pool(osl_svo* t, size_t want_nodes, cudaStream_t st) {
+  if (want_nodes > ((size_t)1 << 30)) return OSL_ERR_POOL_OVERFLOW;
+  if (want_nodes <= t->cap_nodes) return OSL_OK;
+  size_t cap = t->cap_nodes ? t->cap_nodes : 8;
+  while (cap < want_nodes) cap *= 2;
+  if (cap > ((size_t)1 << 30)) cap = (size_t)1 << 30;
+  u32* np;
+  OSL_CUDA(cudaMalloc(&np, cap * 8));
+  const size_t live = (size_t)(t->size > 8 ? t->size : 8);
+  if (t->d_pool) {
+    OSL_CUDA(cudaMemcpyAsync(np, t->d_pool, live * 8, cudaMemcpyDeviceToDevice, st));
+    OSL_CUDA(cudaStreamSynchronize(st));
+    cudaFree(t->d_pool);
+  } else {
+    OSL_CUDA(cudaMemsetAsync(np, 0, 64, st));
+  }
+  t->d_pool = np;
+  t->cap_nodes = cap;
+  return OSL_OK;
+}
+
+osl_status osl_run_integrate(osl_svo* t, const EmitParams& ep, const void* colors, cudaStream_t st) {
+  const int n = ep.n;
+  const int D = t->tp.D;
+  if (n < 0) return OSL_ERR_INVALID;
+  osl_status rc = osl_ensure_workspace(t, (size_t)(n > 0 ? n : 1));
+  if (rc) return rc;
+  const int size0 = t->size > 8 ? t->size : 8;
+  const int fresh = t->size == 0;
+
+  const int etiles = (n + EMIT_TILE - 1) / EMIT_TILE;
+  const int passes = (3 * D + 7) / 8;
+  u64* skeys = (passes & 1) ? t->d_keysB : t->d_keysA;
+  u32* spay = (passes & 1) ? t->d_payB : t->d_payA;
+
+  if (n > 0) {
+    OSL_CUDA(cudaMemsetAsync(t->d_emit_status, 0, (size_t)etiles * sizeof(u32), st));
+    int vec_ok = 0;
+    if (ep.mode == 0) vec_ok = ((reinterpret_cast<uintptr_t>(ep.depth) & 15) == 0);
+    k_emit<<<etiles, EMIT_THREADS, 0, st>>>(ep, t->tp, vec_ok, t->d_keysA, t->d_payA, t->d_emit_status, t->d_fs);
+    OSL_LAUNCHED(1);
+    // cooperative persistent sort
+    int grid = (n + SORT_TILE - 1) / SORT_TILE;
+    if (grid > t->sort_grid) grid = t->sort_grid;
+    if (grid < 1) grid = 1;
+    u64* kA = t->d_keysA; u32* pA = t->d_payA; u64* kB = t->d_keysB; u32* pB = t->d_payB;
+    u32* ch = t->d_cta_hist; const FrameState* fsc = t->d_fs; int pp = passes;
+    void* args[] = {&kA, &pA, &kB, &pB, &ch, &fsc, &pp};
+    OSL_CUDA(cudaLaunchCooperativeKernel((void*)k_sort, dim3(grid), dim3(SORT_THREADS), args, 0, st));
+    OSL_LAUNCHED(1);
+  } else {
+    OSL_CUDA(cudaMemsetAsync(t->d_fs, 0, sizeof(FrameState), st));
+  }
+
+  const int ablocks = (n + AN_THREADS - 1) / AN_THREADS;
+  for (int attempt = 0;; attempt++) {
+    k_frame_begin<<<1, 1, 0, st>>>(t->d_fs, size0, (int)t->cap_nodes);
+    OSL_LAUNCHED(1);
+    if (n > 0) {
+      k_analyze<<<ablocks, AN_THREADS, 0, st>>>(skeys, t->d_pool, t->tp, t->d_fs, t->d_m, t->d_s, t->d_blockcnt);
+      OSL_LAUNCHED(1);
+    }
+    k_scan<<<1, 512, 0, st>>>(t->d_blockcnt, t->d_fs, D);
+    OSL_LAUNCHED(1);
+    OSL_CUDA(cudaMemcpyAsync(t->h_fs, t->d_fs, sizeof(FrameState), cudaMemcpyDeviceToHost, st));
+    OSL_CUDA(cudaStreamSynchronize(st));
+    if (!t->h_fs->overflow) break;
+    if (attempt > 0) return OSL_ERR_CUDA;
+    const long long want = (long long)size0 + 8ll * t->h_fs->n_split;
+    if (want > (1ll << 30)) return OSL_ERR_POOL_OVERFLOW;
+    rc = osl_grow_pool(t, (size_t)want, st);
+    if (rc) return rc;
+  }
+  const FrameState& F = *t->h_fs;
+
+  if (n > 0 && F.n_valid > 0) {
+    k_assign<<<(F.n_valid + AN_THREADS - 1) / AN_THREADS, AN_THREADS, 0, st>>>(
+        skeys, spay, t->d_pool, t->tp, t->d_fs, t->d_m, t->d_s, t->d_blockcnt, t->lv, ep.mode);
+    OSL_LAUNCHED(1);
+    for (int d = D - 1; d >= 0; d--) {
+      const int nd = F.n_level[d];
+      if (nd <= 0) continue;
+      int blocks = (nd + 255) / 256;
+      if (blocks > t->num_sms * 16) blocks = t->num_sms * 16;
+      k_level<<<blocks, 256, 0, st>>>(t->d_pool, t->lv, t->d_fs, d, D, ep.mode, fresh, ep.rgb,
+                                     (const float*)colors);
+      OSL_LAUNCHED(1);
+    }
+  }
+  OSL_CUDA(cudaGetLastError());
+  t->size = F.size_after;  // a fresh tree starts from the 8 root children (svo.cu:646-649)
+
+  osl_counters& c = t->counters;
+  c.n_points = n;
+  c.n_valid = F.n_valid;
+  c.n_unique = F.n_level[D];
+  c.n_split = F.n_split;
+  int64_t psum = 0;
+  for (int i = 0; i <= OSL_MAX_DEPTH; i++) {
+    c.pass_sizes[i] = (i < D) ? F.pass_count[i] : 0;
+    c.parents[i] = (i < D) ? F.n_level[i] : 0;
+    psum += c.parents[i];
+  }
+  c.n_nodes = t->size;
+  const int64_t in_bytes = ep.mode == 0 ? 5ll * n : (ep.mode == 1 ? 15ll * n : 32ll * n);
+  c.algorithmic_bytes = in_bytes + 8 * c.n_unique + 68 * c.n_split + 68 * psum;
+  c.frames++;
+  return OSL_OK;
+}

@@ -1,0 +1,189 @@
+// osl_internal.cuh -- shared definitions of libosl_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/osl_b200.h"
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+#define OSL_FLAG 0x40000000u   // word0 bit 30: node has children            (svo.cu:130,269)
+#define OSL_MASK 0x3FFFFFFFu   // word0 bits 0-29: first-child node index      (svo.cu:136)
+#define OSL_EMPTY 0x7F000000u  // word1 of a freshly split child: alpha 127    (svo.cu:274)
+#define OSL_NEWBIT 0x80000000u // (internal) level-array ctile flag: tile allocated this frame
+#define OSL_NONE 0xFFu         // (internal) "no frontier": the whole path of a key already exists
+
+#define OSL_MAXD OSL_MAX_DEPTH
+#define OSL_NCOUNT(D) ((D) + ((D) + 1) * ((D) + 1))
+#define OSL_CLVL(D, d) ((d)-1)
+#define OSL_CBKT(D, s, d) ((D) + (s) * ((D) + 1) + (d))
+
+// Per-frame device-side state; copied to pinned host memory after the structure phase.
+struct FrameState {
+  int n_in;         // inputs
+  int n_valid;      // V  (inputs with a valid key)
+  int n_invalid_front;  // voxel path: invalid keys sort to the front in the reference (key 1)
+  int n_split;      // S
+  int size_before;  // nodes before this frame (>= 8)
+  int size_after;
+  int overflow;     // 1: size_after exceeds the pool capacity -> nothing was written
+  int capacity;     // nodes
+  int n_level[OSL_MAXD + 2];                  // n_level[d] = distinct touched nodes at depth d (d = 1..D)
+  int pass_count[OSL_MAXD + 1];               // |codes[i]| of reference pass i
+  int base[(OSL_MAXD + 1) * (OSL_MAXD + 1)];  // base[s*(D+1)+d]: first global split rank of bucket (frontier s, depth d)
+};
+
+struct LevelArrays {   // dense per-level node lists, level d at offset off[d]
+  u32* ctile;          // child tile index | OSL_NEWBIT ; 0xFFFFFFFF = none (unsplit leaf)
+  u32* fc;             // first child (index into level d+1); level D: payload (pixel index / sorted position)
+  uint8_t* digit;      // octant of the node inside its parent's tile
+  u32* val;            // word1 value computed bottom-up
+  size_t off[OSL_MAXD + 2];
+};
+
+struct TreeParams {
+  float cx, cy, cz, half;
+  int D;
+  int quirks;
+};
+
+// ---- exact float shapes of the reference (SASS of the reference built with nvcc 12.9) ----------
+
+// image_kernels.cu:24-53: I2F of the integer bracket, FMUL (float)depth, IEEE divide, FMUL 0.001f
+__device__ __forceinline__ void osl_vertex(int d, int x, int y, int width, int height, int img_w, int img_h, float fx,
+                                           float fy, float& X, float& Y, float& Z) {
+  if (d == 0 || d > 15000) {
+    X = Y = Z = __int_as_float(0x7f800000);
+    return;
+  }
+  const float fd = (float)d;
+  X = __fmul_rn(__fdiv_rn(__fmul_rn((float)((img_w / width) * x - img_w / 2), fd), fx), 0.001f);
+  Y = __fmul_rn(__fdiv_rn(__fmul_rn((float)(img_h / 2 - (img_h / height) * y), fd), fy), 0.001f);
+  Z = __fmul_rn(fd, 0.001f);
+}
+
+// image_kernels.cu:206-215 + glm mat4*vec4: t = FMUL(y,m1); t = FFMA(x,m0,t); u = FFMA(z,m2,m3); FADD(t,u)
+__device__ __forceinline__ void osl_transform(const float* __restrict__ M, float& x, float& y, float& z) {
+  float o[3];
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    float t = __fmul_rn(y, M[4 + r]);
+    t = __fmaf_rn(x, M[0 + r], t);
+    float u = __fmaf_rn(z, M[8 + r], M[12 + r]);
+    o[r] = __fadd_rn(t, u);
+  }
+  x = o[0]; y = o[1]; z = o[2];
+}
+
+// svo.cu:33-66 computeKey.  Returns false for invalid points (reference key 1; Q1: only x and z are tested).
+// key = Morton digits WITHOUT the leading 1 (3*D bits).
+__device__ __forceinline__ bool osl_key(float px, float py, float pz, const TreeParams& tp, u64& key) {
+  const bool valid = isfinite(px) && isfinite(pz);
+  float cx = tp.cx, cy = tp.cy, cz = tp.cz, e = tp.half;
+  u64 k = 0;
+  for (int i = 0; i < tp.D; i++) {
+    const bool bx = px > cx, by = py > cy, bz = pz > cz;
+    k = (k << 3) | (u64)((int)bx + 2 * (int)by + 4 * (int)bz);
+    e = __fmul_rn(e, 0.5f);
+    cx = __fadd_rn(cx, bx ? e : -e);
+    cy = __fadd_rn(cy, by ? e : -e);
+    cz = __fadd_rn(cz, bz ? e : -e);
+  }
+  key = k;
+  return valid;
+}
+
+// svo.cu:366-381 leaf blend; every product is exact in FP32 => integer arithmetic
+__device__ __forceinline__ u32 osl_blend_u8(u32 cur, u32 r8, u32 g8, u32 b8) {
+  const u32 a = cur >> 24;
+  const u32 r = ((256u - a) * r8 + a * (cur & 0xFFu)) >> 8;
+  const u32 g = ((256u - a) * g8 + a * ((cur >> 8) & 0xFFu)) >> 8;
+  const u32 b = ((256u - a) * b8 + a * ((cur >> 16) & 0xFFu)) >> 8;
+  const u32 na = min(255u, a + 2u);
+  return r + (g << 8) + (b << 16) + (na << 24);
+}
+
+// svo.cu:318-332 leaf blend for float colours (mesh path, Q15): trunc_s32(FFMA(cur, f2, (c*256)*f1)), fields ADDED
+__device__ __forceinline__ u32 osl_blend_f4(u32 cur, float cr, float cg, float cb) {
+  const int a = (int)(cur >> 24);
+  const float f2 = __fdiv_rn((float)a, 256.0f);
+  const float f1 = __fsub_rn(1.0f, f2);
+  const float r = __fmaf_rn((float)(cur & 0xFFu), f2, __fmul_rn(__fmul_rn(cr, 256.0f), f1));
+  const float g = __fmaf_rn((float)((cur >> 8) & 0xFFu), f2, __fmul_rn(__fmul_rn(cg, 256.0f), f1));
+  const float b = __fmaf_rn((float)((cur >> 16) & 0xFFu), f2, __fmul_rn(__fmul_rn(cb, 256.0f), f1));
+  const int na = min(255, a + 2);
+  return (u32)__float2int_rz(r) + ((u32)__float2int_rz(g) << 8) + ((u32)__float2int_rz(b) << 16) + ((u32)na << 24);
+}
+
+// svo.cu:384-441 averageChildren with Q5 (all 8 children counted): integer mean of RGB, max of alpha
+__device__ __forceinline__ u32 osl_average8(const u32 v[8]) {
+  u32 r = 0, g = 0, b = 0, a = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    r += v[i] & 0xFFu; g += (v[i] >> 8) & 0xFFu; b += (v[i] >> 16) & 0xFFu;
+    a = max(a, v[i] >> 24);
+  }
+  return (r >> 3) + ((g >> 3) << 8) + ((b >> 3) << 16) + (a << 24);
+}
+
+__device__ __forceinline__ u32 lanemask_lt() {
+  u32 m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+// ---- host-side internals ------------------------------------------------------------------------------------
+struct osl_svo {
+  int device;
+  TreeParams tp;
+  u32* d_pool;
+  size_t cap_nodes;
+  int size;           // nodes (host copy, valid after sync)
+  // workspace (sized for ws_cap inputs)
+  size_t ws_cap;
+  u64 *d_keysA, *d_keysB;
+  u32 *d_payA, *d_payB;
+  uint8_t *d_m, *d_s;
+  u32* d_blockcnt;    // [blocks][NC]
+  u32* d_emit_status; // ordered-compaction look-back words
+  u32* d_cta_hist;    // sort: [grid][256]
+  LevelArrays lv;
+  void* d_level_mem;
+  FrameState* d_fs;
+  FrameState* h_fs;   // pinned
+  uint16_t* d_depth_stage; uint8_t* d_rgb_stage; size_t stage_cap;  // for *_host entry points
+  void* h_pin_depth; void* h_pin_rgb;
+  float* d_xyz_stage;
+  osl_counters counters;
+  int sort_grid;      // co-resident CTAs for the cooperative sort
+  int num_sms;
+};
+
+extern int g_osl_last_cuda_error;
+extern long long g_osl_launches;
+#define OSL_CUDA(call)                                   \
+  do {                                                   \
+    cudaError_t e_ = (call);                             \
+    if (e_ != cudaSuccess) {                             \
+      g_osl_last_cuda_error = (int)e_;                   \
+      return e_ == cudaErrorMemoryAllocation ? OSL_ERR_OOM : OSL_ERR_CUDA; \
+    }                                                    \
+  } while (0)
+#define OSL_LAUNCHED(n) (g_osl_launches += (n))
+
+// integrate pipeline (osl_integrate.cu)
+struct EmitParams {
+  const uint16_t* depth; const uint8_t* rgb; int w, h; float fx, fy; float M[16];  // mode 0
+  const float* pts; int stride;                                                      // mode 1 (vec3) / 2 (vec4)
+  int n; int mode;
+};
+osl_status osl_run_integrate(osl_svo* t, const EmitParams& ep, const void* colors, cudaStream_t st);
+osl_status osl_ensure_workspace(osl_svo* t, size_t n);
+int osl_sort_occupancy();  // co-resident k_sort CTAs per SM
+osl_status osl_grow_pool(osl_svo* t, size_t want_nodes, cudaStream_t st);
+
+// raycast / extraction / image kernels
+osl_status osl_launch_raycast(const u32* d_pool, const float center[3], float half_edge, uint8_t* d_out, int w, int h,
+                              float fov_deg, const float view[16], const osl_raycast_params* prm,
+                              unsigned long long* d_stats, cudaStream_t st);

@@ -1,0 +1,187 @@
+// osl_raycast.cu -- octree raycast ("cone trace") of the SVO, one ray per thread, the whole march in registers.
+//
+// Replaces rendering::coneTraceSVO (cone_tracing_kernels.cu:157-198), createRays (:29-51) and coneTrace (:53-146).
+// The reference launches one kernel + one stream compaction + one host sync PER MARCH STEP and round-trips the ray
+// state through global memory; here a thread keeps its ray in registers until it terminates.
+//
+// Every float operation reproduces the shape nvcc 12.9 emits for the reference (SASS inspected, DESIGN.md
+// "Float shapes"), so images are bit-identical to the reference's on the same GPU:
+//   len   = sqrt_rn(fma(z,z, fma(x,x, y*y)))
+//   lod   = (int)ceil(logf(size / (len*pix_scale)) / 0.693147182f)     (libdevice logf, IEEE divides)
+//   step  = size / powf(2, lod);  ray *= (len + step) / len
+// mode 0 (ref_exact) reproduces quirk Q8: the reference re-reads the (never updated) zeroed pixel every step, so the
+// accumulator restarts from 0 each step and a pixel is the single sample taken at the terminating step.
+// mode 1 (fixed_accumulate) keeps the accumulator in registers across steps (what the code was meant to do).
+#include <math.h>
+
+#include "osl_internal.cuh"
+
+struct RayParams {
+  float ox, oy, oz;        // camera origin
+  float xdx, xdy, xdz;     // x_dir
+  float ydx, ydy, ydz;     // y_dir
+  float crx, cry, crz;     // cross(x_dir, -y_dir)
+  float resx, resy;
+  float pix_scale;
+  float cx, cy, cz, size;  // SVO centre, half edge
+  float fx, fy, start_dist, max_range;
+  int mode;
+  int W, H;
+};
+
+__device__ __forceinline__ float ray_length(float x, float y, float z) {
+  return __fsqrt_rn(__fmaf_rn(z, z, __fmaf_rn(x, x, __fmul_rn(y, y))));
+}
+
+// F2I.U32.TRUNC then byte store: NaN/negative -> 0, > 255 wraps mod 256 (Q16)
+__device__ __forceinline__ u32 f2u8(float f) { return __float2uint_rz(f) & 0xFFu; }
+
+__global__ void __launch_bounds__(128)
+k_raycast(const u32* __restrict__ pool, RayParams P, uchar4* __restrict__ out, unsigned long long* stats) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = P.W * P.H;
+  unsigned long long steps = 0, visits = 0;
+  if (idx < n) {
+    const int px = idx % P.W, py = idx / P.W;
+    // createRays (cone_tracing_kernels.cu:29-51)
+    const float magx = __fdiv_rn(__fmaf_rn(P.resx, -0.5f, (float)px), P.fx);
+    const float magy = __fdiv_rn(__fmaf_rn(P.resy, -0.5f, (float)py), P.fy);
+    const float dx = __fadd_rn(__fmaf_rn(magx, P.xdx, __fmul_rn(magy, P.ydx)), P.crx);
+    const float dy = __fadd_rn(__fmaf_rn(magx, P.xdy, __fmul_rn(magy, P.ydy)), P.cry);
+    const float dz = __fadd_rn(__fmaf_rn(magx, P.xdz, __fmul_rn(magy, P.ydz)), P.crz);
+    const float dot = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+    const float inv = __frcp_rn(__fsqrt_rn(dot));
+    float rx = __fmul_rn(__fmul_rn(dx, inv), P.start_dist);
+    float ry = __fmul_rn(__fmul_rn(dy, inv), P.start_dist);
+    float rz = __fmul_rn(__fmul_rn(dz, inv), P.start_dist);
+
+    u32 vx = 0, vy = 0, vz = 0, vw = 0;  // uchar4 accumulator (mod-256 arithmetic)
+    u32 result = 0;
+    for (;;) {
+      steps++;
+      const float tx = __fadd_rn(P.ox, rx), ty = __fadd_rn(P.oy, ry), tz = __fadd_rn(P.oz, rz);
+      const float len = ray_length(rx, ry, rz);
+      const float pix = __fmul_rn(len, P.pix_scale);
+      const float q = __fdiv_rn(P.size, pix);
+      int depth = (int)ceilf(__fdiv_rn(logf(q), 0.693147182464599609375f));
+      u32 node = 0, child = 0;
+      float cx = P.cx, cy = P.cy, cz = P.cz, e = P.size;
+      for (int i = 0; i < depth; i++) {
+        const bool bx = tx > cx, by = ty > cy, bz = tz > cz;
+        node = child + (u32)((int)bx + 2 * (int)by + 4 * (int)bz);
+        const u32 w0 = __ldg(pool + 2 * (size_t)node);
+        visits++;
+        if (!(w0 & OSL_FLAG)) { depth = i + 1; break; }
+        child = w0 & OSL_MASK;
+        e = __fmul_rn(e, 0.5f);
+        cx = __fadd_rn(cx, bx ? e : -e);
+        cy = __fadd_rn(cy, by ? e : -e);
+        cz = __fadd_rn(cz, bz ? e : -e);
+      }
+      if (P.mode == 0) { vx = vy = vz = vw = 0; }  // Q8
+      const u32 ov = __ldg(pool + 2 * (size_t)node + 1);
+      const int alpha = (int)(ov >> 24) - 127;  // Q9: the reference's max(0, unsigned) is a no-op
+      const float af = __fdiv_rn((float)alpha, 127.0f);
+      vx = (vx + f2u8(__fmul_rn((float)(ov & 0xFFu), af))) & 0xFFu;
+      vy = (vy + f2u8(__fmul_rn((float)((ov >> 8) & 0xFFu), af))) & 0xFFu;
+      vz = (vz + f2u8(__fmul_rn((float)((ov >> 16) & 0xFFu), af))) & 0xFFu;
+      if ((int)vw + alpha < 127) {
+        vw = (vw + (u32)alpha) & 0xFFu;
+      } else {
+        result = vx | (vy << 8) | (vz << 16) | (255u << 24);
+        break;
+      }
+      const float nd = __fdiv_rn(P.size, powf(2.0f, (float)depth));
+      const float sc = __fdiv_rn(__fadd_rn(len, nd), len);
+      rx = __fmul_rn(rx, sc); ry = __fmul_rn(ry, sc); rz = __fmul_rn(rz, sc);
+      if (ray_length(rx, ry, rz) > P.max_range) {
+        const float f = __fdiv_rn(127.0f, (float)vw);
+        result = f2u8(__fmul_rn((float)vx, f)) | (f2u8(__fmul_rn((float)vy, f)) << 8) |
+                 (f2u8(__fmul_rn((float)vz, f)) << 16) | (255u << 24);
+        break;
+      }
+    }
+    out[idx] = make_uchar4(result & 0xFF, (result >> 8) & 0xFF, (result >> 16) & 0xFF, result >> 24);
+  }
+  if (stats) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      steps += __shfl_xor_sync(0xFFFFFFFFu, steps, o);
+      visits += __shfl_xor_sync(0xFFFFFFFFu, visits, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(&stats[0], steps);
+      atomicAdd(&stats[1], visits);
+    }
+  }
+}
+
+// glm 0.9.5.4 compute_inverse<tmat4x4> (glm/detail/type_mat4x4.inl:477-529) -- same operation order, host floats
+static void mat4_inverse(const float a[16], float out[16]) {
+#define M(c, r) a[4 * (c) + (r)]
+  const float c00 = M(2, 2) * M(3, 3) - M(3, 2) * M(2, 3), c02 = M(1, 2) * M(3, 3) - M(3, 2) * M(1, 3);
+  const float c03 = M(1, 2) * M(2, 3) - M(2, 2) * M(1, 3), c04 = M(2, 1) * M(3, 3) - M(3, 1) * M(2, 3);
+  const float c06 = M(1, 1) * M(3, 3) - M(3, 1) * M(1, 3), c07 = M(1, 1) * M(2, 3) - M(2, 1) * M(1, 3);
+  const float c08 = M(2, 1) * M(3, 2) - M(3, 1) * M(2, 2), c10 = M(1, 1) * M(3, 2) - M(3, 1) * M(1, 2);
+  const float c11 = M(1, 1) * M(2, 2) - M(2, 1) * M(1, 2), c12 = M(2, 0) * M(3, 3) - M(3, 0) * M(2, 3);
+  const float c14 = M(1, 0) * M(3, 3) - M(3, 0) * M(1, 3), c15 = M(1, 0) * M(2, 3) - M(2, 0) * M(1, 3);
+  const float c16 = M(2, 0) * M(3, 2) - M(3, 0) * M(2, 2), c18 = M(1, 0) * M(3, 2) - M(3, 0) * M(1, 2);
+  const float c19 = M(1, 0) * M(2, 2) - M(2, 0) * M(1, 2), c20 = M(2, 0) * M(3, 1) - M(3, 0) * M(2, 1);
+  const float c22 = M(1, 0) * M(3, 1) - M(3, 0) * M(1, 1), c23 = M(1, 0) * M(2, 1) - M(2, 0) * M(1, 1);
+  const float f0[4] = {c00, c00, c02, c03}, f1[4] = {c04, c04, c06, c07}, f2[4] = {c08, c08, c10, c11};
+  const float f3[4] = {c12, c12, c14, c15}, f4[4] = {c16, c16, c18, c19}, f5[4] = {c20, c20, c22, c23};
+  const float v0[4] = {M(1, 0), M(0, 0), M(0, 0), M(0, 0)}, v1[4] = {M(1, 1), M(0, 1), M(0, 1), M(0, 1)};
+  const float v2[4] = {M(1, 2), M(0, 2), M(0, 2), M(0, 2)}, v3[4] = {M(1, 3), M(0, 3), M(0, 3), M(0, 3)};
+  const float sa[4] = {+1, -1, +1, -1}, sb[4] = {-1, +1, -1, +1};
+  float inv[16];
+  for (int k = 0; k < 4; k++) {
+    inv[0 + k] = ((v1[k] * f0[k] - v2[k] * f1[k]) + v3[k] * f2[k]) * sa[k];
+    inv[4 + k] = ((v0[k] * f0[k] - v2[k] * f3[k]) + v3[k] * f4[k]) * sb[k];
+    inv[8 + k] = ((v0[k] * f1[k] - v1[k] * f3[k]) + v3[k] * f5[k]) * sa[k];
+    inv[12 + k] = ((v0[k] * f2[k] - v1[k] * f4[k]) + v2[k] * f5[k]) * sb[k];
+  }
+  const float dot1 = (M(0, 0) * inv[0] + M(0, 1) * inv[4]) + (M(0, 2) * inv[8] + M(0, 3) * inv[12]);
+#undef M
+  const float ood = 1.0f / dot1;
+  for (int k = 0; k < 16; k++) out[k] = inv[k] * ood;
+}
+
+static void mat4_mul_vec4(const float m[16], const float v[4], float o[4]) {
+  for (int r = 0; r < 4; r++) {
+    const float a = m[0 + r] * v[0], b = m[4 + r] * v[1], c = m[8 + r] * v[2], d = m[12 + r] * v[3];
+    o[r] = (a + b) + (c + d);
+  }
+}
+
+osl_status osl_launch_raycast(const u32* d_pool, const float center[3], float half_edge, uint8_t* d_out, int w, int h,
+                              float fov_deg, const float view[16], const osl_raycast_params* prm,
+                              unsigned long long* d_stats, cudaStream_t st) {
+  if (!d_pool || !d_out || w <= 0 || h <= 0) return OSL_ERR_INVALID;
+  osl_raycast_params p = {532.57f, 531.54f, 0.002f, 10.0f, 0};
+  if (prm) p = *prm;
+  // host part of coneTraceSVO (cone_tracing_kernels.cu:161-171)
+  float inv[16], o4[4], xd[4], yd[4];
+  mat4_inverse(view, inv);
+  const float e_o[4] = {0, 0, 0, 1}, e_x[4] = {-1, 0, 0, 0}, e_y[4] = {0, -1, 0, 0};
+  mat4_mul_vec4(inv, e_o, o4);
+  mat4_mul_vec4(inv, e_x, xd);
+  mat4_mul_vec4(inv, e_y, yd);
+  RayParams P;
+  P.ox = o4[0]; P.oy = o4[1]; P.oz = o4[2];
+  P.xdx = xd[0]; P.xdy = xd[1]; P.xdz = xd[2];
+  P.ydx = yd[0]; P.ydy = yd[1]; P.ydz = yd[2];
+  // cross(x_dir, -y_dir) in the reference's contracted form: FFMA(b, c, -FMUL(d, e))
+  P.crx = fmaf(yd[1], xd[2], -(xd[1] * yd[2]));
+  P.cry = fmaf(xd[0], yd[2], -(yd[0] * xd[2]));
+  P.crz = fmaf(yd[0], xd[1], -(yd[1] * xd[0]));
+  P.resx = (float)w; P.resy = (float)h;
+  P.pix_scale = tanf(fov_deg * 3.14159f / 180.0f) / (float)h;
+  P.cx = center[0]; P.cy = center[1]; P.cz = center[2]; P.size = half_edge;
+  P.fx = p.fx; P.fy = p.fy; P.start_dist = p.start_dist; P.max_range = p.max_range;
+  P.mode = p.mode; P.W = w; P.H = h;
+  const int n = w * h;
+  k_raycast<<<(n + 127) / 128, 128, 0, st>>>(d_pool, P, reinterpret_cast<uchar4*>(d_out), d_stats);
+  OSL_LAUNCHED(1);
+  OSL_CUDA(cudaGetLastError());
+  return OSL_OK;
+}

@@ -1,0 +1,276 @@
+"""Host-side Python mirror of the reference's world / rendering interface for the hot path, over the C ABI.
+
+Names, argument meaning and behaviour follow the reference classes so tests read like the reference's call sites:
+  world::Octree  (include/octree_slam/world/octree.h:83-126, src/world/octree.cpp:251-389)
+  world::Scene   (include/octree_slam/world/scene.h:22-78,  src/world/scene.cpp:98-113)
+  rendering::coneTraceSVO (include/octree_slam/rendering/cone_tracing_kernels.h:16)
+torch is used only to hold device buffers; every computation happens in libosl_b200.so.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import capi
+from .capi import IDENTITY, Counters, RaycastParams, RaycastStats, _check, _f, _hptr, lib, mat_colmajor
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _dev(arr, dtype, device):
+    """numpy / torch -> contiguous CUDA torch tensor of dtype."""
+    torch = _torch()
+    if isinstance(arr, np.ndarray):
+        t = torch.from_numpy(np.ascontiguousarray(arr, dtype=dtype))
+        return t.to("cuda:%d" % device, non_blocking=False)
+    assert arr.is_cuda and arr.is_contiguous()
+    return arr
+
+
+class SVO:
+    """One GPU-resident sparse voxel octree (the reference's OctreeNode::gpu_data_ / gpu_size_)."""
+
+    def __init__(self, center=(0.0, 0.0, 0.0), half_edge=1.0, max_depth=8, reserve_nodes=0, device=0,
+                 quirks=True):
+        self.center = tuple(float(c) for c in center)
+        self.half_edge = float(np.float32(half_edge))
+        self.max_depth = int(max_depth)
+        self.device = device
+        h = C.c_void_p()
+        _check(lib().osl_svo_create(C.byref(h), _f(self.center), self.half_edge, self.max_depth,
+                                    int(reserve_nodes), device), "osl_svo_create")
+        self._h = h
+        if not quirks:
+            _check(lib().osl_svo_set_quirks(self._h, 0), "osl_svo_set_quirks")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().osl_svo_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- integrate -------------------------------------------------------------------------------------
+    def integrate_depth(self, depth, rgb, fx, fy, pose=IDENTITY, stream=None):
+        """depth: (H,W) uint16 mm, rgb: (H,W,3) uint8; numpy (copied to the device) or CUDA torch tensors."""
+        h, w = depth.shape[:2]
+        d = _dev(depth, np.uint16, self.device)
+        c = _dev(rgb, np.uint8, self.device)
+        _check(lib().osl_integrate_depth(self._h, d.data_ptr(), c.data_ptr(), w, h, fx, fy,
+                                         _f(mat_colmajor(pose)), stream), "osl_integrate_depth")
+        return self
+
+    def integrate_depth_host(self, depth, rgb, fx, fy, pose=IDENTITY, stream=None):
+        depth = np.ascontiguousarray(depth, dtype=np.uint16)
+        rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+        h, w = depth.shape
+        _check(lib().osl_integrate_depth_host(self._h, _hptr(depth), _hptr(rgb), w, h, fx, fy,
+                                              _f(mat_colmajor(pose)), stream), "osl_integrate_depth_host")
+        return self
+
+    def integrate_points(self, xyz, rgb, stream=None):
+        p = _dev(xyz, np.float32, self.device)
+        c = _dev(rgb, np.uint8, self.device)
+        n = p.shape[0]
+        _check(lib().osl_integrate_points(self._h, p.data_ptr() if n else None, c.data_ptr() if n else None, n,
+                                          stream), "osl_integrate_points")
+        return self
+
+    def integrate_voxels(self, centers4, colors4, stream=None):
+        p = _dev(centers4, np.float32, self.device)
+        c = _dev(colors4, np.float32, self.device)
+        n = p.shape[0]
+        _check(lib().osl_integrate_voxels(self._h, p.data_ptr() if n else None, c.data_ptr() if n else None, n,
+                                          stream), "osl_integrate_voxels")
+        return self
+
+    # ---- views -----------------------------------------------------------------------------------------
+    @property
+    def size(self):
+        return lib().osl_svo_size(self._h)
+
+    def pool(self):
+        n = self.size
+        out = np.zeros(2 * n, dtype=np.uint32)
+        if n:
+            _check(lib().osl_svo_download(self._h, _hptr(out), n), "osl_svo_download")
+        return out
+
+    def load(self, pool):
+        pool = np.ascontiguousarray(pool, dtype=np.uint32)
+        _check(lib().osl_svo_upload(self._h, _hptr(pool), pool.size // 2), "osl_svo_upload")
+
+    def reset(self):
+        _check(lib().osl_svo_reset(self._h), "osl_svo_reset")
+
+    def view(self):
+        ptr, n = C.c_void_p(), C.c_int()
+        c, he = (C.c_float * 3)(), C.c_float()
+        _check(lib().osl_svo_view(self._h, C.byref(ptr), C.byref(n), c, C.byref(he)), "osl_svo_view")
+        return ptr.value, n.value, tuple(c), he.value
+
+    def counters(self):
+        c = Counters()
+        _check(lib().osl_get_counters(self._h, C.byref(c)), "osl_get_counters")
+        return c
+
+    # ---- raycast ---------------------------------------------------------------------------------------
+    def raycast(self, w, h, fov=45.0, view=IDENTITY, mode=0, stats=None, params=None, stream=None):
+        """Returns an (h, w, 4) uint8 numpy image {R,G,B,A} (host buffers through osl_raycast_host)."""
+        out = np.zeros((h, w, 4), dtype=np.uint8)
+        prm = params if params is not None else RaycastParams(532.57, 531.54, 0.002, 10.0, mode)
+        prm.mode = mode
+        _check(lib().osl_raycast_host(self._h, _hptr(out), w, h, float(fov), _f(mat_colmajor(view)), C.byref(prm),
+                                      C.byref(stats) if stats is not None else None, stream), "osl_raycast_host")
+        return out
+
+    def raycast_device(self, out, w, h, fov=45.0, view=IDENTITY, mode=0, stream=None):
+        prm = RaycastParams(532.57, 531.54, 0.002, 10.0, mode)
+        _check(lib().osl_raycast(self._h, out.data_ptr(), w, h, float(fov), _f(mat_colmajor(view)), C.byref(prm),
+                                 stream), "osl_raycast")
+        return out
+
+    # ---- extraction ------------------------------------------------------------------------------------
+    def extract_voxels(self, max_depth=None):
+        torch = _torch()
+        D = self.max_depth if max_depth is None else int(max_depth)
+        n = C.c_int64()
+        _check(lib().osl_extract_voxels(self._h, D, None, None, None, 0, C.byref(n), None), "osl_extract_voxels")
+        cnt = n.value
+        dev = "cuda:%d" % self.device
+        centers = torch.empty((max(cnt, 1), 4), dtype=torch.float32, device=dev)
+        colors = torch.empty((max(cnt, 1), 4), dtype=torch.float32, device=dev)
+        keys = torch.empty((max(cnt, 1),), dtype=torch.int64, device=dev)
+        if cnt:
+            _check(lib().osl_extract_voxels(self._h, D, centers.data_ptr(), colors.data_ptr(), keys.data_ptr(), cnt,
+                                            C.byref(n), None), "osl_extract_voxels")
+        return centers[:cnt].cpu().numpy(), colors[:cnt].cpu().numpy(), keys[:cnt].cpu().numpy()
+
+
+# ---- per-frame image kernels (image_kernels.h:21,24,52) and computeKeys ------------------------------------
+
+def generateVertexMap(depth, fx, fy, device=0):
+    torch = _torch()
+    h, w = depth.shape
+    d = _dev(depth, np.uint16, device)
+    out = torch.empty((h * w, 3), dtype=torch.float32, device=d.device)
+    _check(lib().osl_generate_vertex_map(d.data_ptr(), out.data_ptr(), w, h, fx, fy, w, h, None),
+           "osl_generate_vertex_map")
+    return out
+
+
+def transformVertexMap(points, trans):
+    _check(lib().osl_transform_vertex_map(points.data_ptr(), _f(mat_colmajor(trans)), points.shape[0], None),
+           "osl_transform_vertex_map")
+    return points
+
+
+def computePointCloudBoundingBox(points, bbox=None):
+    b = _f(bbox if bbox is not None else [0.0] * 6)
+    _check(lib().osl_point_cloud_bbox(points.data_ptr(), points.shape[0], b, None), "osl_point_cloud_bbox")
+    return np.array(list(b), dtype=np.float32)
+
+
+def computeKeys(points, center, half_edge, max_depth, device=0):
+    torch = _torch()
+    p = _dev(points, np.float32, device)
+    n, stride = p.shape
+    keys = torch.empty((n,), dtype=torch.int64, device=p.device)
+    _check(lib().osl_compute_keys(p.data_ptr(), stride, n, _f(center), float(half_edge), int(max_depth),
+                                  keys.data_ptr(), None), "osl_compute_keys")
+    return keys.cpu().numpy()
+
+
+# ---- reference-shaped classes ------------------------------------------------------------------------------
+
+class BoundingBox:
+    """common_types.h:8-17"""
+
+    def __init__(self, bbox0=(0, 0, 0), bbox1=(0, 0, 0)):
+        self.bbox0 = np.array(bbox0, dtype=np.float32)
+        self.bbox1 = np.array(bbox1, dtype=np.float32)
+
+    def contains(self, other):
+        return bool(np.all(self.bbox0 <= other.bbox0) and np.all(self.bbox1 >= other.bbox1))
+
+
+class Octree:
+    """world::Octree (octree.h:83-126).  The root sub-tree is always GPU resident."""
+
+    def __init__(self, resolution, center, size, device=0, reserve_nodes=0):
+        self.resolution_ = float(np.float32(resolution))
+        self.center_ = tuple(float(c) for c in center)
+        self.size_ = float(np.float32(size))
+        self.device = device
+        self._reserve = reserve_nodes
+        self._svo = None
+
+    def _max_depth(self, resolution):
+        # octree.cpp:283-284 for node_depth = 0; the unqualified log() is the double overload under g++
+        edge_length = np.float32(self.size_) / np.float32(math.pow(2.0, 0.0))
+        return int(math.ceil(math.log(float(np.float32(edge_length / np.float32(resolution)))) /
+                             float(np.float32(math.log(2.0)))))
+
+    def _tree(self, max_depth):
+        if self._svo is None:
+            self._svo = SVO(self.center_, self.size_, max_depth, self._reserve, self.device)
+        assert self._svo.max_depth == max_depth
+        return self._svo
+
+    def addCloud(self, origin, points, colors, size=None, bbox=None):
+        """octree.cpp:269-291"""
+        self._tree(self._max_depth(self.resolution_)).integrate_points(points, colors)
+
+    def addDepthFrame(self, depth, rgb, fx, fy, pose=IDENTITY):
+        """fused main.cpp:39-44 (generateVertexMap + transformVertexMap + addCloud)"""
+        self._tree(self._max_depth(self.resolution_)).integrate_depth(depth, rgb, fx, fy, pose)
+
+    def addVoxelGrid(self, centers4, colors4):
+        """octree.cpp:293-313"""
+        self._tree(self._max_depth(self.resolution_)).integrate_voxels(centers4, colors4)
+
+    def extractVoxelGrid(self, scale):
+        """octree.cpp:315-337: max_depth derives from the requested voxel scale"""
+        return self._svo.extract_voxels(self._max_depth(scale))
+
+    def extractSVO(self, bbox=None):
+        """octree.cpp:339-360 -> (device pointer, n_nodes, center, half size)"""
+        return self._svo.view()
+
+    def boundingBox(self):
+        c = np.array(self.center_, dtype=np.float32)
+        return BoundingBox(c - np.float32(self.size_), c + np.float32(self.size_))
+
+    @property
+    def svo(self):
+        return self._svo
+
+
+class Scene:
+    """world::Scene, hot-path methods only (scene.h:35-53)."""
+
+    def __init__(self, device=0):
+        self.tree_ = None
+        self.device = device
+
+    def addPointCloudToOctree(self, origin, points, colors, size, bbox):
+        """scene.cpp:98-113: the first cloud creates Octree(0.01, bbox mid, bbox.bbox1.x) (quirk Q10)."""
+        if self.tree_ is None:
+            self.tree_ = Octree(0.01, (bbox.bbox1 + bbox.bbox0) / np.float32(2.0), bbox.bbox1[0], self.device)
+        self.tree_.addCloud(origin, points, colors, size, bbox)
+
+    def svo(self, bbox=None):
+        return self.tree_.extractSVO(bbox)
+
+
+def coneTraceSVO(svo, resolution, fov, cameraPose, mode=0):
+    """rendering::coneTraceSVO(pos, resolution, fov, cameraPose, octree) (cone_tracing_kernels.cu:157)."""
+    w, h = int(resolution[0]), int(resolution[1])
+    return svo.raycast(w, h, fov, cameraPose, mode)

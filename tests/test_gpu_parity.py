@@ -1,0 +1,264 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+Bit-exact: Morton keys, node indices, node words, raycast pixels (integer / byte work and float work whose operation
+order is reproduced exactly; no tolerance is needed anywhere in this file)."""
+import numpy as np
+import pytest
+
+from common import EMPTY, FLAG, LOOK_PLUS_Z, check_pool_invariants, pkg, random_pose, unique_voxel_points, view_for_pose
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def P():
+    return pkg()
+
+
+def test_library_loads_and_reports_version(P):
+    assert b"sm_100a" in P.lib().osl_version()
+
+
+# ------------------------------------------------------------------------------------------------ KAT
+def test_kat_survey_8c(P):
+    pts = np.array([[0.3, 0.3, 0.3], [0.9, 0.9, 0.9], [-0.9, 0.2, 0.6]], dtype=np.float32)
+    rgb = np.array([[200, 100, 50], [10, 20, 30], [255, 255, 255]], dtype=np.uint8)
+    keys = P.computeKeys(pts, (0, 0, 0), 1.0, 2)
+    assert [oct(int(k)) for k in keys] == ["0o170", "0o177", "0o164"]
+    t = P.SVO((0, 0, 0), 1.0, 2)
+    t.integrate_points(pts, rgb)
+    assert t.size == 24
+    p = t.pool()
+    w0, w1 = p[0::2], p[1::2]
+    assert w0[6] == 0x40000008 and w0[7] == 0x40000010
+    assert w1[12] == 0x81808080 and w1[16] == 0x81193264 and w1[23] == 0x810F0A05
+    assert w1[6] == 0x81101010 and w1[7] == 0x8105070D
+    assert w1[0] == 0x81020203
+    t.integrate_points(pts, rgb)
+    assert t.size == 32 and t.pool()[2 * 23] == 0x40000018  # Q3
+    t2 = P.SVO((0, 0, 0), 1.0, 2, quirks=False)
+    t2.integrate_points(pts, rgb)
+    t2.integrate_points(pts, rgb)
+    assert t2.size == 24
+
+
+# ------------------------------------------------------------------------------------------------ keys / image kernels
+@pytest.mark.parametrize("D", [1, 2, 8, 10, 11, 16, 20])
+@pytest.mark.parametrize("stride", [3, 4])
+def test_compute_keys(P, D, stride):
+    rng = np.random.default_rng(100 + D)
+    n = 20000
+    pts = rng.uniform(-1.3, 1.3, size=(n, stride)).astype(np.float32)
+    pts[::97, 0] = np.inf
+    pts[1::97, 1] = np.nan  # Q1: y is not tested
+    pts[2::97, 2] = -np.inf
+    pts[3::97] = 0.0  # exactly on the centre planes (strict >)
+    center, half = (0.1, -0.2, 0.05), 1.0
+    got = P.computeKeys(pts, center, half, D)
+    want = orc.compute_keys(pts, center, half, D)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("w,h", [(160, 120), (333, 77)])
+def test_vertex_map_and_transform(P, w, h):
+    rng = np.random.default_rng(5)
+    depth = rng.integers(0, 16000, size=(h, w)).astype(np.uint16)
+    depth[0, :7] = 0
+    fx, fy = P.synth.focal(w, h)
+    pose = random_pose(rng)
+    pts = P.generateVertexMap(depth, fx, fy)
+    want = orc.vertex_map(depth, fx, fy)
+    got = pts.cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    P.transformVertexMap(pts, pose)
+    want_t = orc.transform(want, pose)
+    assert np.array_equal(pts.cpu().numpy().view(np.uint32), want_t.view(np.uint32))
+    box = P.computePointCloudBoundingBox(pts)
+    assert np.array_equal(box, orc.bbox(want_t))
+
+
+# ------------------------------------------------------------------------------------------------ integrate
+def _run_frames(P, D, w, h, frames, quirks=True, reserve=0, same_frame=False):
+    center, half = P.synth.tree_params(D)
+    fx, fy = P.synth.focal(w, h)
+    svo = P.SVO(center, half, D, reserve_nodes=reserve, quirks=quirks)
+    ref = orc.OracleSVO(center, half, D, quirks=quirks)
+    for k in range(frames):
+        kk = 0 if same_frame else k
+        pose = P.synth.orbit_pose(25 * kk)
+        depth, rgb = P.synth.make_frame(w, h, pose, seed=kk)
+        svo.integrate_depth(depth, rgb, fx, fy, pose)
+        ref.integrate_depth(depth, rgb, fx, fy, pose)
+        assert svo.size == ref.size, "frame %d: size %d != %d" % (k, svo.size, ref.size)
+        c, rc = svo.counters(), ref.counters()
+        assert c.n_nodes == ref.size
+    got, want = svo.pool(), ref.pool()
+    bad = np.nonzero(got != want)[0]
+    assert bad.size == 0, "first mismatching words %s" % bad[:10]
+    return svo, ref
+
+
+@pytest.mark.parametrize("D,w,h,frames", [(8, 160, 120, 4), (5, 64, 48, 3), (10, 320, 240, 3), (14, 160, 120, 3),
+                                          (16, 320, 240, 2), (20, 96, 72, 2)])
+def test_integrate_depth_matches_oracle(P, D, w, h, frames):
+    svo, ref = _run_frames(P, D, w, h, frames)
+    check_pool_invariants(svo.pool())
+    c, rc = svo.counters(), ref.counters()
+    # per-call counters on our side, running totals on the oracle's
+    assert c.n_unique <= c.n_valid <= c.n_points == w * h
+
+
+def test_integrate_same_frame_repeatedly_q3_and_alpha(P):
+    svo, ref = _run_frames(P, 8, 160, 120, 5, same_frame=True)
+    w1 = svo.pool()[1::2]
+    assert (w1 >> 24).max() == 127 + 2 * 5
+
+
+def test_integrate_without_quirks(P):
+    _run_frames(P, 8, 160, 120, 3, quirks=False, same_frame=True)
+
+
+def test_pool_growth_from_tiny_reserve(P):
+    svo, _ = _run_frames(P, 9, 160, 120, 3, reserve=16)
+    assert svo.size > 16
+
+
+def test_counters_match_oracle_single_frame(P):
+    D, w, h = 8, 160, 120
+    center, half = P.synth.tree_params(D)
+    fx, fy = P.synth.focal(w, h)
+    depth, rgb = P.synth.make_frame(w, h, None, seed=3)
+    svo = P.SVO(center, half, D)
+    ref = orc.OracleSVO(center, half, D)
+    svo.integrate_depth(depth, rgb, fx, fy)
+    ref.integrate_depth(depth, rgb, fx, fy)
+    c, rc = svo.counters(), ref.counters()
+    assert (c.n_points, c.n_valid, c.n_unique, c.n_split) == (rc.n_points, rc.n_valid, rc.n_unique, rc.n_split)
+    assert list(c.pass_sizes)[:D] == list(rc.pass_sizes)[:D]
+    # oracle parents[] is indexed by mip pass (pass p handles depth D-1-p); ours by depth
+    assert [c.parents[D - 1 - p] for p in range(D)] == list(rc.parents)[:D]
+    assert c.algorithmic_bytes == 5 * w * h + 8 * c.n_unique + 68 * c.n_split + 68 * sum(list(c.parents)[:D])
+
+
+@pytest.mark.parametrize("n", [0, 1, 7, 8, 9, 2047, 2048, 2049, 5000])
+def test_integrate_points_ragged_sizes(P, n):
+    rng = np.random.default_rng(n)
+    D = 6
+    pts = rng.uniform(-1.1, 1.1, size=(n, 3)).astype(np.float32)
+    rgb = rng.integers(0, 256, size=(n, 3)).astype(np.uint8)
+    if n > 3:
+        pts[1] = np.inf
+        pts[3] = pts[2]  # duplicate key
+    svo = P.SVO((0, 0, 0), 1.0, D)
+    ref = orc.OracleSVO((0, 0, 0), 1.0, D)
+    for _ in range(2):
+        svo.integrate_points(pts, rgb)
+        ref.integrate_points(pts, rgb)
+    assert svo.size == ref.size
+    assert np.array_equal(svo.pool(), ref.pool())
+
+
+def test_all_invalid_frame(P):
+    D, w, h = 8, 64, 48
+    center, half = P.synth.tree_params(D)
+    depth = np.zeros((h, w), dtype=np.uint16)
+    rgb = np.zeros((h, w, 3), dtype=np.uint8)
+    svo = P.SVO(center, half, D)
+    ref = orc.OracleSVO(center, half, D)
+    svo.integrate_depth(depth, rgb, 100.0, 100.0)
+    ref.integrate_depth(depth, rgb, 100.0, 100.0)
+    assert svo.size == ref.size == 8
+    assert np.array_equal(svo.pool(), ref.pool())
+
+
+def test_out_of_cube_points_fold_into_boundary_cells(P):
+    rng = np.random.default_rng(1)
+    pts = rng.uniform(-5, 5, size=(3000, 3)).astype(np.float32)
+    rgb = rng.integers(0, 256, size=(3000, 3)).astype(np.uint8)
+    svo = P.SVO((0, 0, 0), 1.0, 7)
+    ref = orc.OracleSVO((0, 0, 0), 1.0, 7)
+    svo.integrate_points(pts, rgb)
+    ref.integrate_points(pts, rgb)
+    assert np.array_equal(svo.pool(), ref.pool())
+
+
+def test_alpha_saturates_at_255(P):
+    pts = np.array([[0.3, 0.3, 0.3]], dtype=np.float32)
+    rgb = np.array([[10, 200, 30]], dtype=np.uint8)
+    svo = P.SVO((0, 0, 0), 1.0, 3)
+    ref = orc.OracleSVO((0, 0, 0), 1.0, 3)
+    for _ in range(70):
+        svo.integrate_points(pts, rgb)
+        ref.integrate_points(pts, rgb)
+    assert np.array_equal(svo.pool(), ref.pool())
+    assert (svo.pool()[1::2] >> 24).max() == 255
+
+
+# ------------------------------------------------------------------------------------------------ voxel grid path
+@pytest.mark.parametrize("D,n", [(6, 4000), (9, 20000)])
+def test_integrate_voxels_matches_oracle(P, D, n):
+    rng = np.random.default_rng(17)
+    centers = np.ones((n, 4), dtype=np.float32)
+    centers[:, :3] = rng.uniform(-0.95, 0.95, size=(n, 3))
+    centers[::53, 0] = np.inf
+    colors = rng.uniform(0, 1, size=(n, 4)).astype(np.float32)
+    colors[::11] = 1.0  # Q15: 1.0 * 256 spills into the next channel
+    svo = P.SVO((0, 0, 0), 1.0, D)
+    ref = orc.OracleSVO((0, 0, 0), 1.0, D)
+    for _ in range(2):
+        svo.integrate_voxels(centers, colors)
+        ref.integrate_voxels(centers, colors)
+    assert svo.size == ref.size
+    assert np.array_equal(svo.pool(), ref.pool())
+
+
+# ------------------------------------------------------------------------------------------------ extraction
+def test_extract_voxels_matches_oracle(P):
+    svo, ref = _run_frames(P, 7, 160, 120, 2)
+    for depth in (7, 5, 1):
+        c, k, keys = svo.extract_voxels(depth)
+        rc, rk, rkeys = ref.extract_voxels(depth)
+        assert np.array_equal(keys, rkeys)
+        assert np.all(np.diff(keys) > 0)  # sortedness
+        assert np.array_equal(c.view(np.uint32), rc.view(np.uint32))
+        assert np.array_equal(k.view(np.uint32), rk.view(np.uint32))
+
+
+# ------------------------------------------------------------------------------------------------ raycast
+def _saturated_tree(P, D=7, w=96, h=72, reps=66):
+    center, half = P.synth.tree_params(D)
+    fx, fy = P.synth.focal(w, h)
+    depth, rgb = P.synth.make_frame(w, h, None, seed=1)
+    svo = P.SVO(center, half, D)
+    for _ in range(reps):
+        svo.integrate_depth(depth, rgb, fx, fy)
+    return svo, center, half
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_raycast_matches_oracle(P, mode):
+    svo, center, half = _saturated_tree(P)
+    pool = svo.pool()
+    rng = np.random.default_rng(3)
+    for view in (LOOK_PLUS_Z, view_for_pose(random_pose(rng, 0.2, 0.3)), np.eye(4, dtype=np.float32)):
+        st, cnt = P.RaycastStats(), orc.Counters()
+        img = svo.raycast(96, 72, 45.0, view, mode=mode, stats=st)
+        want = orc.raycast(pool, center, half, 96, 72, 45.0, view, mode=mode, counters=cnt)
+        assert np.array_equal(img, want), "%d pixels differ" % np.count_nonzero(np.any(img != want, axis=2))
+        assert (st.steps, st.visits) == (cnt.ray_steps, cnt.ray_visits)
+    assert img.shape == (72, 96, 4)
+
+
+def test_raycast_sees_the_scene(P):
+    svo, center, half = _saturated_tree(P)
+    img = svo.raycast(96, 72, 45.0, LOOK_PLUS_Z)
+    assert np.all(img[..., 3] == 255)
+    assert np.count_nonzero(img[..., :3].sum(axis=2)) > 0.5 * 96 * 72
+
+
+def test_raycast_other_resolution_and_fov(P):
+    svo, center, half = _saturated_tree(P)
+    pool = svo.pool()
+    img = svo.raycast(131, 57, 60.0, LOOK_PLUS_Z)
+    want = orc.raycast(pool, center, half, 131, 57, 60.0, LOOK_PLUS_Z)
+    assert np.array_equal(img, want)
