@@ -66,3 +66,16 @@ def unique_voxel_points(rng, n, center, half_edge, max_depth):
     jitter = rng.uniform(0.2, 0.8, size=(cells.size, 3))
     pts = np.stack([ix, iy, iz], axis=1) * leaf + jitter * leaf - half_edge + np.asarray(center)
     return pts.astype(np.float32)
+
+
+def float_bits_equal(a, b):
+    """bit-exact float comparison that treats any NaN as equal to any NaN (the NaN payload/sign is not part of the
+    contract: x86 produces 0xFFC00000 where the GPU produces 0x7FFFFFFF)"""
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    b = np.ascontiguousarray(b, dtype=np.float32)
+    if a.shape != b.shape:
+        return False
+    na, nb = np.isnan(a), np.isnan(b)
+    if not np.array_equal(na, nb):
+        return False
+    return np.array_equal(a.view(np.uint32)[~na], b.view(np.uint32)[~nb])

@@ -4,7 +4,7 @@ order is reproduced exactly; no tolerance is needed anywhere in this file)."""
 import numpy as np
 import pytest
 
-from common import EMPTY, FLAG, LOOK_PLUS_Z, check_pool_invariants, pkg, random_pose, unique_voxel_points, view_for_pose
+from common import float_bits_equal, EMPTY, FLAG, LOOK_PLUS_Z, check_pool_invariants, pkg, random_pose, unique_voxel_points, view_for_pose
 from oracle import oracle as orc
 
 pytestmark = pytest.mark.gpu
@@ -69,10 +69,10 @@ def test_vertex_map_and_transform(P, w, h):
     pts = P.generateVertexMap(depth, fx, fy)
     want = orc.vertex_map(depth, fx, fy)
     got = pts.cpu().numpy()
-    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert float_bits_equal(got, want)
     P.transformVertexMap(pts, pose)
     want_t = orc.transform(want, pose)
-    assert np.array_equal(pts.cpu().numpy().view(np.uint32), want_t.view(np.uint32))
+    assert float_bits_equal(pts.cpu().numpy(), want_t)
     box = P.computePointCloudBoundingBox(pts)
     assert np.array_equal(box, orc.bbox(want_t))
 
@@ -220,8 +220,8 @@ def test_extract_voxels_matches_oracle(P):
         rc, rk, rkeys = ref.extract_voxels(depth)
         assert np.array_equal(keys, rkeys)
         assert np.all(np.diff(keys) > 0)  # sortedness
-        assert np.array_equal(c.view(np.uint32), rc.view(np.uint32))
-        assert np.array_equal(k.view(np.uint32), rk.view(np.uint32))
+        assert float_bits_equal(c, rc)
+        assert float_bits_equal(k, rk)
 
 
 # ------------------------------------------------------------------------------------------------ raycast

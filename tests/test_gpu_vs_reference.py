@@ -4,7 +4,7 @@ places where the reference races (Q6: node 0's value word, Q7: duplicate keys) a
 import numpy as np
 import pytest
 
-from common import FLAG, LOOK_PLUS_Z, pkg, random_pose, unique_voxel_points, view_for_pose
+from common import float_bits_equal, FLAG, LOOK_PLUS_Z, pkg, random_pose, unique_voxel_points, view_for_pose
 from oracle import ref as R
 
 pytestmark = [pytest.mark.gpu,
@@ -86,7 +86,7 @@ def test_vertex_map_matches_reference(P):
     pose = random_pose(rng)
     pts = P.transformVertexMap(P.generateVertexMap(depth, fx, fy), pose).cpu().numpy()
     want = R.vertex_map(depth, fx, fy, pose)
-    assert np.array_equal(pts.view(np.uint32), want.view(np.uint32))
+    assert float_bits_equal(pts, want)
 
 
 def test_voxel_grid_matches_reference(P):
@@ -118,8 +118,8 @@ def test_extract_matches_reference(P):
     c, k, keys = svo.extract_voxels(D)
     rc, rk = ref.extract_voxels(D)
     assert c.shape == rc.shape and c.shape[0] == pts.shape[0]
-    assert np.array_equal(c.view(np.uint32), rc.view(np.uint32))
-    assert np.array_equal(k.view(np.uint32), rk.view(np.uint32))
+    assert float_bits_equal(c, rc)
+    assert float_bits_equal(k, rk)
 
 
 @pytest.mark.parametrize("res", [(96, 72), (160, 120)])
