@@ -50,6 +50,8 @@ osl_status osl_svo_create(osl_svo** out, const float center[3], float half_edge,
   do {
     if (cudaMalloc(&t->d_cta_hist, (size_t)t->sort_grid * 256 * sizeof(u32)) != cudaSuccess) { rc = OSL_ERR_OOM; break; }
     if (cudaMalloc(&t->d_fs, sizeof(FrameState)) != cudaSuccess) { rc = OSL_ERR_OOM; break; }
+    if (cudaMalloc(&t->d_scan_totals, (OSL_NCOUNT(OSL_MAXD) + 8) * sizeof(u32)) != cudaSuccess) { rc = OSL_ERR_OOM; break; }
+    if (cudaMemset(t->d_scan_totals, 0, (OSL_NCOUNT(OSL_MAXD) + 8) * sizeof(u32)) != cudaSuccess) { rc = OSL_ERR_CUDA; break; }
     if (cudaMemset(t->d_fs, 0, sizeof(FrameState)) != cudaSuccess) { rc = OSL_ERR_CUDA; break; }
     if (cudaMallocHost(&t->h_fs, sizeof(FrameState)) != cudaSuccess) { rc = OSL_ERR_OOM; break; }
     memset(t->h_fs, 0, sizeof(FrameState));
@@ -69,7 +71,7 @@ void osl_svo_destroy(osl_svo* t) {
   cudaFree(t->d_pool);
   cudaFree(t->d_keysA); cudaFree(t->d_keysB); cudaFree(t->d_payA); cudaFree(t->d_payB);
   cudaFree(t->d_m); cudaFree(t->d_s); cudaFree(t->d_blockcnt); cudaFree(t->d_emit_status);
-  cudaFree(t->d_cta_hist); cudaFree(t->d_level_mem); cudaFree(t->d_fs);
+  cudaFree(t->d_cta_hist); cudaFree(t->d_scan_totals); cudaFree(t->d_level_mem); cudaFree(t->d_fs);
   cudaFree(t->d_depth_stage); cudaFree(t->d_rgb_stage); cudaFree(t->d_xyz_stage);
   if (t->h_fs) cudaFreeHost(t->h_fs);
   if (t->h_pin_depth) cudaFreeHost(t->h_pin_depth);

@@ -148,7 +148,44 @@ k_emit(EmitParams p, TreeParams tp, int vec_ok, u64* __restrict__ keys, u32* __r
 // One launch sorts (key, payload) by the low 8*passes key bits.  Stable LSD radix sort.  Each CTA owns a CONTIGUOUS
 // range of tiles, so a pass needs one grid barrier between "count" and "scatter" and the cross-CTA prefix is just a
 // sum over <= gridDim.x per-CTA histograms (no per-tile look-back chain, which serialises when all tiles are
-// co-resident as they are for one 640x480 frame).
+// co-resident as they are for one 640x480 frame).  When a CTA owns a single tile (the per-frame case) the tile lives
+// in registers for the whole pass and the warp-level ranking is done BEFORE the barrier, so only the prefix and the
+// scatter sit behind it.
+struct SortTile {
+  u64 key[SORT_ITEMS];
+  u32 val[SORT_ITEMS], rank[SORT_ITEMS];
+};
+
+// warp-striped load keeps (warp, item, lane) order == global index order (stability)
+__device__ __forceinline__ void sort_load(SortTile& t, const u64* kin, const u32* pin, int base, int lane, int n) {
+#pragma unroll
+  for (int i = 0; i < SORT_ITEMS; i++) {
+    const int idx = base + i * 32 + lane;
+    const bool ok = idx < n;
+    t.key[i] = ok ? kin[idx] : ~0ull;
+    t.val[i] = ok ? pin[idx] : 0u;
+  }
+}
+
+// rank of every item among the items of the same digit in this warp (match-any), warp digit counts in whist
+__device__ __forceinline__ void sort_rank(SortTile& t, u32* whist, int base, int lane, int n, int shift, u32 lt) {
+#pragma unroll
+  for (int i = 0; i < SORT_ITEMS; i++) {
+    const bool ok = (base + i * 32 + lane) < n;
+    const u32 digit = ok ? ((u32)(t.key[i] >> shift) & 0xFFu) : 256u;
+    const u32 peers = __match_any_sync(FULL, digit);
+    const int leader = __ffs(peers) - 1;
+    u32 old = 0;
+    if (lane == leader && ok) {
+      old = whist[digit];
+      whist[digit] = old + __popc(peers);
+    }
+    old = __shfl_sync(FULL, old, leader);
+    t.rank[i] = old + __popc(peers & lt);
+    __syncwarp();
+  }
+}
+
 __global__ void __launch_bounds__(SORT_THREADS)
 k_sort(u64* kA, u32* pA, u64* kB, u32* pB, u32* cta_hist, const FrameState* fs, int passes) {
   cg::grid_group grid = cg::this_grid();
@@ -165,6 +202,9 @@ k_sort(u64* kA, u32* pA, u64* kB, u32* pB, u32* cta_hist, const FrameState* fs, 
   const int per = (tiles + G - 1) / G;
   const int t0 = min(tiles, (int)blockIdx.x * per), t1 = min(tiles, t0 + per);
   const u32 lt = lanemask_lt();
+  const bool single = (per <= 1);
+  const int Gused = per > 0 ? (tiles + per - 1) / per : 0;  // CTAs that own tiles
+  SortTile T;
 
   for (int pass = 0; pass < passes; pass++) {
     const int shift = 8 * pass;
@@ -172,28 +212,61 @@ k_sort(u64* kA, u32* pA, u64* kB, u32* pB, u32* cta_hist, const FrameState* fs, 
     const u32* pin = (pass & 1) ? pB : pA;
     u64* kout = (pass & 1) ? kA : kB;
     u32* pout = (pass & 1) ? pA : pB;
+    const int base1 = t0 * SORT_TILE + warp * (32 * SORT_ITEMS);
 
     // phase 1: digit histogram of this CTA's tiles
-    s_hist[tid] = 0;
-    __syncthreads();
-    for (int tile = t0; tile < t1; tile++) {
-      const int base = tile * SORT_TILE;
+    if (single) {
 #pragma unroll
-      for (int i = 0; i < SORT_ITEMS; i++) {
-        const int idx = base + i * SORT_THREADS + tid;
-        if (idx < n) atomicAdd(&s_hist[(u32)(kin[idx] >> shift) & 0xFFu], 1u);
+      for (int w = 0; w < SORT_WARPS; w++) s_whist[w][tid] = 0;
+      __syncthreads();
+      if (t0 < t1) {
+        sort_load(T, kin, pin, base1, lane, n);
+        sort_rank(T, s_whist[warp], base1, lane, n, shift, lt);
       }
+      __syncthreads();
+      u32 sum = 0;
+#pragma unroll
+      for (int w = 0; w < SORT_WARPS; w++) {
+        const u32 v = s_whist[w][tid];
+        s_whist[w][tid] = sum;
+        sum += v;
+      }
+      if ((int)blockIdx.x < Gused) cta_hist[blockIdx.x * 256 + tid] = sum;
+    } else {
+      s_hist[tid] = 0;
+      __syncthreads();
+      for (int tile = t0; tile < t1; tile++) {
+        const int base = tile * SORT_TILE;
+#pragma unroll
+        for (int i = 0; i < SORT_ITEMS; i++) {
+          const int idx = base + i * SORT_THREADS + tid;
+          if (idx < n) atomicAdd(&s_hist[(u32)(kin[idx] >> shift) & 0xFFu], 1u);
+        }
+      }
+      __syncthreads();
+      if ((int)blockIdx.x < Gused) cta_hist[blockIdx.x * 256 + tid] = s_hist[tid];
     }
-    __syncthreads();
-    cta_hist[blockIdx.x * 256 + tid] = s_hist[tid];
     grid.sync();
 
     // phase 2: global base of digit `tid` for this CTA = (all smaller digits) + (same digit in earlier CTAs)
     u32 before = 0, tot = 0;
-    for (int c = 0; c < G; c++) {
-      const u32 v = cta_hist[c * 256 + tid];
-      tot += v;
-      if (c < (int)blockIdx.x) before += v;
+    {
+      int c = 0;
+      for (; c + 16 <= Gused; c += 16) {  // 16 independent loads in flight
+        u32 v[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) v[k] = __ldcg(&cta_hist[(c + k) * 256 + tid]);
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+          tot += v[k];
+          if (c + k < (int)blockIdx.x) before += v[k];
+        }
+      }
+      for (; c < Gused; c++) {
+        const u32 v = __ldcg(&cta_hist[c * 256 + tid]);
+        tot += v;
+        if (c < (int)blockIdx.x) before += v;
+      }
     }
     u32 incl = tot;
 #pragma unroll
@@ -210,60 +283,51 @@ k_sort(u64* kA, u32* pA, u64* kB, u32* pB, u32* cta_hist, const FrameState* fs, 
     s_run[tid] = woff + (incl - tot) + before;
     __syncthreads();
 
-    for (int tile = t0; tile < t1; tile++) {
+    if (single) {
+      if (t0 < t1) {
 #pragma unroll
-      for (int w = 0; w < SORT_WARPS; w++) s_whist[w][tid] = 0;
-      __syncthreads();
-      // warp-striped load keeps (warp, item, lane) order == global index order (stability)
-      const int base = tile * SORT_TILE + warp * (32 * SORT_ITEMS);
-      u64 key[SORT_ITEMS];
-      u32 val[SORT_ITEMS], rank[SORT_ITEMS];
-#pragma unroll
-      for (int i = 0; i < SORT_ITEMS; i++) {
-        const int idx = base + i * 32 + lane;
-        const bool ok = idx < n;
-        key[i] = ok ? kin[idx] : ~0ull;
-        val[i] = ok ? pin[idx] : 0u;
-      }
-#pragma unroll
-      for (int i = 0; i < SORT_ITEMS; i++) {
-        const bool ok = (base + i * 32 + lane) < n;
-        const u32 digit = ok ? ((u32)(key[i] >> shift) & 0xFFu) : 256u;
-        const u32 peers = __match_any_sync(FULL, digit);
-        const int leader = __ffs(peers) - 1;
-        u32 old = 0;
-        if (lane == leader && ok) {
-          old = s_whist[warp][digit];
-          s_whist[warp][digit] = old + __popc(peers);
-        }
-        old = __shfl_sync(FULL, old, leader);
-        rank[i] = old + __popc(peers & lt);
-        __syncwarp();
-      }
-      __syncthreads();
-      {  // digit `tid`: exclusive scan over the warps, advance the running base
-        u32 sum = 0;
-#pragma unroll
-        for (int w = 0; w < SORT_WARPS; w++) {
-          const u32 v = s_whist[w][tid];
-          s_whist[w][tid] = sum;
-          sum += v;
-        }
-        const u32 b = s_run[tid];
-        s_base[tid] = b;
-        s_run[tid] = b + sum;
-      }
-      __syncthreads();
-#pragma unroll
-      for (int i = 0; i < SORT_ITEMS; i++) {
-        if ((base + i * 32 + lane) < n) {
-          const u32 digit = (u32)(key[i] >> shift) & 0xFFu;
-          const u32 pos = s_base[digit] + s_whist[warp][digit] + rank[i];
-          kout[pos] = key[i];
-          pout[pos] = val[i];
+        for (int i = 0; i < SORT_ITEMS; i++) {
+          if ((base1 + i * 32 + lane) < n) {
+            const u32 digit = (u32)(T.key[i] >> shift) & 0xFFu;
+            const u32 pos = s_run[digit] + s_whist[warp][digit] + T.rank[i];
+            kout[pos] = T.key[i];
+            pout[pos] = T.val[i];
+          }
         }
       }
-      __syncthreads();
+    } else {
+      for (int tile = t0; tile < t1; tile++) {
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; w++) s_whist[w][tid] = 0;
+        __syncthreads();
+        const int base = tile * SORT_TILE + warp * (32 * SORT_ITEMS);
+        sort_load(T, kin, pin, base, lane, n);
+        sort_rank(T, s_whist[warp], base, lane, n, shift, lt);
+        __syncthreads();
+        {  // digit `tid`: exclusive scan over the warps, advance the running base
+          u32 sum = 0;
+#pragma unroll
+          for (int w = 0; w < SORT_WARPS; w++) {
+            const u32 v = s_whist[w][tid];
+            s_whist[w][tid] = sum;
+            sum += v;
+          }
+          const u32 b = s_run[tid];
+          s_base[tid] = b;
+          s_run[tid] = b + sum;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < SORT_ITEMS; i++) {
+          if ((base + i * 32 + lane) < n) {
+            const u32 digit = (u32)(T.key[i] >> shift) & 0xFFu;
+            const u32 pos = s_base[digit] + s_whist[warp][digit] + T.rank[i];
+            kout[pos] = T.key[i];
+            pout[pos] = T.val[i];
+          }
+        }
+        __syncthreads();
+      }
     }
     grid.sync();
   }
@@ -339,24 +403,50 @@ k_analyze(const u64* __restrict__ keys, const u32* __restrict__ pool, TreeParams
 }
 
 // ------------------------------------------------------------------------------------------------ k_scan
-__global__ void __launch_bounds__(512)
-k_scan(u32* __restrict__ blockcnt, FrameState* fs, int D) {
-  __shared__ u32 s_tot[NC_MAX];
+// Exclusive scan of every counter column over the analyze blocks: one warp per counter, 4 independent loads per lane
+// in flight.  The last CTA to finish (ticket) turns the totals into the frame's allocation plan.
+#define SCAN_THREADS 128
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan(u32* __restrict__ blockcnt, u32* totals, u32* ticket, FrameState* fs, int D, int size_before, int capacity) {
+  __shared__ int s_last;
   const int NC = OSL_NCOUNT(D);
   const int n = fs->n_valid;
   const int nblocks = (n + AN_THREADS - 1) / AN_THREADS;
-  for (int c = threadIdx.x; c < NC; c += blockDim.x) {
-    u32 run = 0;
-    for (int b = 0; b < nblocks; b++) {
-      const u32 v = blockcnt[(size_t)b * NC + c];
-      blockcnt[(size_t)b * NC + c] = run;
-      run += v;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * (SCAN_THREADS / 32) + warp;
+  if (c < NC) {
+    u32 carry = 0;
+    for (int b0 = 0; b0 < nblocks; b0 += 128) {
+      u32 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int b = b0 + k * 32 + lane;
+        v[k] = (b < nblocks) ? blockcnt[(size_t)b * NC + c] : 0u;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        u32 incl = v[k];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const u32 t = __shfl_up_sync(FULL, incl, o);
+          if (lane >= o) incl += t;
+        }
+        const int b = b0 + k * 32 + lane;
+        if (b < nblocks) blockcnt[(size_t)b * NC + c] = carry + incl - v[k];
+        carry += __shfl_sync(FULL, incl, 31);
+      }
     }
-    s_tot[c] = run;
+    if (lane == 0) totals[c] = carry;
   }
+  __threadfence();
   __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
   if (threadIdx.x == 0) {
-    for (int d = 1; d <= D; d++) fs->n_level[d] = (int)s_tot[OSL_CLVL(D, d)];
+    *ticket = 0;
+    for (int d = 1; d <= D; d++) fs->n_level[d] = (int)__ldcg(&totals[OSL_CLVL(D, d)]);
     fs->n_level[0] = fs->n_level[1] > 0 ? 1 : 0;
     fs->n_level[D + 1] = 0;
     // the reference's allocation order: pass i = d - s, inside a pass numeric leading-1 key order
@@ -369,16 +459,18 @@ k_scan(u32* __restrict__ blockcnt, FrameState* fs, int D) {
         if (s < 1) continue;
         if (d == D && s != D) continue;
         fs->base[s * (D + 1) + d] = (int)run;
-        const u32 c = s_tot[OSL_CBKT(D, s, d)];
-        run += c;
-        pc += c;
+        const u32 cc = __ldcg(&totals[OSL_CBKT(D, s, d)]);
+        run += cc;
+        pc += cc;
       }
       fs->pass_count[i] = (int)pc;
     }
     fs->n_split = (int)run;
-    const long long after = (long long)fs->size_before + 8ll * run;
+    fs->size_before = size_before;
+    fs->capacity = capacity;
+    const long long after = (long long)size_before + 8ll * run;
     fs->size_after = (int)min(after, (long long)0x7FFFFFFF);
-    fs->overflow = (after > (long long)fs->capacity) ? 1 : 0;
+    fs->overflow = (after > (long long)capacity) ? 1 : 0;
   }
 }
 
@@ -466,84 +558,98 @@ k_assign(const u64* __restrict__ keys, const u32* __restrict__ pay, const u32* _
 // X's 8-child tile: loads it (64 B) or starts from the split initialiser, folds in its touched children (leaf blend at
 // depth D-1, otherwise the child's mip value and -- for children split this frame -- their new child pointer),
 // writes the tile back and produces X's own mip value for its parent.
+__device__ __forceinline__ void level_node(u32* pool, const LevelArrays& lv, int n_d, int n_c, int d, int D, int mode,
+                                           int fresh_tree, const uint8_t* __restrict__ rgb,
+                                           const float* __restrict__ colors4, int idx) {
+  u32 ct, cbeg, cend;
+  if (d == 0) {
+    ct = fresh_tree ? OSL_NEWBIT : 0u;
+    cbeg = 0; cend = (u32)n_c;
+  } else {
+    const size_t o = lv.off[d] + idx;
+    ct = lv.ctile[o];
+    cbeg = lv.fc[o];
+    cend = (idx + 1 < n_d) ? lv.fc[o + 1] : (u32)n_c;
+  }
+  const u32 T = ct & OSL_MASK;
+  uint4* tile = reinterpret_cast<uint4*>(pool + 2 * (size_t)T);
+  u32 w0[8], w1[8];
+  if (ct & OSL_NEWBIT) {
+    const u32 init = (d == 0) ? 0u : OSL_EMPTY;  // svo.cu:24-31 (root tile zeroed) vs svo.cu:272-275
+#pragma unroll
+    for (int i = 0; i < 8; i++) { w0[i] = 0; w1[i] = init; }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const uint4 q = tile[i];
+      w0[2 * i] = q.x; w1[2 * i] = q.y; w0[2 * i + 1] = q.z; w1[2 * i + 1] = q.w;
+    }
+  }
+  u32 c = cbeg;
+  const size_t oc = lv.off[d + 1];
+  int cd = (c < cend) ? (int)lv.digit[oc + c] : 8;
+#pragma unroll
+  for (int slot = 0; slot < 8; slot++) {
+    if (cd == slot) {
+      const u32 cct = lv.ctile[oc + c];
+      if (d + 1 == D) {
+        const u32 src = lv.fc[oc + c];
+        if (mode == 2) {
+          const float4 col = __ldg(reinterpret_cast<const float4*>(colors4) + src);
+          w1[slot] = osl_blend_f4(w1[slot], col.x, col.y, col.z);
+        } else {
+          const uint8_t* q = rgb + 3 * (size_t)src;
+          w1[slot] = osl_blend_u8(w1[slot], __ldg(q), __ldg(q + 1), __ldg(q + 2));
+        }
+        if (cct != 0xFFFFFFFFu) {  // Q3: the leaf itself gets 8 (phantom) children
+          const u32 pt = cct & OSL_MASK;
+          w0[slot] = OSL_FLAG | pt;
+          uint4* ptile = reinterpret_cast<uint4*>(pool + 2 * (size_t)pt);
+          const uint4 e = make_uint4(0u, OSL_EMPTY, 0u, OSL_EMPTY);
+#pragma unroll
+          for (int i = 0; i < 4; i++) ptile[i] = e;
+        }
+      } else {
+        w1[slot] = lv.val[oc + c];
+        if (cct & OSL_NEWBIT) w0[slot] = OSL_FLAG | (cct & OSL_MASK);
+      }
+      c++;
+      cd = (c < cend) ? (int)lv.digit[oc + c] : 8;
+    }
+  }
+  if (d == 0) {
+    w1[0] = osl_average8(w1);  // Q6: the root average lands in node 0's value word (svo.cu:399-412,439)
+  } else {
+    lv.val[lv.off[d] + idx] = osl_average8(w1);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) tile[i] = make_uint4(w0[2 * i], w1[2 * i], w0[2 * i + 1], w1[2 * i + 1]);
+}
+
 __global__ void __launch_bounds__(256)
-k_level(u32* __restrict__ pool, LevelArrays lv, const FrameState* __restrict__ fs, int d, int D, int mode,
-        int fresh_tree, const uint8_t* __restrict__ rgb, const float* __restrict__ colors4) {
+k_level(u32* pool, LevelArrays lv, const FrameState* __restrict__ fs, int d, int D, int mode, int fresh_tree,
+        const uint8_t* __restrict__ rgb, const float* __restrict__ colors4) {
   if (fs->overflow) return;
   const int n_d = fs->n_level[d];
   const int n_c = fs->n_level[d + 1];
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_d; idx += gridDim.x * blockDim.x) {
-    u32 ct, cbeg, cend;
-    if (d == 0) {
-      ct = fresh_tree ? OSL_NEWBIT : 0u;
-      cbeg = 0; cend = (u32)n_c;
-    } else {
-      const size_t o = lv.off[d] + idx;
-      ct = lv.ctile[o];
-      cbeg = lv.fc[o];
-      cend = (idx + 1 < n_d) ? lv.fc[o + 1] : (u32)n_c;
-    }
-    const u32 T = ct & OSL_MASK;
-    uint4* tile = reinterpret_cast<uint4*>(pool + 2 * (size_t)T);
-    u32 w0[8], w1[8];
-    if (ct & OSL_NEWBIT) {
-      const u32 init = (d == 0) ? 0u : OSL_EMPTY;  // svo.cu:24-31 (root tile zeroed) vs svo.cu:272-275
-#pragma unroll
-      for (int i = 0; i < 8; i++) { w0[i] = 0; w1[i] = init; }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 4; i++) {
-        const uint4 q = tile[i];
-        w0[2 * i] = q.x; w1[2 * i] = q.y; w0[2 * i + 1] = q.z; w1[2 * i + 1] = q.w;
-      }
-    }
-    u32 c = cbeg;
-    const size_t oc = lv.off[d + 1];
-    int cd = (c < cend) ? (int)lv.digit[oc + c] : 8;
-#pragma unroll
-    for (int slot = 0; slot < 8; slot++) {
-      if (cd == slot) {
-        const u32 cct = lv.ctile[oc + c];
-        if (d + 1 == D) {
-          const u32 src = lv.fc[oc + c];
-          if (mode == 2) {
-            const float4 col = __ldg(reinterpret_cast<const float4*>(colors4) + src);
-            w1[slot] = osl_blend_f4(w1[slot], col.x, col.y, col.z);
-          } else {
-            const uint8_t* q = rgb + 3 * (size_t)src;
-            w1[slot] = osl_blend_u8(w1[slot], __ldg(q), __ldg(q + 1), __ldg(q + 2));
-          }
-          if (cct != 0xFFFFFFFFu) {  // Q3: the leaf itself gets 8 (phantom) children
-            const u32 pt = cct & OSL_MASK;
-            w0[slot] = OSL_FLAG | pt;
-            uint4* ptile = reinterpret_cast<uint4*>(pool + 2 * (size_t)pt);
-            const uint4 e = make_uint4(0u, OSL_EMPTY, 0u, OSL_EMPTY);
-#pragma unroll
-            for (int i = 0; i < 4; i++) ptile[i] = e;
-          }
-        } else {
-          w1[slot] = lv.val[oc + c];
-          if (cct & OSL_NEWBIT) w0[slot] = OSL_FLAG | (cct & OSL_MASK);
-        }
-        c++;
-        cd = (c < cend) ? (int)lv.digit[oc + c] : 8;
-      }
-    }
-    if (d == 0) {
-      w1[0] = osl_average8(w1);  // Q6: the root average lands in node 0's value word (svo.cu:399-412,439)
-    } else {
-      lv.val[lv.off[d] + idx] = osl_average8(w1);
-    }
-#pragma unroll
-    for (int i = 0; i < 4; i++) tile[i] = make_uint4(w0[2 * i], w1[2 * i], w0[2 * i + 1], w1[2 * i + 1]);
-  }
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_d; idx += gridDim.x * blockDim.x)
+    level_node(pool, lv, n_d, n_c, d, D, mode, fresh_tree, rgb, colors4, idx);
 }
 
-__global__ void k_frame_begin(FrameState* fs, int size_before, int capacity) {
-  fs->size_before = size_before;
-  fs->capacity = capacity;
-  fs->overflow = 0;
-  fs->n_split = 0;
+// The upper levels of a frame hold a handful of nodes each: one CTA walks them all (levels d_top .. 0) with a block
+// barrier between levels instead of one launch per level.
+#define TAIL_THREADS 1024
+__global__ void __launch_bounds__(TAIL_THREADS)
+k_level_tail(u32* pool, LevelArrays lv, const FrameState* __restrict__ fs, int d_top, int D, int mode, int fresh_tree,
+             const uint8_t* __restrict__ rgb, const float* __restrict__ colors4) {
+  if (fs->overflow) return;
+  for (int d = d_top; d >= 0; d--) {
+    const int n_d = fs->n_level[d];
+    const int n_c = fs->n_level[d + 1];
+    for (int idx = threadIdx.x; idx < n_d; idx += TAIL_THREADS)
+      level_node(pool, lv, n_d, n_c, d, D, mode, fresh_tree, rgb, colors4, idx);
+    __syncthreads();
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -655,14 +761,14 @@ osl_status osl_run_integrate(osl_svo* t, const EmitParams& ep, const void* color
   }
 
   const int ablocks = (n + AN_THREADS - 1) / AN_THREADS;
+  const int NC = OSL_NCOUNT(D);
   for (int attempt = 0;; attempt++) {
-    k_frame_begin<<<1, 1, 0, st>>>(t->d_fs, size0, (int)t->cap_nodes);
-    OSL_LAUNCHED(1);
     if (n > 0) {
       k_analyze<<<ablocks, AN_THREADS, 0, st>>>(skeys, t->d_pool, t->tp, t->d_fs, t->d_m, t->d_s, t->d_blockcnt);
       OSL_LAUNCHED(1);
     }
-    k_scan<<<1, 512, 0, st>>>(t->d_blockcnt, t->d_fs, D);
+    k_scan<<<(NC + SCAN_THREADS / 32 - 1) / (SCAN_THREADS / 32), SCAN_THREADS, 0, st>>>(
+        t->d_blockcnt, t->d_scan_totals, t->d_scan_totals + NC_MAX, t->d_fs, D, size0, (int)t->cap_nodes);
     OSL_LAUNCHED(1);
     OSL_CUDA(cudaMemcpyAsync(t->h_fs, t->d_fs, sizeof(FrameState), cudaMemcpyDeviceToHost, st));
     OSL_CUDA(cudaStreamSynchronize(st));
@@ -679,13 +785,18 @@ osl_status osl_run_integrate(osl_svo* t, const EmitParams& ep, const void* color
     k_assign<<<(F.n_valid + AN_THREADS - 1) / AN_THREADS, AN_THREADS, 0, st>>>(
         skeys, spay, t->d_pool, t->tp, t->d_fs, t->d_m, t->d_s, t->d_blockcnt, t->lv, ep.mode);
     OSL_LAUNCHED(1);
-    for (int d = D - 1; d >= 0; d--) {
+    int d = D - 1;
+    for (; d >= 0 && F.n_level[d] > 2 * TAIL_THREADS; d--) {  // wide levels: one launch each
       const int nd = F.n_level[d];
-      if (nd <= 0) continue;
       int blocks = (nd + 255) / 256;
       if (blocks > t->num_sms * 16) blocks = t->num_sms * 16;
       k_level<<<blocks, 256, 0, st>>>(t->d_pool, t->lv, t->d_fs, d, D, ep.mode, fresh, ep.rgb,
                                      (const float*)colors);
+      OSL_LAUNCHED(1);
+    }
+    if (d >= 0) {  // the narrow upper levels (n_level is monotone in d): one CTA, block barriers
+      k_level_tail<<<1, TAIL_THREADS, 0, st>>>(t->d_pool, t->lv, t->d_fs, d, D, ep.mode, fresh, ep.rgb,
+                                              (const float*)colors);
       OSL_LAUNCHED(1);
     }
   }

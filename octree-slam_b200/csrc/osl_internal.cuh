@@ -148,6 +148,7 @@ struct osl_svo {
   u32* d_blockcnt;    // [blocks][NC]
   u32* d_emit_status; // ordered-compaction look-back words
   u32* d_cta_hist;    // sort: [grid][256]
+  u32* d_scan_totals; // k_scan: [NC_MAX] totals + 1 ticket word
   LevelArrays lv;
   void* d_level_mem;
   FrameState* d_fs;

@@ -59,8 +59,7 @@ def unique_voxel_points(rng, n, center, half_edge, max_depth):
     """n points in distinct leaf cells (no duplicate keys -> the reference's racy paths are deterministic)."""
     res = 1 << max_depth
     cells = rng.choice(res ** 3 if res ** 3 < 2 ** 62 else 2 ** 62, size=4 * n, replace=True)
-    cells = np.unique(cells)[:n]
-    rng.shuffle(cells)
+    cells = rng.permutation(np.unique(cells))[:n]
     iz, iy, ix = cells // (res * res), (cells // res) % res, cells % res
     leaf = 2.0 * half_edge / res
     jitter = rng.uniform(0.2, 0.8, size=(cells.size, 3))
