@@ -1,0 +1,40 @@
+// Minimal stand-in for the subset of glm 0.9.5 the hot-path API uses (vec2/vec3/vec4/mat4 as plain aggregates with the
+// same memory layout: column-major mat4, 12-byte vec3).  Written from scratch for this repository; if the real glm is
+// on the include path first, it is used instead and everything below still compiles (only .x/.y/.z/[] are touched).
+#ifndef OSL_MINI_GLM_HPP_
+#define OSL_MINI_GLM_HPP_
+namespace glm {
+struct vec2 {
+  float x, y;
+  vec2() : x(0), y(0) {}
+  vec2(float a, float b) : x(a), y(b) {}
+};
+struct vec3 {
+  float x, y, z;
+  vec3() : x(0), y(0), z(0) {}
+  explicit vec3(float s) : x(s), y(s), z(s) {}
+  vec3(float a, float b, float c) : x(a), y(b), z(c) {}
+  float& operator[](int i) { return (&x)[i]; }
+  const float& operator[](int i) const { return (&x)[i]; }
+};
+inline vec3 operator+(const vec3& a, const vec3& b) { return vec3(a.x + b.x, a.y + b.y, a.z + b.z); }
+inline vec3 operator-(const vec3& a, const vec3& b) { return vec3(a.x - b.x, a.y - b.y, a.z - b.z); }
+inline vec3 operator/(const vec3& a, float s) { return vec3(a.x / s, a.y / s, a.z / s); }
+inline vec3 operator*(const vec3& a, float s) { return vec3(a.x * s, a.y * s, a.z * s); }
+struct vec4 {
+  float x, y, z, w;
+  vec4() : x(0), y(0), z(0), w(0) {}
+  vec4(float a, float b, float c, float d) : x(a), y(b), z(c), w(d) {}
+  float& operator[](int i) { return (&x)[i]; }
+  const float& operator[](int i) const { return (&x)[i]; }
+};
+struct mat4 {
+  vec4 c[4];  // columns
+  mat4() { c[0] = vec4(1, 0, 0, 0); c[1] = vec4(0, 1, 0, 0); c[2] = vec4(0, 0, 1, 0); c[3] = vec4(0, 0, 0, 1); }
+  explicit mat4(float s) { c[0] = vec4(s, 0, 0, 0); c[1] = vec4(0, s, 0, 0); c[2] = vec4(0, 0, s, 0); c[3] = vec4(0, 0, 0, s); }
+  vec4& operator[](int i) { return c[i]; }
+  const vec4& operator[](int i) const { return c[i]; }
+};
+inline const float* value_ptr(const mat4& m) { return &m.c[0].x; }
+}  // namespace glm
+#endif

@@ -1,0 +1,55 @@
+// Layout contract of the hot path: the reference's POD types (include/octree_slam/common_types.h:8-79 in the
+// reference tree), same names, same memory layout, without the CUDA/GL dependencies.  Device pointers stay raw.
+#ifndef OSL_B200_COMMON_TYPES_H_
+#define OSL_B200_COMMON_TYPES_H_
+#include <stdint.h>
+
+#include "glm/glm.hpp"
+
+#ifndef __VECTOR_TYPES_H__
+struct uchar4 { unsigned char x, y, z, w; };
+struct int2 { int x, y; };
+static inline int2 make_int2(int x, int y) { int2 r; r.x = x; r.y = y; return r; }
+#endif
+
+struct BoundingBox {  // common_types.h:8-17
+  glm::vec3 bbox0 = glm::vec3(0.0f);
+  glm::vec3 bbox1 = glm::vec3(0.0f);
+  bool contains(const BoundingBox& o) const {
+    return bbox0.x <= o.bbox0.x && bbox0.y <= o.bbox0.y && bbox0.z <= o.bbox0.z && bbox1.x >= o.bbox1.x &&
+           bbox1.y >= o.bbox1.y && bbox1.z >= o.bbox1.z;
+  }
+};
+
+struct Camera {  // common_types.h:40-47 (only view and fov are raycast inputs)
+  glm::mat4 model, view, projection, modelview, mvp;
+  float fov = 45.0f;
+};
+
+struct Color256 { uint8_t r, g, b; };  // common_types.h:49-53, 3 bytes
+
+struct VoxelGrid {  // common_types.h:55-63; centers/colors are DEVICE arrays of glm::vec4 owned by the grid
+  ~VoxelGrid();
+  glm::vec4* centers = nullptr;
+  glm::vec4* colors = nullptr;
+  int size = 0;
+  float scale = 0.0f;
+  BoundingBox bbox;
+};
+
+struct RawFrame {  // common_types.h:65-73; color/depth are DEVICE arrays
+  RawFrame(const int w, const int h);
+  ~RawFrame();
+  Color256* color;
+  uint16_t* depth;
+  int height;
+  int width;
+  long long timestamp;
+};
+
+struct SVO {  // common_types.h:75-79: aliases the node pool, no ownership; size = HALF edge length
+  unsigned int* data;
+  glm::vec3 center;
+  float size;
+};
+#endif

@@ -51,7 +51,8 @@ typedef struct osl_counters {
   int64_t parents[OSL_MAX_DEPTH + 1];   /* P_l distinct touched nodes at depth l (l = 0 is the root) */
   int64_t n_nodes;                      /* octree_size after the call (nodes) */
   int64_t algorithmic_bytes;            /* 5N (or bytes of the point inputs) + 8U + 68S + 68*sum(P_l) */
-  int64_t frames;                       /* integrate calls so far */
+  int64_t total_algorithmic_bytes;      /* running sum over all frames */
+  int64_t frames;                       /* integrate calls completed so far */
 } osl_counters;
 
 typedef struct osl_raycast_params {
@@ -82,17 +83,23 @@ osl_status osl_svo_set_quirks(osl_svo* t, int ref_quirks);
 
 /* Fused main.cpp:39-44: generateVertexMap (image_kernels.cu:24-53) -> transformVertexMap (:206-215) ->
  * svoFromPointCloud (svo.cu:642-696).  d_depth: w*h uint16 millimetres, d_rgb: w*h*3 bytes (Color256).
- * Asynchronous on `stream` except when the pool has to grow. */
+ * Asynchronous on `stream` (4 kernel launches, no host synchronisation) except when the pool or the workspace has to
+ * grow.  One stream per tree: consecutive calls on different streams are not ordered against each other. */
 osl_status osl_integrate_depth(osl_svo* t, const uint16_t* d_depth, const uint8_t* d_rgb, int w, int h, float fx,
                                float fy, const float pose[16], void* stream);
-/* Same from host buffers (what OpenNIDevice::readFrame + mainLoop do, openni_device.cpp:122,144): H2D copies, the
- * integrate, and a stream synchronize. */
+/* Same from host buffers (what OpenNIDevice::readFrame + mainLoop do, openni_device.cpp:122,144).  The H2D copies run
+ * on an internal copy stream into rotating device slots so the transfer of frame f+1 overlaps the kernels of frame f;
+ * the call returns without waiting for the device.  Pinned source buffers must stay untouched until the frame has
+ * completed (osl_svo_sync). */
 osl_status osl_integrate_depth_host(osl_svo* t, const uint16_t* h_depth, const uint8_t* h_rgb, int w, int h, float fx,
                                     float fy, const float pose[16], void* stream);
 /* Replaces svoFromPointCloud (svo.h:16, svo.cu:642): d_xyz = n glm::vec3 (12-byte stride), d_rgb = n Color256. */
 osl_status osl_integrate_points(osl_svo* t, const float* d_xyz, const uint8_t* d_rgb, int n, void* stream);
 /* Replaces svoFromVoxelGrid (svo.h:14, svo.cu:584): n glm::vec4 centres and n glm::vec4 colours (0..1 floats). */
 osl_status osl_integrate_voxels(osl_svo* t, const float* d_centers4, const float* d_colors4, int n, void* stream);
+
+/* Wait for every integrate enqueued so far; returns a deferred error (e.g. OSL_ERR_POOL_OVERFLOW) if one occurred. */
+osl_status osl_svo_sync(osl_svo* t);
 
 /* ---- views of the tree ------------------------------------------------------------------------------------- */
 

@@ -20,7 +20,7 @@ STATUS = {0: "OSL_OK", -1: "OSL_ERR_INVALID", -2: "OSL_ERR_CUDA", -3: "OSL_ERR_O
 EXPORTS = [
     "osl_svo_create", "osl_svo_destroy", "osl_svo_reset", "osl_svo_set_quirks",
     "osl_integrate_depth", "osl_integrate_depth_host", "osl_integrate_points", "osl_integrate_voxels",
-    "osl_svo_view", "osl_svo_size", "osl_svo_download", "osl_svo_upload", "osl_get_counters",
+    "osl_svo_sync", "osl_svo_view", "osl_svo_size", "osl_svo_download", "osl_svo_upload", "osl_get_counters",
     "osl_raycast", "osl_raycast_host", "osl_raycast_pool", "osl_extract_voxels",
     "osl_generate_vertex_map", "osl_transform_vertex_map", "osl_point_cloud_bbox", "osl_compute_keys",
     "osl_status_string", "osl_last_cuda_error", "osl_version", "osl_launch_count",
@@ -38,7 +38,8 @@ class Counters(C.Structure):
     _fields_ = [
         ("n_points", C.c_int64), ("n_valid", C.c_int64), ("n_unique", C.c_int64), ("n_split", C.c_int64),
         ("pass_sizes", C.c_int64 * (MAX_DEPTH + 1)), ("parents", C.c_int64 * (MAX_DEPTH + 1)),
-        ("n_nodes", C.c_int64), ("algorithmic_bytes", C.c_int64), ("frames", C.c_int64),
+        ("n_nodes", C.c_int64), ("algorithmic_bytes", C.c_int64), ("total_algorithmic_bytes", C.c_int64),
+        ("frames", C.c_int64),
     ]
 
 
@@ -74,6 +75,7 @@ def lib():
         "osl_integrate_depth_host": (i32, [vp, vp, vp, i32, i32, f32, f32, fp, vp]),
         "osl_integrate_points": (i32, [vp, vp, vp, i32, vp]),
         "osl_integrate_voxels": (i32, [vp, vp, vp, i32, vp]),
+        "osl_svo_sync": (i32, [vp]),
         "osl_svo_view": (i32, [vp, C.POINTER(vp), C.POINTER(i32), fp, fp]),
         "osl_svo_size": (i32, [vp]),
         "osl_svo_download": (i32, [vp, vp, i32]),

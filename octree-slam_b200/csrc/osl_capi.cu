@@ -7,9 +7,23 @@
 int g_osl_last_cuda_error = 0;
 long long g_osl_launches = 0;
 
+// wait for every frame in flight and fold its result block into the host-side state
+static osl_status drain(osl_svo* t) {
+  osl_status rc = osl_poll_results(t, true);
+  if (rc) return rc;
+  return t->sticky_error;
+}
+
+static osl_status set_device_size(osl_svo* t, int size) {
+  // FrameState::cur_size lives on the device (frames are planned there without a host round trip)
+  OSL_CUDA(cudaMemcpy(&t->d_fs->cur_size, &size, sizeof(int), cudaMemcpyHostToDevice));
+  t->size = size;
+  return OSL_OK;
+}
+
 extern "C" {
 
-const char* osl_version(void) { return "osl_b200 0.1 (sm_100a)"; }
+const char* osl_version(void) { return "osl_b200 0.2 (sm_100a)"; }
 int osl_last_cuda_error(void) { return g_osl_last_cuda_error; }
 int64_t osl_launch_count(void) { return g_osl_launches; }
 
@@ -24,7 +38,6 @@ const char* osl_status_string(osl_status s) {
   }
   return "unknown";
 }
-
 
 osl_status osl_svo_create(osl_svo** out, const float center[3], float half_edge, int max_depth, size_t reserve_nodes,
                           int device) {
@@ -42,19 +55,28 @@ osl_status osl_svo_create(osl_svo** out, const float center[3], float half_edge,
   t->tp.D = max_depth;
   t->tp.quirks = 1;
   t->num_sms = prop.multiProcessorCount;
-  int occ = osl_sort_occupancy();
-  if (occ < 1) { delete t; return OSL_ERR_CUDA; }
-  if (occ > 4) occ = 4;
-  t->sort_grid = occ * t->num_sms;
+  const int occ_sort = osl_sort_occupancy(), occ_str = osl_structure_occupancy(), occ_lvl = osl_levels_occupancy();
+  if (occ_sort < 1 || occ_str < 1 || occ_lvl < 1) { delete t; return OSL_ERR_CUDA; }
+  t->sort_grid = (occ_sort > 4 ? 4 : occ_sort) * t->num_sms;
+  t->structure_grid = (occ_str > 2 ? 2 : occ_str) * t->num_sms;
+  t->levels_grid = (occ_lvl > 4 ? 4 : occ_lvl) * t->num_sms;
   osl_status rc = OSL_OK;
   do {
     if (cudaMalloc(&t->d_cta_hist, (size_t)t->sort_grid * 256 * sizeof(u32)) != cudaSuccess) { rc = OSL_ERR_OOM; break; }
     if (cudaMalloc(&t->d_fs, sizeof(FrameState)) != cudaSuccess) { rc = OSL_ERR_OOM; break; }
+    if (cudaMemset(t->d_fs, 0, sizeof(FrameState)) != cudaSuccess) { rc = OSL_ERR_CUDA; break; }
     if (cudaMalloc(&t->d_scan_totals, (OSL_NCOUNT(OSL_MAXD) + 8) * sizeof(u32)) != cudaSuccess) { rc = OSL_ERR_OOM; break; }
     if (cudaMemset(t->d_scan_totals, 0, (OSL_NCOUNT(OSL_MAXD) + 8) * sizeof(u32)) != cudaSuccess) { rc = OSL_ERR_CUDA; break; }
-    if (cudaMemset(t->d_fs, 0, sizeof(FrameState)) != cudaSuccess) { rc = OSL_ERR_CUDA; break; }
-    if (cudaMallocHost(&t->h_fs, sizeof(FrameState)) != cudaSuccess) { rc = OSL_ERR_OOM; break; }
-    memset(t->h_fs, 0, sizeof(FrameState));
+    if (cudaMallocHost(&t->h_ring, sizeof(FrameState) * OSL_RING) != cudaSuccess) { rc = OSL_ERR_OOM; break; }
+    memset(t->h_ring, 0, sizeof(FrameState) * OSL_RING);
+    bool ok = true;
+    for (int i = 0; i < OSL_RING && ok; i++)
+      ok = cudaEventCreateWithFlags(&t->ring_ev[i], cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < OSL_STAGES && ok; i++)
+      ok = cudaEventCreateWithFlags(&t->stage_copied[i], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&t->stage_free[i], cudaEventDisableTiming) == cudaSuccess;
+    if (ok) ok = cudaStreamCreateWithFlags(&t->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    if (!ok) { rc = OSL_ERR_CUDA; break; }
     rc = osl_grow_pool(t, reserve_nodes ? reserve_nodes : ((size_t)1 << 20), 0);
     if (rc) break;
     if (cudaMemset(t->d_pool, 0, 64) != cudaSuccess) { rc = OSL_ERR_CUDA; break; }
@@ -72,21 +94,27 @@ void osl_svo_destroy(osl_svo* t) {
   cudaFree(t->d_keysA); cudaFree(t->d_keysB); cudaFree(t->d_payA); cudaFree(t->d_payB);
   cudaFree(t->d_m); cudaFree(t->d_s); cudaFree(t->d_blockcnt); cudaFree(t->d_emit_status);
   cudaFree(t->d_cta_hist); cudaFree(t->d_scan_totals); cudaFree(t->d_level_mem); cudaFree(t->d_fs);
-  cudaFree(t->d_depth_stage); cudaFree(t->d_rgb_stage); cudaFree(t->d_xyz_stage);
-  if (t->h_fs) cudaFreeHost(t->h_fs);
-  if (t->h_pin_depth) cudaFreeHost(t->h_pin_depth);
-  if (t->h_pin_rgb) cudaFreeHost(t->h_pin_rgb);
+  for (int i = 0; i < OSL_STAGES; i++) {
+    cudaFree(t->d_depth_stage[i]); cudaFree(t->d_rgb_stage[i]);
+    if (t->stage_copied[i]) cudaEventDestroy(t->stage_copied[i]);
+    if (t->stage_free[i]) cudaEventDestroy(t->stage_free[i]);
+  }
+  for (int i = 0; i < OSL_RING; i++)
+    if (t->ring_ev[i]) cudaEventDestroy(t->ring_ev[i]);
+  if (t->copy_stream) cudaStreamDestroy(t->copy_stream);
+  if (t->h_ring) cudaFreeHost(t->h_ring);
   delete t;
 }
 
 osl_status osl_svo_reset(osl_svo* t) {
   if (!t) return OSL_ERR_INVALID;
   OSL_CUDA(cudaSetDevice(t->device));
+  osl_poll_results(t, true);
   OSL_CUDA(cudaDeviceSynchronize());
   OSL_CUDA(cudaMemset(t->d_pool, 0, 64));
-  t->size = 0;
+  t->sticky_error = OSL_OK;
   memset(&t->counters, 0, sizeof(t->counters));
-  return OSL_OK;
+  return set_device_size(t, 0);
 }
 
 osl_status osl_svo_set_quirks(osl_svo* t, int ref_quirks) {
@@ -109,34 +137,44 @@ osl_status osl_integrate_depth(osl_svo* t, const uint16_t* d_depth, const uint8_
 
 static osl_status ensure_stage(osl_svo* t, size_t n) {
   if (n <= t->stage_cap) return OSL_OK;
-  cudaFree(t->d_depth_stage); cudaFree(t->d_rgb_stage);
-  if (t->h_pin_depth) cudaFreeHost(t->h_pin_depth);
-  if (t->h_pin_rgb) cudaFreeHost(t->h_pin_rgb);
-  t->d_depth_stage = nullptr; t->d_rgb_stage = nullptr; t->h_pin_depth = t->h_pin_rgb = nullptr; t->stage_cap = 0;
-  OSL_CUDA(cudaMalloc(&t->d_depth_stage, n * 2));
-  OSL_CUDA(cudaMalloc(&t->d_rgb_stage, n * 3));
-  OSL_CUDA(cudaMallocHost(&t->h_pin_depth, n * 2));
-  OSL_CUDA(cudaMallocHost(&t->h_pin_rgb, n * 3));
+  OSL_CUDA(cudaDeviceSynchronize());
+  for (int i = 0; i < OSL_STAGES; i++) {
+    cudaFree(t->d_depth_stage[i]); cudaFree(t->d_rgb_stage[i]);
+    t->d_depth_stage[i] = nullptr; t->d_rgb_stage[i] = nullptr;
+  }
+  t->stage_cap = 0;
+  for (int i = 0; i < OSL_STAGES; i++) {
+    OSL_CUDA(cudaMalloc(&t->d_depth_stage[i], n * 2));
+    OSL_CUDA(cudaMalloc(&t->d_rgb_stage[i], n * 3));
+  }
   t->stage_cap = n;
+  t->stage_seq = 0;
   return OSL_OK;
 }
 
+// Host frames: the H2D copies run on an internal copy stream into one of OSL_STAGES device slots, so the transfer of
+// frame f+1 overlaps the kernels of frame f; the integrate itself is stream-ordered on `stream`.  Returns without
+// waiting for the device (pinned source buffers make the copies truly asynchronous; pageable ones are staged by the
+// driver).  Pinned source buffers must stay untouched until the frame completes (osl_svo_sync / osl_svo_size /
+// osl_get_counters / osl_svo_view synchronize).
 osl_status osl_integrate_depth_host(osl_svo* t, const uint16_t* h_depth, const uint8_t* h_rgb, int w, int h, float fx,
                                     float fy, const float pose[16], void* stream) {
-  if (!t || !h_depth || !h_rgb || w <= 0 || h <= 0 || !pose) return OSL_ERR_INVALID;
+  if (!t || !h_depth || !h_rgb || w <= 0 || h <= 0 || !pose || (long long)w * h >= (1ll << 30)) return OSL_ERR_INVALID;
   OSL_CUDA(cudaSetDevice(t->device));
   const size_t n = (size_t)w * h;
   osl_status rc = ensure_stage(t, n);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  // caller memory may be pageable: stage through pinned buffers so the copies are true async DMA
-  memcpy(t->h_pin_depth, h_depth, n * 2);
-  memcpy(t->h_pin_rgb, h_rgb, n * 3);
-  OSL_CUDA(cudaMemcpyAsync(t->d_depth_stage, t->h_pin_depth, n * 2, cudaMemcpyHostToDevice, st));
-  OSL_CUDA(cudaMemcpyAsync(t->d_rgb_stage, t->h_pin_rgb, n * 3, cudaMemcpyHostToDevice, st));
-  rc = osl_integrate_depth(t, t->d_depth_stage, t->d_rgb_stage, w, h, fx, fy, pose, stream);
+  const int slot = (int)(t->stage_seq % OSL_STAGES);
+  if (t->stage_seq >= OSL_STAGES) OSL_CUDA(cudaStreamWaitEvent(t->copy_stream, t->stage_free[slot], 0));
+  OSL_CUDA(cudaMemcpyAsync(t->d_depth_stage[slot], h_depth, n * 2, cudaMemcpyHostToDevice, t->copy_stream));
+  OSL_CUDA(cudaMemcpyAsync(t->d_rgb_stage[slot], h_rgb, n * 3, cudaMemcpyHostToDevice, t->copy_stream));
+  OSL_CUDA(cudaEventRecord(t->stage_copied[slot], t->copy_stream));
+  OSL_CUDA(cudaStreamWaitEvent(st, t->stage_copied[slot], 0));
+  rc = osl_integrate_depth(t, t->d_depth_stage[slot], t->d_rgb_stage[slot], w, h, fx, fy, pose, stream);
   if (rc) return rc;
-  OSL_CUDA(cudaStreamSynchronize(st));
+  OSL_CUDA(cudaEventRecord(t->stage_free[slot], st));
+  t->stage_seq++;
   return OSL_OK;
 }
 
@@ -158,22 +196,39 @@ osl_status osl_integrate_voxels(osl_svo* t, const float* d_centers4, const float
   return osl_run_integrate(t, ep, d_colors4, (cudaStream_t)stream);
 }
 
-osl_status osl_svo_view(const osl_svo* t, const uint32_t** d_pool, int* n_nodes, float center[3], float* half_edge) {
+osl_status osl_svo_sync(osl_svo* t) {
   if (!t) return OSL_ERR_INVALID;
   OSL_CUDA(cudaSetDevice(t->device));
-  OSL_CUDA(cudaDeviceSynchronize());
+  return drain(t);
+}
+
+osl_status osl_svo_view(const osl_svo* tc, const uint32_t** d_pool, int* n_nodes, float center[3], float* half_edge) {
+  osl_svo* t = const_cast<osl_svo*>(tc);
+  if (!t) return OSL_ERR_INVALID;
+  OSL_CUDA(cudaSetDevice(t->device));
+  osl_status rc = drain(t);
   if (d_pool) *d_pool = t->d_pool;
   if (n_nodes) *n_nodes = t->size;
   if (center) { center[0] = t->tp.cx; center[1] = t->tp.cy; center[2] = t->tp.cz; }
   if (half_edge) *half_edge = t->tp.half;
-  return OSL_OK;
+  return rc;
 }
 
-int osl_svo_size(const osl_svo* t) { return t ? t->size : 0; }
+int osl_svo_size(const osl_svo* tc) {
+  osl_svo* t = const_cast<osl_svo*>(tc);
+  if (!t) return 0;
+  cudaSetDevice(t->device);
+  osl_poll_results(t, true);
+  return t->size;
+}
 
-osl_status osl_svo_download(const osl_svo* t, uint32_t* h_pool, int cap_nodes) {
-  if (!t || !h_pool || cap_nodes < t->size) return OSL_ERR_INVALID;
+osl_status osl_svo_download(const osl_svo* tc, uint32_t* h_pool, int cap_nodes) {
+  osl_svo* t = const_cast<osl_svo*>(tc);
+  if (!t || !h_pool) return OSL_ERR_INVALID;
   OSL_CUDA(cudaSetDevice(t->device));
+  osl_status rc = drain(t);
+  if (rc) return rc;
+  if (cap_nodes < t->size) return OSL_ERR_INVALID;
   OSL_CUDA(cudaDeviceSynchronize());
   if (t->size > 0) OSL_CUDA(cudaMemcpy(h_pool, t->d_pool, (size_t)t->size * 8, cudaMemcpyDeviceToHost));
   return OSL_OK;
@@ -182,19 +237,24 @@ osl_status osl_svo_download(const osl_svo* t, uint32_t* h_pool, int cap_nodes) {
 osl_status osl_svo_upload(osl_svo* t, const uint32_t* h_pool, int n_nodes) {
   if (!t || n_nodes < 0 || (n_nodes > 0 && !h_pool)) return OSL_ERR_INVALID;
   OSL_CUDA(cudaSetDevice(t->device));
+  osl_poll_results(t, true);
   OSL_CUDA(cudaDeviceSynchronize());
+  t->size = 0;
   osl_status rc = osl_grow_pool(t, (size_t)(n_nodes > 8 ? n_nodes : 8), 0);
   if (rc) return rc;
   if (n_nodes > 0) OSL_CUDA(cudaMemcpy(t->d_pool, h_pool, (size_t)n_nodes * 8, cudaMemcpyHostToDevice));
   else OSL_CUDA(cudaMemset(t->d_pool, 0, 64));
-  t->size = n_nodes;
-  return OSL_OK;
+  t->sticky_error = OSL_OK;
+  return set_device_size(t, n_nodes);
 }
 
-osl_status osl_get_counters(const osl_svo* t, osl_counters* out) {
+osl_status osl_get_counters(const osl_svo* tc, osl_counters* out) {
+  osl_svo* t = const_cast<osl_svo*>(tc);
   if (!t || !out) return OSL_ERR_INVALID;
+  OSL_CUDA(cudaSetDevice(t->device));
+  osl_status rc = osl_poll_results(t, true);
   *out = t->counters;
-  return OSL_OK;
+  return rc;
 }
 
 osl_status osl_raycast_pool(const uint32_t* d_pool, const float center[3], float half_edge, uint8_t* d_out_rgba, int w,
@@ -219,9 +279,10 @@ osl_status osl_raycast_pool(const uint32_t* d_pool, const float center[3], float
   return rc;
 }
 
+// Stream-ordered after the integrates enqueued on the same stream (no host synchronisation needed).
 osl_status osl_raycast(const osl_svo* t, uint8_t* d_out_rgba, int w, int h, float fov_deg, const float view[16],
                        const osl_raycast_params* prm, void* stream) {
-  if (!t || t->size == 0) return OSL_ERR_INVALID;
+  if (!t || (t->size == 0 && t->ring_head == 0)) return OSL_ERR_INVALID;
   OSL_CUDA(cudaSetDevice(t->device));
   const float c[3] = {t->tp.cx, t->tp.cy, t->tp.cz};
   return osl_raycast_pool(t->d_pool, c, t->tp.half, d_out_rgba, w, h, fov_deg, view, prm, nullptr, stream);
@@ -229,9 +290,10 @@ osl_status osl_raycast(const osl_svo* t, uint8_t* d_out_rgba, int w, int h, floa
 
 osl_status osl_raycast_host(const osl_svo* t, uint8_t* h_out_rgba, int w, int h, float fov_deg, const float view[16],
                             const osl_raycast_params* prm, osl_raycast_stats* stats, void* stream) {
-  if (!t || t->size == 0 || !h_out_rgba || w <= 0 || h <= 0) return OSL_ERR_INVALID;
+  if (!t || (t->size == 0 && t->ring_head == 0) || !h_out_rgba || w <= 0 || h <= 0) return OSL_ERR_INVALID;
   OSL_CUDA(cudaSetDevice(t->device));
   cudaStream_t st = (cudaStream_t)stream;
+  if (t->last_stream != st) OSL_CUDA(cudaStreamSynchronize(t->last_stream));
   uint8_t* d_out;
   OSL_CUDA(cudaMalloc(&d_out, (size_t)w * h * 4));
   const float c[3] = {t->tp.cx, t->tp.cy, t->tp.cz};

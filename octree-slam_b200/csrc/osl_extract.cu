@@ -126,6 +126,11 @@ extern "C" osl_status osl_extract_voxels(const osl_svo* t, int max_depth, float*
   if (!t || !n_out || max_depth < 0 || max_depth > OSL_MAX_DEPTH) return OSL_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   *n_out = 0;
+  {
+    osl_status prc = osl_poll_results(const_cast<osl_svo*>(t), true);  // frames in flight define the node count
+    if (prc) return prc;
+    if (t->last_stream != st) OSL_CUDA(cudaStreamSynchronize(t->last_stream));
+  }
   if (t->size == 0) return OSL_OK;
   const size_t maxn = (size_t)t->size + 8;
   long long *kA = nullptr, *kB = nullptr;

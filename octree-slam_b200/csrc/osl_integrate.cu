@@ -4,15 +4,16 @@
 // image kernels that feed it (image_kernels.cu:24-53,206-215).  Same results (node indices, node words), very
 // different structure -- see DESIGN.md section 3:
 //
-//   k_emit     back-project + pose + Morton key per input, ordered compaction of the valid ones (look-back scan)
-//   k_sort     ONE cooperative persistent kernel: LSD radix sort (8-bit digits) of (key, payload), all passes
-//   k_analyze  per sorted key: common-prefix length with its predecessor (=> which tree levels it heads), walk of the
-//              pre-frame tree to the frontier, per-block counts of level heads and of (frontier depth, depth) buckets
-//   k_scan     exclusive scan of the block counts; reproduces the reference's allocation order
-//              (pass = depth - frontier depth, then numeric key) as bucket bases; overflow check
-//   k_assign   dense per-level node lists with deterministic child-tile indices (existing or newly ranked)
-//   k_level    bottom-up, one thread per touched node: read/initialise its 64-byte child tile, blend leaves,
-//              link new tiles, mip-map (integer mean / max), write the tile back
+//   k_emit       back-project + pose + Morton key per input, ordered compaction of the valid ones (look-back scan)
+//   k_sort       ONE cooperative persistent kernel: LSD radix sort (8-bit digits) of (key, payload), all passes
+//   k_structure  ONE cooperative kernel: per sorted key the common-prefix length with its predecessor (=> which tree
+//                levels it heads) and the frontier depth from a walk of the pre-frame tree; scan of per-block counts;
+//                allocation plan in the reference's order (pass = depth - frontier depth, then numeric key);
+//                dense per-level node lists with deterministic child-tile indices; overflow check
+//   k_levels     ONE cooperative kernel, bottom-up, one thread per touched node: read/initialise its 64-byte child
+//                tile, blend leaves, link new tiles, mip-map (integer mean / max), write the tile back
+// A frame is 4 kernel launches + 1 memset + 1 small D2H, all asynchronous on the caller's stream; the host never
+// waits for the device unless the pool has to grow or the caller asks for sizes / counters.
 #include <cooperative_groups.h>
 
 #include "osl_internal.cuh"
@@ -356,16 +357,23 @@ __device__ __forceinline__ int walk_frontier(const u32* __restrict__ pool, u64 k
   return OSL_NONE;
 }
 
-__global__ void __launch_bounds__(AN_THREADS)
-k_analyze(const u64* __restrict__ keys, const u32* __restrict__ pool, TreeParams tp, const FrameState* fs,
-          uint8_t* __restrict__ m8, uint8_t* __restrict__ s8, u32* __restrict__ blockcnt) {
-  __shared__ u32 s_cnt[NC_MAX];
+// ------------------------------------------------------------------------------------------------ k_structure
+// ONE cooperative kernel builds the frame's structure plan:
+//   phase A  (per virtual block of 512 sorted keys) common-prefix length m with the predecessor, frontier depth s
+//            from a walk of the pre-frame tree, per-block counts of level heads and (s, depth) split buckets
+//   -- grid barrier --
+//   phase B  one warp per counter: exclusive scan of the counter column over the virtual blocks
+//   -- grid barrier --
+//   phase B2 every CTA derives the allocation plan from the totals (bucket bases in the reference's order:
+//            pass = depth - s, then numeric key); CTA 0 publishes the FrameState; overflow => nothing is written
+//   phase C  dense per-level node lists with deterministic child-tile indices
+__device__ __forceinline__ void analyze_block(int vb, int n, const u64* __restrict__ keys, const u32* pool,
+                                              const TreeParams& tp, uint8_t* __restrict__ m8, uint8_t* __restrict__ s8,
+                                              u32* __restrict__ blockcnt, u32* s_cnt) {
   const int D = tp.D, NC = OSL_NCOUNT(D);
-  const int n = fs->n_valid;
-  if ((long long)blockIdx.x * AN_THREADS >= n) return;
   for (int c = threadIdx.x; c < NC; c += AN_THREADS) s_cnt[c] = 0;
   __syncthreads();
-  const int j = blockIdx.x * AN_THREADS + threadIdx.x;
+  const int j = vb * AN_THREADS + threadIdx.x;
   if (j < n) {
     const u64 k = keys[j];
     int m = 0;
@@ -399,103 +407,27 @@ k_analyze(const u64* __restrict__ keys, const u32* __restrict__ pool, TreeParams
     }
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < NC; c += AN_THREADS) blockcnt[(size_t)blockIdx.x * NC + c] = s_cnt[c];
+  for (int c = threadIdx.x; c < NC; c += AN_THREADS) blockcnt[(size_t)vb * NC + c] = s_cnt[c];
+  __syncthreads();
 }
 
-// ------------------------------------------------------------------------------------------------ k_scan
-// Exclusive scan of every counter column over the analyze blocks: one warp per counter, 4 independent loads per lane
-// in flight.  The last CTA to finish (ticket) turns the totals into the frame's allocation plan.
-#define SCAN_THREADS 128
-__global__ void __launch_bounds__(SCAN_THREADS)
-k_scan(u32* __restrict__ blockcnt, u32* totals, u32* ticket, FrameState* fs, int D, int size_before, int capacity) {
-  __shared__ int s_last;
-  const int NC = OSL_NCOUNT(D);
-  const int n = fs->n_valid;
-  const int nblocks = (n + AN_THREADS - 1) / AN_THREADS;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int c = blockIdx.x * (SCAN_THREADS / 32) + warp;
-  if (c < NC) {
-    u32 carry = 0;
-    for (int b0 = 0; b0 < nblocks; b0 += 128) {
-      u32 v[4];
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const int b = b0 + k * 32 + lane;
-        v[k] = (b < nblocks) ? blockcnt[(size_t)b * NC + c] : 0u;
-      }
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        u32 incl = v[k];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const u32 t = __shfl_up_sync(FULL, incl, o);
-          if (lane >= o) incl += t;
-        }
-        const int b = b0 + k * 32 + lane;
-        if (b < nblocks) blockcnt[(size_t)b * NC + c] = carry + incl - v[k];
-        carry += __shfl_sync(FULL, incl, 31);
-      }
-    }
-    if (lane == 0) totals[c] = carry;
-  }
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  if (threadIdx.x == 0) {
-    *ticket = 0;
-    for (int d = 1; d <= D; d++) fs->n_level[d] = (int)__ldcg(&totals[OSL_CLVL(D, d)]);
-    fs->n_level[0] = fs->n_level[1] > 0 ? 1 : 0;
-    fs->n_level[D + 1] = 0;
-    // the reference's allocation order: pass i = d - s, inside a pass numeric leading-1 key order
-    // (shallower first, then Morton) -- svo.cu:200-229, 266
-    u32 run = 0;
-    for (int i = 0; i < D; i++) {
-      u32 pc = 0;
-      for (int d = 1; d <= D; d++) {
-        const int s = d - i;
-        if (s < 1) continue;
-        if (d == D && s != D) continue;
-        fs->base[s * (D + 1) + d] = (int)run;
-        const u32 cc = __ldcg(&totals[OSL_CBKT(D, s, d)]);
-        run += cc;
-        pc += cc;
-      }
-      fs->pass_count[i] = (int)pc;
-    }
-    fs->n_split = (int)run;
-    fs->size_before = size_before;
-    fs->capacity = capacity;
-    const long long after = (long long)size_before + 8ll * run;
-    fs->size_after = (int)min(after, (long long)0x7FFFFFFF);
-    fs->overflow = (after > (long long)capacity) ? 1 : 0;
-  }
-}
-
-// ------------------------------------------------------------------------------------------------ k_assign
-__global__ void __launch_bounds__(AN_THREADS)
-k_assign(const u64* __restrict__ keys, const u32* __restrict__ pay, const u32* __restrict__ pool, TreeParams tp,
-         const FrameState* __restrict__ fs, const uint8_t* __restrict__ m8, const uint8_t* __restrict__ s8,
-         const u32* __restrict__ blockbase, LevelArrays lv, int mode) {
-  __shared__ u32 s_w[AN_WARPS][NC_MAX];
+__device__ __forceinline__ void assign_block(int vb, int n, const u64* __restrict__ keys, const u32* __restrict__ pay,
+                                             const u32* pool, const TreeParams& tp, const uint8_t* __restrict__ m8,
+                                             const uint8_t* __restrict__ s8, const u32* blockbase,
+                                             const LevelArrays& lv, int mode, u32 size0, int n_invalid_front,
+                                             const u32* s_plan, u32 (*s_w)[NC_MAX]) {
   const int D = tp.D, NC = OSL_NCOUNT(D);
-  const int n = fs->n_valid;
-  if (fs->overflow) return;
-  if ((long long)blockIdx.x * AN_THREADS >= n) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const u32 lt = lanemask_lt();
-  const int j = blockIdx.x * AN_THREADS + tid;
-
+  const int j = vb * AN_THREADS + tid;
   u64 k = 0;
   int m = D, s = OSL_NONE;
   if (j < n) { k = keys[j]; m = m8[j]; s = s8[j]; }
   const bool unique = m < D;
 
+  // pass 1: per-warp totals of every counter this block can touch
   for (int c = tid; c < AN_WARPS * NC_MAX; c += AN_THREADS) (&s_w[0][0])[c] = 0;
   __syncthreads();
-  // pass 1: per-warp totals of every counter
   for (int d = 1; d <= D; d++) {
     const bool f = unique && m < d;
     const u32 bal = __ballot_sync(FULL, f);
@@ -505,13 +437,9 @@ k_assign(const u64* __restrict__ keys, const u32* __restrict__ pay, const u32* _
     if (sp && lane == __ffs(peers) - 1) s_w[warp][OSL_CBKT(D, s, d)] = __popc(peers);
   }
   __syncthreads();
-  // exclusive scan over the warps, plus the block's global base, plus the bucket's global rank base
+  // exclusive scan over the warps + the block's global base + the bucket's global rank base
   for (int c = tid; c < NC; c += AN_THREADS) {
-    u32 run = blockbase[(size_t)blockIdx.x * NC + c];
-    if (c >= D) {
-      const int sd = c - D;  // = s*(D+1)+d
-      run += (u32)fs->base[sd];
-    }
+    u32 run = __ldcg(&blockbase[(size_t)vb * NC + c]) + s_plan[c];
 #pragma unroll
     for (int w = 0; w < AN_WARPS; w++) {
       const u32 v = s_w[w][c];
@@ -520,10 +448,8 @@ k_assign(const u64* __restrict__ keys, const u32* __restrict__ pay, const u32* _
     }
   }
   __syncthreads();
-
   // pass 2: top-down along the key; existing child tiles come from the pre-frame pool, new ones from their rank
   const int s_eff = (s == OSL_NONE) ? D : s;
-  const u32 size0 = (u32)fs->size_before;
   u32 node = (u32)key_digit(k, D, 1);
   u32 prev_idx = 0;
   for (int d = 1; d <= D; d++) {
@@ -546,11 +472,119 @@ k_assign(const u64* __restrict__ keys, const u32* __restrict__ pay, const u32* _
       const size_t o = lv.off[d] + idx;
       lv.ctile[o] = ct;
       lv.digit[o] = (uint8_t)key_digit(k, D, d);
-      if (d == D) lv.fc[o] = (mode == 2) ? (u32)(fs->n_invalid_front + j) : pay[j];
+      if (d == D) lv.fc[o] = (mode == 2) ? (u32)(n_invalid_front + j) : pay[j];
       if (d > 1 && m < d - 1) lv.fc[lv.off[d - 1] + prev_idx] = idx;
       prev_idx = idx;
     }
   }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(AN_THREADS)
+k_structure(const u64* __restrict__ keys, const u32* __restrict__ pay, const u32* pool, TreeParams tp, FrameState* fs,
+            uint8_t* m8, uint8_t* s8, u32* blockcnt, u32* totals, LevelArrays lv, int mode, int capacity) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ u32 s_w[AN_WARPS][NC_MAX];
+  __shared__ u32 s_plan[NC_MAX];
+  __shared__ u32 s_scan[AN_WARPS];
+  const int D = tp.D, NC = OSL_NCOUNT(D);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = fs->n_valid;
+  const int n_invalid_front = fs->n_invalid_front;
+  const int cur = fs->cur_size;
+  const u32 size0 = (u32)(cur > 8 ? cur : 8);
+  const int nvb = (n + AN_THREADS - 1) / AN_THREADS;
+  const int G = gridDim.x;
+
+  for (int vb = blockIdx.x; vb < nvb; vb += G) analyze_block(vb, n, keys, pool, tp, m8, s8, blockcnt, &s_w[0][0]);
+  grid.sync();
+
+  // phase B: column scans, one warp per counter, 4 independent loads per lane in flight
+  for (int c = blockIdx.x * AN_WARPS + warp; c < NC; c += G * AN_WARPS) {
+    u32 carry = 0;
+    for (int b0 = 0; b0 < nvb; b0 += 128) {
+      u32 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int b = b0 + k * 32 + lane;
+        v[k] = (b < nvb) ? __ldcg(&blockcnt[(size_t)b * NC + c]) : 0u;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        u32 incl = v[k];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const u32 t = __shfl_up_sync(FULL, incl, o);
+          if (lane >= o) incl += t;
+        }
+        const int b = b0 + k * 32 + lane;
+        if (b < nvb) blockcnt[(size_t)b * NC + c] = carry + incl - v[k];
+        carry += __shfl_sync(FULL, incl, 31);
+      }
+    }
+    if (lane == 0) totals[c] = carry;
+  }
+  grid.sync();
+
+  // phase B2: the allocation plan.  Entry e = i*D + (d-1) in the reference's order (pass i, then depth d):
+  // bucket (s = d - i, d).  Exclusive scan over the <= D*D entries gives each bucket's first global rank.
+  for (int c = tid; c < NC; c += AN_THREADS) s_plan[c] = 0;
+  u32 val = 0;
+  int bs = 0, bd = 0;
+  if (tid < D * D) {
+    const int i = tid / D;
+    bd = tid % D + 1;
+    bs = bd - i;
+    if (bs >= 1 && !(bd == D && bs != D)) val = __ldcg(&totals[OSL_CBKT(D, bs, bd)]);
+    else bs = 0;
+  }
+  u32 incl = val;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const u32 t = __shfl_up_sync(FULL, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_scan[warp] = incl;
+  __syncthreads();
+  u32 woff = 0, n_split = 0;
+#pragma unroll
+  for (int w = 0; w < AN_WARPS; w++) {
+    const u32 t = s_scan[w];
+    if (w < warp) woff += t;
+    n_split += t;
+  }
+  if (bs >= 1) s_plan[OSL_CBKT(D, bs, bd)] = woff + incl - val;
+  const long long after = (long long)size0 + 8ll * n_split;
+  const bool overflow = after > (long long)capacity;
+  if (blockIdx.x == 0) {
+    if (bs >= 1) fs->base[bs * (D + 1) + bd] = (int)(woff + incl - val);
+    if (tid < D) {  // |codes[i]| of reference pass i
+      u32 pc = 0;
+      for (int d = 1; d <= D; d++) {
+        const int s = d - tid;
+        if (s >= 1 && !(d == D && s != D)) pc += __ldcg(&totals[OSL_CBKT(D, s, d)]);
+      }
+      fs->pass_count[tid] = (int)pc;
+    }
+    if (tid >= 1 && tid <= D) fs->n_level[tid] = (int)__ldcg(&totals[OSL_CLVL(D, tid)]);
+    if (tid == 0) {
+      fs->n_level[0] = __ldcg(&totals[OSL_CLVL(D, 1)]) > 0 ? 1 : 0;
+      fs->n_level[D + 1] = 0;
+      fs->n_split = (int)n_split;
+      fs->size_before = (int)size0;
+      fs->capacity = capacity;
+      fs->size_after = (int)min(after, (long long)0x7FFFFFFF);
+      fs->overflow = overflow ? 1 : 0;
+      fs->fresh = cur == 0 ? 1 : 0;
+      if (!overflow) fs->cur_size = (int)after;
+      fs->frame_seq += 1;
+    }
+  }
+  __syncthreads();
+  if (overflow) return;
+
+  for (int vb = blockIdx.x; vb < nvb; vb += G)
+    assign_block(vb, n, keys, pay, pool, tp, m8, s8, blockcnt, lv, mode, size0, n_invalid_front, s_plan, s_w);
 }
 
 // ------------------------------------------------------------------------------------------------ k_level
@@ -626,27 +660,30 @@ __device__ __forceinline__ void level_node(u32* pool, const LevelArrays& lv, int
   for (int i = 0; i < 4; i++) tile[i] = make_uint4(w0[2 * i], w1[2 * i], w0[2 * i + 1], w1[2 * i + 1]);
 }
 
-__global__ void __launch_bounds__(256)
-k_level(u32* pool, LevelArrays lv, const FrameState* __restrict__ fs, int d, int D, int mode, int fresh_tree,
-        const uint8_t* __restrict__ rgb, const float* __restrict__ colors4) {
+// Cooperative: wide levels are processed by the whole grid with a grid barrier between them; as soon as a level is
+// narrow (n_level is monotone in d) CTA 0 finishes all remaining levels alone with block barriers.
+#define LEVEL_THREADS 256
+#define LEVEL_NARROW 2048
+__global__ void __launch_bounds__(LEVEL_THREADS)
+k_levels(u32* pool, LevelArrays lv, const FrameState* fs, int D, int mode, const uint8_t* __restrict__ rgb,
+         const float* __restrict__ colors4) {
+  cg::grid_group grid = cg::this_grid();
   if (fs->overflow) return;
-  const int n_d = fs->n_level[d];
-  const int n_c = fs->n_level[d + 1];
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_d; idx += gridDim.x * blockDim.x)
-    level_node(pool, lv, n_d, n_c, d, D, mode, fresh_tree, rgb, colors4, idx);
-}
-
-// The upper levels of a frame hold a handful of nodes each: one CTA walks them all (levels d_top .. 0) with a block
-// barrier between levels instead of one launch per level.
-#define TAIL_THREADS 1024
-__global__ void __launch_bounds__(TAIL_THREADS)
-k_level_tail(u32* pool, LevelArrays lv, const FrameState* __restrict__ fs, int d_top, int D, int mode, int fresh_tree,
-             const uint8_t* __restrict__ rgb, const float* __restrict__ colors4) {
-  if (fs->overflow) return;
-  for (int d = d_top; d >= 0; d--) {
+  const int fresh_tree = fs->fresh;
+  int d = D - 1;
+  for (; d >= 0; d--) {
+    const int n_d = fs->n_level[d];
+    if (n_d <= LEVEL_NARROW) break;
+    const int n_c = fs->n_level[d + 1];
+    for (int idx = blockIdx.x * LEVEL_THREADS + threadIdx.x; idx < n_d; idx += gridDim.x * LEVEL_THREADS)
+      level_node(pool, lv, n_d, n_c, d, D, mode, fresh_tree, rgb, colors4, idx);
+    grid.sync();
+  }
+  if (blockIdx.x != 0) return;
+  for (; d >= 0; d--) {
     const int n_d = fs->n_level[d];
     const int n_c = fs->n_level[d + 1];
-    for (int idx = threadIdx.x; idx < n_d; idx += TAIL_THREADS)
+    for (int idx = threadIdx.x; idx < n_d; idx += LEVEL_THREADS)
       level_node(pool, lv, n_d, n_c, d, D, mode, fresh_tree, rgb, colors4, idx);
     __syncthreads();
   }
@@ -727,14 +764,94 @@ osl_status osl_grow_pool(osl_svo* t, size_t want_nodes, cudaStream_t st) {
   return OSL_OK;
 }
 
+int osl_structure_occupancy() {
+  int occ = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)k_structure, AN_THREADS, 0);
+  if (e != cudaSuccess) { g_osl_last_cuda_error = (int)e; return 0; }
+  return occ;
+}
+int osl_levels_occupancy() {
+  int occ = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)k_levels, LEVEL_THREADS, 0);
+  if (e != cudaSuccess) { g_osl_last_cuda_error = (int)e; return 0; }
+  return occ;
+}
+
+// Consume the result blocks of frames that have completed (non-blocking unless `block`): exact node count, counters.
+osl_status osl_poll_results(osl_svo* t, bool block) {
+  while (t->ring_tail != t->ring_head) {
+    const int slot = (int)(t->ring_tail % OSL_RING);
+    cudaError_t e = block ? cudaEventSynchronize(t->ring_ev[slot]) : cudaEventQuery(t->ring_ev[slot]);
+    if (e == cudaErrorNotReady) break;
+    if (e != cudaSuccess) { g_osl_last_cuda_error = (int)e; return OSL_ERR_CUDA; }
+    const FrameState& F = t->h_ring[slot];
+    t->inflight_headroom -= t->ring_headroom[slot];
+    t->ring_tail++;
+    if (F.overflow) {
+      t->sticky_error = OSL_ERR_POOL_OVERFLOW;  // the frame was dropped on the device (nothing written)
+    } else {
+      t->size = F.size_after;
+    }
+    const int D = t->tp.D;
+    osl_counters& c = t->counters;
+    c.n_points = F.n_in;
+    c.n_valid = F.n_valid;
+    c.n_unique = F.n_level[D];
+    c.n_split = F.n_split;
+    int64_t psum = 0;
+    for (int i = 0; i <= OSL_MAX_DEPTH; i++) {
+      c.pass_sizes[i] = (i < D) ? F.pass_count[i] : 0;
+      c.parents[i] = (i < D) ? F.n_level[i] : 0;
+      psum += c.parents[i];
+    }
+    c.n_nodes = t->size;
+    const int mode = t->ring_mode[slot];
+    const int64_t in_bytes = mode == 0 ? 5ll * F.n_in : (mode == 1 ? 15ll * F.n_in : 32ll * F.n_in);
+    c.algorithmic_bytes = in_bytes + 8 * c.n_unique + 68 * c.n_split + 68 * psum;
+    c.total_algorithmic_bytes += c.algorithmic_bytes;
+    c.frames++;
+  }
+  return OSL_OK;
+}
+
 osl_status osl_run_integrate(osl_svo* t, const EmitParams& ep, const void* colors, cudaStream_t st) {
   const int n = ep.n;
   const int D = t->tp.D;
   if (n < 0) return OSL_ERR_INVALID;
-  osl_status rc = osl_ensure_workspace(t, (size_t)(n > 0 ? n : 1));
+  if (t->sticky_error) return t->sticky_error;
+  osl_status rc = OSL_OK;
+  if ((size_t)(n > 0 ? n : 1) > t->ws_cap) {
+    rc = osl_poll_results(t, true);  // the workspace is in use by frames in flight
+    if (rc) return rc;
+    OSL_CUDA(cudaStreamSynchronize(st));
+    rc = osl_ensure_workspace(t, (size_t)(n > 0 ? n : 1));
+    if (rc) return rc;
+  }
+  rc = osl_poll_results(t, false);
   if (rc) return rc;
-  const int size0 = t->size > 8 ? t->size : 8;
-  const int fresh = t->size == 0;
+  if (t->ring_head - t->ring_tail >= OSL_RING) {  // result ring full: wait for the oldest frame
+    rc = osl_poll_results(t, true);
+    if (rc) return rc;
+  }
+  // Pool head-room.  A frame of n inputs can split at most n*D nodes (8*n*D new nodes); frames in flight are
+  // accounted with the same bound until their exact result has been read back.
+  const size_t headroom = 8ull * (size_t)(n > 0 ? n : 0) * (size_t)D;
+  size_t base = (size_t)(t->size > 8 ? t->size : 8);
+  if (base + t->inflight_headroom + headroom > t->cap_nodes) {
+    rc = osl_poll_results(t, true);  // get the exact size
+    if (rc) return rc;
+    base = (size_t)(t->size > 8 ? t->size : 8);
+    if (base + headroom > t->cap_nodes) {
+      size_t want = base + 2 * headroom;
+      if (want > ((size_t)1 << 30)) want = (size_t)1 << 30;
+      if (want > t->cap_nodes) {
+        rc = osl_grow_pool(t, want, st);
+        if (rc) return rc;
+      }
+      // at the 2^30-node cap the device-side overflow check still protects the pool; the frame is then dropped
+      // and OSL_ERR_POOL_OVERFLOW is reported by the next call
+    }
+  }
 
   const int etiles = (n + EMIT_TILE - 1) / EMIT_TILE;
   const int passes = (3 * D + 7) / 8;
@@ -747,7 +864,6 @@ osl_status osl_run_integrate(osl_svo* t, const EmitParams& ep, const void* color
     if (ep.mode == 0) vec_ok = ((reinterpret_cast<uintptr_t>(ep.depth) & 15) == 0);
     k_emit<<<etiles, EMIT_THREADS, 0, st>>>(ep, t->tp, vec_ok, t->d_keysA, t->d_payA, t->d_emit_status, t->d_fs);
     OSL_LAUNCHED(1);
-    // cooperative persistent sort
     int grid = (n + SORT_TILE - 1) / SORT_TILE;
     if (grid > t->sort_grid) grid = t->sort_grid;
     if (grid < 1) grid = 1;
@@ -757,66 +873,37 @@ osl_status osl_run_integrate(osl_svo* t, const EmitParams& ep, const void* color
     OSL_CUDA(cudaLaunchCooperativeKernel((void*)k_sort, dim3(grid), dim3(SORT_THREADS), args, 0, st));
     OSL_LAUNCHED(1);
   } else {
-    OSL_CUDA(cudaMemsetAsync(t->d_fs, 0, sizeof(FrameState), st));
+    OSL_CUDA(cudaMemsetAsync(t->d_fs, 0, 3 * sizeof(int), st));  // n_in = n_valid = n_invalid_front = 0
   }
-
-  const int ablocks = (n + AN_THREADS - 1) / AN_THREADS;
-  const int NC = OSL_NCOUNT(D);
-  for (int attempt = 0;; attempt++) {
-    if (n > 0) {
-      k_analyze<<<ablocks, AN_THREADS, 0, st>>>(skeys, t->d_pool, t->tp, t->d_fs, t->d_m, t->d_s, t->d_blockcnt);
-      OSL_LAUNCHED(1);
-    }
-    k_scan<<<(NC + SCAN_THREADS / 32 - 1) / (SCAN_THREADS / 32), SCAN_THREADS, 0, st>>>(
-        t->d_blockcnt, t->d_scan_totals, t->d_scan_totals + NC_MAX, t->d_fs, D, size0, (int)t->cap_nodes);
+  {
+    int grid = (n + AN_THREADS - 1) / AN_THREADS;
+    if (grid > t->structure_grid) grid = t->structure_grid;
+    if (grid < 1) grid = 1;
+    const u64* a0 = skeys; const u32* a1 = spay; const u32* a2 = t->d_pool; TreeParams a3 = t->tp; FrameState* a4 = t->d_fs;
+    uint8_t* a5 = t->d_m; uint8_t* a6 = t->d_s; u32* a7 = t->d_blockcnt; u32* a8 = t->d_scan_totals;
+    LevelArrays a9 = t->lv; int a10 = ep.mode; int a11 = (int)t->cap_nodes;
+    void* args[] = {&a0, &a1, &a2, &a3, &a4, &a5, &a6, &a7, &a8, &a9, &a10, &a11};
+    OSL_CUDA(cudaLaunchCooperativeKernel((void*)k_structure, dim3(grid), dim3(AN_THREADS), args, 0, st));
     OSL_LAUNCHED(1);
-    OSL_CUDA(cudaMemcpyAsync(t->h_fs, t->d_fs, sizeof(FrameState), cudaMemcpyDeviceToHost, st));
-    OSL_CUDA(cudaStreamSynchronize(st));
-    if (!t->h_fs->overflow) break;
-    if (attempt > 0) return OSL_ERR_CUDA;
-    const long long want = (long long)size0 + 8ll * t->h_fs->n_split;
-    if (want > (1ll << 30)) return OSL_ERR_POOL_OVERFLOW;
-    rc = osl_grow_pool(t, (size_t)want, st);
-    if (rc) return rc;
   }
-  const FrameState& F = *t->h_fs;
-
-  if (n > 0 && F.n_valid > 0) {
-    k_assign<<<(F.n_valid + AN_THREADS - 1) / AN_THREADS, AN_THREADS, 0, st>>>(
-        skeys, spay, t->d_pool, t->tp, t->d_fs, t->d_m, t->d_s, t->d_blockcnt, t->lv, ep.mode);
+  if (n > 0) {
+    int grid = (n / 4 + LEVEL_THREADS - 1) / LEVEL_THREADS;  // level D-1 rarely exceeds n/4 nodes; grid-stride anyway
+    if (grid > t->levels_grid) grid = t->levels_grid;
+    if (grid < 1) grid = 1;
+    u32* a0 = t->d_pool; LevelArrays a1 = t->lv; const FrameState* a2 = t->d_fs; int a3 = D; int a4 = ep.mode;
+    const uint8_t* a5 = ep.rgb; const float* a6 = (const float*)colors;
+    void* args[] = {&a0, &a1, &a2, &a3, &a4, &a5, &a6};
+    OSL_CUDA(cudaLaunchCooperativeKernel((void*)k_levels, dim3(grid), dim3(LEVEL_THREADS), args, 0, st));
     OSL_LAUNCHED(1);
-    int d = D - 1;
-    for (; d >= 0 && F.n_level[d] > 2 * TAIL_THREADS; d--) {  // wide levels: one launch each
-      const int nd = F.n_level[d];
-      int blocks = (nd + 255) / 256;
-      if (blocks > t->num_sms * 16) blocks = t->num_sms * 16;
-      k_level<<<blocks, 256, 0, st>>>(t->d_pool, t->lv, t->d_fs, d, D, ep.mode, fresh, ep.rgb,
-                                     (const float*)colors);
-      OSL_LAUNCHED(1);
-    }
-    if (d >= 0) {  // the narrow upper levels (n_level is monotone in d): one CTA, block barriers
-      k_level_tail<<<1, TAIL_THREADS, 0, st>>>(t->d_pool, t->lv, t->d_fs, d, D, ep.mode, fresh, ep.rgb,
-                                              (const float*)colors);
-      OSL_LAUNCHED(1);
-    }
   }
-  OSL_CUDA(cudaGetLastError());
-  t->size = F.size_after;  // a fresh tree starts from the 8 root children (svo.cu:646-649)
-
-  osl_counters& c = t->counters;
-  c.n_points = n;
-  c.n_valid = F.n_valid;
-  c.n_unique = F.n_level[D];
-  c.n_split = F.n_split;
-  int64_t psum = 0;
-  for (int i = 0; i <= OSL_MAX_DEPTH; i++) {
-    c.pass_sizes[i] = (i < D) ? F.pass_count[i] : 0;
-    c.parents[i] = (i < D) ? F.n_level[i] : 0;
-    psum += c.parents[i];
-  }
-  c.n_nodes = t->size;
-  const int64_t in_bytes = ep.mode == 0 ? 5ll * n : (ep.mode == 1 ? 15ll * n : 32ll * n);
-  c.algorithmic_bytes = in_bytes + 8 * c.n_unique + 68 * c.n_split + 68 * psum;
-  c.frames++;
+  // result block -> pinned ring (read lazily; the caller never waits for it unless it asks for sizes/counters)
+  const int slot = (int)(t->ring_head % OSL_RING);
+  OSL_CUDA(cudaMemcpyAsync(&t->h_ring[slot], t->d_fs, sizeof(FrameState), cudaMemcpyDeviceToHost, st));
+  OSL_CUDA(cudaEventRecord(t->ring_ev[slot], st));
+  t->ring_headroom[slot] = headroom;
+  t->ring_mode[slot] = ep.mode;
+  t->inflight_headroom += headroom;
+  t->ring_head++;
+  t->last_stream = st;
   return OSL_OK;
 }

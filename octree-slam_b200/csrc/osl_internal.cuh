@@ -15,6 +15,8 @@ typedef unsigned int u32;
 #define OSL_NONE 0xFFu         // (internal) "no frontier": the whole path of a key already exists
 
 #define OSL_MAXD OSL_MAX_DEPTH
+#define OSL_RING 8    // per-frame result blocks in flight
+#define OSL_STAGES 3  // device staging slots of the *_host entry points
 #define OSL_NCOUNT(D) ((D) + ((D) + 1) * ((D) + 1))
 #define OSL_CLVL(D, d) ((d)-1)
 #define OSL_CBKT(D, s, d) ((D) + (s) * ((D) + 1) + (d))
@@ -29,6 +31,9 @@ struct FrameState {
   int size_after;
   int overflow;     // 1: size_after exceeds the pool capacity -> nothing was written
   int capacity;     // nodes
+  int cur_size;     // nodes in the pool (persistent across frames; 0 = fresh tree)
+  int fresh;        // this frame started from an empty tree (root tile is zero-initialised)
+  int frame_seq;    // frames processed
   int n_level[OSL_MAXD + 2];                  // n_level[d] = distinct touched nodes at depth d (d = 1..D)
   int pass_count[OSL_MAXD + 1];               // |codes[i]| of reference pass i
   int base[(OSL_MAXD + 1) * (OSL_MAXD + 1)];  // base[s*(D+1)+d]: first global split rank of bucket (frontier s, depth d)
@@ -152,10 +157,18 @@ struct osl_svo {
   LevelArrays lv;
   void* d_level_mem;
   FrameState* d_fs;
-  FrameState* h_fs;   // pinned
-  uint16_t* d_depth_stage; uint8_t* d_rgb_stage; size_t stage_cap;  // for *_host entry points
-  void* h_pin_depth; void* h_pin_rgb;
-  float* d_xyz_stage;
+  FrameState* h_ring;                    // pinned ring of per-frame result blocks
+  cudaEvent_t ring_ev[OSL_RING];
+  size_t ring_headroom[OSL_RING];
+  int ring_mode[OSL_RING];
+  unsigned long long ring_head, ring_tail;  // frames enqueued / consumed
+  size_t inflight_headroom;              // worst-case node growth of frames not yet read back
+  osl_status sticky_error;
+  cudaStream_t last_stream;
+  cudaStream_t copy_stream;              // *_host entry points: H2D overlaps the previous frame's kernels
+  cudaEvent_t stage_copied[OSL_STAGES], stage_free[OSL_STAGES];
+  uint16_t* d_depth_stage[OSL_STAGES]; uint8_t* d_rgb_stage[OSL_STAGES]; size_t stage_cap; unsigned long long stage_seq;
+  int structure_grid, levels_grid;
   osl_counters counters;
   int sort_grid;      // co-resident CTAs for the cooperative sort
   int num_sms;
@@ -182,6 +195,9 @@ struct EmitParams {
 osl_status osl_run_integrate(osl_svo* t, const EmitParams& ep, const void* colors, cudaStream_t st);
 osl_status osl_ensure_workspace(osl_svo* t, size_t n);
 int osl_sort_occupancy();  // co-resident k_sort CTAs per SM
+int osl_structure_occupancy();
+int osl_levels_occupancy();
+osl_status osl_poll_results(osl_svo* t, bool block);
 osl_status osl_grow_pool(osl_svo* t, size_t want_nodes, cudaStream_t st);
 
 // raycast / extraction / image kernels

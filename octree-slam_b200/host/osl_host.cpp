@@ -1,0 +1,312 @@
+// osl_host.cpp -- C++ host side above the C ABI: the reference's world / rendering / sensor interface for the hot
+// path (same names, argument meaning and ownership rules), implemented as thin forwards to libosl_b200.so.
+// Replaces src/world/octree.cpp:251-389 (Octree), src/world/scene.cpp:87-113 (Scene), the callers' view of
+// src/world/svo/svo.cu:584-745, src/rendering/cone_tracing_kernels.cu:157-198, src/rendering/cuda_renderer.cpp:158-171
+// and src/sensor/image_kernels.cu:55-58,96-102,217-219.  No CUDA code here: device memory is handled by the C ABI
+// and by cudart's C API (cudaMalloc/cudaFree/cudaMemcpy) for the buffers the reference's structs own.
+#include <cuda_runtime_api.h>
+
+#include <cmath>
+#include <cstdio>
+#include <map>
+#include <mutex>
+
+#include <octree_slam/common_types.h>
+#include <octree_slam/rendering/cone_tracing_kernels.h>
+#include <octree_slam/rendering/cuda_renderer.h>
+#include <octree_slam/sensor/image_kernels.h>
+#include <octree_slam/world/octree.h>
+#include <octree_slam/world/scene.h>
+#include <octree_slam/world/svo/svo.h>
+
+#include "osl_b200.h"
+
+// ---- common_types.cu:36-52 -------------------------------------------------------------------------------------
+RawFrame::RawFrame(const int w, const int h) : width(w), height(h) {
+  cudaMalloc((void**)&color, (size_t)h * w * sizeof(Color256));
+  cudaMalloc((void**)&depth, (size_t)h * w * sizeof(uint16_t));
+  timestamp = 0;
+}
+RawFrame::~RawFrame() {
+  cudaFree(color);
+  cudaFree(depth);
+}
+VoxelGrid::~VoxelGrid() {
+  if (size > 0) {
+    cudaFree(centers);
+    cudaFree(colors);
+  }
+}
+
+static void report(osl_status s, const char* where) {
+  // the reference returns void and checks nothing on this path; errors are reported, never fatal
+  if (s != OSL_OK) fprintf(stderr, "[octree_slam] %s: %s (cuda %d)\n", where, osl_status_string(s), osl_last_cuda_error());
+}
+
+namespace octree_slam {
+
+// ---- svo.h -----------------------------------------------------------------------------------------------------
+namespace svo {
+
+// pool pointer -> owning handle (the reference hands raw pool pointers around)
+static std::map<const void*, osl_svo*>& registry() {
+  static std::map<const void*, osl_svo*> r;
+  return r;
+}
+static std::mutex& reg_mutex() {
+  static std::mutex m;
+  return m;
+}
+
+static osl_svo* lookup_or_create(unsigned int* octree, int octree_size, glm::vec3 c, float edge, int max_depth) {
+  std::lock_guard<std::mutex> g(reg_mutex());
+  if (octree_size != 0 && octree) {
+    auto it = registry().find(octree);
+    if (it != registry().end()) return it->second;
+    fprintf(stderr, "[octree_slam] unknown pool pointer %p: pools are created by svoFrom*() with octree_size == 0\n",
+            (void*)octree);
+    return nullptr;
+  }
+  osl_svo* t = nullptr;
+  const float cc[3] = {c.x, c.y, c.z};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  report(osl_svo_create(&t, cc, edge, max_depth, 0, dev), "osl_svo_create");
+  return t;
+}
+
+static void publish(osl_svo* t, unsigned int* old_ptr, unsigned int*& octree, int& octree_size) {
+  const uint32_t* pool = nullptr;
+  int n = 0;
+  report(osl_svo_view(t, &pool, &n, nullptr, nullptr), "osl_svo_view");
+  std::lock_guard<std::mutex> g(reg_mutex());
+  if (old_ptr) registry().erase(old_ptr);
+  registry()[pool] = t;
+  octree = const_cast<unsigned int*>(pool);
+  octree_size = n;
+}
+
+void svoFromPointCloud(const glm::vec3* points, const Color256* colors, const int size, const int max_depth,
+                       unsigned int*& octree, int& octree_size, glm::vec3 octree_center, const float edge_length,
+                       void*) {
+  osl_svo* t = lookup_or_create(octree, octree_size, octree_center, edge_length, max_depth);
+  if (!t) return;
+  report(osl_integrate_points(t, &points->x, &colors->r, size, nullptr), "osl_integrate_points");
+  publish(t, octree_size ? octree : nullptr, octree, octree_size);
+}
+
+void svoFromVoxelGrid(const VoxelGrid& grid, const int max_depth, unsigned int*& octree, int& octree_size,
+                      glm::vec3 octree_center, const float edge_length, void*) {
+  osl_svo* t = lookup_or_create(octree, octree_size, octree_center, edge_length, max_depth);
+  if (!t) return;
+  report(osl_integrate_voxels(t, &grid.centers->x, &grid.colors->x, grid.size, nullptr), "osl_integrate_voxels");
+  publish(t, octree_size ? octree : nullptr, octree, octree_size);
+}
+
+void svoFromDepthFrame(const uint16_t* depth, const Color256* colors, int width, int height, glm::vec2 focal_length,
+                       const glm::mat4& pose, const int max_depth, unsigned int*& octree, int& octree_size,
+                       glm::vec3 octree_center, const float edge_length) {
+  osl_svo* t = lookup_or_create(octree, octree_size, octree_center, edge_length, max_depth);
+  if (!t) return;
+  report(osl_integrate_depth(t, depth, &colors->r, width, height, focal_length.x, focal_length.y,
+                             glm::value_ptr(pose), nullptr), "osl_integrate_depth");
+  publish(t, octree_size ? octree : nullptr, octree, octree_size);
+}
+
+void extractVoxelGridFromSVO(unsigned int*& octree, int& octree_size, const int max_depth, const glm::vec3,
+                             float, VoxelGrid& grid) {
+  osl_svo* t = nullptr;
+  {
+    std::lock_guard<std::mutex> g(reg_mutex());
+    auto it = registry().find(octree);
+    if (it != registry().end()) t = it->second;
+  }
+  if (!t || octree_size == 0) { grid.size = 0; return; }
+  int64_t n = 0;
+  report(osl_extract_voxels(t, max_depth, nullptr, nullptr, nullptr, 0, &n, nullptr), "osl_extract_voxels");
+  grid.size = (int)n;
+  cudaMalloc((void**)&grid.centers, (size_t)(n > 0 ? n : 1) * sizeof(glm::vec4));  // svo.cu:732-733
+  cudaMalloc((void**)&grid.colors, (size_t)(n > 0 ? n : 1) * sizeof(glm::vec4));
+  if (n > 0)
+    report(osl_extract_voxels(t, max_depth, &grid.centers->x, &grid.colors->x, nullptr, n, &n, nullptr),
+           "osl_extract_voxels");
+}
+
+void releaseSVO(unsigned int* octree) {
+  osl_svo* t = nullptr;
+  {
+    std::lock_guard<std::mutex> g(reg_mutex());
+    auto it = registry().find(octree);
+    if (it == registry().end()) return;
+    t = it->second;
+    registry().erase(it);
+  }
+  osl_svo_destroy(t);
+}
+
+}  // namespace svo
+
+// ---- world::Octree (octree.cpp:251-389) ------------------------------------------------------------------------
+namespace world {
+
+Octree::Octree(const float resolution, const glm::vec3& center, const float size)
+    : svo_(nullptr), center_(center), size_(size), resolution_(resolution) {}
+
+Octree::~Octree() {
+  if (svo_) osl_svo_destroy(svo_);
+}
+
+int Octree::maxDepth(float resolution) const {
+  // octree.cpp:283-284 with node_depth = 0 (the root sub-tree is the GPU tree).  Under g++ the reference's
+  // unqualified log() resolves to the double overload; the quotient is taken in double, ceil'd and truncated.
+  const float edge_length = size_ / std::pow(2.0f, (float)0);
+  return (int)std::ceil(std::log((double)(float)(edge_length / resolution)) / (double)std::log(2.0f));
+}
+
+osl_svo* Octree::tree(int max_depth) {
+  if (!svo_) {
+    const float c[3] = {center_.x, center_.y, center_.z};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    report(osl_svo_create(&svo_, c, size_, max_depth, 0, dev), "osl_svo_create");
+  }
+  return svo_;
+}
+
+void Octree::addCloud(const glm::vec3&, const glm::vec3* points, const Color256* colors, const int size,
+                      const BoundingBox&) {
+  osl_svo* t = tree(maxDepth(resolution_));
+  if (t) report(osl_integrate_points(t, &points->x, &colors->r, size, nullptr), "osl_integrate_points");
+}
+
+void Octree::addDepthFrame(const uint16_t* depth, const Color256* colors, int width, int height,
+                           glm::vec2 focal_length, const glm::mat4& pose) {
+  osl_svo* t = tree(maxDepth(resolution_));
+  if (t)
+    report(osl_integrate_depth(t, depth, &colors->r, width, height, focal_length.x, focal_length.y,
+                               glm::value_ptr(pose), nullptr), "osl_integrate_depth");
+}
+
+void Octree::addVoxelGrid(const VoxelGrid& grid) {
+  osl_svo* t = tree(maxDepth(resolution_));
+  if (t) report(osl_integrate_voxels(t, &grid.centers->x, &grid.colors->x, grid.size, nullptr), "osl_integrate_voxels");
+}
+
+void Octree::extractVoxelGrid(VoxelGrid& grid) {
+  if (!svo_) { grid.size = 0; return; }
+  const int max_depth = maxDepth(grid.scale);  // octree.cpp:330
+  int64_t n = 0;
+  report(osl_extract_voxels(svo_, max_depth, nullptr, nullptr, nullptr, 0, &n, nullptr), "osl_extract_voxels");
+  grid.size = (int)n;
+  cudaMalloc((void**)&grid.centers, (size_t)(n > 0 ? n : 1) * sizeof(glm::vec4));
+  cudaMalloc((void**)&grid.colors, (size_t)(n > 0 ? n : 1) * sizeof(glm::vec4));
+  if (n > 0)
+    report(osl_extract_voxels(svo_, max_depth, &grid.centers->x, &grid.colors->x, nullptr, n, &n, nullptr),
+           "osl_extract_voxels");
+}
+
+SVO Octree::extractSVO(const BoundingBox&) {
+  SVO out;
+  out.data = nullptr;
+  out.center = center_;
+  out.size = size_;  // size_/2^node_depth with node_depth = 0 (octree.cpp:357)
+  if (svo_) {
+    const uint32_t* pool = nullptr;
+    report(osl_svo_view(svo_, &pool, nullptr, nullptr, nullptr), "osl_svo_view");
+    out.data = const_cast<unsigned int*>(pool);
+  }
+  return out;
+}
+
+BoundingBox Octree::boundingBox() const {
+  BoundingBox box;
+  box.bbox0 = center_ - glm::vec3(size_, size_, size_);
+  box.bbox1 = center_ + glm::vec3(size_, size_, size_);
+  return box;
+}
+
+void Octree::expandBySize(const float) {
+  // Quirk Q10: the reference re-scales size_ although OctreeNode::expand() refuses GPU-backed nodes, silently
+  // corrupting the map.  The hot-path contract is a fixed (center, half size); expansion is a no-op here.
+}
+
+int Octree::nodeCount() const { return svo_ ? osl_svo_size(svo_) : 0; }
+
+// ---- world::Scene (scene.cpp:87-113) ---------------------------------------------------------------------------
+Scene::Scene() : voxel_grid_(new VoxelGrid()), tree_(nullptr) {}
+
+Scene::~Scene() {
+  delete tree_;
+  delete voxel_grid_;
+}
+
+void Scene::extractVoxelGridFromOctree() {
+  delete voxel_grid_;
+  voxel_grid_ = new VoxelGrid();
+  if (!tree_) return;
+  voxel_grid_->bbox = tree_->boundingBox();
+  voxel_grid_->scale = 0.01f;  // scene.cpp:94
+  tree_->extractVoxelGrid(*voxel_grid_);
+}
+
+void Scene::addPointCloudToOctree(const glm::vec3& origin, const glm::vec3* points, const Color256* colors,
+                                  const int size, const BoundingBox& bbox) {
+  if (!tree_) {
+    // scene.cpp:100-102: resolution 0.01, centre = bbox mid-point, size = bbox.bbox1.x (sic, quirk Q10)
+    tree_ = new Octree(0.01f, (bbox.bbox1 + bbox.bbox0) / 2.0f, bbox.bbox1.x);
+  } else if (!tree_->boundingBox().contains(bbox)) {
+    tree_->expandBySize(0.0f);
+  }
+  tree_->addCloud(origin, points, colors, size, bbox);
+}
+
+}  // namespace world
+
+// ---- rendering (cone_tracing_kernels.cu:157-198, cuda_renderer.cpp:158-171) --------------------------------------
+namespace rendering {
+
+void coneTraceSVO(uchar4* pos, glm::vec2 resolution, float fov, glm::mat4 cameraPose, SVO octree) {
+  const float c[3] = {octree.center.x, octree.center.y, octree.center.z};
+  report(osl_raycast_pool(octree.data, c, octree.size, &pos->x, (int)resolution.x, (int)resolution.y, fov,
+                          glm::value_ptr(cameraPose), nullptr, nullptr, nullptr), "osl_raycast_pool");
+  cudaDeviceSynchronize();  // the reference call is synchronous on return
+}
+
+CUDARenderer::CUDARenderer(const int width, const int height) : width_(width), height_(height), d_pixels_(nullptr) {
+  cudaMalloc((void**)&d_pixels_, (size_t)width * height * sizeof(uchar4));
+}
+CUDARenderer::~CUDARenderer() { cudaFree(d_pixels_); }
+
+void CUDARenderer::coneTraceSVO(const SVO& octree, const Camera& camera, const glm::vec3&) {
+  rendering::coneTraceSVO(d_pixels_, glm::vec2((float)width_, (float)height_), camera.fov, camera.view, octree);
+}
+
+void CUDARenderer::download(uchar4* host_pixels) const {
+  cudaMemcpy(host_pixels, d_pixels_, (size_t)width_ * height_ * sizeof(uchar4), cudaMemcpyDeviceToHost);
+}
+
+}  // namespace rendering
+
+// ---- sensor (image_kernels.cu:55-58, 96-102, 217-219) ------------------------------------------------------------
+namespace sensor {
+
+void generateVertexMap(const uint16_t* depth_pixels, glm::vec3* vertex_map, const int width, const int height,
+                       const glm::vec2 focal_length, const int2 img_size) {
+  report(osl_generate_vertex_map(depth_pixels, &vertex_map->x, width, height, focal_length.x, focal_length.y,
+                                 img_size.x, img_size.y, nullptr), "osl_generate_vertex_map");
+  cudaDeviceSynchronize();  // image_kernels.cu:57
+}
+
+void transformVertexMap(glm::vec3* vertex_map, const glm::mat4& trans, const int size) {
+  report(osl_transform_vertex_map(&vertex_map->x, glm::value_ptr(trans), size, nullptr), "osl_transform_vertex_map");
+}
+
+void computePointCloudBoundingBox(glm::vec3* points, const int num_points, BoundingBox& bbox) {
+  float b[6] = {bbox.bbox0.x, bbox.bbox0.y, bbox.bbox0.z, bbox.bbox1.x, bbox.bbox1.y, bbox.bbox1.z};
+  report(osl_point_cloud_bbox(&points->x, num_points, b, nullptr), "osl_point_cloud_bbox");
+  bbox.bbox0 = glm::vec3(b[0], b[1], b[2]);
+  bbox.bbox1 = glm::vec3(b[3], b[4], b[5]);
+}
+
+}  // namespace sensor
+}  // namespace octree_slam

@@ -65,6 +65,7 @@ class SVO:
         c = _dev(rgb, np.uint8, self.device)
         _check(lib().osl_integrate_depth(self._h, d.data_ptr(), c.data_ptr(), w, h, fx, fy,
                                          _f(mat_colmajor(pose)), stream), "osl_integrate_depth")
+        self._keep = (d, c)  # the call is asynchronous: keep the device buffers alive until the next call
         return self
 
     def integrate_depth_host(self, depth, rgb, fx, fy, pose=IDENTITY, stream=None):
@@ -73,6 +74,7 @@ class SVO:
         h, w = depth.shape
         _check(lib().osl_integrate_depth_host(self._h, _hptr(depth), _hptr(rgb), w, h, fx, fy,
                                               _f(mat_colmajor(pose)), stream), "osl_integrate_depth_host")
+        self._keep = (depth, rgb)
         return self
 
     def integrate_points(self, xyz, rgb, stream=None):
@@ -81,6 +83,7 @@ class SVO:
         n = p.shape[0]
         _check(lib().osl_integrate_points(self._h, p.data_ptr() if n else None, c.data_ptr() if n else None, n,
                                           stream), "osl_integrate_points")
+        self._keep = (p, c)
         return self
 
     def integrate_voxels(self, centers4, colors4, stream=None):
@@ -89,6 +92,7 @@ class SVO:
         n = p.shape[0]
         _check(lib().osl_integrate_voxels(self._h, p.data_ptr() if n else None, c.data_ptr() if n else None, n,
                                           stream), "osl_integrate_voxels")
+        self._keep = (p, c)
         return self
 
     # ---- views -----------------------------------------------------------------------------------------
@@ -106,6 +110,9 @@ class SVO:
     def load(self, pool):
         pool = np.ascontiguousarray(pool, dtype=np.uint32)
         _check(lib().osl_svo_upload(self._h, _hptr(pool), pool.size // 2), "osl_svo_upload")
+
+    def sync(self):
+        _check(lib().osl_svo_sync(self._h), "osl_svo_sync")
 
     def reset(self):
         _check(lib().osl_svo_reset(self._h), "osl_svo_reset")
