@@ -6,7 +6,10 @@
 
 #include "glm/glm.hpp"
 
-#ifndef __VECTOR_TYPES_H__
+#if defined(__has_include) && __has_include(<vector_types.h>)
+#include <vector_types.h>      // CUDA's uchar4 / int2 when the toolkit headers are on the include path
+#include <vector_functions.h>  // make_int2
+#elif !defined(__VECTOR_TYPES_H__)
 struct uchar4 { unsigned char x, y, z, w; };
 struct int2 { int x, y; };
 static inline int2 make_int2(int x, int y) { int2 r; r.x = x; r.y = y; return r; }

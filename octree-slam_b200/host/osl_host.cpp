@@ -22,7 +22,7 @@
 #include "osl_b200.h"
 
 // ---- common_types.cu:36-52 -------------------------------------------------------------------------------------
-RawFrame::RawFrame(const int w, const int h) : width(w), height(h) {
+RawFrame::RawFrame(const int w, const int h) : height(h), width(w) {
   cudaMalloc((void**)&color, (size_t)h * w * sizeof(Color256));
   cudaMalloc((void**)&depth, (size_t)h * w * sizeof(uint16_t));
   timestamp = 0;

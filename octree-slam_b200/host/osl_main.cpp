@@ -1,0 +1,110 @@
+// osl_main.cpp -- headless replay of the reference's frame loop (src/main.cpp:31-62) on top of the drop-in headers.
+// The body of the loop is the reference's call sequence verbatim (main.cpp:38-44, 56-58); what differs is what the
+// reference cannot do headless: frames come from a file instead of an OpenNI camera (openni_device.cpp:96-150), the
+// pose comes with the frame instead of RGBDCamera (whose update is commented out, main.cpp:35), and the renderer
+// writes a device buffer instead of a GL PBO.
+//
+//   osl_main <frames.bin> <out_prefix> [fused]
+// frames.bin: int32 w, h, n; float fx, fy; then n x { float pose[16] (column-major), uint16 depth[w*h], uint8 rgb[w*h*3] }
+// writes <out_prefix>.pool (int32 n_nodes, float center[3], float half, uint32 pool[2n]) and <out_prefix>.rgba (w*h*4).
+#include <cuda_runtime_api.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include <octree_slam/common_types.h>
+#include <octree_slam/rendering/cuda_renderer.h>
+#include <octree_slam/sensor/image_kernels.h>
+#include <octree_slam/world/scene.h>
+
+using namespace octree_slam;
+
+static bool read_exact(FILE* f, void* p, size_t n) { return fread(p, 1, n, f) == n; }
+
+int main(int argc, char** argv) {
+  if (argc < 3) {
+    fprintf(stderr, "usage: %s frames.bin out_prefix [fused]\n", argv[0]);
+    return 2;
+  }
+  const bool fused = argc > 3 && !strcmp(argv[3], "fused");
+  FILE* f = fopen(argv[1], "rb");
+  if (!f) { perror(argv[1]); return 2; }
+  int hdr[3];
+  float focal[2];
+  if (!read_exact(f, hdr, sizeof(hdr)) || !read_exact(f, focal, sizeof(focal))) return 2;
+  const int W = hdr[0], H = hdr[1], n_frames = hdr[2];
+  const int num_points = W * H;
+
+  // init() (main.cpp:86-150) minus GLFW / OpenNI
+  RawFrame frame(W, H);                                   // OpenNIDevice::raw_frame_
+  glm::vec3* points_ = nullptr;                           // main.cpp:139
+  cudaMalloc((void**)&points_, (size_t)num_points * sizeof(glm::vec3));
+  world::Scene* scene_ = new world::Scene();
+  rendering::CUDARenderer* cuda_renderer_ = new rendering::CUDARenderer(W, H);
+  Camera camera;                                          // GLFWCameraController::camera(): fov = 45
+  camera.view[0].x = -1.0f;                               // look down +z like the depth camera (the reference's
+  camera.view[2].z = -1.0f;                               // renderer looks down -z for view = identity)
+  const glm::vec2 focal_length(focal[0], focal[1]);
+
+  std::vector<uint16_t> h_depth((size_t)num_points);
+  std::vector<uint8_t> h_rgb((size_t)num_points * 3);
+  BoundingBox cloud_bbox;
+  for (int k = 0; k < n_frames; k++) {
+    glm::mat4 pose;
+    if (!read_exact(f, &pose[0].x, 64) || !read_exact(f, h_depth.data(), h_depth.size() * 2) ||
+        !read_exact(f, h_rgb.data(), h_rgb.size()))
+      return 2;
+    // OpenNIDevice::readFrame (openni_device.cpp:122,144)
+    cudaMemcpy(frame.depth, h_depth.data(), h_depth.size() * 2, cudaMemcpyHostToDevice);
+    cudaMemcpy(frame.color, h_rgb.data(), h_rgb.size(), cudaMemcpyHostToDevice);
+
+    // main.cpp:38-44
+    sensor::generateVertexMap(frame.depth, points_, W, H, focal_length, make_int2(W, H));
+    sensor::transformVertexMap(points_, pose, W * H);
+    cudaDeviceSynchronize();
+    cloud_bbox = BoundingBox();
+    sensor::computePointCloudBoundingBox(points_, num_points, cloud_bbox);
+    if (fused && scene_->tree()) {
+      // the one-call fast path for every frame after the one that creates the tree
+      scene_->tree()->addDepthFrame(frame.depth, frame.color, W, H, focal_length, pose);
+    } else {
+      scene_->addPointCloudToOctree(glm::vec3(pose[3].x, pose[3].y, pose[3].z), points_, frame.color, num_points,
+                                    cloud_bbox);
+    }
+  }
+  fclose(f);
+
+  // main.cpp:56-58
+  SVO svo = scene_->svo(cloud_bbox);
+  cuda_renderer_->coneTraceSVO(svo, camera, glm::vec3(0.0f));
+
+  const int n_nodes = scene_->tree()->nodeCount();
+  std::vector<uint32_t> pool((size_t)n_nodes * 2);
+  cudaMemcpy(pool.data(), svo.data, pool.size() * 4, cudaMemcpyDeviceToHost);
+  std::vector<uchar4> img((size_t)num_points);
+  cuda_renderer_->download(img.data());
+
+  char path[4096];
+  snprintf(path, sizeof(path), "%s.pool", argv[2]);
+  FILE* o = fopen(path, "wb");
+  if (!o) { perror(path); return 2; }
+  fwrite(&n_nodes, 4, 1, o);
+  fwrite(&svo.center.x, 4, 3, o);
+  fwrite(&svo.size, 4, 1, o);
+  fwrite(pool.data(), 4, pool.size(), o);
+  fclose(o);
+  snprintf(path, sizeof(path), "%s.rgba", argv[2]);
+  o = fopen(path, "wb");
+  if (!o) { perror(path); return 2; }
+  fwrite(img.data(), 4, img.size(), o);
+  fclose(o);
+  printf("osl_main: %d frames %dx%d -> %d nodes (center %.6f %.6f %.6f, half %.6f)\n", n_frames, W, H, n_nodes,
+         svo.center.x, svo.center.y, svo.center.z, svo.size);
+
+  delete cuda_renderer_;
+  delete scene_;
+  cudaFree(points_);
+  return 0;
+}

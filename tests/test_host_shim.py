@@ -1,0 +1,87 @@
+"""The C++ host side above the C ABI (octree-slam_b200/host): libosl_host.so re-creates the reference's
+world / rendering / sensor interface; osl_main replays main.cpp:31-62 headless.  CPU part: the library exports the
+reference's function and class symbols.  GPU part: the replay's pool and image equal the oracle's."""
+import math
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from common import LOOK_PLUS_Z, ROOT, pkg
+from oracle import oracle as orc
+
+PKG_DIR = os.path.join(ROOT, "octree-slam_b200")
+HOST_LIB = os.path.join(PKG_DIR, "libosl_host.so")
+HOST_MAIN = os.path.join(PKG_DIR, "osl_main")
+
+
+def test_host_library_exports_the_reference_interface():
+    pkg()  # build() has produced the libraries
+    assert os.path.exists(HOST_LIB) and os.path.exists(HOST_MAIN)
+    syms = subprocess.check_output(["nm", "-D", "--demangle", "--defined-only", HOST_LIB], text=True)
+    for name in ["octree_slam::svo::svoFromPointCloud(", "octree_slam::svo::svoFromVoxelGrid(",
+                 "octree_slam::svo::extractVoxelGridFromSVO(", "octree_slam::rendering::coneTraceSVO(",
+                 "octree_slam::sensor::generateVertexMap(", "octree_slam::sensor::transformVertexMap(",
+                 "octree_slam::sensor::computePointCloudBoundingBox(", "octree_slam::world::Octree::addCloud(",
+                 "octree_slam::world::Octree::addVoxelGrid(", "octree_slam::world::Octree::extractVoxelGrid(",
+                 "octree_slam::world::Octree::extractSVO(", "octree_slam::world::Scene::addPointCloudToOctree(",
+                 "octree_slam::world::Scene::extractVoxelGridFromOctree(",
+                 "octree_slam::rendering::CUDARenderer::coneTraceSVO("]:
+        assert name in syms, "libosl_host.so does not define %s" % name
+    # the host side contains no device code and needs only the C ABI + cudart
+    needed = subprocess.check_output(["readelf", "-d", HOST_LIB], text=True)
+    assert "libosl_b200.so" in needed and "libcudart" in needed
+
+
+def _write_frames(path, w, h, frames, fx, fy):
+    with open(path, "wb") as f:
+        f.write(struct.pack("<iiiff", w, h, len(frames), fx, fy))
+        for pose, depth, rgb in frames:
+            f.write(np.ascontiguousarray(np.asarray(pose, dtype=np.float32).T).tobytes())  # column-major
+            f.write(np.ascontiguousarray(depth, dtype=np.uint16).tobytes())
+            f.write(np.ascontiguousarray(rgb, dtype=np.uint8).tobytes())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fused", [False, True])
+def test_main_loop_replay_matches_oracle(tmp_path, fused):
+    P = pkg()
+    w, h, n = 160, 120, 3
+    fx, fy = P.synth.focal(w, h)
+    frames = []
+    for k in range(n):
+        pose = P.synth.orbit_pose(20 * k)
+        depth, rgb = P.synth.make_frame(w, h, pose, seed=k)
+        frames.append((pose, depth, rgb))
+    fpath = str(tmp_path / "frames.bin")
+    _write_frames(fpath, w, h, frames, fx, fy)
+    out = str(tmp_path / "out")
+    log = subprocess.check_output([HOST_MAIN, fpath, out] + (["fused"] if fused else []), text=True, timeout=120)
+    assert "osl_main:" in log
+
+    raw = open(out + ".pool", "rb").read()
+    n_nodes, cx, cy, cz, half = struct.unpack("<iffff", raw[:20])
+    pool = np.frombuffer(raw[20:], dtype=np.uint32)
+    assert pool.size == 2 * n_nodes
+    img = np.frombuffer(open(out + ".rgba", "rb").read(), dtype=np.uint8).reshape(h, w, 4)
+
+    # the same loop on the oracle: Scene::addPointCloudToOctree creates Octree(0.01, bbox mid, bbox.bbox1.x)
+    # from the FIRST cloud (scene.cpp:100-102), max_depth from octree.cpp:283-284
+    ref = None
+    for pose, depth, rgb in frames:
+        xyz = orc.transform(orc.vertex_map(depth, fx, fy), pose)
+        if ref is None:
+            b = orc.bbox(xyz)
+            center = (b[3:] + b[:3]) / np.float32(2.0)
+            size = float(b[3])
+            D = int(math.ceil(math.log(float(np.float32(np.float32(size) / np.float32(0.01)))) /
+                              float(np.float32(math.log(2.0)))))
+            ref = orc.OracleSVO(tuple(center), size, D)
+        ref.integrate_points(xyz, rgb.reshape(-1, 3))
+    assert (np.float32(cx), np.float32(cy), np.float32(cz)) == tuple(np.float32(c) for c in ref.center)
+    assert np.float32(half) == np.float32(ref.half_edge)
+    assert n_nodes == ref.size
+    assert np.array_equal(pool, ref.pool())
+    assert np.array_equal(img, ref.raycast(w, h, 45.0, LOOK_PLUS_Z))
