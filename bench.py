@@ -184,21 +184,32 @@ def run_ours(args):
         sampler = ClockSampler(local) if rank == 0 else None
         l0 = lib.osl_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        bytes_alg = 0
+        b0 = svo.counters().total_algorithmic_bytes  # waits for the warm-up frames
+        barrier(world)
         with torch.cuda.stream(stream):
             e0.record(stream)
             for k in range(Wm, Wm + K):
-                fn(svo, k)
-                bytes_alg += svo.counters().algorithmic_bytes
+                fn(svo, k)  # asynchronous: the host only throttles when it is > 3 frames ahead
             e1.record(stream)
         barrier(world)
         ms = e0.elapsed_time(e1)
+        bytes_alg = svo.counters().total_algorithmic_bytes - b0
         clocks = sampler.stop() if sampler else None
         return max_over_ranks(ms, world), lib.osl_launch_count() - l0, bytes_alg, clocks
 
-    svo = pkg.SVO(center, half, DEPTH, reserve_nodes=1 << 24, device=local)
+    # resident inputs are complete before the timed region starts -> pipelined mode (osl_svo_set_pipeline)
+    svo = pkg.SVO(center, half, DEPTH, reserve_nodes=1 << 24, device=local).set_pipeline(True)
     ms, launches, bytes_alg, clocks = timed(integrate_resident, svo)
     nodes = svo.size
+    last = svo.counters()
+    # per-kernel CUDA-event times (non-pipelined frames on the same map), for the roofline of the dominant kernel
+    svo.set_pipeline(False).set_stage_timing(True)
+    stage = np.zeros(4)
+    for k in range(Wm + K, Wm + K + 20):
+        integrate_resident(svo, k)
+        stage += np.array(svo.stage_times())
+    stage /= 20.0
+    svo.set_stage_timing(False)
     # raycast of the fused map from the last camera pose (rays/s, device resident output)
     view = (np.diag([-1.0, 1.0, -1.0, 1.0]) @ np.linalg.inv(poses[(Wm + K - 1) % RING].astype(np.float64))).astype(np.float32)
     out = torch.empty((RAY_H, RAY_W, 4), dtype=torch.uint8, device="cuda")
@@ -241,8 +252,16 @@ def run_ours(args):
                     "algorithmic_gbs": (4 * st.rays + 4 * st.visits + 4 * st.steps) / (ray_ms / 1e3) / 1e9},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": peak_src,
-                     "kernel": "integrate pipeline (k_emit+k_sort+k_analyze+k_scan+k_assign+k_level), "
-                               "B_int = 5N+8U+68S+68*sum(P_l) per frame"},
+                     "kernel": "integrate pipeline per frame (k_emit+k_sort+k_structure+k_levels), "
+                               "B_int = 5N+8U+68S+68*sum(P_l) per frame",
+                     "bytes_per_frame": bytes_alg / float(K),
+                     "counters_last_frame": {"N": int(last.n_points), "V": int(last.n_valid), "U": int(last.n_unique),
+                                             "S": int(last.n_split),
+                                             "sum_P": int(sum(list(last.parents)[:DEPTH]))},
+                     "stage_us_unpipelined": {"k_emit": 1e3 * stage[0], "k_sort": 1e3 * stage[1],
+                                              "k_structure": 1e3 * stage[2], "k_levels": 1e3 * stage[3]},
+                     "note": "latency-bound: a frame's algorithmic bytes (~1.9 MB) take 0.3 us at HBM speed; see "
+                             "DESIGN.md section 3"},
         "clocks": clocks,
     }
     if rank == 0:

@@ -79,12 +79,24 @@ osl_status osl_svo_reset(osl_svo* t);
 /* 1 (default) reproduces reference quirk Q3 (svo.cu:123 `while (r_key >= 15)`); 0 = leaves are never split. */
 osl_status osl_svo_set_quirks(osl_svo* t, int ref_quirks);
 
+/* Pipelined mode for DEVICE-resident inputs (default 0).  With 1 the caller promises that the input buffers of every
+ * osl_integrate_* call are complete when the call is made (not merely stream-ordered before it); the library then runs
+ * back-projection + key sort of frame f+1 on an internal stream, overlapped with the tree update of frame f on the
+ * caller's stream.  Results are identical.  osl_integrate_depth_host always pipelines (it owns the copies). */
+osl_status osl_svo_set_pipeline(osl_svo* t, int enabled);
+
+/* Profiling aid: time k_emit / k_sort / k_structure / k_levels of every NON-pipelined integrate call with CUDA events
+ * on the caller's stream; osl_get_stage_times returns the 4 durations (ms) of the last timed frame (waits for it). */
+osl_status osl_svo_set_stage_timing(osl_svo* t, int enabled);
+osl_status osl_get_stage_times(osl_svo* t, float ms[4]);
+
 /* ---- integrate (svo.h:14-16) ------------------------------------------------------------------------------- */
 
 /* Fused main.cpp:39-44: generateVertexMap (image_kernels.cu:24-53) -> transformVertexMap (:206-215) ->
  * svoFromPointCloud (svo.cu:642-696).  d_depth: w*h uint16 millimetres, d_rgb: w*h*3 bytes (Color256).
  * Asynchronous on `stream` (4 kernel launches, no host synchronisation) except when the pool or the workspace has to
- * grow.  One stream per tree: consecutive calls on different streams are not ordered against each other. */
+ * grow, or when the caller runs more than 3 frames ahead of the device (it then waits for the oldest frame).
+ * One stream per tree: consecutive calls on different streams are not ordered against each other. */
 osl_status osl_integrate_depth(osl_svo* t, const uint16_t* d_depth, const uint8_t* d_rgb, int w, int h, float fx,
                                float fy, const float pose[16], void* stream);
 /* Same from host buffers (what OpenNIDevice::readFrame + mainLoop do, openni_device.cpp:122,144).  The H2D copies run

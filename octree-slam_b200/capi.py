@@ -18,7 +18,7 @@ STATUS = {0: "OSL_OK", -1: "OSL_ERR_INVALID", -2: "OSL_ERR_CUDA", -3: "OSL_ERR_O
           -4: "OSL_ERR_POOL_OVERFLOW", -5: "OSL_ERR_UNSUPPORTED"}
 
 EXPORTS = [
-    "osl_svo_create", "osl_svo_destroy", "osl_svo_reset", "osl_svo_set_quirks",
+    "osl_svo_create", "osl_svo_destroy", "osl_svo_reset", "osl_svo_set_quirks", "osl_svo_set_pipeline", "osl_svo_set_stage_timing", "osl_get_stage_times",
     "osl_integrate_depth", "osl_integrate_depth_host", "osl_integrate_points", "osl_integrate_voxels",
     "osl_svo_sync", "osl_svo_view", "osl_svo_size", "osl_svo_download", "osl_svo_upload", "osl_get_counters",
     "osl_raycast", "osl_raycast_host", "osl_raycast_pool", "osl_extract_voxels",
@@ -71,6 +71,9 @@ def lib():
         "osl_svo_destroy": (None, [vp]),
         "osl_svo_reset": (i32, [vp]),
         "osl_svo_set_quirks": (i32, [vp, i32]),
+        "osl_svo_set_pipeline": (i32, [vp, i32]),
+        "osl_svo_set_stage_timing": (i32, [vp, i32]),
+        "osl_get_stage_times": (i32, [vp, fp]),
         "osl_integrate_depth": (i32, [vp, vp, vp, i32, i32, f32, f32, fp, vp]),
         "osl_integrate_depth_host": (i32, [vp, vp, vp, i32, i32, f32, f32, fp, vp]),
         "osl_integrate_points": (i32, [vp, vp, vp, i32, vp]),

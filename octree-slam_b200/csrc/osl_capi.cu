@@ -61,8 +61,14 @@ osl_status osl_svo_create(osl_svo** out, const float center[3], float half_edge,
   t->structure_grid = (occ_str > 2 ? 2 : occ_str) * t->num_sms;
   t->levels_grid = (occ_lvl > 4 ? 4 : occ_lvl) * t->num_sms;
   osl_status rc = OSL_OK;
+  t->hint_emit = t->hint_level = -1;
   do {
-    if (cudaMalloc(&t->d_cta_hist, (size_t)t->sort_grid * 256 * sizeof(u32)) != cudaSuccess) { rc = OSL_ERR_OOM; break; }
+    bool okh = true;
+    for (int f = 0; f < OSL_FRONT && okh; f++)
+      okh = cudaMalloc(&t->d_cta_hist[f], (size_t)t->sort_grid * 256 * sizeof(u32)) == cudaSuccess;
+    if (!okh) { rc = OSL_ERR_OOM; break; }
+    rc = osl_integrate_init(t);
+    if (rc) break;
     if (cudaMalloc(&t->d_fs, sizeof(FrameState)) != cudaSuccess) { rc = OSL_ERR_OOM; break; }
     if (cudaMemset(t->d_fs, 0, sizeof(FrameState)) != cudaSuccess) { rc = OSL_ERR_CUDA; break; }
     if (cudaMalloc(&t->d_scan_totals, (OSL_NCOUNT(OSL_MAXD) + 8) * sizeof(u32)) != cudaSuccess) { rc = OSL_ERR_OOM; break; }
@@ -75,6 +81,9 @@ osl_status osl_svo_create(osl_svo** out, const float center[3], float half_edge,
     for (int i = 0; i < OSL_STAGES && ok; i++)
       ok = cudaEventCreateWithFlags(&t->stage_copied[i], cudaEventDisableTiming) == cudaSuccess &&
            cudaEventCreateWithFlags(&t->stage_free[i], cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < OSL_FRONT && ok; i++)
+      ok = cudaEventCreateWithFlags(&t->front_done[i], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&t->back_done[i], cudaEventDisableTiming) == cudaSuccess;
     if (ok) ok = cudaStreamCreateWithFlags(&t->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
     if (!ok) { rc = OSL_ERR_CUDA; break; }
     rc = osl_grow_pool(t, reserve_nodes ? reserve_nodes : ((size_t)1 << 20), 0);
@@ -91,9 +100,14 @@ void osl_svo_destroy(osl_svo* t) {
   cudaSetDevice(t->device);
   cudaDeviceSynchronize();
   cudaFree(t->d_pool);
-  cudaFree(t->d_keysA); cudaFree(t->d_keysB); cudaFree(t->d_payA); cudaFree(t->d_payB);
-  cudaFree(t->d_m); cudaFree(t->d_s); cudaFree(t->d_blockcnt); cudaFree(t->d_emit_status);
-  cudaFree(t->d_cta_hist); cudaFree(t->d_scan_totals); cudaFree(t->d_level_mem); cudaFree(t->d_fs);
+  for (int f = 0; f < OSL_FRONT; f++) {
+    cudaFree(t->d_keysA[f]); cudaFree(t->d_keysB[f]); cudaFree(t->d_payA[f]); cudaFree(t->d_payB[f]);
+    cudaFree(t->d_cta_hist[f]);
+    if (t->front_done[f]) cudaEventDestroy(t->front_done[f]);
+    if (t->back_done[f]) cudaEventDestroy(t->back_done[f]);
+  }
+  cudaFree(t->d_m); cudaFree(t->d_s); cudaFree(t->d_blockcnt);
+  cudaFree(t->d_scan_totals); cudaFree(t->d_level_mem); cudaFree(t->d_fs);
   for (int i = 0; i < OSL_STAGES; i++) {
     cudaFree(t->d_depth_stage[i]); cudaFree(t->d_rgb_stage[i]);
     if (t->stage_copied[i]) cudaEventDestroy(t->stage_copied[i]);
@@ -101,6 +115,8 @@ void osl_svo_destroy(osl_svo* t) {
   }
   for (int i = 0; i < OSL_RING; i++)
     if (t->ring_ev[i]) cudaEventDestroy(t->ring_ev[i]);
+  for (int i = 0; i < 5; i++)
+    if (t->stage_ev[i]) cudaEventDestroy(t->stage_ev[i]);
   if (t->copy_stream) cudaStreamDestroy(t->copy_stream);
   if (t->h_ring) cudaFreeHost(t->h_ring);
   delete t;
@@ -115,6 +131,32 @@ osl_status osl_svo_reset(osl_svo* t) {
   t->sticky_error = OSL_OK;
   memset(&t->counters, 0, sizeof(t->counters));
   return set_device_size(t, 0);
+}
+
+// Per-kernel timing of the integrate pipeline (k_emit, k_sort, k_structure, k_levels) with CUDA events on the
+// caller's stream; only non-pipelined frames are timed.  osl_get_stage_times waits for the last timed frame.
+osl_status osl_svo_set_stage_timing(osl_svo* t, int enabled) {
+  if (!t) return OSL_ERR_INVALID;
+  OSL_CUDA(cudaSetDevice(t->device));
+  if (enabled && !t->stage_ev[0])
+    for (int i = 0; i < 5; i++) OSL_CUDA(cudaEventCreate(&t->stage_ev[i]));
+  t->stage_timing = enabled ? 1 : 0;
+  t->stage_valid = 0;
+  return OSL_OK;
+}
+
+osl_status osl_get_stage_times(osl_svo* t, float ms[4]) {
+  if (!t || !ms || !t->stage_valid) return OSL_ERR_INVALID;
+  OSL_CUDA(cudaSetDevice(t->device));
+  OSL_CUDA(cudaEventSynchronize(t->stage_ev[4]));
+  for (int i = 0; i < 4; i++) OSL_CUDA(cudaEventElapsedTime(&ms[i], t->stage_ev[i], t->stage_ev[i + 1]));
+  return OSL_OK;
+}
+
+osl_status osl_svo_set_pipeline(osl_svo* t, int enabled) {
+  if (!t) return OSL_ERR_INVALID;
+  t->pipeline = enabled ? 1 : 0;
+  return OSL_OK;
 }
 
 osl_status osl_svo_set_quirks(osl_svo* t, int ref_quirks) {
@@ -132,7 +174,7 @@ osl_status osl_integrate_depth(osl_svo* t, const uint16_t* d_depth, const uint8_
   ep.depth = d_depth; ep.rgb = d_rgb; ep.w = w; ep.h = h; ep.fx = fx; ep.fy = fy;
   memcpy(ep.M, pose, sizeof(ep.M));
   ep.n = w * h; ep.mode = 0;
-  return osl_run_integrate(t, ep, nullptr, (cudaStream_t)stream);
+  return osl_run_integrate(t, ep, nullptr, (cudaStream_t)stream, false);
 }
 
 static osl_status ensure_stage(osl_svo* t, size_t n) {
@@ -169,9 +211,12 @@ osl_status osl_integrate_depth_host(osl_svo* t, const uint16_t* h_depth, const u
   if (t->stage_seq >= OSL_STAGES) OSL_CUDA(cudaStreamWaitEvent(t->copy_stream, t->stage_free[slot], 0));
   OSL_CUDA(cudaMemcpyAsync(t->d_depth_stage[slot], h_depth, n * 2, cudaMemcpyHostToDevice, t->copy_stream));
   OSL_CUDA(cudaMemcpyAsync(t->d_rgb_stage[slot], h_rgb, n * 3, cudaMemcpyHostToDevice, t->copy_stream));
-  OSL_CUDA(cudaEventRecord(t->stage_copied[slot], t->copy_stream));
-  OSL_CUDA(cudaStreamWaitEvent(st, t->stage_copied[slot], 0));
-  rc = osl_integrate_depth(t, t->d_depth_stage[slot], t->d_rgb_stage[slot], w, h, fx, fy, pose, stream);
+  EmitParams ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.depth = t->d_depth_stage[slot]; ep.rgb = t->d_rgb_stage[slot]; ep.w = w; ep.h = h; ep.fx = fx; ep.fy = fy;
+  memcpy(ep.M, pose, sizeof(ep.M));
+  ep.n = w * h; ep.mode = 0;
+  rc = osl_run_integrate(t, ep, nullptr, st, true);  // k_emit + k_sort follow the copies on the front stream
   if (rc) return rc;
   OSL_CUDA(cudaEventRecord(t->stage_free[slot], st));
   t->stage_seq++;
@@ -184,7 +229,7 @@ osl_status osl_integrate_points(osl_svo* t, const float* d_xyz, const uint8_t* d
   EmitParams ep;
   memset(&ep, 0, sizeof(ep));
   ep.pts = d_xyz; ep.stride = 3; ep.rgb = d_rgb; ep.n = n; ep.mode = 1;
-  return osl_run_integrate(t, ep, nullptr, (cudaStream_t)stream);
+  return osl_run_integrate(t, ep, nullptr, (cudaStream_t)stream, false);
 }
 
 osl_status osl_integrate_voxels(osl_svo* t, const float* d_centers4, const float* d_colors4, int n, void* stream) {
@@ -193,7 +238,7 @@ osl_status osl_integrate_voxels(osl_svo* t, const float* d_centers4, const float
   EmitParams ep;
   memset(&ep, 0, sizeof(ep));
   ep.pts = d_centers4; ep.stride = 4; ep.n = n; ep.mode = 2;
-  return osl_run_integrate(t, ep, d_colors4, (cudaStream_t)stream);
+  return osl_run_integrate(t, ep, d_colors4, (cudaStream_t)stream, false);
 }
 
 osl_status osl_svo_sync(osl_svo* t) {

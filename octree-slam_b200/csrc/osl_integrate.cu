@@ -23,44 +23,67 @@ namespace cg = cooperative_groups;
 #define FULL 0xFFFFFFFFu
 
 // ------------------------------------------------------------------------------------------------ k_emit
+// One CTA per 64x32-pixel tile (mode 0) or per 2048 consecutive inputs (modes 1, 2); 8 inputs per thread.
+// Back-projection + pose + Morton key in registers, then the tile's keys are DE-DUPLICATED in a shared-memory hash
+// table (64-bit CAS on the key, atomicMin on the input index): a 1 cm leaf is seen by ~20 neighbouring pixels of a
+// 640x480 frame, so ~2048 pixels collapse to ~150 (key, lowest pixel) entries before anything is sorted.  Tiles
+// append their entries to the key list with one atomicAdd; the order of the list is irrelevant because the sort is by
+// key and k_structure takes the MINIMUM payload of every run of equal keys (canonical Q7: lowest pixel wins).
+// Mode 2 (voxel grid, Q11: colour j goes to the j-th smallest key) must keep duplicates and only compacts.
 #define EMIT_THREADS 256
 #define EMIT_PPT 8
 #define EMIT_TILE (EMIT_THREADS * EMIT_PPT)
-
-__device__ __forceinline__ u32 ld_volatile_u32(const u32* p) { return *(const volatile u32*)p; }
-__device__ __forceinline__ void st_volatile_u32(u32* p, u32 v) { *(volatile u32*)p = v; }
+#define EMIT_TW 64
+#define EMIT_TH 32
+#define EMIT_SLOTS 4096
+#define EMIT_EMPTY 0xFFFFFFFFFFFFFFFFull
+#define EMIT_SMEM (EMIT_SLOTS * 8 + EMIT_SLOTS * 4 + EMIT_TILE * 2)
 
 __global__ void __launch_bounds__(EMIT_THREADS)
-k_emit(EmitParams p, TreeParams tp, int vec_ok, u64* __restrict__ keys, u32* __restrict__ pay, u32* status,
-       FrameState* fs) {
-  __shared__ u32 s_warp[EMIT_THREADS / 32];
-  __shared__ u32 s_base;
-  const int tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int first = tile * EMIT_TILE + tid * EMIT_PPT;
+k_emit(EmitParams p, TreeParams tp, int vec_ok, u64* __restrict__ keys, u32* __restrict__ pay, FrameState* fs,
+       int parity) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  u64* s_key = reinterpret_cast<u64*>(s_raw);
+  u32* s_pay = reinterpret_cast<u32*>(s_raw + EMIT_SLOTS * 8);
+  unsigned short* s_list = reinterpret_cast<unsigned short*>(s_raw + EMIT_SLOTS * 12);
+  __shared__ u32 s_count, s_valid, s_base;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const bool dedup = p.mode != 2;
+
+  if (dedup) {
+    uint4* k4 = reinterpret_cast<uint4*>(s_key);
+    for (int i = tid; i < EMIT_SLOTS / 2; i += EMIT_THREADS) k4[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
+    uint4* p4 = reinterpret_cast<uint4*>(s_pay);
+    for (int i = tid; i < EMIT_SLOTS / 4; i += EMIT_THREADS) p4[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
+  }
+  if (tid == 0) { s_count = 0; s_valid = 0; }
 
   u64 k[EMIT_PPT];
   u32 vmask = 0;
+  int first;  // input index of this thread's first element (its 8 elements are consecutive)
   if (p.mode == 0) {
+    const int tx = blockIdx.x % p.tiles_x, ty = blockIdx.x / p.tiles_x;
+    const int y = ty * EMIT_TH + (tid >> 3), x0 = tx * EMIT_TW + (tid & 7) * EMIT_PPT;
+    first = y * p.w + x0;
     int dv[EMIT_PPT];
-    if (vec_ok && first + EMIT_PPT <= p.n) {  // 128-bit load of 8 depth pixels
+    if (y < p.h && vec_ok && x0 + EMIT_PPT <= p.w) {  // 128-bit load of 8 depth pixels
       const uint4 q = __ldg(reinterpret_cast<const uint4*>(p.depth + first));
       dv[0] = q.x & 0xFFFF; dv[1] = q.x >> 16; dv[2] = q.y & 0xFFFF; dv[3] = q.y >> 16;
       dv[4] = q.z & 0xFFFF; dv[5] = q.z >> 16; dv[6] = q.w & 0xFFFF; dv[7] = q.w >> 16;
     } else {
 #pragma unroll
-      for (int i = 0; i < EMIT_PPT; i++) dv[i] = (first + i < p.n) ? (int)__ldg(p.depth + first + i) : 0;
+      for (int i = 0; i < EMIT_PPT; i++) dv[i] = (y < p.h && x0 + i < p.w) ? (int)__ldg(p.depth + first + i) : 0;
     }
-    int x = first % p.w, y = first / p.w;
 #pragma unroll
     for (int i = 0; i < EMIT_PPT; i++) {
       float X, Y, Z;
-      osl_vertex(dv[i], x, y, p.w, p.h, p.w, p.h, p.fx, p.fy, X, Y, Z);
+      osl_vertex(dv[i], x0 + i, y, p.w, p.h, p.w, p.h, p.fx, p.fy, X, Y, Z);
       osl_transform(p.M, X, Y, Z);
-      const bool ok = osl_key(X, Y, Z, tp, k[i]) && (first + i < p.n);
+      const bool ok = osl_key(X, Y, Z, tp, k[i]) && (y < p.h && x0 + i < p.w);
       vmask |= (u32)ok << i;
-      if (++x == p.w) { x = 0; y++; }
     }
   } else {
+    first = blockIdx.x * EMIT_TILE + tid * EMIT_PPT;
 #pragma unroll
     for (int i = 0; i < EMIT_PPT; i++) {
       const int idx = first + i;
@@ -73,70 +96,45 @@ k_emit(EmitParams p, TreeParams tp, int vec_ok, u64* __restrict__ keys, u32* __r
       vmask |= (u32)ok << i;
     }
   }
-
-  // block-wide exclusive scan of the per-thread valid counts
-  const u32 cnt = __popc(vmask);
-  u32 incl = cnt;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const u32 v = __shfl_up_sync(FULL, incl, o);
-    if (lane >= o) incl += v;
-  }
-  if (lane == 31) s_warp[warp] = incl;
-  __syncthreads();
-  u32 woff = 0, total = 0;
-#pragma unroll
-  for (int w = 0; w < EMIT_THREADS / 32; w++) {
-    const u32 v = s_warp[w];
-    if (w < warp) woff += v;
-    total += v;
-  }
-
-  // ordered compaction: decoupled look-back over the tiles' valid counts, one warp, 32 predecessors per step.
-  // status word = flag(2 bits: 1 aggregate, 2 inclusive prefix) | value(30 bits)
-  if (warp == 0) {
-    u32 excl = 0;
-    if (tile == 0) {
-      if (lane == 0) st_volatile_u32(&status[0], (2u << 30) | total);
-    } else {
-      if (lane == 0) st_volatile_u32(&status[tile], (1u << 30) | total);
-      int look = tile - 1;
-      for (;;) {
-        const int idx = look - lane;
-        u32 v = (idx >= 0) ? ld_volatile_u32(&status[idx]) : (2u << 30);
-        while (__any_sync(FULL, (v >> 30) == 0)) {
-          if ((v >> 30) == 0) v = ld_volatile_u32(&status[idx]);
-        }
-        const u32 inc_mask = __ballot_sync(FULL, (v >> 30) == 2);
-        const int stop = inc_mask ? (__ffs(inc_mask) - 1) : 31;
-        u32 c = (lane <= stop) ? (v & OSL_MASK) : 0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
-        excl += c;
-        if (inc_mask) break;
-        look -= 32;
-      }
-      if (lane == 0) st_volatile_u32(&status[tile], (2u << 30) | (excl + total));
-    }
-    if (lane == 0) {
-      s_base = excl;
-      if (tile == gridDim.x - 1) {
-        fs->n_in = p.n;
-        fs->n_valid = (int)(excl + total);
-        fs->n_invalid_front = p.n - (int)(excl + total);
-      }
-    }
-  }
   __syncthreads();
 
-  u32 pos = s_base + woff + (incl - cnt);
+  {  // valid inputs of the tile (statistics; mode 2: the number of invalid keys that sort to the front)
+    u32 c = __popc(vmask);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
+    if (lane == 0 && c) atomicAdd(&s_valid, c);
+  }
 #pragma unroll
   for (int i = 0; i < EMIT_PPT; i++) {
-    if ((vmask >> i) & 1u) {
-      keys[pos] = k[i];
-      pay[pos] = (u32)(first + i);
-      pos++;
+    if (!((vmask >> i) & 1u)) continue;
+    const u32 src = (u32)(first + i);
+    if (dedup) {
+      if (i > 0 && ((vmask >> (i - 1)) & 1u) && k[i] == k[i - 1]) continue;  // the earlier element already won
+      u32 slot = (u32)((k[i] * 0x9E3779B97F4A7C15ull) >> 52);
+      for (;;) {
+        const u64 prev = atomicCAS(reinterpret_cast<unsigned long long*>(&s_key[slot]), EMIT_EMPTY, k[i]);
+        if (prev == EMIT_EMPTY) s_list[atomicAdd(&s_count, 1u)] = (unsigned short)slot;
+        if (prev == EMIT_EMPTY || prev == k[i]) { atomicMin(&s_pay[slot], src); break; }
+        slot = (slot + 1) & (EMIT_SLOTS - 1);
+      }
+    } else {
+      const u32 pos = atomicAdd(&s_count, 1u);
+      s_key[pos] = k[i];
+      s_pay[pos] = src;
     }
+  }
+  __syncthreads();
+  const u32 cnt = s_count;
+  if (tid == 0) {
+    s_base = cnt ? atomicAdd(reinterpret_cast<u32*>(&fs->acc_emit[parity]), cnt) : 0u;
+    if (s_valid) atomicAdd(reinterpret_cast<u32*>(&fs->acc_valid[parity]), s_valid);
+  }
+  __syncthreads();
+  const u32 base = s_base;
+  for (u32 i = tid; i < cnt; i += EMIT_THREADS) {
+    const u32 slot = dedup ? (u32)s_list[i] : i;
+    keys[base + i] = s_key[slot];
+    pay[base + i] = s_pay[slot];
   }
 }
 
@@ -188,7 +186,7 @@ __device__ __forceinline__ void sort_rank(SortTile& t, u32* whist, int base, int
 }
 
 __global__ void __launch_bounds__(SORT_THREADS)
-k_sort(u64* kA, u32* pA, u64* kB, u32* pB, u32* cta_hist, const FrameState* fs, int passes) {
+k_sort(u64* kA, u32* pA, u64* kB, u32* pB, u32* cta_hist, const FrameState* fs, int passes, int parity) {
   cg::grid_group grid = cg::this_grid();
   __shared__ u32 s_hist[256];
   __shared__ u32 s_whist[SORT_WARPS][256];
@@ -197,7 +195,7 @@ k_sort(u64* kA, u32* pA, u64* kB, u32* pB, u32* cta_hist, const FrameState* fs, 
   __shared__ u32 s_wsum[SORT_WARPS];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int n = fs->n_valid;
+  const int n = fs->acc_emit[parity];
   const int tiles = (n + SORT_TILE - 1) / SORT_TILE;
   const int G = gridDim.x;
   const int per = (tiles + G - 1) / G;
@@ -367,9 +365,9 @@ __device__ __forceinline__ int walk_frontier(const u32* __restrict__ pool, u64 k
 //   phase B2 every CTA derives the allocation plan from the totals (bucket bases in the reference's order:
 //            pass = depth - s, then numeric key); CTA 0 publishes the FrameState; overflow => nothing is written
 //   phase C  dense per-level node lists with deterministic child-tile indices
-__device__ __forceinline__ void analyze_block(int vb, int n, const u64* __restrict__ keys, const u32* pool,
-                                              const TreeParams& tp, uint8_t* __restrict__ m8, uint8_t* __restrict__ s8,
-                                              u32* __restrict__ blockcnt, u32* s_cnt) {
+__device__ __forceinline__ void analyze_block(int vb, int n, const u64* __restrict__ keys, u32* pay, int mode,
+                                              const u32* pool, const TreeParams& tp, uint8_t* __restrict__ m8,
+                                              uint8_t* __restrict__ s8, u32* __restrict__ blockcnt, u32* s_cnt) {
   const int D = tp.D, NC = OSL_NCOUNT(D);
   for (int c = threadIdx.x; c < NC; c += AN_THREADS) s_cnt[c] = 0;
   __syncthreads();
@@ -383,6 +381,11 @@ __device__ __forceinline__ void analyze_block(int vb, int n, const u64* __restri
     }
     int s = OSL_NONE;
     if (m < D) {
+      if (mode != 2) {  // canonical Q7: the lowest input index of the run of equal keys wins (runs are short:
+        u32 pm = pay[j];  // one entry per 64x32-pixel tile that saw the leaf)
+        for (int jj = j + 1; jj < n && keys[jj] == k; jj++) pm = min(pm, pay[jj]);
+        pay[j] = pm;
+      }
       s = walk_frontier(pool, k, D, tp.quirks);
       atomicAdd(&s_cnt[OSL_CLVL(D, m + 1)], 1u);  // heads every level d > m
       if (s != OSL_NONE) {
@@ -411,7 +414,7 @@ __device__ __forceinline__ void analyze_block(int vb, int n, const u64* __restri
   __syncthreads();
 }
 
-__device__ __forceinline__ void assign_block(int vb, int n, const u64* __restrict__ keys, const u32* __restrict__ pay,
+__device__ __forceinline__ void assign_block(int vb, int n, const u64* __restrict__ keys, const u32* pay,
                                              const u32* pool, const TreeParams& tp, const uint8_t* __restrict__ m8,
                                              const uint8_t* __restrict__ s8, const u32* blockbase,
                                              const LevelArrays& lv, int mode, u32 size0, int n_invalid_front,
@@ -472,7 +475,7 @@ __device__ __forceinline__ void assign_block(int vb, int n, const u64* __restric
       const size_t o = lv.off[d] + idx;
       lv.ctile[o] = ct;
       lv.digit[o] = (uint8_t)key_digit(k, D, d);
-      if (d == D) lv.fc[o] = (mode == 2) ? (u32)(n_invalid_front + j) : pay[j];
+      if (d == D) lv.fc[o] = (mode == 2) ? (u32)(n_invalid_front + j) : __ldcg(&pay[j]);
       if (d > 1 && m < d - 1) lv.fc[lv.off[d - 1] + prev_idx] = idx;
       prev_idx = idx;
     }
@@ -481,22 +484,24 @@ __device__ __forceinline__ void assign_block(int vb, int n, const u64* __restric
 }
 
 __global__ void __launch_bounds__(AN_THREADS)
-k_structure(const u64* __restrict__ keys, const u32* __restrict__ pay, const u32* pool, TreeParams tp, FrameState* fs,
-            uint8_t* m8, uint8_t* s8, u32* blockcnt, u32* totals, LevelArrays lv, int mode, int capacity) {
+k_structure(const u64* __restrict__ keys, u32* pay, const u32* pool, TreeParams tp, FrameState* fs,
+            uint8_t* m8, uint8_t* s8, u32* blockcnt, u32* totals, LevelArrays lv, int mode, int capacity, int n_in,
+            int parity) {
   cg::grid_group grid = cg::this_grid();
   __shared__ u32 s_w[AN_WARPS][NC_MAX];
   __shared__ u32 s_plan[NC_MAX];
   __shared__ u32 s_scan[AN_WARPS];
   const int D = tp.D, NC = OSL_NCOUNT(D);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int n = fs->n_valid;
-  const int n_invalid_front = fs->n_invalid_front;
+  const int n = fs->acc_emit[parity];
+  const int n_valid = fs->acc_valid[parity];
+  const int n_invalid_front = n_in - n_valid;
   const int cur = fs->cur_size;
   const u32 size0 = (u32)(cur > 8 ? cur : 8);
   const int nvb = (n + AN_THREADS - 1) / AN_THREADS;
   const int G = gridDim.x;
 
-  for (int vb = blockIdx.x; vb < nvb; vb += G) analyze_block(vb, n, keys, pool, tp, m8, s8, blockcnt, &s_w[0][0]);
+  for (int vb = blockIdx.x; vb < nvb; vb += G) analyze_block(vb, n, keys, pay, mode, pool, tp, m8, s8, blockcnt, &s_w[0][0]);
   grid.sync();
 
   // phase B: column scans, one warp per counter, 4 independent loads per lane in flight
@@ -568,6 +573,8 @@ k_structure(const u64* __restrict__ keys, const u32* __restrict__ pay, const u32
     }
     if (tid >= 1 && tid <= D) fs->n_level[tid] = (int)__ldcg(&totals[OSL_CLVL(D, tid)]);
     if (tid == 0) {
+      fs->n_in = n_in; fs->n_valid = n_valid; fs->n_emit = n; fs->n_invalid_front = n_invalid_front;
+      fs->acc_valid[parity] = 0; fs->acc_emit[parity] = 0;  // every CTA has read them (two grid barriers ago)
       fs->n_level[0] = __ldcg(&totals[OSL_CLVL(D, 1)]) > 0 ? 1 : 0;
       fs->n_level[D + 1] = 0;
       fs->n_split = (int)n_split;
@@ -709,23 +716,26 @@ osl_status osl_ensure_workspace(osl_svo* t, size_t n) {
   size_t cap = t->ws_cap ? t->ws_cap : 1;
   while (cap < n) cap *= 2;
   if (cap < 4096) cap = 4096;
-  cudaFree(t->d_keysA); cudaFree(t->d_keysB); cudaFree(t->d_payA); cudaFree(t->d_payB);
-  cudaFree(t->d_m); cudaFree(t->d_s); cudaFree(t->d_blockcnt); cudaFree(t->d_emit_status);
+  for (int f = 0; f < OSL_FRONT; f++) {
+    cudaFree(t->d_keysA[f]); cudaFree(t->d_keysB[f]); cudaFree(t->d_payA[f]); cudaFree(t->d_payB[f]);
+    t->d_keysA[f] = t->d_keysB[f] = nullptr; t->d_payA[f] = t->d_payB[f] = nullptr;
+  }
+  cudaFree(t->d_m); cudaFree(t->d_s); cudaFree(t->d_blockcnt);
   cudaFree(t->d_level_mem);
-  t->d_keysA = t->d_keysB = nullptr; t->d_payA = t->d_payB = nullptr; t->d_m = t->d_s = nullptr;
-  t->d_blockcnt = t->d_emit_status = nullptr; t->d_level_mem = nullptr;
+  t->d_m = t->d_s = nullptr;
+  t->d_blockcnt = nullptr; t->d_level_mem = nullptr;
   t->ws_cap = 0;
   const int D = t->tp.D;
-  OSL_CUDA(cudaMalloc(&t->d_keysA, cap * sizeof(u64)));
-  OSL_CUDA(cudaMalloc(&t->d_keysB, cap * sizeof(u64)));
-  OSL_CUDA(cudaMalloc(&t->d_payA, cap * sizeof(u32)));
-  OSL_CUDA(cudaMalloc(&t->d_payB, cap * sizeof(u32)));
+  for (int f = 0; f < OSL_FRONT; f++) {
+    OSL_CUDA(cudaMalloc(&t->d_keysA[f], cap * sizeof(u64)));
+    OSL_CUDA(cudaMalloc(&t->d_keysB[f], cap * sizeof(u64)));
+    OSL_CUDA(cudaMalloc(&t->d_payA[f], cap * sizeof(u32)));
+    OSL_CUDA(cudaMalloc(&t->d_payB[f], cap * sizeof(u32)));
+  }
   OSL_CUDA(cudaMalloc(&t->d_m, cap));
   OSL_CUDA(cudaMalloc(&t->d_s, cap));
   const size_t nblocks = (cap + AN_THREADS - 1) / AN_THREADS;
   OSL_CUDA(cudaMalloc(&t->d_blockcnt, nblocks * OSL_NCOUNT(D) * sizeof(u32)));
-  const size_t etiles = (cap + EMIT_TILE - 1) / EMIT_TILE;
-  OSL_CUDA(cudaMalloc(&t->d_emit_status, etiles * sizeof(u32)));
   size_t total = 0;
   for (int d = 0; d <= D + 1; d++) {
     t->lv.off[d] = total;
@@ -740,6 +750,11 @@ osl_status osl_ensure_workspace(osl_svo* t, size_t n) {
   t->lv.val = t->lv.fc + total;
   t->lv.digit = reinterpret_cast<uint8_t*>(t->lv.val + total);
   t->ws_cap = cap;
+  return OSL_OK;
+}
+
+osl_status osl_integrate_init(osl_svo* t) {
+  OSL_CUDA(cudaFuncSetAttribute((const void*)k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, EMIT_SMEM));
   return OSL_OK;
 }
 
@@ -777,6 +792,8 @@ int osl_levels_occupancy() {
   return occ;
 }
 
+static inline int mode_of(const osl_svo* t, int slot) { return t->ring_mode[slot]; }
+
 // Consume the result blocks of frames that have completed (non-blocking unless `block`): exact node count, counters.
 osl_status osl_poll_results(osl_svo* t, bool block) {
   while (t->ring_tail != t->ring_head) {
@@ -794,6 +811,11 @@ osl_status osl_poll_results(osl_svo* t, bool block) {
     }
     const int D = t->tp.D;
     osl_counters& c = t->counters;
+    if (mode_of(t, slot) != 2 && F.n_in > 0) {
+      int widest = 0;
+      for (int d = 0; d < D; d++) widest = F.n_level[d] > widest ? F.n_level[d] : widest;  // k_levels: one thread per node of depth < D
+      t->hint_emit = F.n_emit; t->hint_level = widest; t->hint_n_in = F.n_in;
+    }
     c.n_points = F.n_in;
     c.n_valid = F.n_valid;
     c.n_unique = F.n_level[D];
@@ -814,7 +836,29 @@ osl_status osl_poll_results(osl_svo* t, bool block) {
   return OSL_OK;
 }
 
-osl_status osl_run_integrate(osl_svo* t, const EmitParams& ep, const void* colors, cudaStream_t st) {
+// Wait for the OLDEST frame in flight only (throttling), fold its result block.
+static osl_status wait_oldest(osl_svo* t) {
+  if (t->ring_tail == t->ring_head) return OSL_OK;
+  const int slot = (int)(t->ring_tail % OSL_RING);
+  cudaError_t e = cudaEventSynchronize(t->ring_ev[slot]);
+  if (e != cudaSuccess) { g_osl_last_cuda_error = (int)e; return OSL_ERR_CUDA; }
+  return osl_poll_results(t, false);
+}
+
+static int grid_for(long long items, int per_cta, int cap) {
+  long long g = (items + per_cta - 1) / per_cta;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// One frame: k_emit -> k_sort -> k_structure -> k_levels (+ the 1.6 KB result block into the pinned ring).
+// `inputs_on_front`: the inputs were produced on the front stream (host frames staged by osl_integrate_depth_host).
+// Pipelined (t->pipeline or inputs_on_front): k_emit + k_sort of frame f run on the front stream and overlap
+// k_structure + k_levels of frame f-1 on `st`; two key-list buffers alternate.  Otherwise everything is enqueued on
+// `st` in order.  Cooperative grids are capped at num_sms/2 CTAs so that a front and a back cooperative kernel are
+// always co-resident (<= num_sms CTAs in total: a waiting CTA always finds an empty SM), hence no barrier deadlock.
+osl_status osl_run_integrate(osl_svo* t, EmitParams& ep, const void* colors, cudaStream_t st, bool inputs_on_front) {
   const int n = ep.n;
   const int D = t->tp.D;
   if (n < 0) return OSL_ERR_INVALID;
@@ -824,78 +868,115 @@ osl_status osl_run_integrate(osl_svo* t, const EmitParams& ep, const void* color
     rc = osl_poll_results(t, true);  // the workspace is in use by frames in flight
     if (rc) return rc;
     OSL_CUDA(cudaStreamSynchronize(st));
+    OSL_CUDA(cudaStreamSynchronize(t->copy_stream));
     rc = osl_ensure_workspace(t, (size_t)(n > 0 ? n : 1));
     if (rc) return rc;
   }
   rc = osl_poll_results(t, false);
   if (rc) return rc;
   if (t->ring_head - t->ring_tail >= OSL_RING) {  // result ring full: wait for the oldest frame
-    rc = osl_poll_results(t, true);
+    rc = wait_oldest(t);
     if (rc) return rc;
   }
-  // Pool head-room.  A frame of n inputs can split at most n*D nodes (8*n*D new nodes); frames in flight are
-  // accounted with the same bound until their exact result has been read back.
+  // Pool head-room.  A frame of n inputs splits at most n*D nodes (8*n*D new nodes); a frame in flight is accounted
+  // with that bound until its exact result has been read back.  The pool is grown to hold OSL_PIPE_DEPTH such
+  // frames beyond the known size, so in steady state the host never waits here; when it runs further ahead it waits
+  // for the oldest frame only.  (The device re-checks exactly: a frame that would overflow writes nothing.)
   const size_t headroom = 8ull * (size_t)(n > 0 ? n : 0) * (size_t)D;
-  size_t base = (size_t)(t->size > 8 ? t->size : 8);
-  if (base + t->inflight_headroom + headroom > t->cap_nodes) {
-    rc = osl_poll_results(t, true);  // get the exact size
+  const size_t limit = (size_t)1 << 30;
+  for (;;) {
+    const size_t base = (size_t)(t->size > 8 ? t->size : 8);
+    if (base + t->inflight_headroom + headroom <= t->cap_nodes) break;
+    size_t want = base + (size_t)(OSL_PIPE_DEPTH + 1) * headroom;
+    if (want > limit) want = limit;
+    if (want > t->cap_nodes) {  // grow (rare, geometric): needs the exact size, i.e. an idle pipeline
+      rc = osl_poll_results(t, true);
+      if (rc) return rc;
+      OSL_CUDA(cudaStreamSynchronize(st));
+      rc = osl_grow_pool(t, want, st);
+      if (rc) return rc;
+      continue;
+    }
+    if (t->ring_tail == t->ring_head) break;  // at the 2^30-node cap: the device-side check protects the pool
+    rc = wait_oldest(t);
     if (rc) return rc;
-    base = (size_t)(t->size > 8 ? t->size : 8);
-    if (base + headroom > t->cap_nodes) {
-      size_t want = base + 2 * headroom;
-      if (want > ((size_t)1 << 30)) want = (size_t)1 << 30;
-      if (want > t->cap_nodes) {
-        rc = osl_grow_pool(t, want, st);
-        if (rc) return rc;
-      }
-      // at the 2^30-node cap the device-side overflow check still protects the pool; the frame is then dropped
-      // and OSL_ERR_POOL_OVERFLOW is reported by the next call
+  }
+
+  const int par = (int)(t->seq % OSL_FRONT);
+  const bool piped = (t->pipeline || inputs_on_front) && n > 0;
+  cudaStream_t fst = piped ? t->copy_stream : st;
+  if (piped && !t->front_active) {
+    // first pipelined frame: earlier frames used uncapped cooperative grids, keep them out of the overlap window
+    if (t->seq >= 1) OSL_CUDA(cudaStreamWaitEvent(fst, t->back_done[par ^ 1], 0));
+    t->front_active = 1;
+  }
+  const int coop_cap = t->front_active ? (t->num_sms / 2 > 0 ? t->num_sms / 2 : 1) : 0x7FFFFFFF;
+  const int passes = (3 * D + 7) / 8;
+  u64* skeys = (passes & 1) ? t->d_keysB[par] : t->d_keysA[par];
+  u32* spay = (passes & 1) ? t->d_payB[par] : t->d_payA[par];
+  // expected number of sorted entries / widest level, from the last completed frame (grid sizing only: every
+  // kernel is grid-stride, a wrong guess costs time, not correctness)
+  long long exp_emit = n, exp_level = n;
+  if (t->hint_emit >= 0 && t->hint_n_in > 0 && ep.mode != 2) {
+    const double scale = 1.5 * (double)n / (double)t->hint_n_in;
+    exp_emit = (long long)(t->hint_emit * scale) + SORT_TILE;
+    exp_level = (long long)(t->hint_level * scale) + LEVEL_THREADS;
+    if (exp_emit > n) exp_emit = n;
+    if (exp_level > n) exp_level = n;
+  }
+
+  const bool timing = t->stage_timing && !piped && n > 0;
+  if (timing) OSL_CUDA(cudaEventRecord(t->stage_ev[0], st));
+  if (n > 0) {
+    if (piped) {
+      // the front buffer `par` was last read by k_structure/k_levels of frame seq-2
+      if (t->seq >= OSL_FRONT) OSL_CUDA(cudaStreamWaitEvent(fst, t->back_done[par], 0));
+    }
+    int vec_ok = 0;
+    int etiles;
+    if (ep.mode == 0) {
+      vec_ok = ((reinterpret_cast<uintptr_t>(ep.depth) & 15) == 0) && (ep.w % 8 == 0);
+      ep.tiles_x = (ep.w + EMIT_TW - 1) / EMIT_TW;
+      ep.tiles_y = (ep.h + EMIT_TH - 1) / EMIT_TH;
+      etiles = ep.tiles_x * ep.tiles_y;
+    } else {
+      etiles = (n + EMIT_TILE - 1) / EMIT_TILE;
+    }
+    k_emit<<<etiles, EMIT_THREADS, EMIT_SMEM, fst>>>(ep, t->tp, vec_ok, t->d_keysA[par], t->d_payA[par], t->d_fs, par);
+    OSL_LAUNCHED(1);
+    if (timing) OSL_CUDA(cudaEventRecord(t->stage_ev[1], st));
+    const int grid = grid_for(exp_emit, SORT_TILE, t->sort_grid < coop_cap ? t->sort_grid : coop_cap);
+    u64* kA = t->d_keysA[par]; u32* pA = t->d_payA[par]; u64* kB = t->d_keysB[par]; u32* pB = t->d_payB[par];
+    u32* ch = t->d_cta_hist[par]; const FrameState* fsc = t->d_fs; int pp = passes; int parity = par;
+    void* args[] = {&kA, &pA, &kB, &pB, &ch, &fsc, &pp, &parity};
+    OSL_CUDA(cudaLaunchCooperativeKernel((void*)k_sort, dim3(grid), dim3(SORT_THREADS), args, 0, fst));
+    OSL_LAUNCHED(1);
+    if (timing) OSL_CUDA(cudaEventRecord(t->stage_ev[2], st));
+    if (piped) {
+      OSL_CUDA(cudaEventRecord(t->front_done[par], fst));
+      OSL_CUDA(cudaStreamWaitEvent(st, t->front_done[par], 0));
     }
   }
-
-  const int etiles = (n + EMIT_TILE - 1) / EMIT_TILE;
-  const int passes = (3 * D + 7) / 8;
-  u64* skeys = (passes & 1) ? t->d_keysB : t->d_keysA;
-  u32* spay = (passes & 1) ? t->d_payB : t->d_payA;
-
-  if (n > 0) {
-    OSL_CUDA(cudaMemsetAsync(t->d_emit_status, 0, (size_t)etiles * sizeof(u32), st));
-    int vec_ok = 0;
-    if (ep.mode == 0) vec_ok = ((reinterpret_cast<uintptr_t>(ep.depth) & 15) == 0);
-    k_emit<<<etiles, EMIT_THREADS, 0, st>>>(ep, t->tp, vec_ok, t->d_keysA, t->d_payA, t->d_emit_status, t->d_fs);
-    OSL_LAUNCHED(1);
-    int grid = (n + SORT_TILE - 1) / SORT_TILE;
-    if (grid > t->sort_grid) grid = t->sort_grid;
-    if (grid < 1) grid = 1;
-    u64* kA = t->d_keysA; u32* pA = t->d_payA; u64* kB = t->d_keysB; u32* pB = t->d_payB;
-    u32* ch = t->d_cta_hist; const FrameState* fsc = t->d_fs; int pp = passes;
-    void* args[] = {&kA, &pA, &kB, &pB, &ch, &fsc, &pp};
-    OSL_CUDA(cudaLaunchCooperativeKernel((void*)k_sort, dim3(grid), dim3(SORT_THREADS), args, 0, st));
-    OSL_LAUNCHED(1);
-  } else {
-    OSL_CUDA(cudaMemsetAsync(t->d_fs, 0, 3 * sizeof(int), st));  // n_in = n_valid = n_invalid_front = 0
-  }
   {
-    int grid = (n + AN_THREADS - 1) / AN_THREADS;
-    if (grid > t->structure_grid) grid = t->structure_grid;
-    if (grid < 1) grid = 1;
-    const u64* a0 = skeys; const u32* a1 = spay; const u32* a2 = t->d_pool; TreeParams a3 = t->tp; FrameState* a4 = t->d_fs;
+    const int grid = grid_for(exp_emit, AN_THREADS, t->structure_grid < coop_cap ? t->structure_grid : coop_cap);
+    const u64* a0 = skeys; u32* a1 = spay; const u32* a2 = t->d_pool; TreeParams a3 = t->tp; FrameState* a4 = t->d_fs;
     uint8_t* a5 = t->d_m; uint8_t* a6 = t->d_s; u32* a7 = t->d_blockcnt; u32* a8 = t->d_scan_totals;
-    LevelArrays a9 = t->lv; int a10 = ep.mode; int a11 = (int)t->cap_nodes;
-    void* args[] = {&a0, &a1, &a2, &a3, &a4, &a5, &a6, &a7, &a8, &a9, &a10, &a11};
+    LevelArrays a9 = t->lv; int a10 = ep.mode; int a11 = (int)t->cap_nodes; int a12 = n; int a13 = par;
+    void* args[] = {&a0, &a1, &a2, &a3, &a4, &a5, &a6, &a7, &a8, &a9, &a10, &a11, &a12, &a13};
     OSL_CUDA(cudaLaunchCooperativeKernel((void*)k_structure, dim3(grid), dim3(AN_THREADS), args, 0, st));
     OSL_LAUNCHED(1);
+    if (timing) OSL_CUDA(cudaEventRecord(t->stage_ev[3], st));
   }
   if (n > 0) {
-    int grid = (n / 4 + LEVEL_THREADS - 1) / LEVEL_THREADS;  // level D-1 rarely exceeds n/4 nodes; grid-stride anyway
-    if (grid > t->levels_grid) grid = t->levels_grid;
-    if (grid < 1) grid = 1;
+    const int grid = grid_for(exp_level, LEVEL_THREADS, t->levels_grid < coop_cap ? t->levels_grid : coop_cap);
     u32* a0 = t->d_pool; LevelArrays a1 = t->lv; const FrameState* a2 = t->d_fs; int a3 = D; int a4 = ep.mode;
     const uint8_t* a5 = ep.rgb; const float* a6 = (const float*)colors;
     void* args[] = {&a0, &a1, &a2, &a3, &a4, &a5, &a6};
     OSL_CUDA(cudaLaunchCooperativeKernel((void*)k_levels, dim3(grid), dim3(LEVEL_THREADS), args, 0, st));
     OSL_LAUNCHED(1);
   }
+  if (timing) { OSL_CUDA(cudaEventRecord(t->stage_ev[4], st)); t->stage_valid = 1; }
+  OSL_CUDA(cudaEventRecord(t->back_done[par], st));
   // result block -> pinned ring (read lazily; the caller never waits for it unless it asks for sizes/counters)
   const int slot = (int)(t->ring_head % OSL_RING);
   OSL_CUDA(cudaMemcpyAsync(&t->h_ring[slot], t->d_fs, sizeof(FrameState), cudaMemcpyDeviceToHost, st));
@@ -904,6 +985,7 @@ osl_status osl_run_integrate(osl_svo* t, const EmitParams& ep, const void* color
   t->ring_mode[slot] = ep.mode;
   t->inflight_headroom += headroom;
   t->ring_head++;
+  t->seq++;
   t->last_stream = st;
   return OSL_OK;
 }

@@ -17,14 +17,19 @@ typedef unsigned int u32;
 #define OSL_MAXD OSL_MAX_DEPTH
 #define OSL_RING 8    // per-frame result blocks in flight
 #define OSL_STAGES 3  // device staging slots of the *_host entry points
+#define OSL_PIPE_DEPTH 3  // frames in flight the pool head-room is sized for
+#define OSL_FRONT 2   // key-list buffers: emit+sort of frame f+1 overlap structure+levels of frame f
 #define OSL_NCOUNT(D) ((D) + ((D) + 1) * ((D) + 1))
 #define OSL_CLVL(D, d) ((d)-1)
 #define OSL_CBKT(D, s, d) ((D) + (s) * ((D) + 1) + (d))
 
 // Per-frame device-side state; copied to pinned host memory after the structure phase.
 struct FrameState {
+  int acc_valid[2];  // [frame parity] accumulated by k_emit (atomicAdd), consumed and zeroed by k_structure
+  int acc_emit[2];   // [frame parity] entries k_emit appended to the key list
   int n_in;         // inputs
   int n_valid;      // V  (inputs with a valid key)
+  int n_emit;       // entries sorted (modes 0/1: after the tile-local de-duplication; mode 2: == n_valid)
   int n_invalid_front;  // voxel path: invalid keys sort to the front in the reference (key 1)
   int n_split;      // S
   int size_before;  // nodes before this frame (>= 8)
@@ -147,12 +152,11 @@ struct osl_svo {
   int size;           // nodes (host copy, valid after sync)
   // workspace (sized for ws_cap inputs)
   size_t ws_cap;
-  u64 *d_keysA, *d_keysB;
-  u32 *d_payA, *d_payB;
+  u64 *d_keysA[OSL_FRONT], *d_keysB[OSL_FRONT];  // sort ping/pong per front buffer
+  u32 *d_payA[OSL_FRONT], *d_payB[OSL_FRONT];
   uint8_t *d_m, *d_s;
   u32* d_blockcnt;    // [blocks][NC]
-  u32* d_emit_status; // ordered-compaction look-back words
-  u32* d_cta_hist;    // sort: [grid][256]
+  u32* d_cta_hist[OSL_FRONT];  // sort: [grid][256]
   u32* d_scan_totals; // k_scan: [NC_MAX] totals + 1 ticket word
   LevelArrays lv;
   void* d_level_mem;
@@ -165,7 +169,15 @@ struct osl_svo {
   size_t inflight_headroom;              // worst-case node growth of frames not yet read back
   osl_status sticky_error;
   cudaStream_t last_stream;
-  cudaStream_t copy_stream;              // *_host entry points: H2D overlaps the previous frame's kernels
+  cudaStream_t copy_stream;              // front stream: H2D of host frames, and (pipelined mode) k_emit + k_sort
+  int stage_timing, stage_valid;         // per-kernel CUDA-event timing of non-pipelined frames (bench / profiling)
+  cudaEvent_t stage_ev[5];
+  int front_active;                      // the front stream has been used: cooperative grids stay <= num_sms/2
+  int pipeline;                          // 1: emit+sort run on the front stream (inputs are ready at call time)
+  cudaEvent_t front_done[OSL_FRONT], back_done[OSL_FRONT];
+  unsigned long long seq;                // frames enqueued (front buffer = seq % OSL_FRONT)
+  int hint_emit, hint_level;             // last known n_emit / widest level (grid sizing); -1 = unknown
+  int hint_n_in;
   cudaEvent_t stage_copied[OSL_STAGES], stage_free[OSL_STAGES];
   uint16_t* d_depth_stage[OSL_STAGES]; uint8_t* d_rgb_stage[OSL_STAGES]; size_t stage_cap; unsigned long long stage_seq;
   int structure_grid, levels_grid;
@@ -189,10 +201,12 @@ extern long long g_osl_launches;
 // integrate pipeline (osl_integrate.cu)
 struct EmitParams {
   const uint16_t* depth; const uint8_t* rgb; int w, h; float fx, fy; float M[16];  // mode 0
+  int tiles_x, tiles_y;                                                             // mode 0: 64x32-pixel tiles
   const float* pts; int stride;                                                      // mode 1 (vec3) / 2 (vec4)
   int n; int mode;
 };
-osl_status osl_run_integrate(osl_svo* t, const EmitParams& ep, const void* colors, cudaStream_t st);
+osl_status osl_run_integrate(osl_svo* t, EmitParams& ep, const void* colors, cudaStream_t st, bool inputs_on_front);
+osl_status osl_integrate_init(osl_svo* t);
 osl_status osl_ensure_workspace(osl_svo* t, size_t n);
 int osl_sort_occupancy();  // co-resident k_sort CTAs per SM
 int osl_structure_occupancy();

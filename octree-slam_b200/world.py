@@ -46,6 +46,21 @@ class SVO:
         if not quirks:
             _check(lib().osl_svo_set_quirks(self._h, 0), "osl_svo_set_quirks")
 
+    def set_pipeline(self, enabled=True):
+        """inputs of later integrate calls are complete at call time -> frame f+1's sort overlaps frame f's tree update"""
+        _check(lib().osl_svo_set_pipeline(self._h, int(bool(enabled))), "osl_svo_set_pipeline")
+        return self
+
+    def set_stage_timing(self, enabled=True):
+        _check(lib().osl_svo_set_stage_timing(self._h, int(bool(enabled))), "osl_svo_set_stage_timing")
+        return self
+
+    def stage_times(self):
+        """ms of (k_emit, k_sort, k_structure, k_levels) of the last timed (non-pipelined) frame"""
+        ms = (C.c_float * 4)()
+        _check(lib().osl_get_stage_times(self._h, ms), "osl_get_stage_times")
+        return [float(x) for x in ms]
+
     def close(self):
         if getattr(self, "_h", None):
             lib().osl_svo_destroy(self._h)

@@ -108,6 +108,77 @@ def test_integrate_depth_matches_oracle(P, D, w, h, frames):
     assert c.n_unique <= c.n_valid <= c.n_points == w * h
 
 
+@pytest.mark.parametrize("w,h", [(333, 77), (70, 33), (8, 8), (64, 32), (65, 31), (1, 1), (640, 480)])
+def test_integrate_depth_ragged_image_sizes(P, w, h):
+    """tile edges of the 64x32-pixel emit tiles, widths that defeat the 128-bit depth loads"""
+    _run_frames(P, 9, w, h, 2)
+
+
+def test_pipelined_mode_matches_oracle(P):
+    """emit + sort of frame f+1 on the front stream, overlapped with the tree update of frame f"""
+    import torch
+    D, w, h, frames = 12, 320, 240, 12
+    center, half = P.synth.tree_params(D)
+    fx, fy = P.synth.focal(w, h)
+    svo = P.SVO(center, half, D).set_pipeline(True)
+    ref = orc.OracleSVO(center, half, D)
+    keep = []
+    for k in range(frames):
+        pose = P.synth.orbit_pose(7 * k)
+        depth, rgb = P.synth.make_frame(w, h, pose, seed=k)
+        d, c = torch.from_numpy(depth).cuda(), torch.from_numpy(rgb).cuda()
+        keep.append((d, c))
+        ref.integrate_depth(depth, rgb, fx, fy, pose)
+    torch.cuda.synchronize()  # the promise of pipelined mode: inputs are complete when the call is made
+    for k in range(frames):
+        svo.integrate_depth(keep[k][0], keep[k][1], fx, fy, P.synth.orbit_pose(7 * k))
+    assert svo.size == ref.size
+    assert np.array_equal(svo.pool(), ref.pool())
+
+
+def test_host_frames_pipeline_matches_oracle(P):
+    D, w, h, frames = 10, 320, 240, 9
+    center, half = P.synth.tree_params(D)
+    fx, fy = P.synth.focal(w, h)
+    svo = P.SVO(center, half, D)
+    ref = orc.OracleSVO(center, half, D)
+    keep = []
+    for k in range(frames):
+        pose = P.synth.orbit_pose(11 * k)
+        depth, rgb = P.synth.make_frame(w, h, pose, seed=k)
+        keep.append((depth, rgb))  # host buffers must stay untouched until the frame completes
+        svo.integrate_depth_host(depth, rgb, fx, fy, pose)
+        ref.integrate_depth(depth, rgb, fx, fy, pose)
+    assert svo.size == ref.size
+    assert np.array_equal(svo.pool(), ref.pool())
+
+
+def test_stage_times_are_reported(P):
+    D, w, h = 8, 160, 120
+    center, half = P.synth.tree_params(D)
+    fx, fy = P.synth.focal(w, h)
+    depth, rgb = P.synth.make_frame(w, h, None, seed=3)
+    svo = P.SVO(center, half, D).set_stage_timing(True)
+    svo.integrate_depth(depth, rgb, fx, fy)
+    ms = svo.stage_times()
+    assert len(ms) == 4 and all(0.0 < x < 100.0 for x in ms)
+
+
+def test_duplicate_points_lowest_index_wins_across_tiles(P):
+    """the same leaf hit from different emit tiles (inputs 2048 apart): canonical Q7 = lowest input index"""
+    rng = np.random.default_rng(4)
+    n = 3 * 2048 + 17
+    base = rng.uniform(-0.9, 0.9, size=(37, 3)).astype(np.float32)
+    pts = base[rng.integers(0, 37, size=n)]
+    rgb = rng.integers(0, 256, size=(n, 3)).astype(np.uint8)
+    svo = P.SVO((0, 0, 0), 1.0, 6)
+    ref = orc.OracleSVO((0, 0, 0), 1.0, 6)
+    svo.integrate_points(pts, rgb)
+    ref.integrate_points(pts, rgb)
+    assert np.array_equal(svo.pool(), ref.pool())
+    assert svo.counters().n_unique == ref.counters().n_unique <= 37
+
+
 def test_integrate_same_frame_repeatedly_q3_and_alpha(P):
     svo, ref = _run_frames(P, 8, 160, 120, 5, same_frame=True)
     w1 = svo.pool()[1::2]
