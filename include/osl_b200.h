@@ -76,7 +76,8 @@ osl_status osl_svo_create(osl_svo** out, const float center[3], float half_edge,
 void osl_svo_destroy(osl_svo* t);
 /* Drop all nodes (octree_size = 0), keep the allocations. */
 osl_status osl_svo_reset(osl_svo* t);
-/* 1 (default) reproduces reference quirk Q3 (svo.cu:123 `while (r_key >= 15)`); 0 = leaves are never split. */
+/* bit 0: 1 (default) reproduces reference quirk Q3 (svo.cu:123 `while (r_key >= 15)`); 0 = leaves are never split.
+ * bit 1 (testing aid): always sort with the cooperative grid radix sort, never with the splitter-based bucket sort. */
 osl_status osl_svo_set_quirks(osl_svo* t, int ref_quirks);
 
 /* Pipelined mode for DEVICE-resident inputs (default 0).  With 1 the caller promises that the input buffers of every

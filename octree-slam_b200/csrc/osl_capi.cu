@@ -55,6 +55,7 @@ osl_status osl_svo_create(osl_svo** out, const float center[3], float half_edge,
   t->tp.D = max_depth;
   t->tp.quirks = 1;
   t->num_sms = prop.multiProcessorCount;
+  if (osl_integrate_init(t) != OSL_OK) { delete t; return OSL_ERR_CUDA; }  // dynamic shared-memory opt-ins first
   const int occ_sort = osl_sort_occupancy(), occ_str = osl_structure_occupancy(), occ_lvl = osl_levels_occupancy();
   if (occ_sort < 1 || occ_str < 1 || occ_lvl < 1) { delete t; return OSL_ERR_CUDA; }
   t->sort_grid = (occ_sort > 4 ? 4 : occ_sort) * t->num_sms;
@@ -67,8 +68,6 @@ osl_status osl_svo_create(osl_svo** out, const float center[3], float half_edge,
     for (int f = 0; f < OSL_FRONT && okh; f++)
       okh = cudaMalloc(&t->d_cta_hist[f], (size_t)t->sort_grid * 256 * sizeof(u32)) == cudaSuccess;
     if (!okh) { rc = OSL_ERR_OOM; break; }
-    rc = osl_integrate_init(t);
-    if (rc) break;
     if (cudaMalloc(&t->d_fs, sizeof(FrameState)) != cudaSuccess) { rc = OSL_ERR_OOM; break; }
     if (cudaMemset(t->d_fs, 0, sizeof(FrameState)) != cudaSuccess) { rc = OSL_ERR_CUDA; break; }
     if (cudaMalloc(&t->d_scan_totals, (OSL_NCOUNT(OSL_MAXD) + 8) * sizeof(u32)) != cudaSuccess) { rc = OSL_ERR_OOM; break; }
@@ -107,6 +106,7 @@ void osl_svo_destroy(osl_svo* t) {
     if (t->back_done[f]) cudaEventDestroy(t->back_done[f]);
   }
   cudaFree(t->d_m); cudaFree(t->d_s); cudaFree(t->d_blockcnt);
+  cudaFree(t->d_keysC); cudaFree(t->d_payC); cudaFree(t->d_split);
   cudaFree(t->d_scan_totals); cudaFree(t->d_level_mem); cudaFree(t->d_fs);
   for (int i = 0; i < OSL_STAGES; i++) {
     cudaFree(t->d_depth_stage[i]); cudaFree(t->d_rgb_stage[i]);
@@ -161,7 +161,8 @@ osl_status osl_svo_set_pipeline(osl_svo* t, int enabled) {
 
 osl_status osl_svo_set_quirks(osl_svo* t, int ref_quirks) {
   if (!t) return OSL_ERR_INVALID;
-  t->tp.quirks = ref_quirks ? 1 : 0;
+  t->tp.quirks = (ref_quirks & 1) ? 1 : 0;
+  t->force_grid_sort = (ref_quirks & 2) ? 1 : 0;  // bit 1 (testing): never use the bucket sort
   return OSL_OK;
 }
 

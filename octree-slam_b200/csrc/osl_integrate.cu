@@ -332,6 +332,234 @@ k_sort(u64* kA, u32* pA, u64* kB, u32* pB, u32* cta_hist, const FrameState* fs, 
   }
 }
 
+// ------------------------------------------------------------------------------------------------ k_sort_bucket
+// The per-frame sort when the key list is small (after de-duplication a 640x480 frame is ~20-30 k entries): no grid
+// barrier at all.  The key space is cut into BK_BUCKETS contiguous ranges by splitters taken from the sorted keys of
+// an earlier frame (k_structure writes them; consecutive frames see almost the same surface, so the ranges stay
+// balanced).  CTA b scans the whole list (L2-resident), keeps the entries of its range in shared memory, counts the
+// entries of lower ranges (= its output offset), sorts its <= 2048 entries with a shared-memory LSD radix sort that
+// skips the digits on which all its keys agree (a contiguous key range shares its high digits), and writes them out.
+// A bucket that does not fit (scene cut, first frames) is sorted by the same CTA through global memory: slow but
+// correct, and the next frame gets fresh splitters.
+#define BK_BUCKETS 64
+#define BK_THREADS SORT_THREADS
+#define BK_CAP SORT_TILE
+#define BK_SMEM (2 * BK_CAP * 8 + 2 * BK_CAP * 4)
+
+struct BucketShared {
+  u32 whist[SORT_WARPS][256];
+  u32 run[256];
+  u32 base[256];
+  u32 wsum[SORT_WARPS];
+  u32 cnt, below, or_lo, or_hi, and_lo, and_hi;
+};
+
+__device__ __forceinline__ void sort_load_s(SortTile& t, const u64* kin, const u32* pin, int base, int lane, int n) {
+#pragma unroll
+  for (int i = 0; i < SORT_ITEMS; i++) {
+    const int idx = base + i * 32 + lane;
+    const bool ok = idx < n;
+    t.key[i] = ok ? kin[idx] : ~0ull;
+    t.val[i] = ok ? pin[idx] : 0u;
+  }
+}
+
+// exclusive scan of the 256 per-digit totals held one per thread; returns this digit's exclusive prefix
+__device__ __forceinline__ u32 block_excl_scan_256(u32 v, u32* s_wsum, int lane, int warp) {
+  u32 incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const u32 t = __shfl_up_sync(FULL, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_wsum[warp] = incl;
+  __syncthreads();
+  u32 woff = 0;
+#pragma unroll
+  for (int w = 0; w < SORT_WARPS; w++)
+    if (w < warp) woff += s_wsum[w];
+  return woff + incl - v;
+}
+
+// single-CTA stable LSD radix sort of c entries through global memory (k0/p0 <-> k1/p1); result ends in k0/p0
+__device__ void cta_sort_global(u64* k0, u32* p0, u64* k1, u32* p1, int c, int passes, BucketShared& S) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const u32 lt = lanemask_lt();
+  SortTile T;
+  int cur = 0;
+  for (int pass = 0; pass < passes; pass++) {
+    const int shift = 8 * pass;
+    u64* kin = cur ? k1 : k0; u32* pin = cur ? p1 : p0;
+    u64* kout = cur ? k0 : k1; u32* pout = cur ? p0 : p1;
+    S.run[tid] = 0;
+    __syncthreads();
+    for (int idx = tid; idx < c; idx += BK_THREADS) atomicAdd(&S.run[(u32)(kin[idx] >> shift) & 0xFFu], 1u);
+    __syncthreads();
+    const u32 tot = S.run[tid];
+    const u32 ex = block_excl_scan_256(tot, S.wsum, lane, warp);
+    __syncthreads();
+    S.run[tid] = ex;
+    __syncthreads();
+    for (int tile0 = 0; tile0 < c; tile0 += SORT_TILE) {
+#pragma unroll
+      for (int w = 0; w < SORT_WARPS; w++) S.whist[w][tid] = 0;
+      __syncthreads();
+      const int base = tile0 + warp * (32 * SORT_ITEMS);
+      sort_load_s(T, kin, pin, base, lane, c);
+      sort_rank(T, S.whist[warp], base, lane, c, shift, lt);
+      __syncthreads();
+      {
+        u32 sum = 0;
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; w++) {
+          const u32 v = S.whist[w][tid];
+          S.whist[w][tid] = sum;
+          sum += v;
+        }
+        const u32 b = S.run[tid];
+        S.base[tid] = b;
+        S.run[tid] = b + sum;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < SORT_ITEMS; i++) {
+        if ((base + i * 32 + lane) < c) {
+          const u32 digit = (u32)(T.key[i] >> shift) & 0xFFu;
+          const u32 pos = S.base[digit] + S.whist[warp][digit] + T.rank[i];
+          kout[pos] = T.key[i];
+          pout[pos] = T.val[i];
+        }
+      }
+      __syncthreads();
+    }
+    cur ^= 1;
+  }
+  if (cur) {
+    for (int idx = tid; idx < c; idx += BK_THREADS) { k0[idx] = k1[idx]; p0[idx] = p1[idx]; }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(BK_THREADS)
+k_sort_bucket(const u64* kin, const u32* pin, u64* kout, u32* pout, u64* kscr, u32* pscr, const FrameState* fs,
+              const u64* __restrict__ split, int passes, int parity) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  __shared__ BucketShared S;
+  u64* const s_key0 = reinterpret_cast<u64*>(s_raw);                    // [2][BK_CAP]
+  u32* const s_pay0 = reinterpret_cast<u32*>(s_raw + 2 * BK_CAP * 8);   // [2][BK_CAP]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const u32 lt = lanemask_lt();
+  const int n = fs->acc_emit[parity];
+  const int b = blockIdx.x;
+  const u64 lo = (b == 0) ? 0ull : __ldg(&split[b - 1]);
+  const u64 hi = (b == BK_BUCKETS - 1) ? ~0ull : __ldg(&split[b]);
+  if (tid == 0) { S.cnt = 0; S.below = 0; S.or_lo = S.or_hi = 0u; S.and_lo = S.and_hi = ~0u; }
+  __syncthreads();
+
+  // scan the whole list: entries of lower buckets are counted, entries of this bucket are kept
+  u32 below = 0;
+  for (int i0 = 0; i0 < n; i0 += BK_THREADS * 4) {
+    u64 k[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int i = i0 + u * BK_THREADS + tid;
+      k[u] = (i < n) ? kin[i] : ~0ull;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int i = i0 + u * BK_THREADS + tid;
+      if (i >= n) continue;
+      if (k[u] < lo) {
+        below++;
+      } else if (k[u] < hi || b == BK_BUCKETS - 1) {
+        const u32 pos = atomicAdd(&S.cnt, 1u);
+        if (pos < BK_CAP) { s_key0[pos] = k[u]; s_pay0[pos] = pin[i]; }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(FULL, below, o);
+  if (lane == 0 && below) atomicAdd(&S.below, below);
+  __syncthreads();
+  const int c = (int)S.cnt;
+  const u32 offset = S.below;
+  if (c == 0) return;
+
+  if (c > BK_CAP) {
+    // slow path: gather this bucket into its own output range, sort it there through global scratch
+    __syncthreads();
+    if (tid == 0) S.cnt = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += BK_THREADS) {
+      const u64 k = kin[i];
+      if (k >= lo && (k < hi || b == BK_BUCKETS - 1)) {
+        const u32 pos = atomicAdd(&S.cnt, 1u);
+        kout[offset + pos] = k;
+        pout[offset + pos] = pin[i];
+      }
+    }
+    __syncthreads();
+    cta_sort_global(kout + offset, pout + offset, kscr + offset, pscr + offset, c, passes, S);
+    return;
+  }
+
+  // digits on which all keys of the bucket agree need no pass
+  {
+    u32 olo = 0, ohi = 0, alo = ~0u, ahi = ~0u;
+    for (int i = tid; i < c; i += BK_THREADS) {
+      const u64 k = s_key0[i];
+      olo |= (u32)k; ohi |= (u32)(k >> 32); alo &= (u32)k; ahi &= (u32)(k >> 32);
+    }
+    olo = __reduce_or_sync(FULL, olo); ohi = __reduce_or_sync(FULL, ohi);
+    alo = __reduce_and_sync(FULL, alo); ahi = __reduce_and_sync(FULL, ahi);
+    if (lane == 0) {
+      atomicOr(&S.or_lo, olo); atomicOr(&S.or_hi, ohi);
+      atomicAnd(&S.and_lo, alo); atomicAnd(&S.and_hi, ahi);
+    }
+  }
+  __syncthreads();
+  const u64 diff = ((u64)(S.or_hi ^ S.and_hi) << 32) | (u64)(S.or_lo ^ S.and_lo);
+
+  SortTile T;
+  int cur = 0;
+  const int base = warp * (32 * SORT_ITEMS);
+  for (int pass = 0; pass < passes; pass++) {
+    const int shift = 8 * pass;
+    if (((diff >> shift) & 0xFFull) == 0) continue;
+#pragma unroll
+    for (int w = 0; w < SORT_WARPS; w++) S.whist[w][tid] = 0;
+    __syncthreads();
+    sort_load_s(T, s_key0 + cur * BK_CAP, s_pay0 + cur * BK_CAP, base, lane, c);
+    sort_rank(T, S.whist[warp], base, lane, c, shift, lt);
+    __syncthreads();
+    u32 sum = 0;
+#pragma unroll
+    for (int w = 0; w < SORT_WARPS; w++) {
+      const u32 v = S.whist[w][tid];
+      S.whist[w][tid] = sum;
+      sum += v;
+    }
+    const u32 ex = block_excl_scan_256(sum, S.wsum, lane, warp);
+    S.run[tid] = ex;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; i++) {
+      if ((base + i * 32 + lane) < c) {
+        const u32 digit = (u32)(T.key[i] >> shift) & 0xFFu;
+        const u32 pos = S.run[digit] + S.whist[warp][digit] + T.rank[i];
+        s_key0[(cur ^ 1) * BK_CAP + pos] = T.key[i];
+        s_pay0[(cur ^ 1) * BK_CAP + pos] = T.val[i];
+      }
+    }
+    __syncthreads();
+    cur ^= 1;
+  }
+  for (int i = tid; i < c; i += BK_THREADS) {
+    kout[offset + i] = s_key0[cur * BK_CAP + i];
+    pout[offset + i] = s_pay0[cur * BK_CAP + i];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ k_analyze
 #define AN_THREADS 512
 #define AN_WARPS (AN_THREADS / 32)
@@ -453,8 +681,9 @@ __device__ __forceinline__ void assign_block(int vb, int n, const u64* __restric
   __syncthreads();
   // pass 2: top-down along the key; existing child tiles come from the pre-frame pool, new ones from their rank
   const int s_eff = (s == OSL_NONE) ? D : s;
+  const u32 le = lt | (1u << lane);
   u32 node = (u32)key_digit(k, D, 1);
-  u32 prev_idx = 0;
+  u32 par_idx = 0;  // index (in level d-1) of the node on this key's path
   for (int d = 1; d <= D; d++) {
     const bool f = unique && m < d;
     const u32 bal = __ballot_sync(FULL, f);
@@ -470,15 +699,16 @@ __device__ __forceinline__ void assign_block(int vb, int n, const u64* __restric
         ct = (size0 + 8u * rank) | OSL_NEWBIT;
       }
     }
+    const u32 lbase = s_w[warp][OSL_CLVL(D, d)];
     if (f) {
-      const u32 idx = s_w[warp][OSL_CLVL(D, d)] + __popc(bal & lt);
-      const size_t o = lv.off[d] + idx;
+      const size_t o = lv.off[d] + lbase + __popc(bal & lt);
       lv.ctile[o] = ct;
       lv.digit[o] = (uint8_t)key_digit(k, D, d);
-      if (d == D) lv.fc[o] = (mode == 2) ? (u32)(n_invalid_front + j) : __ldcg(&pay[j]);
-      if (d > 1 && m < d - 1) lv.fc[lv.off[d - 1] + prev_idx] = idx;
-      prev_idx = idx;
+      lv.par[o] = par_idx;
+      if (d == D) lv.src[lbase + __popc(bal & lt)] = (mode == 2) ? (u32)(n_invalid_front + j) : __ldcg(&pay[j]);
     }
+    // the level-d node on this key's path: its own if it heads it, else the last one headed before it
+    par_idx = lbase + __popc(bal & le) - 1u;
   }
   __syncthreads();
 }
@@ -486,7 +716,7 @@ __device__ __forceinline__ void assign_block(int vb, int n, const u64* __restric
 __global__ void __launch_bounds__(AN_THREADS)
 k_structure(const u64* __restrict__ keys, u32* pay, const u32* pool, TreeParams tp, FrameState* fs,
             uint8_t* m8, uint8_t* s8, u32* blockcnt, u32* totals, LevelArrays lv, int mode, int capacity, int n_in,
-            int parity) {
+            int parity, u64* split_out) {
   cg::grid_group grid = cg::this_grid();
   __shared__ u32 s_w[AN_WARPS][NC_MAX];
   __shared__ u32 s_plan[NC_MAX];
@@ -501,6 +731,9 @@ k_structure(const u64* __restrict__ keys, u32* pay, const u32* pool, TreeParams 
   const int nvb = (n + AN_THREADS - 1) / AN_THREADS;
   const int G = gridDim.x;
 
+  // splitters for k_sort_bucket of a later frame: BK_BUCKETS-quantiles of this frame's sorted keys
+  if (blockIdx.x == G - 1 && tid < BK_BUCKETS - 1 && n >= BK_BUCKETS)
+    split_out[tid] = keys[(size_t)(((long long)(tid + 1) * n) / BK_BUCKETS)];
   for (int vb = blockIdx.x; vb < nvb; vb += G) analyze_block(vb, n, keys, pay, mode, pool, tp, m8, s8, blockcnt, &s_w[0][0]);
   grid.sync();
 
@@ -594,105 +827,179 @@ k_structure(const u64* __restrict__ keys, u32* pay, const u32* pool, TreeParams 
     assign_block(vb, n, keys, pay, pool, tp, m8, s8, blockcnt, lv, mode, size0, n_invalid_front, s_plan, s_w);
 }
 
-// ------------------------------------------------------------------------------------------------ k_level
-// One thread per touched node X at depth d (d = 0 is the implicit root whose "tile" is nodes 0..7).  The thread owns
-// X's 8-child tile: loads it (64 B) or starts from the split initialiser, folds in its touched children (leaf blend at
-// depth D-1, otherwise the child's mip value and -- for children split this frame -- their new child pointer),
-// writes the tile back and produces X's own mip value for its parent.
-__device__ __forceinline__ void level_node(u32* pool, const LevelArrays& lv, int n_d, int n_c, int d, int D, int mode,
-                                           int fresh_tree, const uint8_t* __restrict__ rgb,
-                                           const float* __restrict__ colors4, int idx) {
-  u32 ct, cbeg, cend;
-  if (d == 0) {
-    ct = fresh_tree ? OSL_NEWBIT : 0u;
-    cbeg = 0; cend = (u32)n_c;
+// ------------------------------------------------------------------------------------------------ k_levels
+// Bottom-up tree update, "scatter to parent": every touched node writes its new value (and, when it was split this
+// frame, its child pointer) into ITS slot of its parent's tile; one step per level, so a level costs one 64-byte tile
+// load per touched node and one or two 4-byte stores, all independent.
+//   phase 0  (all levels at once) initialise the tiles allocated this frame (svo.cu:272-275; Q3 phantom tiles
+//            included) and resolve every node's parent tile (ptile)
+//   phase 1  leaves: blend the winning input's colour into word1 (svo.cu:366-381 / :318-332), link Q3 tiles
+//   phase 2  d = D-1 .. 1: word1 = integer mean / max of the node's 8 children (svo.cu:384-441, Q5); link new tiles
+//   phase 3  Q6: the root average lands in node 0's value word (svo.cu:399-412,439)
+// Cooperative: wide steps use the whole grid with a grid barrier, and as soon as a level fits one CTA (n_level is
+// monotone in d) CTA 0 finishes the remaining levels alone with block barriers.
+#define LEVEL_THREADS 1024
+#define LEVEL_NARROW 1024
+
+__device__ __forceinline__ void level_leaf(u32* pool, const LevelArrays& lv, size_t oD, int idx, int mode,
+                                           const uint8_t* __restrict__ rgb, const float* __restrict__ colors4) {
+  const u32 ct = __ldg(&lv.ctile[oD + idx]);
+  const u32 node = __ldcg(&lv.ptile[oD + idx]) + (u32)__ldg(&lv.digit[oD + idx]);
+  const u32 src = __ldg(&lv.src[idx]);
+  u32* w = pool + 2 * (size_t)node;
+  const u32 cur = __ldcg(w + 1);
+  u32 nv;
+  if (mode == 2) {
+    const float4 col = __ldg(reinterpret_cast<const float4*>(colors4) + src);
+    nv = osl_blend_f4(cur, col.x, col.y, col.z);
   } else {
-    const size_t o = lv.off[d] + idx;
-    ct = lv.ctile[o];
-    cbeg = lv.fc[o];
-    cend = (idx + 1 < n_d) ? lv.fc[o + 1] : (u32)n_c;
+    const uint8_t* q = rgb + 3 * (size_t)src;
+    nv = osl_blend_u8(cur, __ldg(q), __ldg(q + 1), __ldg(q + 2));
   }
-  const u32 T = ct & OSL_MASK;
-  uint4* tile = reinterpret_cast<uint4*>(pool + 2 * (size_t)T);
-  u32 w0[8], w1[8];
-  if (ct & OSL_NEWBIT) {
-    const u32 init = (d == 0) ? 0u : OSL_EMPTY;  // svo.cu:24-31 (root tile zeroed) vs svo.cu:272-275
-#pragma unroll
-    for (int i = 0; i < 8; i++) { w0[i] = 0; w1[i] = init; }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const uint4 q = tile[i];
-      w0[2 * i] = q.x; w1[2 * i] = q.y; w0[2 * i + 1] = q.z; w1[2 * i + 1] = q.w;
-    }
-  }
-  u32 c = cbeg;
-  const size_t oc = lv.off[d + 1];
-  int cd = (c < cend) ? (int)lv.digit[oc + c] : 8;
-#pragma unroll
-  for (int slot = 0; slot < 8; slot++) {
-    if (cd == slot) {
-      const u32 cct = lv.ctile[oc + c];
-      if (d + 1 == D) {
-        const u32 src = lv.fc[oc + c];
-        if (mode == 2) {
-          const float4 col = __ldg(reinterpret_cast<const float4*>(colors4) + src);
-          w1[slot] = osl_blend_f4(w1[slot], col.x, col.y, col.z);
-        } else {
-          const uint8_t* q = rgb + 3 * (size_t)src;
-          w1[slot] = osl_blend_u8(w1[slot], __ldg(q), __ldg(q + 1), __ldg(q + 2));
-        }
-        if (cct != 0xFFFFFFFFu) {  // Q3: the leaf itself gets 8 (phantom) children
-          const u32 pt = cct & OSL_MASK;
-          w0[slot] = OSL_FLAG | pt;
-          uint4* ptile = reinterpret_cast<uint4*>(pool + 2 * (size_t)pt);
-          const uint4 e = make_uint4(0u, OSL_EMPTY, 0u, OSL_EMPTY);
-#pragma unroll
-          for (int i = 0; i < 4; i++) ptile[i] = e;
-        }
-      } else {
-        w1[slot] = lv.val[oc + c];
-        if (cct & OSL_NEWBIT) w0[slot] = OSL_FLAG | (cct & OSL_MASK);
-      }
-      c++;
-      cd = (c < cend) ? (int)lv.digit[oc + c] : 8;
-    }
-  }
-  if (d == 0) {
-    w1[0] = osl_average8(w1);  // Q6: the root average lands in node 0's value word (svo.cu:399-412,439)
-  } else {
-    lv.val[lv.off[d] + idx] = osl_average8(w1);
-  }
-#pragma unroll
-  for (int i = 0; i < 4; i++) tile[i] = make_uint4(w0[2 * i], w1[2 * i], w0[2 * i + 1], w1[2 * i + 1]);
+  w[1] = nv;
+  if (ct != 0xFFFFFFFFu) w[0] = OSL_FLAG | (ct & OSL_MASK);  // Q3: the leaf itself got 8 (phantom) children
 }
 
-// Cooperative: wide levels are processed by the whole grid with a grid barrier between them; as soon as a level is
-// narrow (n_level is monotone in d) CTA 0 finishes all remaining levels alone with block barriers.
-#define LEVEL_THREADS 256
-#define LEVEL_NARROW 2048
+__device__ __forceinline__ void level_inner(u32* pool, const LevelArrays& lv, size_t od, int idx) {
+  const u32 ct = __ldg(&lv.ctile[od + idx]);
+  const u32 node = __ldcg(&lv.ptile[od + idx]) + (u32)__ldg(&lv.digit[od + idx]);
+  const uint4* tile = reinterpret_cast<const uint4*>(pool + 2 * (size_t)(ct & OSL_MASK));
+  u32 v[8];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const uint4 q = __ldcg(tile + i);
+    v[2 * i] = q.y; v[2 * i + 1] = q.w;
+  }
+  u32* w = pool + 2 * (size_t)node;
+  w[1] = osl_average8(v);
+  if (ct & OSL_NEWBIT) w[0] = OSL_FLAG | (ct & OSL_MASK);
+}
+
+// shared-memory staging of the narrow top of the touched sub-tree (CTA 0): per staged node its 8 child values,
+// its own node index, its child tile word and the staged index of its parent
+#define LEVEL_STAGE 2048
+#define LEVEL_SMEM (LEVEL_STAGE * (32 + 4 + 4 + 2 + 2) + 64)
+
 __global__ void __launch_bounds__(LEVEL_THREADS)
 k_levels(u32* pool, LevelArrays lv, const FrameState* fs, int D, int mode, const uint8_t* __restrict__ rgb,
          const float* __restrict__ colors4) {
   cg::grid_group grid = cg::this_grid();
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  __shared__ int s_nl[OSL_MAXD + 2];   // n_level[d]
+  __shared__ int s_pre[OSL_MAXD + 2];  // s_pre[d] = sum of n_level[1..d-1]
   if (fs->overflow) return;
-  const int fresh_tree = fs->fresh;
-  int d = D - 1;
-  for (; d >= 0; d--) {
-    const int n_d = fs->n_level[d];
-    if (n_d <= LEVEL_NARROW) break;
-    const int n_c = fs->n_level[d + 1];
-    for (int idx = blockIdx.x * LEVEL_THREADS + threadIdx.x; idx < n_d; idx += gridDim.x * LEVEL_THREADS)
-      level_node(pool, lv, n_d, n_c, d, D, mode, fresh_tree, rgb, colors4, idx);
-    grid.sync();
+  const int tid = threadIdx.x;
+  const int gtid = blockIdx.x * LEVEL_THREADS + tid, gsz = gridDim.x * LEVEL_THREADS;
+  if (tid == 0) {
+    int run = 0;
+    s_nl[0] = 0; s_pre[0] = 0;
+    for (int d = 1; d <= D; d++) { const int v = fs->n_level[d]; s_nl[d] = v; s_pre[d] = run; run += v; }
+    s_pre[D + 1] = run;
   }
+  __syncthreads();
+  const int total = s_pre[D + 1];
+
+  // phase 0: every touched node of every level at once
+  for (int e = gtid; e < total; e += gsz) {
+    int d = 1;
+    while (d < D && e >= s_pre[d + 1]) d++;
+    const int idx = e - s_pre[d];
+    const size_t od = lv.off[d], op = lv.off[d - 1];
+    const u32 ct = __ldg(&lv.ctile[od + idx]);
+    const u32 pt = (d == 1) ? 0u : (__ldg(&lv.ctile[op + __ldg(&lv.par[od + idx])]) & OSL_MASK);
+    if (ct != 0xFFFFFFFFu && (ct & OSL_NEWBIT)) {
+      uint4* tile = reinterpret_cast<uint4*>(pool + 2 * (size_t)(ct & OSL_MASK));
+      const uint4 init = make_uint4(0u, OSL_EMPTY, 0u, OSL_EMPTY);
+#pragma unroll
+      for (int i = 0; i < 4; i++) tile[i] = init;
+    }
+    lv.ptile[od + idx] = pt;
+  }
+  grid.sync();
+
+  // phase 1: leaves
+  {
+    const int n_D = s_nl[D];
+    const size_t oD = lv.off[D];
+    for (int idx = gtid; idx < n_D; idx += gsz) level_leaf(pool, lv, oD, idx, mode, rgb, colors4);
+  }
+
+  // phase 2: wide levels with the whole grid
+  int d = D - 1;
+  for (; d >= 1; d--) {
+    const int n_d = s_nl[d];
+    if (n_d <= LEVEL_NARROW) break;
+    grid.sync();
+    const size_t od = lv.off[d];
+    for (int idx = gtid; idx < n_d; idx += gsz) level_inner(pool, lv, od, idx);
+  }
+  grid.sync();
   if (blockIdx.x != 0) return;
-  for (; d >= 0; d--) {
-    const int n_d = fs->n_level[d];
-    const int n_c = fs->n_level[d + 1];
-    for (int idx = threadIdx.x; idx < n_d; idx += LEVEL_THREADS)
-      level_node(pool, lv, n_d, n_c, d, D, mode, fresh_tree, rgb, colors4, idx);
+
+  // narrow levels d..1 + the root: CTA 0 alone
+  const int staged = (d >= 1) ? s_pre[d + 1] : 0;  // nodes of levels 1..d
+  if (staged + 1 <= LEVEL_STAGE) {
+    // All their tiles are fetched at once (independent loads, one L2 round trip), the bottom-up fold then runs in
+    // shared memory with one block barrier per level; each node's result is also written to its slot in the pool.
+    u32 (*s_w1)[8] = reinterpret_cast<u32 (*)[8]>(s_raw);
+    u32* s_node = reinterpret_cast<u32*>(s_raw + LEVEL_STAGE * 32);
+    u32* s_ct = s_node + LEVEL_STAGE;
+    unsigned short* s_par = reinterpret_cast<unsigned short*>(s_ct + LEVEL_STAGE);
+    unsigned short* s_dig = s_par + LEVEL_STAGE;
+    // staged index: root = 0, node idx of level l = 1 + s_pre[l] + idx
+    for (int e = tid; e <= staged; e += LEVEL_THREADS) {
+      u32 ct = 0u, node = 0u, par = 0u, dig = 0u;
+      if (e > 0) {
+        int l = 1;
+        while (l < d && (e - 1) >= s_pre[l + 1]) l++;
+        const int idx = e - 1 - s_pre[l];
+        const size_t ol = lv.off[l];
+        ct = __ldg(&lv.ctile[ol + idx]);
+        dig = (u32)__ldg(&lv.digit[ol + idx]);
+        node = __ldcg(&lv.ptile[ol + idx]) + dig;
+        par = (l == 1) ? 0u : (u32)(1 + s_pre[l - 1]) + __ldg(&lv.par[ol + idx]);
+      }
+      const uint4* tile = reinterpret_cast<const uint4*>(pool + 2 * (size_t)(ct & OSL_MASK));
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const uint4 q = __ldcg(tile + i);
+        s_w1[e][2 * i] = q.y; s_w1[e][2 * i + 1] = q.w;
+      }
+      s_node[e] = node; s_ct[e] = ct; s_par[e] = (unsigned short)par; s_dig[e] = (unsigned short)dig;
+    }
     __syncthreads();
+    for (int l = d; l >= 1; l--) {
+      const int n_l = s_nl[l], base = 1 + s_pre[l];
+      for (int idx = tid; idx < n_l; idx += LEVEL_THREADS) {
+        const int e = base + idx;
+        const u32 avg = osl_average8(s_w1[e]);
+        const u32 ct = s_ct[e];
+        u32* w = pool + 2 * (size_t)s_node[e];
+        w[1] = avg;
+        if (ct & OSL_NEWBIT) w[0] = OSL_FLAG | (ct & OSL_MASK);
+        s_w1[s_par[e]][s_dig[e]] = avg;
+      }
+      __syncthreads();
+    }
+    if (tid == 0 && s_nl[1] > 0) pool[1] = osl_average8(s_w1[0]);  // phase 3 (Q6)
+    return;
+  }
+  // fallback: the narrow part does not fit the staging area -> one block barrier + one L2 round trip per level
+  for (; d >= 1; d--) {
+    const int n_d = s_nl[d];
+    const size_t od = lv.off[d];
+    for (int idx = tid; idx < n_d; idx += LEVEL_THREADS) level_inner(pool, lv, od, idx);
+    __syncthreads();
+  }
+  if (tid == 0 && s_nl[1] > 0) {  // phase 3 (Q6)
+    const uint4* tile = reinterpret_cast<const uint4*>(pool);
+    u32 v[8];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const uint4 q = __ldcg(tile + i);
+      v[2 * i] = q.y; v[2 * i + 1] = q.w;
+    }
+    pool[1] = osl_average8(v);
   }
 }
 
@@ -721,7 +1028,8 @@ osl_status osl_ensure_workspace(osl_svo* t, size_t n) {
     t->d_keysA[f] = t->d_keysB[f] = nullptr; t->d_payA[f] = t->d_payB[f] = nullptr;
   }
   cudaFree(t->d_m); cudaFree(t->d_s); cudaFree(t->d_blockcnt);
-  cudaFree(t->d_level_mem);
+  cudaFree(t->d_level_mem); cudaFree(t->d_keysC); cudaFree(t->d_payC);
+  t->d_keysC = nullptr; t->d_payC = nullptr;
   t->d_m = t->d_s = nullptr;
   t->d_blockcnt = nullptr; t->d_level_mem = nullptr;
   t->ws_cap = 0;
@@ -732,6 +1040,8 @@ osl_status osl_ensure_workspace(osl_svo* t, size_t n) {
     OSL_CUDA(cudaMalloc(&t->d_payA[f], cap * sizeof(u32)));
     OSL_CUDA(cudaMalloc(&t->d_payB[f], cap * sizeof(u32)));
   }
+  OSL_CUDA(cudaMalloc(&t->d_keysC, cap * sizeof(u64)));  // k_sort_bucket's slow-path scratch
+  OSL_CUDA(cudaMalloc(&t->d_payC, cap * sizeof(u32)));
   OSL_CUDA(cudaMalloc(&t->d_m, cap));
   OSL_CUDA(cudaMalloc(&t->d_s, cap));
   const size_t nblocks = (cap + AN_THREADS - 1) / AN_THREADS;
@@ -741,20 +1051,29 @@ osl_status osl_ensure_workspace(osl_svo* t, size_t n) {
     t->lv.off[d] = total;
     total += (d >= 1 && d <= D) ? level_cap(cap, d) : 0;
   }
-  // ctile(4) + fc(4) + val(4) + digit(1) bytes per level entry
+  // ctile(4) + par(4) + ptile(4) + digit(1) bytes per level entry, src(4) per leaf
   uint8_t* mem;
-  OSL_CUDA(cudaMalloc(&mem, total * 13 + 64));
+  OSL_CUDA(cudaMalloc(&mem, total * 13 + cap * 4 + 64));
   t->d_level_mem = mem;
   t->lv.ctile = reinterpret_cast<u32*>(mem);
-  t->lv.fc = t->lv.ctile + total;
-  t->lv.val = t->lv.fc + total;
-  t->lv.digit = reinterpret_cast<uint8_t*>(t->lv.val + total);
+  t->lv.par = t->lv.ctile + total;
+  t->lv.ptile = t->lv.par + total;
+  t->lv.src = t->lv.ptile + total;
+  t->lv.digit = reinterpret_cast<uint8_t*>(t->lv.src + cap);
   t->ws_cap = cap;
   return OSL_OK;
 }
 
 osl_status osl_integrate_init(osl_svo* t) {
   OSL_CUDA(cudaFuncSetAttribute((const void*)k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, EMIT_SMEM));
+  OSL_CUDA(cudaFuncSetAttribute((const void*)k_levels, cudaFuncAttributeMaxDynamicSharedMemorySize, LEVEL_SMEM));
+  OSL_CUDA(cudaFuncSetAttribute((const void*)k_sort_bucket, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM));
+  // default splitters: an even partition of the key space (valid, merely unbalanced) until a frame has written some
+  OSL_CUDA(cudaMalloc(&t->d_split, 2 * BK_BUCKETS * sizeof(u64)));
+  u64 h_split[2 * BK_BUCKETS];
+  for (int i = 0; i < 2 * BK_BUCKETS; i++)
+    h_split[i] = (u64)((i % BK_BUCKETS) + 1) * ((1ull << (3 * t->tp.D)) / BK_BUCKETS);
+  OSL_CUDA(cudaMemcpy(t->d_split, h_split, sizeof(h_split), cudaMemcpyHostToDevice));
   return OSL_OK;
 }
 
@@ -787,7 +1106,7 @@ int osl_structure_occupancy() {
 }
 int osl_levels_occupancy() {
   int occ = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)k_levels, LEVEL_THREADS, 0);
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)k_levels, LEVEL_THREADS, LEVEL_SMEM);
   if (e != cudaSuccess) { g_osl_last_cuda_error = (int)e; return 0; }
   return occ;
 }
@@ -813,7 +1132,7 @@ osl_status osl_poll_results(osl_svo* t, bool block) {
     osl_counters& c = t->counters;
     if (mode_of(t, slot) != 2 && F.n_in > 0) {
       int widest = 0;
-      for (int d = 0; d < D; d++) widest = F.n_level[d] > widest ? F.n_level[d] : widest;  // k_levels: one thread per node of depth < D
+      for (int d = 0; d <= D; d++) widest = F.n_level[d] > widest ? F.n_level[d] : widest;
       t->hint_emit = F.n_emit; t->hint_level = widest; t->hint_n_in = F.n_in;
     }
     c.n_points = F.n_in;
@@ -914,6 +1233,7 @@ osl_status osl_run_integrate(osl_svo* t, EmitParams& ep, const void* colors, cud
   const int passes = (3 * D + 7) / 8;
   u64* skeys = (passes & 1) ? t->d_keysB[par] : t->d_keysA[par];
   u32* spay = (passes & 1) ? t->d_payB[par] : t->d_payA[par];
+  bool use_bucket = false;
   // expected number of sorted entries / widest level, from the last completed frame (grid sizing only: every
   // kernel is grid-stride, a wrong guess costs time, not correctness)
   long long exp_emit = n, exp_level = n;
@@ -923,7 +1243,10 @@ osl_status osl_run_integrate(osl_svo* t, EmitParams& ep, const void* colors, cud
     exp_level = (long long)(t->hint_level * scale) + LEVEL_THREADS;
     if (exp_emit > n) exp_emit = n;
     if (exp_level > n) exp_level = n;
+    // small key list and splitters of frame seq-2 in place -> barrier-free bucket sort
+    use_bucket = t->seq >= 2 && exp_emit <= (long long)BK_BUCKETS * BK_CAP / 2 && !t->force_grid_sort;
   }
+  if (use_bucket) { skeys = t->d_keysB[par]; spay = t->d_payB[par]; }
 
   const bool timing = t->stage_timing && !piped && n > 0;
   if (timing) OSL_CUDA(cudaEventRecord(t->stage_ev[0], st));
@@ -945,11 +1268,17 @@ osl_status osl_run_integrate(osl_svo* t, EmitParams& ep, const void* colors, cud
     k_emit<<<etiles, EMIT_THREADS, EMIT_SMEM, fst>>>(ep, t->tp, vec_ok, t->d_keysA[par], t->d_payA[par], t->d_fs, par);
     OSL_LAUNCHED(1);
     if (timing) OSL_CUDA(cudaEventRecord(t->stage_ev[1], st));
-    const int grid = grid_for(exp_emit, SORT_TILE, t->sort_grid < coop_cap ? t->sort_grid : coop_cap);
-    u64* kA = t->d_keysA[par]; u32* pA = t->d_payA[par]; u64* kB = t->d_keysB[par]; u32* pB = t->d_payB[par];
-    u32* ch = t->d_cta_hist[par]; const FrameState* fsc = t->d_fs; int pp = passes; int parity = par;
-    void* args[] = {&kA, &pA, &kB, &pB, &ch, &fsc, &pp, &parity};
-    OSL_CUDA(cudaLaunchCooperativeKernel((void*)k_sort, dim3(grid), dim3(SORT_THREADS), args, 0, fst));
+    if (use_bucket) {
+      k_sort_bucket<<<BK_BUCKETS, BK_THREADS, BK_SMEM, fst>>>(t->d_keysA[par], t->d_payA[par], t->d_keysB[par],
+                                                              t->d_payB[par], t->d_keysC, t->d_payC, t->d_fs,
+                                                              t->d_split + par * BK_BUCKETS, passes, par);
+    } else {
+      const int grid = grid_for(exp_emit, SORT_TILE, t->sort_grid < coop_cap ? t->sort_grid : coop_cap);
+      u64* kA = t->d_keysA[par]; u32* pA = t->d_payA[par]; u64* kB = t->d_keysB[par]; u32* pB = t->d_payB[par];
+      u32* ch = t->d_cta_hist[par]; const FrameState* fsc = t->d_fs; int pp = passes; int parity = par;
+      void* args[] = {&kA, &pA, &kB, &pB, &ch, &fsc, &pp, &parity};
+      OSL_CUDA(cudaLaunchCooperativeKernel((void*)k_sort, dim3(grid), dim3(SORT_THREADS), args, 0, fst));
+    }
     OSL_LAUNCHED(1);
     if (timing) OSL_CUDA(cudaEventRecord(t->stage_ev[2], st));
     if (piped) {
@@ -962,7 +1291,8 @@ osl_status osl_run_integrate(osl_svo* t, EmitParams& ep, const void* colors, cud
     const u64* a0 = skeys; u32* a1 = spay; const u32* a2 = t->d_pool; TreeParams a3 = t->tp; FrameState* a4 = t->d_fs;
     uint8_t* a5 = t->d_m; uint8_t* a6 = t->d_s; u32* a7 = t->d_blockcnt; u32* a8 = t->d_scan_totals;
     LevelArrays a9 = t->lv; int a10 = ep.mode; int a11 = (int)t->cap_nodes; int a12 = n; int a13 = par;
-    void* args[] = {&a0, &a1, &a2, &a3, &a4, &a5, &a6, &a7, &a8, &a9, &a10, &a11, &a12, &a13};
+    u64* a14 = t->d_split + par * BK_BUCKETS;
+    void* args[] = {&a0, &a1, &a2, &a3, &a4, &a5, &a6, &a7, &a8, &a9, &a10, &a11, &a12, &a13, &a14};
     OSL_CUDA(cudaLaunchCooperativeKernel((void*)k_structure, dim3(grid), dim3(AN_THREADS), args, 0, st));
     OSL_LAUNCHED(1);
     if (timing) OSL_CUDA(cudaEventRecord(t->stage_ev[3], st));
@@ -972,7 +1302,7 @@ osl_status osl_run_integrate(osl_svo* t, EmitParams& ep, const void* colors, cud
     u32* a0 = t->d_pool; LevelArrays a1 = t->lv; const FrameState* a2 = t->d_fs; int a3 = D; int a4 = ep.mode;
     const uint8_t* a5 = ep.rgb; const float* a6 = (const float*)colors;
     void* args[] = {&a0, &a1, &a2, &a3, &a4, &a5, &a6};
-    OSL_CUDA(cudaLaunchCooperativeKernel((void*)k_levels, dim3(grid), dim3(LEVEL_THREADS), args, 0, st));
+    OSL_CUDA(cudaLaunchCooperativeKernel((void*)k_levels, dim3(grid), dim3(LEVEL_THREADS), args, LEVEL_SMEM, st));
     OSL_LAUNCHED(1);
   }
   if (timing) { OSL_CUDA(cudaEventRecord(t->stage_ev[4], st)); t->stage_valid = 1; }

@@ -44,11 +44,12 @@ struct FrameState {
   int base[(OSL_MAXD + 1) * (OSL_MAXD + 1)];  // base[s*(D+1)+d]: first global split rank of bucket (frontier s, depth d)
 };
 
-struct LevelArrays {   // dense per-level node lists, level d at offset off[d]
+struct LevelArrays {   // dense per-level lists of the nodes a frame touches, level d at offset off[d]
   u32* ctile;          // child tile index | OSL_NEWBIT ; 0xFFFFFFFF = none (unsplit leaf)
-  u32* fc;             // first child (index into level d+1); level D: payload (pixel index / sorted position)
+  u32* par;            // index (in level d-1) of the parent node
+  u32* ptile;          // tile that holds the node itself (= parent's ctile; resolved by k_levels phase 0)
+  u32* src;            // leaves only: winning input (pixel index / sorted position), indexed by the level-D index
   uint8_t* digit;      // octant of the node inside its parent's tile
-  u32* val;            // word1 value computed bottom-up
   size_t off[OSL_MAXD + 2];
 };
 
@@ -154,6 +155,9 @@ struct osl_svo {
   size_t ws_cap;
   u64 *d_keysA[OSL_FRONT], *d_keysB[OSL_FRONT];  // sort ping/pong per front buffer
   u32 *d_payA[OSL_FRONT], *d_payB[OSL_FRONT];
+  u64* d_keysC; u32* d_payC;   // k_sort_bucket slow-path scratch
+  u64* d_split;                // [2][BK_BUCKETS] splitters written by k_structure of frame f (set f & 1)
+  int force_grid_sort;         // testing: always use the cooperative grid sort
   uint8_t *d_m, *d_s;
   u32* d_blockcnt;    // [blocks][NC]
   u32* d_cta_hist[OSL_FRONT];  // sort: [grid][256]

@@ -34,7 +34,7 @@ class SVO:
     """One GPU-resident sparse voxel octree (the reference's OctreeNode::gpu_data_ / gpu_size_)."""
 
     def __init__(self, center=(0.0, 0.0, 0.0), half_edge=1.0, max_depth=8, reserve_nodes=0, device=0,
-                 quirks=True):
+                 quirks=True, force_grid_sort=False):
         self.center = tuple(float(c) for c in center)
         self.half_edge = float(np.float32(half_edge))
         self.max_depth = int(max_depth)
@@ -43,8 +43,9 @@ class SVO:
         _check(lib().osl_svo_create(C.byref(h), _f(self.center), self.half_edge, self.max_depth,
                                     int(reserve_nodes), device), "osl_svo_create")
         self._h = h
-        if not quirks:
-            _check(lib().osl_svo_set_quirks(self._h, 0), "osl_svo_set_quirks")
+        if not quirks or force_grid_sort:
+            _check(lib().osl_svo_set_quirks(self._h, int(bool(quirks)) | (2 if force_grid_sort else 0)),
+                   "osl_svo_set_quirks")
 
     def set_pipeline(self, enabled=True):
         """inputs of later integrate calls are complete at call time -> frame f+1's sort overlaps frame f's tree update"""

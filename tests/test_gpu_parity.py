@@ -153,6 +153,29 @@ def test_host_frames_pipeline_matches_oracle(P):
     assert np.array_equal(svo.pool(), ref.pool())
 
 
+def test_bucket_sort_slow_path_after_a_scene_cut(P):
+    """splitters come from an earlier frame: a frame whose keys all fall into ONE splitter range (> 2048 of them)
+    takes k_sort_bucket's global-memory path; a frame of the old distribution afterwards takes the fast path again"""
+    rng = np.random.default_rng(8)
+    D = 9
+    svo = P.SVO((0, 0, 0), 1.0, D)
+    grid = P.SVO((0, 0, 0), 1.0, D, force_grid_sort=True)
+    ref = orc.OracleSVO((0, 0, 0), 1.0, D)
+
+    def cloud(n, lo, hi):
+        pts = rng.uniform(lo, hi, size=(n, 3)).astype(np.float32)
+        return pts, rng.integers(0, 256, size=(n, 3)).astype(np.uint8)
+
+    frames = [cloud(6000, -0.9, -0.1)] * 3 + [cloud(30000, 0.1, 0.9)] + [cloud(6000, -0.9, 0.9)] * 2
+    for pts, rgb in frames:
+        for t in (svo, grid, ref):
+            t.integrate_points(pts, rgb)
+        svo.sync()  # completed frames feed the grid-size / sort-selection hints
+        assert svo.size == ref.size == grid.size
+    assert np.array_equal(svo.pool(), ref.pool())
+    assert np.array_equal(grid.pool(), ref.pool())
+
+
 def test_stage_times_are_reported(P):
     D, w, h = 8, 160, 120
     center, half = P.synth.tree_params(D)

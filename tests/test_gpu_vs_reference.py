@@ -71,9 +71,11 @@ def test_depth_frames_structure_matches_reference(P):
         assert svo.size == ref.size
     a, b = svo.pool(), ref.pool()
     assert np.array_equal(a[0::2], b[0::2]), "child pointers / node indices differ"
-    # alpha is order independent except for the rare double increment
+    # alpha: ours is the canonical (minimum legal) outcome -- exactly one +2 per observed leaf per frame; the
+    # reference adds 2 once per duplicate whose read-modify-write did not overlap another one (Q7), so it is >= ours
     da = (a[1::2] >> 24).astype(int) - (b[1::2] >> 24).astype(int)
-    assert np.all(np.abs(da) <= 2 * 3)
+    assert np.all(da <= 0)
+    assert np.mean(da == 0) > 0.9
     same = np.mean(a[1::2] == b[1::2])
     assert same > 0.5, same
 
