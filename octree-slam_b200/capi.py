@@ -23,7 +23,7 @@ EXPORTS = [
     "osl_svo_sync", "osl_svo_view", "osl_svo_size", "osl_svo_download", "osl_svo_upload", "osl_get_counters",
     "osl_raycast", "osl_raycast_host", "osl_raycast_pool", "osl_extract_voxels",
     "osl_generate_vertex_map", "osl_transform_vertex_map", "osl_point_cloud_bbox", "osl_compute_keys",
-    "osl_status_string", "osl_last_cuda_error", "osl_version", "osl_launch_count",
+    "osl_status_string", "osl_last_cuda_error", "osl_version", "osl_launch_count", "osl_debug_profile",
 ]
 
 
@@ -97,6 +97,7 @@ def lib():
         "osl_last_cuda_error": (i32, []),
         "osl_version": (C.c_char_p, []),
         "osl_launch_count": (i64, []),
+        "osl_debug_profile": (i32, [vp, i32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

@@ -106,7 +106,7 @@ void osl_svo_destroy(osl_svo* t) {
     if (t->back_done[f]) cudaEventDestroy(t->back_done[f]);
   }
   cudaFree(t->d_m); cudaFree(t->d_s); cudaFree(t->d_blockcnt);
-  cudaFree(t->d_keysC); cudaFree(t->d_payC); cudaFree(t->d_split);
+  cudaFree(t->d_keysC); cudaFree(t->d_payC); cudaFree(t->d_split); cudaFree(t->d_start); cudaFree(t->d_flags);
   cudaFree(t->d_scan_totals); cudaFree(t->d_level_mem); cudaFree(t->d_fs);
   for (int i = 0; i < OSL_STAGES; i++) {
     cudaFree(t->d_depth_stage[i]); cudaFree(t->d_rgb_stage[i]);

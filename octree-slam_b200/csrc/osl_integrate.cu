@@ -22,6 +22,10 @@ namespace cg = cooperative_groups;
 
 #define FULL 0xFFFFFFFFu
 
+// phase checkpoints (SM clock of CTA 0 / thread 0) for tools/phase_profile.py; one predicated store each
+__device__ unsigned long long g_osl_prof[64];
+#define PROF(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_osl_prof[i] = (unsigned long long)clock64(); } while (0)
+
 // ------------------------------------------------------------------------------------------------ k_emit
 // One CTA per 64x32-pixel tile (mode 0) or per 2048 consecutive inputs (modes 1, 2); 8 inputs per thread.
 // Back-projection + pose + Morton key in registers, then the tile's keys are DE-DUPLICATED in a shared-memory hash
@@ -49,6 +53,7 @@ k_emit(EmitParams p, TreeParams tp, int vec_ok, u64* __restrict__ keys, u32* __r
   __shared__ u32 s_count, s_valid, s_base;
   const int tid = threadIdx.x, lane = tid & 31;
   const bool dedup = p.mode != 2;
+  PROF(0);
 
   if (dedup) {
     uint4* k4 = reinterpret_cast<uint4*>(s_key);
@@ -97,6 +102,7 @@ k_emit(EmitParams p, TreeParams tp, int vec_ok, u64* __restrict__ keys, u32* __r
     }
   }
   __syncthreads();
+  PROF(1);
 
   {  // valid inputs of the tile (statistics; mode 2: the number of invalid keys that sort to the front)
     u32 c = __popc(vmask);
@@ -124,6 +130,7 @@ k_emit(EmitParams p, TreeParams tp, int vec_ok, u64* __restrict__ keys, u32* __r
     }
   }
   __syncthreads();
+  PROF(2);
   const u32 cnt = s_count;
   if (tid == 0) {
     s_base = cnt ? atomicAdd(reinterpret_cast<u32*>(&fs->acc_emit[parity]), cnt) : 0u;
@@ -136,6 +143,7 @@ k_emit(EmitParams p, TreeParams tp, int vec_ok, u64* __restrict__ keys, u32* __r
     keys[base + i] = s_key[slot];
     pay[base + i] = s_pay[slot];
   }
+  PROF(3);
 }
 
 // ------------------------------------------------------------------------------------------------ k_sort
@@ -455,18 +463,19 @@ k_sort_bucket(const u64* kin, const u32* pin, u64* kout, u32* pout, u64* kscr, u
   const u64 hi = (b == BK_BUCKETS - 1) ? ~0ull : __ldg(&split[b]);
   if (tid == 0) { S.cnt = 0; S.below = 0; S.or_lo = S.or_hi = 0u; S.and_lo = S.and_hi = ~0u; }
   __syncthreads();
+  PROF(8);
 
   // scan the whole list: entries of lower buckets are counted, entries of this bucket are kept
   u32 below = 0;
-  for (int i0 = 0; i0 < n; i0 += BK_THREADS * 4) {
-    u64 k[4];
+  for (int i0 = 0; i0 < n; i0 += BK_THREADS * 16) {  // 16 independent loads in flight per thread
+    u64 k[16];
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
+    for (int u = 0; u < 16; u++) {
       const int i = i0 + u * BK_THREADS + tid;
       k[u] = (i < n) ? kin[i] : ~0ull;
     }
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
+    for (int u = 0; u < 16; u++) {
       const int i = i0 + u * BK_THREADS + tid;
       if (i >= n) continue;
       if (k[u] < lo) {
@@ -483,6 +492,7 @@ k_sort_bucket(const u64* kin, const u32* pin, u64* kout, u32* pout, u64* kscr, u
   __syncthreads();
   const int c = (int)S.cnt;
   const u32 offset = S.below;
+  PROF(9);
   if (c == 0) return;
 
   if (c > BK_CAP) {
@@ -554,10 +564,12 @@ k_sort_bucket(const u64* kin, const u32* pin, u64* kout, u32* pout, u64* kscr, u
     __syncthreads();
     cur ^= 1;
   }
+  PROF(10);
   for (int i = tid; i < c; i += BK_THREADS) {
     kout[offset + i] = s_key0[cur * BK_CAP + i];
     pout[offset + i] = s_pay0[cur * BK_CAP + i];
   }
+  PROF(11);
 }
 
 // ------------------------------------------------------------------------------------------------ k_analyze
@@ -570,9 +582,11 @@ __device__ __forceinline__ int key_digit(u64 key, int D, int d) { return (int)((
 // Walk the PRE-FRAME tree along `key` (splitKeys, svo.cu:108-142).  Returns the frontier depth s: the depth of the
 // first node on the path without the has-children flag, OSL_NONE if the path exists down to the leaf's parent.
 // Q3 (svo.cu:123 `>= 15`): when the last digit is 7 the reference also tests the LEAF and reports it for splitting.
-__device__ __forceinline__ int walk_frontier(const u32* __restrict__ pool, u64 key, int D, int quirks) {
+__device__ __forceinline__ int walk_frontier(const u32* __restrict__ pool, u64 key, int D, int quirks, int m,
+                                             u32& start) {
   u32 node = (u32)key_digit(key, D, 1);
   for (int t = 1; t <= D - 1; t++) {
+    if (t == m + 1) start = node;  // the first node this key heads: where phase C resumes the walk
     const u32 w0 = pool[2 * (size_t)node];
     if (!(w0 & OSL_FLAG)) return t;
     node = (w0 & OSL_MASK) + (u32)key_digit(key, D, t + 1);
@@ -585,17 +599,22 @@ __device__ __forceinline__ int walk_frontier(const u32* __restrict__ pool, u64 k
 
 // ------------------------------------------------------------------------------------------------ k_structure
 // ONE cooperative kernel builds the frame's structure plan:
-//   phase A  (per virtual block of 512 sorted keys) common-prefix length m with the predecessor, frontier depth s
-//            from a walk of the pre-frame tree, per-block counts of level heads and (s, depth) split buckets
-//   -- grid barrier --
-//   phase B  one warp per counter: exclusive scan of the counter column over the virtual blocks
-//   -- grid barrier --
+//   phase A  (per virtual block of 512 sorted keys) common-prefix length m with the predecessor, lowest payload of
+//            each run of equal keys, frontier depth s from a walk of the pre-frame tree, per-block counts of level
+//            heads and (s, depth) split buckets
+//   exchange small frames (<= AN_FLAG_MAX virtual blocks): every block publishes its count vector behind a flag and
+//            every CTA sums all vectors itself (totals + its own exclusive prefix) -- one wait, no grid barrier;
+//            large frames: grid barrier, one warp per counter scans its column over the blocks, grid barrier
 //   phase B2 every CTA derives the allocation plan from the totals (bucket bases in the reference's order:
 //            pass = depth - s, then numeric key); CTA 0 publishes the FrameState; overflow => nothing is written
-//   phase C  dense per-level node lists with deterministic child-tile indices
+//   phase C  dense per-level node lists with deterministic child-tile indices; tiles allocated this frame are
+//            initialised here (svo.cu:272-275) -- they lie beyond the pre-frame pool, which is all phase C reads
+#define AN_FLAG_MAX 160
+
 __device__ __forceinline__ void analyze_block(int vb, int n, const u64* __restrict__ keys, u32* pay, int mode,
                                               const u32* pool, const TreeParams& tp, uint8_t* __restrict__ m8,
-                                              uint8_t* __restrict__ s8, u32* __restrict__ blockcnt, u32* s_cnt) {
+                                              uint8_t* __restrict__ s8, u32* __restrict__ start,
+                                              u32* __restrict__ blockcnt, u32* s_cnt) {
   const int D = tp.D, NC = OSL_NCOUNT(D);
   for (int c = threadIdx.x; c < NC; c += AN_THREADS) s_cnt[c] = 0;
   __syncthreads();
@@ -614,7 +633,9 @@ __device__ __forceinline__ void analyze_block(int vb, int n, const u64* __restri
         for (int jj = j + 1; jj < n && keys[jj] == k; jj++) pm = min(pm, pay[jj]);
         pay[j] = pm;
       }
-      s = walk_frontier(pool, k, D, tp.quirks);
+      u32 st = 0;
+      s = walk_frontier(pool, k, D, tp.quirks, m, st);
+      start[j] = st;
       atomicAdd(&s_cnt[OSL_CLVL(D, m + 1)], 1u);  // heads every level d > m
       if (s != OSL_NONE) {
         const int lo = (s == D) ? D : max(m + 1, s);
@@ -642,18 +663,20 @@ __device__ __forceinline__ void analyze_block(int vb, int n, const u64* __restri
   __syncthreads();
 }
 
-__device__ __forceinline__ void assign_block(int vb, int n, const u64* __restrict__ keys, const u32* pay,
-                                             const u32* pool, const TreeParams& tp, const uint8_t* __restrict__ m8,
-                                             const uint8_t* __restrict__ s8, const u32* blockbase,
-                                             const LevelArrays& lv, int mode, u32 size0, int n_invalid_front,
-                                             const u32* s_plan, u32 (*s_w)[NC_MAX]) {
+// s_base: this block's exclusive prefix of every counter (shared memory)
+__device__ __forceinline__ void assign_block(int vb, int n, const u64* __restrict__ keys, const u32* pay, u32* pool,
+                                             const TreeParams& tp, const uint8_t* __restrict__ m8,
+                                             const uint8_t* __restrict__ s8, const u32* __restrict__ start,
+                                             const u32* s_base, const LevelArrays& lv, int mode, u32 size0,
+                                             int n_invalid_front, const u32* s_plan, u32 (*s_w)[NC_MAX]) {
   const int D = tp.D, NC = OSL_NCOUNT(D);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const u32 lt = lanemask_lt();
   const int j = vb * AN_THREADS + tid;
   u64 k = 0;
   int m = D, s = OSL_NONE;
-  if (j < n) { k = keys[j]; m = m8[j]; s = s8[j]; }
+  u32 node = 0;
+  if (j < n) { k = keys[j]; m = m8[j]; s = s8[j]; node = start[j]; }
   const bool unique = m < D;
 
   // pass 1: per-warp totals of every counter this block can touch
@@ -670,7 +693,7 @@ __device__ __forceinline__ void assign_block(int vb, int n, const u64* __restric
   __syncthreads();
   // exclusive scan over the warps + the block's global base + the bucket's global rank base
   for (int c = tid; c < NC; c += AN_THREADS) {
-    u32 run = __ldcg(&blockbase[(size_t)vb * NC + c]) + s_plan[c];
+    u32 run = s_base[c] + s_plan[c];
 #pragma unroll
     for (int w = 0; w < AN_WARPS; w++) {
       const u32 v = s_w[w][c];
@@ -679,10 +702,10 @@ __device__ __forceinline__ void assign_block(int vb, int n, const u64* __restric
     }
   }
   __syncthreads();
-  // pass 2: top-down along the key; existing child tiles come from the pre-frame pool, new ones from their rank
+  // pass 2: down the levels this key heads (d > m), resuming the walk of phase A at depth m+1; existing child tiles
+  // come from the pre-frame pool, new ones from their rank
   const int s_eff = (s == OSL_NONE) ? D : s;
   const u32 le = lt | (1u << lane);
-  u32 node = (u32)key_digit(k, D, 1);
   u32 par_idx = 0;  // index (in level d-1) of the node on this key's path
   for (int d = 1; d <= D; d++) {
     const bool f = unique && m < d;
@@ -690,13 +713,18 @@ __device__ __forceinline__ void assign_block(int vb, int n, const u64* __restric
     const bool sp = f && s != OSL_NONE && s <= d && (d <= D - 1 || s == D);
     const u32 peers = __match_any_sync(FULL, sp ? s : 0);
     u32 ct = 0xFFFFFFFFu;
-    if (unique) {
+    if (f) {
       if (d < D && d < s_eff) {
         ct = pool[2 * (size_t)node] & OSL_MASK;
         node = ct + (u32)key_digit(k, D, d + 1);
       } else if (sp) {
         const u32 rank = s_w[warp][OSL_CBKT(D, s, d)] + __popc(peers & lt);
-        ct = (size0 + 8u * rank) | OSL_NEWBIT;
+        const u32 tile = size0 + 8u * rank;
+        ct = tile | OSL_NEWBIT;
+        uint4* tp4 = reinterpret_cast<uint4*>(pool + 2 * (size_t)tile);  // svo.cu:272-275
+        const uint4 init = make_uint4(0u, OSL_EMPTY, 0u, OSL_EMPTY);
+#pragma unroll
+        for (int i = 0; i < 4; i++) tp4[i] = init;
       }
     }
     const u32 lbase = s_w[warp][OSL_CLVL(D, d)];
@@ -713,56 +741,104 @@ __device__ __forceinline__ void assign_block(int vb, int n, const u64* __restric
   __syncthreads();
 }
 
+__device__ __forceinline__ u32 ld_vol(const u32* p) { return *(const volatile u32*)p; }
+
 __global__ void __launch_bounds__(AN_THREADS)
-k_structure(const u64* __restrict__ keys, u32* pay, const u32* pool, TreeParams tp, FrameState* fs,
-            uint8_t* m8, uint8_t* s8, u32* blockcnt, u32* totals, LevelArrays lv, int mode, int capacity, int n_in,
-            int parity, u64* split_out) {
+k_structure(const u64* __restrict__ keys, u32* pay, u32* pool, TreeParams tp, FrameState* fs,
+            uint8_t* m8, uint8_t* s8, u32* start, u32* blockcnt, u32* totals, u32* flags, u32 epoch, LevelArrays lv,
+            int mode, int capacity, int n_in, int parity, u64* split_out) {
   cg::grid_group grid = cg::this_grid();
   __shared__ u32 s_w[AN_WARPS][NC_MAX];
   __shared__ u32 s_plan[NC_MAX];
+  __shared__ u32 s_tot[NC_MAX];
+  __shared__ u32 s_base[NC_MAX];
   __shared__ u32 s_scan[AN_WARPS];
   const int D = tp.D, NC = OSL_NCOUNT(D);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int n = fs->acc_emit[parity];
-  const int n_valid = fs->acc_valid[parity];
+  const int n = __ldcg(&fs->acc_emit[parity]);
+  const int n_valid = __ldcg(&fs->acc_valid[parity]);
   const int n_invalid_front = n_in - n_valid;
-  const int cur = fs->cur_size;
+  const int cur = __ldcg(&fs->cur_size);
   const u32 size0 = (u32)(cur > 8 ? cur : 8);
   const int nvb = (n + AN_THREADS - 1) / AN_THREADS;
   const int G = gridDim.x;
+  const bool flagpath = nvb <= AN_FLAG_MAX;
 
+  PROF(16);
   // splitters for k_sort_bucket of a later frame: BK_BUCKETS-quantiles of this frame's sorted keys
   if (blockIdx.x == G - 1 && tid < BK_BUCKETS - 1 && n >= BK_BUCKETS)
     split_out[tid] = keys[(size_t)(((long long)(tid + 1) * n) / BK_BUCKETS)];
-  for (int vb = blockIdx.x; vb < nvb; vb += G) analyze_block(vb, n, keys, pay, mode, pool, tp, m8, s8, blockcnt, &s_w[0][0]);
-  grid.sync();
-
-  // phase B: column scans, one warp per counter, 4 independent loads per lane in flight
-  for (int c = blockIdx.x * AN_WARPS + warp; c < NC; c += G * AN_WARPS) {
-    u32 carry = 0;
-    for (int b0 = 0; b0 < nvb; b0 += 128) {
-      u32 v[4];
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const int b = b0 + k * 32 + lane;
-        v[k] = (b < nvb) ? __ldcg(&blockcnt[(size_t)b * NC + c]) : 0u;
-      }
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        u32 incl = v[k];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const u32 t = __shfl_up_sync(FULL, incl, o);
-          if (lane >= o) incl += t;
-        }
-        const int b = b0 + k * 32 + lane;
-        if (b < nvb) blockcnt[(size_t)b * NC + c] = carry + incl - v[k];
-        carry += __shfl_sync(FULL, incl, 31);
-      }
+  for (int vb = blockIdx.x; vb < nvb; vb += G) {
+    analyze_block(vb, n, keys, pay, mode, pool, tp, m8, s8, start, blockcnt, &s_w[0][0]);
+    if (flagpath && tid == 0) {  // publish (analyze_block ends with a block barrier after the stores)
+      __threadfence();
+      *(volatile u32*)&flags[vb] = epoch;
     }
-    if (lane == 0) totals[c] = carry;
   }
-  grid.sync();
+  PROF(17);
+
+  if (flagpath) {
+    // wait for every block's vector, then sum them: totals for the plan, exclusive prefix for the own block(s)
+    if (warp == 0) {
+      for (int b = lane; b < nvb; b += 32)
+        while (ld_vol(&flags[b]) != epoch) {}
+      __threadfence();
+    }
+    __syncthreads();
+    PROF(18);
+    for (int c = tid; c < NC; c += AN_THREADS) {
+      u32 tot = 0, pre = 0;
+      const int mine = (int)blockIdx.x;
+      for (int b0 = 0; b0 < nvb; b0 += 8) {
+        u32 v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = (b0 + k < nvb) ? __ldcg(&blockcnt[(size_t)(b0 + k) * NC + c]) : 0u;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          tot += v[k];
+          if (b0 + k < mine) pre += v[k];
+        }
+      }
+      s_tot[c] = tot;
+      s_base[c] = pre;
+    }
+    __syncthreads();
+    PROF(19);
+    PROF(20);
+  } else {
+    grid.sync();
+    PROF(18);
+    // phase B: column scans, one warp per counter, 4 independent loads per lane in flight
+    for (int c = blockIdx.x * AN_WARPS + warp; c < NC; c += G * AN_WARPS) {
+      u32 carry = 0;
+      for (int b0 = 0; b0 < nvb; b0 += 128) {
+        u32 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const int b = b0 + k * 32 + lane;
+          v[k] = (b < nvb) ? __ldcg(&blockcnt[(size_t)b * NC + c]) : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          u32 incl = v[k];
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const u32 t = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += t;
+          }
+          const int b = b0 + k * 32 + lane;
+          if (b < nvb) blockcnt[(size_t)b * NC + c] = carry + incl - v[k];
+          carry += __shfl_sync(FULL, incl, 31);
+        }
+      }
+      if (lane == 0) totals[c] = carry;
+    }
+    PROF(19);
+    grid.sync();
+    PROF(20);
+    for (int c = tid; c < NC; c += AN_THREADS) s_tot[c] = __ldcg(&totals[c]);
+    __syncthreads();
+  }
 
   // phase B2: the allocation plan.  Entry e = i*D + (d-1) in the reference's order (pass i, then depth d):
   // bucket (s = d - i, d).  Exclusive scan over the <= D*D entries gives each bucket's first global rank.
@@ -773,7 +849,7 @@ k_structure(const u64* __restrict__ keys, u32* pay, const u32* pool, TreeParams 
     const int i = tid / D;
     bd = tid % D + 1;
     bs = bd - i;
-    if (bs >= 1 && !(bd == D && bs != D)) val = __ldcg(&totals[OSL_CBKT(D, bs, bd)]);
+    if (bs >= 1 && !(bd == D && bs != D)) val = s_tot[OSL_CBKT(D, bs, bd)];
     else bs = 0;
   }
   u32 incl = val;
@@ -800,15 +876,17 @@ k_structure(const u64* __restrict__ keys, u32* pay, const u32* pool, TreeParams 
       u32 pc = 0;
       for (int d = 1; d <= D; d++) {
         const int s = d - tid;
-        if (s >= 1 && !(d == D && s != D)) pc += __ldcg(&totals[OSL_CBKT(D, s, d)]);
+        if (s >= 1 && !(d == D && s != D)) pc += s_tot[OSL_CBKT(D, s, d)];
       }
       fs->pass_count[tid] = (int)pc;
     }
-    if (tid >= 1 && tid <= D) fs->n_level[tid] = (int)__ldcg(&totals[OSL_CLVL(D, tid)]);
+    if (tid >= 1 && tid <= D) fs->n_level[tid] = (int)s_tot[OSL_CLVL(D, tid)];
     if (tid == 0) {
       fs->n_in = n_in; fs->n_valid = n_valid; fs->n_emit = n; fs->n_invalid_front = n_invalid_front;
-      fs->acc_valid[parity] = 0; fs->acc_emit[parity] = 0;  // every CTA has read them (two grid barriers ago)
-      fs->n_level[0] = __ldcg(&totals[OSL_CLVL(D, 1)]) > 0 ? 1 : 0;
+      // every CTA that has work read these before it published / passed the barrier; a CTA that starts later
+      // sees 0 entries and idles
+      fs->acc_valid[parity] = 0; fs->acc_emit[parity] = 0;
+      fs->n_level[0] = s_tot[OSL_CLVL(D, 1)] > 0 ? 1 : 0;
       fs->n_level[D + 1] = 0;
       fs->n_split = (int)n_split;
       fs->size_before = (int)size0;
@@ -821,31 +899,57 @@ k_structure(const u64* __restrict__ keys, u32* pay, const u32* pool, TreeParams 
     }
   }
   __syncthreads();
+  PROF(21);
   if (overflow) return;
 
-  for (int vb = blockIdx.x; vb < nvb; vb += G)
-    assign_block(vb, n, keys, pay, pool, tp, m8, s8, blockcnt, lv, mode, size0, n_invalid_front, s_plan, s_w);
+  int prev_vb = (int)blockIdx.x;
+  for (int vb = blockIdx.x; vb < nvb; vb += G) {
+    if (!flagpath) {
+      for (int c = tid; c < NC; c += AN_THREADS) s_base[c] = __ldcg(&blockcnt[(size_t)vb * NC + c]);
+    } else if (vb != prev_vb) {  // a CTA with several blocks: extend the prefix by the blocks in between
+      for (int c = tid; c < NC; c += AN_THREADS) {
+        u32 pre = s_base[c];
+        for (int b = prev_vb; b < vb; b++) pre += __ldcg(&blockcnt[(size_t)b * NC + c]);
+        s_base[c] = pre;
+      }
+      prev_vb = vb;
+    }
+    __syncthreads();
+    assign_block(vb, n, keys, pay, pool, tp, m8, s8, start, s_base, lv, mode, size0, n_invalid_front, s_plan, s_w);
+  }
+  PROF(22);
 }
 
 // ------------------------------------------------------------------------------------------------ k_levels
 // Bottom-up tree update, "scatter to parent": every touched node writes its new value (and, when it was split this
 // frame, its child pointer) into ITS slot of its parent's tile; one step per level, so a level costs one 64-byte tile
-// load per touched node and one or two 4-byte stores, all independent.
-//   phase 0  (all levels at once) initialise the tiles allocated this frame (svo.cu:272-275; Q3 phantom tiles
-//            included) and resolve every node's parent tile (ptile)
+// load per touched node and one or two 4-byte stores, all independent.  (Tiles allocated this frame were initialised
+// by k_structure.)
 //   phase 1  leaves: blend the winning input's colour into word1 (svo.cu:366-381 / :318-332), link Q3 tiles
 //   phase 2  d = D-1 .. 1: word1 = integer mean / max of the node's 8 children (svo.cu:384-441, Q5); link new tiles
 //   phase 3  Q6: the root average lands in node 0's value word (svo.cu:399-412,439)
-// Cooperative: wide steps use the whole grid with a grid barrier, and as soon as a level fits one CTA (n_level is
-// monotone in d) CTA 0 finishes the remaining levels alone with block barriers.
+// Cooperative.  Wide levels use the whole grid with a grid barrier in between.  As soon as a level fits one CTA
+// (n_level is monotone in d) the other CTAs signal "done" and exit, and CTA 0 finishes alone: it fetches the tiles
+// of ALL remaining levels at once (independent loads) and folds them bottom-up in shared memory, block barriers
+// while a level is wider than a warp, warp barriers above that.
 #define LEVEL_THREADS 1024
 #define LEVEL_NARROW 1024
+#define LEVEL_STAGE 2048
+#define LEVEL_SMEM (LEVEL_STAGE * (32 + 4 + 4 + 2 + 2) + 64)
 
-__device__ __forceinline__ void level_leaf(u32* pool, const LevelArrays& lv, size_t oD, int idx, int mode,
+// the node's own index: (tile that its parent points to) + its octant
+__device__ __forceinline__ u32 level_self(const LevelArrays& lv, int d, size_t od, int idx) {
+  const u32 dig = (u32)__ldg(&lv.digit[od + idx]);
+  if (d == 1) return dig;
+  return (__ldg(&lv.ctile[lv.off[d - 1] + __ldg(&lv.par[od + idx])]) & OSL_MASK) + dig;
+}
+
+__device__ __forceinline__ void level_leaf(u32* pool, const LevelArrays& lv, int D, int idx, int mode,
                                            const uint8_t* __restrict__ rgb, const float* __restrict__ colors4) {
+  const size_t oD = lv.off[D];
   const u32 ct = __ldg(&lv.ctile[oD + idx]);
-  const u32 node = __ldcg(&lv.ptile[oD + idx]) + (u32)__ldg(&lv.digit[oD + idx]);
   const u32 src = __ldg(&lv.src[idx]);
+  const u32 node = level_self(lv, D, oD, idx);
   u32* w = pool + 2 * (size_t)node;
   const u32 cur = __ldcg(w + 1);
   u32 nv;
@@ -860,9 +964,10 @@ __device__ __forceinline__ void level_leaf(u32* pool, const LevelArrays& lv, siz
   if (ct != 0xFFFFFFFFu) w[0] = OSL_FLAG | (ct & OSL_MASK);  // Q3: the leaf itself got 8 (phantom) children
 }
 
-__device__ __forceinline__ void level_inner(u32* pool, const LevelArrays& lv, size_t od, int idx) {
+__device__ __forceinline__ void level_inner(u32* pool, const LevelArrays& lv, int d, int idx) {
+  const size_t od = lv.off[d];
   const u32 ct = __ldg(&lv.ctile[od + idx]);
-  const u32 node = __ldcg(&lv.ptile[od + idx]) + (u32)__ldg(&lv.digit[od + idx]);
+  const u32 node = level_self(lv, d, od, idx);
   const uint4* tile = reinterpret_cast<const uint4*>(pool + 2 * (size_t)(ct & OSL_MASK));
   u32 v[8];
 #pragma unroll
@@ -875,14 +980,9 @@ __device__ __forceinline__ void level_inner(u32* pool, const LevelArrays& lv, si
   if (ct & OSL_NEWBIT) w[0] = OSL_FLAG | (ct & OSL_MASK);
 }
 
-// shared-memory staging of the narrow top of the touched sub-tree (CTA 0): per staged node its 8 child values,
-// its own node index, its child tile word and the staged index of its parent
-#define LEVEL_STAGE 2048
-#define LEVEL_SMEM (LEVEL_STAGE * (32 + 4 + 4 + 2 + 2) + 64)
-
 __global__ void __launch_bounds__(LEVEL_THREADS)
-k_levels(u32* pool, LevelArrays lv, const FrameState* fs, int D, int mode, const uint8_t* __restrict__ rgb,
-         const float* __restrict__ colors4) {
+k_levels(u32* pool, LevelArrays lv, const FrameState* fs, u32* done, int D, int mode,
+         const uint8_t* __restrict__ rgb, const float* __restrict__ colors4) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(16) unsigned char s_raw[];
   __shared__ int s_nl[OSL_MAXD + 2];   // n_level[d]
@@ -897,32 +997,14 @@ k_levels(u32* pool, LevelArrays lv, const FrameState* fs, int D, int mode, const
     s_pre[D + 1] = run;
   }
   __syncthreads();
-  const int total = s_pre[D + 1];
-
-  // phase 0: every touched node of every level at once
-  for (int e = gtid; e < total; e += gsz) {
-    int d = 1;
-    while (d < D && e >= s_pre[d + 1]) d++;
-    const int idx = e - s_pre[d];
-    const size_t od = lv.off[d], op = lv.off[d - 1];
-    const u32 ct = __ldg(&lv.ctile[od + idx]);
-    const u32 pt = (d == 1) ? 0u : (__ldg(&lv.ctile[op + __ldg(&lv.par[od + idx])]) & OSL_MASK);
-    if (ct != 0xFFFFFFFFu && (ct & OSL_NEWBIT)) {
-      uint4* tile = reinterpret_cast<uint4*>(pool + 2 * (size_t)(ct & OSL_MASK));
-      const uint4 init = make_uint4(0u, OSL_EMPTY, 0u, OSL_EMPTY);
-#pragma unroll
-      for (int i = 0; i < 4; i++) tile[i] = init;
-    }
-    lv.ptile[od + idx] = pt;
-  }
-  grid.sync();
+  PROF(32);
 
   // phase 1: leaves
   {
     const int n_D = s_nl[D];
-    const size_t oD = lv.off[D];
-    for (int idx = gtid; idx < n_D; idx += gsz) level_leaf(pool, lv, oD, idx, mode, rgb, colors4);
+    for (int idx = gtid; idx < n_D; idx += gsz) level_leaf(pool, lv, D, idx, mode, rgb, colors4);
   }
+  PROF(35);
 
   // phase 2: wide levels with the whole grid
   int d = D - 1;
@@ -930,17 +1012,27 @@ k_levels(u32* pool, LevelArrays lv, const FrameState* fs, int D, int mode, const
     const int n_d = s_nl[d];
     if (n_d <= LEVEL_NARROW) break;
     grid.sync();
-    const size_t od = lv.off[d];
-    for (int idx = gtid; idx < n_d; idx += gsz) level_inner(pool, lv, od, idx);
+    for (int idx = gtid; idx < n_d; idx += gsz) level_inner(pool, lv, d, idx);
   }
-  grid.sync();
+  PROF(36);
+  // one-sided barrier: everybody signals, only CTA 0 waits
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    atomicAdd(done, 1u);
+  }
   if (blockIdx.x != 0) return;
+  if (tid == 0) {
+    while (*(volatile u32*)done != gridDim.x) {}
+    *(volatile u32*)done = 0u;  // the next launch starts from zero (launches of one tree are stream-ordered)
+    __threadfence();
+  }
+  __syncthreads();
+  PROF(37);
 
   // narrow levels d..1 + the root: CTA 0 alone
   const int staged = (d >= 1) ? s_pre[d + 1] : 0;  // nodes of levels 1..d
   if (staged + 1 <= LEVEL_STAGE) {
-    // All their tiles are fetched at once (independent loads, one L2 round trip), the bottom-up fold then runs in
-    // shared memory with one block barrier per level; each node's result is also written to its slot in the pool.
     u32 (*s_w1)[8] = reinterpret_cast<u32 (*)[8]>(s_raw);
     u32* s_node = reinterpret_cast<u32*>(s_raw + LEVEL_STAGE * 32);
     u32* s_ct = s_node + LEVEL_STAGE;
@@ -956,8 +1048,9 @@ k_levels(u32* pool, LevelArrays lv, const FrameState* fs, int D, int mode, const
         const size_t ol = lv.off[l];
         ct = __ldg(&lv.ctile[ol + idx]);
         dig = (u32)__ldg(&lv.digit[ol + idx]);
-        node = __ldcg(&lv.ptile[ol + idx]) + dig;
-        par = (l == 1) ? 0u : (u32)(1 + s_pre[l - 1]) + __ldg(&lv.par[ol + idx]);
+        const u32 pi = __ldg(&lv.par[ol + idx]);
+        node = ((l == 1) ? 0u : (__ldg(&lv.ctile[lv.off[l - 1] + pi]) & OSL_MASK)) + dig;
+        par = (l == 1) ? 0u : (u32)(1 + s_pre[l - 1]) + pi;
       }
       const uint4* tile = reinterpret_cast<const uint4*>(pool + 2 * (size_t)(ct & OSL_MASK));
 #pragma unroll
@@ -968,7 +1061,9 @@ k_levels(u32* pool, LevelArrays lv, const FrameState* fs, int D, int mode, const
       s_node[e] = node; s_ct[e] = ct; s_par[e] = (unsigned short)par; s_dig[e] = (unsigned short)dig;
     }
     __syncthreads();
-    for (int l = d; l >= 1; l--) {
+    PROF(38);
+    int l = d;
+    for (; l >= 1 && s_nl[l] > 32; l--) {
       const int n_l = s_nl[l], base = 1 + s_pre[l];
       for (int idx = tid; idx < n_l; idx += LEVEL_THREADS) {
         const int e = base + idx;
@@ -981,14 +1076,29 @@ k_levels(u32* pool, LevelArrays lv, const FrameState* fs, int D, int mode, const
       }
       __syncthreads();
     }
-    if (tid == 0 && s_nl[1] > 0) pool[1] = osl_average8(s_w1[0]);  // phase 3 (Q6)
+    if (tid < 32) {  // levels of at most 32 nodes: one warp, warp barriers
+      for (; l >= 1; l--) {
+        const int n_l = s_nl[l], base = 1 + s_pre[l];
+        if (tid < n_l) {
+          const int e = base + tid;
+          const u32 avg = osl_average8(s_w1[e]);
+          const u32 ct = s_ct[e];
+          u32* w = pool + 2 * (size_t)s_node[e];
+          w[1] = avg;
+          if (ct & OSL_NEWBIT) w[0] = OSL_FLAG | (ct & OSL_MASK);
+          s_w1[s_par[e]][s_dig[e]] = avg;
+        }
+        __syncwarp();
+      }
+      if (tid == 0 && s_nl[1] > 0) pool[1] = osl_average8(s_w1[0]);  // phase 3 (Q6)
+    }
+    PROF(39);
     return;
   }
   // fallback: the narrow part does not fit the staging area -> one block barrier + one L2 round trip per level
   for (; d >= 1; d--) {
     const int n_d = s_nl[d];
-    const size_t od = lv.off[d];
-    for (int idx = tid; idx < n_d; idx += LEVEL_THREADS) level_inner(pool, lv, od, idx);
+    for (int idx = tid; idx < n_d; idx += LEVEL_THREADS) level_inner(pool, lv, d, idx);
     __syncthreads();
   }
   if (tid == 0 && s_nl[1] > 0) {  // phase 3 (Q6)
@@ -1028,8 +1138,8 @@ osl_status osl_ensure_workspace(osl_svo* t, size_t n) {
     t->d_keysA[f] = t->d_keysB[f] = nullptr; t->d_payA[f] = t->d_payB[f] = nullptr;
   }
   cudaFree(t->d_m); cudaFree(t->d_s); cudaFree(t->d_blockcnt);
-  cudaFree(t->d_level_mem); cudaFree(t->d_keysC); cudaFree(t->d_payC);
-  t->d_keysC = nullptr; t->d_payC = nullptr;
+  cudaFree(t->d_level_mem); cudaFree(t->d_keysC); cudaFree(t->d_payC); cudaFree(t->d_start); cudaFree(t->d_flags);
+  t->d_keysC = nullptr; t->d_payC = nullptr; t->d_start = nullptr; t->d_flags = nullptr;
   t->d_m = t->d_s = nullptr;
   t->d_blockcnt = nullptr; t->d_level_mem = nullptr;
   t->ws_cap = 0;
@@ -1046,6 +1156,9 @@ osl_status osl_ensure_workspace(osl_svo* t, size_t n) {
   OSL_CUDA(cudaMalloc(&t->d_s, cap));
   const size_t nblocks = (cap + AN_THREADS - 1) / AN_THREADS;
   OSL_CUDA(cudaMalloc(&t->d_blockcnt, nblocks * OSL_NCOUNT(D) * sizeof(u32)));
+  OSL_CUDA(cudaMalloc(&t->d_start, cap * sizeof(u32)));
+  OSL_CUDA(cudaMalloc(&t->d_flags, nblocks * sizeof(u32)));
+  OSL_CUDA(cudaMemset(t->d_flags, 0, nblocks * sizeof(u32)));  // epoch-tagged (frame number + 1), never reset
   size_t total = 0;
   for (int d = 0; d <= D + 1; d++) {
     t->lv.off[d] = total;
@@ -1288,20 +1401,23 @@ osl_status osl_run_integrate(osl_svo* t, EmitParams& ep, const void* colors, cud
   }
   {
     const int grid = grid_for(exp_emit, AN_THREADS, t->structure_grid < coop_cap ? t->structure_grid : coop_cap);
-    const u64* a0 = skeys; u32* a1 = spay; const u32* a2 = t->d_pool; TreeParams a3 = t->tp; FrameState* a4 = t->d_fs;
-    uint8_t* a5 = t->d_m; uint8_t* a6 = t->d_s; u32* a7 = t->d_blockcnt; u32* a8 = t->d_scan_totals;
+    const u64* a0 = skeys; u32* a1 = spay; u32* a2 = t->d_pool; TreeParams a3 = t->tp; FrameState* a4 = t->d_fs;
+    uint8_t* a5 = t->d_m; uint8_t* a6 = t->d_s; u32* a6b = t->d_start; u32* a7 = t->d_blockcnt;
+    u32* a8 = t->d_scan_totals; u32* a8b = t->d_flags; u32 a8c = (u32)(t->seq + 1);
     LevelArrays a9 = t->lv; int a10 = ep.mode; int a11 = (int)t->cap_nodes; int a12 = n; int a13 = par;
     u64* a14 = t->d_split + par * BK_BUCKETS;
-    void* args[] = {&a0, &a1, &a2, &a3, &a4, &a5, &a6, &a7, &a8, &a9, &a10, &a11, &a12, &a13, &a14};
+    void* args[] = {&a0, &a1, &a2, &a3, &a4, &a5, &a6, &a6b, &a7, &a8, &a8b, &a8c, &a9, &a10, &a11, &a12, &a13, &a14};
     OSL_CUDA(cudaLaunchCooperativeKernel((void*)k_structure, dim3(grid), dim3(AN_THREADS), args, 0, st));
     OSL_LAUNCHED(1);
     if (timing) OSL_CUDA(cudaEventRecord(t->stage_ev[3], st));
   }
   if (n > 0) {
     const int grid = grid_for(exp_level, LEVEL_THREADS, t->levels_grid < coop_cap ? t->levels_grid : coop_cap);
-    u32* a0 = t->d_pool; LevelArrays a1 = t->lv; const FrameState* a2 = t->d_fs; int a3 = D; int a4 = ep.mode;
+    u32* a0 = t->d_pool; LevelArrays a1 = t->lv; const FrameState* a2 = t->d_fs;
+    u32* a2b = t->d_scan_totals + OSL_NCOUNT(OSL_MAXD);  // arrival counter of the one-sided barrier (zero at rest)
+    int a3 = D; int a4 = ep.mode;
     const uint8_t* a5 = ep.rgb; const float* a6 = (const float*)colors;
-    void* args[] = {&a0, &a1, &a2, &a3, &a4, &a5, &a6};
+    void* args[] = {&a0, &a1, &a2, &a2b, &a3, &a4, &a5, &a6};
     OSL_CUDA(cudaLaunchCooperativeKernel((void*)k_levels, dim3(grid), dim3(LEVEL_THREADS), args, LEVEL_SMEM, st));
     OSL_LAUNCHED(1);
   }
@@ -1317,5 +1433,12 @@ osl_status osl_run_integrate(osl_svo* t, EmitParams& ep, const void* colors, cud
   t->ring_head++;
   t->seq++;
   t->last_stream = st;
+  return OSL_OK;
+}
+
+extern "C" osl_status osl_debug_profile(unsigned long long* out, int n) {
+  if (!out || n < 0 || n > 64) return OSL_ERR_INVALID;
+  OSL_CUDA(cudaDeviceSynchronize());
+  OSL_CUDA(cudaMemcpyFromSymbol(out, g_osl_prof, sizeof(unsigned long long) * (size_t)n));
   return OSL_OK;
 }

@@ -159,6 +159,8 @@ struct osl_svo {
   u64* d_split;                // [2][BK_BUCKETS] splitters written by k_structure of frame f (set f & 1)
   int force_grid_sort;         // testing: always use the cooperative grid sort
   uint8_t *d_m, *d_s;
+  u32* d_start;       // per sorted key: node at the first depth it heads (k_structure phase A -> C)
+  u32* d_flags;       // per virtual block: epoch of the frame whose count vector is published
   u32* d_blockcnt;    // [blocks][NC]
   u32* d_cta_hist[OSL_FRONT];  // sort: [grid][256]
   u32* d_scan_totals; // k_scan: [NC_MAX] totals + 1 ticket word
