@@ -210,19 +210,30 @@ def run_ours(args):
         stage += np.array(svo.stage_times())
     stage /= 20.0
     svo.set_stage_timing(False)
-    # raycast of the fused map from the last camera pose (rays/s, device resident output)
+    # raycast of the fused map from the last camera pose: image rows dealt to the ranks in interleaved bands; at N > 1
+    # rank 0's tree is first replicated to every rank (NCCL broadcast of the flat pool), time = max over ranks
     view = (np.diag([-1.0, 1.0, -1.0, 1.0]) @ np.linalg.inv(poses[(Wm + K - 1) % RING].astype(np.float64))).astype(np.float32)
-    out = torch.empty((RAY_H, RAY_W, 4), dtype=torch.uint8, device="cuda")
+    if world > 1:
+        torch.cuda.synchronize()
+        pkg.shard.replicate_tree(svo, 0, device="cuda")
+    bands = pkg.shard.row_bands(RAY_H, world, rank)
+    outs = [torch.empty((rows, RAY_W, 4), dtype=torch.uint8, device="cuda") for _, rows in bands]
+
+    def render():
+        for (row0, rows), o in zip(bands, outs):
+            svo.raycast_rows(o, RAY_W, RAY_H, row0, rows, FOV, view, stream=sp)
+
     r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for _ in range(3):
-        svo.raycast_device(out, RAY_W, RAY_H, FOV, view, stream=sp)
+        render()
+    barrier(world)
     with torch.cuda.stream(stream):
         r0.record(stream)
-        for _ in range(5):
-            svo.raycast_device(out, RAY_W, RAY_H, FOV, view, stream=sp)
+        for _ in range(10):
+            render()
         r1.record(stream)
-    torch.cuda.synchronize()
-    ray_ms = r0.elapsed_time(r1) / 5
+    barrier(world)
+    ray_ms = max_over_ranks(r0.elapsed_time(r1) / 10, world)
     st = pkg.RaycastStats()
     svo.raycast(RAY_W, RAY_H, FOV, view, stats=st)
     svo.close()
@@ -248,7 +259,8 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": W * H * 5, "d2h_bytes_per_step": 608},
         "gpu_launches": int(launches),
         "raycast": {"mrays_per_s": RAY_W * RAY_H / (ray_ms / 1e3) / 1e6, "ms": ray_ms, "res": [RAY_W, RAY_H],
-                    "mode": "ref_exact", "steps_per_ray": st.steps / float(st.rays),
+                    "mode": "ref_exact", "rows": "interleaved bands over %d rank(s)" % world,
+                    "steps_per_ray": st.steps / float(st.rays),
                     "algorithmic_gbs": (4 * st.rays + 4 * st.visits + 4 * st.steps) / (ray_ms / 1e3) / 1e9},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": peak_src,

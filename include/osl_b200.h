@@ -131,6 +131,11 @@ osl_status osl_raycast(const osl_svo* t, uint8_t* d_out_rgba, int w, int h, floa
                        const osl_raycast_params* prm, void* stream);
 osl_status osl_raycast_host(const osl_svo* t, uint8_t* h_out_rgba, int w, int h, float fov_deg, const float view[16],
                             const osl_raycast_params* prm, osl_raycast_stats* stats, void* stream);
+/* Rows [row0, row0 + rows) of the w x h image only, written to d_out_rgba[0 .. rows*w*4): the multi-GPU
+ * decomposition of coneTraceSVO (rays are independent; every GPU holds the tree).  h_stats may be NULL. */
+osl_status osl_raycast_rows(const osl_svo* t, uint8_t* d_out_rgba, int w, int h, int row0, int rows, float fov_deg,
+                            const float view[16], const osl_raycast_params* prm, osl_raycast_stats* h_stats,
+                            void* stream);
 /* Raycast an arbitrary pool (SVO struct by value in the reference). */
 osl_status osl_raycast_pool(const uint32_t* d_pool, const float center[3], float half_edge, uint8_t* d_out_rgba, int w,
                             int h, float fov_deg, const float view[16], const osl_raycast_params* prm,

@@ -8,3 +8,4 @@ from .capi import Counters, OslError, RaycastParams, RaycastStats, lib  # noqa: 
 from .world import (SVO, BoundingBox, Octree, Scene, computeKeys, computePointCloudBoundingBox,  # noqa: F401
                     coneTraceSVO, generateVertexMap, transformVertexMap)
 from . import synth  # noqa: F401
+from . import shard  # noqa: F401

@@ -303,9 +303,10 @@ osl_status osl_get_counters(const osl_svo* tc, osl_counters* out) {
   return rc;
 }
 
-osl_status osl_raycast_pool(const uint32_t* d_pool, const float center[3], float half_edge, uint8_t* d_out_rgba, int w,
-                            int h, float fov_deg, const float view[16], const osl_raycast_params* prm,
-                            osl_raycast_stats* h_stats, void* stream) {
+static osl_status raycast_rows_pool(const uint32_t* d_pool, const float center[3], float half_edge,
+                                    uint8_t* d_out_rgba, int w, int h, int row0, int rows, float fov_deg,
+                                    const float view[16], const osl_raycast_params* prm, osl_raycast_stats* h_stats,
+                                    void* stream) {
   if (!d_pool || !center || !d_out_rgba || !view) return OSL_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   unsigned long long* d_stats = nullptr;
@@ -313,16 +314,34 @@ osl_status osl_raycast_pool(const uint32_t* d_pool, const float center[3], float
     OSL_CUDA(cudaMalloc(&d_stats, 16));
     OSL_CUDA(cudaMemsetAsync(d_stats, 0, 16, st));
   }
-  osl_status rc = osl_launch_raycast(d_pool, center, half_edge, d_out_rgba, w, h, fov_deg, view, prm, d_stats, st);
+  osl_status rc = osl_launch_raycast(d_pool, center, half_edge, d_out_rgba, w, h, row0, rows, fov_deg, view, prm,
+                                     d_stats, st);
   if (h_stats) {
     unsigned long long s[2] = {0, 0};
     cudaError_t e = cudaMemcpyAsync(s, d_stats, 16, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     cudaFree(d_stats);
     if (rc == OSL_OK) OSL_CUDA(e);
-    h_stats->rays = (int64_t)w * h; h_stats->steps = (int64_t)s[0]; h_stats->visits = (int64_t)s[1];
+    h_stats->rays = (int64_t)w * rows; h_stats->steps = (int64_t)s[0]; h_stats->visits = (int64_t)s[1];
   }
   return rc;
+}
+
+osl_status osl_raycast_pool(const uint32_t* d_pool, const float center[3], float half_edge, uint8_t* d_out_rgba, int w,
+                            int h, float fov_deg, const float view[16], const osl_raycast_params* prm,
+                            osl_raycast_stats* h_stats, void* stream) {
+  return raycast_rows_pool(d_pool, center, half_edge, d_out_rgba, w, h, 0, h, fov_deg, view, prm, h_stats, stream);
+}
+
+// Image rows [row0, row0 + rows) only, into d_out_rgba[0 .. rows*w*4): the multi-GPU decomposition of the raycast
+// (rays are independent; every GPU holds the tree).  Stream-ordered after the integrates on the same stream.
+osl_status osl_raycast_rows(const osl_svo* t, uint8_t* d_out_rgba, int w, int h, int row0, int rows, float fov_deg,
+                            const float view[16], const osl_raycast_params* prm, osl_raycast_stats* h_stats,
+                            void* stream) {
+  if (!t || (t->size == 0 && t->ring_head == 0)) return OSL_ERR_INVALID;
+  OSL_CUDA(cudaSetDevice(t->device));
+  const float c[3] = {t->tp.cx, t->tp.cy, t->tp.cz};
+  return raycast_rows_pool(t->d_pool, c, t->tp.half, d_out_rgba, w, h, row0, rows, fov_deg, view, prm, h_stats, stream);
 }
 
 // Stream-ordered after the integrates enqueued on the same stream (no host synchronisation needed).

@@ -27,6 +27,7 @@ struct RayParams {
   float fx, fy, start_dist, max_range;
   int mode;
   int W, H;
+  int row0, rows;          // image rows [row0, row0 + rows) are rendered into out[0 .. rows*W)
 };
 
 __device__ __forceinline__ float ray_length(float x, float y, float z) {
@@ -36,13 +37,43 @@ __device__ __forceinline__ float ray_length(float x, float y, float z) {
 // F2I.U32.TRUNC then byte store: NaN/negative -> 0, > 255 wraps mod 256 (Q16)
 __device__ __forceinline__ u32 f2u8(float f) { return __float2uint_rz(f) & 0xFFu; }
 
-__global__ void __launch_bounds__(128)
+// lod = (int)ceil(logf(q) / ln2f), the reference's expression (cone_tracing_kernels.cu:69).  For a finite positive
+// normal q = 1.m * 2^e whose mantissa is at least 2^-10 away from a power of two, log2(q) lies in
+// (e + 1.4e-3, e + 1 - 7e-4) while the float evaluation is off by at most |log2 q| * 2e-7 < 3e-5, so the result is
+// e + 1 and neither logf nor the division is needed.  Everything else takes the reference's expression verbatim.
+__device__ __forceinline__ int lod_depth(float q) {
+  const u32 b = __float_as_uint(q);
+  const u32 ex = b >> 23;  // sign + exponent
+  const u32 man = b & 0x7FFFFFu;
+  if (ex >= 1u && ex <= 254u && man > 0x2000u && man < 0x7FE000u) return (int)ex - 126;
+  return (int)ceilf(__fdiv_rn(logf(q), 0.693147182464599609375f));
+}
+
+// size / powf(2, depth) (cone_tracing_kernels.cu:126): powf(2, n) is exactly 2^n, and dividing by 2^n equals
+// multiplying by 2^-n (both are the correctly rounded size * 2^-n)
+__device__ __forceinline__ float node_step(float size, int depth) {
+  if (depth >= -126 && depth <= 126) return __fmul_rn(size, __uint_as_float((u32)(127 - depth) << 23));
+  return __fdiv_rn(size, powf(2.0f, (float)depth));
+}
+
+#define RAY_THREADS 128
+
+// One ray per thread, the whole march in registers.  Per step the reference descends from the root to the LOD level;
+// here a thread remembers one ancestor cell of its last sample (child pointer, centre, half size and the EXACT
+// half-open bounds the root descent implies for it: the centres compared on the way down) and resumes the descent
+// there whenever the next sample lies inside -- consecutive samples are half a leaf apart, so most steps walk 3-4
+// levels instead of 8-16.  The result is identical by construction: a point inside those bounds takes exactly the
+// same branches from the root.
+__global__ void __launch_bounds__(RAY_THREADS)
 k_raycast(const u32* __restrict__ pool, RayParams P, uchar4* __restrict__ out, unsigned long long* stats) {
+  __shared__ float s_af[256];  // (A - 127) / 127.0f for every alpha byte (Q9: no clamp)
+  for (int a = threadIdx.x; a < 256; a += RAY_THREADS) s_af[a] = __fdiv_rn((float)(a - 127), 127.0f);
+  __syncthreads();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  const int n = P.W * P.H;
+  const int n = P.W * P.rows;
   unsigned long long steps = 0, visits = 0;
   if (idx < n) {
-    const int px = idx % P.W, py = idx / P.W;
+    const int px = idx % P.W, py = P.row0 + idx / P.W;
     // createRays (cone_tracing_kernels.cu:29-51)
     const float magx = __fdiv_rn(__fmaf_rn(P.resx, -0.5f, (float)px), P.fx);
     const float magy = __fdiv_rn(__fmaf_rn(P.resy, -0.5f, (float)py), P.fy);
@@ -54,34 +85,86 @@ k_raycast(const u32* __restrict__ pool, RayParams P, uchar4* __restrict__ out, u
     float rx = __fmul_rn(__fmul_rn(dx, inv), P.start_dist);
     float ry = __fmul_rn(__fmul_rn(dy, inv), P.start_dist);
     float rz = __fmul_rn(__fmul_rn(dz, inv), P.start_dist);
+    float len = ray_length(rx, ry, rz);
+
+    const float INF = __int_as_float(0x7f800000);
+    // cached ancestor cell (level c_lvl >= 1; -1 = none)
+    int c_lvl = -1;
+    u32 c_child = 0, c_self = 0;
+    float c_cx = 0.f, c_cy = 0.f, c_cz = 0.f, c_e = 0.f;
+    float lox = -INF, hix = INF, loy = -INF, hiy = INF, loz = -INF, hiz = INF;
+    int last_lvl = 8;
 
     u32 vx = 0, vy = 0, vz = 0, vw = 0;  // uchar4 accumulator (mod-256 arithmetic)
     u32 result = 0;
     for (;;) {
       steps++;
       const float tx = __fadd_rn(P.ox, rx), ty = __fadd_rn(P.oy, ry), tz = __fadd_rn(P.oz, rz);
-      const float len = ray_length(rx, ry, rz);
       const float pix = __fmul_rn(len, P.pix_scale);
       const float q = __fdiv_rn(P.size, pix);
-      int depth = (int)ceilf(__fdiv_rn(logf(q), 0.693147182464599609375f));
+      int depth = lod_depth(q);
+
       u32 node = 0, child = 0;
       float cx = P.cx, cy = P.cy, cz = P.cz, e = P.size;
-      for (int i = 0; i < depth; i++) {
-        const bool bx = tx > cx, by = ty > cy, bz = tz > cz;
-        node = child + (u32)((int)bx + 2 * (int)by + 4 * (int)bz);
-        const u32 w0 = __ldg(pool + 2 * (size_t)node);
-        visits++;
-        if (!(w0 & OSL_FLAG)) { depth = i + 1; break; }
-        child = w0 & OSL_MASK;
-        e = __fmul_rn(e, 0.5f);
-        cx = __fadd_rn(cx, bx ? e : -e);
-        cy = __fadd_rn(cy, by ? e : -e);
-        cz = __fadd_rn(cz, bz ? e : -e);
+      int i = 0;
+      const bool hit = c_lvl >= 1 && depth >= c_lvl && tx > lox && !(tx > hix) && ty > loy && !(ty > hiy) &&
+                       tz > loz && !(tz > hiz);
+      float blx, bhx, bly, bhy, blz, bhz;  // bounds of the current cell while they are tracked
+      if (hit) {
+        i = c_lvl; node = c_self; child = c_child; cx = c_cx; cy = c_cy; cz = c_cz; e = c_e;
+        blx = lox; bhx = hix; bly = loy; bhy = hiy; blz = loz; bhz = hiz;
+        visits += (unsigned long long)c_lvl;  // the word0 reads the root descent would have made
+      } else {
+        blx = -INF; bhx = INF; bly = -INF; bhy = INF; blz = -INF; bhz = INF;
       }
+      bool open = true;  // the descent has not met a node without children
+      // tracked segment: down to level lt, remembering the bounds, then snapshot
+      const int lt = max(last_lvl - 3, 1);
+      if (i < lt) {
+        for (; i < depth && i < lt;) {
+          const bool bx = tx > cx, by = ty > cy, bz = tz > cz;
+          node = child + (u32)((int)bx + 2 * (int)by + 4 * (int)bz);
+          const u32 w0 = __ldg(pool + 2 * (size_t)node);
+          visits++;
+          if (!(w0 & OSL_FLAG)) { depth = i + 1; open = false; break; }
+          child = w0 & OSL_MASK;
+          if (bx) blx = fmaxf(blx, cx); else bhx = fminf(bhx, cx);
+          if (by) bly = fmaxf(bly, cy); else bhy = fminf(bhy, cy);
+          if (bz) blz = fmaxf(blz, cz); else bhz = fminf(bhz, cz);
+          e = __fmul_rn(e, 0.5f);
+          cx = __fadd_rn(cx, bx ? e : -e);
+          cy = __fadd_rn(cy, by ? e : -e);
+          cz = __fadd_rn(cz, bz ? e : -e);
+          i++;
+        }
+        if (open && i == lt) {
+          c_lvl = lt; c_self = node; c_child = child; c_cx = cx; c_cy = cy; c_cz = cz; c_e = e;
+          lox = blx; hix = bhx; loy = bly; hiy = bhy; loz = blz; hiz = bhz;
+        } else if (!hit) {
+          c_lvl = -1;
+        }
+      }
+      if (open) {
+        for (; i < depth;) {
+          const bool bx = tx > cx, by = ty > cy, bz = tz > cz;
+          node = child + (u32)((int)bx + 2 * (int)by + 4 * (int)bz);
+          const u32 w0 = __ldg(pool + 2 * (size_t)node);
+          visits++;
+          if (!(w0 & OSL_FLAG)) { depth = i + 1; break; }
+          child = w0 & OSL_MASK;
+          e = __fmul_rn(e, 0.5f);
+          cx = __fadd_rn(cx, bx ? e : -e);
+          cy = __fadd_rn(cy, by ? e : -e);
+          cz = __fadd_rn(cz, bz ? e : -e);
+          i++;
+        }
+      }
+      last_lvl = depth;
+
       if (P.mode == 0) { vx = vy = vz = vw = 0; }  // Q8
       const u32 ov = __ldg(pool + 2 * (size_t)node + 1);
       const int alpha = (int)(ov >> 24) - 127;  // Q9: the reference's max(0, unsigned) is a no-op
-      const float af = __fdiv_rn((float)alpha, 127.0f);
+      const float af = s_af[ov >> 24];
       vx = (vx + f2u8(__fmul_rn((float)(ov & 0xFFu), af))) & 0xFFu;
       vy = (vy + f2u8(__fmul_rn((float)((ov >> 8) & 0xFFu), af))) & 0xFFu;
       vz = (vz + f2u8(__fmul_rn((float)((ov >> 16) & 0xFFu), af))) & 0xFFu;
@@ -91,10 +174,11 @@ k_raycast(const u32* __restrict__ pool, RayParams P, uchar4* __restrict__ out, u
         result = vx | (vy << 8) | (vz << 16) | (255u << 24);
         break;
       }
-      const float nd = __fdiv_rn(P.size, powf(2.0f, (float)depth));
+      const float nd = node_step(P.size, depth);
       const float sc = __fdiv_rn(__fadd_rn(len, nd), len);
       rx = __fmul_rn(rx, sc); ry = __fmul_rn(ry, sc); rz = __fmul_rn(rz, sc);
-      if (ray_length(rx, ry, rz) > P.max_range) {
+      len = ray_length(rx, ry, rz);  // also the next step's |ray| (the reference recomputes the same value)
+      if (len > P.max_range) {
         const float f = __fdiv_rn(127.0f, (float)vw);
         result = f2u8(__fmul_rn((float)vx, f)) | (f2u8(__fmul_rn((float)vy, f)) << 8) |
                  (f2u8(__fmul_rn((float)vz, f)) << 16) | (255u << 24);
@@ -154,9 +238,10 @@ static void mat4_mul_vec4(const float m[16], const float v[4], float o[4]) {
 }
 
 osl_status osl_launch_raycast(const u32* d_pool, const float center[3], float half_edge, uint8_t* d_out, int w, int h,
-                              float fov_deg, const float view[16], const osl_raycast_params* prm,
+                              int row0, int rows, float fov_deg, const float view[16], const osl_raycast_params* prm,
                               unsigned long long* d_stats, cudaStream_t st) {
-  if (!d_pool || !d_out || w <= 0 || h <= 0) return OSL_ERR_INVALID;
+  if (!d_pool || !d_out || w <= 0 || h <= 0 || row0 < 0 || rows < 0 || row0 + rows > h) return OSL_ERR_INVALID;
+  if (rows == 0) return OSL_OK;
   osl_raycast_params p = {532.57f, 531.54f, 0.002f, 10.0f, 0};
   if (prm) p = *prm;
   // host part of coneTraceSVO (cone_tracing_kernels.cu:161-171)
@@ -178,9 +263,10 @@ osl_status osl_launch_raycast(const u32* d_pool, const float center[3], float ha
   P.pix_scale = tanf(fov_deg * 3.14159f / 180.0f) / (float)h;
   P.cx = center[0]; P.cy = center[1]; P.cz = center[2]; P.size = half_edge;
   P.fx = p.fx; P.fy = p.fy; P.start_dist = p.start_dist; P.max_range = p.max_range;
-  P.mode = p.mode; P.W = w; P.H = h;
-  const int n = w * h;
-  k_raycast<<<(n + 127) / 128, 128, 0, st>>>(d_pool, P, reinterpret_cast<uchar4*>(d_out), d_stats);
+  P.mode = p.mode; P.W = w; P.H = h; P.row0 = row0; P.rows = rows;
+  const int n = w * rows;
+  k_raycast<<<(n + RAY_THREADS - 1) / RAY_THREADS, RAY_THREADS, 0, st>>>(d_pool, P, reinterpret_cast<uchar4*>(d_out),
+                                                                         d_stats);
   OSL_LAUNCHED(1);
   OSL_CUDA(cudaGetLastError());
   return OSL_OK;

@@ -1,0 +1,107 @@
+"""Multi-GPU decomposition of the hot path, one process per GPU over torch.distributed.
+
+  integrate  one map per rank: every rank fuses its own RGB-D stream ("replicas", weak scaling, no data-path
+             collective).  Frames of ONE incremental map cannot be sharded over ranks (alpha += 2 and the colour blend
+             are order dependent per leaf); the spatially sharded single map needs only the exclusive prefix of the
+             per-pass split counts over ranks (`split_count_prefix`, the north-star's "NCCL only for the per-level
+             node-count prefix") and is designed in DESIGN.md section 7.
+  raycast    rays are independent: image rows are dealt to ranks in interleaved bands (`row_bands`), every rank holds
+             the whole tree (`replicate_tree`: broadcast of the flat 2*n uint32 pool, the reference's own wire format,
+             octree.cpp:113-169), `gather_image` assembles the picture on one rank.
+
+Works with the NCCL backend (CUDA tensors) and with gloo (CPU tensors; used by the CPU test-suite)."""
+import numpy as np
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
+def row_bands(h, world, rank, band=None):
+    """Rows of an h-row image owned by `rank`: interleaved bands of `band` rows (default: about 4 bands per rank, so
+    that sky / near-geometry imbalance averages out).  Returns a list of (row0, rows); over all ranks the bands
+    partition [0, h)."""
+    if world <= 1:
+        return [(0, h)]
+    if band is None:
+        band = max(1, -(-h // (4 * world)))
+    out = []
+    k = 0
+    for row0 in range(0, h, band):
+        if k % world == rank:
+            out.append((row0, min(band, h - row0)))
+        k += 1
+    return out
+
+
+def split_count_prefix(counts, group=None):
+    """counts: int64 tensor [P] of this rank's per-pass split counts (|codes[i]| restricted to the rank's key range;
+    rank order = key order).  Returns (base, total): base[i] = number of tiles allocated in pass i by lower ranks plus
+    everything allocated in earlier passes by ANY rank -- the rank's first global tile rank in pass i, reproducing the
+    reference's allocation order (pass, then numeric key; svo.cu:220,284) -- and total = tiles allocated by all ranks."""
+    import torch
+    dist = _dist()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    gathered = [torch.empty_like(counts) for _ in range(world)]
+    dist.all_gather(gathered, counts, group=group)
+    allc = torch.stack(gathered)                      # [world, P]
+    per_pass = allc.sum(dim=0)                        # [P]
+    pass_base = torch.cumsum(per_pass, 0) - per_pass  # exclusive over passes
+    lower = allc[:rank].sum(dim=0) if rank > 0 else torch.zeros_like(counts)
+    return pass_base + lower, int(per_pass.sum().item())
+
+
+def replicate_tree(svo, src=0, group=None, device=None):
+    """Broadcast the node pool of rank `src` to every rank and load it into `svo` (all ranks then hold the same tree).
+    `svo` needs .pool() -> uint32[2n] and .load(uint32[2n])."""
+    import torch
+    dist = _dist()
+    rank = dist.get_rank(group)
+    n = torch.zeros(1, dtype=torch.int64, device=device)
+    pool = None
+    if rank == src:
+        pool = np.ascontiguousarray(svo.pool(), dtype=np.uint32)
+        n[0] = pool.size
+    dist.broadcast(n, src, group=group)
+    words = int(n.item())
+    buf = torch.empty(words, dtype=torch.int32, device=device)
+    if rank == src:
+        buf.copy_(torch.from_numpy(pool.view(np.int32)))
+    dist.broadcast(buf, src, group=group)
+    if rank != src:
+        svo.load(buf.cpu().numpy().view(np.uint32))
+    return words // 2
+
+
+def gather_image(bands, tiles, h, w, dst=0, group=None):
+    """bands: this rank's [(row0, rows)], tiles: matching list of uint8 tensors [rows, w, 4].  Returns the h x w x 4
+    image on rank `dst` (None elsewhere)."""
+    import torch
+    dist = _dist()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = tiles[0].device if tiles else torch.device("cpu")
+    mine = torch.cat([t.reshape(-1) for t in tiles]) if tiles else torch.empty(0, dtype=torch.uint8, device=dev)
+    sizes = [sum(r for _, r in row_bands_like(bands, h, world, k)) * w * 4 for k in range(world)]
+    cap = max(sizes)
+    padded = torch.zeros(cap, dtype=torch.uint8, device=dev)
+    padded[:mine.numel()] = mine
+    gathered = [torch.empty(cap, dtype=torch.uint8, device=dev) for _ in range(world)]
+    dist.all_gather(gathered, padded, group=group)
+    if rank != dst:
+        return None
+    img = torch.empty((h, w, 4), dtype=torch.uint8, device=dev)
+    for k in range(world):
+        off = 0
+        for row0, rows in row_bands_like(bands, h, world, k):
+            img[row0:row0 + rows] = gathered[k][off:off + rows * w * 4].reshape(rows, w, 4)
+            off += rows * w * 4
+    return img
+
+
+def row_bands_like(bands, h, world, rank):
+    """the band layout of `rank` given this rank's bands (all ranks use the same band height)"""
+    band = bands[0][1] if bands and len(bands) > 1 else None
+    if band is None:
+        return row_bands(h, world, rank)
+    return row_bands(h, world, rank, band)

@@ -160,6 +160,13 @@ class SVO:
                                  stream), "osl_raycast")
         return out
 
+    def raycast_rows(self, out, w, h, row0, rows, fov=45.0, view=IDENTITY, mode=0, stream=None):
+        """rows [row0, row0+rows) of the w x h image into the CUDA tensor `out` (rows x w x 4 uint8)"""
+        prm = RaycastParams(532.57, 531.54, 0.002, 10.0, mode)
+        _check(lib().osl_raycast_rows(self._h, out.data_ptr(), w, h, row0, rows, float(fov), _f(mat_colmajor(view)),
+                                      C.byref(prm), None, stream), "osl_raycast_rows")
+        return out
+
     # ---- extraction ------------------------------------------------------------------------------------
     def extract_voxels(self, max_depth=None):
         torch = _torch()

@@ -356,3 +356,42 @@ def test_raycast_other_resolution_and_fov(P):
     img = svo.raycast(131, 57, 60.0, LOOK_PLUS_Z)
     want = orc.raycast(pool, center, half, 131, 57, 60.0, LOOK_PLUS_Z)
     assert np.array_equal(img, want)
+
+
+def test_raycast_rows_tile_the_full_image(P):
+    """the multi-GPU decomposition of the raycast: interleaved row bands rendered separately == the full image"""
+    import torch
+    svo, center, half = _saturated_tree(P)
+    w, h = 96, 72
+    full = svo.raycast(w, h, 45.0, LOOK_PLUS_Z)
+    img = np.zeros_like(full)
+    for world in (3,):
+        for rank in range(world):
+            for row0, rows in P.shard.row_bands(h, world, rank):
+                out = torch.empty((rows, w, 4), dtype=torch.uint8, device="cuda")
+                svo.raycast_rows(out, w, h, row0, rows, 45.0, LOOK_PLUS_Z)
+                img[row0:row0 + rows] = out.cpu().numpy()
+    assert np.array_equal(img, full)
+
+
+@pytest.mark.parametrize("D,res", [(12, (320, 240)), (16, (160, 120))])
+def test_raycast_deep_tree_matches_oracle(P, D, res):
+    """deep trees exercise the cached-ancestor descent (most steps resume 3-4 levels above the sample)"""
+    w, h = res
+    center, half = P.synth.tree_params(D)
+    fx, fy = P.synth.focal(w, h)
+    svo = P.SVO(center, half, D)
+    for k in range(3):
+        pose = P.synth.orbit_pose(40 * k)
+        depth, rgb = P.synth.make_frame(w, h, pose, seed=k)
+        for _ in range(22):
+            svo.integrate_depth(depth, rgb, fx, fy, pose)
+    pool = svo.pool()
+    for k in (0, 1):
+        view = view_for_pose(P.synth.orbit_pose(40 * k))
+        for mode in (0, 1):
+            st, cnt = P.RaycastStats(), orc.Counters()
+            img = svo.raycast(w, h, 45.0, view, mode=mode, stats=st)
+            want = orc.raycast(pool, center, half, w, h, 45.0, view, mode=mode, counters=cnt)
+            assert np.array_equal(img, want), "%d pixels differ" % np.count_nonzero(np.any(img != want, axis=2))
+            assert (st.steps, st.visits) == (cnt.ray_steps, cnt.ray_visits)
