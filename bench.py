@@ -190,6 +190,7 @@ def run_ours(args):
             e0.record(stream)
             for k in range(Wm, Wm + K):
                 fn(svo, k)  # asynchronous: the host only throttles when it is > 3 frames ahead
+            svo.join(sp)  # pipelined frames finish on the library's streams: order the timing event after them
             e1.record(stream)
         barrier(world)
         ms = e0.elapsed_time(e1)

@@ -111,6 +111,12 @@ osl_status osl_integrate_points(osl_svo* t, const float* d_xyz, const uint8_t* d
 /* Replaces svoFromVoxelGrid (svo.h:14, svo.cu:584): n glm::vec4 centres and n glm::vec4 colours (0..1 floats). */
 osl_status osl_integrate_voxels(osl_svo* t, const float* d_centers4, const float* d_colors4, int n, void* stream);
 
+/* Order `stream` after every integrate enqueued so far (device-side wait, the host does not block).  Strict-mode
+ * frames are stream-ordered anyway; pipelined frames finish on an internal stream, and this library's own entry
+ * points (raycast, extraction, download, view) join automatically -- call this before FOREIGN work on `stream` that
+ * reads the pool, or before recording a timing event. */
+osl_status osl_svo_join(osl_svo* t, void* stream);
+
 /* Wait for every integrate enqueued so far; returns a deferred error (e.g. OSL_ERR_POOL_OVERFLOW) if one occurred. */
 osl_status osl_svo_sync(osl_svo* t);
 

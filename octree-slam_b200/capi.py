@@ -20,7 +20,7 @@ STATUS = {0: "OSL_OK", -1: "OSL_ERR_INVALID", -2: "OSL_ERR_CUDA", -3: "OSL_ERR_O
 EXPORTS = [
     "osl_svo_create", "osl_svo_destroy", "osl_svo_reset", "osl_svo_set_quirks", "osl_svo_set_pipeline", "osl_svo_set_stage_timing", "osl_get_stage_times",
     "osl_integrate_depth", "osl_integrate_depth_host", "osl_integrate_points", "osl_integrate_voxels",
-    "osl_svo_sync", "osl_svo_view", "osl_svo_size", "osl_svo_download", "osl_svo_upload", "osl_get_counters",
+    "osl_svo_sync", "osl_svo_join", "osl_svo_view", "osl_svo_size", "osl_svo_download", "osl_svo_upload", "osl_get_counters",
     "osl_raycast", "osl_raycast_host", "osl_raycast_pool", "osl_raycast_rows", "osl_extract_voxels",
     "osl_generate_vertex_map", "osl_transform_vertex_map", "osl_point_cloud_bbox", "osl_compute_keys",
     "osl_status_string", "osl_last_cuda_error", "osl_version", "osl_launch_count", "osl_debug_profile",
@@ -79,6 +79,7 @@ def lib():
         "osl_integrate_points": (i32, [vp, vp, vp, i32, vp]),
         "osl_integrate_voxels": (i32, [vp, vp, vp, i32, vp]),
         "osl_svo_sync": (i32, [vp]),
+        "osl_svo_join": (i32, [vp, vp]),
         "osl_svo_view": (i32, [vp, C.POINTER(vp), C.POINTER(i32), fp, fp]),
         "osl_svo_size": (i32, [vp]),
         "osl_svo_download": (i32, [vp, vp, i32]),

@@ -68,8 +68,8 @@ osl_status osl_svo_create(osl_svo** out, const float center[3], float half_edge,
     for (int f = 0; f < OSL_FRONT && okh; f++)
       okh = cudaMalloc(&t->d_cta_hist[f], (size_t)t->sort_grid * 256 * sizeof(u32)) == cudaSuccess;
     if (!okh) { rc = OSL_ERR_OOM; break; }
-    if (cudaMalloc(&t->d_fs, sizeof(FrameState)) != cudaSuccess) { rc = OSL_ERR_OOM; break; }
-    if (cudaMemset(t->d_fs, 0, sizeof(FrameState)) != cudaSuccess) { rc = OSL_ERR_CUDA; break; }
+    if (cudaMalloc(&t->d_fs, sizeof(FrameState) * (1 + OSL_BACK)) != cudaSuccess) { rc = OSL_ERR_OOM; break; }
+    if (cudaMemset(t->d_fs, 0, sizeof(FrameState) * (1 + OSL_BACK)) != cudaSuccess) { rc = OSL_ERR_CUDA; break; }
     if (cudaMalloc(&t->d_scan_totals, (OSL_NCOUNT(OSL_MAXD) + 8) * sizeof(u32)) != cudaSuccess) { rc = OSL_ERR_OOM; break; }
     if (cudaMemset(t->d_scan_totals, 0, (OSL_NCOUNT(OSL_MAXD) + 8) * sizeof(u32)) != cudaSuccess) { rc = OSL_ERR_CUDA; break; }
     if (cudaMallocHost(&t->h_ring, sizeof(FrameState) * OSL_RING) != cudaSuccess) { rc = OSL_ERR_OOM; break; }
@@ -81,9 +81,12 @@ osl_status osl_svo_create(osl_svo** out, const float center[3], float half_edge,
       ok = cudaEventCreateWithFlags(&t->stage_copied[i], cudaEventDisableTiming) == cudaSuccess &&
            cudaEventCreateWithFlags(&t->stage_free[i], cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < OSL_FRONT && ok; i++)
-      ok = cudaEventCreateWithFlags(&t->front_done[i], cudaEventDisableTiming) == cudaSuccess &&
-           cudaEventCreateWithFlags(&t->back_done[i], cudaEventDisableTiming) == cudaSuccess;
+      ok = cudaEventCreateWithFlags(&t->emit_done[i], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&t->sort_done[i], cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < OSL_RING && ok; i++)
+      ok = cudaEventCreateWithFlags(&t->struct_ev[i], cudaEventDisableTiming) == cudaSuccess;
     if (ok) ok = cudaStreamCreateWithFlags(&t->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 4 && ok; i++) ok = cudaStreamCreateWithFlags(&t->pipe[i], cudaStreamNonBlocking) == cudaSuccess;
     if (!ok) { rc = OSL_ERR_CUDA; break; }
     rc = osl_grow_pool(t, reserve_nodes ? reserve_nodes : ((size_t)1 << 20), 0);
     if (rc) break;
@@ -102,12 +105,17 @@ void osl_svo_destroy(osl_svo* t) {
   for (int f = 0; f < OSL_FRONT; f++) {
     cudaFree(t->d_keysA[f]); cudaFree(t->d_keysB[f]); cudaFree(t->d_payA[f]); cudaFree(t->d_payB[f]);
     cudaFree(t->d_cta_hist[f]);
-    if (t->front_done[f]) cudaEventDestroy(t->front_done[f]);
-    if (t->back_done[f]) cudaEventDestroy(t->back_done[f]);
+    if (t->emit_done[f]) cudaEventDestroy(t->emit_done[f]);
+    if (t->sort_done[f]) cudaEventDestroy(t->sort_done[f]);
   }
+  for (int b = 0; b < OSL_BACK; b++) cudaFree(t->d_level_mem[b]);
+  for (int i = 0; i < OSL_RING; i++)
+    if (t->struct_ev[i]) cudaEventDestroy(t->struct_ev[i]);
+  for (int i = 0; i < 4; i++)
+    if (t->pipe[i]) cudaStreamDestroy(t->pipe[i]);
   cudaFree(t->d_m); cudaFree(t->d_s); cudaFree(t->d_blockcnt);
   cudaFree(t->d_keysC); cudaFree(t->d_payC); cudaFree(t->d_split); cudaFree(t->d_start); cudaFree(t->d_flags);
-  cudaFree(t->d_scan_totals); cudaFree(t->d_level_mem); cudaFree(t->d_fs);
+  cudaFree(t->d_scan_totals); cudaFree(t->d_fs);
   for (int i = 0; i < OSL_STAGES; i++) {
     cudaFree(t->d_depth_stage[i]); cudaFree(t->d_rgb_stage[i]);
     if (t->stage_copied[i]) cudaEventDestroy(t->stage_copied[i]);
@@ -127,7 +135,7 @@ osl_status osl_svo_reset(osl_svo* t) {
   OSL_CUDA(cudaSetDevice(t->device));
   osl_poll_results(t, true);
   OSL_CUDA(cudaDeviceSynchronize());
-  OSL_CUDA(cudaMemset(t->d_pool, 0, 64));
+  OSL_CUDA(cudaMemset(t->d_pool, 0, (size_t)(t->size > 8 ? t->size : 8) * 8));  // pool beyond the live nodes stays zero
   t->sticky_error = OSL_OK;
   memset(&t->counters, 0, sizeof(t->counters));
   return set_device_size(t, 0);
@@ -212,14 +220,15 @@ osl_status osl_integrate_depth_host(osl_svo* t, const uint16_t* h_depth, const u
   if (t->stage_seq >= OSL_STAGES) OSL_CUDA(cudaStreamWaitEvent(t->copy_stream, t->stage_free[slot], 0));
   OSL_CUDA(cudaMemcpyAsync(t->d_depth_stage[slot], h_depth, n * 2, cudaMemcpyHostToDevice, t->copy_stream));
   OSL_CUDA(cudaMemcpyAsync(t->d_rgb_stage[slot], h_rgb, n * 3, cudaMemcpyHostToDevice, t->copy_stream));
+  OSL_CUDA(cudaEventRecord(t->stage_copied[slot], t->copy_stream));  // k_emit (stream E) waits for it
   EmitParams ep;
   memset(&ep, 0, sizeof(ep));
   ep.depth = t->d_depth_stage[slot]; ep.rgb = t->d_rgb_stage[slot]; ep.w = w; ep.h = h; ep.fx = fx; ep.fy = fy;
   memcpy(ep.M, pose, sizeof(ep.M));
   ep.n = w * h; ep.mode = 0;
-  rc = osl_run_integrate(t, ep, nullptr, st, true);  // k_emit + k_sort follow the copies on the front stream
+  rc = osl_run_integrate(t, ep, nullptr, st, true);  // always pipelined: the library owns the copies
   if (rc) return rc;
-  OSL_CUDA(cudaEventRecord(t->stage_free[slot], st));
+  OSL_CUDA(cudaEventRecord(t->stage_free[slot], t->pipe[3]));  // the colours are last read by k_levels (stream V)
   t->stage_seq++;
   return OSL_OK;
 }
@@ -240,6 +249,12 @@ osl_status osl_integrate_voxels(osl_svo* t, const float* d_centers4, const float
   memset(&ep, 0, sizeof(ep));
   ep.pts = d_centers4; ep.stride = 4; ep.n = n; ep.mode = 2;
   return osl_run_integrate(t, ep, d_colors4, (cudaStream_t)stream, false);
+}
+
+osl_status osl_svo_join(osl_svo* t, void* stream) {
+  if (!t) return OSL_ERR_INVALID;
+  OSL_CUDA(cudaSetDevice(t->device));
+  return osl_join(t, (cudaStream_t)stream);
 }
 
 osl_status osl_svo_sync(osl_svo* t) {
@@ -285,11 +300,12 @@ osl_status osl_svo_upload(osl_svo* t, const uint32_t* h_pool, int n_nodes) {
   OSL_CUDA(cudaSetDevice(t->device));
   osl_poll_results(t, true);
   OSL_CUDA(cudaDeviceSynchronize());
+  const size_t old = (size_t)(t->size > 8 ? t->size : 8);
+  OSL_CUDA(cudaMemset(t->d_pool, 0, old * 8));  // keep the pool beyond the live nodes zero
   t->size = 0;
   osl_status rc = osl_grow_pool(t, (size_t)(n_nodes > 8 ? n_nodes : 8), 0);
   if (rc) return rc;
   if (n_nodes > 0) OSL_CUDA(cudaMemcpy(t->d_pool, h_pool, (size_t)n_nodes * 8, cudaMemcpyHostToDevice));
-  else OSL_CUDA(cudaMemset(t->d_pool, 0, 64));
   t->sticky_error = OSL_OK;
   return set_device_size(t, n_nodes);
 }
@@ -341,6 +357,8 @@ osl_status osl_raycast_rows(const osl_svo* t, uint8_t* d_out_rgba, int w, int h,
   if (!t || (t->size == 0 && t->ring_head == 0)) return OSL_ERR_INVALID;
   OSL_CUDA(cudaSetDevice(t->device));
   const float c[3] = {t->tp.cx, t->tp.cy, t->tp.cz};
+  osl_status jr = osl_join(const_cast<osl_svo*>(t), (cudaStream_t)stream);
+  if (jr) return jr;
   return raycast_rows_pool(t->d_pool, c, t->tp.half, d_out_rgba, w, h, row0, rows, fov_deg, view, prm, h_stats, stream);
 }
 
@@ -350,6 +368,8 @@ osl_status osl_raycast(const osl_svo* t, uint8_t* d_out_rgba, int w, int h, floa
   if (!t || (t->size == 0 && t->ring_head == 0)) return OSL_ERR_INVALID;
   OSL_CUDA(cudaSetDevice(t->device));
   const float c[3] = {t->tp.cx, t->tp.cy, t->tp.cz};
+  osl_status jr = osl_join(const_cast<osl_svo*>(t), (cudaStream_t)stream);
+  if (jr) return jr;
   return osl_raycast_pool(t->d_pool, c, t->tp.half, d_out_rgba, w, h, fov_deg, view, prm, nullptr, stream);
 }
 
@@ -358,7 +378,10 @@ osl_status osl_raycast_host(const osl_svo* t, uint8_t* h_out_rgba, int w, int h,
   if (!t || (t->size == 0 && t->ring_head == 0) || !h_out_rgba || w <= 0 || h <= 0) return OSL_ERR_INVALID;
   OSL_CUDA(cudaSetDevice(t->device));
   cudaStream_t st = (cudaStream_t)stream;
-  if (t->last_stream != st) OSL_CUDA(cudaStreamSynchronize(t->last_stream));
+  {
+    osl_status jr = osl_join(const_cast<osl_svo*>(t), st);
+    if (jr) return jr;
+  }
   uint8_t* d_out;
   OSL_CUDA(cudaMalloc(&d_out, (size_t)w * h * 4));
   const float c[3] = {t->tp.cx, t->tp.cy, t->tp.cz};

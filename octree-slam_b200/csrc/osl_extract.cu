@@ -129,7 +129,8 @@ extern "C" osl_status osl_extract_voxels(const osl_svo* t, int max_depth, float*
   {
     osl_status prc = osl_poll_results(const_cast<osl_svo*>(t), true);  // frames in flight define the node count
     if (prc) return prc;
-    if (t->last_stream != st) OSL_CUDA(cudaStreamSynchronize(t->last_stream));
+    osl_status jr = osl_join(const_cast<osl_svo*>(t), st);
+    if (jr) return jr;
   }
   if (t->size == 0) return OSL_OK;
   const size_t maxn = (size_t)t->size + 8;

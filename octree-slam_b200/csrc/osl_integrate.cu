@@ -591,6 +591,7 @@ __device__ __forceinline__ int walk_frontier(const u32* __restrict__ pool, u64 k
     if (!(w0 & OSL_FLAG)) return t;
     node = (w0 & OSL_MASK) + (u32)key_digit(key, D, t + 1);
   }
+  if (m + 1 == D) start = node;  // the leaf itself (its whole path exists)
   if (quirks && key_digit(key, D, D) == 7) {
     if (!(pool[2 * (size_t)node] & OSL_FLAG)) return D;
   }
@@ -703,15 +704,28 @@ __device__ __forceinline__ void assign_block(int vb, int n, const u64* __restric
   }
   __syncthreads();
   // pass 2: down the levels this key heads (d > m), resuming the walk of phase A at depth m+1; existing child tiles
-  // come from the pre-frame pool, new ones from their rank
+  // come from the pre-frame pool, new ones from their rank.  Every head also knows ITS OWN node index:
+  //   first headed level (d = m+1): the node phase A reached (start) when it pre-exists, else its slot in the tile
+  //     its parent received this frame -- that tile's rank follows from the same bucket counters, because the
+  //     parent's head (an earlier key with the same first m digits) has the same frontier depth s;
+  //   deeper levels: slot in the child tile found / allocated one iteration earlier.
+  // With it the head writes the child pointer of a node split this frame (svo.cu:269) right here, and k_levels
+  // needs no dependent look-ups.  New tiles only get their value words initialised (svo.cu:272-275): the pool
+  // beyond the live nodes is kept zero, so their word0 is already 0 and cannot race with the pointer writes.
   const int s_eff = (s == OSL_NONE) ? D : s;
   const u32 le = lt | (1u << lane);
-  u32 par_idx = 0;  // index (in level d-1) of the node on this key's path
+  u32 par_idx = 0;   // index (in level d-1) of the node on this key's path
+  u32 path_tile = 0; // tile holding the level-(d) nodes below this key's level-(d-1) node (root: tile 0)
   for (int d = 1; d <= D; d++) {
     const bool f = unique && m < d;
     const u32 bal = __ballot_sync(FULL, f);
     const bool sp = f && s != OSL_NONE && s <= d && (d <= D - 1 || s == D);
     const u32 peers = __match_any_sync(FULL, sp ? s : 0);
+    // same frontier depth among ALL unique keys of the warp (heads or not), for the parent-tile rank below
+    const u32 same_s = __match_any_sync(FULL, unique ? s : 0x100 + lane);
+    const u32 spmask = __ballot_sync(FULL, sp);
+    u32 self = 0;
+    if (f) self = (d == m + 1 && m < s_eff) ? node : path_tile + (u32)key_digit(k, D, d);
     u32 ct = 0xFFFFFFFFu;
     if (f) {
       if (d < D && d < s_eff) {
@@ -721,11 +735,17 @@ __device__ __forceinline__ void assign_block(int vb, int n, const u64* __restric
         const u32 rank = s_w[warp][OSL_CBKT(D, s, d)] + __popc(peers & lt);
         const u32 tile = size0 + 8u * rank;
         ct = tile | OSL_NEWBIT;
-        uint4* tp4 = reinterpret_cast<uint4*>(pool + 2 * (size_t)tile);  // svo.cu:272-275
-        const uint4 init = make_uint4(0u, OSL_EMPTY, 0u, OSL_EMPTY);
+        u32* tw = pool + 2 * (size_t)tile;
 #pragma unroll
-        for (int i = 0; i < 4; i++) tp4[i] = init;
+        for (int i = 0; i < 8; i++) tw[2 * i + 1] = OSL_EMPTY;
+        pool[2 * (size_t)self] = OSL_FLAG | tile;
       }
+      path_tile = ct & OSL_MASK;
+    } else if (unique && d == m && s != OSL_NONE && s <= d && d <= D - 1) {
+      // not a head here, but a head one level down whose parent was split this frame by an earlier key: the
+      // parent is the last level-d head with frontier s at or before this lane (or before this warp)
+      const u32 rank = s_w[warp][OSL_CBKT(D, s, d)] + __popc(same_s & spmask & le) - 1u;
+      path_tile = size0 + 8u * rank;
     }
     const u32 lbase = s_w[warp][OSL_CLVL(D, d)];
     if (f) {
@@ -733,6 +753,7 @@ __device__ __forceinline__ void assign_block(int vb, int n, const u64* __restric
       lv.ctile[o] = ct;
       lv.digit[o] = (uint8_t)key_digit(k, D, d);
       lv.par[o] = par_idx;
+      lv.self[o] = self;
       if (d == D) lv.src[lbase + __popc(bal & lt)] = (mode == 2) ? (u32)(n_invalid_front + j) : __ldcg(&pay[j]);
     }
     // the level-d node on this key's path: its own if it heads it, else the last one headed before it
@@ -744,8 +765,8 @@ __device__ __forceinline__ void assign_block(int vb, int n, const u64* __restric
 __device__ __forceinline__ u32 ld_vol(const u32* p) { return *(const volatile u32*)p; }
 
 __global__ void __launch_bounds__(AN_THREADS)
-k_structure(const u64* __restrict__ keys, u32* pay, u32* pool, TreeParams tp, FrameState* fs,
-            uint8_t* m8, uint8_t* s8, u32* start, u32* blockcnt, u32* totals, u32* flags, u32 epoch, LevelArrays lv,
+k_structure(const u64* __restrict__ keys, u32* pay, u32* pool, TreeParams tp, FrameState* fs, FrameState* fr,
+            FrameState* hr, uint8_t* m8, uint8_t* s8, u32* start, u32* blockcnt, u32* totals, u32* flags, u32 epoch, LevelArrays lv,
             int mode, int capacity, int n_in, int parity, u64* split_out) {
   cg::grid_group grid = cg::this_grid();
   __shared__ u32 s_w[AN_WARPS][NC_MAX];
@@ -871,34 +892,42 @@ k_structure(const u64* __restrict__ keys, u32* pay, u32* pool, TreeParams tp, Fr
   const long long after = (long long)size0 + 8ll * n_split;
   const bool overflow = after > (long long)capacity;
   if (blockIdx.x == 0) {
-    if (bs >= 1) fs->base[bs * (D + 1) + bd] = (int)(woff + incl - val);
+    if (bs >= 1) fr->base[bs * (D + 1) + bd] = (int)(woff + incl - val);
     if (tid < D) {  // |codes[i]| of reference pass i
       u32 pc = 0;
       for (int d = 1; d <= D; d++) {
         const int s = d - tid;
         if (s >= 1 && !(d == D && s != D)) pc += s_tot[OSL_CBKT(D, s, d)];
       }
-      fs->pass_count[tid] = (int)pc;
+      fr->pass_count[tid] = (int)pc;
     }
-    if (tid >= 1 && tid <= D) fs->n_level[tid] = (int)s_tot[OSL_CLVL(D, tid)];
+    if (tid >= 1 && tid <= D) fr->n_level[tid] = (int)s_tot[OSL_CLVL(D, tid)];
     if (tid == 0) {
-      fs->n_in = n_in; fs->n_valid = n_valid; fs->n_emit = n; fs->n_invalid_front = n_invalid_front;
+      fr->n_in = n_in; fr->n_valid = n_valid; fr->n_emit = n; fr->n_invalid_front = n_invalid_front;
       // every CTA that has work read these before it published / passed the barrier; a CTA that starts later
       // sees 0 entries and idles
       fs->acc_valid[parity] = 0; fs->acc_emit[parity] = 0;
-      fs->n_level[0] = s_tot[OSL_CLVL(D, 1)] > 0 ? 1 : 0;
-      fs->n_level[D + 1] = 0;
-      fs->n_split = (int)n_split;
-      fs->size_before = (int)size0;
-      fs->capacity = capacity;
-      fs->size_after = (int)min(after, (long long)0x7FFFFFFF);
-      fs->overflow = overflow ? 1 : 0;
-      fs->fresh = cur == 0 ? 1 : 0;
+      fr->n_level[0] = s_tot[OSL_CLVL(D, 1)] > 0 ? 1 : 0;
+      fr->n_level[D + 1] = 0;
+      fr->n_split = (int)n_split;
+      fr->size_before = (int)size0;
+      fr->capacity = capacity;
+      fr->size_after = (int)min(after, (long long)0x7FFFFFFF);
+      fr->overflow = overflow ? 1 : 0;
+      fr->fresh = cur == 0 ? 1 : 0;
       if (!overflow) fs->cur_size = (int)after;
       fs->frame_seq += 1;
+      fr->frame_seq = fs->frame_seq; fr->cur_size = overflow ? cur : (int)after;
     }
   }
   __syncthreads();
+  if (blockIdx.x == 0) {
+    // the result block also goes straight to the pinned host ring (no cudaMemcpyAsync per frame); the host reads it
+    // after the event that follows this frame's k_levels
+    const int* src = reinterpret_cast<const int*>(fr);
+    int* dst = reinterpret_cast<int*>(hr);
+    for (int i = tid; i < (int)(sizeof(FrameState) / sizeof(int)); i += AN_THREADS) dst[i] = __ldcg(src + i);
+  }
   PROF(21);
   if (overflow) return;
 
@@ -921,12 +950,11 @@ k_structure(const u64* __restrict__ keys, u32* pay, u32* pool, TreeParams tp, Fr
 }
 
 // ------------------------------------------------------------------------------------------------ k_levels
-// Bottom-up tree update, "scatter to parent": every touched node writes its new value (and, when it was split this
-// frame, its child pointer) into ITS slot of its parent's tile; one step per level, so a level costs one 64-byte tile
-// load per touched node and one or two 4-byte stores, all independent.  (Tiles allocated this frame were initialised
-// by k_structure.)
-//   phase 1  leaves: blend the winning input's colour into word1 (svo.cu:366-381 / :318-332), link Q3 tiles
-//   phase 2  d = D-1 .. 1: word1 = integer mean / max of the node's 8 children (svo.cu:384-441, Q5); link new tiles
+// Bottom-up VALUE update (word1 only; every word0 is final after k_structure, which is what lets the next frame's
+// k_structure overlap this kernel): every touched node writes its new value into its own slot; one step per level,
+// so a level costs one 64-byte tile load per touched node and one 4-byte store, all independent.
+//   phase 1  leaves: blend the winning input's colour into word1 (svo.cu:366-381 / :318-332)
+//   phase 2  d = D-1 .. 1: word1 = integer mean / max of the node's 8 children (svo.cu:384-441, Q5)
 //   phase 3  Q6: the root average lands in node 0's value word (svo.cu:399-412,439)
 // Cooperative.  Wide levels use the whole grid with a grid barrier in between.  As soon as a level fits one CTA
 // (n_level is monotone in d) the other CTAs signal "done" and exit, and CTA 0 finishes alone: it fetches the tiles
@@ -937,19 +965,11 @@ k_structure(const u64* __restrict__ keys, u32* pay, u32* pool, TreeParams tp, Fr
 #define LEVEL_STAGE 2048
 #define LEVEL_SMEM (LEVEL_STAGE * (32 + 4 + 4 + 2 + 2) + 64)
 
-// the node's own index: (tile that its parent points to) + its octant
-__device__ __forceinline__ u32 level_self(const LevelArrays& lv, int d, size_t od, int idx) {
-  const u32 dig = (u32)__ldg(&lv.digit[od + idx]);
-  if (d == 1) return dig;
-  return (__ldg(&lv.ctile[lv.off[d - 1] + __ldg(&lv.par[od + idx])]) & OSL_MASK) + dig;
-}
-
 __device__ __forceinline__ void level_leaf(u32* pool, const LevelArrays& lv, int D, int idx, int mode,
                                            const uint8_t* __restrict__ rgb, const float* __restrict__ colors4) {
   const size_t oD = lv.off[D];
-  const u32 ct = __ldg(&lv.ctile[oD + idx]);
   const u32 src = __ldg(&lv.src[idx]);
-  const u32 node = level_self(lv, D, oD, idx);
+  const u32 node = __ldg(&lv.self[oD + idx]);
   u32* w = pool + 2 * (size_t)node;
   const u32 cur = __ldcg(w + 1);
   u32 nv;
@@ -961,13 +981,12 @@ __device__ __forceinline__ void level_leaf(u32* pool, const LevelArrays& lv, int
     nv = osl_blend_u8(cur, __ldg(q), __ldg(q + 1), __ldg(q + 2));
   }
   w[1] = nv;
-  if (ct != 0xFFFFFFFFu) w[0] = OSL_FLAG | (ct & OSL_MASK);  // Q3: the leaf itself got 8 (phantom) children
 }
 
 __device__ __forceinline__ void level_inner(u32* pool, const LevelArrays& lv, int d, int idx) {
   const size_t od = lv.off[d];
   const u32 ct = __ldg(&lv.ctile[od + idx]);
-  const u32 node = level_self(lv, d, od, idx);
+  const u32 node = __ldg(&lv.self[od + idx]);
   const uint4* tile = reinterpret_cast<const uint4*>(pool + 2 * (size_t)(ct & OSL_MASK));
   u32 v[8];
 #pragma unroll
@@ -975,25 +994,23 @@ __device__ __forceinline__ void level_inner(u32* pool, const LevelArrays& lv, in
     const uint4 q = __ldcg(tile + i);
     v[2 * i] = q.y; v[2 * i + 1] = q.w;
   }
-  u32* w = pool + 2 * (size_t)node;
-  w[1] = osl_average8(v);
-  if (ct & OSL_NEWBIT) w[0] = OSL_FLAG | (ct & OSL_MASK);
+  pool[2 * (size_t)node + 1] = osl_average8(v);
 }
 
 __global__ void __launch_bounds__(LEVEL_THREADS)
-k_levels(u32* pool, LevelArrays lv, const FrameState* fs, u32* done, int D, int mode,
+k_levels(u32* pool, LevelArrays lv, const FrameState* fr, u32* done, int D, int mode,
          const uint8_t* __restrict__ rgb, const float* __restrict__ colors4) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(16) unsigned char s_raw[];
   __shared__ int s_nl[OSL_MAXD + 2];   // n_level[d]
   __shared__ int s_pre[OSL_MAXD + 2];  // s_pre[d] = sum of n_level[1..d-1]
-  if (fs->overflow) return;
+  if (fr->overflow) return;
   const int tid = threadIdx.x;
   const int gtid = blockIdx.x * LEVEL_THREADS + tid, gsz = gridDim.x * LEVEL_THREADS;
   if (tid == 0) {
     int run = 0;
     s_nl[0] = 0; s_pre[0] = 0;
-    for (int d = 1; d <= D; d++) { const int v = fs->n_level[d]; s_nl[d] = v; s_pre[d] = run; run += v; }
+    for (int d = 1; d <= D; d++) { const int v = fr->n_level[d]; s_nl[d] = v; s_pre[d] = run; run += v; }
     s_pre[D + 1] = run;
   }
   __syncthreads();
@@ -1048,9 +1065,8 @@ k_levels(u32* pool, LevelArrays lv, const FrameState* fs, u32* done, int D, int 
         const size_t ol = lv.off[l];
         ct = __ldg(&lv.ctile[ol + idx]);
         dig = (u32)__ldg(&lv.digit[ol + idx]);
-        const u32 pi = __ldg(&lv.par[ol + idx]);
-        node = ((l == 1) ? 0u : (__ldg(&lv.ctile[lv.off[l - 1] + pi]) & OSL_MASK)) + dig;
-        par = (l == 1) ? 0u : (u32)(1 + s_pre[l - 1]) + pi;
+        node = __ldg(&lv.self[ol + idx]);
+        par = (l == 1) ? 0u : (u32)(1 + s_pre[l - 1]) + __ldg(&lv.par[ol + idx]);
       }
       const uint4* tile = reinterpret_cast<const uint4*>(pool + 2 * (size_t)(ct & OSL_MASK));
 #pragma unroll
@@ -1068,10 +1084,7 @@ k_levels(u32* pool, LevelArrays lv, const FrameState* fs, u32* done, int D, int 
       for (int idx = tid; idx < n_l; idx += LEVEL_THREADS) {
         const int e = base + idx;
         const u32 avg = osl_average8(s_w1[e]);
-        const u32 ct = s_ct[e];
-        u32* w = pool + 2 * (size_t)s_node[e];
-        w[1] = avg;
-        if (ct & OSL_NEWBIT) w[0] = OSL_FLAG | (ct & OSL_MASK);
+        pool[2 * (size_t)s_node[e] + 1] = avg;
         s_w1[s_par[e]][s_dig[e]] = avg;
       }
       __syncthreads();
@@ -1082,10 +1095,7 @@ k_levels(u32* pool, LevelArrays lv, const FrameState* fs, u32* done, int D, int 
         if (tid < n_l) {
           const int e = base + tid;
           const u32 avg = osl_average8(s_w1[e]);
-          const u32 ct = s_ct[e];
-          u32* w = pool + 2 * (size_t)s_node[e];
-          w[1] = avg;
-          if (ct & OSL_NEWBIT) w[0] = OSL_FLAG | (ct & OSL_MASK);
+          pool[2 * (size_t)s_node[e] + 1] = avg;
           s_w1[s_par[e]][s_dig[e]] = avg;
         }
         __syncwarp();
@@ -1138,10 +1148,11 @@ osl_status osl_ensure_workspace(osl_svo* t, size_t n) {
     t->d_keysA[f] = t->d_keysB[f] = nullptr; t->d_payA[f] = t->d_payB[f] = nullptr;
   }
   cudaFree(t->d_m); cudaFree(t->d_s); cudaFree(t->d_blockcnt);
-  cudaFree(t->d_level_mem); cudaFree(t->d_keysC); cudaFree(t->d_payC); cudaFree(t->d_start); cudaFree(t->d_flags);
+  for (int b = 0; b < OSL_BACK; b++) { cudaFree(t->d_level_mem[b]); t->d_level_mem[b] = nullptr; }
+  cudaFree(t->d_keysC); cudaFree(t->d_payC); cudaFree(t->d_start); cudaFree(t->d_flags);
   t->d_keysC = nullptr; t->d_payC = nullptr; t->d_start = nullptr; t->d_flags = nullptr;
   t->d_m = t->d_s = nullptr;
-  t->d_blockcnt = nullptr; t->d_level_mem = nullptr;
+  t->d_blockcnt = nullptr;
   t->ws_cap = 0;
   const int D = t->tp.D;
   for (int f = 0; f < OSL_FRONT; f++) {
@@ -1159,20 +1170,23 @@ osl_status osl_ensure_workspace(osl_svo* t, size_t n) {
   OSL_CUDA(cudaMalloc(&t->d_start, cap * sizeof(u32)));
   OSL_CUDA(cudaMalloc(&t->d_flags, nblocks * sizeof(u32)));
   OSL_CUDA(cudaMemset(t->d_flags, 0, nblocks * sizeof(u32)));  // epoch-tagged (frame number + 1), never reset
-  size_t total = 0;
-  for (int d = 0; d <= D + 1; d++) {
-    t->lv.off[d] = total;
-    total += (d >= 1 && d <= D) ? level_cap(cap, d) : 0;
+  for (int b = 0; b < OSL_BACK; b++) {
+    LevelArrays& lv = t->lv[b];
+    size_t total = 0;
+    for (int d = 0; d <= D + 1; d++) {
+      lv.off[d] = total;
+      total += (d >= 1 && d <= D) ? level_cap(cap, d) : 0;
+    }
+    // ctile(4) + par(4) + self(4) + digit(1) bytes per level entry, src(4) per leaf
+    uint8_t* mem;
+    OSL_CUDA(cudaMalloc(&mem, total * 13 + cap * 4 + 64));
+    t->d_level_mem[b] = mem;
+    lv.ctile = reinterpret_cast<u32*>(mem);
+    lv.par = lv.ctile + total;
+    lv.self = lv.par + total;
+    lv.src = lv.self + total;
+    lv.digit = reinterpret_cast<uint8_t*>(lv.src + cap);
   }
-  // ctile(4) + par(4) + ptile(4) + digit(1) bytes per level entry, src(4) per leaf
-  uint8_t* mem;
-  OSL_CUDA(cudaMalloc(&mem, total * 13 + cap * 4 + 64));
-  t->d_level_mem = mem;
-  t->lv.ctile = reinterpret_cast<u32*>(mem);
-  t->lv.par = t->lv.ctile + total;
-  t->lv.ptile = t->lv.par + total;
-  t->lv.src = t->lv.ptile + total;
-  t->lv.digit = reinterpret_cast<uint8_t*>(t->lv.src + cap);
   t->ws_cap = cap;
   return OSL_OK;
 }
@@ -1182,14 +1196,17 @@ osl_status osl_integrate_init(osl_svo* t) {
   OSL_CUDA(cudaFuncSetAttribute((const void*)k_levels, cudaFuncAttributeMaxDynamicSharedMemorySize, LEVEL_SMEM));
   OSL_CUDA(cudaFuncSetAttribute((const void*)k_sort_bucket, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM));
   // default splitters: an even partition of the key space (valid, merely unbalanced) until a frame has written some
-  OSL_CUDA(cudaMalloc(&t->d_split, 2 * BK_BUCKETS * sizeof(u64)));
-  u64 h_split[2 * BK_BUCKETS];
-  for (int i = 0; i < 2 * BK_BUCKETS; i++)
+  OSL_CUDA(cudaMalloc(&t->d_split, OSL_FRONT * BK_BUCKETS * sizeof(u64)));
+  u64 h_split[OSL_FRONT * BK_BUCKETS];
+  for (int i = 0; i < OSL_FRONT * BK_BUCKETS; i++)
     h_split[i] = (u64)((i % BK_BUCKETS) + 1) * ((1ull << (3 * t->tp.D)) / BK_BUCKETS);
   OSL_CUDA(cudaMemcpy(t->d_split, h_split, sizeof(h_split), cudaMemcpyHostToDevice));
   return OSL_OK;
 }
 
+// Invariant: every word of the pool beyond the live nodes is ZERO (a tile allocated by a frame then already has
+// word0 = 0, so k_structure only writes its value words and the child pointers written by other threads cannot race
+// with an initialisation).
 osl_status osl_grow_pool(osl_svo* t, size_t want_nodes, cudaStream_t st) {
   if (want_nodes > ((size_t)1 << 30)) return OSL_ERR_POOL_OVERFLOW;
   if (want_nodes <= t->cap_nodes) return OSL_OK;
@@ -1198,13 +1215,12 @@ osl_status osl_grow_pool(osl_svo* t, size_t want_nodes, cudaStream_t st) {
   if (cap > ((size_t)1 << 30)) cap = (size_t)1 << 30;
   u32* np;
   OSL_CUDA(cudaMalloc(&np, cap * 8));
-  const size_t live = (size_t)(t->size > 8 ? t->size : 8);
+  const size_t live = t->d_pool ? (size_t)(t->size > 8 ? t->size : 8) : 0;
+  OSL_CUDA(cudaMemsetAsync(np + 2 * live, 0, (cap - live) * 8, st));
   if (t->d_pool) {
     OSL_CUDA(cudaMemcpyAsync(np, t->d_pool, live * 8, cudaMemcpyDeviceToDevice, st));
     OSL_CUDA(cudaStreamSynchronize(st));
     cudaFree(t->d_pool);
-  } else {
-    OSL_CUDA(cudaMemsetAsync(np, 0, 64, st));
   }
   t->d_pool = np;
   t->cap_nodes = cap;
@@ -1284,12 +1300,25 @@ static int grid_for(long long items, int per_cta, int cap) {
   return (int)g;
 }
 
-// One frame: k_emit -> k_sort -> k_structure -> k_levels (+ the 1.6 KB result block into the pinned ring).
-// `inputs_on_front`: the inputs were produced on the front stream (host frames staged by osl_integrate_depth_host).
-// Pipelined (t->pipeline or inputs_on_front): k_emit + k_sort of frame f run on the front stream and overlap
-// k_structure + k_levels of frame f-1 on `st`; two key-list buffers alternate.  Otherwise everything is enqueued on
-// `st` in order.  Cooperative grids are capped at num_sms/2 CTAs so that a front and a back cooperative kernel are
-// always co-resident (<= num_sms CTAs in total: a waiting CTA always finds an empty SM), hence no barrier deadlock.
+static osl_status drain_streams(osl_svo* t, cudaStream_t st) {
+  OSL_CUDA(cudaStreamSynchronize(st));
+  OSL_CUDA(cudaStreamSynchronize(t->copy_stream));
+  for (int i = 0; i < 4; i++) OSL_CUDA(cudaStreamSynchronize(t->pipe[i]));
+  return OSL_OK;
+}
+
+// One frame: k_emit -> k_sort(_bucket) -> k_structure -> k_link -> k_levels (+ the result block into the pinned ring).
+//
+// Strict mode (default for device inputs): everything is enqueued on the caller's stream, in order.
+// Pipelined mode (osl_svo_set_pipeline, and always for host frames whose copies the library owns): the four stages
+// run on four internal streams, so that consecutive frames overlap --
+//     E: k_emit(f+3)   So: k_sort(f+2)   S: k_structure + k_link (f+1)   V: k_levels(f)
+// k_structure(f+1) only needs the STRUCTURE of the tree after frame f (word0, final after k_link(f)); the value
+// fold of frame f (word1) runs concurrently.  Buffers: 3 key-list slots (E/So/S), 2 level-list + result slots (S/V).
+// The caller's stream is made to wait for the frame (cudaStreamWaitEvent), so work enqueued on it afterwards sees the
+// updated tree.  Cooperative grids are capped at num_sms/3 CTAs in this mode: at most three cooperative kernels
+// (grid sort, k_structure, k_levels) run concurrently, <= num_sms CTAs in total, so a waiting CTA always finds an
+// empty SM and no grid barrier can deadlock.
 osl_status osl_run_integrate(osl_svo* t, EmitParams& ep, const void* colors, cudaStream_t st, bool inputs_on_front) {
   const int n = ep.n;
   const int D = t->tp.D;
@@ -1299,8 +1328,8 @@ osl_status osl_run_integrate(osl_svo* t, EmitParams& ep, const void* colors, cud
   if ((size_t)(n > 0 ? n : 1) > t->ws_cap) {
     rc = osl_poll_results(t, true);  // the workspace is in use by frames in flight
     if (rc) return rc;
-    OSL_CUDA(cudaStreamSynchronize(st));
-    OSL_CUDA(cudaStreamSynchronize(t->copy_stream));
+    rc = drain_streams(t, st);
+    if (rc) return rc;
     rc = osl_ensure_workspace(t, (size_t)(n > 0 ? n : 1));
     if (rc) return rc;
   }
@@ -1324,7 +1353,8 @@ osl_status osl_run_integrate(osl_svo* t, EmitParams& ep, const void* colors, cud
     if (want > t->cap_nodes) {  // grow (rare, geometric): needs the exact size, i.e. an idle pipeline
       rc = osl_poll_results(t, true);
       if (rc) return rc;
-      OSL_CUDA(cudaStreamSynchronize(st));
+      rc = drain_streams(t, st);
+      if (rc) return rc;
       rc = osl_grow_pool(t, want, st);
       if (rc) return rc;
       continue;
@@ -1334,18 +1364,25 @@ osl_status osl_run_integrate(osl_svo* t, EmitParams& ep, const void* colors, cud
     if (rc) return rc;
   }
 
-  const int par = (int)(t->seq % OSL_FRONT);
-  const bool piped = (t->pipeline || inputs_on_front) && n > 0;
-  cudaStream_t fst = piped ? t->copy_stream : st;
-  if (piped && !t->front_active) {
-    // first pipelined frame: earlier frames used uncapped cooperative grids, keep them out of the overlap window
-    if (t->seq >= 1) OSL_CUDA(cudaStreamWaitEvent(fst, t->back_done[par ^ 1], 0));
-    t->front_active = 1;
+  const unsigned long long f = t->seq;
+  const int fslot = (int)(f % OSL_FRONT), bslot = (int)(f % OSL_BACK);
+  const bool piped = t->pipeline || inputs_on_front;
+  cudaStream_t sE = piped ? t->pipe[0] : st, sSo = piped ? t->pipe[1] : st, sS = piped ? t->pipe[2] : st,
+               sV = piped ? t->pipe[3] : st;
+  if (f > 0 && (piped != (t->last_piped != 0) || (!piped && st != t->last_stream))) {
+    // mode (or stream) switch: the previous frame must be complete before anything of this one starts
+    cudaEvent_t prev = t->ring_ev[(f - 1) % OSL_RING];
+    OSL_CUDA(cudaStreamWaitEvent(sE, prev, 0));
+    if (piped) {
+      OSL_CUDA(cudaStreamWaitEvent(sSo, prev, 0));
+      OSL_CUDA(cudaStreamWaitEvent(sS, prev, 0));
+      OSL_CUDA(cudaStreamWaitEvent(sV, prev, 0));
+    }
   }
-  const int coop_cap = t->front_active ? (t->num_sms / 2 > 0 ? t->num_sms / 2 : 1) : 0x7FFFFFFF;
+  const int coop_cap = piped ? (t->num_sms / 3 > 0 ? t->num_sms / 3 : 1) : 0x7FFFFFFF;
   const int passes = (3 * D + 7) / 8;
-  u64* skeys = (passes & 1) ? t->d_keysB[par] : t->d_keysA[par];
-  u32* spay = (passes & 1) ? t->d_payB[par] : t->d_payA[par];
+  u64* skeys = (passes & 1) ? t->d_keysB[fslot] : t->d_keysA[fslot];
+  u32* spay = (passes & 1) ? t->d_payB[fslot] : t->d_payA[fslot];
   bool use_bucket = false;
   // expected number of sorted entries / widest level, from the last completed frame (grid sizing only: every
   // kernel is grid-stride, a wrong guess costs time, not correctness)
@@ -1356,18 +1393,21 @@ osl_status osl_run_integrate(osl_svo* t, EmitParams& ep, const void* colors, cud
     exp_level = (long long)(t->hint_level * scale) + LEVEL_THREADS;
     if (exp_emit > n) exp_emit = n;
     if (exp_level > n) exp_level = n;
-    // small key list and splitters of frame seq-2 in place -> barrier-free bucket sort
-    use_bucket = t->seq >= 2 && exp_emit <= (long long)BK_BUCKETS * BK_CAP / 2 && !t->force_grid_sort;
+    // small key list and splitters of frame f - OSL_FRONT in place -> barrier-free bucket sort
+    use_bucket = f >= OSL_FRONT && exp_emit <= (long long)BK_BUCKETS * BK_CAP / 2 && !t->force_grid_sort;
   }
-  if (use_bucket) { skeys = t->d_keysB[par]; spay = t->d_payB[par]; }
+  if (use_bucket) { skeys = t->d_keysB[fslot]; spay = t->d_payB[fslot]; }
+  FrameState* fs = t->d_fs;              // persistent part
+  FrameState* fr = t->d_fs + 1 + bslot;  // this frame's result block
+  const LevelArrays& lv = t->lv[bslot];
 
   const bool timing = t->stage_timing && !piped && n > 0;
   if (timing) OSL_CUDA(cudaEventRecord(t->stage_ev[0], st));
   if (n > 0) {
-    if (piped) {
-      // the front buffer `par` was last read by k_structure/k_levels of frame seq-2
-      if (t->seq >= OSL_FRONT) OSL_CUDA(cudaStreamWaitEvent(fst, t->back_done[par], 0));
-    }
+    // ---- E: back-projection, keys, tile-local de-duplication
+    if (piped && f >= OSL_FRONT)  // the key-list slot was last read by k_structure of frame f - 3
+      OSL_CUDA(cudaStreamWaitEvent(sE, t->struct_ev[(f - OSL_FRONT) % OSL_RING], 0));
+    if (inputs_on_front) OSL_CUDA(cudaStreamWaitEvent(sE, t->stage_copied[t->stage_seq % OSL_STAGES], 0));
     int vec_ok = 0;
     int etiles;
     if (ep.mode == 0) {
@@ -1378,61 +1418,87 @@ osl_status osl_run_integrate(osl_svo* t, EmitParams& ep, const void* colors, cud
     } else {
       etiles = (n + EMIT_TILE - 1) / EMIT_TILE;
     }
-    k_emit<<<etiles, EMIT_THREADS, EMIT_SMEM, fst>>>(ep, t->tp, vec_ok, t->d_keysA[par], t->d_payA[par], t->d_fs, par);
+    k_emit<<<etiles, EMIT_THREADS, EMIT_SMEM, sE>>>(ep, t->tp, vec_ok, t->d_keysA[fslot], t->d_payA[fslot], fs, fslot);
     OSL_LAUNCHED(1);
     if (timing) OSL_CUDA(cudaEventRecord(t->stage_ev[1], st));
+    // ---- So: sort
+    if (piped) {
+      OSL_CUDA(cudaEventRecord(t->emit_done[fslot], sE));
+      OSL_CUDA(cudaStreamWaitEvent(sSo, t->emit_done[fslot], 0));
+    }
     if (use_bucket) {
-      k_sort_bucket<<<BK_BUCKETS, BK_THREADS, BK_SMEM, fst>>>(t->d_keysA[par], t->d_payA[par], t->d_keysB[par],
-                                                              t->d_payB[par], t->d_keysC, t->d_payC, t->d_fs,
-                                                              t->d_split + par * BK_BUCKETS, passes, par);
+      k_sort_bucket<<<BK_BUCKETS, BK_THREADS, BK_SMEM, sSo>>>(t->d_keysA[fslot], t->d_payA[fslot], t->d_keysB[fslot],
+                                                              t->d_payB[fslot], t->d_keysC, t->d_payC, fs,
+                                                              t->d_split + fslot * BK_BUCKETS, passes, fslot);
     } else {
       const int grid = grid_for(exp_emit, SORT_TILE, t->sort_grid < coop_cap ? t->sort_grid : coop_cap);
-      u64* kA = t->d_keysA[par]; u32* pA = t->d_payA[par]; u64* kB = t->d_keysB[par]; u32* pB = t->d_payB[par];
-      u32* ch = t->d_cta_hist[par]; const FrameState* fsc = t->d_fs; int pp = passes; int parity = par;
+      u64* kA = t->d_keysA[fslot]; u32* pA = t->d_payA[fslot]; u64* kB = t->d_keysB[fslot]; u32* pB = t->d_payB[fslot];
+      u32* ch = t->d_cta_hist[fslot]; const FrameState* fsc = fs; int pp = passes; int parity = fslot;
       void* args[] = {&kA, &pA, &kB, &pB, &ch, &fsc, &pp, &parity};
-      OSL_CUDA(cudaLaunchCooperativeKernel((void*)k_sort, dim3(grid), dim3(SORT_THREADS), args, 0, fst));
+      OSL_CUDA(cudaLaunchCooperativeKernel((void*)k_sort, dim3(grid), dim3(SORT_THREADS), args, 0, sSo));
     }
     OSL_LAUNCHED(1);
     if (timing) OSL_CUDA(cudaEventRecord(t->stage_ev[2], st));
     if (piped) {
-      OSL_CUDA(cudaEventRecord(t->front_done[par], fst));
-      OSL_CUDA(cudaStreamWaitEvent(st, t->front_done[par], 0));
+      OSL_CUDA(cudaEventRecord(t->sort_done[fslot], sSo));
+      OSL_CUDA(cudaStreamWaitEvent(sS, t->sort_done[fslot], 0));
     }
   }
+  // ---- S: structure plan + child pointers
+  if (piped && f >= OSL_BACK)  // level lists + result block of this slot were last read by k_levels of frame f - 2
+    OSL_CUDA(cudaStreamWaitEvent(sS, t->ring_ev[(f - OSL_BACK) % OSL_RING], 0));
   {
     const int grid = grid_for(exp_emit, AN_THREADS, t->structure_grid < coop_cap ? t->structure_grid : coop_cap);
-    const u64* a0 = skeys; u32* a1 = spay; u32* a2 = t->d_pool; TreeParams a3 = t->tp; FrameState* a4 = t->d_fs;
+    const u64* a0 = skeys; u32* a1 = spay; u32* a2 = t->d_pool; TreeParams a3 = t->tp; FrameState* a4 = fs;
+    FrameState* a4b = fr;
     uint8_t* a5 = t->d_m; uint8_t* a6 = t->d_s; u32* a6b = t->d_start; u32* a7 = t->d_blockcnt;
-    u32* a8 = t->d_scan_totals; u32* a8b = t->d_flags; u32 a8c = (u32)(t->seq + 1);
-    LevelArrays a9 = t->lv; int a10 = ep.mode; int a11 = (int)t->cap_nodes; int a12 = n; int a13 = par;
-    u64* a14 = t->d_split + par * BK_BUCKETS;
-    void* args[] = {&a0, &a1, &a2, &a3, &a4, &a5, &a6, &a6b, &a7, &a8, &a8b, &a8c, &a9, &a10, &a11, &a12, &a13, &a14};
-    OSL_CUDA(cudaLaunchCooperativeKernel((void*)k_structure, dim3(grid), dim3(AN_THREADS), args, 0, st));
+    u32* a8 = t->d_scan_totals; u32* a8b = t->d_flags; u32 a8c = (u32)(f + 1);
+    LevelArrays a9 = lv; int a10 = ep.mode; int a11 = (int)t->cap_nodes; int a12 = n; int a13 = fslot;
+    u64* a14 = t->d_split + fslot * BK_BUCKETS;
+    FrameState* a4c = &t->h_ring[f % OSL_RING];  // pinned host memory, device-accessible (UVA)
+    void* args[] = {&a0, &a1, &a2, &a3, &a4, &a4b, &a4c, &a5, &a6, &a6b, &a7, &a8, &a8b, &a8c, &a9, &a10, &a11, &a12,
+                    &a13, &a14};
+    OSL_CUDA(cudaLaunchCooperativeKernel((void*)k_structure, dim3(grid), dim3(AN_THREADS), args, 0, sS));
     OSL_LAUNCHED(1);
     if (timing) OSL_CUDA(cudaEventRecord(t->stage_ev[3], st));
+    if (piped) {
+      OSL_CUDA(cudaEventRecord(t->struct_ev[f % OSL_RING], sS));
+      OSL_CUDA(cudaStreamWaitEvent(sV, t->struct_ev[f % OSL_RING], 0));
+    }
   }
+  // ---- V: values, bottom-up
   if (n > 0) {
     const int grid = grid_for(exp_level, LEVEL_THREADS, t->levels_grid < coop_cap ? t->levels_grid : coop_cap);
-    u32* a0 = t->d_pool; LevelArrays a1 = t->lv; const FrameState* a2 = t->d_fs;
+    u32* a0 = t->d_pool; LevelArrays a1 = lv; const FrameState* a2 = fr;
     u32* a2b = t->d_scan_totals + OSL_NCOUNT(OSL_MAXD);  // arrival counter of the one-sided barrier (zero at rest)
     int a3 = D; int a4 = ep.mode;
     const uint8_t* a5 = ep.rgb; const float* a6 = (const float*)colors;
     void* args[] = {&a0, &a1, &a2, &a2b, &a3, &a4, &a5, &a6};
-    OSL_CUDA(cudaLaunchCooperativeKernel((void*)k_levels, dim3(grid), dim3(LEVEL_THREADS), args, LEVEL_SMEM, st));
+    OSL_CUDA(cudaLaunchCooperativeKernel((void*)k_levels, dim3(grid), dim3(LEVEL_THREADS), args, LEVEL_SMEM, sV));
     OSL_LAUNCHED(1);
   }
   if (timing) { OSL_CUDA(cudaEventRecord(t->stage_ev[4], st)); t->stage_valid = 1; }
-  OSL_CUDA(cudaEventRecord(t->back_done[par], st));
-  // result block -> pinned ring (read lazily; the caller never waits for it unless it asks for sizes/counters)
-  const int slot = (int)(t->ring_head % OSL_RING);
-  OSL_CUDA(cudaMemcpyAsync(&t->h_ring[slot], t->d_fs, sizeof(FrameState), cudaMemcpyDeviceToHost, st));
-  OSL_CUDA(cudaEventRecord(t->ring_ev[slot], st));
+  // end of frame: k_structure has written the result block into the pinned ring slot; the host reads it lazily
+  // after this event (the caller never waits for it unless it asks for sizes / counters)
+  const int slot = (int)(f % OSL_RING);
+  OSL_CUDA(cudaEventRecord(t->ring_ev[slot], sV));
+  t->join_pending = piped ? 1 : 0;  // other streams are ordered after the pipeline by osl_svo_join (lazily)
   t->ring_headroom[slot] = headroom;
   t->ring_mode[slot] = ep.mode;
   t->inflight_headroom += headroom;
   t->ring_head++;
   t->seq++;
   t->last_stream = st;
+  t->last_piped = piped ? 1 : 0;
+  return OSL_OK;
+}
+
+// Orders `stream` after every frame enqueued so far (one cudaStreamWaitEvent).  Strict-mode frames are already
+// stream-ordered; pipelined frames complete on an internal stream.
+osl_status osl_join(osl_svo* t, cudaStream_t st) {
+  if (t->seq == 0) return OSL_OK;
+  if (t->join_pending || st != t->last_stream)
+    OSL_CUDA(cudaStreamWaitEvent(st, t->ring_ev[(t->seq - 1) % OSL_RING], 0));
   return OSL_OK;
 }
 

@@ -16,17 +16,18 @@ typedef unsigned int u32;
 
 #define OSL_MAXD OSL_MAX_DEPTH
 #define OSL_RING 8    // per-frame result blocks in flight
-#define OSL_STAGES 3  // device staging slots of the *_host entry points
+#define OSL_STAGES 6  // device staging slots of the *_host entry points (a frame's colours live until its k_levels)
 #define OSL_PIPE_DEPTH 3  // frames in flight the pool head-room is sized for
-#define OSL_FRONT 2   // key-list buffers: emit+sort of frame f+1 overlap structure+levels of frame f
+#define OSL_FRONT 3   // key-list slots (k_emit / k_sort / k_structure of three consecutive frames overlap)
+#define OSL_BACK 2    // level-list + result-block slots (k_structure of frame f+1 overlaps k_levels of frame f)
 #define OSL_NCOUNT(D) ((D) + ((D) + 1) * ((D) + 1))
 #define OSL_CLVL(D, d) ((d)-1)
 #define OSL_CBKT(D, s, d) ((D) + (s) * ((D) + 1) + (d))
 
 // Per-frame device-side state; copied to pinned host memory after the structure phase.
 struct FrameState {
-  int acc_valid[2];  // [frame parity] accumulated by k_emit (atomicAdd), consumed and zeroed by k_structure
-  int acc_emit[2];   // [frame parity] entries k_emit appended to the key list
+  int acc_valid[OSL_FRONT];  // [key-list slot] accumulated by k_emit (atomicAdd), consumed and zeroed by k_structure
+  int acc_emit[OSL_FRONT];   // [key-list slot] entries k_emit appended to the key list
   int n_in;         // inputs
   int n_valid;      // V  (inputs with a valid key)
   int n_emit;       // entries sorted (modes 0/1: after the tile-local de-duplication; mode 2: == n_valid)
@@ -47,7 +48,7 @@ struct FrameState {
 struct LevelArrays {   // dense per-level lists of the nodes a frame touches, level d at offset off[d]
   u32* ctile;          // child tile index | OSL_NEWBIT ; 0xFFFFFFFF = none (unsplit leaf)
   u32* par;            // index (in level d-1) of the parent node
-  u32* ptile;          // tile that holds the node itself (= parent's ctile; resolved by k_levels phase 0)
+  u32* self;           // the node's own index in the pool
   u32* src;            // leaves only: winning input (pixel index / sorted position), indexed by the level-D index
   uint8_t* digit;      // octant of the node inside its parent's tile
   size_t off[OSL_MAXD + 2];
@@ -156,7 +157,7 @@ struct osl_svo {
   u64 *d_keysA[OSL_FRONT], *d_keysB[OSL_FRONT];  // sort ping/pong per front buffer
   u32 *d_payA[OSL_FRONT], *d_payB[OSL_FRONT];
   u64* d_keysC; u32* d_payC;   // k_sort_bucket slow-path scratch
-  u64* d_split;                // [2][BK_BUCKETS] splitters written by k_structure of frame f (set f & 1)
+  u64* d_split;                // [OSL_FRONT][BK_BUCKETS] splitters written by k_structure of frame f (set f % OSL_FRONT)
   int force_grid_sort;         // testing: always use the cooperative grid sort
   uint8_t *d_m, *d_s;
   u32* d_start;       // per sorted key: node at the first depth it heads (k_structure phase A -> C)
@@ -164,9 +165,9 @@ struct osl_svo {
   u32* d_blockcnt;    // [blocks][NC]
   u32* d_cta_hist[OSL_FRONT];  // sort: [grid][256]
   u32* d_scan_totals; // k_scan: [NC_MAX] totals + 1 ticket word
-  LevelArrays lv;
-  void* d_level_mem;
-  FrameState* d_fs;
+  LevelArrays lv[OSL_BACK];
+  void* d_level_mem[OSL_BACK];
+  FrameState* d_fs;                      // [0] persistent part (slot counters, cur_size), [1 + b] result block of slot b
   FrameState* h_ring;                    // pinned ring of per-frame result blocks
   cudaEvent_t ring_ev[OSL_RING];
   size_t ring_headroom[OSL_RING];
@@ -175,12 +176,15 @@ struct osl_svo {
   size_t inflight_headroom;              // worst-case node growth of frames not yet read back
   osl_status sticky_error;
   cudaStream_t last_stream;
-  cudaStream_t copy_stream;              // front stream: H2D of host frames, and (pipelined mode) k_emit + k_sort
+  cudaStream_t copy_stream;              // H2D of host frames
+  cudaStream_t pipe[4];                  // pipelined mode: E (k_emit), So (k_sort), S (k_structure + k_link), V (k_levels)
+  cudaEvent_t emit_done[OSL_FRONT], sort_done[OSL_FRONT];
+  cudaEvent_t struct_ev[OSL_RING];       // k_structure of frame f done (slot f % OSL_RING); ring_ev = k_levels done
+  int last_piped;
+  int join_pending;                      // pipelined frames are in flight that other streams have not been ordered after
   int stage_timing, stage_valid;         // per-kernel CUDA-event timing of non-pipelined frames (bench / profiling)
   cudaEvent_t stage_ev[5];
-  int front_active;                      // the front stream has been used: cooperative grids stay <= num_sms/2
   int pipeline;                          // 1: emit+sort run on the front stream (inputs are ready at call time)
-  cudaEvent_t front_done[OSL_FRONT], back_done[OSL_FRONT];
   unsigned long long seq;                // frames enqueued (front buffer = seq % OSL_FRONT)
   int hint_emit, hint_level;             // last known n_emit / widest level (grid sizing); -1 = unknown
   int hint_n_in;
@@ -219,6 +223,7 @@ int osl_structure_occupancy();
 int osl_levels_occupancy();
 osl_status osl_poll_results(osl_svo* t, bool block);
 osl_status osl_grow_pool(osl_svo* t, size_t want_nodes, cudaStream_t st);
+osl_status osl_join(osl_svo* t, cudaStream_t st);
 
 // raycast / extraction / image kernels
 osl_status osl_launch_raycast(const u32* d_pool, const float center[3], float half_edge, uint8_t* d_out, int w, int h,

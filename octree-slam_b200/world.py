@@ -127,6 +127,10 @@ class SVO:
         pool = np.ascontiguousarray(pool, dtype=np.uint32)
         _check(lib().osl_svo_upload(self._h, _hptr(pool), pool.size // 2), "osl_svo_upload")
 
+    def join(self, stream=None):
+        """order `stream` after every frame enqueued so far (device-side)"""
+        _check(lib().osl_svo_join(self._h, stream), "osl_svo_join")
+
     def sync(self):
         _check(lib().osl_svo_sync(self._h), "osl_svo_sync")
 
