@@ -217,12 +217,12 @@ def run_ours(args):
     if world > 1:
         torch.cuda.synchronize()
         pkg.shard.replicate_tree(svo, 0, device="cuda")
-    bands = pkg.shard.row_bands(RAY_H, world, rank)
-    outs = [torch.empty((rows, RAY_W, 4), dtype=torch.uint8, device="cuda") for _, rows in bands]
+    band = pkg.shard.band_height(RAY_H, world)
+    my_rows = sum(r for _, r in pkg.shard.row_bands(RAY_H, world, rank, band))
+    out_rows = torch.empty((max(my_rows, 1), RAY_W, 4), dtype=torch.uint8, device="cuda")
 
-    def render():
-        for (row0, rows), o in zip(bands, outs):
-            svo.raycast_rows(o, RAY_W, RAY_H, row0, rows, FOV, view, stream=sp)
+    def render():  # one launch: all the interleaved bands this rank owns
+        svo.raycast_bands(out_rows, RAY_W, RAY_H, band, world, rank, FOV, view, stream=sp)
 
     r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for _ in range(3):
@@ -310,11 +310,12 @@ def run_reference(args):
     fx, fy = pkg.synth.focal(W, H)
     ring = min(RING, max(8, K + Wm))
     depths, rgbs, poses = make_ring(pkg.synth, ring)
-    base = {"metric": METRIC, "unit": "frames/s", "n_gpus": 1, "steps": K, "warmup": Wm, "higher_is_better": True,
+    base = {"metric": METRIC, "unit": "frames/s", "n_gpus": args.gpus, "steps": K, "warmup": Wm, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u64 keys / u32 nodes / f32 geometry",
             "data": "synthetic", "impl": "reference",
             "config": {"workload": "cfg3/4-style: 640x480 synthetic RGB-D orbit, incremental fusion into one depth-16 "
-                                   "SVO (1 cm leaves, half edge 655.36 m)"}}
+                                   "SVO (1 cm leaves, half edge 655.36 m)",
+                       "multi_gpu": "the reference has no multi-GPU path: rank 0 runs it on one GPU whatever --gpus says"}}
     have_gpu_ref = False
     try:
         import torch

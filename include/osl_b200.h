@@ -142,6 +142,12 @@ osl_status osl_raycast_host(const osl_svo* t, uint8_t* h_out_rgba, int w, int h,
 osl_status osl_raycast_rows(const osl_svo* t, uint8_t* d_out_rgba, int w, int h, int row0, int rows, float fov_deg,
                             const float view[16], const osl_raycast_params* prm, osl_raycast_stats* h_stats,
                             void* stream);
+/* All rows one rank owns under the interleaved-band decomposition, in one launch: bands of band_h rows are dealt
+ * round-robin to n_ranks ranks (band k -> rank k % n_ranks); the rank's rows land compactly, in image order, in
+ * d_out_rgba.  *rows_out (may be NULL) = number of rows rendered. */
+osl_status osl_raycast_bands(const osl_svo* t, uint8_t* d_out_rgba, int w, int h, int band_h, int n_ranks, int rank,
+                             float fov_deg, const float view[16], const osl_raycast_params* prm, int* rows_out,
+                             void* stream);
 /* Raycast an arbitrary pool (SVO struct by value in the reference). */
 osl_status osl_raycast_pool(const uint32_t* d_pool, const float center[3], float half_edge, uint8_t* d_out_rgba, int w,
                             int h, float fov_deg, const float view[16], const osl_raycast_params* prm,

@@ -320,7 +320,8 @@ osl_status osl_get_counters(const osl_svo* tc, osl_counters* out) {
 }
 
 static osl_status raycast_rows_pool(const uint32_t* d_pool, const float center[3], float half_edge,
-                                    uint8_t* d_out_rgba, int w, int h, int row0, int rows, float fov_deg,
+                                    uint8_t* d_out_rgba, int w, int h, int row0, int rows, int band_h,
+                                    int band_stride, float fov_deg,
                                     const float view[16], const osl_raycast_params* prm, osl_raycast_stats* h_stats,
                                     void* stream) {
   if (!d_pool || !center || !d_out_rgba || !view) return OSL_ERR_INVALID;
@@ -330,8 +331,8 @@ static osl_status raycast_rows_pool(const uint32_t* d_pool, const float center[3
     OSL_CUDA(cudaMalloc(&d_stats, 16));
     OSL_CUDA(cudaMemsetAsync(d_stats, 0, 16, st));
   }
-  osl_status rc = osl_launch_raycast(d_pool, center, half_edge, d_out_rgba, w, h, row0, rows, fov_deg, view, prm,
-                                     d_stats, st);
+  osl_status rc = osl_launch_raycast(d_pool, center, half_edge, d_out_rgba, w, h, row0, rows, band_h, band_stride,
+                                     fov_deg, view, prm, d_stats, st);
   if (h_stats) {
     unsigned long long s[2] = {0, 0};
     cudaError_t e = cudaMemcpyAsync(s, d_stats, 16, cudaMemcpyDeviceToHost, st);
@@ -346,7 +347,8 @@ static osl_status raycast_rows_pool(const uint32_t* d_pool, const float center[3
 osl_status osl_raycast_pool(const uint32_t* d_pool, const float center[3], float half_edge, uint8_t* d_out_rgba, int w,
                             int h, float fov_deg, const float view[16], const osl_raycast_params* prm,
                             osl_raycast_stats* h_stats, void* stream) {
-  return raycast_rows_pool(d_pool, center, half_edge, d_out_rgba, w, h, 0, h, fov_deg, view, prm, h_stats, stream);
+  return raycast_rows_pool(d_pool, center, half_edge, d_out_rgba, w, h, 0, h, h, 1, fov_deg, view, prm, h_stats,
+                           stream);
 }
 
 // Image rows [row0, row0 + rows) only, into d_out_rgba[0 .. rows*w*4): the multi-GPU decomposition of the raycast
@@ -359,7 +361,27 @@ osl_status osl_raycast_rows(const osl_svo* t, uint8_t* d_out_rgba, int w, int h,
   const float c[3] = {t->tp.cx, t->tp.cy, t->tp.cz};
   osl_status jr = osl_join(const_cast<osl_svo*>(t), (cudaStream_t)stream);
   if (jr) return jr;
-  return raycast_rows_pool(t->d_pool, c, t->tp.half, d_out_rgba, w, h, row0, rows, fov_deg, view, prm, h_stats, stream);
+  return raycast_rows_pool(t->d_pool, c, t->tp.half, d_out_rgba, w, h, row0, rows, rows > 0 ? rows : 1, 1, fov_deg,
+                           view, prm, h_stats, stream);
+}
+
+// All rows one rank owns under the interleaved-band decomposition, in ONE launch: bands of band_h rows are dealt
+// round-robin to n_ranks ranks (band k belongs to rank k % n_ranks); the rank's rows are written compactly, in image
+// order, to d_out_rgba.  *rows_out (optional) receives the number of rows rendered.
+osl_status osl_raycast_bands(const osl_svo* t, uint8_t* d_out_rgba, int w, int h, int band_h, int n_ranks, int rank,
+                             float fov_deg, const float view[16], const osl_raycast_params* prm, int* rows_out,
+                             void* stream) {
+  if (!t || (t->size == 0 && t->ring_head == 0) || band_h < 1 || n_ranks < 1 || rank < 0 || rank >= n_ranks || h <= 0)
+    return OSL_ERR_INVALID;
+  OSL_CUDA(cudaSetDevice(t->device));
+  int rows = 0;
+  for (int row0 = rank * band_h; row0 < h; row0 += band_h * n_ranks) rows += (h - row0 < band_h) ? (h - row0) : band_h;
+  if (rows_out) *rows_out = rows;
+  const float c[3] = {t->tp.cx, t->tp.cy, t->tp.cz};
+  osl_status jr = osl_join(const_cast<osl_svo*>(t), (cudaStream_t)stream);
+  if (jr) return jr;
+  return raycast_rows_pool(t->d_pool, c, t->tp.half, d_out_rgba, w, h, rank * band_h, rows, band_h, n_ranks, fov_deg,
+                           view, prm, nullptr, stream);
 }
 
 // Stream-ordered after the integrates enqueued on the same stream (no host synchronisation needed).

@@ -680,10 +680,13 @@ __device__ __forceinline__ void assign_block(int vb, int n, const u64* __restric
   if (j < n) { k = keys[j]; m = m8[j]; s = s8[j]; node = start[j]; }
   const bool unique = m < D;
 
+  // No lane of this warp heads a level <= the warp's smallest m: the per-level collectives start one level above it
+  // (one level early so that par_idx / path_tile of the first headed level come out of the loop itself).
+  const int d0 = max(1, (int)__reduce_min_sync(FULL, (unsigned)m));
   // pass 1: per-warp totals of every counter this block can touch
-  for (int c = tid; c < AN_WARPS * NC_MAX; c += AN_THREADS) (&s_w[0][0])[c] = 0;
-  __syncthreads();
-  for (int d = 1; d <= D; d++) {
+  for (int c = lane; c < NC; c += 32) s_w[warp][c] = 0;
+  __syncwarp();
+  for (int d = d0; d <= D; d++) {
     const bool f = unique && m < d;
     const u32 bal = __ballot_sync(FULL, f);
     if (lane == 0) s_w[warp][OSL_CLVL(D, d)] = __popc(bal);
@@ -714,9 +717,11 @@ __device__ __forceinline__ void assign_block(int vb, int n, const u64* __restric
   // beyond the live nodes is kept zero, so their word0 is already 0 and cannot race with the pointer writes.
   const int s_eff = (s == OSL_NONE) ? D : s;
   const u32 le = lt | (1u << lane);
-  u32 par_idx = 0;   // index (in level d-1) of the node on this key's path
+  // index (in level d-1) of the node on this key's path; below d0 the warp has no heads, so it is the last node
+  // headed before this warp
+  u32 par_idx = (d0 > 1) ? s_w[warp][OSL_CLVL(D, d0 - 1)] - 1u : 0u;
   u32 path_tile = 0; // tile holding the level-(d) nodes below this key's level-(d-1) node (root: tile 0)
-  for (int d = 1; d <= D; d++) {
+  for (int d = d0; d <= D; d++) {
     const bool f = unique && m < d;
     const u32 bal = __ballot_sync(FULL, f);
     const bool sp = f && s != OSL_NONE && s <= d && (d <= D - 1 || s == D);
@@ -810,12 +815,12 @@ k_structure(const u64* __restrict__ keys, u32* pay, u32* pool, TreeParams tp, Fr
     for (int c = tid; c < NC; c += AN_THREADS) {
       u32 tot = 0, pre = 0;
       const int mine = (int)blockIdx.x;
-      for (int b0 = 0; b0 < nvb; b0 += 8) {
-        u32 v[8];
+      for (int b0 = 0; b0 < nvb; b0 += 16) {
+        u32 v[16];
 #pragma unroll
-        for (int k = 0; k < 8; k++) v[k] = (b0 + k < nvb) ? __ldcg(&blockcnt[(size_t)(b0 + k) * NC + c]) : 0u;
+        for (int k = 0; k < 16; k++) v[k] = (b0 + k < nvb) ? __ldcg(&blockcnt[(size_t)(b0 + k) * NC + c]) : 0u;
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
+        for (int k = 0; k < 16; k++) {
           tot += v[k];
           if (b0 + k < mine) pre += v[k];
         }
@@ -891,62 +896,68 @@ k_structure(const u64* __restrict__ keys, u32* pay, u32* pool, TreeParams tp, Fr
   if (bs >= 1) s_plan[OSL_CBKT(D, bs, bd)] = woff + incl - val;
   const long long after = (long long)size0 + 8ll * n_split;
   const bool overflow = after > (long long)capacity;
-  if (blockIdx.x == 0) {
-    if (bs >= 1) fr->base[bs * (D + 1) + bd] = (int)(woff + incl - val);
+  PROF(21);
+  if (!overflow) {
+    int prev_vb = (int)blockIdx.x;
+    for (int vb = blockIdx.x; vb < nvb; vb += G) {
+      if (!flagpath) {
+        for (int c = tid; c < NC; c += AN_THREADS) s_base[c] = __ldcg(&blockcnt[(size_t)vb * NC + c]);
+      } else if (vb != prev_vb) {  // a CTA with several blocks: extend the prefix by the blocks in between
+        for (int c = tid; c < NC; c += AN_THREADS) {
+          u32 pre = s_base[c];
+          for (int b = prev_vb; b < vb; b++) pre += __ldcg(&blockcnt[(size_t)b * NC + c]);
+          s_base[c] = pre;
+        }
+        prev_vb = vb;
+      }
+      __syncthreads();
+      assign_block(vb, n, keys, pay, pool, tp, m8, s8, start, s_base, lv, mode, size0, n_invalid_front, s_plan, s_w);
+    }
+  }
+  PROF(22);
+
+  // Book-keeping by the LAST CTA (the grid is sized with a margin, so it usually has no block of its own and this
+  // stays off the critical path): the frame's result block, to the device copy k_levels reads and straight to the
+  // pinned host ring (no cudaMemcpyAsync per frame; the host reads it after the event that follows k_levels).
+  if ((int)blockIdx.x == G - 1) {
+    if (bs >= 1) {
+      const int v = (int)(woff + incl - val);
+      fr->base[bs * (D + 1) + bd] = v; hr->base[bs * (D + 1) + bd] = v;
+    }
     if (tid < D) {  // |codes[i]| of reference pass i
       u32 pc = 0;
       for (int d = 1; d <= D; d++) {
         const int s = d - tid;
         if (s >= 1 && !(d == D && s != D)) pc += s_tot[OSL_CBKT(D, s, d)];
       }
-      fr->pass_count[tid] = (int)pc;
+      fr->pass_count[tid] = (int)pc; hr->pass_count[tid] = (int)pc;
     }
-    if (tid >= 1 && tid <= D) fr->n_level[tid] = (int)s_tot[OSL_CLVL(D, tid)];
+    if (tid >= 1 && tid <= D) { const int v = (int)s_tot[OSL_CLVL(D, tid)]; fr->n_level[tid] = v; hr->n_level[tid] = v; }
     if (tid == 0) {
-      fr->n_in = n_in; fr->n_valid = n_valid; fr->n_emit = n; fr->n_invalid_front = n_invalid_front;
-      // every CTA that has work read these before it published / passed the barrier; a CTA that starts later
-      // sees 0 entries and idles
-      fs->acc_valid[parity] = 0; fs->acc_emit[parity] = 0;
-      fr->n_level[0] = s_tot[OSL_CLVL(D, 1)] > 0 ? 1 : 0;
-      fr->n_level[D + 1] = 0;
-      fr->n_split = (int)n_split;
-      fr->size_before = (int)size0;
-      fr->capacity = capacity;
-      fr->size_after = (int)min(after, (long long)0x7FFFFFFF);
-      fr->overflow = overflow ? 1 : 0;
-      fr->fresh = cur == 0 ? 1 : 0;
-      if (!overflow) fs->cur_size = (int)after;
-      fs->frame_seq += 1;
-      fr->frame_seq = fs->frame_seq; fr->cur_size = overflow ? cur : (int)after;
-    }
-  }
-  __syncthreads();
-  if (blockIdx.x == 0) {
-    // the result block also goes straight to the pinned host ring (no cudaMemcpyAsync per frame); the host reads it
-    // after the event that follows this frame's k_levels
-    const int* src = reinterpret_cast<const int*>(fr);
-    int* dst = reinterpret_cast<int*>(hr);
-    for (int i = tid; i < (int)(sizeof(FrameState) / sizeof(int)); i += AN_THREADS) dst[i] = __ldcg(src + i);
-  }
-  PROF(21);
-  if (overflow) return;
-
-  int prev_vb = (int)blockIdx.x;
-  for (int vb = blockIdx.x; vb < nvb; vb += G) {
-    if (!flagpath) {
-      for (int c = tid; c < NC; c += AN_THREADS) s_base[c] = __ldcg(&blockcnt[(size_t)vb * NC + c]);
-    } else if (vb != prev_vb) {  // a CTA with several blocks: extend the prefix by the blocks in between
-      for (int c = tid; c < NC; c += AN_THREADS) {
-        u32 pre = s_base[c];
-        for (int b = prev_vb; b < vb; b++) pre += __ldcg(&blockcnt[(size_t)b * NC + c]);
-        s_base[c] = pre;
+      const int seq = __ldcg(&fs->frame_seq) + 1;
+      FrameState* out[2] = {fr, hr};
+#pragma unroll
+      for (int k = 0; k < 2; k++) {
+        FrameState* o = out[k];
+        o->n_in = n_in; o->n_valid = n_valid; o->n_emit = n; o->n_invalid_front = n_invalid_front;
+        o->n_level[0] = s_tot[OSL_CLVL(D, 1)] > 0 ? 1 : 0;
+        o->n_level[D + 1] = 0;
+        o->n_split = (int)n_split;
+        o->size_before = (int)size0;
+        o->capacity = capacity;
+        o->size_after = (int)min(after, (long long)0x7FFFFFFF);
+        o->overflow = overflow ? 1 : 0;
+        o->fresh = cur == 0 ? 1 : 0;
+        o->frame_seq = seq;
+        o->cur_size = overflow ? cur : (int)after;
       }
-      prev_vb = vb;
+      // every CTA that has work read these before it published / passed the barrier; a CTA that starts later sees
+      // 0 entries and idles
+      fs->acc_valid[parity] = 0; fs->acc_emit[parity] = 0;
+      if (!overflow) fs->cur_size = (int)after;
+      fs->frame_seq = seq;
     }
-    __syncthreads();
-    assign_block(vb, n, keys, pay, pool, tp, m8, s8, start, s_base, lv, mode, size0, n_invalid_front, s_plan, s_w);
   }
-  PROF(22);
 }
 
 // ------------------------------------------------------------------------------------------------ k_levels

@@ -227,5 +227,5 @@ osl_status osl_join(osl_svo* t, cudaStream_t st);
 
 // raycast / extraction / image kernels
 osl_status osl_launch_raycast(const u32* d_pool, const float center[3], float half_edge, uint8_t* d_out, int w, int h,
-                              int row0, int rows, float fov_deg, const float view[16], const osl_raycast_params* prm,
+                              int row0, int rows, int band_h, int band_stride, float fov_deg, const float view[16], const osl_raycast_params* prm,
                               unsigned long long* d_stats, cudaStream_t st);

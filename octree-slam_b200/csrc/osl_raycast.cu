@@ -27,7 +27,8 @@ struct RayParams {
   float fx, fy, start_dist, max_range;
   int mode;
   int W, H;
-  int row0, rows;          // image rows [row0, row0 + rows) are rendered into out[0 .. rows*W)
+  int row0, rows;          // `rows` image rows are rendered into out[0 .. rows*W): local row r is image row
+  int band_h, band_stride; // row0 + (r / band_h) * band_h * band_stride + r % band_h  (interleaved bands of a rank)
 };
 
 __device__ __forceinline__ float ray_length(float x, float y, float z) {
@@ -73,7 +74,8 @@ k_raycast(const u32* __restrict__ pool, RayParams P, uchar4* __restrict__ out, u
   const int n = P.W * P.rows;
   unsigned long long steps = 0, visits = 0;
   if (idx < n) {
-    const int px = idx % P.W, py = P.row0 + idx / P.W;
+    const int lr = idx / P.W;
+    const int px = idx % P.W, py = P.row0 + (lr / P.band_h) * P.band_h * P.band_stride + lr % P.band_h;
     // createRays (cone_tracing_kernels.cu:29-51)
     const float magx = __fdiv_rn(__fmaf_rn(P.resx, -0.5f, (float)px), P.fx);
     const float magy = __fdiv_rn(__fmaf_rn(P.resy, -0.5f, (float)py), P.fy);
@@ -238,10 +240,15 @@ static void mat4_mul_vec4(const float m[16], const float v[4], float o[4]) {
 }
 
 osl_status osl_launch_raycast(const u32* d_pool, const float center[3], float half_edge, uint8_t* d_out, int w, int h,
-                              int row0, int rows, float fov_deg, const float view[16], const osl_raycast_params* prm,
-                              unsigned long long* d_stats, cudaStream_t st) {
-  if (!d_pool || !d_out || w <= 0 || h <= 0 || row0 < 0 || rows < 0 || row0 + rows > h) return OSL_ERR_INVALID;
+                              int row0, int rows, int band_h, int band_stride, float fov_deg, const float view[16],
+                              const osl_raycast_params* prm, unsigned long long* d_stats, cudaStream_t st) {
+  if (!d_pool || !d_out || w <= 0 || h <= 0 || row0 < 0 || rows < 0 || band_h < 1 || band_stride < 1)
+    return OSL_ERR_INVALID;
   if (rows == 0) return OSL_OK;
+  {  // the last local row must lie inside the image
+    const int lr = rows - 1;
+    if (row0 + (lr / band_h) * band_h * band_stride + lr % band_h >= h) return OSL_ERR_INVALID;
+  }
   osl_raycast_params p = {532.57f, 531.54f, 0.002f, 10.0f, 0};
   if (prm) p = *prm;
   // host part of coneTraceSVO (cone_tracing_kernels.cu:161-171)
@@ -263,7 +270,7 @@ osl_status osl_launch_raycast(const u32* d_pool, const float center[3], float ha
   P.pix_scale = tanf(fov_deg * 3.14159f / 180.0f) / (float)h;
   P.cx = center[0]; P.cy = center[1]; P.cz = center[2]; P.size = half_edge;
   P.fx = p.fx; P.fy = p.fy; P.start_dist = p.start_dist; P.max_range = p.max_range;
-  P.mode = p.mode; P.W = w; P.H = h; P.row0 = row0; P.rows = rows;
+  P.mode = p.mode; P.W = w; P.H = h; P.row0 = row0; P.rows = rows; P.band_h = band_h; P.band_stride = band_stride;
   const int n = w * rows;
   k_raycast<<<(n + RAY_THREADS - 1) / RAY_THREADS, RAY_THREADS, 0, st>>>(d_pool, P, reinterpret_cast<uchar4*>(d_out),
                                                                          d_stats);

@@ -35,6 +35,11 @@ def row_bands(h, world, rank, band=None):
     return out
 
 
+def band_height(h, world):
+    """band height `row_bands` uses by default (about 4 bands per rank)"""
+    return h if world <= 1 else max(1, -(-h // (4 * world)))
+
+
 def split_count_prefix(counts, group=None):
     """counts: int64 tensor [P] of this rank's per-pass split counts (|codes[i]| restricted to the rank's key range;
     rank order = key order).  Returns (base, total): base[i] = number of tiles allocated in pass i by lower ranks plus

@@ -171,6 +171,16 @@ class SVO:
                                       C.byref(prm), None, stream), "osl_raycast_rows")
         return out
 
+    def raycast_bands(self, out, w, h, band_h, n_ranks, rank, fov=45.0, view=IDENTITY, mode=0, stream=None):
+        """every row `rank` owns (interleaved bands of band_h rows over n_ranks ranks) in one launch, compactly into
+        the CUDA tensor `out`; returns the number of rows rendered"""
+        prm = RaycastParams(532.57, 531.54, 0.002, 10.0, mode)
+        rows = C.c_int()
+        _check(lib().osl_raycast_bands(self._h, out.data_ptr(), w, h, band_h, n_ranks, rank, float(fov),
+                                       _f(mat_colmajor(view)), C.byref(prm), C.byref(rows), stream),
+               "osl_raycast_bands")
+        return rows.value
+
     # ---- extraction ------------------------------------------------------------------------------------
     def extract_voxels(self, max_depth=None):
         torch = _torch()

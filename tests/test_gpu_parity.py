@@ -372,6 +372,20 @@ def test_raycast_rows_tile_the_full_image(P):
                 svo.raycast_rows(out, w, h, row0, rows, 45.0, LOOK_PLUS_Z)
                 img[row0:row0 + rows] = out.cpu().numpy()
     assert np.array_equal(img, full)
+    # the same decomposition with ONE launch per rank (osl_raycast_bands)
+    for world in (1, 2, 5):
+        img2 = np.zeros_like(full)
+        band = P.shard.band_height(h, world)
+        for rank in range(world):
+            bands = P.shard.row_bands(h, world, rank, band)
+            rows = sum(r for _, r in bands)
+            out = torch.empty((max(rows, 1), w, 4), dtype=torch.uint8, device="cuda")
+            assert svo.raycast_bands(out, w, h, band, world, rank, 45.0, LOOK_PLUS_Z) == rows
+            got, off = out.cpu().numpy(), 0
+            for row0, r in bands:
+                img2[row0:row0 + r] = got[off:off + r]
+                off += r
+        assert np.array_equal(img2, full)
 
 
 @pytest.mark.parametrize("D,res", [(12, (320, 240)), (16, (160, 120))])
