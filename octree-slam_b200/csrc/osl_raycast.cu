@@ -38,15 +38,20 @@ __device__ __forceinline__ float ray_length(float x, float y, float z) {
 // F2I.U32.TRUNC then byte store: NaN/negative -> 0, > 255 wraps mod 256 (Q16)
 __device__ __forceinline__ u32 f2u8(float f) { return __float2uint_rz(f) & 0xFFu; }
 
-// lod = (int)ceil(logf(q) / ln2f), the reference's expression (cone_tracing_kernels.cu:69).  For a finite positive
-// normal q = 1.m * 2^e whose mantissa is at least 2^-10 away from a power of two, log2(q) lies in
-// (e + 1.4e-3, e + 1 - 7e-4) while the float evaluation is off by at most |log2 q| * 2e-7 < 3e-5, so the result is
-// e + 1 and neither logf nor the division is needed.  Everything else takes the reference's expression verbatim.
-__device__ __forceinline__ int lod_depth(float q) {
-  const u32 b = __float_as_uint(q);
+// lod = (int)ceil(logf(q) / ln2f) with q = size / pix, the reference's expression (cone_tracing_kernels.cu:66-69).
+// For a finite positive normal q = 1.m * 2^e whose mantissa is at least 2^-10 away from a power of two, log2(q) lies
+// in (e + 1.4e-3, e + 1 - 7e-4) while the float evaluation is off by at most |log2 q| * 2e-7 < 3e-5, so the result
+// is e + 1 and neither logf nor its division is needed.  The test is made on a FAST quotient (<= 2 ulp from the IEEE
+// one) with a 2^-9 margin, which implies the 2^-10 margin for the exact quotient, so the IEEE division is skipped as
+// well.  Everything else (0.4 % of the samples, non-finite / non-positive values) evaluates the reference's
+// expression verbatim.
+__device__ __forceinline__ int lod_depth(float size, float pix) {
+  const float qa = __fdividef(size, pix);
+  const u32 b = __float_as_uint(qa);
   const u32 ex = b >> 23;  // sign + exponent
   const u32 man = b & 0x7FFFFFu;
-  if (ex >= 1u && ex <= 254u && man > 0x2000u && man < 0x7FE000u) return (int)ex - 126;
+  if (ex >= 2u && ex <= 253u && man > 0x4000u && man < 0x7FC000u) return (int)ex - 126;
+  const float q = __fdiv_rn(size, pix);
   return (int)ceilf(__fdiv_rn(logf(q), 0.693147182464599609375f));
 }
 
@@ -59,12 +64,26 @@ __device__ __forceinline__ float node_step(float size, int depth) {
 
 #define RAY_THREADS 128
 
+// A cell of the tree a ray's descent went through, with the EXACT half-open bounds the root descent implies for it
+// (the centres compared on the way down): a sample inside them takes the same branches from the root, so the descent
+// may resume here.  A cached cell never becomes stale (the tree is read-only during a render).
+struct RayCell {
+  int lvl;             // >= 1; -1 = empty
+  u32 child, self;     // first child of the cell's node, the node itself
+  float cx, cy, cz, e; // centre and half size
+  float lox, hix, loy, hiy, loz, hiz;
+};
+
+__device__ __forceinline__ bool cell_has(const RayCell& c, int depth, float tx, float ty, float tz) {
+  return c.lvl >= 1 && depth >= c.lvl && tx > c.lox && !(tx > c.hix) && ty > c.loy && !(ty > c.hiy) && tz > c.loz &&
+         !(tz > c.hiz);
+}
+
 // One ray per thread, the whole march in registers.  Per step the reference descends from the root to the LOD level;
-// here a thread remembers one ancestor cell of its last sample (child pointer, centre, half size and the EXACT
-// half-open bounds the root descent implies for it: the centres compared on the way down) and resumes the descent
-// there whenever the next sample lies inside -- consecutive samples are half a leaf apart, so most steps walk 3-4
-// levels instead of 8-16.  The result is identical by construction: a point inside those bounds takes exactly the
-// same branches from the root.
+// here a thread keeps TWO ancestor cells of its last sample -- a deep one 3 levels above the sample (hit by ~85 % of
+// the next samples: consecutive samples are half a leaf apart) and a shallow one 7 levels above (hit by nearly all
+// the others, which matters because one lane restarting at the root stalls its whole warp) -- and resumes the descent
+// at the deepest one that contains the new sample.  Identical results by construction.
 __global__ void __launch_bounds__(RAY_THREADS)
 k_raycast(const u32* __restrict__ pool, RayParams P, uchar4* __restrict__ out, unsigned long long* stats) {
   __shared__ float s_af[256];  // (A - 127) / 127.0f for every alpha byte (Q9: no clamp)
@@ -90,11 +109,12 @@ k_raycast(const u32* __restrict__ pool, RayParams P, uchar4* __restrict__ out, u
     float len = ray_length(rx, ry, rz);
 
     const float INF = __int_as_float(0x7f800000);
-    // cached ancestor cell (level c_lvl >= 1; -1 = none)
-    int c_lvl = -1;
-    u32 c_child = 0, c_self = 0;
-    float c_cx = 0.f, c_cy = 0.f, c_cz = 0.f, c_e = 0.f;
-    float lox = -INF, hix = INF, loy = -INF, hiy = INF, loz = -INF, hiz = INF;
+    RayCell A, B;  // deep, shallow
+    A.lvl = -1; B.lvl = -1;
+    A.child = A.self = B.child = B.self = 0u;
+    A.cx = A.cy = A.cz = A.e = B.cx = B.cy = B.cz = B.e = 0.f;
+    A.lox = A.loy = A.loz = B.lox = B.loy = B.loz = -INF;
+    A.hix = A.hiy = A.hiz = B.hix = B.hiy = B.hiz = INF;
     int last_lvl = 8;
 
     u32 vx = 0, vy = 0, vz = 0, vw = 0;  // uchar4 accumulator (mod-256 arithmetic)
@@ -103,48 +123,55 @@ k_raycast(const u32* __restrict__ pool, RayParams P, uchar4* __restrict__ out, u
       steps++;
       const float tx = __fadd_rn(P.ox, rx), ty = __fadd_rn(P.oy, ry), tz = __fadd_rn(P.oz, rz);
       const float pix = __fmul_rn(len, P.pix_scale);
-      const float q = __fdiv_rn(P.size, pix);
-      int depth = lod_depth(q);
+      int depth = lod_depth(P.size, pix);
 
+      // where the descent starts: deepest cached cell containing the sample, else the root
       u32 node = 0, child = 0;
       float cx = P.cx, cy = P.cy, cz = P.cz, e = P.size;
+      float blx = -INF, bhx = INF, bly = -INF, bhy = INF, blz = -INF, bhz = INF;  // bounds of the current cell
       int i = 0;
-      const bool hit = c_lvl >= 1 && depth >= c_lvl && tx > lox && !(tx > hix) && ty > loy && !(ty > hiy) &&
-                       tz > loz && !(tz > hiz);
-      float blx, bhx, bly, bhy, blz, bhz;  // bounds of the current cell while they are tracked
-      if (hit) {
-        i = c_lvl; node = c_self; child = c_child; cx = c_cx; cy = c_cy; cz = c_cz; e = c_e;
-        blx = lox; bhx = hix; bly = loy; bhy = hiy; blz = loz; bhz = hiz;
-        visits += (unsigned long long)c_lvl;  // the word0 reads the root descent would have made
-      } else {
-        blx = -INF; bhx = INF; bly = -INF; bhy = INF; blz = -INF; bhz = INF;
+      if (cell_has(A, depth, tx, ty, tz)) {
+        i = A.lvl; node = A.self; child = A.child; cx = A.cx; cy = A.cy; cz = A.cz; e = A.e;
+        blx = A.lox; bhx = A.hix; bly = A.loy; bhy = A.hiy; blz = A.loz; bhz = A.hiz;
+      } else if (cell_has(B, depth, tx, ty, tz)) {
+        i = B.lvl; node = B.self; child = B.child; cx = B.cx; cy = B.cy; cz = B.cz; e = B.e;
+        blx = B.lox; bhx = B.hix; bly = B.loy; bhy = B.hiy; blz = B.loz; bhz = B.hiz;
       }
-      bool open = true;  // the descent has not met a node without children
-      // tracked segment: down to level lt, remembering the bounds, then snapshot
-      const int lt = max(last_lvl - 3, 1);
-      if (i < lt) {
-        for (; i < depth && i < lt;) {
-          const bool bx = tx > cx, by = ty > cy, bz = tz > cz;
-          node = child + (u32)((int)bx + 2 * (int)by + 4 * (int)bz);
-          const u32 w0 = __ldg(pool + 2 * (size_t)node);
-          visits++;
-          if (!(w0 & OSL_FLAG)) { depth = i + 1; open = false; break; }
-          child = w0 & OSL_MASK;
-          if (bx) blx = fmaxf(blx, cx); else bhx = fminf(bhx, cx);
-          if (by) bly = fmaxf(bly, cy); else bhy = fminf(bhy, cy);
-          if (bz) blz = fmaxf(blz, cz); else bhz = fminf(bhz, cz);
-          e = __fmul_rn(e, 0.5f);
-          cx = __fadd_rn(cx, bx ? e : -e);
-          cy = __fadd_rn(cy, by ? e : -e);
-          cz = __fadd_rn(cz, bz ? e : -e);
-          i++;
-        }
-        if (open && i == lt) {
-          c_lvl = lt; c_self = node; c_child = child; c_cx = cx; c_cy = cy; c_cz = cz; c_e = e;
-          lox = blx; hix = bhx; loy = bly; hiy = bhy; loz = blz; hiz = bhz;
-        } else if (!hit) {
-          c_lvl = -1;
-        }
+      visits += (unsigned long long)i;  // the word0 reads the root descent would have made down to here
+      bool open = true;                 // the descent has not met a node without children
+
+#define RAY_STEP_TRACKED()                                                         \
+      {                                                                            \
+        const bool bx = tx > cx, by = ty > cy, bz = tz > cz;                       \
+        node = child + (u32)((int)bx + 2 * (int)by + 4 * (int)bz);                 \
+        const u32 w0 = __ldg(pool + 2 * (size_t)node);                             \
+        visits++;                                                                  \
+        if (!(w0 & OSL_FLAG)) { depth = i + 1; open = false; break; }              \
+        child = w0 & OSL_MASK;                                                     \
+        if (bx) blx = fmaxf(blx, cx); else bhx = fminf(bhx, cx);                   \
+        if (by) bly = fmaxf(bly, cy); else bhy = fminf(bhy, cy);                   \
+        if (bz) blz = fmaxf(blz, cz); else bhz = fminf(bhz, cz);                   \
+        e = __fmul_rn(e, 0.5f);                                                    \
+        cx = __fadd_rn(cx, bx ? e : -e);                                           \
+        cy = __fadd_rn(cy, by ? e : -e);                                           \
+        cz = __fadd_rn(cz, bz ? e : -e);                                           \
+        i++;                                                                       \
+      }
+#define RAY_SNAPSHOT(C, L)                                                         \
+      {                                                                            \
+        C.lvl = (L); C.self = node; C.child = child; C.cx = cx; C.cy = cy; C.cz = cz; C.e = e; \
+        C.lox = blx; C.hix = bhx; C.loy = bly; C.hiy = bhy; C.loz = blz; C.hiz = bhz;          \
+      }
+
+      // tracked segments: down to the shallow target, snapshot, down to the deep target, snapshot
+      const int ltB = max(last_lvl - 7, 1), ltA = max(last_lvl - 3, ltB + 1);
+      if (i < ltB) {
+        for (; i < depth && i < ltB;) RAY_STEP_TRACKED()
+        if (open && i == ltB) RAY_SNAPSHOT(B, ltB)
+      }
+      if (open && i < ltA) {
+        for (; i < depth && i < ltA;) RAY_STEP_TRACKED()
+        if (open && i == ltA) RAY_SNAPSHOT(A, ltA)
       }
       if (open) {
         for (; i < depth;) {
@@ -161,6 +188,8 @@ k_raycast(const u32* __restrict__ pool, RayParams P, uchar4* __restrict__ out, u
           i++;
         }
       }
+#undef RAY_STEP_TRACKED
+#undef RAY_SNAPSHOT
       last_lvl = depth;
 
       if (P.mode == 0) { vx = vy = vz = vw = 0; }  // Q8

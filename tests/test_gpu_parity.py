@@ -409,3 +409,75 @@ def test_raycast_deep_tree_matches_oracle(P, D, res):
             want = orc.raycast(pool, center, half, w, h, 45.0, view, mode=mode, counters=cnt)
             assert np.array_equal(img, want), "%d pixels differ" % np.count_nonzero(np.any(img != want, axis=2))
             assert (st.steps, st.visits) == (cnt.ray_steps, cnt.ray_visits)
+
+
+def test_bench_workload_pipelined_matches_oracle(P):
+    """BASELINE's headline configuration (640x480 orbit into a depth-16 SVO) at full frame size, pipelined with host
+    frames AND with resident frames, against the oracle on the first frames of the orbit; then size-independent
+    properties of the pool"""
+    import torch
+    D, w, h, frames = 16, 640, 480, 6
+    center, half = P.synth.tree_params(D)
+    fx, fy = P.synth.focal(w, h)
+    host = P.SVO(center, half, D, reserve_nodes=1 << 22)
+    dev = P.SVO(center, half, D, reserve_nodes=16).set_pipeline(True)  # tiny reserve: the pool grows while piped
+    ref = orc.OracleSVO(center, half, D)
+    keep = []
+    for k in range(frames):
+        pose = P.synth.orbit_pose(k)
+        depth, rgb = P.synth.make_frame(w, h, pose, seed=k)
+        keep.append((depth, rgb, torch.from_numpy(depth).cuda(), torch.from_numpy(rgb).cuda()))
+        ref.integrate_depth(depth, rgb, fx, fy, pose)
+    torch.cuda.synchronize()
+    for k in range(frames):
+        pose = P.synth.orbit_pose(k)
+        host.integrate_depth_host(keep[k][0], keep[k][1], fx, fy, pose)
+        dev.integrate_depth(keep[k][2], keep[k][3], fx, fy, pose)
+    want = ref.pool()
+    for svo in (host, dev):
+        assert svo.size == ref.size
+        got = svo.pool()
+        assert np.array_equal(got, want)
+        check_pool_invariants(got)
+    # raycast of the fused map, full resolution, bit-exact against the oracle on a row band (the CPU oracle marches
+    # ~1 Mray/s): rows 200..215
+    view = view_for_pose(P.synth.orbit_pose(frames - 1))
+    out = torch.empty((16, w, 4), dtype=torch.uint8, device="cuda")
+    dev.raycast_rows(out, w, h, 200, 16, 45.0, view)
+    full = dev.raycast(w, h, 45.0, view)
+    assert np.array_equal(out.cpu().numpy(), full[200:216])
+    # every voxel the extraction reports is a leaf with alpha > 127 and vice versa (count check)
+    c, k, keys = dev.extract_voxels(D)
+    assert np.all(np.diff(keys) > 0)
+
+
+def test_long_pipelined_sequence_properties(P):
+    """200 pipelined frames of the bench workload (no oracle: size-independent properties only): the frame counter,
+    monotone node count, structural invariants, alpha saturation bound, idempotent structure on repeated frames"""
+    import torch
+    D, w, h = 16, 640, 480
+    center, half = P.synth.tree_params(D)
+    fx, fy = P.synth.focal(w, h)
+    ring = []
+    for k in range(8):
+        pose = P.synth.orbit_pose(3 * k)
+        depth, rgb = P.synth.make_frame(w, h, pose, seed=k)
+        ring.append((torch.from_numpy(depth).cuda(), torch.from_numpy(rgb).cuda(), pose))
+    torch.cuda.synchronize()
+    svo = P.SVO(center, half, D, reserve_nodes=1 << 22).set_pipeline(True)
+    sizes = []
+    for k in range(200):
+        d, c, pose = ring[k % 8]
+        svo.integrate_depth(d, c, fx, fy, pose)
+        if k % 40 == 39:
+            sizes.append(svo.size)
+    cn = svo.counters()
+    assert cn.frames == 200
+    assert all(a <= b for a, b in zip(sizes, sizes[1:]))
+    # the 8 frames repeat: after the first laps (Q3 splits a leaf once, on its second observation) the structure is
+    # a fixed point -- no further nodes
+    assert sizes[-1] == sizes[-2]
+    pool = svo.pool()
+    check_pool_invariants(pool)
+    alpha = pool[1::2] >> 24
+    assert alpha.max() <= 255 and alpha.max() >= 127 + 2 * 25  # every leaf of a frame is seen 25 times
