@@ -1,0 +1,39 @@
+#!/bin/sh
+# compute-sanitizer over a small end-to-end run (strict + pipelined + host frames + raycast + extraction).
+# Usage (on the GPU box): sh tools/sanitize.sh [memcheck|racecheck|synccheck|initcheck]
+tool=${1:-memcheck}
+compute-sanitizer --tool $tool --error-exitcode 1 --print-limit 20 python - <<'PY'
+import sys, numpy as np
+sys.path.insert(0, '.')
+import __graft_entry__ as g
+P = g.load_package()
+import torch
+D, w, h = 12, 160, 120
+center, half = P.synth.tree_params(D)
+fx, fy = P.synth.focal(w, h)
+frames = []
+for k in range(6):
+    pose = P.synth.orbit_pose(9 * k)
+    d, c = P.synth.make_frame(w, h, pose, seed=k)
+    frames.append((d, c, torch.from_numpy(d).cuda(), torch.from_numpy(c).cuda(), pose))
+torch.cuda.synchronize()
+a = P.SVO(center, half, D)                       # strict
+b = P.SVO(center, half, D).set_pipeline(True)    # pipelined, resident inputs
+c = P.SVO(center, half, D)                       # pipelined, host frames
+for d_, c_, dd, cc, pose in frames:
+    a.integrate_depth(dd, cc, fx, fy, pose)
+    b.integrate_depth(dd, cc, fx, fy, pose)
+    c.integrate_depth_host(d_, c_, fx, fy, pose)
+    a.sync()  # feeds the hints -> bucket sort from frame 3 on
+pa, pb, pc = a.pool(), b.pool(), c.pool()
+assert np.array_equal(pa, pb) and np.array_equal(pa, pc)
+img = a.raycast(w, h, 45.0, np.diag([-1.0, 1.0, -1.0, 1.0]).astype(np.float32))
+cen, col, keys = a.extract_voxels(D)
+pts = np.random.default_rng(0).uniform(-1, 1, size=(5000, 3)).astype(np.float32)
+rgb = np.zeros((5000, 3), dtype=np.uint8)
+v = P.SVO((0, 0, 0), 1.0, 7)
+v.integrate_points(pts, rgb)
+cent = np.ones((3000, 4), dtype=np.float32); cent[:, :3] = pts[:3000]
+v.integrate_voxels(cent, np.ones((3000, 4), dtype=np.float32) * 0.5)
+print("sanitize run ok:", a.size, img.shape, keys.size, v.size)
+PY
