@@ -481,3 +481,45 @@ def test_long_pipelined_sequence_properties(P):
     check_pool_invariants(pool)
     alpha = pool[1::2] >> 24
     assert alpha.max() <= 255 and alpha.max() >= 127 + 2 * 25  # every leaf of a frame is seen 25 times
+
+
+def test_cfg4_frame_size_1280x960_depth16_matches_oracle(P):
+    """BASELINE configs[3] frame size: 1280x960 into a depth-16 SVO (2 frames; the oracle needs ~1 s per frame)"""
+    D, w, h = 16, 1280, 960
+    center, half = P.synth.tree_params(D)
+    fx, fy = P.synth.focal(w, h)
+    svo = P.SVO(center, half, D, reserve_nodes=1 << 22)
+    ref = orc.OracleSVO(center, half, D)
+    keep = []
+    for k in range(2):
+        pose = P.synth.orbit_pose(5 * k)
+        depth, rgb = P.synth.make_frame(w, h, pose, seed=k)
+        keep.append((depth, rgb))
+        svo.integrate_depth_host(depth, rgb, fx, fy, pose)
+        ref.integrate_depth(depth, rgb, fx, fy, pose)
+    assert svo.size == ref.size
+    assert np.array_equal(svo.pool(), ref.pool())
+    c, rc = svo.counters(), ref.counters()
+    assert c.n_points == w * h
+
+
+def test_cfg3_orbit_depth14_incremental_matches_oracle(P):
+    """BASELINE configs[2] shape (incremental fusion along the orbit, depth-14 SVO), first 12 frames at 320x240
+    against the oracle, pipelined"""
+    import torch
+    D, w, h, frames = 14, 320, 240, 12
+    center, half = P.synth.tree_params(D)
+    fx, fy = P.synth.focal(w, h)
+    svo = P.SVO(center, half, D).set_pipeline(True)
+    ref = orc.OracleSVO(center, half, D)
+    keep = []
+    for k in range(frames):
+        pose = P.synth.orbit_pose(k)
+        depth, rgb = P.synth.make_frame(w, h, pose, seed=k)
+        keep.append((torch.from_numpy(depth).cuda(), torch.from_numpy(rgb).cuda()))
+        ref.integrate_depth(depth, rgb, fx, fy, pose)
+    torch.cuda.synchronize()
+    for k in range(frames):
+        svo.integrate_depth(keep[k][0], keep[k][1], fx, fy, P.synth.orbit_pose(k))
+    assert svo.size == ref.size
+    assert np.array_equal(svo.pool(), ref.pool())
