@@ -24,6 +24,22 @@ struct BoundingBox {  // common_types.h:8-17
   }
 };
 
+struct Mesh {  // common_types.h:20-32 ("a lighter weight version of obj"): HOST arrays
+  int vbosize = 0, nbosize = 0, cbosize = 0, ibosize = 0, tbosize = 0;
+  float* vbo = nullptr;  // 3 floats per vertex
+  float* nbo = nullptr;
+  float* cbo = nullptr;
+  int* ibo = nullptr;    // 3 indices per triangle
+  float* tbo = nullptr;  // 6 floats per triangle (u, v of its three corners), voxelization.cu:113-118
+  BoundingBox bbox;
+};
+
+struct bmp_texture {  // common_types.h:34-38
+  glm::vec3* data = nullptr;
+  int width = 0;
+  int height = 0;
+};
+
 struct Camera {  // common_types.h:40-47 (only view and fov are raycast inputs)
   glm::mat4 model, view, projection, modelview, mvp;
   float fov = 45.0f;

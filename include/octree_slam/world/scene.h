@@ -12,6 +12,9 @@ class Scene {
  public:
   Scene();
   ~Scene();
+  // scene.cpp:26-33 without the OBJ/BMP file readers: the caller hands over a loaded mesh (and texture)
+  void addMesh(const Mesh& mesh, const bmp_texture& texture) { meshes_ = &mesh; textures_ = &texture; }
+  void voxelizeMeshes(const bool octree);  // scene.cpp:64-85
   void extractVoxelGridFromOctree();
   void addPointCloudToOctree(const glm::vec3& origin, const glm::vec3* points, const Color256* colors, const int size,
                              const BoundingBox& bbox);
@@ -22,6 +25,8 @@ class Scene {
  private:
   VoxelGrid* voxel_grid_;
   Octree* tree_;
+  const Mesh* meshes_ = nullptr;
+  const bmp_texture* textures_ = nullptr;
 };
 
 }  // namespace world

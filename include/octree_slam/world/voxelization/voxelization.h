@@ -1,0 +1,22 @@
+// Drop-in for include/octree_slam/world/voxelization/voxelization.h:19-21 (meshToVoxelGrid only; voxelGridToMesh
+// builds cube meshes for the OpenGL voxel view and is out of scope).  Sparse: works at any depth, not the reference's
+// compile-time dense 256^3 (voxelization.cu:24).
+#ifndef OSL_B200_VOXELIZATION_H_
+#define OSL_B200_VOXELIZATION_H_
+#include <octree_slam/common_types.h>
+
+namespace octree_slam {
+namespace voxelization {
+
+inline int log_N() { return 8; }  // voxelization.cu:24 GRID_RES
+
+// Reference signature.  The grid is the depth-log_N() leaf grid of the cube (centre = bbox mid-point, half edge =
+// bbox.bbox1.x) Scene::voxelizeMeshes builds its Octree on (scene.cpp:78), so every voxel centre is a leaf centre.
+void meshToVoxelGrid(const Mesh& m_in, const bmp_texture* tex, VoxelGrid& grid_out);
+// same on an explicit cube / depth
+void meshToVoxelGrid(const Mesh& m_in, const bmp_texture* tex, const glm::vec3& center, float half_edge, int depth,
+                     VoxelGrid& grid_out);
+
+}  // namespace voxelization
+}  // namespace octree_slam
+#endif

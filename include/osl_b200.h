@@ -160,6 +160,22 @@ osl_status osl_raycast_pool(const uint32_t* d_pool, const float center[3], float
 osl_status osl_extract_voxels(const osl_svo* t, int max_depth, float* d_centers4, float* d_colors4, int64_t* d_keys,
                               int64_t cap, int64_t* n_out, void* stream);
 
+/* ---- mesh voxelisation (voxelization.h:19-21) ---------------------------------------------------------------- */
+
+/* Sparse stand-in for voxelization::meshToVoxelGrid (voxelization.cu:238-323,381-405; dense 256^3 via voxelpipe, which
+ * no longer builds): the leaf cells of the depth-max_depth grid over the tree cube that overlap a triangle, as a
+ * VoxelGrid in Morton-key order (so svoFromVoxelGrid's key sort is the identity and quirk Q11 leaves every colour on
+ * its voxel).  d_vertices: n_vertices x 3 floats, d_triangles: n_triangles x 3 ints, d_tri_colors4: one glm::vec4 per
+ * triangle (NULL = white).  The outputs are cudaMalloc'd here (as extractVoxelGridFromSVO does for VoxelGrid,
+ * svo.cu:732-733) and released with osl_free_device / cudaFree; d_keys_out / d_tris_out may be NULL. */
+osl_status osl_voxelize_mesh(const float* d_vertices, int n_vertices, const int* d_triangles, int n_triangles,
+                             const float* d_tri_colors4, const float center[3], float half_edge, int max_depth,
+                             float** d_centers4_out, float** d_colors4_out, int64_t** d_keys_out, int** d_tris_out,
+                             int64_t* n_out, void* stream);
+void osl_free_device(void* p);
+/* device-to-device copy (for bindings that must move a library-allocated result into a buffer they own) */
+osl_status osl_copy_device(void* d_dst, const void* d_src, size_t bytes);
+
 /* ---- per-frame image kernels (image_kernels.h:21,24,52) ---------------------------------------------------- */
 
 osl_status osl_generate_vertex_map(const uint16_t* d_depth, float* d_xyz, int width, int height, float fx, float fy,

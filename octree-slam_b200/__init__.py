@@ -6,6 +6,6 @@ The directory name contains a hyphen (the layout the task prescribes); import it
 from . import capi  # noqa: F401
 from .capi import Counters, OslError, RaycastParams, RaycastStats, lib  # noqa: F401
 from .world import (SVO, BoundingBox, Octree, Scene, computeKeys, computePointCloudBoundingBox,  # noqa: F401
-                    coneTraceSVO, generateVertexMap, transformVertexMap)
+                    coneTraceSVO, generateVertexMap, meshToVoxelGrid, transformVertexMap)
 from . import synth  # noqa: F401
 from . import shard  # noqa: F401

@@ -10,7 +10,9 @@ LIB = os.path.join(HERE, "libosl_b200.so")
 HOST = os.path.join(HERE, "host")
 HOST_LIB = os.path.join(HERE, "libosl_host.so")
 HOST_MAIN = os.path.join(HERE, "osl_main")
-SOURCES = ["osl_capi.cu", "osl_integrate.cu", "osl_raycast.cu", "osl_extract.cu", "osl_image.cu"]
+SOURCES = ["osl_capi.cu", "osl_integrate.cu", "osl_raycast.cu", "osl_extract.cu", "osl_image.cu", "osl_voxelize.cu"]
+# the voxeliser is checked bit-exactly against a plain-C restatement: no FMA contraction there
+EXTRA_FLAGS = {"osl_voxelize.cu": ["-fmad=false"]}
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off", "-Xcompiler", "-fno-fast-math"]
 
@@ -36,7 +38,8 @@ def build(force=False, verbose=False):
     for s in SOURCES:
         o = os.path.join(objdir, s.replace(".cu", ".o"))
         objs.append(o)
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, s), "-o", o]
+        cmd = ([nvcc] + NVCC_FLAGS + EXTRA_FLAGS.get(s, []) + (["-Xptxas", "-v"] if verbose else []) +
+               ["-c", os.path.join(CSRC, s), "-o", o])
         procs.append((cmd, subprocess.Popen(cmd)))
     for cmd, p in procs:
         if p.wait() != 0:

@@ -1513,6 +1513,38 @@ osl_status osl_join(osl_svo* t, cudaStream_t st) {
   return OSL_OK;
 }
 
+// Stand-alone use of the cooperative LSD radix sort (k_sort) for callers outside the frame pipeline (the mesh
+// voxeliser): sorts n (key, value) pairs by the low key_bits bits; *in_B tells which buffer holds the result.
+osl_status osl_device_sort_pairs(u64* kA, u32* pA, u64* kB, u32* pB, int n, int key_bits, cudaStream_t st, int* in_B) {
+  const int passes = (key_bits + 7) / 8;
+  *in_B = passes & 1;
+  if (n <= 0) return OSL_OK;
+  int dev = 0, sms = 0;
+  OSL_CUDA(cudaGetDevice(&dev));
+  OSL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  int occ = osl_sort_occupancy();
+  if (occ < 1) return OSL_ERR_CUDA;
+  const int cap = (occ > 4 ? 4 : occ) * sms;
+  const int grid = grid_for(n, SORT_TILE, cap);
+  FrameState* fs = nullptr;
+  u32* hist = nullptr;
+  OSL_CUDA(cudaMalloc(&fs, sizeof(FrameState)));
+  cudaError_t e = cudaMalloc(&hist, (size_t)grid * 256 * sizeof(u32));
+  if (e == cudaSuccess) e = cudaMemsetAsync(fs, 0, sizeof(FrameState), st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&fs->acc_emit[0], &n, sizeof(int), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) {
+    const FrameState* fsc = fs; int pp = passes; int parity = 0;
+    void* args[] = {&kA, &pA, &kB, &pB, &hist, &fsc, &pp, &parity};
+    e = cudaLaunchCooperativeKernel((void*)k_sort, dim3(grid), dim3(SORT_THREADS), args, 0, st);
+    OSL_LAUNCHED(1);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(hist);
+  cudaFree(fs);
+  OSL_CUDA(e);
+  return OSL_OK;
+}
+
 extern "C" osl_status osl_debug_profile(unsigned long long* out, int n) {
   if (!out || n < 0 || n > 64) return OSL_ERR_INVALID;
   OSL_CUDA(cudaDeviceSynchronize());

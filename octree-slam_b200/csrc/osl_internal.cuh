@@ -224,6 +224,7 @@ int osl_levels_occupancy();
 osl_status osl_poll_results(osl_svo* t, bool block);
 osl_status osl_grow_pool(osl_svo* t, size_t want_nodes, cudaStream_t st);
 osl_status osl_join(osl_svo* t, cudaStream_t st);
+osl_status osl_device_sort_pairs(u64* kA, u32* pA, u64* kB, u32* pB, int n, int key_bits, cudaStream_t st, int* in_B);
 
 // raycast / extraction / image kernels
 osl_status osl_launch_raycast(const u32* d_pool, const float center[3], float half_edge, uint8_t* d_out, int w, int h,

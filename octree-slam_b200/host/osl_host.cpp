@@ -8,6 +8,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <vector>
 #include <map>
 #include <mutex>
 
@@ -18,6 +19,7 @@
 #include <octree_slam/world/octree.h>
 #include <octree_slam/world/scene.h>
 #include <octree_slam/world/svo/svo.h>
+#include <octree_slam/world/voxelization/voxelization.h>
 
 #include "osl_b200.h"
 
@@ -146,6 +148,63 @@ void releaseSVO(unsigned int* octree) {
 
 }  // namespace svo
 
+// ---- voxelization (voxelization.cu:90-139 ColorShader, :219-236 createVoxelGrid, :381-405 meshToVoxelGrid) --------
+namespace voxelization {
+
+static inline float clamp01(float v) { return v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v); }
+
+void meshToVoxelGrid(const Mesh& m_in, const bmp_texture* tex, const glm::vec3& center, float half_edge, int depth,
+                     VoxelGrid& grid_out) {
+  const int n_tri = m_in.ibosize / 3, n_vert = m_in.vbosize / 3;
+  // per-triangle flat colour, the reference's ColorShader: no texture -> green; no texture coordinates -> texel 0;
+  // else the texel at the FIRST corner ("TODO: interpolate", voxelization.cu:125-126); quantised to 8 bits and
+  // returned as byte / 255.0 (createVoxelGrid)
+  std::vector<float> tri_col((size_t)n_tri * 4, 0.0f);
+  for (int t = 0; t < n_tri; t++) {
+    int r = 0, g = 255, b = 0;
+    if (tex && tex->width > 0 && tex->data) {
+      glm::vec3 c = tex->data[0];
+      if (m_in.tbosize > 0 && m_in.tbo) {
+        int tx = (int)(m_in.tbo[6 * t] * tex->width), ty = (int)(m_in.tbo[6 * t + 1] * tex->height);
+        tx = tx < 0 ? 0 : (tx >= tex->width ? tex->width - 1 : tx);     // (the reference indexes unchecked)
+        ty = ty < 0 ? 0 : (ty >= tex->height ? tex->height - 1 : ty);
+        c = tex->data[ty * tex->width + tx];
+        r = (int)(clamp01(c.x) * 255.0f); g = (int)(clamp01(c.y) * 255.0f); b = (int)(clamp01(c.z) * 255.0f);
+      } else {
+        r = (int)(c.x * 255.0); g = (int)(c.y * 255.0); b = (int)(c.z * 255.0);
+      }
+    }
+    tri_col[4 * t] = (float)((r & 0xFF) / 255.0); tri_col[4 * t + 1] = (float)((g & 0xFF) / 255.0);
+    tri_col[4 * t + 2] = (float)((b & 0xFF) / 255.0);
+  }
+  float *d_v = nullptr, *d_c = nullptr;
+  int* d_i = nullptr;
+  cudaMalloc((void**)&d_v, sizeof(float) * 3 * (size_t)(n_vert > 0 ? n_vert : 1));
+  cudaMalloc((void**)&d_i, sizeof(int) * 3 * (size_t)(n_tri > 0 ? n_tri : 1));
+  cudaMalloc((void**)&d_c, sizeof(float) * 4 * (size_t)(n_tri > 0 ? n_tri : 1));
+  cudaMemcpy(d_v, m_in.vbo, sizeof(float) * 3 * (size_t)n_vert, cudaMemcpyHostToDevice);
+  cudaMemcpy(d_i, m_in.ibo, sizeof(int) * 3 * (size_t)n_tri, cudaMemcpyHostToDevice);
+  cudaMemcpy(d_c, tri_col.data(), sizeof(float) * 4 * (size_t)n_tri, cudaMemcpyHostToDevice);
+  if (grid_out.size > 0) { cudaFree(grid_out.centers); cudaFree(grid_out.colors); grid_out.size = 0; }
+  float *centers = nullptr, *colors = nullptr;
+  int64_t n = 0;
+  const float c3[3] = {center.x, center.y, center.z};
+  report(osl_voxelize_mesh(d_v, n_vert, d_i, n_tri, d_c, c3, half_edge, depth, &centers, &colors, nullptr, nullptr, &n,
+                           nullptr), "osl_voxelize_mesh");
+  cudaFree(d_v); cudaFree(d_i); cudaFree(d_c);
+  grid_out.centers = reinterpret_cast<glm::vec4*>(centers);
+  grid_out.colors = reinterpret_cast<glm::vec4*>(colors);
+  grid_out.size = (int)n;
+  grid_out.scale = (2.0f * half_edge) / (float)(1 << depth);
+  grid_out.bbox = m_in.bbox;
+}
+
+void meshToVoxelGrid(const Mesh& m_in, const bmp_texture* tex, VoxelGrid& grid_out) {
+  meshToVoxelGrid(m_in, tex, (m_in.bbox.bbox1 + m_in.bbox.bbox0) / 2.0f, m_in.bbox.bbox1.x, log_N(), grid_out);
+}
+
+}  // namespace voxelization
+
 // ---- world::Octree (octree.cpp:251-389) ------------------------------------------------------------------------
 namespace world {
 
@@ -238,6 +297,24 @@ Scene::Scene() : voxel_grid_(new VoxelGrid()), tree_(nullptr) {}
 Scene::~Scene() {
   delete tree_;
   delete voxel_grid_;
+}
+
+void Scene::voxelizeMeshes(const bool octree) {  // scene.cpp:64-85
+  if (!meshes_) return;
+  const Mesh& m = *meshes_;
+  const float scale = m.bbox.bbox1.x / (float)(1 << voxelization::log_N());
+  if (!octree) {
+    voxelization::meshToVoxelGrid(m, textures_, *voxel_grid_);
+    voxel_grid_->scale = scale;
+  } else {
+    VoxelGrid grid;
+    voxelization::meshToVoxelGrid(m, textures_, grid);
+    voxel_grid_->scale = scale;
+    if (!tree_) tree_ = new Octree(scale, (m.bbox.bbox1 + m.bbox.bbox0) / 2.0f, m.bbox.bbox1.x);
+    tree_->addVoxelGrid(grid);
+    voxel_grid_->bbox = tree_->boundingBox();
+    tree_->extractVoxelGrid(*voxel_grid_);
+  }
 }
 
 void Scene::extractVoxelGridFromOctree() {

@@ -23,7 +23,53 @@ using namespace octree_slam;
 
 static bool read_exact(FILE* f, void* p, size_t n) { return fread(p, 1, n, f) == n; }
 
+// osl_main mesh <mesh.bin> <out_prefix>: Scene::voxelizeMeshes(true) (scene.cpp:64-85) on a mesh file
+// mesh.bin: int32 nv, nt; float vertices[3*nv]; int32 indices[3*nt]   (bbox = min/max of the vertices)
+static int mesh_main(const char* mesh_path, const char* out_prefix) {
+  FILE* f = fopen(mesh_path, "rb");
+  if (!f) { perror(mesh_path); return 2; }
+  int hdr[2];
+  if (!read_exact(f, hdr, sizeof(hdr))) return 2;
+  std::vector<float> vbo((size_t)hdr[0] * 3);
+  std::vector<int> ibo((size_t)hdr[1] * 3);
+  if (!read_exact(f, vbo.data(), vbo.size() * 4) || !read_exact(f, ibo.data(), ibo.size() * 4)) return 2;
+  fclose(f);
+  Mesh mesh;
+  mesh.vbo = vbo.data(); mesh.vbosize = (int)vbo.size();
+  mesh.ibo = ibo.data(); mesh.ibosize = (int)ibo.size();
+  mesh.bbox.bbox0 = glm::vec3(vbo[0], vbo[1], vbo[2]);
+  mesh.bbox.bbox1 = mesh.bbox.bbox0;
+  for (int i = 0; i < hdr[0]; i++)
+    for (int d = 0; d < 3; d++) {
+      const float v = vbo[3 * i + d];
+      if (v < mesh.bbox.bbox0[d]) mesh.bbox.bbox0[d] = v;
+      if (v > mesh.bbox.bbox1[d]) mesh.bbox.bbox1[d] = v;
+    }
+  bmp_texture no_texture;  // -> the reference's ColorShader paints green (voxelization.cu:100-102)
+  world::Scene scene;
+  scene.addMesh(mesh, no_texture);
+  scene.voxelizeMeshes(true);
+  BoundingBox any;
+  SVO svo = scene.svo(any);
+  const int n_nodes = scene.tree()->nodeCount();
+  std::vector<uint32_t> pool((size_t)n_nodes * 2);
+  cudaMemcpy(pool.data(), svo.data, pool.size() * 4, cudaMemcpyDeviceToHost);
+  char path[4096];
+  snprintf(path, sizeof(path), "%s.pool", out_prefix);
+  FILE* o = fopen(path, "wb");
+  if (!o) { perror(path); return 2; }
+  fwrite(&n_nodes, 4, 1, o);
+  fwrite(&svo.center.x, 4, 3, o);
+  fwrite(&svo.size, 4, 1, o);
+  fwrite(pool.data(), 4, pool.size(), o);
+  fclose(o);
+  printf("osl_main: mesh %d vertices %d triangles -> %d voxels, %d nodes (center %.6f %.6f %.6f, half %.6f)\n", hdr[0],
+         hdr[1], scene.voxel_grid().size, n_nodes, svo.center.x, svo.center.y, svo.center.z, svo.size);
+  return 0;
+}
+
 int main(int argc, char** argv) {
+  if (argc == 4 && !strcmp(argv[1], "mesh")) return mesh_main(argv[2], argv[3]);
   if (argc < 3) {
     fprintf(stderr, "usage: %s frames.bin out_prefix [fused]\n", argv[0]);
     return 2;

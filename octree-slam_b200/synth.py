@@ -86,3 +86,50 @@ def tree_params(max_depth, resolution=0.01):
     for _ in range(max_depth):
         he = np.float32(he * np.float32(2.0))
     return (0.0, 0.0, 0.0), float(he)
+
+
+def icosphere(subdiv=3, radius=0.8, center=(0.0, 0.0, 0.0)):
+    """Triangle mesh of a sphere (20 * 4^subdiv triangles) -- procedural input for the mesh voxeliser (the GPU box has
+    no access to the reference's objs/).  Returns (vertices float32 [nv,3], triangles int32 [nt,3])."""
+    t = (1.0 + 5.0 ** 0.5) / 2.0
+    v = [(-1, t, 0), (1, t, 0), (-1, -t, 0), (1, -t, 0), (0, -1, t), (0, 1, t), (0, -1, -t), (0, 1, -t),
+         (t, 0, -1), (t, 0, 1), (-t, 0, -1), (-t, 0, 1)]
+    f = [(0, 11, 5), (0, 5, 1), (0, 1, 7), (0, 7, 10), (0, 10, 11), (1, 5, 9), (5, 11, 4), (11, 10, 2), (10, 7, 6),
+         (7, 1, 8), (3, 9, 4), (3, 4, 2), (3, 2, 6), (3, 6, 8), (3, 8, 9), (4, 9, 5), (2, 4, 11), (6, 2, 10), (8, 6, 7),
+         (9, 8, 1)]
+    v = [np.array(p, dtype=np.float64) / np.linalg.norm(p) for p in v]
+    for _ in range(subdiv):
+        cache, nf = {}, []
+
+        def mid(a, b):
+            key = (min(a, b), max(a, b))
+            if key not in cache:
+                m = v[a] + v[b]
+                v.append(m / np.linalg.norm(m))
+                cache[key] = len(v) - 1
+            return cache[key]
+
+        for a, b, c in f:
+            ab, bc, ca = mid(a, b), mid(b, c), mid(c, a)
+            nf += [(a, ab, ca), (b, bc, ab), (c, ca, bc), (ab, bc, ca)]
+        f = nf
+    V = (np.array(v) * radius + np.asarray(center)).astype(np.float32)
+    return V, np.array(f, dtype=np.int32)
+
+
+def load_obj(path):
+    """Minimal Wavefront OBJ reader (v / f, polygons fan-triangulated like the reference's objUtil, obj.cpp:44-90)."""
+    vs, fs = [], []
+    with open(path) as fh:
+        for line in fh:
+            p = line.split()
+            if not p:
+                continue
+            if p[0] == "v":
+                vs.append([float(x) for x in p[1:4]])
+            elif p[0] == "f":
+                idx = [int(tok.split("/")[0]) for tok in p[1:]]
+                idx = [i - 1 if i > 0 else len(vs) + i for i in idx]
+                for k in range(1, len(idx) - 1):
+                    fs.append([idx[0], idx[k], idx[k + 1]])
+    return np.array(vs, dtype=np.float32), np.array(fs, dtype=np.int32)

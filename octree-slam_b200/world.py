@@ -232,6 +232,38 @@ def computeKeys(points, center, half_edge, max_depth, device=0):
     return keys.cpu().numpy()
 
 
+def meshToVoxelGrid(vertices, triangles, tri_colors4, center, half_edge, max_depth, device=0, want_keys=False):
+    """voxelization::meshToVoxelGrid (voxelization.h:21), sparse: -> (centers4, colors4) CUDA tensors [n, 4] in
+    Morton-key order (+ int64 keys and int32 lowest-triangle indices when want_keys)."""
+    torch = _torch()
+    V = _dev(np.asarray(vertices, dtype=np.float32), np.float32, device)
+    T = _dev(np.asarray(triangles, dtype=np.int32), np.int32, device)
+    Cc = _dev(np.asarray(tri_colors4, dtype=np.float32), np.float32, device) if tri_colors4 is not None else None
+    pc, pk, pkeys, ptris, n = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_int64()
+    _check(lib().osl_voxelize_mesh(V.data_ptr(), V.shape[0], T.data_ptr(), T.shape[0],
+                                   Cc.data_ptr() if Cc is not None else None, _f(center), float(half_edge),
+                                   int(max_depth), C.byref(pc), C.byref(pk),
+                                   C.byref(pkeys) if want_keys else None, C.byref(ptris) if want_keys else None,
+                                   C.byref(n), None), "osl_voxelize_mesh")
+    cnt = n.value
+    dev = "cuda:%d" % device
+
+    centers = torch.empty((cnt, 4), dtype=torch.float32, device=dev)
+    colors = torch.empty((cnt, 4), dtype=torch.float32, device=dev)
+    outs = [(pc, centers), (pk, colors)]
+    keys = tris = None
+    if want_keys:
+        keys = torch.empty((cnt,), dtype=torch.int64, device=dev)
+        tris = torch.empty((cnt,), dtype=torch.int32, device=dev)
+        outs += [(pkeys, keys), (ptris, tris)]
+    for ptr, dst in outs:
+        if cnt and ptr.value:
+            _check(lib().osl_copy_device(dst.data_ptr(), ptr, dst.numel() * dst.element_size()), "osl_copy_device")
+        if ptr.value:
+            lib().osl_free_device(ptr)
+    return (centers, colors, keys, tris) if want_keys else (centers, colors)
+
+
 # ---- reference-shaped classes ------------------------------------------------------------------------------
 
 class BoundingBox:

@@ -73,6 +73,9 @@ def lib():
         L.orc_extract_voxels.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
         L.orc_raycast.argtypes = [C.c_void_p, f3, C.c_float, C.c_void_p, C.c_int, C.c_int, C.c_float,
                                   f3, C.POINTER(RaycastParams), C.POINTER(Counters), C.c_int64]
+        L.orc_voxelize_mesh.restype = C.c_int64
+        L.orc_voxelize_mesh.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, f3, C.c_float, C.c_int,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
         L.orc_nv_logf.restype = C.c_float
         L.orc_nv_logf.argtypes = [C.c_float]
         L.orc_mat4_inverse.argtypes = [f3, f3]
@@ -203,3 +206,17 @@ def raycast(pool, center, half_edge, w, h, fov=45.0, view=IDENTITY, mode=0, max_
                       _f(mat_colmajor(view)), C.byref(prm),
                       C.byref(counters) if counters is not None else None, int(max_steps))
     return out
+
+
+def voxelize_mesh(vertices, triangles, center, half_edge, max_depth):
+    """-> (keys int64[n] ascending leading-1 Morton keys, tris int32[n] lowest triangle per cell, centers float32[n,4])"""
+    V = np.ascontiguousarray(vertices, dtype=np.float32)
+    T = np.ascontiguousarray(triangles, dtype=np.int32)
+    n = lib().orc_voxelize_mesh(_ptr(V), V.shape[0], _ptr(T), T.shape[0], _f(center), float(half_edge),
+                                int(max_depth), None, None, None, 0)
+    keys = np.empty(n, dtype=np.int64)
+    tris = np.empty(n, dtype=np.int32)
+    cen = np.empty((n, 4), dtype=np.float32)
+    lib().orc_voxelize_mesh(_ptr(V), V.shape[0], _ptr(T), T.shape[0], _f(center), float(half_edge),
+                            int(max_depth), _ptr(keys), _ptr(tris), _ptr(cen), n)
+    return keys, tris, cen

@@ -85,3 +85,34 @@ def test_main_loop_replay_matches_oracle(tmp_path, fused):
     assert n_nodes == ref.size
     assert np.array_equal(pool, ref.pool())
     assert np.array_equal(img, ref.raycast(w, h, 45.0, LOOK_PLUS_Z))
+
+
+@pytest.mark.gpu
+def test_scene_voxelize_meshes_replay_matches_oracle(tmp_path):
+    """Scene::voxelizeMeshes(true) (scene.cpp:64-85) through the C++ shim: mesh -> VoxelGrid -> Octree::addVoxelGrid"""
+    P = pkg()
+    V, T = P.synth.icosphere(2, 0.6, (0.9, 0.8, 0.7))  # bbox1.x = 1.5 is the half edge the reference would use
+    mpath = str(tmp_path / "mesh.bin")
+    with open(mpath, "wb") as f:
+        f.write(struct.pack("<ii", V.shape[0], T.shape[0]))
+        f.write(V.tobytes())
+        f.write(T.tobytes())
+    out = str(tmp_path / "mesh_out")
+    log = subprocess.check_output([HOST_MAIN, "mesh", mpath, out], text=True, timeout=120)
+    assert "osl_main: mesh" in log
+    raw = open(out + ".pool", "rb").read()
+    n_nodes, cx, cy, cz, half = struct.unpack("<iffff", raw[:20])
+    pool = np.frombuffer(raw[20:], dtype=np.uint32)
+    # the oracle side of the same call sequence: scale = bbox1.x / 256, Octree(scale, bbox mid, bbox1.x) -> depth 8
+    b0, b1 = V.min(axis=0), V.max(axis=0)
+    center = (b1 + b0) / np.float32(2.0)
+    size = float(b1[0])
+    assert (np.float32(cx), np.float32(cy), np.float32(cz)) == tuple(np.float32(c) for c in center)
+    assert np.float32(half) == np.float32(size)
+    keys, tris, cen = orc.voxelize_mesh(V, T, tuple(center), size, 8)
+    colors = np.zeros((keys.size, 4), dtype=np.float32)
+    colors[:, 1] = np.float32(255 / 255.0)  # no texture: green
+    ref = orc.OracleSVO(tuple(center), size, 8)
+    ref.integrate_voxels(cen, colors)
+    assert n_nodes == ref.size
+    assert np.array_equal(pool, ref.pool())
