@@ -15,7 +15,10 @@ def main():
     import torch
     pkg = graft.load_package()
     lib = pkg.lib()
-    W, H, D, R = 640, 480, 16, 32
+    W = int(sys.argv[1]) if len(sys.argv) > 1 else 640
+    H = int(sys.argv[2]) if len(sys.argv) > 2 else 480
+    D = int(sys.argv[3]) if len(sys.argv) > 3 else 16
+    R = 32
     center, half = pkg.synth.tree_params(D)
     fx, fy = pkg.synth.focal(W, H)
     frames = [pkg.synth.make_frame(W, H, pkg.synth.orbit_pose(k), seed=k) for k in range(R)]
