@@ -237,6 +237,20 @@ def run_ours(args):
     ray_ms = max_over_ranks(r0.elapsed_time(r1) / 10, world)
     st = pkg.RaycastStats()
     svo.raycast(RAY_W, RAY_H, FOV, view, stats=st)
+    # the same map at configs[1]'s render size (1920x1080), rank 0's share of the bands
+    hd_rows = sum(r for _, r in pkg.shard.row_bands(1080, world, rank, pkg.shard.band_height(1080, world)))
+    out_hd = torch.empty((max(hd_rows, 1), 1920, 4), dtype=torch.uint8, device="cuda")
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(2):
+        svo.raycast_bands(out_hd, 1920, 1080, pkg.shard.band_height(1080, world), world, rank, FOV, view, stream=sp)
+    barrier(world)
+    with torch.cuda.stream(stream):
+        h0.record(stream)
+        for _ in range(5):
+            svo.raycast_bands(out_hd, 1920, 1080, pkg.shard.band_height(1080, world), world, rank, FOV, view, stream=sp)
+        h1.record(stream)
+    barrier(world)
+    hd_ms = max_over_ranks(h0.elapsed_time(h1) / 5, world)
     svo.close()
 
     svo2 = pkg.SVO(center, half, DEPTH, reserve_nodes=1 << 24, device=local)
@@ -257,14 +271,21 @@ def run_ours(args):
                    "l2": "inputs cycle through a %d-frame ring (%.0f MB > 126 MB L2)" % (RING, RING * W * H * 5 / 1e6),
                    "multi_gpu": "replicas only: one independent stream+map per rank, no data-path collective",
                    "nodes_after": nodes},
-        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": W * H * 5, "d2h_bytes_per_step": 608},
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": W * H * 5,
+                "d2h_bytes_per_step": int(lib.osl_frame_result_bytes()),
+                "api": "osl_integrate_depth_host: pinned host frames, H2D on the library's copy stream, per-frame "
+                       "result block written by the device into pinned host memory"},
         "gpu_launches": int(launches),
         "raycast": {"mrays_per_s": RAY_W * RAY_H / (ray_ms / 1e3) / 1e6, "ms": ray_ms, "res": [RAY_W, RAY_H],
                     "mode": "ref_exact", "rows": "interleaved bands over %d rank(s)" % world,
                     "steps_per_ray": st.steps / float(st.rays),
-                    "algorithmic_gbs": (4 * st.rays + 4 * st.visits + 4 * st.steps) / (ray_ms / 1e3) / 1e9},
+                    "algorithmic_gbs": (4 * st.rays + 4 * st.visits + 4 * st.steps) / (ray_ms / 1e3) / 1e9,
+                    "at_1920x1080": {"ms": hd_ms, "mrays_per_s": 1920 * 1080 / (hd_ms / 1e3) / 1e6}},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of the four kernels of one frame, one ncu --set full
+                     # capture (profiles/r01_ncu_full_summary_v05.csv; cold caches: ncu flushes L2 between kernels)
+                     "traffic": 2307584, "traffic_source": "profiles/r01_ncu_full_summary_v05.csv",
+                     "peak_source": peak_src,
                      "kernel": "integrate pipeline per frame (k_emit+k_sort+k_structure+k_levels), "
                                "B_int = 5N+8U+68S+68*sum(P_l) per frame",
                      "bytes_per_frame": bytes_alg / float(K),

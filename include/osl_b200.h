@@ -192,6 +192,8 @@ osl_status osl_compute_keys(const float* d_pts, int stride, int n, const float c
 const char* osl_status_string(osl_status s);
 int osl_last_cuda_error(void);
 const char* osl_version(void);
+/* bytes of the per-frame result block the device writes into pinned host memory (sizes, counters) */
+int osl_frame_result_bytes(void);
 /* Profiling aid: SM-clock checkpoints written by CTA 0 of the last k_emit / k_sort_bucket / k_structure / k_levels
  * launches (indices documented in tools/phase_profile.py).  Synchronizes the device. */
 osl_status osl_debug_profile(unsigned long long* out, int n);

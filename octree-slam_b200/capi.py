@@ -23,7 +23,7 @@ EXPORTS = [
     "osl_svo_sync", "osl_svo_join", "osl_svo_view", "osl_svo_size", "osl_svo_download", "osl_svo_upload", "osl_get_counters",
     "osl_raycast", "osl_raycast_host", "osl_raycast_pool", "osl_raycast_rows", "osl_raycast_bands", "osl_extract_voxels", "osl_voxelize_mesh", "osl_free_device", "osl_copy_device",
     "osl_generate_vertex_map", "osl_transform_vertex_map", "osl_point_cloud_bbox", "osl_compute_keys",
-    "osl_status_string", "osl_last_cuda_error", "osl_version", "osl_launch_count", "osl_debug_profile",
+    "osl_status_string", "osl_last_cuda_error", "osl_version", "osl_frame_result_bytes", "osl_launch_count", "osl_debug_profile",
 ]
 
 
@@ -105,6 +105,7 @@ def lib():
         "osl_status_string": (C.c_char_p, [i32]),
         "osl_last_cuda_error": (i32, []),
         "osl_version": (C.c_char_p, []),
+        "osl_frame_result_bytes": (i32, []),
         "osl_launch_count": (i64, []),
         "osl_debug_profile": (i32, [vp, i32]),
     }

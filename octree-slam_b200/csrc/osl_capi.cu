@@ -23,7 +23,8 @@ static osl_status set_device_size(osl_svo* t, int size) {
 
 extern "C" {
 
-const char* osl_version(void) { return "osl_b200 0.2 (sm_100a)"; }
+const char* osl_version(void) { return "osl_b200 0.5 (sm_100a)"; }
+int osl_frame_result_bytes(void) { return (int)sizeof(FrameState); }
 int osl_last_cuda_error(void) { return g_osl_last_cuda_error; }
 int64_t osl_launch_count(void) { return g_osl_launches; }
 
@@ -59,7 +60,7 @@ osl_status osl_svo_create(osl_svo** out, const float center[3], float half_edge,
   const int occ_sort = osl_sort_occupancy(), occ_str = osl_structure_occupancy(), occ_lvl = osl_levels_occupancy();
   if (occ_sort < 1 || occ_str < 1 || occ_lvl < 1) { delete t; return OSL_ERR_CUDA; }
   t->sort_grid = (occ_sort > 4 ? 4 : occ_sort) * t->num_sms;
-  t->structure_grid = (occ_str > 2 ? 2 : occ_str) * t->num_sms;
+  t->structure_grid = (occ_str > 4 ? 4 : occ_str) * t->num_sms;
   t->levels_grid = (occ_lvl > 4 ? 4 : occ_lvl) * t->num_sms;
   osl_status rc = OSL_OK;
   t->hint_emit = t->hint_level = -1;

@@ -158,6 +158,8 @@ k_emit(EmitParams p, TreeParams tp, int vec_ok, u64* __restrict__ keys, u32* __r
 // co-resident as they are for one 640x480 frame).  When a CTA owns a single tile (the per-frame case) the tile lives
 // in registers for the whole pass and the warp-level ranking is done BEFORE the barrier, so only the prefix and the
 // scatter sit behind it.
+__device__ __forceinline__ u32 block_excl_scan_256(u32 v, u32* s_wsum, int lane, int warp);
+
 struct SortTile {
   u64 key[SORT_ITEMS];
   u32 val[SORT_ITEMS], rank[SORT_ITEMS];
@@ -200,7 +202,10 @@ k_sort(u64* kA, u32* pA, u64* kB, u32* pB, u32* cta_hist, const FrameState* fs, 
   __shared__ u32 s_whist[SORT_WARPS][256];
   __shared__ u32 s_run[256];
   __shared__ u32 s_base[256];
+  __shared__ u32 s_goff[256];
   __shared__ u32 s_wsum[SORT_WARPS];
+  __shared__ u64 s_skey[SORT_TILE];  // multi-tile path: the tile staged in digit order
+  __shared__ u32 s_sval[SORT_TILE];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = fs->acc_emit[parity];
@@ -311,7 +316,7 @@ k_sort(u64* kA, u32* pA, u64* kB, u32* pB, u32* cta_hist, const FrameState* fs, 
         sort_load(T, kin, pin, base, lane, n);
         sort_rank(T, s_whist[warp], base, lane, n, shift, lt);
         __syncthreads();
-        {  // digit `tid`: exclusive scan over the warps, advance the running base
+        {  // digit `tid`: exclusive scan over the warps, advance the running base; tile-local order of the digits
           u32 sum = 0;
 #pragma unroll
           for (int w = 0; w < SORT_WARPS; w++) {
@@ -320,18 +325,30 @@ k_sort(u64* kA, u32* pA, u64* kB, u32* pB, u32* cta_hist, const FrameState* fs, 
             sum += v;
           }
           const u32 b = s_run[tid];
-          s_base[tid] = b;
           s_run[tid] = b + sum;
+          const u32 lex = block_excl_scan_256(sum, s_wsum, lane, warp);  // (contains a block barrier)
+          s_base[tid] = lex;      // first tile-local slot of the digit
+          s_goff[tid] = b - lex;  // global position = s_goff[digit] + tile-local slot
         }
         __syncthreads();
+        // stage the tile in digit order in shared memory, then write it out linearly: runs of equal digits go to
+        // consecutive global addresses (coalesced) instead of one 32-byte sector per 8-byte key
 #pragma unroll
         for (int i = 0; i < SORT_ITEMS; i++) {
           if ((base + i * 32 + lane) < n) {
             const u32 digit = (u32)(T.key[i] >> shift) & 0xFFu;
-            const u32 pos = s_base[digit] + s_whist[warp][digit] + T.rank[i];
-            kout[pos] = T.key[i];
-            pout[pos] = T.val[i];
+            const u32 lp = s_base[digit] + s_whist[warp][digit] + T.rank[i];
+            s_skey[lp] = T.key[i];
+            s_sval[lp] = T.val[i];
           }
+        }
+        __syncthreads();
+        const int cnt = min(SORT_TILE, n - tile * SORT_TILE);
+        for (int l = tid; l < cnt; l += SORT_THREADS) {
+          const u64 k = s_skey[l];
+          const u32 pos = s_goff[(u32)(k >> shift) & 0xFFu] + (u32)l;
+          kout[pos] = k;
+          pout[pos] = s_sval[l];
         }
         __syncthreads();
       }
@@ -603,19 +620,18 @@ __device__ __forceinline__ int walk_frontier(const u32* __restrict__ pool, u64 k
 //   phase A  (per virtual block of 512 sorted keys) common-prefix length m with the predecessor, lowest payload of
 //            each run of equal keys, frontier depth s from a walk of the pre-frame tree, per-block counts of level
 //            heads and (s, depth) split buckets
-//   exchange small frames (<= AN_FLAG_MAX virtual blocks): every block publishes its count vector behind a flag and
-//            every CTA sums all vectors itself (totals + its own exclusive prefix) -- one wait, no grid barrier;
-//            large frames: grid barrier, one warp per counter scans its column over the blocks, grid barrier
+//   exchange every CTA owns a contiguous range of blocks, publishes the counter vector of its range behind an epoch
+//            flag and sums all CTAs' vectors itself (totals + its own exclusive prefix) -- one wait, no grid barrier
+//            and no per-block counters in global memory
 //   phase B2 every CTA derives the allocation plan from the totals (bucket bases in the reference's order:
 //            pass = depth - s, then numeric key); CTA 0 publishes the FrameState; overflow => nothing is written
 //   phase C  dense per-level node lists with deterministic child-tile indices; tiles allocated this frame are
 //            initialised here (svo.cu:272-275) -- they lie beyond the pre-frame pool, which is all phase C reads
-#define AN_FLAG_MAX 160
 
 __device__ __forceinline__ void analyze_block(int vb, int n, const u64* __restrict__ keys, u32* pay, int mode,
                                               const u32* pool, const TreeParams& tp, uint8_t* __restrict__ m8,
                                               uint8_t* __restrict__ s8, u32* __restrict__ start,
-                                              u32* __restrict__ blockcnt, u32* s_cnt) {
+                                              u32* s_ctot, u32* s_cnt) {
   const int D = tp.D, NC = OSL_NCOUNT(D);
   for (int c = threadIdx.x; c < NC; c += AN_THREADS) s_cnt[c] = 0;
   __syncthreads();
@@ -660,7 +676,7 @@ __device__ __forceinline__ void analyze_block(int vb, int n, const u64* __restri
     }
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < NC; c += AN_THREADS) blockcnt[(size_t)vb * NC + c] = s_cnt[c];
+  for (int c = threadIdx.x; c < NC; c += AN_THREADS) s_ctot[c] += s_cnt[c];  // this CTA's running total
   __syncthreads();
 }
 
@@ -668,7 +684,7 @@ __device__ __forceinline__ void analyze_block(int vb, int n, const u64* __restri
 __device__ __forceinline__ void assign_block(int vb, int n, const u64* __restrict__ keys, const u32* pay, u32* pool,
                                              const TreeParams& tp, const uint8_t* __restrict__ m8,
                                              const uint8_t* __restrict__ s8, const u32* __restrict__ start,
-                                             const u32* s_base, const LevelArrays& lv, int mode, u32 size0,
+                                             u32* s_base, const LevelArrays& lv, int mode, u32 size0,
                                              int n_invalid_front, const u32* s_plan, u32 (*s_w)[NC_MAX]) {
   const int D = tp.D, NC = OSL_NCOUNT(D);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -704,6 +720,7 @@ __device__ __forceinline__ void assign_block(int vb, int n, const u64* __restric
       s_w[w][c] = run;
       run += v;
     }
+    s_base[c] = run - s_plan[c];  // exclusive prefix of the CTA's NEXT block
   }
   __syncthreads();
   // pass 2: down the levels this key heads (d > m), resuming the walk of phase A at depth m+1; existing child tiles
@@ -771,13 +788,13 @@ __device__ __forceinline__ u32 ld_vol(const u32* p) { return *(const volatile u3
 
 __global__ void __launch_bounds__(AN_THREADS)
 k_structure(const u64* __restrict__ keys, u32* pay, u32* pool, TreeParams tp, FrameState* fs, FrameState* fr,
-            FrameState* hr, uint8_t* m8, uint8_t* s8, u32* start, u32* blockcnt, u32* totals, u32* flags, u32 epoch, LevelArrays lv,
+            FrameState* hr, uint8_t* m8, uint8_t* s8, u32* start, u32* ctatot, u32* flags, u32 epoch, LevelArrays lv,
             int mode, int capacity, int n_in, int parity, u64* split_out) {
-  cg::grid_group grid = cg::this_grid();
   __shared__ u32 s_w[AN_WARPS][NC_MAX];
   __shared__ u32 s_plan[NC_MAX];
   __shared__ u32 s_tot[NC_MAX];
   __shared__ u32 s_base[NC_MAX];
+  __shared__ u32 s_ctot[NC_MAX];
   __shared__ u32 s_scan[AN_WARPS];
   const int D = tp.D, NC = OSL_NCOUNT(D);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -788,83 +805,56 @@ k_structure(const u64* __restrict__ keys, u32* pay, u32* pool, TreeParams tp, Fr
   const u32 size0 = (u32)(cur > 8 ? cur : 8);
   const int nvb = (n + AN_THREADS - 1) / AN_THREADS;
   const int G = gridDim.x;
-  const bool flagpath = nvb <= AN_FLAG_MAX;
+  // every CTA owns a CONTIGUOUS range of virtual blocks: the exclusive prefix of its first block is the sum of the
+  // lower CTAs' totals, and the prefix of each further block follows by adding the previous block's counts
+  const int per = (nvb + G - 1) / G;
+  const int vb0 = min(nvb, (int)blockIdx.x * per), vb1 = min(nvb, vb0 + per);
 
   PROF(16);
   // splitters for k_sort_bucket of a later frame: BK_BUCKETS-quantiles of this frame's sorted keys
   if (blockIdx.x == G - 1 && tid < BK_BUCKETS - 1 && n >= BK_BUCKETS)
     split_out[tid] = keys[(size_t)(((long long)(tid + 1) * n) / BK_BUCKETS)];
-  for (int vb = blockIdx.x; vb < nvb; vb += G) {
-    analyze_block(vb, n, keys, pay, mode, pool, tp, m8, s8, start, blockcnt, &s_w[0][0]);
-    if (flagpath && tid == 0) {  // publish (analyze_block ends with a block barrier after the stores)
-      __threadfence();
-      *(volatile u32*)&flags[vb] = epoch;
-    }
+  for (int c = tid; c < NC; c += AN_THREADS) s_ctot[c] = 0;
+  __syncthreads();
+  for (int vb = vb0; vb < vb1; vb++)
+    analyze_block(vb, n, keys, pay, mode, pool, tp, m8, s8, start, s_ctot, &s_w[0][0]);
+  // publish this CTA's counter vector behind an epoch flag (every CTA publishes, also one without blocks)
+  for (int c = tid; c < NC; c += AN_THREADS) ctatot[(size_t)blockIdx.x * NC + c] = s_ctot[c];
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    *(volatile u32*)&flags[blockIdx.x] = epoch;
   }
   PROF(17);
 
-  if (flagpath) {
-    // wait for every block's vector, then sum them: totals for the plan, exclusive prefix for the own block(s)
-    if (warp == 0) {
-      for (int b = lane; b < nvb; b += 32)
-        while (ld_vol(&flags[b]) != epoch) {}
-      __threadfence();
-    }
-    __syncthreads();
-    PROF(18);
-    for (int c = tid; c < NC; c += AN_THREADS) {
-      u32 tot = 0, pre = 0;
-      const int mine = (int)blockIdx.x;
-      for (int b0 = 0; b0 < nvb; b0 += 16) {
-        u32 v[16];
-#pragma unroll
-        for (int k = 0; k < 16; k++) v[k] = (b0 + k < nvb) ? __ldcg(&blockcnt[(size_t)(b0 + k) * NC + c]) : 0u;
-#pragma unroll
-        for (int k = 0; k < 16; k++) {
-          tot += v[k];
-          if (b0 + k < mine) pre += v[k];
-        }
-      }
-      s_tot[c] = tot;
-      s_base[c] = pre;
-    }
-    __syncthreads();
-    PROF(19);
-    PROF(20);
-  } else {
-    grid.sync();
-    PROF(18);
-    // phase B: column scans, one warp per counter, 4 independent loads per lane in flight
-    for (int c = blockIdx.x * AN_WARPS + warp; c < NC; c += G * AN_WARPS) {
-      u32 carry = 0;
-      for (int b0 = 0; b0 < nvb; b0 += 128) {
-        u32 v[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          const int b = b0 + k * 32 + lane;
-          v[k] = (b < nvb) ? __ldcg(&blockcnt[(size_t)b * NC + c]) : 0u;
-        }
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          u32 incl = v[k];
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const u32 t = __shfl_up_sync(FULL, incl, o);
-            if (lane >= o) incl += t;
-          }
-          const int b = b0 + k * 32 + lane;
-          if (b < nvb) blockcnt[(size_t)b * NC + c] = carry + incl - v[k];
-          carry += __shfl_sync(FULL, incl, 31);
-        }
-      }
-      if (lane == 0) totals[c] = carry;
-    }
-    PROF(19);
-    grid.sync();
-    PROF(20);
-    for (int c = tid; c < NC; c += AN_THREADS) s_tot[c] = __ldcg(&totals[c]);
-    __syncthreads();
+  // wait for every CTA's vector (all CTAs are co-resident: cooperative launch), then sum them: totals for the plan,
+  // exclusive prefix for the own range -- one wait, no grid barrier
+  if (warp == 0) {
+    for (int b = lane; b < G; b += 32)
+      while (ld_vol(&flags[b]) != epoch) {}
+    __threadfence();
   }
+  __syncthreads();
+  PROF(18);
+  for (int c = tid; c < NC; c += AN_THREADS) {
+    u32 tot = 0, pre = 0;
+    const int mine = (int)blockIdx.x;
+    for (int b0 = 0; b0 < G; b0 += 16) {
+      u32 v[16];
+#pragma unroll
+      for (int k = 0; k < 16; k++) v[k] = (b0 + k < G) ? __ldcg(&ctatot[(size_t)(b0 + k) * NC + c]) : 0u;
+#pragma unroll
+      for (int k = 0; k < 16; k++) {
+        tot += v[k];
+        if (b0 + k < mine) pre += v[k];
+      }
+    }
+    s_tot[c] = tot;
+    s_base[c] = pre;
+  }
+  __syncthreads();
+  PROF(19);
+  PROF(20);
 
   // phase B2: the allocation plan.  Entry e = i*D + (d-1) in the reference's order (pass i, then depth d):
   // bucket (s = d - i, d).  Exclusive scan over the <= D*D entries gives each bucket's first global rank.
@@ -898,21 +888,8 @@ k_structure(const u64* __restrict__ keys, u32* pay, u32* pool, TreeParams tp, Fr
   const bool overflow = after > (long long)capacity;
   PROF(21);
   if (!overflow) {
-    int prev_vb = (int)blockIdx.x;
-    for (int vb = blockIdx.x; vb < nvb; vb += G) {
-      if (!flagpath) {
-        for (int c = tid; c < NC; c += AN_THREADS) s_base[c] = __ldcg(&blockcnt[(size_t)vb * NC + c]);
-      } else if (vb != prev_vb) {  // a CTA with several blocks: extend the prefix by the blocks in between
-        for (int c = tid; c < NC; c += AN_THREADS) {
-          u32 pre = s_base[c];
-          for (int b = prev_vb; b < vb; b++) pre += __ldcg(&blockcnt[(size_t)b * NC + c]);
-          s_base[c] = pre;
-        }
-        prev_vb = vb;
-      }
-      __syncthreads();
+    for (int vb = vb0; vb < vb1; vb++)
       assign_block(vb, n, keys, pay, pool, tp, m8, s8, start, s_base, lv, mode, size0, n_invalid_front, s_plan, s_w);
-    }
   }
   PROF(22);
 
@@ -1176,11 +1153,11 @@ osl_status osl_ensure_workspace(osl_svo* t, size_t n) {
   OSL_CUDA(cudaMalloc(&t->d_payC, cap * sizeof(u32)));
   OSL_CUDA(cudaMalloc(&t->d_m, cap));
   OSL_CUDA(cudaMalloc(&t->d_s, cap));
-  const size_t nblocks = (cap + AN_THREADS - 1) / AN_THREADS;
-  OSL_CUDA(cudaMalloc(&t->d_blockcnt, nblocks * OSL_NCOUNT(D) * sizeof(u32)));
+  const size_t nctas = (size_t)(t->structure_grid > 0 ? t->structure_grid : 1);
+  OSL_CUDA(cudaMalloc(&t->d_blockcnt, nctas * OSL_NCOUNT(D) * sizeof(u32)));  // one counter vector per CTA
   OSL_CUDA(cudaMalloc(&t->d_start, cap * sizeof(u32)));
-  OSL_CUDA(cudaMalloc(&t->d_flags, nblocks * sizeof(u32)));
-  OSL_CUDA(cudaMemset(t->d_flags, 0, nblocks * sizeof(u32)));  // epoch-tagged (frame number + 1), never reset
+  OSL_CUDA(cudaMalloc(&t->d_flags, nctas * sizeof(u32)));
+  OSL_CUDA(cudaMemset(t->d_flags, 0, nctas * sizeof(u32)));  // epoch-tagged (frame number + 1), never reset
   for (int b = 0; b < OSL_BACK; b++) {
     LevelArrays& lv = t->lv[b];
     size_t total = 0;
@@ -1463,11 +1440,11 @@ osl_status osl_run_integrate(osl_svo* t, EmitParams& ep, const void* colors, cud
     const u64* a0 = skeys; u32* a1 = spay; u32* a2 = t->d_pool; TreeParams a3 = t->tp; FrameState* a4 = fs;
     FrameState* a4b = fr;
     uint8_t* a5 = t->d_m; uint8_t* a6 = t->d_s; u32* a6b = t->d_start; u32* a7 = t->d_blockcnt;
-    u32* a8 = t->d_scan_totals; u32* a8b = t->d_flags; u32 a8c = (u32)(f + 1);
+    u32* a8b = t->d_flags; u32 a8c = (u32)(f + 1);
     LevelArrays a9 = lv; int a10 = ep.mode; int a11 = (int)t->cap_nodes; int a12 = n; int a13 = fslot;
     u64* a14 = t->d_split + fslot * BK_BUCKETS;
     FrameState* a4c = &t->h_ring[f % OSL_RING];  // pinned host memory, device-accessible (UVA)
-    void* args[] = {&a0, &a1, &a2, &a3, &a4, &a4b, &a4c, &a5, &a6, &a6b, &a7, &a8, &a8b, &a8c, &a9, &a10, &a11, &a12,
+    void* args[] = {&a0, &a1, &a2, &a3, &a4, &a4b, &a4c, &a5, &a6, &a6b, &a7, &a8b, &a8c, &a9, &a10, &a11, &a12,
                     &a13, &a14};
     OSL_CUDA(cudaLaunchCooperativeKernel((void*)k_structure, dim3(grid), dim3(AN_THREADS), args, 0, sS));
     OSL_LAUNCHED(1);
