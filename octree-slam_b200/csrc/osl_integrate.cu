@@ -4,16 +4,18 @@
 // image kernels that feed it (image_kernels.cu:24-53,206-215).  Same results (node indices, node words), very
 // different structure -- see DESIGN.md section 3:
 //
-//   k_emit       back-project + pose + Morton key per input, ordered compaction of the valid ones (look-back scan)
-//   k_sort       ONE cooperative persistent kernel: LSD radix sort (8-bit digits) of (key, payload), all passes
-//   k_structure  ONE cooperative kernel: per sorted key the common-prefix length with its predecessor (=> which tree
-//                levels it heads) and the frontier depth from a walk of the pre-frame tree; scan of per-block counts;
-//                allocation plan in the reference's order (pass = depth - frontier depth, then numeric key);
-//                dense per-level node lists with deterministic child-tile indices; overflow check
-//   k_levels     ONE cooperative kernel, bottom-up, one thread per touched node: read/initialise its 64-byte child
-//                tile, blend leaves, link new tiles, mip-map (integer mean / max), write the tile back
-// A frame is 4 kernel launches + 1 memset + 1 small D2H, all asynchronous on the caller's stream; the host never
-// waits for the device unless the pool has to grow or the caller asks for sizes / counters.
+//   k_emit        back-project + pose + Morton key per input; tile-local de-duplication in a shared-memory hash
+//   k_sort_bucket barrier-free sort of the (small) de-duplicated key list: splitter ranges, one CTA per range
+//   k_sort        cooperative multi-CTA LSD radix sort (8-bit digits) for large lists (voxel grids, first frames)
+//   k_structure   cooperative: per sorted key the common-prefix length with its predecessor (=> which tree levels it
+//                 heads) and the frontier depth from ONE walk of the pre-frame tree; per-CTA counter vectors behind
+//                 flags; allocation plan in the reference's order (pass = depth - frontier depth, then numeric key);
+//                 dense per-level node lists with deterministic node / child-tile indices; child pointers and the
+//                 value words of new tiles written here -- after this kernel the tree's STRUCTURE (word0) is final
+//   k_levels      cooperative, bottom-up, VALUES only (word1): leaf blends, integer mean / max per touched node
+// A frame is 4 kernel launches, asynchronous; in pipelined mode the four stages of consecutive frames overlap on four
+// streams (osl_run_integrate).  The host never waits for the device unless the pool has to grow, the caller asks for
+// sizes / counters, or it runs more than 3 frames ahead.
 #include <cooperative_groups.h>
 
 #include "osl_internal.cuh"
@@ -27,15 +29,16 @@ __device__ unsigned long long g_osl_prof[64];
 #define PROF(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_osl_prof[i] = (unsigned long long)clock64(); } while (0)
 
 // ------------------------------------------------------------------------------------------------ k_emit
-// One CTA per 64x32-pixel tile (mode 0) or per 2048 consecutive inputs (modes 1, 2); 8 inputs per thread.
+// One CTA per 64x32-pixel tile (mode 0) or per 2048 consecutive inputs (modes 1, 2); 4 inputs per thread (16 warps per
+// CTA hide the latency of the dependent float descent better than 8 inputs on 8 warps).
 // Back-projection + pose + Morton key in registers, then the tile's keys are DE-DUPLICATED in a shared-memory hash
 // table (64-bit CAS on the key, atomicMin on the input index): a 1 cm leaf is seen by ~20 neighbouring pixels of a
 // 640x480 frame, so ~2048 pixels collapse to ~150 (key, lowest pixel) entries before anything is sorted.  Tiles
 // append their entries to the key list with one atomicAdd; the order of the list is irrelevant because the sort is by
 // key and k_structure takes the MINIMUM payload of every run of equal keys (canonical Q7: lowest pixel wins).
 // Mode 2 (voxel grid, Q11: colour j goes to the j-th smallest key) must keep duplicates and only compacts.
-#define EMIT_THREADS 256
-#define EMIT_PPT 8
+#define EMIT_THREADS 512
+#define EMIT_PPT 4
 #define EMIT_TILE (EMIT_THREADS * EMIT_PPT)
 #define EMIT_TW 64
 #define EMIT_TH 32
@@ -68,13 +71,12 @@ k_emit(EmitParams p, TreeParams tp, int vec_ok, u64* __restrict__ keys, u32* __r
   int first;  // input index of this thread's first element (its 8 elements are consecutive)
   if (p.mode == 0) {
     const int tx = blockIdx.x % p.tiles_x, ty = blockIdx.x / p.tiles_x;
-    const int y = ty * EMIT_TH + (tid >> 3), x0 = tx * EMIT_TW + (tid & 7) * EMIT_PPT;
+    const int y = ty * EMIT_TH + tid / (EMIT_TW / EMIT_PPT), x0 = tx * EMIT_TW + (tid % (EMIT_TW / EMIT_PPT)) * EMIT_PPT;
     first = y * p.w + x0;
     int dv[EMIT_PPT];
-    if (y < p.h && vec_ok && x0 + EMIT_PPT <= p.w) {  // 128-bit load of 8 depth pixels
-      const uint4 q = __ldg(reinterpret_cast<const uint4*>(p.depth + first));
+    if (y < p.h && vec_ok && x0 + EMIT_PPT <= p.w) {  // one 64-bit load of 4 depth pixels (a warp reads 256 B)
+      const uint2 q = __ldg(reinterpret_cast<const uint2*>(p.depth + first));
       dv[0] = q.x & 0xFFFF; dv[1] = q.x >> 16; dv[2] = q.y & 0xFFFF; dv[3] = q.y >> 16;
-      dv[4] = q.z & 0xFFFF; dv[5] = q.z >> 16; dv[6] = q.w & 0xFFFF; dv[7] = q.w >> 16;
     } else {
 #pragma unroll
       for (int i = 0; i < EMIT_PPT; i++) dv[i] = (y < p.h && x0 + i < p.w) ? (int)__ldg(p.depth + first + i) : 0;
@@ -924,7 +926,6 @@ k_structure(const u64* __restrict__ keys, u32* pay, u32* pool, TreeParams tp, Fr
         o->capacity = capacity;
         o->size_after = (int)min(after, (long long)0x7FFFFFFF);
         o->overflow = overflow ? 1 : 0;
-        o->fresh = cur == 0 ? 1 : 0;
         o->frame_seq = seq;
         o->cur_size = overflow ? cur : (int)after;
       }
@@ -1399,7 +1400,7 @@ osl_status osl_run_integrate(osl_svo* t, EmitParams& ep, const void* colors, cud
     int vec_ok = 0;
     int etiles;
     if (ep.mode == 0) {
-      vec_ok = ((reinterpret_cast<uintptr_t>(ep.depth) & 15) == 0) && (ep.w % 8 == 0);
+      vec_ok = ((reinterpret_cast<uintptr_t>(ep.depth) & 7) == 0) && (ep.w % 4 == 0);
       ep.tiles_x = (ep.w + EMIT_TW - 1) / EMIT_TW;
       ep.tiles_y = (ep.h + EMIT_TH - 1) / EMIT_TH;
       etiles = ep.tiles_x * ep.tiles_y;

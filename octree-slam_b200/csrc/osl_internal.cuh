@@ -38,7 +38,6 @@ struct FrameState {
   int overflow;     // 1: size_after exceeds the pool capacity -> nothing was written
   int capacity;     // nodes
   int cur_size;     // nodes in the pool (persistent across frames; 0 = fresh tree)
-  int fresh;        // this frame started from an empty tree (root tile is zero-initialised)
   int frame_seq;    // frames processed
   int n_level[OSL_MAXD + 2];                  // n_level[d] = distinct touched nodes at depth d (d = 1..D)
   int pass_count[OSL_MAXD + 1];               // |codes[i]| of reference pass i
@@ -162,9 +161,9 @@ struct osl_svo {
   uint8_t *d_m, *d_s;
   u32* d_start;       // per sorted key: node at the first depth it heads (k_structure phase A -> C)
   u32* d_flags;       // per virtual block: epoch of the frame whose count vector is published
-  u32* d_blockcnt;    // [blocks][NC]
+  u32* d_blockcnt;    // [k_structure CTAs][NC] per-CTA counter vectors
   u32* d_cta_hist[OSL_FRONT];  // sort: [grid][256]
-  u32* d_scan_totals; // k_scan: [NC_MAX] totals + 1 ticket word
+  u32* d_scan_totals; // [NC_MAX + 8] scratch words; word NC_MAX = arrival counter of k_levels' one-sided barrier
   LevelArrays lv[OSL_BACK];
   void* d_level_mem[OSL_BACK];
   FrameState* d_fs;                      // [0] persistent part (slot counters, cur_size), [1 + b] result block of slot b
