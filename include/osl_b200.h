@@ -128,6 +128,11 @@ int osl_svo_size(const osl_svo* t); /* nodes; synchronizes */
 osl_status osl_svo_download(const osl_svo* t, uint32_t* h_pool, int cap_nodes);
 osl_status osl_svo_upload(osl_svo* t, const uint32_t* h_pool, int n_nodes);
 osl_status osl_get_counters(const osl_svo* t, osl_counters* out);
+/* Checkpoint / resume: 32-byte header (magic, max_depth, n_nodes, centre, half edge) + the flat 2*n uint32 pool (the
+ * array OctreeNode::pullToCPU / pushToGPU exchange, octree.cpp:41-169).  osl_svo_load requires a tree created with
+ * the same max_depth / centre / half edge. */
+osl_status osl_svo_save(const osl_svo* t, const char* path);
+osl_status osl_svo_load(osl_svo* t, const char* path);
 
 /* ---- raycast (cone_tracing_kernels.h:16) ------------------------------------------------------------------- */
 

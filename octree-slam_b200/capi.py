@@ -20,7 +20,7 @@ STATUS = {0: "OSL_OK", -1: "OSL_ERR_INVALID", -2: "OSL_ERR_CUDA", -3: "OSL_ERR_O
 EXPORTS = [
     "osl_svo_create", "osl_svo_destroy", "osl_svo_reset", "osl_svo_set_quirks", "osl_svo_set_pipeline", "osl_svo_set_stage_timing", "osl_get_stage_times",
     "osl_integrate_depth", "osl_integrate_depth_host", "osl_integrate_points", "osl_integrate_voxels",
-    "osl_svo_sync", "osl_svo_join", "osl_svo_view", "osl_svo_size", "osl_svo_download", "osl_svo_upload", "osl_get_counters",
+    "osl_svo_sync", "osl_svo_join", "osl_svo_view", "osl_svo_size", "osl_svo_download", "osl_svo_upload", "osl_get_counters", "osl_svo_save", "osl_svo_load",
     "osl_raycast", "osl_raycast_host", "osl_raycast_pool", "osl_raycast_rows", "osl_raycast_bands", "osl_extract_voxels", "osl_voxelize_mesh", "osl_free_device", "osl_copy_device",
     "osl_generate_vertex_map", "osl_transform_vertex_map", "osl_point_cloud_bbox", "osl_compute_keys",
     "osl_status_string", "osl_last_cuda_error", "osl_version", "osl_frame_result_bytes", "osl_launch_count", "osl_debug_profile",
@@ -85,6 +85,8 @@ def lib():
         "osl_svo_download": (i32, [vp, vp, i32]),
         "osl_svo_upload": (i32, [vp, vp, i32]),
         "osl_get_counters": (i32, [vp, C.POINTER(Counters)]),
+        "osl_svo_save": (i32, [vp, C.c_char_p]),
+        "osl_svo_load": (i32, [vp, C.c_char_p]),
         "osl_raycast": (i32, [vp, vp, i32, i32, f32, fp, C.POINTER(RaycastParams), vp]),
         "osl_raycast_host": (i32, [vp, vp, i32, i32, f32, fp, C.POINTER(RaycastParams), C.POINTER(RaycastStats), vp]),
         "osl_raycast_rows": (i32, [vp, vp, i32, i32, i32, i32, f32, fp, C.POINTER(RaycastParams),

@@ -311,6 +311,65 @@ osl_status osl_svo_upload(osl_svo* t, const uint32_t* h_pool, int n_nodes) {
   return set_device_size(t, n_nodes);
 }
 
+// Checkpoint / resume (the reference has none; its de-facto wire format is the flat 2*n uint
+// array OctreeNode::pullToCPU/pushToGPU exchange, octree.cpp:41-169).  File = 32-byte header + that array.
+struct osl_file_header {
+  char magic[8];      // "OSLSVO1\0"
+  int32_t max_depth;
+  int32_t n_nodes;
+  float center[3];
+  float half_edge;
+};
+
+osl_status osl_svo_save(const osl_svo* tc, const char* path) {
+  osl_svo* t = const_cast<osl_svo*>(tc);
+  if (!t || !path) return OSL_ERR_INVALID;
+  OSL_CUDA(cudaSetDevice(t->device));
+  osl_status rc = drain(t);
+  if (rc) return rc;
+  OSL_CUDA(cudaDeviceSynchronize());
+  osl_file_header h;
+  memset(&h, 0, sizeof(h));
+  memcpy(h.magic, "OSLSVO1", 8);
+  h.max_depth = t->tp.D; h.n_nodes = t->size;
+  h.center[0] = t->tp.cx; h.center[1] = t->tp.cy; h.center[2] = t->tp.cz; h.half_edge = t->tp.half;
+  FILE* f = fopen(path, "wb");
+  if (!f) return OSL_ERR_INVALID;
+  bool ok = fwrite(&h, sizeof(h), 1, f) == 1;
+  const size_t chunk_nodes = (size_t)1 << 22;  // 32 MB staging
+  uint32_t* buf = (uint32_t*)malloc(chunk_nodes * 8);
+  if (!buf) { fclose(f); return OSL_ERR_OOM; }
+  for (size_t off = 0; ok && off < (size_t)t->size; off += chunk_nodes) {
+    const size_t cnt = ((size_t)t->size - off < chunk_nodes) ? (size_t)t->size - off : chunk_nodes;
+    if (cudaMemcpy(buf, t->d_pool + 2 * off, cnt * 8, cudaMemcpyDeviceToHost) != cudaSuccess) { ok = false; break; }
+    ok = fwrite(buf, 8, cnt, f) == cnt;
+  }
+  free(buf);
+  ok = (fclose(f) == 0) && ok;
+  return ok ? OSL_OK : OSL_ERR_INVALID;
+}
+
+// Loads a checkpoint into an existing tree; max_depth, centre and half edge must match the tree's (they define the
+// meaning of every node index).  `t` may hold anything before: it is replaced.
+osl_status osl_svo_load(osl_svo* t, const char* path) {
+  if (!t || !path) return OSL_ERR_INVALID;
+  FILE* f = fopen(path, "rb");
+  if (!f) return OSL_ERR_INVALID;
+  osl_file_header h;
+  if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "OSLSVO1", 8) != 0 || h.n_nodes < 0 || h.max_depth != t->tp.D ||
+      h.center[0] != t->tp.cx || h.center[1] != t->tp.cy || h.center[2] != t->tp.cz || h.half_edge != t->tp.half) {
+    fclose(f);
+    return OSL_ERR_INVALID;
+  }
+  uint32_t* buf = (uint32_t*)malloc((size_t)(h.n_nodes > 0 ? h.n_nodes : 1) * 8);
+  if (!buf) { fclose(f); return OSL_ERR_OOM; }
+  const bool ok = fread(buf, 8, (size_t)h.n_nodes, f) == (size_t)h.n_nodes;
+  fclose(f);
+  osl_status rc = ok ? osl_svo_upload(t, buf, h.n_nodes) : OSL_ERR_INVALID;
+  free(buf);
+  return rc;
+}
+
 osl_status osl_get_counters(const osl_svo* tc, osl_counters* out) {
   osl_svo* t = const_cast<osl_svo*>(tc);
   if (!t || !out) return OSL_ERR_INVALID;

@@ -131,6 +131,12 @@ class SVO:
         """order `stream` after every frame enqueued so far (device-side)"""
         _check(lib().osl_svo_join(self._h, stream), "osl_svo_join")
 
+    def save(self, path):
+        _check(lib().osl_svo_save(self._h, str(path).encode()), "osl_svo_save")
+
+    def restore(self, path):
+        _check(lib().osl_svo_load(self._h, str(path).encode()), "osl_svo_load")
+
     def sync(self):
         _check(lib().osl_svo_sync(self._h), "osl_svo_sync")
 

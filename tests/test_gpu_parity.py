@@ -523,3 +523,35 @@ def test_cfg3_orbit_depth14_incremental_matches_oracle(P):
         svo.integrate_depth(keep[k][0], keep[k][1], fx, fy, P.synth.orbit_pose(k))
     assert svo.size == ref.size
     assert np.array_equal(svo.pool(), ref.pool())
+
+
+def test_checkpoint_resume_continues_bit_exactly(P, tmp_path):
+    """save after 3 frames, restore into a fresh tree, integrate 3 more on both: identical pools (and == oracle)"""
+    D, w, h = 10, 160, 120
+    center, half = P.synth.tree_params(D)
+    fx, fy = P.synth.focal(w, h)
+    frames = []
+    for k in range(6):
+        pose = P.synth.orbit_pose(12 * k)
+        depth, rgb = P.synth.make_frame(w, h, pose, seed=k)
+        frames.append((depth, rgb, pose))
+    a = P.SVO(center, half, D)
+    ref = orc.OracleSVO(center, half, D)
+    for depth, rgb, pose in frames[:3]:
+        a.integrate_depth(depth, rgb, fx, fy, pose)
+    path = tmp_path / "map.oslsvo"
+    a.save(path)
+    b = P.SVO(center, half, D)
+    b.restore(path)
+    assert b.size == a.size and np.array_equal(a.pool(), b.pool())
+    for depth, rgb, pose in frames[3:]:
+        a.integrate_depth(depth, rgb, fx, fy, pose)
+        b.integrate_depth_host(depth, rgb, fx, fy, pose)
+    for depth, rgb, pose in frames:
+        ref.integrate_depth(depth, rgb, fx, fy, pose)
+    assert np.array_equal(a.pool(), b.pool())
+    assert np.array_equal(a.pool(), ref.pool())
+    # a checkpoint of another tree geometry is refused
+    c = P.SVO(center, half, D + 1)
+    with pytest.raises(P.OslError):
+        c.restore(path)
