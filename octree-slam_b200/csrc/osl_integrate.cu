@@ -47,8 +47,8 @@ __device__ unsigned long long g_osl_prof[64];
 #define EMIT_SMEM (EMIT_SLOTS * 8 + EMIT_SLOTS * 4 + EMIT_TILE * 2)
 
 __global__ void __launch_bounds__(EMIT_THREADS)
-k_emit(EmitParams p, TreeParams tp, int vec_ok, u64* __restrict__ keys, u32* __restrict__ pay, FrameState* fs,
-       int parity) {
+k_emit(EmitParams p, TreeParams tp, int vec_ok, u64* __restrict__ keys, u32* __restrict__ pay,
+       u64* __restrict__ keys_dense, FrameState* fs, int parity) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   u64* s_key = reinterpret_cast<u64*>(s_raw);
   u32* s_pay = reinterpret_cast<u32*>(s_raw + EMIT_SLOTS * 8);
@@ -91,6 +91,7 @@ k_emit(EmitParams p, TreeParams tp, int vec_ok, u64* __restrict__ keys, u32* __r
     }
   } else {
     first = blockIdx.x * EMIT_TILE + tid * EMIT_PPT;
+    bool bad = false;  // mode 2: an invalid input, or a key smaller than its predecessor's
 #pragma unroll
     for (int i = 0; i < EMIT_PPT; i++) {
       const int idx = first + i;
@@ -99,8 +100,24 @@ k_emit(EmitParams p, TreeParams tp, int vec_ok, u64* __restrict__ keys, u32* __r
       if (idx < p.n) {
         const float* q = p.pts + (size_t)p.stride * idx;
         ok = osl_key(__ldg(q), __ldg(q + 1), __ldg(q + 2), tp, k[i]);
+        bad |= !ok || (i > 0 && k[i] < k[i - 1]);
       }
       vmask |= (u32)ok << i;
+    }
+    if (p.mode == 2) {
+      // Voxel grids usually arrive in Morton order already (the voxeliser and the extraction emit them that way):
+      // keep a dense copy in input order and tell k_sort / k_structure when it is sorted and gap-free, so the whole
+      // radix sort is skipped (svoFromVoxelGrid's own sort, svo.cu:602, is then the identity as well).
+      if (first < p.n && first > 0) {  // the predecessor of this thread's first input
+        const float* q = p.pts + (size_t)p.stride * (first - 1);
+        u64 kp;
+        const bool okp = osl_key(__ldg(q), __ldg(q + 1), __ldg(q + 2), tp, kp);
+        bad |= okp && (vmask & 1u) && k[0] < kp;
+      }
+#pragma unroll
+      for (int i = 0; i < EMIT_PPT; i++)
+        if (first + i < p.n) keys_dense[first + i] = k[i];
+      if (__any_sync(FULL, bad) && lane == 0) atomicOr(reinterpret_cast<u32*>(&fs->acc_unsorted[parity]), 1u);
     }
   }
   __syncthreads();
@@ -198,8 +215,9 @@ __device__ __forceinline__ void sort_rank(SortTile& t, u32* whist, int base, int
 }
 
 __global__ void __launch_bounds__(SORT_THREADS)
-k_sort(u64* kA, u32* pA, u64* kB, u32* pB, u32* cta_hist, const FrameState* fs, int passes, int parity) {
+k_sort(u64* kA, u32* pA, u64* kB, u32* pB, u32* cta_hist, const FrameState* fs, int passes, int parity, int mode) {
   cg::grid_group grid = cg::this_grid();
+  if (mode == 2 && fs->acc_unsorted[parity] == 0) return;  // k_emit's dense copy is already sorted (uniform exit)
   __shared__ u32 s_hist[256];
   __shared__ u32 s_whist[SORT_WARPS][256];
   __shared__ u32 s_run[256];
@@ -789,9 +807,9 @@ __device__ __forceinline__ void assign_block(int vb, int n, const u64* __restric
 __device__ __forceinline__ u32 ld_vol(const u32* p) { return *(const volatile u32*)p; }
 
 __global__ void __launch_bounds__(AN_THREADS)
-k_structure(const u64* __restrict__ keys, u32* pay, u32* pool, TreeParams tp, FrameState* fs, FrameState* fr,
-            FrameState* hr, uint8_t* m8, uint8_t* s8, u32* start, u32* ctatot, u32* flags, u32 epoch, LevelArrays lv,
-            int mode, int capacity, int n_in, int parity, u64* split_out) {
+k_structure(const u64* __restrict__ keys_sorted, const u64* __restrict__ keys_dense, u32* pay, u32* pool, TreeParams tp,
+            FrameState* fs, FrameState* fr, FrameState* hr, uint8_t* m8, uint8_t* s8, u32* start, u32* ctatot,
+            u32* flags, u32 epoch, LevelArrays lv, int mode, int capacity, int n_in, int parity, u64* split_out) {
   __shared__ u32 s_w[AN_WARPS][NC_MAX];
   __shared__ u32 s_plan[NC_MAX];
   __shared__ u32 s_tot[NC_MAX];
@@ -804,6 +822,8 @@ k_structure(const u64* __restrict__ keys, u32* pay, u32* pool, TreeParams tp, Fr
   const int n_valid = __ldcg(&fs->acc_valid[parity]);
   const int n_invalid_front = n_in - n_valid;
   const int cur = __ldcg(&fs->cur_size);
+  // voxel grids that arrived sorted and gap-free were not sorted again: read k_emit's dense copy
+  const u64* __restrict__ keys = (mode == 2 && __ldcg(&fs->acc_unsorted[parity]) == 0) ? keys_dense : keys_sorted;
   const u32 size0 = (u32)(cur > 8 ? cur : 8);
   const int nvb = (n + AN_THREADS - 1) / AN_THREADS;
   const int G = gridDim.x;
@@ -931,7 +951,7 @@ k_structure(const u64* __restrict__ keys, u32* pay, u32* pool, TreeParams tp, Fr
       }
       // every CTA that has work read these before it published / passed the barrier; a CTA that starts later sees
       // 0 entries and idles
-      fs->acc_valid[parity] = 0; fs->acc_emit[parity] = 0;
+      fs->acc_valid[parity] = 0; fs->acc_emit[parity] = 0; fs->acc_unsorted[parity] = 0;
       if (!overflow) fs->cur_size = (int)after;
       fs->frame_seq = seq;
     }
@@ -993,13 +1013,18 @@ k_levels(u32* pool, LevelArrays lv, const FrameState* fr, u32* done, int D, int 
   extern __shared__ __align__(16) unsigned char s_raw[];
   __shared__ int s_nl[OSL_MAXD + 2];   // n_level[d]
   __shared__ int s_pre[OSL_MAXD + 2];  // s_pre[d] = sum of n_level[1..d-1]
-  if (fr->overflow) return;
+  __shared__ int s_overflow;
   const int tid = threadIdx.x;
   const int gtid = blockIdx.x * LEVEL_THREADS + tid, gsz = gridDim.x * LEVEL_THREADS;
+  // the frame's level counts: one parallel round trip, then a prefix over <= 20 values
+  if (tid <= D && tid >= 1) s_nl[tid] = fr->n_level[tid];
+  if (tid == 0) s_overflow = fr->overflow;
+  __syncthreads();
+  if (s_overflow) return;
   if (tid == 0) {
     int run = 0;
     s_nl[0] = 0; s_pre[0] = 0;
-    for (int d = 1; d <= D; d++) { const int v = fr->n_level[d]; s_nl[d] = v; s_pre[d] = run; run += v; }
+    for (int d = 1; d <= D; d++) { s_pre[d] = run; run += s_nl[d]; }
     s_pre[D + 1] = run;
   }
   __syncthreads();
@@ -1407,7 +1432,8 @@ osl_status osl_run_integrate(osl_svo* t, EmitParams& ep, const void* colors, cud
     } else {
       etiles = (n + EMIT_TILE - 1) / EMIT_TILE;
     }
-    k_emit<<<etiles, EMIT_THREADS, EMIT_SMEM, sE>>>(ep, t->tp, vec_ok, t->d_keysA[fslot], t->d_payA[fslot], fs, fslot);
+    k_emit<<<etiles, EMIT_THREADS, EMIT_SMEM, sE>>>(ep, t->tp, vec_ok, t->d_keysA[fslot], t->d_payA[fslot],
+                                                   t->d_keysB[fslot], fs, fslot);
     OSL_LAUNCHED(1);
     if (timing) OSL_CUDA(cudaEventRecord(t->stage_ev[1], st));
     // ---- So: sort
@@ -1423,7 +1449,8 @@ osl_status osl_run_integrate(osl_svo* t, EmitParams& ep, const void* colors, cud
       const int grid = grid_for(exp_emit, SORT_TILE, t->sort_grid < coop_cap ? t->sort_grid : coop_cap);
       u64* kA = t->d_keysA[fslot]; u32* pA = t->d_payA[fslot]; u64* kB = t->d_keysB[fslot]; u32* pB = t->d_payB[fslot];
       u32* ch = t->d_cta_hist[fslot]; const FrameState* fsc = fs; int pp = passes; int parity = fslot;
-      void* args[] = {&kA, &pA, &kB, &pB, &ch, &fsc, &pp, &parity};
+      int md = ep.mode;
+      void* args[] = {&kA, &pA, &kB, &pB, &ch, &fsc, &pp, &parity, &md};
       OSL_CUDA(cudaLaunchCooperativeKernel((void*)k_sort, dim3(grid), dim3(SORT_THREADS), args, 0, sSo));
     }
     OSL_LAUNCHED(1);
@@ -1438,15 +1465,18 @@ osl_status osl_run_integrate(osl_svo* t, EmitParams& ep, const void* colors, cud
     OSL_CUDA(cudaStreamWaitEvent(sS, t->ring_ev[(f - OSL_BACK) % OSL_RING], 0));
   {
     const int grid = grid_for(exp_emit, AN_THREADS, t->structure_grid < coop_cap ? t->structure_grid : coop_cap);
-    const u64* a0 = skeys; u32* a1 = spay; u32* a2 = t->d_pool; TreeParams a3 = t->tp; FrameState* a4 = fs;
+    const u64* a0 = skeys; const u64* a0b = t->d_keysB[fslot]; u32* a1 = spay; u32* a2 = t->d_pool;
+    TreeParams a3 = t->tp; FrameState* a4 = fs;
     FrameState* a4b = fr;
     uint8_t* a5 = t->d_m; uint8_t* a6 = t->d_s; u32* a6b = t->d_start; u32* a7 = t->d_blockcnt;
     u32* a8b = t->d_flags; u32 a8c = (u32)(f + 1);
     LevelArrays a9 = lv; int a10 = ep.mode; int a11 = (int)t->cap_nodes; int a12 = n; int a13 = fslot;
     u64* a14 = t->d_split + fslot * BK_BUCKETS;
     FrameState* a4c = &t->h_ring[f % OSL_RING];  // pinned host memory, device-accessible (UVA)
-    void* args[] = {&a0, &a1, &a2, &a3, &a4, &a4b, &a4c, &a5, &a6, &a6b, &a7, &a8b, &a8c, &a9, &a10, &a11, &a12,
+    void* args[] = {&a0, &a0b, &a1, &a2, &a3, &a4, &a4b, &a4c, &a5, &a6, &a6b, &a7, &a8b, &a8c, &a9, &a10, &a11, &a12,
                     &a13, &a14};
+    // (a plain launch was measured to be no faster than the cooperative one, which guarantees the co-residency the
+    // flag exchange relies on)
     OSL_CUDA(cudaLaunchCooperativeKernel((void*)k_structure, dim3(grid), dim3(AN_THREADS), args, 0, sS));
     OSL_LAUNCHED(1);
     if (timing) OSL_CUDA(cudaEventRecord(t->stage_ev[3], st));
@@ -1511,8 +1541,8 @@ osl_status osl_device_sort_pairs(u64* kA, u32* pA, u64* kB, u32* pB, int n, int 
   if (e == cudaSuccess) e = cudaMemsetAsync(fs, 0, sizeof(FrameState), st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(&fs->acc_emit[0], &n, sizeof(int), cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) {
-    const FrameState* fsc = fs; int pp = passes; int parity = 0;
-    void* args[] = {&kA, &pA, &kB, &pB, &hist, &fsc, &pp, &parity};
+    const FrameState* fsc = fs; int pp = passes; int parity = 0; int md = 0;
+    void* args[] = {&kA, &pA, &kB, &pB, &hist, &fsc, &pp, &parity, &md};
     e = cudaLaunchCooperativeKernel((void*)k_sort, dim3(grid), dim3(SORT_THREADS), args, 0, st);
     OSL_LAUNCHED(1);
   }

@@ -28,6 +28,7 @@ typedef unsigned int u32;
 struct FrameState {
   int acc_valid[OSL_FRONT];  // [key-list slot] accumulated by k_emit (atomicAdd), consumed and zeroed by k_structure
   int acc_emit[OSL_FRONT];   // [key-list slot] entries k_emit appended to the key list
+  int acc_unsorted[OSL_FRONT];  // [key-list slot] voxel path: the inputs are NOT (sorted and all valid)
   int n_in;         // inputs
   int n_valid;      // V  (inputs with a valid key)
   int n_emit;       // entries sorted (modes 0/1: after the tile-local de-duplication; mode 2: == n_valid)

@@ -555,3 +555,31 @@ def test_checkpoint_resume_continues_bit_exactly(P, tmp_path):
     c = P.SVO(center, half, D + 1)
     with pytest.raises(P.OslError):
         c.restore(path)
+
+
+@pytest.mark.parametrize("variant", ["sorted", "sorted_with_duplicates", "sorted_with_invalid", "reversed"])
+def test_voxel_grids_in_morton_order_skip_the_sort(P, variant):
+    """a VoxelGrid that arrives sorted and gap-free is not sorted again (k_emit keeps a dense copy); every variant
+    must still equal the oracle, which always sorts (svo.cu:602)"""
+    rng = np.random.default_rng(5)
+    D, n = 7, 6000
+    pts = unique_voxel_points(rng, n, (0, 0, 0), 1.0, D)
+    keys = orc.compute_keys(pts, (0, 0, 0), 1.0, D)
+    pts = pts[np.argsort(keys, kind="stable")]
+    if variant == "sorted_with_duplicates":
+        pts[100:104] = pts[100]
+        pts[2000] = pts[1999]
+    elif variant == "sorted_with_invalid":
+        pts[777, 0] = np.inf
+    elif variant == "reversed":
+        pts = pts[::-1].copy()
+    centers = np.ones((pts.shape[0], 4), dtype=np.float32)
+    centers[:, :3] = pts
+    colors = rng.uniform(0, 1, size=centers.shape).astype(np.float32)
+    svo = P.SVO((0, 0, 0), 1.0, D)
+    ref = orc.OracleSVO((0, 0, 0), 1.0, D)
+    for _ in range(2):
+        svo.integrate_voxels(centers, colors)
+        ref.integrate_voxels(centers, colors)
+    assert svo.size == ref.size
+    assert np.array_equal(svo.pool(), ref.pool())
