@@ -102,6 +102,7 @@ void osl_svo_destroy(osl_svo* t) {
   if (!t) return;
   cudaSetDevice(t->device);
   cudaDeviceSynchronize();
+  if (t->counted_piped && g_osl_piped_trees > 0) g_osl_piped_trees--;
   cudaFree(t->d_pool);
   for (int f = 0; f < OSL_FRONT; f++) {
     cudaFree(t->d_keysA[f]); cudaFree(t->d_keysB[f]); cudaFree(t->d_payA[f]); cudaFree(t->d_payB[f]);

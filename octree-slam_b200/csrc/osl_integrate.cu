@@ -848,6 +848,9 @@ k_structure(const u64* __restrict__ keys_sorted, const u64* __restrict__ keys_de
     split_out[tid] = keys[(size_t)(((long long)(tid + 1) * n) / BK_BUCKETS)];
   for (int c = tid; c < NC; c += AN_THREADS) s_ctot[c] = 0;
   __syncthreads();
+  // (Sharing walks between the blocks of a CTA -- thread 0 walks the block's first key, the others resume where they
+  // leave its path -- was measured at 50 M keys: 3.5 ms against 3.2 ms for these independent walks; with 4 CTAs per
+  // SM the walk latency is already hidden and the extra serial step only adds two block barriers per block.)
   for (int vb = vb0; vb < vb1; vb++)
     analyze_block(vb, n, keys, pay, mode, pool, tp, m8, s8, start, s_ctot, &s_w[0][0]);
   // publish this CTA's counter vector behind an epoch flag (every CTA publishes, also one without blocks)
@@ -1331,7 +1334,9 @@ static osl_status drain_streams(osl_svo* t, cudaStream_t st) {
   return OSL_OK;
 }
 
-// One frame: k_emit -> k_sort(_bucket) -> k_structure -> k_link -> k_levels (+ the result block into the pinned ring).
+int g_osl_piped_trees = 0;  // trees of this process that have used pipelined mode and are still alive
+
+// One frame: k_emit -> k_sort(_bucket) -> k_structure -> k_levels (the result block goes straight into the pinned ring).
 //
 // Strict mode (default for device inputs): everything is enqueued on the caller's stream, in order.
 // Pipelined mode (osl_svo_set_pipeline, and always for host frames whose copies the library owns): the four stages
@@ -1340,9 +1345,9 @@ static osl_status drain_streams(osl_svo* t, cudaStream_t st) {
 // k_structure(f+1) only needs the STRUCTURE of the tree after frame f (word0, final after k_link(f)); the value
 // fold of frame f (word1) runs concurrently.  Buffers: 3 key-list slots (E/So/S), 2 level-list + result slots (S/V).
 // The caller's stream is made to wait for the frame (cudaStreamWaitEvent), so work enqueued on it afterwards sees the
-// updated tree.  Cooperative grids are capped at num_sms/3 CTAs in this mode: at most three cooperative kernels
-// (grid sort, k_structure, k_levels) run concurrently, <= num_sms CTAs in total, so a waiting CTA always finds an
-// empty SM and no grid barrier can deadlock.
+// updated tree.  Cooperative grids are capped at num_sms/3 CTAs in this mode (num_sms/(3*T) when T trees of the
+// process pipeline): at most three cooperative kernels per tree (grid sort, k_structure, k_levels) run concurrently,
+// <= num_sms CTAs in total, so a waiting CTA always finds an empty SM and no grid barrier can deadlock.
 osl_status osl_run_integrate(osl_svo* t, EmitParams& ep, const void* colors, cudaStream_t st, bool inputs_on_front) {
   const int n = ep.n;
   const int D = t->tp.D;
@@ -1403,7 +1408,12 @@ osl_status osl_run_integrate(osl_svo* t, EmitParams& ep, const void* colors, cud
       OSL_CUDA(cudaStreamWaitEvent(sV, prev, 0));
     }
   }
-  const int coop_cap = piped ? (t->num_sms / 3 > 0 ? t->num_sms / 3 : 1) : 0x7FFFFFFF;
+  if (piped && !t->counted_piped) {  // trees that pipeline share the device: the CTA budget is split between them
+    t->counted_piped = 1;
+    g_osl_piped_trees++;
+  }
+  const int sharers = 3 * (g_osl_piped_trees > 0 ? g_osl_piped_trees : 1);
+  const int coop_cap = piped ? (t->num_sms / sharers > 0 ? t->num_sms / sharers : 1) : 0x7FFFFFFF;
   const int passes = (3 * D + 7) / 8;
   u64* skeys = (passes & 1) ? t->d_keysB[fslot] : t->d_keysA[fslot];
   u32* spay = (passes & 1) ? t->d_payB[fslot] : t->d_payA[fslot];

@@ -181,6 +181,7 @@ struct osl_svo {
   cudaEvent_t emit_done[OSL_FRONT], sort_done[OSL_FRONT];
   cudaEvent_t struct_ev[OSL_RING];       // k_structure of frame f done (slot f % OSL_RING); ring_ev = k_levels done
   int last_piped;
+  int counted_piped;                     // this tree is counted in g_osl_piped_trees
   int join_pending;                      // pipelined frames are in flight that other streams have not been ordered after
   int stage_timing, stage_valid;         // per-kernel CUDA-event timing of non-pipelined frames (bench / profiling)
   cudaEvent_t stage_ev[5];
@@ -198,6 +199,7 @@ struct osl_svo {
 
 extern int g_osl_last_cuda_error;
 extern long long g_osl_launches;
+extern int g_osl_piped_trees;
 #define OSL_CUDA(call)                                   \
   do {                                                   \
     cudaError_t e_ = (call);                             \

@@ -583,3 +583,45 @@ def test_voxel_grids_in_morton_order_skip_the_sort(P, variant):
         ref.integrate_voxels(centers, colors)
     assert svo.size == ref.size
     assert np.array_equal(svo.pool(), ref.pool())
+
+
+def test_two_pipelined_trees_interleaved(P):
+    """two maps fed in lock-step from one host thread, both pipelined (cooperative-grid budget is shared)"""
+    import torch
+    D, w, h, frames = 12, 320, 240, 10
+    center, half = P.synth.tree_params(D)
+    fx, fy = P.synth.focal(w, h)
+    a = P.SVO(center, half, D).set_pipeline(True)
+    b = P.SVO(center, half, D)
+    ra, rb = orc.OracleSVO(center, half, D), orc.OracleSVO(center, half, D)
+    keep = []
+    for k in range(frames):
+        pa, pb = P.synth.orbit_pose(5 * k), P.synth.orbit_pose(300 + 5 * k)
+        da, ca = P.synth.make_frame(w, h, pa, seed=k)
+        db, cb = P.synth.make_frame(w, h, pb, seed=100 + k)
+        keep.append((torch.from_numpy(da).cuda(), torch.from_numpy(ca).cuda(), db, cb))
+        ra.integrate_depth(da, ca, fx, fy, pa)
+        rb.integrate_depth(db, cb, fx, fy, pb)
+    torch.cuda.synchronize()
+    for k in range(frames):
+        a.integrate_depth(keep[k][0], keep[k][1], fx, fy, P.synth.orbit_pose(5 * k))
+        b.integrate_depth_host(keep[k][2], keep[k][3], fx, fy, P.synth.orbit_pose(300 + 5 * k))
+    assert np.array_equal(a.pool(), ra.pool())
+    assert np.array_equal(b.pool(), rb.pool())
+
+
+@pytest.mark.parametrize("n,D", [(400000, 10), (700000, 13)])
+def test_large_point_clouds_shared_walks(P, n, D):
+    """enough unique keys that every k_structure CTA owns several 512-key blocks (contiguous ranges, shared tree
+    walks, multi-tile radix sort), two frames so that the second one walks a real tree"""
+    rng = np.random.default_rng(n)
+    svo = P.SVO((0, 0, 0), 1.0, D, reserve_nodes=1 << 22)
+    ref = orc.OracleSVO((0, 0, 0), 1.0, D)
+    for frame in range(2):
+        pts = rng.uniform(-1, 1, size=(n, 3)).astype(np.float32)
+        pts[: n // 3] *= 0.2  # a dense cluster: long shared prefixes next to sparse space
+        rgb = rng.integers(0, 256, size=(n, 3)).astype(np.uint8)
+        svo.integrate_points(pts, rgb)
+        ref.integrate_points(pts, rgb)
+        assert svo.size == ref.size
+    assert np.array_equal(svo.pool(), ref.pool())
