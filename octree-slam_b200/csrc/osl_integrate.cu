@@ -1342,11 +1342,11 @@ int g_osl_piped_trees = 0;  // trees of this process that have used pipelined mo
 // Strict mode (default for device inputs): everything is enqueued on the caller's stream, in order.
 // Pipelined mode (osl_svo_set_pipeline, and always for host frames whose copies the library owns): the four stages
 // run on four internal streams, so that consecutive frames overlap --
-//     E: k_emit(f+3)   So: k_sort(f+2)   S: k_structure + k_link (f+1)   V: k_levels(f)
-// k_structure(f+1) only needs the STRUCTURE of the tree after frame f (word0, final after k_link(f)); the value
+//     E: k_emit(f+3)   So: k_sort(f+2)   S: k_structure(f+1)   V: k_levels(f)
+// k_structure(f+1) only needs the STRUCTURE of the tree after frame f (word0, final after k_structure(f)); the value
 // fold of frame f (word1) runs concurrently.  Buffers: 3 key-list slots (E/So/S), 2 level-list + result slots (S/V).
-// The caller's stream is made to wait for the frame (cudaStreamWaitEvent), so work enqueued on it afterwards sees the
-// updated tree.  Cooperative grids are capped at num_sms/3 CTAs in this mode (num_sms/(3*T) when T trees of the
+// Other streams are ordered after the pipeline lazily (osl_join: the library's own raycast / extraction / download
+// entry points call it; foreign work calls osl_svo_join).  Cooperative grids are capped at num_sms/3 CTAs in this mode (num_sms/(3*T) when T trees of the
 // process pipeline): at most three cooperative kernels per tree (grid sort, k_structure, k_levels) run concurrently,
 // <= num_sms CTAs in total, so a waiting CTA always finds an empty SM and no grid barrier can deadlock.
 osl_status osl_run_integrate(osl_svo* t, EmitParams& ep, const void* colors, cudaStream_t st, bool inputs_on_front) {
