@@ -214,7 +214,7 @@ __device__ __forceinline__ void sort_rank(SortTile& t, u32* whist, int base, int
   }
 }
 
-__global__ void __launch_bounds__(SORT_THREADS)
+__global__ void __launch_bounds__(SORT_THREADS, 3)
 k_sort(u64* kA, u32* pA, u64* kB, u32* pB, u32* cta_hist, const FrameState* fs, int passes, int parity, int mode) {
   cg::grid_group grid = cg::this_grid();
   if (mode == 2 && fs->acc_unsorted[parity] == 0) return;  // k_emit's dense copy is already sorted (uniform exit)
@@ -866,8 +866,11 @@ k_structure(const u64* __restrict__ keys_sorted, const u64* __restrict__ keys_de
   // wait for every CTA's vector (all CTAs are co-resident: cooperative launch), then sum them: totals for the plan,
   // exclusive prefix for the own range -- one wait, no grid barrier
   if (warp == 0) {
-    for (int b = lane; b < G; b += 32)
-      while (ld_vol(&flags[b]) != epoch) {}
+    for (int b = lane; b < G; b += 32) {
+      long long spin = 0;  // bounded: a vector that never arrives traps (error to the host) instead of hanging the GPU
+      while (ld_vol(&flags[b]) != epoch)
+        if (++spin > (1ll << 31)) __trap();
+    }
     __threadfence();
   }
   __syncthreads();
@@ -1068,7 +1071,9 @@ k_levels(u32* pool, LevelArrays lv, const FrameState* fr, u32* done, int D, int 
   }
   if (blockIdx.x != 0) return;
   if (tid == 0) {
-    while (*(volatile u32*)done != gridDim.x) {}
+    long long spin = 0;
+    while (*(volatile u32*)done != gridDim.x)
+      if (++spin > (1ll << 31)) __trap();  // bounded wait, see k_structure
     *(volatile u32*)done = 0u;  // the next launch starts from zero (launches of one tree are stream-ordered)
     __threadfence();
   }

@@ -34,6 +34,9 @@ def main():
     torch.cuda.synchronize()
     t_vox2 = time.perf_counter() - t0
     n = cen.shape[0]
+    if len(sys.argv) > 4 and sys.argv[4] == "shuffle":  # a grid that does NOT arrive in Morton order: the radix sort runs
+        perm = torch.randperm(n, device="cuda")
+        cen, col = cen[perm].contiguous(), col[perm].contiguous()
     svo = pkg.SVO(center, half, D, reserve_nodes=max(1 << 20, 3 * n))
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
     ev[0].record()
