@@ -283,8 +283,8 @@ def run_ours(args):
                     "at_1920x1080": {"ms": hd_ms, "mrays_per_s": 1920 * 1080 / (hd_ms / 1e3) / 1e6}},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      # dram__bytes_read.sum + dram__bytes_write.sum of the four kernels of one frame, one ncu --set full
-                     # capture (profiles/r01_ncu_full_summary_v05.csv; cold caches: ncu flushes L2 between kernels)
-                     "traffic": 2307584, "traffic_source": "profiles/r01_ncu_full_summary_v05.csv",
+                     # capture (profiles/r01_ncu_full_summary_v07.csv; cold caches: ncu flushes L2 between kernels)
+                     "traffic": 2269184, "traffic_source": "profiles/r01_ncu_full_summary_v07.csv",
                      "peak_source": peak_src,
                      "kernel": "integrate pipeline per frame (k_emit+k_sort+k_structure+k_levels), "
                                "B_int = 5N+8U+68S+68*sum(P_l) per frame",
