@@ -625,3 +625,57 @@ def test_large_point_clouds_shared_walks(P, n, D):
         ref.integrate_points(pts, rgb)
         assert svo.size == ref.size
     assert np.array_equal(svo.pool(), ref.pool())
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_fuzz_mixed_modes_sizes_and_entry_points(P, seed):
+    """random sequence of depth frames (device strict / device pipelined / host), point clouds and voxel grids of
+    random sizes into ONE tree, with mode switches, syncs and raycasts in between -- against the oracle"""
+    import torch
+    rng = np.random.default_rng(100 + seed)
+    D = int(rng.integers(6, 13))
+    center, half = P.synth.tree_params(D)
+    svo = P.SVO(center, half, D, reserve_nodes=int(rng.choice([16, 1 << 16])))
+    ref = orc.OracleSVO(center, half, D)
+    keep = []
+    for step in range(24):
+        kind = rng.choice(["strict", "piped", "host", "points", "voxels"], p=[0.25, 0.25, 0.25, 0.15, 0.10])
+        if kind in ("strict", "piped", "host"):
+            w, h = [(64, 48), (160, 120), (200, 150), (320, 240)][int(rng.integers(0, 4))]
+            fx, fy = P.synth.focal(w, h)
+            pose = P.synth.orbit_pose(int(rng.integers(0, 400)))
+            depth, rgb = P.synth.make_frame(w, h, pose, seed=int(rng.integers(0, 1000)))
+            ref.integrate_depth(depth, rgb, fx, fy, pose)
+            if kind == "host":
+                keep.append((depth, rgb))
+                svo.integrate_depth_host(depth, rgb, fx, fy, pose)
+            else:
+                d, c = torch.from_numpy(depth).cuda(), torch.from_numpy(rgb).cuda()
+                torch.cuda.synchronize()
+                keep.append((d, c))
+                svo.set_pipeline(kind == "piped")
+                svo.integrate_depth(d, c, fx, fy, pose)
+        elif kind == "points":
+            n = int(rng.integers(0, 5000))
+            pts = rng.uniform(-1.5 * half / 100, 1.5 * half / 100, size=(n, 3)).astype(np.float32)
+            rgb = rng.integers(0, 256, size=(n, 3)).astype(np.uint8)
+            svo.set_pipeline(bool(rng.integers(0, 2)))
+            svo.integrate_points(pts, rgb)
+            ref.integrate_points(pts, rgb)
+        else:
+            n = int(rng.integers(1, 3000))
+            cen = np.ones((n, 4), dtype=np.float32)
+            cen[:, :3] = rng.uniform(-half / 50, half / 50, size=(n, 3))
+            col = rng.uniform(0, 1, size=(n, 4)).astype(np.float32)
+            svo.set_pipeline(False)
+            svo.integrate_voxels(cen, col)
+            ref.integrate_voxels(cen, col)
+        r = rng.random()
+        if r < 0.2:
+            assert svo.size == ref.size, "step %d (%s)" % (step, kind)
+        elif r < 0.3:
+            svo.raycast(32, 24, 45.0, LOOK_PLUS_Z)
+        elif r < 0.35:
+            svo.sync()
+    assert svo.size == ref.size
+    assert np.array_equal(svo.pool(), ref.pool())
