@@ -104,11 +104,42 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
 
 
+def bind_to_gpu_numa_node(local):
+    """Pin this rank to the CPU cores of the NUMA node its GPU hangs off, BEFORE any pinned host memory is allocated
+    (first-touch puts the frame ring next to the GPU's PCIe root): with 8 ranks the H2D copies of the e2e path
+    otherwise all pull from one socket.  Best effort: silently does nothing when the topology cannot be read."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:  # nvml prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 def dist_setup(n_gpus):
     import torch
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    bind_to_gpu_numa_node(local)
     torch.cuda.set_device(local)
     if world > 1:
         import torch.distributed as dist
