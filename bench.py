@@ -195,16 +195,20 @@ def run_ours(args):
     stream = torch.cuda.Stream()
     sp = stream.cuda_stream
 
+    # raw pointers of every ring slot, taken once: the timed loops must not pay for tensor indexing
+    dptr = [(d_depth[j].data_ptr(), d_rgb[j].data_ptr()) for j in range(RING)]
+    hptr = [(h_depth[j].data_ptr(), h_rgb[j].data_ptr()) for j in range(RING)]
+    f_dev, f_host = lib.osl_integrate_depth, lib.osl_integrate_depth_host
+
     def integrate_resident(svo, k):
         j = k % RING
-        rc = lib.osl_integrate_depth(svo._h, d_depth[j].data_ptr(), d_rgb[j].data_ptr(), W, H, fx, fy, pose_c[j], sp)
+        rc = f_dev(svo._h, dptr[j][0], dptr[j][1], W, H, fx, fy, pose_c[j], sp)
         if rc:
             raise RuntimeError("osl_integrate_depth -> %d" % rc)
 
     def integrate_host(svo, k):
         j = k % RING
-        rc = lib.osl_integrate_depth_host(svo._h, h_depth[j].data_ptr(), h_rgb[j].data_ptr(), W, H, fx, fy,
-                                          pose_c[j], sp)
+        rc = f_host(svo._h, hptr[j][0], hptr[j][1], W, H, fx, fy, pose_c[j], sp)
         if rc:
             raise RuntimeError("osl_integrate_depth_host -> %d" % rc)
 
