@@ -986,7 +986,7 @@ k_structure(const u64* __restrict__ keys_sorted, const u64* __restrict__ keys_de
 // (n_level is monotone in d) the other CTAs signal "done" and exit, and CTA 0 finishes alone: it fetches the tiles
 // of ALL remaining levels at once (independent loads) and folds them bottom-up in shared memory, block barriers
 // while a level is wider than a warp, warp barriers above that.
-#define LEVEL_THREADS 1024
+#define LEVEL_THREADS 512
 #define LEVEL_NARROW 1024
 #define LEVEL_STAGE 2048
 #define LEVEL_SMEM (LEVEL_STAGE * (32 + 4 + 4 + 2 + 2) + 64)
