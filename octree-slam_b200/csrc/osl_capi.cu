@@ -118,6 +118,7 @@ void osl_svo_destroy(osl_svo* t) {
   cudaFree(t->d_m); cudaFree(t->d_s); cudaFree(t->d_blockcnt);
   cudaFree(t->d_keysC); cudaFree(t->d_payC); cudaFree(t->d_split); cudaFree(t->d_start); cudaFree(t->d_flags);
   cudaFree(t->d_scan_totals); cudaFree(t->d_fs);
+  cudaFree(t->ex_kA); cudaFree(t->ex_kB); cudaFree(t->ex_nA); cudaFree(t->ex_nB); cudaFree(t->ex_status); cudaFree(t->ex_cnt);
   for (int i = 0; i < OSL_STAGES; i++) {
     cudaFree(t->d_depth_stage[i]); cudaFree(t->d_rgb_stage[i]);
     if (t->stage_copied[i]) cudaEventDestroy(t->stage_copied[i]);
@@ -139,6 +140,7 @@ osl_status osl_svo_reset(osl_svo* t) {
   OSL_CUDA(cudaDeviceSynchronize());
   OSL_CUDA(cudaMemset(t->d_pool, 0, (size_t)(t->size > 8 ? t->size : 8) * 8));  // pool beyond the live nodes stays zero
   t->sticky_error = OSL_OK;
+  t->upload_count++;  // invalidates the cached extraction frontier
   memset(&t->counters, 0, sizeof(t->counters));
   return set_device_size(t, 0);
 }
@@ -309,6 +311,7 @@ osl_status osl_svo_upload(osl_svo* t, const uint32_t* h_pool, int n_nodes) {
   if (rc) return rc;
   if (n_nodes > 0) OSL_CUDA(cudaMemcpy(t->d_pool, h_pool, (size_t)n_nodes * 8, cudaMemcpyHostToDevice));
   t->sticky_error = OSL_OK;
+  t->upload_count++;  // invalidates the cached extraction frontier
   return set_device_size(t, n_nodes);
 }
 

@@ -193,6 +193,9 @@ struct osl_svo {
   uint16_t* d_depth_stage[OSL_STAGES]; uint8_t* d_rgb_stage[OSL_STAGES]; size_t stage_cap; unsigned long long stage_seq;
   int structure_grid, levels_grid;
   osl_counters counters;
+  // extraction scratch + the frontier of the last call (count / fill call pairs)
+  long long *ex_kA, *ex_kB, *ex_res_k; u32 *ex_nA, *ex_nB, *ex_res_n; unsigned long long* ex_status; int* ex_cnt;
+  size_t ex_cap; unsigned long long ex_epoch, ex_seq, ex_uploads, upload_count; int ex_valid, ex_depth, ex_size, ex_n;
   int sort_grid;      // co-resident CTAs for the cooperative sort
   int num_sms;
 };

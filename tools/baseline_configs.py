@@ -44,6 +44,13 @@ def run(name, W, H, D, frames, same_frame, patched, ray=False):
     torch.cuda.synchronize()
     ref_fps = frames / (time.perf_counter() - t0)
     out = {"config": name, "frames": frames, "reference_frames_per_s": ref_fps, "reference_nodes": t.size}
+    if ray:  # row (f)-1: SVO -> voxel list (svo.cu:699-745)
+        t.extract_voxels(D)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            rc, rk = t.extract_voxels(D)
+        out["reference_extract_ms"] = (time.perf_counter() - t0) / 5 * 1e3
+        out["reference_extract_voxels"] = int(rc.shape[0])
     view = (np.diag([-1.0, 1.0, -1.0, 1.0]) @ np.linalg.inv(np.asarray(data[0][2], dtype=np.float64))).astype(np.float32)
     if ray:
         t.raycast(W, H, 45.0, view, want_image=False)
@@ -66,6 +73,12 @@ def run(name, W, H, D, frames, same_frame, patched, ray=False):
     out["ours_frames_per_s"] = frames / (time.perf_counter() - t0)
     out["ours_nodes"] = s.size
     if ray:
+        s.extract_voxels(D)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            c_, k_, keys_ = s.extract_voxels(D)
+        out["ours_extract_ms"] = (time.perf_counter() - t0) / 5 * 1e3
+        out["ours_extract_voxels"] = int(c_.shape[0])
         img = torch.empty((H, W, 4), dtype=torch.uint8, device="cuda")
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         for _ in range(3):
