@@ -220,10 +220,17 @@ __global__ void __launch_bounds__(256)
 k_vox_compact(const unsigned long long* __restrict__ table_key, const u32* __restrict__ table_tri,
               unsigned long long table_size, int D, u64* keys, u32* tris, unsigned long long* count) {
   const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= table_size) return;
-  const unsigned long long code = table_key[i];
-  if (code == VX_EMPTY) return;
-  const unsigned long long pos = atomicAdd(count, 1ull);
+  const unsigned long long code = (i < table_size) ? table_key[i] : VX_EMPTY;
+  const bool hit = code != VX_EMPTY;
+  // one atomicAdd per warp, not per voxel (50 M atomics on one address cost 3 ms)
+  const u32 bal = __ballot_sync(0xFFFFFFFFu, hit);
+  if (!bal) return;
+  const int lane = threadIdx.x & 31, leader = __ffs(bal) - 1;
+  unsigned long long base = 0;
+  if (lane == leader) base = atomicAdd(count, (unsigned long long)__popc(bal));
+  base = __shfl_sync(0xFFFFFFFFu, base, leader);
+  if (!hit) return;
+  const unsigned long long pos = base + (unsigned long long)__popc(bal & ((1u << lane) - 1u));
   keys[pos] = vx_morton((int)(code & 0x1FFFFF), (int)((code >> 21) & 0x1FFFFF), (int)((code >> 42) & 0x1FFFFF), D);
   tris[pos] = table_tri[i];
 }
@@ -265,6 +272,18 @@ extern "C" osl_status osl_voxelize_mesh(const float* d_vertices, int n_vertices,
     return OSL_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   *n_out = 0;
+  {
+    static bool pool_ready = false;  // keep the scratch of one call in the pool for the next one
+    if (!pool_ready) {
+      int dev = 0;
+      cudaMemPool_t mp;
+      if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&mp, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+      pool_ready = true;
+    }
+  }
   if (d_centers4_out) *d_centers4_out = nullptr;
   if (d_colors4_out) *d_colors4_out = nullptr;
   if (d_keys_out) *d_keys_out = nullptr;
@@ -292,8 +311,8 @@ extern "C" osl_status osl_voxelize_mesh(const float* d_vertices, int n_vertices,
   unsigned long long tsize = 0;
   long long n = 0;
 #define VX_CHECK(x) do { e = (x); if (e != cudaSuccess) { g_osl_last_cuda_error = (int)e; rc = (e == cudaErrorMemoryAllocation) ? OSL_ERR_OOM : OSL_ERR_CUDA; goto done; } } while (0)
-  VX_CHECK(cudaMalloc(&tri, sizeof(VoxTri) * (size_t)n_triangles));
-  VX_CHECK(cudaMalloc(&d_ctr, 4 * sizeof(unsigned long long)));
+  VX_CHECK(cudaMallocAsync(&tri, sizeof(VoxTri) * (size_t)n_triangles, st));
+  VX_CHECK(cudaMallocAsync(&d_ctr, 4 * sizeof(unsigned long long), st));
   VX_CHECK(cudaMemsetAsync(d_ctr, 0, 4 * sizeof(unsigned long long), st));
   k_vox_setup<<<(n_triangles + 255) / 256, 256, 0, st>>>(d_vertices, d_triangles, n_triangles, g, tri, d_ctr);
   OSL_LAUNCHED(1);
@@ -301,7 +320,7 @@ extern "C" osl_status osl_voxelize_mesh(const float* d_vertices, int n_vertices,
   VX_CHECK(cudaStreamSynchronize(st));
   if (h_ctr[0] == 0) goto done;
   if (h_ctr[0] > (1ull << 31)) { rc = OSL_ERR_UNSUPPORTED; goto done; }  // > 2^41 columns: not a sparse problem
-  VX_CHECK(cudaMalloc(&items, sizeof(uint2) * h_ctr[0]));
+  VX_CHECK(cudaMallocAsync(&items, sizeof(uint2) * h_ctr[0], st));
   k_vox_items<<<(n_triangles + 255) / 256, 256, 0, st>>>(tri, n_triangles, items, d_ctr + 1);
   OSL_LAUNCHED(1);
   {
@@ -315,16 +334,16 @@ extern "C" osl_status osl_voxelize_mesh(const float* d_vertices, int n_vertices,
     if (h_ctr[2] >= (1ull << 31)) { rc = OSL_ERR_POOL_OVERFLOW; goto done; }
     tsize = 1024;
     while (tsize < 2 * h_ctr[2]) tsize <<= 1;
-    VX_CHECK(cudaMalloc(&tkey, tsize * 8));
-    VX_CHECK(cudaMalloc(&ttri, tsize * 4));
+    VX_CHECK(cudaMallocAsync(&tkey, tsize * 8, st));
+    VX_CHECK(cudaMallocAsync(&ttri, tsize * 4, st));
     VX_CHECK(cudaMemsetAsync(tkey, 0xFF, tsize * 8, st));
     VX_CHECK(cudaMemsetAsync(ttri, 0xFF, tsize * 4, st));
     k_vox_raster<true><<<(unsigned)blocks, 256, 0, st>>>(d_vertices, d_triangles, tri, items, h_ctr[0], g, d_ctr + 2,
                                                          tkey, ttri, tsize - 1);
     OSL_LAUNCHED(1);
   }
-  VX_CHECK(cudaMalloc(&kA, h_ctr[2] * 8)); VX_CHECK(cudaMalloc(&kB, h_ctr[2] * 8));
-  VX_CHECK(cudaMalloc(&pA, h_ctr[2] * 4)); VX_CHECK(cudaMalloc(&pB, h_ctr[2] * 4));
+  VX_CHECK(cudaMallocAsync(&kA, h_ctr[2] * 8, st)); VX_CHECK(cudaMallocAsync(&kB, h_ctr[2] * 8, st));
+  VX_CHECK(cudaMallocAsync(&pA, h_ctr[2] * 4, st)); VX_CHECK(cudaMallocAsync(&pB, h_ctr[2] * 4, st));
   k_vox_compact<<<(unsigned)((tsize + 255) / 256), 256, 0, st>>>(tkey, ttri, tsize, max_depth, kA, pA, d_ctr + 3);
   OSL_LAUNCHED(1);
   VX_CHECK(cudaMemcpyAsync(h_ctr, d_ctr, sizeof(h_ctr), cudaMemcpyDeviceToHost, st));
@@ -351,8 +370,13 @@ extern "C" osl_status osl_voxelize_mesh(const float* d_vertices, int n_vertices,
   if (d_keys_out) { *d_keys_out = reinterpret_cast<int64_t*>(keys_out); keys_out = nullptr; }
   if (d_tris_out) { *d_tris_out = tris_out; tris_out = nullptr; }
 done:
-  cudaFree(tri); cudaFree(d_ctr); cudaFree(items); cudaFree(tkey); cudaFree(ttri);
-  cudaFree(kA); cudaFree(kB); cudaFree(pA); cudaFree(pB);
+  // scratch comes from the stream-ordered pool (cudaMallocAsync): after the first call these are pool hits, not
+  // multi-gigabyte driver allocations; the outputs are plain cudaMalloc (the caller frees them with cudaFree)
+  {
+    void* scratch[] = {tri, d_ctr, items, tkey, ttri, kA, kB, pA, pB};
+    for (void* q : scratch)
+      if (q) cudaFreeAsync(q, st);
+  }
   cudaFree(centers); cudaFree(colors); cudaFree(keys_out); cudaFree(tris_out);
   return rc;
 #undef VX_CHECK
