@@ -20,7 +20,7 @@ class Octree {
   void extractVoxelGrid(VoxelGrid& grid);
   SVO extractSVO(const BoundingBox& bbox);
   BoundingBox boundingBox() const;
-  void expandBySize(const float add_size);  // not supported for GPU-backed trees in the reference either (Q10): no-op
+  void expandBySize(const float add_size);  // re-roots the GPU tree (the reference cannot: quirk Q10)
   // fused main.cpp:39-44
   void addDepthFrame(const uint16_t* depth, const Color256* colors, int width, int height, glm::vec2 focal_length,
                      const glm::mat4& pose);

@@ -76,6 +76,15 @@ osl_status osl_svo_create(osl_svo** out, const float center[3], float half_edge,
 void osl_svo_destroy(osl_svo* t);
 /* Drop all nodes (octree_size = 0), keep the allocations. */
 osl_status osl_svo_reset(osl_svo* t);
+/* Map growth.  Replaces Octree::expandBySize + OctreeNode::expand (octree.cpp:362-378, 183-206), which the reference
+ * cannot run on a GPU-backed tree (quirk Q10: `expand()` refuses and `size_` is re-scaled anyway).  Each layer doubles
+ * the half edge about the SAME centre and deepens the tree by one level, so the resolution is kept: the eight root
+ * children move one level down, old child i becoming child 7-i (`oppositeNode(i)`) of a new node i whose other
+ * seven children are empty (word0 = 0, value 127<<24 as splitNodes initialises them, svo.cu:271-275) and whose value
+ * is averageChildren of that tile (svo.cu:384-441).  64 nodes are appended per layer.  Waits for the pipeline.
+ * OSL_ERR_UNSUPPORTED when max_depth + layers > 20. */
+osl_status osl_svo_expand(osl_svo* t, int layers);
+int osl_svo_max_depth(const osl_svo* t);
 /* bit 0: 1 (default) reproduces reference quirk Q3 (svo.cu:123 `while (r_key >= 15)`); 0 = leaves are never split.
  * bit 1 (testing aid): always sort with the cooperative grid radix sort, never with the splitter-based bucket sort. */
 osl_status osl_svo_set_quirks(osl_svo* t, int ref_quirks);

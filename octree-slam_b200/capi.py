@@ -18,7 +18,7 @@ STATUS = {0: "OSL_OK", -1: "OSL_ERR_INVALID", -2: "OSL_ERR_CUDA", -3: "OSL_ERR_O
           -4: "OSL_ERR_POOL_OVERFLOW", -5: "OSL_ERR_UNSUPPORTED"}
 
 EXPORTS = [
-    "osl_svo_create", "osl_svo_destroy", "osl_svo_reset", "osl_svo_set_quirks", "osl_svo_set_pipeline", "osl_svo_set_stage_timing", "osl_get_stage_times",
+    "osl_svo_create", "osl_svo_destroy", "osl_svo_reset", "osl_svo_expand", "osl_svo_max_depth", "osl_svo_set_quirks", "osl_svo_set_pipeline", "osl_svo_set_stage_timing", "osl_get_stage_times",
     "osl_integrate_depth", "osl_integrate_depth_host", "osl_integrate_points", "osl_integrate_voxels",
     "osl_svo_sync", "osl_svo_join", "osl_svo_view", "osl_svo_size", "osl_svo_download", "osl_svo_upload", "osl_get_counters", "osl_svo_save", "osl_svo_load",
     "osl_raycast", "osl_raycast_host", "osl_raycast_pool", "osl_raycast_rows", "osl_raycast_bands", "osl_extract_voxels", "osl_voxelize_mesh", "osl_free_device", "osl_copy_device",
@@ -70,6 +70,8 @@ def lib():
         "osl_svo_create": (i32, [C.POINTER(vp), fp, f32, i32, C.c_size_t, i32]),
         "osl_svo_destroy": (None, [vp]),
         "osl_svo_reset": (i32, [vp]),
+        "osl_svo_expand": (i32, [vp, i32]),
+        "osl_svo_max_depth": (i32, [vp]),
         "osl_svo_set_quirks": (i32, [vp, i32]),
         "osl_svo_set_pipeline": (i32, [vp, i32]),
         "osl_svo_set_stage_timing": (i32, [vp, i32]),

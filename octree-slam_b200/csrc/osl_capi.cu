@@ -21,9 +21,33 @@ static osl_status set_device_size(osl_svo* t, int size) {
   return OSL_OK;
 }
 
+// One layer of map growth (osl_svo_expand): the root tile (nodes 0-7) is pushed one level down.  Thread 8*i+k owns
+// child k of the new tile of root child i; the tile is nodes [size + 8*i, size + 8*i + 8).  Single CTA of 64 threads.
+__global__ void k_expand_root(u32* __restrict__ pool, int size) {
+  __shared__ u32 s_val[64];
+  const int i = threadIdx.x >> 3, k = threadIdx.x & 7;
+  const uint2 old = reinterpret_cast<const uint2*>(pool)[i];
+  __syncthreads();  // every old root child is in registers before any is overwritten
+  const bool moved = k == 7 - i;  // oppositeNode(i): the octant of new child i that touches the centre
+  const uint2 w = moved ? old : make_uint2(0u, 127u << 24);
+  reinterpret_cast<uint2*>(pool)[size + threadIdx.x] = w;
+  s_val[threadIdx.x] = w.y;
+  __syncthreads();
+  if (k == 0) {  // averageChildren of the new tile (all eight counted, Q5; alpha = max)
+    u32 r = 0, g = 0, b = 0, a = 0;
+    for (int c = 0; c < 8; c++) {
+      const u32 v = s_val[8 * i + c];
+      r += v & 0xFF; g += (v >> 8) & 0xFF; b += (v >> 16) & 0xFF;
+      a = max(a, v >> 24);
+    }
+    reinterpret_cast<uint2*>(pool)[i] =
+        make_uint2((1u << 30) | (u32)(size + 8 * i), (r >> 3) | ((g >> 3) << 8) | ((b >> 3) << 16) | (a << 24));
+  }
+}
+
 extern "C" {
 
-const char* osl_version(void) { return "osl_b200 0.5 (sm_100a)"; }
+const char* osl_version(void) { return "osl_b200 0.6 (sm_100a)"; }
 int osl_frame_result_bytes(void) { return (int)sizeof(FrameState); }
 int osl_last_cuda_error(void) { return g_osl_last_cuda_error; }
 int64_t osl_launch_count(void) { return g_osl_launches; }
@@ -144,6 +168,36 @@ osl_status osl_svo_reset(osl_svo* t) {
   memset(&t->counters, 0, sizeof(t->counters));
   return set_device_size(t, 0);
 }
+
+osl_status osl_svo_expand(osl_svo* t, int layers) {
+  if (!t || layers < 1) return OSL_ERR_INVALID;
+  if (t->tp.D + layers > OSL_MAX_DEPTH) return OSL_ERR_UNSUPPORTED;
+  OSL_CUDA(cudaSetDevice(t->device));
+  osl_status rc = drain(t);
+  if (rc) return rc;
+  OSL_CUDA(cudaDeviceSynchronize());
+  for (int l = 0; l < layers; l++) {
+    if (t->size > 0) {  // an empty tree only changes its geometry
+      if ((size_t)t->size + 64 > ((size_t)1 << 30)) return OSL_ERR_POOL_OVERFLOW;
+      rc = osl_grow_pool(t, (size_t)t->size + 64, 0);
+      if (rc) return rc;
+      k_expand_root<<<1, 64>>>(t->d_pool, t->size);
+      OSL_CUDA(cudaGetLastError());
+      g_osl_launches++;
+      rc = set_device_size(t, t->size + 64);
+      if (rc) return rc;
+    }
+    t->tp.half *= 2.0f;
+    t->tp.D += 1;
+  }
+  OSL_CUDA(cudaDeviceSynchronize());
+  t->upload_count++;        // invalidates the cached extraction frontier
+  t->hint_emit = t->hint_level = -1;
+  osl_drop_workspace(t);    // counter vectors and level arrays are laid out per max_depth
+  return osl_reset_splitters(t);
+}
+
+int osl_svo_max_depth(const osl_svo* t) { return t ? t->tp.D : 0; }
 
 // Per-kernel timing of the integrate pipeline (k_emit, k_sort, k_structure, k_levels) with CUDA events on the
 // caller's stream; only non-pipelined frames are timed.  osl_get_stage_times waits for the last timed frame.

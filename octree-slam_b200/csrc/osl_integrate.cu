@@ -1173,7 +1173,7 @@ int osl_sort_occupancy() {
 
 osl_status osl_ensure_workspace(osl_svo* t, size_t n) {
   if (n <= t->ws_cap) return OSL_OK;
-  size_t cap = t->ws_cap ? t->ws_cap : 1;
+  size_t cap = t->ws_cap ? t->ws_cap : (t->ws_want ? t->ws_want : 1);  // ws_want: capacity before osl_drop_workspace
   while (cap < n) cap *= 2;
   if (cap < 4096) cap = 4096;
   for (int f = 0; f < OSL_FRONT; f++) {
@@ -1228,13 +1228,24 @@ osl_status osl_integrate_init(osl_svo* t) {
   OSL_CUDA(cudaFuncSetAttribute((const void*)k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, EMIT_SMEM));
   OSL_CUDA(cudaFuncSetAttribute((const void*)k_levels, cudaFuncAttributeMaxDynamicSharedMemorySize, LEVEL_SMEM));
   OSL_CUDA(cudaFuncSetAttribute((const void*)k_sort_bucket, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM));
-  // default splitters: an even partition of the key space (valid, merely unbalanced) until a frame has written some
   OSL_CUDA(cudaMalloc(&t->d_split, OSL_FRONT * BK_BUCKETS * sizeof(u64)));
+  return osl_reset_splitters(t);
+}
+
+// default splitters: an even partition of the key space (valid, merely unbalanced) until a frame has written some
+osl_status osl_reset_splitters(osl_svo* t) {
   u64 h_split[OSL_FRONT * BK_BUCKETS];
   for (int i = 0; i < OSL_FRONT * BK_BUCKETS; i++)
     h_split[i] = (u64)((i % BK_BUCKETS) + 1) * ((1ull << (3 * t->tp.D)) / BK_BUCKETS);
   OSL_CUDA(cudaMemcpy(t->d_split, h_split, sizeof(h_split), cudaMemcpyHostToDevice));
   return OSL_OK;
+}
+
+// The workspace layout depends on max_depth (counter vectors, level arrays): drop it so that the next frame
+// re-allocates it.  The pipeline must be idle.
+void osl_drop_workspace(osl_svo* t) {
+  t->ws_want = t->ws_cap > t->ws_want ? t->ws_cap : t->ws_want;
+  t->ws_cap = 0;
 }
 
 // Invariant: every word of the pool beyond the live nodes is ZERO (a tile allocated by a frame then already has

@@ -154,6 +154,7 @@ struct osl_svo {
   int size;           // nodes (host copy, valid after sync)
   // workspace (sized for ws_cap inputs)
   size_t ws_cap;
+  size_t ws_want;     // capacity to restore after osl_drop_workspace
   u64 *d_keysA[OSL_FRONT], *d_keysB[OSL_FRONT];  // sort ping/pong per front buffer
   u32 *d_payA[OSL_FRONT], *d_payB[OSL_FRONT];
   u64* d_keysC; u32* d_payC;   // k_sort_bucket slow-path scratch
@@ -228,6 +229,8 @@ int osl_structure_occupancy();
 int osl_levels_occupancy();
 osl_status osl_poll_results(osl_svo* t, bool block);
 osl_status osl_grow_pool(osl_svo* t, size_t want_nodes, cudaStream_t st);
+osl_status osl_reset_splitters(osl_svo* t);
+void osl_drop_workspace(osl_svo* t);
 osl_status osl_join(osl_svo* t, cudaStream_t st);
 osl_status osl_device_sort_pairs(u64* kA, u32* pA, u64* kB, u32* pB, int n, int key_bits, cudaStream_t st, int* in_B);
 

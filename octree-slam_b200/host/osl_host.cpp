@@ -284,9 +284,19 @@ BoundingBox Octree::boundingBox() const {
   return box;
 }
 
-void Octree::expandBySize(const float) {
-  // Quirk Q10: the reference re-scales size_ although OctreeNode::expand() refuses GPU-backed nodes, silently
-  // corrupting the map.  The hot-path contract is a fixed (center, half size); expansion is a no-op here.
+void Octree::expandBySize(const float add_size) {
+  // octree.cpp:362-378.  Quirk Q10: the reference re-scales size_ although OctreeNode::expand() refuses GPU-backed
+  // nodes, silently corrupting the map; here the GPU tree is re-rooted (osl_svo_expand) by enough doublings to hold
+  // size_ + add_size, keeping centre and resolution.
+  if (!(add_size > 0.0f)) return;
+  const int add_layers = (int)std::ceil(std::log2((double)((size_ + add_size) / size_)));
+  if (add_layers < 1) return;
+  if (svo_) {
+    const osl_status rc = osl_svo_expand(svo_, add_layers);
+    report(rc, "osl_svo_expand");
+    if (rc != OSL_OK) return;
+  }
+  size_ = std::pow(2.0f, (float)add_layers) * size_;
 }
 
 int Octree::nodeCount() const { return svo_ ? osl_svo_size(svo_) : 0; }

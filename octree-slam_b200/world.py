@@ -143,6 +143,13 @@ class SVO:
     def reset(self):
         _check(lib().osl_svo_reset(self._h), "osl_svo_reset")
 
+    def expand(self, layers=1):
+        """Map growth (octree.cpp:183-206, 362-378; quirk Q10 fixed): double the half edge about the same centre
+        `layers` times, one more level each, resolution kept."""
+        _check(lib().osl_svo_expand(self._h, int(layers)), "osl_svo_expand")
+        self.max_depth = lib().osl_svo_max_depth(self._h)
+        self.half_edge = self.view()[3]
+
     def view(self):
         ptr, n = C.c_void_p(), C.c_int()
         c, he = (C.c_float * 3)(), C.c_float()
@@ -325,6 +332,16 @@ class Octree:
     def extractSVO(self, bbox=None):
         """octree.cpp:339-360 -> (device pointer, n_nodes, center, half size)"""
         return self._svo.view()
+
+    def expandBySize(self, add_size):
+        """octree.cpp:362-378 made to work on the GPU tree (Q10): enough doublings for size_ + add_size."""
+        ratio = (np.float32(self.size_) + np.float32(add_size)) / np.float32(self.size_)
+        layers = int(math.ceil(math.log2(float(ratio)))) if ratio > 1.0 else 0
+        if layers < 1:
+            return
+        if self._svo is not None:
+            self._svo.expand(layers)
+        self.size_ = float(np.float32(self.size_) * np.float32(2.0 ** layers))
 
     def boundingBox(self):
         c = np.array(self.center_, dtype=np.float32)

@@ -64,6 +64,10 @@ def lib():
         L.orc_svo_pool.restype = C.c_void_p
         L.orc_svo_pool.argtypes = [C.c_void_p]
         L.orc_svo_counters.argtypes = [C.c_void_p, C.POINTER(Counters)]
+        L.orc_svo_expand.argtypes = [C.c_void_p, C.c_int]
+        L.orc_svo_half_edge.restype = C.c_float
+        L.orc_svo_half_edge.argtypes = [C.c_void_p]
+        L.orc_svo_max_depth.argtypes = [C.c_void_p]
         L.orc_svo_load.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.orc_integrate_points.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.orc_integrate_depth.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
@@ -158,6 +162,12 @@ class OracleSVO:
     def load(self, pool):
         pool = np.ascontiguousarray(pool, dtype=np.uint32)
         lib().orc_svo_load(self._h, _ptr(pool), pool.size // 2)
+
+    def expand(self, layers=1):
+        if lib().orc_svo_expand(self._h, int(layers)) != 0:
+            raise ValueError("bad layers")
+        self.half_edge = float(lib().orc_svo_half_edge(self._h))
+        self.max_depth = int(lib().orc_svo_max_depth(self._h))
 
     def counters(self):
         c = Counters()

@@ -679,3 +679,96 @@ def test_fuzz_mixed_modes_sizes_and_entry_points(P, seed):
             svo.sync()
     assert svo.size == ref.size
     assert np.array_equal(svo.pool(), ref.pool())
+
+
+# ------------------------------------------------------------------------------------------------ map growth
+@pytest.mark.parametrize("mode", ["strict", "pipelined", "host"])
+def test_expand_then_keep_integrating_matches_oracle(P, mode):
+    """osl_svo_expand (octree.cpp:183-206, 362-378 made to work, Q10): pool bit-exact against the oracle's restatement
+    right after the expansion and after further frames, some of them outside the old cube; voxel set unchanged."""
+    import torch
+    D, w, h = 8, 160, 120
+    center, half = (0.0, 0.0, 0.0), 4.0
+    fx, fy = P.synth.focal(w, h)
+    svo = P.SVO(center, half, D).set_pipeline(mode == "pipelined")
+    ref = orc.OracleSVO(center, half, D)
+    keep = []
+
+    def feed(k, shift=0.0):
+        pose = P.synth.orbit_pose(23 * k)
+        pose[0, 3] += shift
+        depth, rgb = P.synth.make_frame(w, h, pose, seed=k)
+        ref.integrate_depth(depth, rgb, fx, fy, pose)
+        if mode == "host":
+            keep.append((depth, rgb))
+            svo.integrate_depth_host(depth, rgb, fx, fy, pose)
+        else:
+            d, c = torch.from_numpy(depth).cuda(), torch.from_numpy(rgb).cuda()
+            keep.append((d, c))
+            torch.cuda.synchronize()
+            svo.integrate_depth(d, c, fx, fy, pose)
+
+    for k in range(3):
+        feed(k)
+    cen0, col0, _ = svo.extract_voxels()
+    svo.expand(1)
+    ref.expand(1)
+    assert (svo.max_depth, svo.half_edge) == (D + 1, 8.0) == (ref.max_depth, ref.half_edge)
+    assert svo.size == ref.size
+    assert np.array_equal(svo.pool(), ref.pool())
+    cen1, col1, keys1 = svo.extract_voxels()
+    o0 = np.lexsort((cen0[:, 2], cen0[:, 1], cen0[:, 0]))
+    o1 = np.lexsort((cen1[:, 2], cen1[:, 1], cen1[:, 0]))
+    assert np.array_equal(cen0[o0], cen1[o1]) and np.array_equal(col0[o0], col1[o1])
+    rc, rk, rkeys = ref.extract_voxels()
+    assert np.array_equal(keys1, rkeys) and float_bits_equal(cen1, rc) and float_bits_equal(col1, rk)
+    for k in range(3, 8):
+        feed(k, 4.5 if k % 2 else 0.0)
+    assert svo.size == ref.size
+    pool = svo.pool()
+    assert np.array_equal(pool, ref.pool())
+    check_pool_invariants(pool)
+    view = view_for_pose(P.synth.orbit_pose(0))
+    img = svo.raycast(96, 72, 45.0, view, mode=1)
+    assert np.array_equal(img, orc.raycast(pool, center, 8.0, 96, 72, 45.0, view, mode=1))
+    # two more layers at once, then a frame
+    svo.expand(2)
+    ref.expand(2)
+    feed(9, -9.0)
+    assert (svo.max_depth, svo.half_edge) == (D + 3, 32.0)
+    assert np.array_equal(svo.pool(), ref.pool())
+
+
+def test_expand_empty_tree_and_depth_limit(P):
+    svo = P.SVO((0, 0, 0), 1.0, 18)
+    svo.expand(2)
+    assert svo.size == 0 and svo.max_depth == 20 and svo.half_edge == 4.0
+    with pytest.raises(Exception):
+        svo.expand(1)
+    pts = np.array([[0.3, 0.3, 0.3], [3.9, 3.9, 3.9], [-3.9, 0.2, 0.6]], dtype=np.float32)
+    rgb = np.array([[200, 100, 50], [10, 20, 30], [255, 255, 255]], dtype=np.uint8)
+    svo.integrate_points(pts, rgb)
+    ref = orc.OracleSVO((0, 0, 0), 4.0, 20)
+    ref.integrate_points(pts, rgb)
+    assert np.array_equal(svo.pool(), ref.pool())
+
+
+def test_octree_expand_by_size(P):
+    """world::Octree::expandBySize (octree.cpp:362-378): enough doublings for size_ + add_size, resolution kept"""
+    w, h = 96, 72
+    fx, fy = P.synth.focal(w, h)
+    depth, rgb = P.synth.make_frame(w, h, None, seed=4)
+    oc = P.Octree(0.0625, (0.0, 0.0, 0.0), 4.0)
+    oc.addDepthFrame(depth, rgb, fx, fy)
+    D = oc.svo.max_depth
+    n = oc.svo.size
+    oc.expandBySize(0.0)
+    assert oc.svo.size == n
+    oc.expandBySize(5.0)  # 9 / 4 -> 2 doublings
+    assert oc.size_ == 16.0 and oc.svo.max_depth == D + 2 and oc.svo.size == n + 128
+    oc.addDepthFrame(depth, rgb, fx, fy)  # _max_depth(resolution) follows size_
+    ref = orc.OracleSVO((0, 0, 0), 4.0, D)
+    ref.integrate_depth(depth, rgb, fx, fy)
+    ref.expand(2)
+    ref.integrate_depth(depth, rgb, fx, fy)
+    assert np.array_equal(oc.svo.pool(), ref.pool())
