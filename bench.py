@@ -292,6 +292,25 @@ def run_ours(args):
     ms_e2e, _, _, _ = timed(integrate_host, svo2)
     svo2.close()
 
+    # camera tracking (the step before integration): frame-to-frame ICP on resident depth frames,
+    # 26 launches per frame, pose read back once at the end
+    cam = pkg.RGBDCamera(W, H, (fx, fy), exact_jacobian=True, device=local)
+    n_trk = min(K, 100)
+    for k in range(3):
+        lib.osl_tracker_update(cam._h, dptr[k % RING][0], sp)
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = lib.osl_launch_count()
+    with torch.cuda.stream(stream):
+        c0.record(stream)
+        for k in range(3, 3 + n_trk):
+            lib.osl_tracker_update(cam._h, dptr[k % RING][0], sp)
+        c1.record(stream)
+    torch.cuda.synchronize()
+    trk_ms = max_over_ranks(c0.elapsed_time(c1) / n_trk, world)
+    trk_launches = (lib.osl_launch_count() - l0) / n_trk
+    trk_lost = cam.lost
+    del cam
+
     total_frames = sum_over_ranks(float(K), world)
     value = total_frames / (ms / 1e3)
     e2e_value = total_frames / (ms_e2e / 1e3)
@@ -316,6 +335,9 @@ def run_ours(args):
                     "steps_per_ray": st.steps / float(st.rays),
                     "algorithmic_gbs": (4 * st.rays + 4 * st.visits + 4 * st.steps) / (ray_ms / 1e3) / 1e9,
                     "at_1920x1080": {"ms": hd_ms, "mrays_per_s": 1920 * 1080 / (hd_ms / 1e3) / 1e6}},
+        "tracking": {"frames_per_s": 1e3 / trk_ms * world, "ms_per_frame": trk_ms, "launches_per_frame": trk_launches,
+                     "lost": bool(trk_lost), "what": "sensor::RGBDCamera::update: bilateral + 3-level pyramid + "
+                     "19 ICP iterations, device-side solve, depth frames resident"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      # dram__bytes_read.sum + dram__bytes_write.sum of the four kernels of one frame, one ncu --set full
                      # capture (profiles/r01_ncu_full_summary_v07.csv; cold caches: ncu flushes L2 between kernels)
@@ -404,6 +426,13 @@ def run_reference(args):
         view = (np.diag([-1.0, 1.0, -1.0, 1.0]) @ np.linalg.inv(poses[(Wm + K - 1) % ring].astype(np.float64))).astype(np.float32)
         _, ray_ms = t.raycast(RAY_W, RAY_H, FOV, view, want_image=False)
         _, ray_ms = t.raycast(RAY_W, RAY_H, FOV, view, want_image=False)
+        trk = R.RefTracker(W, H, fx, fy)
+        n_trk = min(K, 20)
+        for k in range(3):
+            trk.update(depths[k % ring])
+        trk_ms = sum(trk.update(depths[k % ring]) for k in range(3, 3 + n_trk)) / n_trk
+        base["tracking"] = {"frames_per_s": 1e3 / trk_ms, "ms_per_frame": trk_ms,
+                            "what": "the reference's own RGBDCamera::update (rgbd_camera.cpp + its CUDA kernels)"}
         value = K / dt
         base.update({"value": value, "ms_per_step": dt / K * 1e3,
                      "cpu_baseline": {"value": value, "unit": "frames/s", "cores": 1, "kind": "reference",

@@ -1,4 +1,4 @@
-// Minimal stand-in for the subset of glm 0.9.5 the hot-path API uses (vec2/vec3/vec4/mat4 as plain aggregates with the
+// Minimal stand-in for the subset of glm 0.9.5 the hot-path API uses (vec2/vec3/vec4/mat3/mat4 as plain aggregates with the
 // same memory layout: column-major mat4, 12-byte vec3).  Written from scratch for this repository; if the real glm is
 // on the include path first, it is used instead and everything below still compiles (only .x/.y/.z/[] are touched).
 #ifndef OSL_MINI_GLM_HPP_
@@ -34,6 +34,15 @@ struct mat4 {
   explicit mat4(float s) { c[0] = vec4(s, 0, 0, 0); c[1] = vec4(0, s, 0, 0); c[2] = vec4(0, 0, s, 0); c[3] = vec4(0, 0, 0, s); }
   vec4& operator[](int i) { return c[i]; }
   const vec4& operator[](int i) const { return c[i]; }
+};
+struct mat3 {
+  vec3 c[3];  // columns
+  mat3() { c[0] = vec3(1, 0, 0); c[1] = vec3(0, 1, 0); c[2] = vec3(0, 0, 1); }
+  explicit mat3(const mat4& m) {
+    for (int i = 0; i < 3; i++) c[i] = vec3(m.c[i].x, m.c[i].y, m.c[i].z);
+  }
+  vec3& operator[](int i) { return c[i]; }
+  const vec3& operator[](int i) const { return c[i]; }
 };
 inline const float* value_ptr(const mat4& m) { return &m.c[0].x; }
 }  // namespace glm

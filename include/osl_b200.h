@@ -202,6 +202,46 @@ osl_status osl_point_cloud_bbox(const float* d_xyz, int n, float bbox[6], void* 
 osl_status osl_compute_keys(const float* d_pts, int stride, int n, const float center[3], float half_edge,
                             int max_depth, int64_t* d_keys, void* stream);
 
+/* ---- camera tracking (the step main.cpp:35 has commented out) ------------------- */
+
+/* Free functions of image_kernels.h on device buffers; asynchronous on `stream`.
+ * bilateralFilter (image_kernels.cu:168-176; 7x7, sigma 4.5 px / 40 mm). */
+osl_status osl_bilateral_filter(const uint16_t* d_in, uint16_t* d_out, int width, int height, void* stream);
+/* subsampleDepth<uint16_t> / subsample<float> (image_kernels.cu:262-321).  (width, height) are the dimensions of
+ * d_in; d_out receives (width/2) x (height/2) and must not alias d_in (the reference copies back in place). */
+osl_status osl_subsample_depth(const uint16_t* d_in, uint16_t* d_out, int width, int height, void* stream);
+osl_status osl_subsample_f32(const float* d_in, float* d_out, int width, int height, void* stream);
+/* generateNormalMap (image_kernels.cu:131-135), transformNormalMap (:228-230), colorToIntensity (:188-192). */
+osl_status osl_generate_normal_map(const float* d_vertex, float* d_normal, int width, int height, void* stream);
+osl_status osl_transform_normal_map(float* d_normal, const float trans_colmajor[16], int n, void* stream);
+osl_status osl_color_to_intensity(const uint8_t* d_rgb, float* d_out, int n, void* stream);
+/* computeICPCost2 (localization_kernels.h:40, localization_kernels.cu:313-330): A[36] (row-major) and b[6] are HOST
+ * arrays; the call synchronises `stream`.  flags bit 0: use the exact point-to-plane Jacobian v2 x n1 instead of
+ * the reference's mis-indexed G^T (quirk Q17). */
+osl_status osl_icp_cost(const float* d_last_vertex, const float* d_last_normal, const float* d_this_vertex,
+                        const float* d_this_normal, int n, int flags, float A[36], float b[6], int* pairs,
+                        void* stream);
+
+/* sensor::RGBDCamera (rgbd_camera.h:17-82, rgbd_camera.cpp:21-191).  flags bit 0 = 0 reproduces the reference
+ * (quirks Q17, Q18: the Jacobian above, angles negated, position_ never leaves 0); flags bit 0 = 1 is the
+ * corrected tracker (exact Jacobian, increment T*R, camera-to-world pose accumulated as world * update). */
+typedef struct osl_tracker osl_tracker;
+osl_status osl_tracker_create(osl_tracker** out, int width, int height, float fx, float fy, int flags, int device);
+void osl_tracker_destroy(osl_tracker* t);
+osl_status osl_tracker_reset(osl_tracker* t);
+/* RGBDCamera::update: bilateral filter, 3-level pyramid of vertex + normal maps, 4 + 5 + 10 Gauss-Newton
+ * iterations coarse to fine against the previous frame, pose update.  26 launches, no host round trip;
+ * asynchronous on `stream`.  _host: the depth image is in host memory (pinned for a truly asynchronous copy). */
+osl_status osl_tracker_update(osl_tracker* t, const uint16_t* d_depth, void* stream);
+osl_status osl_tracker_update_host(osl_tracker* t, const uint16_t* h_depth, void* stream);
+/* Waits for the last update.  pose (column-major) = the matrix main.cpp:40 applies to the vertex map,
+ * mat4(orientation_) * translate(mat4(1), position_); any output may be NULL. */
+osl_status osl_tracker_get_pose(osl_tracker* t, float pose_colmajor[16], float position[3],
+                                float orientation_colmajor[9], int* lost, int* pairs);
+/* The pyramid level of the last processed frame (device pointers, valid until the next update). */
+osl_status osl_tracker_view(osl_tracker* t, int level, const float** d_vertex, const float** d_normal, int* width,
+                            int* height);
+
 /* ---- misc -------------------------------------------------------------------------------------------------- */
 const char* osl_status_string(osl_status s);
 int osl_last_cuda_error(void);

@@ -7,5 +7,7 @@ from . import capi  # noqa: F401
 from .capi import Counters, OslError, RaycastParams, RaycastStats, lib  # noqa: F401
 from .world import (SVO, BoundingBox, Octree, Scene, computeKeys, computePointCloudBoundingBox,  # noqa: F401
                     coneTraceSVO, generateVertexMap, meshToVoxelGrid, transformVertexMap)
+from . import sensor  # noqa: F401
+from .sensor import RGBDCamera  # noqa: F401
 from . import synth  # noqa: F401
 from . import shard  # noqa: F401

@@ -23,6 +23,10 @@ EXPORTS = [
     "osl_svo_sync", "osl_svo_join", "osl_svo_view", "osl_svo_size", "osl_svo_download", "osl_svo_upload", "osl_get_counters", "osl_svo_save", "osl_svo_load",
     "osl_raycast", "osl_raycast_host", "osl_raycast_pool", "osl_raycast_rows", "osl_raycast_bands", "osl_extract_voxels", "osl_voxelize_mesh", "osl_free_device", "osl_copy_device",
     "osl_generate_vertex_map", "osl_transform_vertex_map", "osl_point_cloud_bbox", "osl_compute_keys",
+    "osl_bilateral_filter", "osl_subsample_depth", "osl_subsample_f32", "osl_generate_normal_map", "osl_transform_normal_map",
+    "osl_color_to_intensity", "osl_icp_cost",
+    "osl_tracker_create", "osl_tracker_destroy", "osl_tracker_reset", "osl_tracker_update", "osl_tracker_update_host",
+    "osl_tracker_get_pose", "osl_tracker_view",
     "osl_status_string", "osl_last_cuda_error", "osl_version", "osl_frame_result_bytes", "osl_launch_count", "osl_debug_profile",
 ]
 
@@ -106,6 +110,20 @@ def lib():
         "osl_transform_vertex_map": (i32, [vp, fp, i32, vp]),
         "osl_point_cloud_bbox": (i32, [vp, i32, fp, vp]),
         "osl_compute_keys": (i32, [vp, i32, i32, fp, f32, i32, vp, vp]),
+        "osl_bilateral_filter": (i32, [vp, vp, i32, i32, vp]),
+        "osl_subsample_depth": (i32, [vp, vp, i32, i32, vp]),
+        "osl_subsample_f32": (i32, [vp, vp, i32, i32, vp]),
+        "osl_generate_normal_map": (i32, [vp, vp, i32, i32, vp]),
+        "osl_transform_normal_map": (i32, [vp, fp, i32, vp]),
+        "osl_color_to_intensity": (i32, [vp, vp, i32, vp]),
+        "osl_icp_cost": (i32, [vp, vp, vp, vp, i32, i32, fp, fp, C.POINTER(i32), vp]),
+        "osl_tracker_create": (i32, [C.POINTER(vp), i32, i32, f32, f32, i32, i32]),
+        "osl_tracker_destroy": (None, [vp]),
+        "osl_tracker_reset": (i32, [vp]),
+        "osl_tracker_update": (i32, [vp, vp, vp]),
+        "osl_tracker_update_host": (i32, [vp, vp, vp]),
+        "osl_tracker_get_pose": (i32, [vp, fp, fp, fp, C.POINTER(i32), C.POINTER(i32)]),
+        "osl_tracker_view": (i32, [vp, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(i32), C.POINTER(i32)]),
         "osl_status_string": (C.c_char_p, [i32]),
         "osl_last_cuda_error": (i32, []),
         "osl_version": (C.c_char_p, []),

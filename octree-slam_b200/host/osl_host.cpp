@@ -16,6 +16,8 @@
 #include <octree_slam/rendering/cone_tracing_kernels.h>
 #include <octree_slam/rendering/cuda_renderer.h>
 #include <octree_slam/sensor/image_kernels.h>
+#include <octree_slam/sensor/localization_kernels.h>
+#include <octree_slam/sensor/rgbd_camera.h>
 #include <octree_slam/world/octree.h>
 #include <octree_slam/world/scene.h>
 #include <octree_slam/world/svo/svo.h>
@@ -393,6 +395,136 @@ void computePointCloudBoundingBox(glm::vec3* points, const int num_points, Bound
   report(osl_point_cloud_bbox(&points->x, num_points, b, nullptr), "osl_point_cloud_bbox");
   bbox.bbox0 = glm::vec3(b[0], b[1], b[2]);
   bbox.bbox1 = glm::vec3(b[3], b[4], b[5]);
+}
+
+// ---- camera tracking (image_kernels.cu:104-321, localization_kernels.cu, rgbd_camera.cpp) -----------------------
+void generateNormalMap(const glm::vec3* vertex_map, glm::vec3* normal_map, const int width, const int height) {
+  report(osl_generate_normal_map(&vertex_map->x, &normal_map->x, width, height, nullptr), "osl_generate_normal_map");
+  cudaDeviceSynchronize();  // image_kernels.cu:134
+}
+
+void bilateralFilter(const uint16_t* depth_in, uint16_t* filtered_out, const int width, const int height) {
+  report(osl_bilateral_filter(depth_in, filtered_out, width, height, nullptr), "osl_bilateral_filter");
+  cudaDeviceSynchronize();  // image_kernels.cu:175
+}
+
+void colorToIntensity(const Color256* color_in, float* intensity_out, const int size) {
+  report(osl_color_to_intensity(&color_in->r, intensity_out, size, nullptr), "osl_color_to_intensity");
+  cudaDeviceSynchronize();  // image_kernels.cu:191
+}
+
+void transformNormalMap(glm::vec3* normal_map, const glm::mat4& trans, const int size) {
+  report(osl_transform_normal_map(&normal_map->x, glm::value_ptr(trans), size, nullptr), "osl_transform_normal_map");
+}
+
+// image_kernels.cu:262-277 / 299-313: temporary of a quarter of the size, kernel, copy back over the input
+template <>
+void subsampleDepth<uint16_t>(uint16_t* data, const int width, const int height) {
+  const size_t bytes = sizeof(uint16_t) * (size_t)(width / 2) * (size_t)(height / 2);
+  uint16_t* tmp = nullptr;
+  if (cudaMalloc((void**)&tmp, bytes ? bytes : 1) != cudaSuccess) return report(OSL_ERR_OOM, "subsampleDepth");
+  report(osl_subsample_depth(data, tmp, width, height, nullptr), "osl_subsample_depth");
+  cudaMemcpy(data, tmp, bytes, cudaMemcpyDeviceToDevice);
+  cudaFree(tmp);
+}
+
+template <>
+void subsample<float>(float* data, const int width, const int height) {
+  const size_t bytes = sizeof(float) * (size_t)(width / 2) * (size_t)(height / 2);
+  float* tmp = nullptr;
+  if (cudaMalloc((void**)&tmp, bytes ? bytes : 1) != cudaSuccess) return report(OSL_ERR_OOM, "subsample");
+  report(osl_subsample_f32(data, tmp, width, height, nullptr), "osl_subsample_f32");
+  cudaMemcpy(data, tmp, bytes, cudaMemcpyDeviceToDevice);
+  cudaFree(tmp);
+}
+
+ICPFrame::ICPFrame(const int w, const int h) : vertex(nullptr), normal(nullptr), width(w), height(h) {
+  cudaMalloc((void**)&vertex, (size_t)w * h * sizeof(glm::vec3));
+  cudaMalloc((void**)&normal, (size_t)w * h * sizeof(glm::vec3));
+}
+
+ICPFrame::~ICPFrame() {
+  cudaFree(vertex);
+  cudaFree(normal);
+}
+
+RGBDFrame::RGBDFrame(const int w, const int h) : intensity(nullptr), vertex(nullptr), width(w), height(h) {
+  cudaMalloc((void**)&intensity, (size_t)w * h * sizeof(float));
+  cudaMalloc((void**)&vertex, (size_t)w * h * sizeof(glm::vec3));
+}
+
+RGBDFrame::~RGBDFrame() {
+  cudaFree(intensity);
+  cudaFree(vertex);
+}
+
+void computeICPCost2(const ICPFrame* last_frame, const ICPFrame& this_frame, float* A, float* b) {
+  report(osl_icp_cost(&last_frame->vertex->x, &last_frame->normal->x, &this_frame.vertex->x, &this_frame.normal->x,
+                      this_frame.width * this_frame.height, 0, A, b, nullptr, nullptr), "osl_icp_cost");
+}
+
+void computeICPCost(const ICPFrame* last_frame, const ICPFrame& this_frame, float* A, float* b) {
+  computeICPCost2(last_frame, this_frame, A, b);
+}
+
+void computeRGBDCost(const RGBDFrame*, const RGBDFrame&, float*, float*) { cudaDeviceSynchronize(); }
+
+RGBDCamera::RGBDCamera(const int width, const int height, const glm::vec2& focal_length, const bool exact_jacobian)
+    : tracker_(nullptr), focal_length_(focal_length), width_(width), height_(height), latest_stamp_(-1) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  report(osl_tracker_create(&tracker_, width, height, focal_length.x, focal_length.y, exact_jacobian ? 1 : 0, dev),
+         "osl_tracker_create");
+}
+
+RGBDCamera::~RGBDCamera() { osl_tracker_destroy(tracker_); }
+
+void RGBDCamera::update(const RawFrame* this_frame) {
+  if (!tracker_ || !this_frame) return;
+  if (this_frame->timestamp <= latest_stamp_) return;  // rgbd_camera.cpp:55-59
+  latest_stamp_ = this_frame->timestamp;
+  if (this_frame->width != width_ || this_frame->height != height_)
+    return report(OSL_ERR_INVALID, "RGBDCamera::update (frame size)");
+  report(osl_tracker_update(tracker_, this_frame->depth, nullptr), "osl_tracker_update");
+}
+
+const glm::vec3 RGBDCamera::position() const {
+  glm::vec3 p;
+  if (tracker_) report(osl_tracker_get_pose(tracker_, nullptr, &p.x, nullptr, nullptr, nullptr), "osl_tracker_get_pose");
+  return p;
+}
+
+const glm::mat3 RGBDCamera::orientation() const {
+  float o[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  if (tracker_) report(osl_tracker_get_pose(tracker_, nullptr, nullptr, o, nullptr, nullptr), "osl_tracker_get_pose");
+  glm::mat3 m;
+  for (int c = 0; c < 3; c++)
+    for (int r = 0; r < 3; r++) m[c][r] = o[3 * c + r];
+  return m;
+}
+
+const glm::mat4 RGBDCamera::pose() const {
+  float p[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  if (tracker_) report(osl_tracker_get_pose(tracker_, p, nullptr, nullptr, nullptr, nullptr), "osl_tracker_get_pose");
+  glm::mat4 m;
+  for (int c = 0; c < 4; c++)
+    for (int r = 0; r < 4; r++) m[c][r] = p[4 * c + r];
+  return m;
+}
+
+bool RGBDCamera::lost() const {
+  int l = 0;
+  if (tracker_) report(osl_tracker_get_pose(tracker_, nullptr, nullptr, nullptr, &l, nullptr), "osl_tracker_get_pose");
+  return l != 0;
+}
+
+const Camera RGBDCamera::camera() const {  // rgbd_camera.cpp:40-51 (projection is a TODO there: left at identity)
+  Camera cam;
+  cam.model = glm::mat4(1.0f);
+  cam.view = pose();
+  cam.modelview = cam.view;  // view * identity
+  cam.mvp = cam.view;        // identity projection * modelview
+  return cam;
 }
 
 }  // namespace sensor

@@ -4,7 +4,9 @@
 // pose comes with the frame instead of RGBDCamera (whose update is commented out, main.cpp:35), and the renderer
 // writes a device buffer instead of a GL PBO.
 //
-//   osl_main <frames.bin> <out_prefix> [fused]
+//   osl_main <frames.bin> <out_prefix> [fused|track]
+// track: main.cpp:35 uncommented -- the pose of every frame comes from sensor::RGBDCamera (corrected tracker) instead
+//        of the file; the estimated poses are written to <out_prefix>.poses (n x 16 floats, column-major).
 // frames.bin: int32 w, h, n; float fx, fy; then n x { float pose[16] (column-major), uint16 depth[w*h], uint8 rgb[w*h*3] }
 // writes <out_prefix>.pool (int32 n_nodes, float center[3], float half, uint32 pool[2n]) and <out_prefix>.rgba (w*h*4).
 #include <cuda_runtime_api.h>
@@ -17,6 +19,7 @@
 #include <octree_slam/common_types.h>
 #include <octree_slam/rendering/cuda_renderer.h>
 #include <octree_slam/sensor/image_kernels.h>
+#include <octree_slam/sensor/rgbd_camera.h>
 #include <octree_slam/world/scene.h>
 
 using namespace octree_slam;
@@ -71,10 +74,11 @@ static int mesh_main(const char* mesh_path, const char* out_prefix) {
 int main(int argc, char** argv) {
   if (argc == 4 && !strcmp(argv[1], "mesh")) return mesh_main(argv[2], argv[3]);
   if (argc < 3) {
-    fprintf(stderr, "usage: %s frames.bin out_prefix [fused]\n", argv[0]);
+    fprintf(stderr, "usage: %s frames.bin out_prefix [fused|track]\n", argv[0]);
     return 2;
   }
   const bool fused = argc > 3 && !strcmp(argv[3], "fused");
+  const bool track = argc > 3 && !strcmp(argv[3], "track");
   FILE* f = fopen(argv[1], "rb");
   if (!f) { perror(argv[1]); return 2; }
   int hdr[3];
@@ -94,6 +98,9 @@ int main(int argc, char** argv) {
   camera.view[2].z = -1.0f;                               // renderer looks down -z for view = identity)
   const glm::vec2 focal_length(focal[0], focal[1]);
 
+  sensor::RGBDCamera* camera_estimation_ = track ? new sensor::RGBDCamera(W, H, focal_length, true) : nullptr;
+  std::vector<float> est_poses;
+
   std::vector<uint16_t> h_depth((size_t)num_points);
   std::vector<uint8_t> h_rgb((size_t)num_points * 3);
   BoundingBox cloud_bbox;
@@ -105,6 +112,13 @@ int main(int argc, char** argv) {
     // OpenNIDevice::readFrame (openni_device.cpp:122,144)
     cudaMemcpy(frame.depth, h_depth.data(), h_depth.size() * 2, cudaMemcpyHostToDevice);
     cudaMemcpy(frame.color, h_rgb.data(), h_rgb.size(), cudaMemcpyHostToDevice);
+
+    if (track) {  // main.cpp:35 + :40
+      frame.timestamp = k + 1;
+      camera_estimation_->update(&frame);
+      pose = camera_estimation_->pose();
+      est_poses.insert(est_poses.end(), &pose[0].x, &pose[0].x + 16);
+    }
 
     // main.cpp:38-44
     sensor::generateVertexMap(frame.depth, points_, W, H, focal_length, make_int2(W, H));
@@ -146,6 +160,14 @@ int main(int argc, char** argv) {
   if (!o) { perror(path); return 2; }
   fwrite(img.data(), 4, img.size(), o);
   fclose(o);
+  if (track) {
+    snprintf(path, sizeof(path), "%s.poses", argv[2]);
+    o = fopen(path, "wb");
+    if (!o) { perror(path); return 2; }
+    fwrite(est_poses.data(), 4, est_poses.size(), o);
+    fclose(o);
+    delete camera_estimation_;
+  }
   printf("osl_main: %d frames %dx%d -> %d nodes (center %.6f %.6f %.6f, half %.6f)\n", n_frames, W, H, n_nodes,
          svo.center.x, svo.center.y, svo.center.z, svo.size);
 

@@ -15,14 +15,17 @@ LIB = os.path.join(BUILD, "libosl_oracle.so")
 MAX_DEPTH = 20
 
 
+SOURCES = ["osl_oracle.c", "osl_oracle_track.c"]
+
+
 def build(force=False):
-    src = os.path.join(HERE, "osl_oracle.c")
-    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= os.path.getmtime(src):
+    srcs = [os.path.join(HERE, s) for s in SOURCES]
+    if not force and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(s) for s in srcs):
         return LIB
     os.makedirs(BUILD, exist_ok=True)
     subprocess.check_call(
-        ["gcc", "-O2", "-std=c11", "-ffp-contract=off", "-fno-fast-math", "-shared", "-fPIC",
-         src, "-o", LIB, "-lm"])
+        ["gcc", "-O2", "-std=c11", "-ffp-contract=off", "-fno-fast-math", "-shared", "-fPIC"] + srcs +
+        ["-o", LIB, "-lm"])
     return LIB
 
 
@@ -80,6 +83,25 @@ def lib():
         L.orc_voxelize_mesh.restype = C.c_int64
         L.orc_voxelize_mesh.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, f3, C.c_float, C.c_int,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+        u16p = C.c_void_p
+        L.orc_bilateral.argtypes = [u16p, u16p, C.c_int, C.c_int]
+        L.orc_subsample_depth.argtypes = [u16p, u16p, C.c_int, C.c_int]
+        L.orc_normal_map.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.orc_transform_normals.argtypes = [C.c_void_p, C.c_int, f3]
+        L.orc_color_to_intensity.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_subsample_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.orc_icp_cost.restype = C.c_int64
+        L.orc_icp_cost.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, f3, f3]
+        L.orc_solve_cholesky.argtypes = [C.c_int, f3, f3, f3]
+        L.orc_pose_increment.argtypes = [f3, C.c_int, f3]
+        L.orc_tracker_create.restype = C.c_void_p
+        L.orc_tracker_create.argtypes = [C.c_int, C.c_int, C.c_float, C.c_float, C.c_int]
+        L.orc_tracker_destroy.argtypes = [C.c_void_p]
+        L.orc_tracker_update.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_tracker_pose.argtypes = [C.c_void_p, f3, f3, f3]
+        L.orc_tracker_lost.argtypes = [C.c_void_p]
+        L.orc_tracker_pairs.restype = C.c_int64
+        L.orc_tracker_pairs.argtypes = [C.c_void_p]
         L.orc_nv_logf.restype = C.c_float
         L.orc_nv_logf.argtypes = [C.c_float]
         L.orc_mat4_inverse.argtypes = [f3, f3]
@@ -230,3 +252,109 @@ def voxelize_mesh(vertices, triangles, center, half_edge, max_depth):
     lib().orc_voxelize_mesh(_ptr(V), V.shape[0], _ptr(T), T.shape[0], _f(center), float(half_edge),
                             int(max_depth), _ptr(keys), _ptr(tris), _ptr(cen), n)
     return keys, tris, cen
+
+
+# ---------------------------------------------------------------------------------------------- camera tracking
+def bilateral(depth):
+    d = np.ascontiguousarray(depth, dtype=np.uint16)
+    out = np.empty_like(d)
+    lib().orc_bilateral(_ptr(d), _ptr(out), d.shape[1], d.shape[0])
+    return out
+
+
+def subsample_depth(depth):
+    d = np.ascontiguousarray(depth, dtype=np.uint16)
+    h, w = d.shape
+    out = np.empty((h // 2, w // 2), dtype=np.uint16)
+    lib().orc_subsample_depth(_ptr(d), _ptr(out), w, h)
+    return out
+
+
+def normal_map(vtx, w, h):
+    v = np.ascontiguousarray(vtx, dtype=np.float32).reshape(h * w, 3)
+    out = np.empty_like(v)
+    lib().orc_normal_map(_ptr(v), _ptr(out), w, h)
+    return out
+
+
+def transform_normals(nrm, M):
+    p = np.ascontiguousarray(nrm, dtype=np.float32).copy()
+    lib().orc_transform_normals(_ptr(p), p.shape[0], _f(mat_colmajor(M)))
+    return p
+
+
+def color_to_intensity(rgb):
+    c = np.ascontiguousarray(rgb, dtype=np.uint8).reshape(-1, 3)
+    out = np.empty(c.shape[0], dtype=np.float32)
+    lib().orc_color_to_intensity(_ptr(c), _ptr(out), c.shape[0])
+    return out
+
+
+def subsample_f32(img):
+    a = np.ascontiguousarray(img, dtype=np.float32)
+    h, w = a.shape
+    out = np.empty((h // 2, w // 2), dtype=np.float32)
+    lib().orc_subsample_f32(_ptr(a), _ptr(out), w, h)
+    return out
+
+
+def icp_cost(last_v, last_n, cur_v, cur_n, exact_jacobian=False):
+    """-> (A 6x6, b 6, pairs): localization_kernels.cu computeICPCost2, sums in double"""
+    arrs = [np.ascontiguousarray(a, dtype=np.float32).reshape(-1, 3) for a in (last_v, last_n, cur_v, cur_n)]
+    A, b = (C.c_float * 36)(), (C.c_float * 6)()
+    pairs = lib().orc_icp_cost(*[_ptr(a) for a in arrs], arrs[0].shape[0], int(exact_jacobian), A, b)
+    return np.array(A, dtype=np.float32).reshape(6, 6), np.array(b, dtype=np.float32), int(pairs)
+
+
+def solve_cholesky(A, b):
+    x = (C.c_float * 6)()
+    lib().orc_solve_cholesky(6, _f(np.asarray(A, dtype=np.float32).reshape(36)), _f(b), x)
+    return np.array(x, dtype=np.float32)
+
+
+def pose_increment(x, exact_jacobian=False):
+    out = (C.c_float * 16)()
+    lib().orc_pose_increment(_f(x), int(exact_jacobian), out)
+    return np.array(out, dtype=np.float32).reshape(4, 4).T  # math convention m[r][c]
+
+
+class OracleTracker:
+    """CPU restatement of sensor::RGBDCamera (rgbd_camera.cpp:53-191)."""
+
+    def __init__(self, w, h, fx, fy, exact_jacobian=False):
+        self._h = lib().orc_tracker_create(int(w), int(h), float(fx), float(fy), int(exact_jacobian))
+        self.w, self.h = int(w), int(h)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_tracker_destroy(self._h)
+            self._h = None
+
+    def update(self, depth):
+        d = np.ascontiguousarray(depth, dtype=np.uint16)
+        assert d.shape == (self.h, self.w)
+        lib().orc_tracker_update(self._h, _ptr(d))
+
+    def pose(self):
+        """main.cpp:40's mat4(orientation) * translate(position), math convention m[r][c]"""
+        m = (C.c_float * 16)()
+        lib().orc_tracker_pose(self._h, m, None, None)
+        return np.array(m, dtype=np.float32).reshape(4, 4).T
+
+    def position(self):
+        p = (C.c_float * 3)()
+        lib().orc_tracker_pose(self._h, None, p, None)
+        return np.array(p, dtype=np.float32)
+
+    def orientation(self):
+        o = (C.c_float * 9)()
+        lib().orc_tracker_pose(self._h, None, None, o)
+        return np.array(o, dtype=np.float32).reshape(3, 3).T
+
+    @property
+    def lost(self):
+        return bool(lib().orc_tracker_lost(self._h))
+
+    @property
+    def pairs(self):
+        return int(lib().orc_tracker_pairs(self._h))

@@ -42,6 +42,19 @@ def lib(patched64=False):
         L.ref_extract_voxels.restype = C.c_longlong
         L.ref_extract_voxels.argtypes = [vp, i32, vp, vp, C.c_longlong]
         L.ref_raycast.argtypes = [vp, vp, i32, i32, f32, fp, dp]
+        L.ref_bilateral.argtypes = [vp, i32, i32, vp]
+        L.ref_subsample_depth.argtypes = [vp, i32, i32, vp]
+        L.ref_subsample_f32.argtypes = [vp, i32, i32, vp]
+        L.ref_normal_map.argtypes = [vp, i32, i32, vp]
+        L.ref_transform_normals.argtypes = [vp, i32, fp]
+        L.ref_color_to_intensity.argtypes = [vp, i32, vp]
+        L.ref_icp_cost2.argtypes = [vp, vp, vp, vp, i32, i32, fp, fp]
+        L.ref_tracker_create.restype = vp
+        L.ref_tracker_create.argtypes = [i32, i32, f32, f32]
+        L.ref_tracker_destroy.argtypes = [vp]
+        L.ref_tracker_update.restype = C.c_double
+        L.ref_tracker_update.argtypes = [vp, vp]
+        L.ref_tracker_pose.argtypes = [vp, fp, fp]
         _libs[patched64] = L
     return _libs[patched64]
 
@@ -157,3 +170,82 @@ def bbox(points, init=None, patched64=False):
     rc = lib(patched64).ref_bbox(_p(p), p.shape[0], b)
     assert rc == 0
     return np.array(list(b), dtype=np.float32)
+
+
+# ---- camera tracking: the reference's image / localization kernels and its RGBDCamera -----------------------------
+def bilateral(depth):
+    d = np.ascontiguousarray(depth, dtype=np.uint16)
+    out = np.empty_like(d)
+    assert lib().ref_bilateral(_p(d), d.shape[1], d.shape[0], _p(out)) == 0
+    return out
+
+
+def subsample_depth(depth):
+    d = np.ascontiguousarray(depth, dtype=np.uint16)
+    h, w = d.shape
+    out = np.empty((h // 2, w // 2), dtype=np.uint16)
+    assert lib().ref_subsample_depth(_p(d), w, h, _p(out)) == 0
+    return out
+
+
+def subsample_f32(img):
+    a = np.ascontiguousarray(img, dtype=np.float32)
+    h, w = a.shape
+    out = np.empty((h // 2, w // 2), dtype=np.float32)
+    assert lib().ref_subsample_f32(_p(a), w, h, _p(out)) == 0
+    return out
+
+
+def normal_map(vtx, w, h):
+    v = np.ascontiguousarray(vtx, dtype=np.float32).reshape(h * w, 3)
+    out = np.empty_like(v)
+    assert lib().ref_normal_map(_p(v), w, h, _p(out)) == 0
+    return out
+
+
+def transform_normals(nrm, M):
+    p = np.ascontiguousarray(nrm, dtype=np.float32).copy()
+    assert lib().ref_transform_normals(_p(p), p.shape[0], _f(mat_colmajor(M))) == 0
+    return p
+
+
+def color_to_intensity(rgb):
+    c = np.ascontiguousarray(rgb, dtype=np.uint8).reshape(-1, 3)
+    out = np.empty(c.shape[0], dtype=np.float32)
+    assert lib().ref_color_to_intensity(_p(c), c.shape[0], _p(out)) == 0
+    return out
+
+
+def icp_cost2(last_v, last_n, cur_v, cur_n, w, h):
+    arrs = [np.ascontiguousarray(a, dtype=np.float32).reshape(h * w, 3) for a in (last_v, last_n, cur_v, cur_n)]
+    A, b = (C.c_float * 36)(), (C.c_float * 6)()
+    assert lib().ref_icp_cost2(*[_p(a) for a in arrs], w, h, A, b) == 0
+    return np.array(A, dtype=np.float32).reshape(6, 6), np.array(b, dtype=np.float32)
+
+
+class RefTracker:
+    """The reference's own sensor::RGBDCamera (rgbd_camera.cpp), fed with host depth frames."""
+
+    def __init__(self, w, h, fx, fy):
+        self._h = lib().ref_tracker_create(int(w), int(h), float(fx), float(fy))
+        self.w, self.h = int(w), int(h)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().ref_tracker_destroy(self._h)
+            self._h = None
+
+    def update(self, depth):
+        d = np.ascontiguousarray(depth, dtype=np.uint16)
+        assert d.shape == (self.h, self.w)
+        return lib().ref_tracker_update(self._h, _p(d))  # milliseconds
+
+    def position(self):
+        p, o = (C.c_float * 3)(), (C.c_float * 9)()
+        lib().ref_tracker_pose(self._h, p, o)
+        return np.array(p, dtype=np.float32)
+
+    def orientation(self):
+        p, o = (C.c_float * 3)(), (C.c_float * 9)()
+        lib().ref_tracker_pose(self._h, p, o)
+        return np.array(o, dtype=np.float32).reshape(3, 3).T

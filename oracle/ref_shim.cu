@@ -12,13 +12,17 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <new>
 
 #include <cuda_runtime.h>
 
 #include <octree_slam/common_types.h>
 #include <octree_slam/rendering/cone_tracing_kernels.h>
 #include <octree_slam/sensor/image_kernels.h>
+#include <octree_slam/sensor/localization_kernels.h>
+#include <octree_slam/sensor/rgbd_camera.h>
 #include <octree_slam/world/svo/svo.h>
 
 namespace os = octree_slam;
@@ -222,6 +226,132 @@ int ref_raycast(const ref_tree* t, uint8_t* h_out, int w, int h, float fov_deg, 
   if (h_out) cudaMemcpy(h_out, d_out, sizeof(uchar4) * (size_t)w * h, cudaMemcpyDeviceToHost);
   cudaFree(d_out);
   return (int)cudaGetLastError();
+}
+
+// ---- camera tracking (image_kernels.cu:104-321, localization_kernels.cu, rgbd_camera.cpp) ----------------------
+
+int ref_bilateral(const uint16_t* h_in, int w, int h, uint16_t* h_out) {
+  const size_t n = (size_t)w * h;
+  uint16_t *d_in, *d_out;
+  cudaMalloc((void**)&d_in, 2 * n); cudaMalloc((void**)&d_out, 2 * n);
+  cudaMemcpy(d_in, h_in, 2 * n, cudaMemcpyHostToDevice);
+  os::sensor::bilateralFilter(d_in, d_out, w, h);
+  cudaMemcpy(h_out, d_out, 2 * n, cudaMemcpyDeviceToHost);
+  cudaFree(d_in); cudaFree(d_out);
+  return (int)cudaGetLastError();
+}
+
+// subsampleDepth<uint16_t> works in place: the first (w/2)*(h/2) elements of the buffer are the result
+int ref_subsample_depth(const uint16_t* h_in, int w, int h, uint16_t* h_out) {
+  const size_t n = (size_t)w * h;
+  uint16_t* d;
+  cudaMalloc((void**)&d, 2 * n);
+  cudaMemcpy(d, h_in, 2 * n, cudaMemcpyHostToDevice);
+  os::sensor::subsampleDepth<uint16_t>(d, w, h);
+  cudaMemcpy(h_out, d, 2 * (n / 4), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  return (int)cudaGetLastError();
+}
+
+int ref_subsample_f32(const float* h_in, int w, int h, float* h_out) {
+  const size_t n = (size_t)w * h;
+  float* d;
+  cudaMalloc((void**)&d, 4 * n);
+  cudaMemcpy(d, h_in, 4 * n, cudaMemcpyHostToDevice);
+  os::sensor::subsample<float>(d, w, h);
+  cudaMemcpy(h_out, d, 4 * (n / 4), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  return (int)cudaGetLastError();
+}
+
+int ref_normal_map(const float* h_vtx, int w, int h, float* h_nrm) {
+  const size_t n = (size_t)w * h;
+  glm::vec3 *d_v, *d_n;
+  cudaMalloc((void**)&d_v, 12 * n); cudaMalloc((void**)&d_n, 12 * n);
+  cudaMemcpy(d_v, h_vtx, 12 * n, cudaMemcpyHostToDevice);
+  os::sensor::generateNormalMap(d_v, d_n, w, h);
+  cudaMemcpy(h_nrm, d_n, 12 * n, cudaMemcpyDeviceToHost);
+  cudaFree(d_v); cudaFree(d_n);
+  return (int)cudaGetLastError();
+}
+
+int ref_transform_normals(float* h_nrm, int n, const float m[16]) {
+  glm::vec3* d;
+  cudaMalloc((void**)&d, 12 * (size_t)n);
+  cudaMemcpy(d, h_nrm, 12 * (size_t)n, cudaMemcpyHostToDevice);
+  os::sensor::transformNormalMap(d, mat_from(m), n);
+  cudaDeviceSynchronize();
+  cudaMemcpy(h_nrm, d, 12 * (size_t)n, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  return (int)cudaGetLastError();
+}
+
+int ref_color_to_intensity(const uint8_t* h_rgb, int n, float* h_out) {
+  Color256* d_c; float* d_o;
+  cudaMalloc((void**)&d_c, 3 * (size_t)n); cudaMalloc((void**)&d_o, 4 * (size_t)n);
+  cudaMemcpy(d_c, h_rgb, 3 * (size_t)n, cudaMemcpyHostToDevice);
+  os::sensor::colorToIntensity(d_c, d_o, n);
+  cudaMemcpy(h_out, d_o, 4 * (size_t)n, cudaMemcpyDeviceToHost);
+  cudaFree(d_c); cudaFree(d_o);
+  return (int)cudaGetLastError();
+}
+
+// computeICPCost2 on host copies of the four maps
+int ref_icp_cost2(const float* last_v, const float* last_n, const float* this_v, const float* this_n, int w, int h,
+                  float A[36], float b[6]) {
+  const size_t bytes = 12 * (size_t)w * h;
+  os::sensor::ICPFrame last(w, h), cur(w, h);
+  cudaMemcpy(last.vertex, last_v, bytes, cudaMemcpyHostToDevice);
+  cudaMemcpy(last.normal, last_n, bytes, cudaMemcpyHostToDevice);
+  cudaMemcpy(cur.vertex, this_v, bytes, cudaMemcpyHostToDevice);
+  cudaMemcpy(cur.normal, this_n, bytes, cudaMemcpyHostToDevice);
+  os::sensor::computeICPCost2(&last, cur, A, b);
+  return (int)cudaGetLastError();
+}
+
+// RGBDCamera (rgbd_camera.cpp), driven with host depth frames
+struct ref_tracker {
+  os::sensor::RGBDCamera* cam;
+  RawFrame* frame;
+  long long stamp;
+};
+
+ref_tracker* ref_tracker_create(int w, int h, float fx, float fy) {
+  ref_tracker* t = new ref_tracker();
+  // the constructor leaves latest_stamp_ uninitialised (rgbd_camera.cpp:22-24) and update() drops frames whose
+  // timestamp is not newer: construct into zeroed storage so that the timestamps 1, 2, ... are always accepted
+  void* mem = calloc(1, sizeof(os::sensor::RGBDCamera));
+  t->cam = new (mem) os::sensor::RGBDCamera(w, h, glm::vec2(fx, fy));
+  t->frame = new RawFrame(w, h);
+  t->stamp = 0;
+  return t;
+}
+
+void ref_tracker_destroy(ref_tracker* t) {
+  if (!t) return;
+  t->cam->~RGBDCamera();
+  free(t->cam);
+  delete t->frame;
+  delete t;
+}
+
+double ref_tracker_update(ref_tracker* t, const uint16_t* h_depth) {
+  cudaMemcpy(t->frame->depth, h_depth, 2 * (size_t)t->frame->width * t->frame->height, cudaMemcpyHostToDevice);
+  cudaMemset(t->frame->color, 0, 3 * (size_t)t->frame->width * t->frame->height);
+  t->frame->timestamp = ++t->stamp;
+  cudaDeviceSynchronize();
+  const double t0 = now_ms();
+  t->cam->update(t->frame);
+  cudaDeviceSynchronize();
+  return now_ms() - t0;
+}
+
+void ref_tracker_pose(const ref_tracker* t, float position[3], float orientation[9]) {
+  const glm::vec3 p = t->cam->position();
+  const glm::mat3 o = t->cam->orientation();
+  position[0] = p.x; position[1] = p.y; position[2] = p.z;
+  for (int c = 0; c < 3; c++)
+    for (int r = 0; r < 3; r++) orientation[3 * c + r] = o[c][r];
 }
 
 }  // extern "C"

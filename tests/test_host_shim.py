@@ -28,7 +28,14 @@ def test_host_library_exports_the_reference_interface():
                  "octree_slam::world::Octree::addVoxelGrid(", "octree_slam::world::Octree::extractVoxelGrid(",
                  "octree_slam::world::Octree::extractSVO(", "octree_slam::world::Scene::addPointCloudToOctree(",
                  "octree_slam::world::Scene::extractVoxelGridFromOctree(",
-                 "octree_slam::rendering::CUDARenderer::coneTraceSVO("]:
+                 "octree_slam::rendering::CUDARenderer::coneTraceSVO(",
+                 "octree_slam::world::Octree::expandBySize(",
+                 "octree_slam::sensor::bilateralFilter(", "octree_slam::sensor::generateNormalMap(",
+                 "octree_slam::sensor::transformNormalMap(", "octree_slam::sensor::colorToIntensity(",
+                 "void octree_slam::sensor::subsampleDepth<unsigned short>(", "void octree_slam::sensor::subsample<float>(",
+                 "octree_slam::sensor::computeICPCost2(", "octree_slam::sensor::ICPFrame::ICPFrame(",
+                 "octree_slam::sensor::RGBDCamera::update(", "octree_slam::sensor::RGBDCamera::position(",
+                 "octree_slam::sensor::RGBDCamera::orientation(", "octree_slam::sensor::RGBDCamera::camera("]:
         assert name in syms, "libosl_host.so does not define %s" % name
     # the host side contains no device code and needs only the C ABI + cudart
     needed = subprocess.check_output(["readelf", "-d", HOST_LIB], text=True)
@@ -116,3 +123,42 @@ def test_scene_voxelize_meshes_replay_matches_oracle(tmp_path):
     ref.integrate_voxels(cen, colors)
     assert n_nodes == ref.size
     assert np.array_equal(pool, ref.pool())
+
+
+@pytest.mark.gpu
+def test_main_loop_with_camera_tracking_matches_oracle(tmp_path):
+    """main.cpp:33-44 with line 35 live: sensor::RGBDCamera estimates every pose, the map is built with the estimates"""
+    P = pkg()
+    w, h, n = 160, 120, 4
+    fx, fy = P.synth.focal(w, h)
+    frames = []
+    for k in range(n):
+        pose = np.eye(4, dtype=np.float32)
+        pose[0, 3] = 0.01 * k
+        depth, rgb = P.synth.make_frame(w, h, pose, seed=k, invalid_frac=0.01, noise_mm=1)
+        frames.append((pose, depth, rgb))
+    fpath = str(tmp_path / "frames.bin")
+    _write_frames(fpath, w, h, frames, fx, fy)
+    out = str(tmp_path / "out")
+    log = subprocess.check_output([HOST_MAIN, fpath, out, "track"], text=True, timeout=120)
+    assert "osl_main:" in log
+    est = np.frombuffer(open(out + ".poses", "rb").read(), dtype=np.float32).reshape(n, 4, 4).transpose(0, 2, 1)
+    track = orc.OracleTracker(w, h, fx, fy, exact_jacobian=True)
+    ref = None
+    for k, (_, depth, rgb) in enumerate(frames):
+        track.update(depth)
+        assert np.abs(est[k] - track.pose()).max() <= 1e-4, (k, est[k], track.pose())
+        xyz = orc.transform(orc.vertex_map(depth, fx, fy), est[k])   # the map follows the ESTIMATED poses
+        if ref is None:
+            b = orc.bbox(xyz)
+            center = (b[3:] + b[:3]) / np.float32(2.0)
+            size = float(b[3])
+            D = int(math.ceil(math.log(float(np.float32(np.float32(size) / np.float32(0.01)))) /
+                              float(np.float32(math.log(2.0)))))
+            ref = orc.OracleSVO(tuple(center), size, D)
+        ref.integrate_points(xyz, rgb.reshape(-1, 3))
+    assert np.abs(est[-1][0, 3] - 0.03) < 6e-3   # the tracker follows the 3 cm of true motion
+    raw = open(out + ".pool", "rb").read()
+    n_nodes = struct.unpack("<i", raw[:4])[0]
+    assert n_nodes == ref.size
+    assert np.array_equal(np.frombuffer(raw[20:], dtype=np.uint32), ref.pool())
