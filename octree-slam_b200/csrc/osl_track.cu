@@ -211,20 +211,25 @@ __global__ void k_subsample_f32(const float* __restrict__ in, float* __restrict_
 
 // ------------------------------------------------------------------------------------------------ pose algebra
 
-__device__ void trk_identity(float* m) {
+__device__ __forceinline__ void trk_identity(float* m) {
+#pragma unroll
   for (int i = 0; i < 16; i++) m[i] = (i % 5 == 0) ? 1.0f : 0.0f;
 }
 
-__device__ void trk_mul(const float* a, const float* b, float* out) {  // out = a * b, column-major; out may alias
+// out = a * b, column-major; out may alias.  Unrolled: the matrices live in registers.
+__device__ __forceinline__ void trk_mul(const float* a, const float* b, float* out) {
   float r[16];
+#pragma unroll
   for (int c = 0; c < 4; c++)
+#pragma unroll
     for (int k = 0; k < 4; k++)
       r[4 * c + k] = a[k] * b[4 * c] + a[4 + k] * b[4 * c + 1] + a[8 + k] * b[4 * c + 2] + a[12 + k] * b[4 * c + 3];
+#pragma unroll
   for (int i = 0; i < 16; i++) out[i] = r[i];
 }
 
 // glm::rotate(mat4(1), degrees, unit axis) (gtc/matrix_transform.inl:48-86)
-__device__ void trk_rotate_deg(float angle_deg, float ax, float ay, float az, float* out) {
+__device__ __forceinline__ void trk_rotate_deg(float angle_deg, float ax, float ay, float az, float* out) {
   const float a = angle_deg * 0.01745329251994329576923690768489f;
   const float c = cosf(a), s = sinf(a);
   const float t0 = (1.0f - c) * ax, t1 = (1.0f - c) * ay, t2 = (1.0f - c) * az;
@@ -236,7 +241,7 @@ __device__ void trk_rotate_deg(float angle_deg, float ax, float ay, float az, fl
 
 // rgbd_camera.cpp:153-158: Rz(-x2) * Ry(-x1) * Rx(-x0) * T(x3, x4, x5), angles through 180 / 3.14159f.
 // exact: T * Rz(x2) * Ry(x1) * Rx(x0) -- the increment the linearised residual n . (v + w x v + t - v1) solves for.
-__device__ void trk_increment(const float* x, bool exact, float* out) {
+__device__ __forceinline__ void trk_increment(const float* x, bool exact, float* out) {
   float rz[16], ry[16], rx[16], t[16], m[16];
   const float sg = exact ? 1.0f : -1.0f;
   trk_rotate_deg(sg * x[2] * 180.0f / 3.14159f, 0.0f, 0.0f, 1.0f, rz);
@@ -250,27 +255,37 @@ __device__ void trk_increment(const float* x, bool exact, float* out) {
   else trk_mul(m, t, out);
 }
 
-// rgbd_camera.cpp:193-224: float storage, double sums
-__device__ void trk_cholesky(const float* A, const float* b, float* x) {
+// rgbd_camera.cpp:193-224: float storage, double sums.  Every loop has constant bounds and is unrolled so that the
+// factor stays in registers (this runs on ONE thread at the end of every ICP iteration: its latency is serial).
+__device__ __forceinline__ void trk_cholesky(const float* A, const float* b, float* x) {
   float LU[36], yv[6];
+#pragma unroll
   for (int i = 0; i < 36; i++) LU[i] = 0.0f;
+#pragma unroll
   for (int k = 0; k < 6; k++) {
     double sum = 0.0;
+#pragma unroll
     for (int p = 0; p < k; p++) sum += LU[k * 6 + p] * LU[k * 6 + p];
     LU[k * 6 + k] = (float)sqrt(A[k * 6 + k] - sum);
+#pragma unroll
     for (int i = k + 1; i < 6; i++) {
       double s2 = 0.0;
+#pragma unroll
       for (int p = 0; p < k; p++) s2 += LU[i * 6 + p] * LU[k * 6 + p];
       LU[i * 6 + k] = (float)((A[i * 6 + k] - s2) / LU[k * 6 + k]);
     }
   }
+#pragma unroll
   for (int i = 0; i < 6; i++) {
     double sum = 0.0;
+#pragma unroll
     for (int k = 0; k < i; k++) sum += LU[i * 6 + k] * yv[k];
     yv[i] = (float)((b[i] - sum) / LU[i * 6 + i]);
   }
+#pragma unroll
   for (int i = 5; i >= 0; i--) {
     double sum = 0.0;
+#pragma unroll
     for (int k = i + 1; k < 6; k++) sum += LU[k * 6 + i] * x[k];
     x[i] = (float)((yv[i] - sum) / LU[i * 6 + i]);
   }
@@ -299,10 +314,29 @@ __global__ void __launch_bounds__(TRK_THREADS) k_icp_step(const float* __restric
 #pragma unroll
   for (int i = 0; i < TRK_TERMS; i++) acc[i] = 0.0f;
   int pairs = 0;
-  for (int i = blockIdx.x * TRK_THREADS + threadIdx.x; i < n; i += gridDim.x * TRK_THREADS) {
+  // software pipeline: the 12 values of the thread's next point are in flight while the current one is processed
+  // (a thread only ever rewrites its own points, so reading ahead of the stores is safe)
+  const int stride = gridDim.x * TRK_THREADS;
+  float nx[12];
+  {
+    const int i0 = blockIdx.x * TRK_THREADS + threadIdx.x;
+    if (i0 < n) {
+      const size_t o = 3 * (size_t)i0;
+#pragma unroll
+      for (int k = 0; k < 3; k++) { nx[k] = src_v[o + k]; nx[3 + k] = src_n[o + k]; nx[6 + k] = last_v[o + k]; nx[9 + k] = last_n[o + k]; }
+    }
+  }
+  for (int i = blockIdx.x * TRK_THREADS + threadIdx.x; i < n; i += stride) {
     const size_t o = 3 * (size_t)i;
-    float v2x = src_v[o], v2y = src_v[o + 1], v2z = src_v[o + 2];
-    float n2x = src_n[o], n2y = src_n[o + 1], n2z = src_n[o + 2];
+    float v2x = nx[0], v2y = nx[1], v2z = nx[2];
+    float n2x = nx[3], n2y = nx[4], n2z = nx[5];
+    const float v1x = nx[6], v1y = nx[7], v1z = nx[8];
+    const float n1x = nx[9], n1y = nx[10], n1z = nx[11];
+    if (i + stride < n) {
+      const size_t o2 = 3 * (size_t)(i + stride);
+#pragma unroll
+      for (int k = 0; k < 3; k++) { nx[k] = src_v[o2 + k]; nx[3 + k] = src_n[o2 + k]; nx[6 + k] = last_v[o2 + k]; nx[9 + k] = last_n[o2 + k]; }
+    }
     if (apply) {
       osl_transform(s_M, v2x, v2y, v2z);
       trk_rotate(s_M, n2x, n2y, n2z);
@@ -311,8 +345,6 @@ __global__ void __launch_bounds__(TRK_THREADS) k_icp_step(const float* __restric
       dst_v[o] = v2x; dst_v[o + 1] = v2y; dst_v[o + 2] = v2z;
       dst_n[o] = n2x; dst_n[o + 1] = n2y; dst_n[o + 2] = n2z;
     }
-    const float v1x = last_v[o], v1y = last_v[o + 1], v1z = last_v[o + 2];
-    const float n1x = last_n[o], n1y = last_n[o + 1], n1z = last_n[o + 2];
     bool ok = isfinite(v2x) && isfinite(v2y) && isfinite(v2z) && isfinite(v1x) && isfinite(v1y) && isfinite(v1z) &&
               !(v1z < 0.1f) && !(v2z < 0.1f) && !(v1z > 10.0f) && !(v2z > 10.0f);
     ok = ok && isfinite(n2x) && isfinite(n2y) && isfinite(n2z) && isfinite(n1x) && isfinite(n1y) && isfinite(n1z);
@@ -372,30 +404,52 @@ __global__ void __launch_bounds__(TRK_THREADS) k_icp_step(const float* __restric
   __syncthreads();
   if (!s_last) return;
 
-  // last CTA: fold the partials in CTA order (deterministic), in double
+  // last CTA: fold the partials deterministically, in double: 8 row groups x 28 columns of threads, group g sums the
+  // CTAs g, g + 8, ... in order, then column c adds the 8 groups in order
   __threadfence();
+  __shared__ double s_fold[8][TRK_TERMS + 1];
   __shared__ float s_sum[TRK_TERMS];
-  if (threadIdx.x < TRK_TERMS) {
+  {
+    const int g = threadIdx.x >> 5, c = threadIdx.x & 31;
+    if (c <= TRK_TERMS) {
+      double v = 0.0;
+      int cnt = 0;
+      for (u32 k = g; k < gridDim.x; k += 8) {
+        const float p = __ldcg(partials + (size_t)k * (TRK_TERMS + 1) + c);
+        v += (double)p;
+        cnt += __float_as_int(p);
+      }
+      s_fold[g][c] = c < TRK_TERMS ? v : (double)cnt;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x <= TRK_TERMS) {
     double v = 0.0;
-    for (u32 c = 0; c < gridDim.x; c++) v += (double)__ldcg(partials + (size_t)c * (TRK_TERMS + 1) + threadIdx.x);
-    s_sum[threadIdx.x] = (float)v;
-  } else if (threadIdx.x == TRK_TERMS) {
-    int c = 0;
-    for (u32 k = 0; k < gridDim.x; k++) c += __float_as_int(__ldcg(partials + (size_t)k * (TRK_TERMS + 1) + TRK_TERMS));
-    st->pairs = c;
+#pragma unroll
+    for (int g = 0; g < 8; g++) v += s_fold[g][threadIdx.x];
+    if (threadIdx.x < TRK_TERMS) s_sum[threadIdx.x] = (float)v;
+    else st->pairs = (int)v;
   }
   __syncthreads();
   if (threadIdx.x != 0) return;
   st->ticket = 0;
   float A[36], b[6], x[6];
-  int k = 0;
-  for (int r = 0; r < 6; r++)
-    for (int c = r; c < 6; c++) { A[6 * r + c] = s_sum[k]; A[6 * c + r] = s_sum[k]; k++; }
+  {
+    int k = 0;
+#pragma unroll
+    for (int r = 0; r < 6; r++)
+#pragma unroll
+      for (int c = r; c < 6; c++) { A[6 * r + c] = s_sum[k]; A[6 * c + r] = s_sum[k]; k++; }
+  }
+#pragma unroll
   for (int r = 0; r < 6; r++) b[r] = s_sum[21 + r];
+#pragma unroll
   for (int i = 0; i < 36; i++) st->A[i] = A[i];
+#pragma unroll
   for (int i = 0; i < 6; i++) st->b[i] = b[i];
   if (!solve) return;
   trk_cholesky(A, b, x);
+#pragma unroll
   for (int i = 0; i < 6; i++) st->x[i] = x[i];
   if (isnan(x[0]) || isnan(x[1]) || isnan(x[2]) || isnan(x[3]) || isnan(x[4]) || isnan(x[5])) {
     st->level_lost[level] = 1;  // "Camera tracking is lost": the remaining iterations of this level are skipped
@@ -404,8 +458,10 @@ __global__ void __launch_bounds__(TRK_THREADS) k_icp_step(const float* __restric
   }
   float inc[16], upd[16];
   trk_increment(x, exact != 0, inc);
+#pragma unroll
   for (int i = 0; i < 16; i++) upd[i] = st->update[i];
   trk_mul(inc, upd, upd);
+#pragma unroll
   for (int i = 0; i < 16; i++) { st->inc[i] = inc[i]; st->update[i] = upd[i]; }
 }
 
@@ -452,8 +508,10 @@ __global__ void k_track_finish(TrackState* st, int tracked, int exact) {
 // ------------------------------------------------------------------------------------------------ host side
 
 static int icp_grid(int n, int num_sms) {
-  int g = (n + TRK_THREADS - 1) / TRK_THREADS;
-  const int cap = num_sms * 4 < TRK_MAX_CTAS ? num_sms * 4 : TRK_MAX_CTAS;  // multiple of the SM count
+  // about 4 points per thread (the 27-term reduction of a CTA costs as much as a few points per thread), at most
+  // two CTAs per SM: the last CTA folds one partial row per CTA
+  int g = (n + 4 * TRK_THREADS - 1) / (4 * TRK_THREADS);
+  const int cap = num_sms * 2 < TRK_MAX_CTAS ? num_sms * 2 : TRK_MAX_CTAS;
   return g < cap ? (g > 0 ? g : 1) : cap;
 }
 
