@@ -1,5 +1,6 @@
 #!/bin/sh
-# compute-sanitizer over a small end-to-end run (strict + pipelined + host frames + raycast + extraction).
+# compute-sanitizer over a small end-to-end run (strict + pipelined + host frames + raycast + extraction + map growth
+# + camera tracking).
 # Usage (on the GPU box): sh tools/sanitize.sh [memcheck|racecheck|synccheck|initcheck]
 tool=${1:-memcheck}
 compute-sanitizer --tool $tool --error-exitcode 1 --print-limit 20 python - <<'PY'
@@ -35,5 +36,19 @@ v = P.SVO((0, 0, 0), 1.0, 7)
 v.integrate_points(pts, rgb)
 cent = np.ones((3000, 4), dtype=np.float32); cent[:, :3] = pts[:3000]
 v.integrate_voxels(cent, np.ones((3000, 4), dtype=np.float32) * 0.5)
-print("sanitize run ok:", a.size, img.shape, keys.size, v.size)
+# map growth, then more frames; camera tracking (both modes) and the free sensor functions
+a.expand(1)
+a.integrate_depth(frames[0][2], frames[0][3], fx, fy, frames[0][4])
+a.sync()
+for exact in (False, True):
+    cam = P.RGBDCamera(w, h, (fx, fy), exact_jacobian=exact)
+    for d_, _, dd, _, _ in frames[:3]:
+        cam.update(dd if exact else d_)
+    pose = cam.pose()
+f = P.sensor.bilateralFilter(frames[0][0])
+s = P.sensor.subsampleDepth(f)
+vm = P.generateVertexMap(f, fx, fy)
+nm = P.sensor.generateNormalMap(vm, w, h)
+A, b_, pairs = P.sensor.computeICPCost2(vm, nm, vm, nm)
+print("sanitize run ok:", a.size, img.shape, keys.size, v.size, pairs)
 PY
