@@ -309,6 +309,31 @@ def run_ours(args):
     trk_ms = max_over_ranks(c0.elapsed_time(c1) / n_trk, world)
     trk_launches = (lib.osl_launch_count() - l0) / n_trk
     trk_lost = cam.lost
+    # the whole SLAM frame of main.cpp:33-44 with tracking live: tracker, then integration with the pose read on the
+    # device (osl_integrate_depth_posed) -- 31 launches, no host round trip
+    svo3 = pkg.SVO(center, half, DEPTH, reserve_nodes=1 << 24, device=local).set_pipeline(True)
+    d_pose = cam.pose_device()
+
+    def slam_frame(k):
+        j = k % RING
+        lib.osl_tracker_update(cam._h, dptr[j][0], sp)
+        rc = lib.osl_integrate_depth_posed(svo3._h, dptr[j][0], dptr[j][1], W, H, fx, fy, d_pose, sp)
+        if rc:
+            raise RuntimeError("osl_integrate_depth_posed -> %d" % rc)
+
+    for k in range(5):
+        slam_frame(k)
+    svo3.counters()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        s0.record(stream)
+        for k in range(5, 5 + n_trk):
+            slam_frame(k)
+        svo3.join(sp)
+        s1.record(stream)
+    torch.cuda.synchronize()
+    slam_ms = max_over_ranks(s0.elapsed_time(s1) / n_trk, world)
+    svo3.close()
     del cam
 
     total_frames = sum_over_ranks(float(K), world)
@@ -336,7 +361,8 @@ def run_ours(args):
                     "algorithmic_gbs": (4 * st.rays + 4 * st.visits + 4 * st.steps) / (ray_ms / 1e3) / 1e9,
                     "at_1920x1080": {"ms": hd_ms, "mrays_per_s": 1920 * 1080 / (hd_ms / 1e3) / 1e6}},
         "tracking": {"frames_per_s": 1e3 / trk_ms * world, "ms_per_frame": trk_ms, "launches_per_frame": trk_launches,
-                     "lost": bool(trk_lost), "what": "sensor::RGBDCamera::update: bilateral + 3-level pyramid + "
+                     "lost": bool(trk_lost), "slam_frames_per_s": 1e3 / slam_ms * world, "slam_ms_per_frame": slam_ms,
+                     "what": "sensor::RGBDCamera::update: bilateral + 3-level pyramid + "
                      "19 ICP iterations, device-side solve, depth frames resident"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      # dram__bytes_read.sum + dram__bytes_write.sum of the four kernels of one frame, one ncu --set full

@@ -22,6 +22,7 @@ class RGBDCamera {
   // mat4(orientation()) * translate(mat4(1), position()): the matrix main.cpp:40 hands to transformVertexMap
   const glm::mat4 pose() const;
   bool lost() const;
+  const float* poseDevice() const;  // pose() in device memory (column-major), rewritten by every update
 
  private:
   RGBDCamera(const RGBDCamera&);

@@ -8,6 +8,7 @@
 struct osl_svo;
 
 namespace octree_slam {
+namespace sensor { class RGBDCamera; }
 namespace world {
 
 class Octree {
@@ -24,6 +25,10 @@ class Octree {
   // fused main.cpp:39-44
   void addDepthFrame(const uint16_t* depth, const Color256* colors, int width, int height, glm::vec2 focal_length,
                      const glm::mat4& pose);
+  // the same with the pose taken from `camera` ON THE DEVICE: camera.update(frame) must have been called for this
+  // frame; nothing waits for the tracker on the host (osl_integrate_depth_posed)
+  void addDepthFrame(const uint16_t* depth, const Color256* colors, int width, int height, glm::vec2 focal_length,
+                     const sensor::RGBDCamera& camera);
   int nodeCount() const;
 
  private:

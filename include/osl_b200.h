@@ -109,6 +109,10 @@ osl_status osl_get_stage_times(osl_svo* t, float ms[4]);
  * One stream per tree: consecutive calls on different streams are not ordered against each other. */
 osl_status osl_integrate_depth(osl_svo* t, const uint16_t* d_depth, const uint8_t* d_rgb, int w, int h, float fx,
                                float fy, const float pose[16], void* stream);
+/* Same with the pose in DEVICE memory (16 floats, column-major), read when the first kernel of the frame runs: the
+ * pose may be the result of work queued earlier on `stream` (osl_tracker_update + osl_tracker_pose_device). */
+osl_status osl_integrate_depth_posed(osl_svo* t, const uint16_t* d_depth, const uint8_t* d_rgb, int w, int h, float fx,
+                                     float fy, const float* d_pose_colmajor, void* stream);
 /* Same from host buffers (what OpenNIDevice::readFrame + mainLoop do, openni_device.cpp:122,144).  The H2D copies run
  * on an internal copy stream into rotating device slots so the transfer of frame f+1 overlaps the kernels of frame f;
  * the call returns without waiting for the device.  Pinned source buffers must stay untouched until the frame has
@@ -238,6 +242,10 @@ osl_status osl_tracker_update_host(osl_tracker* t, const uint16_t* h_depth, void
  * mat4(orientation_) * translate(mat4(1), position_); any output may be NULL. */
 osl_status osl_tracker_get_pose(osl_tracker* t, float pose_colmajor[16], float position[3],
                                 float orientation_colmajor[9], int* lost, int* pairs);
+/* Device address of the pose matrix (16 floats, column-major; what osl_tracker_get_pose returns as `pose`), rewritten
+ * by every update.  With osl_integrate_depth_posed on the same stream the SLAM loop of main.cpp:33-44 (tracking
+ * live) runs without any host round trip: 27 + 4 launches per frame. */
+osl_status osl_tracker_pose_device(osl_tracker* t, const float** d_pose);
 /* The pyramid level of the last processed frame (device pointers, valid until the next update). */
 osl_status osl_tracker_view(osl_tracker* t, int level, const float** d_vertex, const float** d_normal, int* width,
                             int* height);

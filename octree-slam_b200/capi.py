@@ -19,14 +19,14 @@ STATUS = {0: "OSL_OK", -1: "OSL_ERR_INVALID", -2: "OSL_ERR_CUDA", -3: "OSL_ERR_O
 
 EXPORTS = [
     "osl_svo_create", "osl_svo_destroy", "osl_svo_reset", "osl_svo_expand", "osl_svo_max_depth", "osl_svo_set_quirks", "osl_svo_set_pipeline", "osl_svo_set_stage_timing", "osl_get_stage_times",
-    "osl_integrate_depth", "osl_integrate_depth_host", "osl_integrate_points", "osl_integrate_voxels",
+    "osl_integrate_depth", "osl_integrate_depth_posed", "osl_integrate_depth_host", "osl_integrate_points", "osl_integrate_voxels",
     "osl_svo_sync", "osl_svo_join", "osl_svo_view", "osl_svo_size", "osl_svo_download", "osl_svo_upload", "osl_get_counters", "osl_svo_save", "osl_svo_load",
     "osl_raycast", "osl_raycast_host", "osl_raycast_pool", "osl_raycast_rows", "osl_raycast_bands", "osl_extract_voxels", "osl_voxelize_mesh", "osl_free_device", "osl_copy_device",
     "osl_generate_vertex_map", "osl_transform_vertex_map", "osl_point_cloud_bbox", "osl_compute_keys",
     "osl_bilateral_filter", "osl_subsample_depth", "osl_subsample_f32", "osl_generate_normal_map", "osl_transform_normal_map",
     "osl_color_to_intensity", "osl_icp_cost",
     "osl_tracker_create", "osl_tracker_destroy", "osl_tracker_reset", "osl_tracker_update", "osl_tracker_update_host",
-    "osl_tracker_get_pose", "osl_tracker_view",
+    "osl_tracker_get_pose", "osl_tracker_pose_device", "osl_tracker_view",
     "osl_status_string", "osl_last_cuda_error", "osl_version", "osl_frame_result_bytes", "osl_launch_count", "osl_debug_profile",
 ]
 
@@ -81,6 +81,7 @@ def lib():
         "osl_svo_set_stage_timing": (i32, [vp, i32]),
         "osl_get_stage_times": (i32, [vp, fp]),
         "osl_integrate_depth": (i32, [vp, vp, vp, i32, i32, f32, f32, fp, vp]),
+        "osl_integrate_depth_posed": (i32, [vp, vp, vp, i32, i32, f32, f32, vp, vp]),
         "osl_integrate_depth_host": (i32, [vp, vp, vp, i32, i32, f32, f32, fp, vp]),
         "osl_integrate_points": (i32, [vp, vp, vp, i32, vp]),
         "osl_integrate_voxels": (i32, [vp, vp, vp, i32, vp]),
@@ -123,6 +124,7 @@ def lib():
         "osl_tracker_update": (i32, [vp, vp, vp]),
         "osl_tracker_update_host": (i32, [vp, vp, vp]),
         "osl_tracker_get_pose": (i32, [vp, fp, fp, fp, C.POINTER(i32), C.POINTER(i32)]),
+        "osl_tracker_pose_device": (i32, [vp, C.POINTER(vp)]),
         "osl_tracker_view": (i32, [vp, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(i32), C.POINTER(i32)]),
         "osl_status_string": (C.c_char_p, [i32]),
         "osl_last_cuda_error": (i32, []),

@@ -244,6 +244,21 @@ osl_status osl_integrate_depth(osl_svo* t, const uint16_t* d_depth, const uint8_
   return osl_run_integrate(t, ep, nullptr, (cudaStream_t)stream, false);
 }
 
+// The pose lives in device memory and is read when k_emit runs: lets a tracker's result drive the integration of
+// the same frame without a host round trip (osl_tracker_pose_device).  Ordered after the work already queued on
+// `stream` (in pipelined mode the library's emit stream waits for it).
+osl_status osl_integrate_depth_posed(osl_svo* t, const uint16_t* d_depth, const uint8_t* d_rgb, int w, int h, float fx,
+                                     float fy, const float* d_pose, void* stream) {
+  if (!t || !d_depth || !d_rgb || w <= 0 || h <= 0 || !d_pose || (long long)w * h >= (1ll << 30)) return OSL_ERR_INVALID;
+  OSL_CUDA(cudaSetDevice(t->device));
+  EmitParams ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.depth = d_depth; ep.rgb = d_rgb; ep.w = w; ep.h = h; ep.fx = fx; ep.fy = fy;
+  ep.M_dev = d_pose;
+  ep.n = w * h; ep.mode = 0;
+  return osl_run_integrate(t, ep, nullptr, (cudaStream_t)stream, false);
+}
+
 static osl_status ensure_stage(osl_svo* t, size_t n) {
   if (n <= t->stage_cap) return OSL_OK;
   OSL_CUDA(cudaDeviceSynchronize());

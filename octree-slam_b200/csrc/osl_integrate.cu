@@ -81,11 +81,19 @@ k_emit(EmitParams p, TreeParams tp, int vec_ok, u64* __restrict__ keys, u32* __r
 #pragma unroll
       for (int i = 0; i < EMIT_PPT; i++) dv[i] = (y < p.h && x0 + i < p.w) ? (int)__ldg(p.depth + first + i) : 0;
     }
+    float M[16];  // the pose: a launch parameter, or (tracked frames) device memory written earlier on the stream
+    if (p.M_dev) {
+#pragma unroll
+      for (int i = 0; i < 16; i++) M[i] = p.M_dev[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; i++) M[i] = p.M[i];
+    }
 #pragma unroll
     for (int i = 0; i < EMIT_PPT; i++) {
       float X, Y, Z;
       osl_vertex(dv[i], x0 + i, y, p.w, p.h, p.w, p.h, p.fx, p.fy, X, Y, Z);
-      osl_transform(p.M, X, Y, Z);
+      osl_transform(M, X, Y, Z);
       const bool ok = osl_key(X, Y, Z, tp, k[i]) && (y < p.h && x0 + i < p.w);
       vmask |= (u32)ok << i;
     }
@@ -1459,6 +1467,11 @@ osl_status osl_run_integrate(osl_svo* t, EmitParams& ep, const void* colors, cud
     if (piped && f >= OSL_FRONT)  // the key-list slot was last read by k_structure of frame f - 3
       OSL_CUDA(cudaStreamWaitEvent(sE, t->struct_ev[(f - OSL_FRONT) % OSL_RING], 0));
     if (inputs_on_front) OSL_CUDA(cudaStreamWaitEvent(sE, t->stage_copied[t->stage_seq % OSL_STAGES], 0));
+    if (piped && ep.mode == 0 && ep.M_dev) {  // the pose is produced by work queued on the caller's stream
+      if (!t->pose_ev) OSL_CUDA(cudaEventCreateWithFlags(&t->pose_ev, cudaEventDisableTiming));
+      OSL_CUDA(cudaEventRecord(t->pose_ev, st));
+      OSL_CUDA(cudaStreamWaitEvent(sE, t->pose_ev, 0));
+    }
     int vec_ok = 0;
     int etiles;
     if (ep.mode == 0) {

@@ -155,6 +155,7 @@ struct osl_svo {
   // workspace (sized for ws_cap inputs)
   size_t ws_cap;
   size_t ws_want;     // capacity to restore after osl_drop_workspace
+  cudaEvent_t pose_ev;  // pipelined frames whose pose is produced on the caller's stream (lazily created)
   u64 *d_keysA[OSL_FRONT], *d_keysB[OSL_FRONT];  // sort ping/pong per front buffer
   u32 *d_payA[OSL_FRONT], *d_payB[OSL_FRONT];
   u64* d_keysC; u32* d_payC;   // k_sort_bucket slow-path scratch
@@ -217,6 +218,7 @@ extern int g_osl_piped_trees;
 // integrate pipeline (osl_integrate.cu)
 struct EmitParams {
   const uint16_t* depth; const uint8_t* rgb; int w, h; float fx, fy; float M[16];  // mode 0
+  const float* M_dev;  // mode 0: when set, the pose is read from device memory at kernel time (osl_integrate_depth_posed)
   int tiles_x, tiles_y;                                                             // mode 0: 64x32-pixel tiles
   const float* pts; int stride;                                                      // mode 1 (vec3) / 2 (vec4)
   int n; int mode;

@@ -26,6 +26,7 @@ struct TrackState {
   float world[16];      // exact mode: camera-to-world pose
   float position[3];    // RGBDCamera::position_
   float orientation[9]; // RGBDCamera::orientation_ (column-major mat3)
+  float pose[16];       // what main.cpp:40 applies to the vertex map: mat4(orientation) * translate(position)
   float A[36], b[6], x[6];
   int level_lost[TRK_LEVELS];
   int lost;
@@ -479,15 +480,33 @@ __global__ void k_track_begin(TrackState* st) {
 // rgbd_camera.cpp:171-173: position_ = vec3(vec4(position_, 1) * update_trans) (row vector times matrix: quirk Q18,
 // an affine update leaves a zero position at zero); orientation_ = mat3(mat4(orientation_) * update_trans).
 // exact: world = world * update, position / orientation read from it.
+__device__ void trk_publish_pose(TrackState* st, int exact) {
+  if (exact) {
+    for (int i = 0; i < 16; i++) st->pose[i] = st->world[i];
+    return;
+  }
+  // mat4(orientation) * translate(position): columns 0-2 = orientation, column 3 = orientation * position
+  for (int i = 0; i < 16; i++) st->pose[i] = (i % 5 == 0) ? 1.0f : 0.0f;
+  for (int c = 0; c < 3; c++)
+    for (int k = 0; k < 3; k++) st->pose[4 * c + k] = st->orientation[3 * c + k];
+  for (int k = 0; k < 3; k++)
+    st->pose[12 + k] = st->orientation[k] * st->position[0] + st->orientation[3 + k] * st->position[1] +
+                       st->orientation[6 + k] * st->position[2] + 0.0f;
+}
+
 __global__ void k_track_finish(TrackState* st, int tracked, int exact) {
   if (threadIdx.x != 0) return;
   st->frames++;
-  if (!tracked) return;
+  if (!tracked) {
+    trk_publish_pose(st, exact);
+    return;
+  }
   if (exact) {
     trk_mul(st->world, st->update, st->world);
     for (int c = 0; c < 3; c++)
       for (int k = 0; k < 3; k++) st->orientation[3 * c + k] = st->world[4 * c + k];
     for (int k = 0; k < 3; k++) st->position[k] = st->world[12 + k];
+    trk_publish_pose(st, exact);
     return;
   }
   const float p[4] = {st->position[0], st->position[1], st->position[2], 1.0f};
@@ -503,6 +522,7 @@ __global__ void k_track_finish(TrackState* st, int tracked, int exact) {
   trk_mul(o, st->update, r);
   for (int c = 0; c < 3; c++)
     for (int k = 0; k < 3; k++) st->orientation[3 * c + k] = r[4 * c + k];
+  trk_publish_pose(st, exact);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -518,7 +538,7 @@ static int icp_grid(int n, int num_sms) {
 static osl_status init_state(osl_tracker* t) {
   TrackState s;
   memset(&s, 0, sizeof(s));
-  for (int i = 0; i < 16; i++) s.update[i] = s.inc[i] = s.world[i] = (i % 5 == 0) ? 1.0f : 0.0f;
+  for (int i = 0; i < 16; i++) s.update[i] = s.inc[i] = s.world[i] = s.pose[i] = (i % 5 == 0) ? 1.0f : 0.0f;
   s.orientation[0] = s.orientation[4] = s.orientation[8] = 1.0f;  // glm's default constructors (rgbd_camera.cpp:22)
   *t->h_state = s;
   OSL_CUDA(cudaMemcpy(t->d_state, &s, sizeof(s), cudaMemcpyHostToDevice));
@@ -660,19 +680,16 @@ osl_status osl_tracker_get_pose(osl_tracker* t, float pose[16], float position[3
   if (orientation) memcpy(orientation, s.orientation, 36);
   if (lost) *lost = s.lost;
   if (pairs) *pairs = s.pairs;
-  if (pose) {
-    if (t->flags & 1) {
-      memcpy(pose, s.world, 64);
-    } else {
-      // mat4(orientation) * translate(position): columns 0-2 = orientation, column 3 = orientation * position
-      for (int i = 0; i < 16; i++) pose[i] = (i % 5 == 0) ? 1.0f : 0.0f;
-      for (int c = 0; c < 3; c++)
-        for (int k = 0; k < 3; k++) pose[4 * c + k] = s.orientation[3 * c + k];
-      for (int k = 0; k < 3; k++)
-        pose[12 + k] = s.orientation[k] * s.position[0] + s.orientation[3 + k] * s.position[1] +
-                       s.orientation[6 + k] * s.position[2] + 0.0f;
-    }
-  }
+  if (pose) memcpy(pose, s.pose, 64);
+  return OSL_OK;
+}
+
+// Device address of the 16 floats osl_tracker_get_pose reports as `pose` (column-major), valid for the tracker's
+// lifetime and rewritten by every update: hand it to osl_integrate_depth_posed on the same stream to fuse the frame
+// the tracker has just localised without waiting for the pose on the host.
+osl_status osl_tracker_pose_device(osl_tracker* t, const float** d_pose) {
+  if (!t || !d_pose) return OSL_ERR_INVALID;
+  *d_pose = t->d_state->pose;
   return OSL_OK;
 }
 

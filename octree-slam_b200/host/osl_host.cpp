@@ -248,6 +248,15 @@ void Octree::addDepthFrame(const uint16_t* depth, const Color256* colors, int wi
                                glm::value_ptr(pose), nullptr), "osl_integrate_depth");
 }
 
+void Octree::addDepthFrame(const uint16_t* depth, const Color256* colors, int width, int height,
+                           glm::vec2 focal_length, const sensor::RGBDCamera& camera) {
+  osl_svo* t = tree(maxDepth(resolution_));
+  const float* d_pose = camera.poseDevice();
+  if (t && d_pose)
+    report(osl_integrate_depth_posed(t, depth, &colors->r, width, height, focal_length.x, focal_length.y, d_pose,
+                                     nullptr), "osl_integrate_depth_posed");
+}
+
 void Octree::addVoxelGrid(const VoxelGrid& grid) {
   osl_svo* t = tree(maxDepth(resolution_));
   if (t) report(osl_integrate_voxels(t, &grid.centers->x, &grid.colors->x, grid.size, nullptr), "osl_integrate_voxels");
@@ -510,6 +519,12 @@ const glm::mat4 RGBDCamera::pose() const {
   for (int c = 0; c < 4; c++)
     for (int r = 0; r < 4; r++) m[c][r] = p[4 * c + r];
   return m;
+}
+
+const float* RGBDCamera::poseDevice() const {
+  const float* p = nullptr;
+  if (tracker_) report(osl_tracker_pose_device(tracker_, &p), "osl_tracker_pose_device");
+  return p;
 }
 
 bool RGBDCamera::lost() const {

@@ -4,9 +4,11 @@
 // pose comes with the frame instead of RGBDCamera (whose update is commented out, main.cpp:35), and the renderer
 // writes a device buffer instead of a GL PBO.
 //
-//   osl_main <frames.bin> <out_prefix> [fused|track]
+//   osl_main <frames.bin> <out_prefix> [fused|track|slam]
 // track: main.cpp:35 uncommented -- the pose of every frame comes from sensor::RGBDCamera (corrected tracker) instead
 //        of the file; the estimated poses are written to <out_prefix>.poses (n x 16 floats, column-major).
+// slam:  track, and every frame after the first is fused with the pose read ON THE DEVICE (Octree::addDepthFrame
+//        with the camera): tracker and integration of a frame are 31 launches without a host round trip.
 // frames.bin: int32 w, h, n; float fx, fy; then n x { float pose[16] (column-major), uint16 depth[w*h], uint8 rgb[w*h*3] }
 // writes <out_prefix>.pool (int32 n_nodes, float center[3], float half, uint32 pool[2n]) and <out_prefix>.rgba (w*h*4).
 #include <cuda_runtime_api.h>
@@ -74,11 +76,12 @@ static int mesh_main(const char* mesh_path, const char* out_prefix) {
 int main(int argc, char** argv) {
   if (argc == 4 && !strcmp(argv[1], "mesh")) return mesh_main(argv[2], argv[3]);
   if (argc < 3) {
-    fprintf(stderr, "usage: %s frames.bin out_prefix [fused|track]\n", argv[0]);
+    fprintf(stderr, "usage: %s frames.bin out_prefix [fused|track|slam]\n", argv[0]);
     return 2;
   }
   const bool fused = argc > 3 && !strcmp(argv[3], "fused");
-  const bool track = argc > 3 && !strcmp(argv[3], "track");
+  const bool slam = argc > 3 && !strcmp(argv[3], "slam");  // track + the pose stays on the device (fused frames)
+  const bool track = slam || (argc > 3 && !strcmp(argv[3], "track"));
   FILE* f = fopen(argv[1], "rb");
   if (!f) { perror(argv[1]); return 2; }
   int hdr[3];
@@ -126,7 +129,10 @@ int main(int argc, char** argv) {
     cudaDeviceSynchronize();
     cloud_bbox = BoundingBox();
     sensor::computePointCloudBoundingBox(points_, num_points, cloud_bbox);
-    if (fused && scene_->tree()) {
+    if (slam && scene_->tree()) {
+      // tracker -> integration of the same frame with no host round trip (the pose above was only read for the log)
+      scene_->tree()->addDepthFrame(frame.depth, frame.color, W, H, focal_length, *camera_estimation_);
+    } else if (fused && scene_->tree()) {
       // the one-call fast path for every frame after the one that creates the tree
       scene_->tree()->addDepthFrame(frame.depth, frame.color, W, H, focal_length, pose);
     } else {

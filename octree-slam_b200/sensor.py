@@ -111,6 +111,12 @@ class RGBDCamera:
             self._keep = depth
             _check(lib().osl_tracker_update(self._h, depth.data_ptr(), None), "osl_tracker_update")
 
+    def pose_device(self):
+        """device address of the pose matrix (osl_tracker_pose_device), for SVO.integrate_depth_tracked"""
+        p = C.c_void_p()
+        _check(lib().osl_tracker_pose_device(self._h, C.byref(p)), "osl_tracker_pose_device")
+        return p.value
+
     def _get(self):
         pose, pos, ori = (C.c_float * 16)(), (C.c_float * 3)(), (C.c_float * 9)()
         lost, pairs = C.c_int(), C.c_int()

@@ -84,6 +84,18 @@ class SVO:
         self._keep = (d, c)  # the call is asynchronous: keep the device buffers alive until the next call
         return self
 
+    def integrate_depth_tracked(self, depth, rgb, fx, fy, camera, stream=None):
+        """main.cpp:33-44 with the tracking line live and no host round trip: `camera` (sensor.RGBDCamera) localises
+        the frame on `stream`, its pose stays in device memory and drives the integration of the same frame."""
+        h, w = depth.shape[:2]
+        d = _dev(depth, np.uint16, self.device)
+        c = _dev(rgb, np.uint8, self.device)
+        _check(lib().osl_tracker_update(camera._h, d.data_ptr(), stream), "osl_tracker_update")
+        _check(lib().osl_integrate_depth_posed(self._h, d.data_ptr(), c.data_ptr(), w, h, fx, fy,
+                                               camera.pose_device(), stream), "osl_integrate_depth_posed")
+        self._keep = (d, c)
+        return self
+
     def integrate_depth_host(self, depth, rgb, fx, fy, pose=IDENTITY, stream=None):
         depth = np.ascontiguousarray(depth, dtype=np.uint16)
         rgb = np.ascontiguousarray(rgb, dtype=np.uint8)

@@ -223,3 +223,30 @@ def test_tracker_feeds_integration(P):
         track.update(d)
         assert np.abs(est - track.pose()).max() <= 1e-4
     assert np.array_equal(svo.pool(), ref_svo.pool())
+
+
+@pytest.mark.parametrize("piped", [False, True])
+@pytest.mark.parametrize("exact", [False, True])
+def test_tracked_integration_without_host_round_trip(P, piped, exact):
+    """osl_tracker_update + osl_integrate_depth_posed on one stream: the pose never visits the host before it is used;
+    reading it back AFTERWARDS and replaying the oracle with it gives the same pool bit for bit"""
+    import torch
+    w, h, D = 320, 240, 10
+    fx, fy = P.synth.focal(w, h)
+    center, half = P.synth.tree_params(D)
+    cam = P.RGBDCamera(w, h, (fx, fy), exact_jacobian=exact)
+    svo = P.SVO(center, half, D).set_pipeline(piped)
+    ref_svo = orc.OracleSVO(center, half, D)
+    frames = [P.synth.make_frame(w, h, pose, seed=k, invalid_frac=0.01, noise_mm=1) for k, pose in enumerate(_poses(5))]
+    dev = [(torch.from_numpy(d).cuda(), torch.from_numpy(c).cuda()) for d, c in frames]
+    torch.cuda.synchronize()
+    used = []
+    for d, c in dev:
+        svo.integrate_depth_tracked(d, c, fx, fy, cam)
+        used.append(cam.pose())          # waits for the tracker only; read after the frame was queued
+    for (d, c), pose in zip(frames, used):
+        ref_svo.integrate_depth(d, c, fx, fy, pose)
+    assert svo.size == ref_svo.size
+    assert np.array_equal(svo.pool(), ref_svo.pool())
+    if exact:
+        assert np.abs(used[-1][:3, 3] - [0.04, 0.0, 0.02]).max() < 8e-3

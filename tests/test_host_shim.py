@@ -126,7 +126,8 @@ def test_scene_voxelize_meshes_replay_matches_oracle(tmp_path):
 
 
 @pytest.mark.gpu
-def test_main_loop_with_camera_tracking_matches_oracle(tmp_path):
+@pytest.mark.parametrize("mode", ["track", "slam"])
+def test_main_loop_with_camera_tracking_matches_oracle(tmp_path, mode):
     """main.cpp:33-44 with line 35 live: sensor::RGBDCamera estimates every pose, the map is built with the estimates"""
     P = pkg()
     w, h, n = 160, 120, 4
@@ -140,7 +141,7 @@ def test_main_loop_with_camera_tracking_matches_oracle(tmp_path):
     fpath = str(tmp_path / "frames.bin")
     _write_frames(fpath, w, h, frames, fx, fy)
     out = str(tmp_path / "out")
-    log = subprocess.check_output([HOST_MAIN, fpath, out, "track"], text=True, timeout=120)
+    log = subprocess.check_output([HOST_MAIN, fpath, out, mode], text=True, timeout=120)
     assert "osl_main:" in log
     est = np.frombuffer(open(out + ".poses", "rb").read(), dtype=np.float32).reshape(n, 4, 4).transpose(0, 2, 1)
     track = orc.OracleTracker(w, h, fx, fy, exact_jacobian=True)
