@@ -107,6 +107,38 @@ def main(out_dir):
             frames["rgb%d" % f] = rgb
             frames["pool%d" % f] = t.pool()
         np.savez_compressed(os.path.join(out_dir, "g6_clouds_d12_ref64.npz"), half=half, D=D, **frames)
+    # G7: camera tracking -- the reference's image / localization kernels and its own RGBDCamera::update
+    # (image_kernels.cu:104-321, localization_kernels.cu, rgbd_camera.cpp) on four frames of a small synthetic orbit
+    import __graft_entry__ as graft
+    synth = graft.load_package().synth
+    w, h = 160, 120
+    fx, fy = synth.focal(w, h)
+    depths = []
+    for k in range(4):
+        M = np.eye(4)
+        a = np.radians(0.3 * k)
+        M[:3, :3] = [[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]]
+        M[:3, 3] = [0.01 * k, 0.0, 0.005 * k]
+        depths.append(synth.make_frame(w, h, M.astype(np.float32), seed=k, invalid_frac=0.02, noise_mm=2)[0])
+    depths = np.stack(depths)
+    filt = [R.bilateral(d) for d in depths[:2]]
+    sub = R.subsample_depth(filt[0])
+    maps = []
+    for f in filt:
+        v = R.vertex_map(f, fx, fy, None)
+        maps.append((v, R.normal_map(v, w, h)))
+    A, b = R.icp_cost2(maps[0][0], maps[0][1], maps[1][0], maps[1][1], w, h)
+    rng = np.random.default_rng(7)
+    rgb = rng.integers(0, 256, size=(500, 3), dtype=np.uint8)
+    cam = R.RefTracker(w, h, fx, fy)
+    ori, pos = [], []
+    for d in depths:
+        cam.update(d)
+        ori.append(cam.orientation())
+        pos.append(cam.position())
+    np.savez_compressed(os.path.join(out_dir, "g7_tracking.npz"), depths=depths, fx=fx, fy=fy, bilateral0=filt[0],
+                        subsample0=sub, normals0=maps[0][1], icp_A=A, icp_b=b, rgb=rgb,
+                        intensity=R.color_to_intensity(rgb), orientation=np.stack(ori), position=np.stack(pos))
     print("golden vectors written to", out_dir)
 
 

@@ -79,3 +79,34 @@ def test_g6_deep_tree_ref64():
     for f in range(2):
         t.integrate_points(g["pts%d" % f], g["rgb%d" % f])
         assert _eq_except_node0_value(t.pool(), g["pool%d" % f])
+
+
+def test_g7_camera_tracking_against_the_reference_kernels_and_rgbd_camera():
+    """bilateralFilter, subsampleDepth, generateNormalMap, computeICPCost2, colorToIntensity and four frames of the
+    reference's own RGBDCamera::update, all run by the reference's code on a B200."""
+    g = _load("g7_tracking.npz")
+    depths, fx, fy = g["depths"], float(g["fx"]), float(g["fy"])
+    h, w = depths.shape[1:]
+    f0 = orc.bilateral(depths[0])
+    diff = np.abs(f0.astype(np.int64) - g["bilateral0"].astype(np.int64))
+    assert diff.max() <= 1 and np.mean(diff != 0) <= 0.005   # exp2f on the CPU vs MUFU.EX2 (see osl_oracle_track.c)
+    # downstream of the reference's OWN filtered image everything is exact or a float sum
+    assert np.array_equal(orc.subsample_depth(g["bilateral0"]), g["subsample0"])
+    v0 = orc.vertex_map(g["bilateral0"], fx, fy)
+    n0 = orc.normal_map(v0, w, h)
+    assert float_bits_equal(n0, g["normals0"])
+    f1 = orc.bilateral(depths[1])
+    v1 = orc.vertex_map(f1, fx, fy)
+    n1 = orc.normal_map(v1, w, h)
+    A, b, pairs = orc.icp_cost(v0, n0, v1, n1)
+    assert pairs > 0.3 * w * h
+    assert np.abs(A - g["icp_A"]).max() <= 2e-4 * np.abs(g["icp_A"]).max()   # incl. the 1 mm bilateral differences
+    assert np.abs(b - g["icp_b"]).max() <= 2e-4 * np.abs(g["icp_A"]).max()
+    assert float_bits_equal(orc.color_to_intensity(g["rgb"]), g["intensity"])
+    t = orc.OracleTracker(w, h, fx, fy)
+    for k in range(depths.shape[0]):
+        t.update(depths[k])
+        assert np.abs(t.orientation() - g["orientation"][k]).max() <= 1e-4, k
+        assert np.abs(t.position() - g["position"][k]).max() <= 1e-4
+    assert not np.array_equal(g["orientation"][-1], np.eye(3, dtype=np.float32))
+    assert np.array_equal(g["position"][-1], np.zeros(3, dtype=np.float32))   # quirk Q18, in the reference itself
