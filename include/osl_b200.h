@@ -143,7 +143,7 @@ osl_status osl_svo_upload(osl_svo* t, const uint32_t* h_pool, int n_nodes);
 osl_status osl_get_counters(const osl_svo* t, osl_counters* out);
 /* Checkpoint / resume: 32-byte header (magic, max_depth, n_nodes, centre, half edge) + the flat 2*n uint32 pool (the
  * array OctreeNode::pullToCPU / pushToGPU exchange, octree.cpp:41-169).  osl_svo_load requires a tree created with
- * the same max_depth / centre / half edge. */
+ * the same max_depth / centre / half edge (after osl_svo_expand: the expanded values, osl_svo_max_depth / osl_svo_view). */
 osl_status osl_svo_save(const osl_svo* t, const char* path);
 osl_status osl_svo_load(osl_svo* t, const char* path);
 
@@ -229,6 +229,7 @@ osl_status osl_icp_cost(const float* d_last_vertex, const float* d_last_normal, 
 /* sensor::RGBDCamera (rgbd_camera.h:17-82, rgbd_camera.cpp:21-191).  flags bit 0 = 0 reproduces the reference
  * (quirks Q17, Q18: the Jacobian above, angles negated, position_ never leaves 0); flags bit 0 = 1 is the
  * corrected tracker (exact Jacobian, increment T*R, camera-to-world pose accumulated as world * update). */
+/* width and height must be multiples of 4 (two pyramid halvings) and at least 8. */
 typedef struct osl_tracker osl_tracker;
 osl_status osl_tracker_create(osl_tracker** out, int width, int height, float fx, float fy, int flags, int device);
 void osl_tracker_destroy(osl_tracker* t);

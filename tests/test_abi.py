@@ -37,3 +37,26 @@ def test_invalid_arguments_are_rejected_without_touching_the_gpu():
     assert P.lib().osl_svo_create(ctypes.byref(h), c, 1.0, 21, 0, 0) == -1     # max_depth > 20
     assert P.lib().osl_svo_create(ctypes.byref(h), c, -1.0, 8, 0, 0) == -1     # half_edge <= 0
     assert P.lib().osl_integrate_points(None, None, None, 3, None) == -1
+    # map growth and camera tracking entry points
+    assert P.lib().osl_svo_expand(None, 1) == -1
+    assert P.lib().osl_svo_max_depth(None) == 0
+    assert P.lib().osl_integrate_depth_posed(None, None, None, 4, 4, 1.0, 1.0, None, None) == -1
+    t = ctypes.c_void_p()
+    assert P.lib().osl_tracker_create(None, 640, 480, 500.0, 500.0, 0, 0) == -1          # no out pointer
+    assert P.lib().osl_tracker_create(ctypes.byref(t), 642, 480, 500.0, 500.0, 0, 0) == -1  # width not a multiple of 4
+    assert P.lib().osl_tracker_create(ctypes.byref(t), 640, 480, 0.0, 500.0, 0, 0) == -1  # focal length <= 0
+    assert P.lib().osl_tracker_update(None, None, None) == -1
+    assert P.lib().osl_tracker_update_host(None, None, None) == -1
+    assert P.lib().osl_tracker_get_pose(None, None, None, None, None, None) == -1
+    assert P.lib().osl_tracker_pose_device(None, None) == -1
+    assert P.lib().osl_tracker_view(None, 0, None, None, None, None) == -1
+    assert P.lib().osl_tracker_reset(None) == -1
+    P.lib().osl_tracker_destroy(None)                                                   # a no-op
+    A, b = (ctypes.c_float * 36)(), (ctypes.c_float * 6)()
+    assert P.lib().osl_icp_cost(None, None, None, None, 10, 0, A, b, None, None) == -1
+    assert P.lib().osl_bilateral_filter(None, None, 8, 8, None) == -1
+    assert P.lib().osl_subsample_depth(None, None, 8, 8, None) == -1
+    assert P.lib().osl_subsample_f32(None, None, 8, 8, None) == -1
+    assert P.lib().osl_generate_normal_map(None, None, 8, 8, None) == -1
+    assert P.lib().osl_transform_normal_map(None, None, 8, None) == -1
+    assert P.lib().osl_color_to_intensity(None, None, 8, None) == -1

@@ -772,3 +772,16 @@ def test_octree_expand_by_size(P):
     ref.expand(2)
     ref.integrate_depth(depth, rgb, fx, fy)
     assert np.array_equal(oc.svo.pool(), ref.pool())
+
+
+def test_checkpoint_of_an_expanded_tree(P, tmp_path):
+    svo, ref = _run_frames(P, 7, 96, 72, 2)
+    svo.expand(1)
+    ref.expand(1)
+    path = str(tmp_path / "grown.svo")
+    svo.save(path)
+    again = P.SVO(svo.view()[2], svo.half_edge, svo.max_depth)
+    again.restore(path)
+    assert again.size == ref.size and np.array_equal(again.pool(), ref.pool())
+    with pytest.raises(Exception):
+        P.SVO(svo.view()[2], svo.half_edge / 2, svo.max_depth - 1).restore(path)  # the geometry before the expansion
