@@ -74,9 +74,9 @@ static int mesh_main(const char* mesh_path, const char* out_prefix) {
 }
 
 int main(int argc, char** argv) {
-  // the frame pipeline's streams are served best by 4 hardware work queues; must precede
+  // the frame pipeline's streams are served best by 3 hardware work queues; must precede
   // the first CUDA call, an explicit setting in the environment wins
-  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "4", 0);
+  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "3", 0);
   if (argc == 4 && !strcmp(argv[1], "mesh")) return mesh_main(argv[2], argv[3]);
   if (argc < 3) {
     fprintf(stderr, "usage: %s frames.bin out_prefix [fused|track|slam]\n", argv[0]);
