@@ -550,20 +550,14 @@ static osl_status init_state(osl_tracker* t) {
 
 extern "C" {
 
-osl_status osl_tracker_create(osl_tracker** out, int width, int height, float fx, float fy, int flags, int device) {
-  if (!out || width < 8 || height < 8 || (width % 4) || (height % 4) || !(fx > 0.0f) || !(fy > 0.0f))
-    return OSL_ERR_INVALID;
-  OSL_CUDA(cudaSetDevice(device));
-  osl_tracker* t = new osl_tracker();
-  memset(t, 0, sizeof(*t));
-  t->device = device; t->w = width; t->h = height; t->fx = fx; t->fy = fy; t->flags = flags;
+static osl_status tracker_alloc(osl_tracker* t) {
   cudaDeviceProp prop;
-  OSL_CUDA(cudaGetDeviceProperties(&prop, device));
+  OSL_CUDA(cudaGetDeviceProperties(&prop, t->device));
   t->num_sms = prop.multiProcessorCount;
-  const size_t n0 = (size_t)width * height;
+  const size_t n0 = (size_t)t->w * t->h;
   for (int s = 0; s < 2; s++)
     for (int i = 0; i < TRK_LEVELS; i++) {
-      const size_t n = (size_t)(width >> i) * (size_t)(height >> i);
+      const size_t n = (size_t)(t->w >> i) * (size_t)(t->h >> i);
       OSL_CUDA(cudaMalloc(&t->vtx[s][i], 12 * n));
       OSL_CUDA(cudaMalloc(&t->nrm[s][i], 12 * n));
     }
@@ -576,8 +570,21 @@ osl_status osl_tracker_create(osl_tracker** out, int width, int height, float fx
   OSL_CUDA(cudaMalloc(&t->d_state, sizeof(TrackState)));
   OSL_CUDA(cudaMallocHost(&t->h_state, sizeof(TrackState)));
   OSL_CUDA(cudaEventCreateWithFlags(&t->done, cudaEventDisableTiming));
-  osl_status rc = init_state(t);
-  if (rc) return rc;
+  return init_state(t);
+}
+
+osl_status osl_tracker_create(osl_tracker** out, int width, int height, float fx, float fy, int flags, int device) {
+  if (!out || width < 8 || height < 8 || (width % 4) || (height % 4) || !(fx > 0.0f) || !(fy > 0.0f))
+    return OSL_ERR_INVALID;
+  OSL_CUDA(cudaSetDevice(device));
+  osl_tracker* t = new osl_tracker();
+  memset(t, 0, sizeof(*t));
+  t->device = device; t->w = width; t->h = height; t->fx = fx; t->fy = fy; t->flags = flags;
+  const osl_status rc = tracker_alloc(t);
+  if (rc) {  // release whatever was allocated before the failure (every pointer starts out null)
+    osl_tracker_destroy(t);
+    return rc;
+  }
   *out = t;
   return OSL_OK;
 }
@@ -590,8 +597,8 @@ void osl_tracker_destroy(osl_tracker* t) {
     for (int i = 0; i < TRK_LEVELS; i++) { cudaFree(t->vtx[s][i]); cudaFree(t->nrm[s][i]); }
   cudaFree(t->work_v); cudaFree(t->work_n); cudaFree(t->filt); cudaFree(t->tmp); cudaFree(t->stage);
   cudaFree(t->partials); cudaFree(t->d_state);
-  cudaFreeHost(t->h_state);
-  cudaEventDestroy(t->done);
+  if (t->h_state) cudaFreeHost(t->h_state);
+  if (t->done) cudaEventDestroy(t->done);
   delete t;
 }
 
