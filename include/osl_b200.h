@@ -110,7 +110,8 @@ osl_status osl_get_stage_times(osl_svo* t, float ms[4]);
 osl_status osl_integrate_depth(osl_svo* t, const uint16_t* d_depth, const uint8_t* d_rgb, int w, int h, float fx,
                                float fy, const float pose[16], void* stream);
 /* Same with the pose in DEVICE memory (16 floats, column-major), read when the first kernel of the frame runs: the
- * pose may be the result of work queued earlier on `stream` (osl_tracker_update + osl_tracker_pose_device). */
+ * pose may be the result of work queued earlier on `stream` (osl_tracker_update + osl_tracker_pose_device), and
+ * work queued on `stream` afterwards may overwrite it (in pipelined mode `stream` is ordered after that kernel). */
 osl_status osl_integrate_depth_posed(osl_svo* t, const uint16_t* d_depth, const uint8_t* d_rgb, int w, int h, float fx,
                                      float fy, const float* d_pose_colmajor, void* stream);
 /* Same from host buffers (what OpenNIDevice::readFrame + mainLoop do, openni_device.cpp:122,144).  The H2D copies run

@@ -152,6 +152,8 @@ void osl_svo_destroy(osl_svo* t) {
     if (t->ring_ev[i]) cudaEventDestroy(t->ring_ev[i]);
   for (int i = 0; i < 5; i++)
     if (t->stage_ev[i]) cudaEventDestroy(t->stage_ev[i]);
+  if (t->pose_ev) cudaEventDestroy(t->pose_ev);
+  if (t->pose_read_ev) cudaEventDestroy(t->pose_read_ev);
   if (t->copy_stream) cudaStreamDestroy(t->copy_stream);
   if (t->h_ring) cudaFreeHost(t->h_ring);
   delete t;

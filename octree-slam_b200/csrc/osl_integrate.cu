@@ -1485,6 +1485,13 @@ osl_status osl_run_integrate(osl_svo* t, EmitParams& ep, const void* colors, cud
     k_emit<<<etiles, EMIT_THREADS, EMIT_SMEM, sE>>>(ep, t->tp, vec_ok, t->d_keysA[fslot], t->d_payA[fslot],
                                                    t->d_keysB[fslot], fs, fslot);
     OSL_LAUNCHED(1);
+    if (piped && ep.mode == 0 && ep.M_dev) {
+      // the producer of the pose (a tracker on the caller's stream) rewrites it for the next frame: order the
+      // caller's stream after the only kernel that reads it
+      if (!t->pose_read_ev) OSL_CUDA(cudaEventCreateWithFlags(&t->pose_read_ev, cudaEventDisableTiming));
+      OSL_CUDA(cudaEventRecord(t->pose_read_ev, sE));
+      OSL_CUDA(cudaStreamWaitEvent(st, t->pose_read_ev, 0));
+    }
     if (timing) OSL_CUDA(cudaEventRecord(t->stage_ev[1], st));
     // ---- So: sort
     if (piped) {

@@ -156,6 +156,7 @@ struct osl_svo {
   size_t ws_cap;
   size_t ws_want;     // capacity to restore after osl_drop_workspace
   cudaEvent_t pose_ev;  // pipelined frames whose pose is produced on the caller's stream (lazily created)
+  cudaEvent_t pose_read_ev;  // ... and the caller's stream is ordered after the kernel that reads it
   u64 *d_keysA[OSL_FRONT], *d_keysB[OSL_FRONT];  // sort ping/pong per front buffer
   u32 *d_payA[OSL_FRONT], *d_payB[OSL_FRONT];
   u64* d_keysC; u32* d_payC;   // k_sort_bucket slow-path scratch
