@@ -299,7 +299,7 @@ def run_ours(args):
     svo2.close()
 
     # camera tracking (the step before integration): frame-to-frame ICP on resident depth frames,
-    # 26 launches per frame, pose read back once at the end
+    # 27 launches per frame, pose read back once at the end
     cam = pkg.RGBDCamera(W, H, (fx, fy), exact_jacobian=True, device=local)
     n_trk = min(K, 100)
     for k in range(3):

@@ -236,7 +236,7 @@ osl_status osl_tracker_create(osl_tracker** out, int width, int height, float fx
 void osl_tracker_destroy(osl_tracker* t);
 osl_status osl_tracker_reset(osl_tracker* t);
 /* RGBDCamera::update: bilateral filter, 3-level pyramid of vertex + normal maps, 4 + 5 + 10 Gauss-Newton
- * iterations coarse to fine against the previous frame, pose update.  26 launches, no host round trip;
+ * iterations coarse to fine against the previous frame, pose update.  27 launches, no host round trip;
  * asynchronous on `stream`.  _host: the depth image is in host memory (pinned for a truly asynchronous copy). */
 osl_status osl_tracker_update(osl_tracker* t, const uint16_t* d_depth, void* stream);
 osl_status osl_tracker_update_host(osl_tracker* t, const uint16_t* h_depth, void* stream);

@@ -5,7 +5,7 @@
 //           sensor::computeICPCost2                     localization_kernels.cu:155-231, 313-330
 //           sensor::RGBDCamera::update / solveCholesky   rgbd_camera.cpp:53-224
 //
-// Design (not the reference's): one frame of tracking is 26 asynchronous launches on one stream and NO host round
+// Design (not the reference's): one frame of tracking is 27 asynchronous launches on one stream and NO host round
 // trip.  The reference synchronises after every kernel, copies 42 floats to the host 19 times per frame, solves the
 // 6x6 system there and materialises a transformed copy of the vertex / normal maps between iterations.  Here each
 // ICP iteration is ONE kernel: it applies the previous iteration's increment to the working maps on the fly,
