@@ -45,6 +45,13 @@ for exact in (False, True):
     for d_, _, dd, _, _ in frames[:3]:
         cam.update(dd if exact else d_)
     pose = cam.pose()
+# tracked SLAM frames: the pose stays on the device (strict and pipelined)
+for piped in (False, True):
+    cam = P.RGBDCamera(w, h, (fx, fy), exact_jacobian=True)
+    tsvo = P.SVO(center, half, D).set_pipeline(piped)
+    for _, _, dd, cc, _ in frames[:4]:
+        tsvo.integrate_depth_tracked(dd, cc, fx, fy, cam)
+    tsvo.sync()
 f = P.sensor.bilateralFilter(frames[0][0])
 s = P.sensor.subsampleDepth(f)
 vm = P.generateVertexMap(f, fx, fy)
