@@ -782,22 +782,28 @@ osl_status osl_icp_cost(const float* d_last_vertex, const float* d_last_normal, 
   int dev = 0, sms = 0;
   OSL_CUDA(cudaGetDevice(&dev));
   OSL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  TrackState* d_state;
-  float* d_part;
-  OSL_CUDA(cudaMallocAsync(&d_state, sizeof(TrackState), st));
-  OSL_CUDA(cudaMallocAsync(&d_part, (size_t)TRK_MAX_CTAS * (TRK_TERMS + 1) * sizeof(float), st));
-  OSL_CUDA(cudaMemsetAsync(d_state, 0, sizeof(TrackState), st));
-  float* nv = const_cast<float*>(d_this_vertex);
-  float* nn = const_cast<float*>(d_this_normal);
-  k_icp_step<<<icp_grid(n, sms), TRK_THREADS, 0, st>>>(d_last_vertex, d_last_normal, d_this_vertex, d_this_normal, nv,
-                                                      nn, n, 0, 0, 0, flags & 1, d_state, d_part);
-  OSL_CUDA(cudaGetLastError());
-  OSL_LAUNCHED(1);
+  TrackState* d_state = nullptr;
+  float* d_part = nullptr;
   TrackState h;
-  OSL_CUDA(cudaMemcpyAsync(&h, d_state, sizeof(h), cudaMemcpyDeviceToHost, st));
-  OSL_CUDA(cudaFreeAsync(d_state, st));
-  OSL_CUDA(cudaFreeAsync(d_part, st));
-  OSL_CUDA(cudaStreamSynchronize(st));
+  cudaError_t e = cudaMallocAsync(&d_state, sizeof(TrackState), st);
+  if (e == cudaSuccess) e = cudaMallocAsync(&d_part, (size_t)TRK_MAX_CTAS * (TRK_TERMS + 1) * sizeof(float), st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_state, 0, sizeof(TrackState), st);
+  if (e == cudaSuccess) {
+    float* nv = const_cast<float*>(d_this_vertex);  // never written: apply = 0 and dst == src
+    float* nn = const_cast<float*>(d_this_normal);
+    k_icp_step<<<icp_grid(n, sms), TRK_THREADS, 0, st>>>(d_last_vertex, d_last_normal, d_this_vertex, d_this_normal, nv,
+                                                        nn, n, 0, 0, 0, flags & 1, d_state, d_part);
+    e = cudaGetLastError();
+    OSL_LAUNCHED(1);
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&h, d_state, sizeof(h), cudaMemcpyDeviceToHost, st);
+  if (d_state) cudaFreeAsync(d_state, st);  // released on every path
+  if (d_part) cudaFreeAsync(d_part, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) {
+    g_osl_last_cuda_error = (int)e;
+    return e == cudaErrorMemoryAllocation ? OSL_ERR_OOM : OSL_ERR_CUDA;
+  }
   memcpy(A, h.A, sizeof(h.A));
   memcpy(b, h.b, sizeof(h.b));
   if (pairs) *pairs = h.pairs;
