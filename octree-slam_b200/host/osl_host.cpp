@@ -42,6 +42,10 @@ VoxelGrid::~VoxelGrid() {
   }
 }
 
+// column-major float[16] view of a mat4; works with the reference's glm 0.9.5.4 (where value_ptr lives in a gtc
+// header main.cpp's translation units do not all include) and with include/glm/glm.hpp alike
+static inline const float* mat_ptr(const glm::mat4& m) { return &m[0].x; }
+
 static void report(osl_status s, const char* where) {
   // the reference returns void and checks nothing on this path; errors are reported, never fatal
   if (s != OSL_OK) fprintf(stderr, "[octree_slam] %s: %s (cuda %d)\n", where, osl_status_string(s), osl_last_cuda_error());
@@ -113,7 +117,7 @@ void svoFromDepthFrame(const uint16_t* depth, const Color256* colors, int width,
   osl_svo* t = lookup_or_create(octree, octree_size, octree_center, edge_length, max_depth);
   if (!t) return;
   report(osl_integrate_depth(t, depth, &colors->r, width, height, focal_length.x, focal_length.y,
-                             glm::value_ptr(pose), nullptr), "osl_integrate_depth");
+                             mat_ptr(pose), nullptr), "osl_integrate_depth");
   publish(t, octree_size ? octree : nullptr, octree, octree_size);
 }
 
@@ -245,7 +249,7 @@ void Octree::addDepthFrame(const uint16_t* depth, const Color256* colors, int wi
   osl_svo* t = tree(maxDepth(resolution_));
   if (t)
     report(osl_integrate_depth(t, depth, &colors->r, width, height, focal_length.x, focal_length.y,
-                               glm::value_ptr(pose), nullptr), "osl_integrate_depth");
+                               mat_ptr(pose), nullptr), "osl_integrate_depth");
 }
 
 void Octree::addDepthFrame(const uint16_t* depth, const Color256* colors, int width, int height,
@@ -366,7 +370,7 @@ namespace rendering {
 void coneTraceSVO(uchar4* pos, glm::vec2 resolution, float fov, glm::mat4 cameraPose, SVO octree) {
   const float c[3] = {octree.center.x, octree.center.y, octree.center.z};
   report(osl_raycast_pool(octree.data, c, octree.size, &pos->x, (int)resolution.x, (int)resolution.y, fov,
-                          glm::value_ptr(cameraPose), nullptr, nullptr, nullptr), "osl_raycast_pool");
+                          mat_ptr(cameraPose), nullptr, nullptr, nullptr), "osl_raycast_pool");
   cudaDeviceSynchronize();  // the reference call is synchronous on return
 }
 
@@ -396,7 +400,7 @@ void generateVertexMap(const uint16_t* depth_pixels, glm::vec3* vertex_map, cons
 }
 
 void transformVertexMap(glm::vec3* vertex_map, const glm::mat4& trans, const int size) {
-  report(osl_transform_vertex_map(&vertex_map->x, glm::value_ptr(trans), size, nullptr), "osl_transform_vertex_map");
+  report(osl_transform_vertex_map(&vertex_map->x, mat_ptr(trans), size, nullptr), "osl_transform_vertex_map");
 }
 
 void computePointCloudBoundingBox(glm::vec3* points, const int num_points, BoundingBox& bbox) {
@@ -423,7 +427,7 @@ void colorToIntensity(const Color256* color_in, float* intensity_out, const int 
 }
 
 void transformNormalMap(glm::vec3* normal_map, const glm::mat4& trans, const int size) {
-  report(osl_transform_normal_map(&normal_map->x, glm::value_ptr(trans), size, nullptr), "osl_transform_normal_map");
+  report(osl_transform_normal_map(&normal_map->x, mat_ptr(trans), size, nullptr), "osl_transform_normal_map");
 }
 
 // image_kernels.cu:262-277 / 299-313: temporary of a quarter of the size, kernel, copy back over the input

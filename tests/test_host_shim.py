@@ -42,6 +42,26 @@ def test_host_library_exports_the_reference_interface():
     assert "libosl_b200.so" in needed and "libcudart" in needed
 
 
+REF_GLM = "/root/reference/external/include"
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF_GLM, "glm")),
+                    reason="the reference tree (its vendored glm 0.9.5.4) is not mounted here")
+def test_shim_builds_against_the_reference_glm(tmp_path):
+    """a maintainer compiles the shim inside the reference tree, i.e. with the reference's
+    own glm first on the include path; the replay of main.cpp must compile unchanged too."""
+    inc = ["-I" + REF_GLM, "-I" + os.path.join(ROOT, "include"), "-I/usr/local/cuda/include"]
+    host = os.path.join(PKG_DIR, "host")
+    out = str(tmp_path / "libosl_host_refglm.so")
+    subprocess.check_call(["g++", "-std=c++14", "-O1", "-fPIC", "-w", "-shared"] + inc +
+                          [os.path.join(host, "osl_host.cpp"), "-o", out], stderr=subprocess.DEVNULL)
+    syms = subprocess.check_output(["nm", "-D", "--demangle", "--defined-only", out], text=True)
+    assert "glm::detail::tvec3<float" in syms            # really the reference's glm types in the signatures
+    assert "octree_slam::sensor::RGBDCamera::update(" in syms and "octree_slam::world::Octree::addCloud(" in syms
+    subprocess.check_call(["g++", "-std=c++14", "-w", "-fsyntax-only"] + inc + [os.path.join(host, "osl_main.cpp")],
+                          stderr=subprocess.DEVNULL)
+
+
 def _write_frames(path, w, h, frames, fx, fy):
     with open(path, "wb") as f:
         f.write(struct.pack("<iiiff", w, h, len(frames), fx, fy))
