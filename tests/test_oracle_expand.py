@@ -104,3 +104,35 @@ def test_expand_keeps_the_voxel_set_and_matches_a_tree_built_in_the_larger_cube(
     cenb, colb = _voxel_set(b)
     assert cen1[:, 0].max() > 4.0
     assert np.array_equal(cen1, cenb) and np.array_equal(col1, colb)
+
+
+def test_expand_properties_on_random_clouds():
+    """seeded random clouds, several depths and layer counts: growing keeps every occupied voxel (centre and colour),
+    and growing then inserting equals inserting into a tree that was created large"""
+    from common import unique_voxel_points
+    for seed, (D, layers) in enumerate([(3, 1), (5, 2), (6, 3), (8, 1), (4, 2)]):
+        rng = np.random.default_rng(100 + seed)
+        half = 1.0
+        a = orc.OracleSVO((0, 0, 0), half, D)
+        b = orc.OracleSVO((0, 0, 0), half * 2 ** layers, D + layers)
+        pts = unique_voxel_points(rng, 400, (0, 0, 0), half, D)
+        rgb = rng.integers(0, 256, size=(pts.shape[0], 3)).astype(np.uint8)
+        for t in (a, b):
+            t.integrate_points(pts, rgb)
+            t.integrate_points(pts, rgb)          # alpha > 127 everywhere that is occupied
+        before = _voxel_set(a)
+        n0 = a.size
+        a.expand(layers)
+        assert a.size == n0 + 64 * layers and a.max_depth == D + layers and a.half_edge == half * 2 ** layers
+        check_pool_invariants(a.pool())
+        after = _voxel_set(a)
+        assert np.array_equal(before[0], after[0]) and np.array_equal(before[1], after[1])
+        big = _voxel_set(b)
+        assert np.array_equal(after[0], big[0]) and np.array_equal(after[1], big[1])
+        more = unique_voxel_points(rng, 300, (0, 0, 0), half * 2 ** layers, D + layers)
+        rgb2 = rng.integers(0, 256, size=(more.shape[0], 3)).astype(np.uint8)
+        for t in (a, b):
+            t.integrate_points(more, rgb2)
+            t.integrate_points(more, rgb2)
+        ga, gb = _voxel_set(a), _voxel_set(b)
+        assert np.array_equal(ga[0], gb[0]) and np.array_equal(ga[1], gb[1]), (seed, D, layers)
