@@ -785,3 +785,29 @@ def test_checkpoint_of_an_expanded_tree(P, tmp_path):
     assert again.size == ref.size and np.array_equal(again.pool(), ref.pool())
     with pytest.raises(Exception):
         P.SVO(svo.view()[2], svo.half_edge / 2, svo.max_depth - 1).restore(path)  # the geometry before the expansion
+
+
+@pytest.mark.parametrize("seed,D,layers", [(0, 3, 1), (1, 5, 2), (2, 6, 3), (3, 9, 1), (4, 17, 3)])
+def test_expand_random_clouds_match_oracle(P, seed, D, layers):
+    rng = np.random.default_rng(200 + seed)
+    half = 1.0
+    svo, ref = P.SVO((0, 0, 0), half, D), orc.OracleSVO((0, 0, 0), half, D)
+    pts = rng.uniform(-1.0, 1.0, size=(3000, 3)).astype(np.float32)     # duplicates included
+    rgb = rng.integers(0, 256, size=(pts.shape[0], 3)).astype(np.uint8)
+    for t in (svo, ref):
+        t.integrate_points(pts, rgb)
+        t.expand(layers)
+    assert np.array_equal(svo.pool(), ref.pool())
+    big = half * 2 ** layers
+    more = rng.uniform(-big, big, size=(5000, 3)).astype(np.float32)
+    rgb2 = rng.integers(0, 256, size=(more.shape[0], 3)).astype(np.uint8)
+    for t in (svo, ref):
+        t.integrate_points(more, rgb2)
+        t.integrate_points(pts, rgb)
+    assert svo.size == ref.size
+    pool = svo.pool()
+    assert np.array_equal(pool, ref.pool())
+    check_pool_invariants(pool)
+    c, k, keys = svo.extract_voxels()
+    rc, rk, rkeys = ref.extract_voxels()
+    assert np.array_equal(keys, rkeys) and float_bits_equal(c, rc) and float_bits_equal(k, rk)
