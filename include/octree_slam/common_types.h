@@ -15,13 +15,11 @@ struct int2 { int x, y; };
 static inline int2 make_int2(int x, int y) { int2 r; r.x = x; r.y = y; return r; }
 #endif
 
-struct BoundingBox {  // common_types.h:8-17
-  glm::vec3 bbox0 = glm::vec3(0.0f);
-  glm::vec3 bbox1 = glm::vec3(0.0f);
-  bool contains(const BoundingBox& o) const {
-    return bbox0.x <= o.bbox0.x && bbox0.y <= o.bbox0.y && bbox0.z <= o.bbox0.z && bbox1.x >= o.bbox1.x &&
-           bbox1.y >= o.bbox1.y && bbox1.z >= o.bbox1.z;
-  }
+struct BoundingBox {  // common_types.h:8-17; the two members are defined out of line (common_types.cu:8-34 in the
+  glm::vec3 bbox0 = glm::vec3(0.0f);  // reference, osl_host.cpp here) so that objects compiled against the
+  glm::vec3 bbox1 = glm::vec3(0.0f);  // reference's header find them in libosl_host.so
+  bool contains(const BoundingBox& other) const;
+  float distanceOutside(const BoundingBox& other) const;
 };
 
 struct Mesh {  // common_types.h:20-32 ("a lighter weight version of obj"): HOST arrays

@@ -6,7 +6,8 @@
 namespace octree_slam {
 namespace rendering {
 // pos: DEVICE buffer of resolution.x * resolution.y uchar4 (a mapped GL PBO in the reference)
-void coneTraceSVO(uchar4* pos, glm::vec2 resolution, float fov, glm::mat4 cameraPose, SVO octree);
+// (`extern "C"` as in the reference: the symbol is the unmangled `coneTraceSVO`)
+extern "C" void coneTraceSVO(uchar4* pos, glm::vec2 resolution, float fov, glm::mat4 cameraPose, SVO octree);
 }  // namespace rendering
 }  // namespace octree_slam
 #endif

@@ -26,12 +26,12 @@ struct RGBDFrame {  // localization_kernels.h:26-33
 
 // localization_kernels.h:40: normal equations of the point-to-plane ICP, every pixel paired with the same pixel of
 // the last frame.  A: 36 floats (row-major 6x6), b: 6 floats, in host memory.
-void computeICPCost2(const ICPFrame* last_frame, const ICPFrame& this_frame, float* A, float* b);
+extern "C" void computeICPCost2(const ICPFrame* last_frame, const ICPFrame& this_frame, float* A, float* b);
 // localization_kernels.h:37: in the reference this variant compacts the correspondences first and sums the same
 // terms without the depth-range test of computeICPCost2; here it forwards to computeICPCost2.
-void computeICPCost(const ICPFrame* last_frame, const ICPFrame& this_frame, float* A, float* b);
+extern "C" void computeICPCost(const ICPFrame* last_frame, const ICPFrame& this_frame, float* A, float* b);
 // localization_kernels.h:43: empty in the reference (localization_kernels.cu:332-335); empty here.
-void computeRGBDCost(const RGBDFrame* last_frame, const RGBDFrame& this_frame, float* A, float* b);
+extern "C" void computeRGBDCost(const RGBDFrame* last_frame, const RGBDFrame& this_frame, float* A, float* b);
 
 }  // namespace sensor
 }  // namespace octree_slam

@@ -12,10 +12,11 @@ inline int log_N() { return 8; }  // voxelization.cu:24 GRID_RES
 
 // Reference signature.  The grid is the depth-log_N() leaf grid of the cube (centre = bbox mid-point, half edge =
 // bbox.bbox1.x) Scene::voxelizeMeshes builds its Octree on (scene.cpp:78), so every voxel centre is a leaf centre.
-void meshToVoxelGrid(const Mesh& m_in, const bmp_texture* tex, VoxelGrid& grid_out);
-// same on an explicit cube / depth
-void meshToVoxelGrid(const Mesh& m_in, const bmp_texture* tex, const glm::vec3& center, float half_edge, int depth,
-                     VoxelGrid& grid_out);
+// (`extern "C"` as in the reference, voxelization.h:21)
+extern "C" void meshToVoxelGrid(const Mesh& m_in, const bmp_texture* tex, VoxelGrid& grid_out);
+// same on an explicit cube / depth (new; C++ linkage -- an extern "C" name cannot be overloaded)
+void meshToVoxelGridAt(const Mesh& m_in, const bmp_texture* tex, const glm::vec3& center, float half_edge, int depth,
+                       VoxelGrid& grid_out);
 
 }  // namespace voxelization
 }  // namespace octree_slam

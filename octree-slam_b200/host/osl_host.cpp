@@ -25,7 +25,29 @@
 
 #include "osl_b200.h"
 
-// ---- common_types.cu:36-52 -------------------------------------------------------------------------------------
+#include <type_traits>
+// The seam takes glm types and SVO by value; with glm 0.9.5.4 they are "non-trivial for the purposes of calls" (passed
+// by invisible reference).  Whatever glm this file is compiled against must agree, or the symbols would link and the
+// arguments would arrive garbled.
+static_assert(!std::is_trivially_copy_constructible<glm::vec2>::value && !std::is_trivially_copy_constructible<glm::vec3>::value &&
+              !std::is_trivially_copy_constructible<glm::mat4>::value && !std::is_trivially_copy_constructible<SVO>::value,
+              "glm types must have glm 0.9.5's calling convention (user-provided copy constructors)");
+static_assert(sizeof(glm::vec3) == 12 && sizeof(glm::mat4) == 64 && sizeof(SVO) == 24 && sizeof(Color256) == 3 &&
+              sizeof(BoundingBox) == 24, "layout contract of the reference's POD types");
+
+// ---- common_types.cu:8-52 --------------------------------------------------------------------------------------
+bool BoundingBox::contains(const BoundingBox& o) const {
+  return bbox0.x <= o.bbox0.x && bbox0.y <= o.bbox0.y && bbox0.z <= o.bbox0.z && bbox1.x >= o.bbox1.x &&
+         bbox1.y >= o.bbox1.y && bbox1.z >= o.bbox1.z;
+}
+// largest overhang of THIS box beyond `o` along any axis (0 when inside), common_types.cu:22-34
+float BoundingBox::distanceOutside(const BoundingBox& o) const {
+  float d = 0.0f;
+  const float lo[3] = {o.bbox0.x - bbox0.x, o.bbox0.y - bbox0.y, o.bbox0.z - bbox0.z};
+  const float hi[3] = {bbox1.x - o.bbox1.x, bbox1.y - o.bbox1.y, bbox1.z - o.bbox1.z};
+  for (int i = 0; i < 3; i++) d = std::fmax(d, std::fmax(lo[i], hi[i]));
+  return d;
+}
 RawFrame::RawFrame(const int w, const int h) : height(h), width(w) {
   cudaMalloc((void**)&color, (size_t)h * w * sizeof(Color256));
   cudaMalloc((void**)&depth, (size_t)h * w * sizeof(uint16_t));
@@ -159,8 +181,8 @@ namespace voxelization {
 
 static inline float clamp01(float v) { return v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v); }
 
-void meshToVoxelGrid(const Mesh& m_in, const bmp_texture* tex, const glm::vec3& center, float half_edge, int depth,
-                     VoxelGrid& grid_out) {
+void meshToVoxelGridAt(const Mesh& m_in, const bmp_texture* tex, const glm::vec3& center, float half_edge, int depth,
+                       VoxelGrid& grid_out) {
   const int n_tri = m_in.ibosize / 3, n_vert = m_in.vbosize / 3;
   // per-triangle flat colour, the reference's ColorShader: no texture -> green; no texture coordinates -> texel 0;
   // else the texel at the FIRST corner ("TODO: interpolate", voxelization.cu:125-126); quantised to 8 bits and
@@ -206,7 +228,7 @@ void meshToVoxelGrid(const Mesh& m_in, const bmp_texture* tex, const glm::vec3& 
 }
 
 void meshToVoxelGrid(const Mesh& m_in, const bmp_texture* tex, VoxelGrid& grid_out) {
-  meshToVoxelGrid(m_in, tex, (m_in.bbox.bbox1 + m_in.bbox.bbox0) / 2.0f, m_in.bbox.bbox1.x, log_N(), grid_out);
+  meshToVoxelGridAt(m_in, tex, (m_in.bbox.bbox1 + m_in.bbox.bbox0) / 2.0f, m_in.bbox.bbox1.x, log_N(), grid_out);
 }
 
 }  // namespace voxelization

@@ -78,3 +78,121 @@ def float_bits_equal(a, b):
     if not np.array_equal(na, nb):
         return False
     return np.array_equal(a.view(np.uint32)[~na], b.view(np.uint32)[~nb])
+
+
+# ---- per-leaf legal-outcome check of one integrated frame (reference quirk Q7, svo.cu:366-381) -------------------
+
+def blend_u8(cur, rgb):
+    """fillNodes(Color256) (svo.cu:366-381) in integers: cur uint32 word1 [n], rgb uint8 [n, 3] -> new word1 [n]"""
+    cur = np.asarray(cur, dtype=np.uint64)
+    a = cur >> 24
+    out = np.zeros_like(cur)
+    for ch in range(3):
+        c = (cur >> (8 * ch)) & 0xFF
+        out |= ((((256 - a) * rgb[:, ch].astype(np.uint64) + a * c) >> 8) & 0xFF) << (8 * ch)
+    return (out | (np.minimum(255, a + 2) << 24)).astype(np.uint32)
+
+
+def average8(vals):
+    """averageChildren with Q5 (svo.cu:384-441): vals uint32 [n, 8] -> uint32 [n]"""
+    v = np.asarray(vals, dtype=np.uint64)
+    out = np.zeros(v.shape[0], dtype=np.uint64)
+    for ch in range(3):
+        out |= (((v >> (8 * ch)) & 0xFF).sum(axis=1) >> 3) << (8 * ch)
+    return (out | ((v >> 24).max(axis=1) << 24)).astype(np.uint32)
+
+
+def descend(pool, keys, D):
+    """node index at every depth 1..D for leading-1 Morton keys (int64 [n]) whose whole path exists in `pool`.
+    Returns int64 [D, n] (row d-1 = the depth-d node)."""
+    keys = np.asarray(keys, dtype=np.int64)
+    w0 = pool[0::2]
+    path = np.zeros((D, keys.size), dtype=np.int64)
+    node = (keys >> (3 * (D - 1))) & 7
+    path[0] = node
+    for d in range(2, D + 1):
+        w = w0[node]
+        assert np.all(w & FLAG), "path of a key is not in the tree at depth %d" % (d - 1)
+        node = (w & MASK).astype(np.int64) + ((keys >> (3 * (D - d))) & 7)
+        path[d - 1] = node
+    return path
+
+
+def check_frame_outcome(before, after, keys, rgb, D, canonical):
+    """One integrated depth frame, every leaf and every touched node checked.
+
+    before / after: uint32 pools (2 words per node) around the frame; keys: int64 leading-1 key per input (1 =
+    invalid); rgb: uint8 [n, 3].  canonical=True (ours): a leaf's value is the blend of the LOWEST input index that
+    maps to it, alpha += 2 once.  canonical=False (the reference's racing read-modify-writes): the value must be
+    reachable by m >= 1 successive blends of colours of inputs that map to the leaf, alpha += 2m.  Both: untouched
+    value words are unchanged, every touched inner node holds averageChildren of its tile (node 0 apart: Q6)."""
+    n_after, n_before = after.size // 2, before.size // 2
+    bw1 = np.full(n_after, EMPTY, dtype=np.uint32)
+    bw1[:n_before] = before[1::2]
+    if n_before == 0:
+        bw1[:8] = 0  # initOctree (svo.cu:24-31): the root's children start as {0, 0}
+    aw1 = after[1::2]
+    keys = np.asarray(keys, dtype=np.int64).ravel()
+    rgb = np.asarray(rgb, dtype=np.uint8).reshape(-1, 3)
+    valid = np.flatnonzero(keys != 1)
+    order = valid[np.lexsort((valid, keys[valid]))]      # by key, then by input index
+    ks = keys[order]
+    head = np.ones(ks.size, dtype=bool)
+    head[1:] = ks[1:] != ks[:-1]
+    starts = np.flatnonzero(head)
+    ukeys = ks[starts]
+    counts = np.diff(np.append(starts, ks.size))
+    path = descend(after, ukeys, D)
+    leaf = path[D - 1]
+    group = np.cumsum(head) - 1                           # leaf group of every sorted input
+    cur = bw1[leaf]
+    got = aw1[leaf]
+    # leaves whose alpha may saturate under racing duplicates (boundary cells that swallow everything outside the
+    # cube): only their alpha range is checked in the non-canonical case
+    sat = (cur >> 24).astype(int) + 2 * counts > 255
+    if canonical:
+        want = blend_u8(cur, rgb[order[starts]])
+        bad = np.flatnonzero(want != got)
+        assert bad.size == 0, "%d leaves are not the blend of their lowest input" % bad.size
+    else:
+        m = ((got >> 24).astype(int) - (cur >> 24).astype(int))
+        assert np.all(m[~sat] % 2 == 0) and np.all(m >= np.minimum(2, 255 - (cur >> 24).astype(int))) and \
+            np.all(m <= 2 * counts), "alpha outside {+2 .. +2k}"
+        one = blend_u8(cur[group], rgb[order]) == got[group]
+        ok = np.zeros(ukeys.size, dtype=bool)
+        np.logical_or.at(ok, group, one)
+        ok &= (m == 2)
+        assert sat.mean() < 0.02, "too many leaves near alpha saturation for a meaningful check"
+        for g in np.flatnonzero(~ok & ~sat):                     # serialised duplicates (rare): chains of m/2 blends
+            cols = rgb[order[starts[g]:starts[g] + counts[g]]]
+            states = {int(cur[g])}
+            for _ in range(m[g] // 2):
+                nxt = set()
+                for s in states:
+                    nxt.update(int(x) for x in blend_u8(np.full(cols.shape[0], s, dtype=np.uint32), cols))
+                states = nxt
+            assert int(got[g]) in states, "leaf %d: value %08x is no blend of its %d inputs" % (leaf[g], got[g], counts[g])
+    # inner nodes on the touched paths: averageChildren of their tile; node 0's value word is Q6's
+    touched = np.zeros(n_after, dtype=bool)
+    touched[leaf] = True
+    w0 = after[0::2]
+    for d in range(1, D):
+        nodes = np.unique(path[d - 1])
+        touched[nodes] = True
+        nodes = nodes[nodes != 0]
+        tiles = (w0[nodes] & MASK).astype(np.int64)
+        want = average8(aw1[tiles[:, None] + np.arange(8)[None, :]])
+        assert np.array_equal(want, aw1[nodes]), "depth-%d node values are not averageChildren of their tiles" % d
+    if canonical and n_after >= 8 and D >= 2 and ukeys.size:
+        # Q6 canon: the root average is taken once, from node 0's own (pre-clobber) value: averageChildren of its
+        # tile when node 0 lies on a touched path, else the word it held before the frame
+        v = aw1[:8].copy()
+        v[0] = bw1[0]
+        if touched[0] and (w0[0] & FLAG):
+            t0 = int(w0[0] & MASK)
+            v[0] = average8(aw1[t0:t0 + 8][None, :])[0]
+        assert aw1[0] == average8(v[None, :])[0], "node 0 (Q6) is not the canonical root average"
+    untouched = ~touched
+    untouched[0] = False
+    assert np.array_equal(aw1[untouched], bw1[untouched]), "a value word off the touched paths changed"
+    return ukeys.size

@@ -4,7 +4,9 @@ places where the reference races (Q6: node 0's value word, Q7: duplicate keys) a
 import numpy as np
 import pytest
 
-from common import float_bits_equal, FLAG, LOOK_PLUS_Z, pkg, random_pose, unique_voxel_points, view_for_pose
+from common import (check_frame_outcome, float_bits_equal, FLAG, LOOK_PLUS_Z, pkg, random_pose, unique_voxel_points,
+                    view_for_pose)
+from oracle import oracle as orc
 from oracle import ref as R
 
 pytestmark = [pytest.mark.gpu,
@@ -56,28 +58,30 @@ def test_deep_trees_match_patched_reference(P, D):
 
 
 def test_depth_frames_structure_matches_reference(P):
-    """Real frames have duplicate keys (Q7): node INDICES / child pointers must still match exactly; value words of
-    leaves hit by one pixel only are identical, the rest is one of the racing duplicates."""
+    """Real frames have duplicate keys (Q7, svo.cu:366-381): node INDICES / child pointers must match exactly, and
+    EVERY leaf is checked against its legal outcomes after every frame -- ours must be the blend of the lowest input
+    index that maps to the leaf (alpha += 2 once), the reference's must be reachable by m >= 1 successive blends of
+    inputs of that leaf (alpha += 2m); inner nodes are averageChildren of their tiles on both sides."""
     D, w, h = 8, 320, 240
     center, half = P.synth.tree_params(D)
     fx, fy = P.synth.focal(w, h)
     svo = P.SVO(center, half, D)
     ref = R.RefSVO(center, half, D)
+    a0 = b0 = np.zeros(0, dtype=np.uint32)
     for k in range(3):
         pose = P.synth.orbit_pose(30 * k)
         depth, rgb = P.synth.make_frame(w, h, pose, seed=k)
+        keys = orc.compute_keys(orc.transform(orc.vertex_map(depth, fx, fy), pose), center, half, D)
         svo.integrate_depth(depth, rgb, fx, fy, pose)
         ref.integrate_depth(depth, rgb, fx, fy, pose)
         assert svo.size == ref.size
-    a, b = svo.pool(), ref.pool()
-    assert np.array_equal(a[0::2], b[0::2]), "child pointers / node indices differ"
-    # alpha: ours is the canonical (minimum legal) outcome -- exactly one +2 per observed leaf per frame; the
-    # reference adds 2 once per duplicate whose read-modify-write did not overlap another one (Q7), so it is >= ours
-    da = (a[1::2] >> 24).astype(int) - (b[1::2] >> 24).astype(int)
-    assert np.all(da <= 0)
-    assert np.mean(da == 0) > 0.9
-    same = np.mean(a[1::2] == b[1::2])
-    assert same > 0.5, same
+        a, b = svo.pool(), ref.pool()
+        assert np.array_equal(a[0::2], b[0::2]), "child pointers / node indices differ"
+        n = check_frame_outcome(a0, a, keys, rgb, D, canonical=True)
+        assert check_frame_outcome(b0, b, keys, rgb, D, canonical=False) == n
+        # alpha: ours is the canonical (minimum legal) outcome
+        assert np.all((a[1::2] >> 24) <= (b[1::2] >> 24))
+        a0, b0 = a, b
 
 
 def test_vertex_map_matches_reference(P):

@@ -21,19 +21,23 @@ def test_host_library_exports_the_reference_interface():
     pkg()  # build() has produced the libraries
     assert os.path.exists(HOST_LIB) and os.path.exists(HOST_MAIN)
     syms = subprocess.check_output(["nm", "-D", "--demangle", "--defined-only", HOST_LIB], text=True)
-    for name in ["octree_slam::svo::svoFromPointCloud(", "octree_slam::svo::svoFromVoxelGrid(",
-                 "octree_slam::svo::extractVoxelGridFromSVO(", "octree_slam::rendering::coneTraceSVO(",
-                 "octree_slam::sensor::generateVertexMap(", "octree_slam::sensor::transformVertexMap(",
-                 "octree_slam::sensor::computePointCloudBoundingBox(", "octree_slam::world::Octree::addCloud(",
+    # the seam functions have C linkage INSIDE their namespaces, exactly like the reference's declarations
+    # (svo.h:14-18, cone_tracing_kernels.h:16, image_kernels.h:21-55, localization_kernels.h:36-42,
+    # voxelization.h:21): unmangled symbols, so objects compiled against the reference's headers link here
+    plain = set(subprocess.check_output(["nm", "-D", "--defined-only", HOST_LIB], text=True).split())
+    for name in ["svoFromPointCloud", "svoFromVoxelGrid", "extractVoxelGridFromSVO", "coneTraceSVO",
+                 "generateVertexMap", "transformVertexMap", "computePointCloudBoundingBox", "generateNormalMap",
+                 "bilateralFilter", "colorToIntensity", "transformNormalMap", "computeICPCost2", "computeICPCost",
+                 "computeRGBDCost", "meshToVoxelGrid"]:
+        assert name in plain, "libosl_host.so does not define the C-linkage symbol %s" % name
+    for name in ["octree_slam::world::Octree::addCloud(",
                  "octree_slam::world::Octree::addVoxelGrid(", "octree_slam::world::Octree::extractVoxelGrid(",
                  "octree_slam::world::Octree::extractSVO(", "octree_slam::world::Scene::addPointCloudToOctree(",
                  "octree_slam::world::Scene::extractVoxelGridFromOctree(",
                  "octree_slam::rendering::CUDARenderer::coneTraceSVO(",
-                 "octree_slam::world::Octree::expandBySize(",
-                 "octree_slam::sensor::bilateralFilter(", "octree_slam::sensor::generateNormalMap(",
-                 "octree_slam::sensor::transformNormalMap(", "octree_slam::sensor::colorToIntensity(",
+                 "octree_slam::world::Octree::expandBySize(", "BoundingBox::contains(", "BoundingBox::distanceOutside(",
                  "void octree_slam::sensor::subsampleDepth<unsigned short>(", "void octree_slam::sensor::subsample<float>(",
-                 "octree_slam::sensor::computeICPCost2(", "octree_slam::sensor::ICPFrame::ICPFrame(",
+                 "octree_slam::sensor::ICPFrame::ICPFrame(",
                  "octree_slam::sensor::RGBDCamera::update(", "octree_slam::sensor::RGBDCamera::position(",
                  "octree_slam::sensor::RGBDCamera::orientation(", "octree_slam::sensor::RGBDCamera::camera("]:
         assert name in syms, "libosl_host.so does not define %s" % name
@@ -60,6 +64,71 @@ def test_shim_builds_against_the_reference_glm(tmp_path):
     assert "octree_slam::sensor::RGBDCamera::update(" in syms and "octree_slam::world::Octree::addCloud(" in syms
     subprocess.check_call(["g++", "-std=c++14", "-w", "-fsyntax-only"] + inc + [os.path.join(host, "osl_main.cpp")],
                           stderr=subprocess.DEVNULL)
+
+
+DROPIN = os.path.join(ROOT, "oracle", "_ref", "ref_octree_dropin")
+
+
+@pytest.mark.skipif(not os.path.isfile("/root/reference/src/world/octree.cpp"),
+                    reason="the reference tree is not mounted here")
+def test_reference_octree_cpp_links_against_the_shim():
+    """Link-level drop-in: the reference's OWN src/world/octree.cpp, compiled against the
+    reference's OWN headers and glm, links against libosl_host.so -- its undefined seam symbols are the unmangled names
+    of svo.h:14-18 and libosl_host.so defines exactly those."""
+    pkg()
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "dropin"])
+    obj = os.path.join(ROOT, "oracle", "_ref", "obj", "ref_octree.o")
+    undefined = set(subprocess.check_output(["nm", "-u", obj], text=True).split())
+    defined = set(subprocess.check_output(["nm", "-D", "--defined-only", HOST_LIB], text=True).split())
+    for name in ("svoFromPointCloud", "svoFromVoxelGrid", "extractVoxelGridFromSVO"):
+        assert name in undefined and name in defined
+    needed = subprocess.check_output(["readelf", "-d", DROPIN], text=True)
+    assert "libosl_host.so" in needed  # (which in turn needs libosl_b200.so, checked above)
+    # nothing of the reference's device code is in the binary: the only CUDA it can reach is ours
+    syms = subprocess.check_output(["nm", "--demangle", DROPIN], text=True)
+    assert "splitNodes" not in syms and "coneTrace(" not in syms and "fillNodes" not in syms
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.isfile(DROPIN), reason="oracle/_ref/ref_octree_dropin not built (needs /root/reference)")
+def test_reference_octree_class_runs_on_our_library(tmp_path):
+    """The reference's own world::Octree (its octree.cpp object) drives our library through the unmangled seam:
+    addCloud x 2 -> extractSVO -> coneTraceSVO -> extractVoxelGrid; pool, image and voxels equal the oracle's."""
+    P = pkg()
+    rng = np.random.default_rng(77)
+    D, w, h = 7, 96, 72
+    center, half = (0.0, 0.0, 0.0), P.synth.tree_params(D)[1]
+    pts = rng.uniform(-0.9 * half, 0.9 * half, size=(20000, 3)).astype(np.float32)
+    pts[::50] = np.float32(np.inf)  # invalid points (svo.cu:38)
+    rgb = rng.integers(0, 256, size=(pts.shape[0], 3)).astype(np.uint8)
+    view = LOOK_PLUS_Z
+    src, dst = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    with open(src, "wb") as f:
+        f.write(struct.pack("<iii", pts.shape[0], w, h))
+        f.write(struct.pack("<3f", *center))
+        f.write(struct.pack("<fff", half, 0.01, 45.0))
+        f.write(np.ascontiguousarray(view.T, dtype=np.float32).tobytes())  # column-major
+        f.write(pts.tobytes())
+        f.write(rgb.tobytes())
+    out = subprocess.run([DROPIN, src, dst], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    raw = open(dst, "rb").read()
+    n_nodes = struct.unpack_from("<i", raw, 0)[0]
+    pool = np.frombuffer(raw, dtype=np.uint32, count=2 * n_nodes, offset=4)
+    off = 4 + 8 * n_nodes
+    img = np.frombuffer(raw, dtype=np.uint8, count=w * h * 4, offset=off).reshape(h, w, 4)
+    off += w * h * 4
+    n_vox = struct.unpack_from("<i", raw, off)[0]
+    cen = np.frombuffer(raw, dtype=np.float32, count=4 * n_vox, offset=off + 4).reshape(n_vox, 4)
+    col = np.frombuffer(raw, dtype=np.float32, count=4 * n_vox, offset=off + 4 + 16 * n_vox).reshape(n_vox, 4)
+    ref = orc.OracleSVO(center, half, D)   # Octree::addCloud derives max_depth = 7 from size / resolution (octree.cpp:284)
+    ref.integrate_points(pts, rgb)
+    ref.integrate_points(pts, rgb)
+    assert n_nodes == ref.size
+    assert np.array_equal(pool, ref.pool())
+    assert np.array_equal(img, ref.raycast(w, h, 45.0, view))
+    rc, rk, _ = ref.extract_voxels(D)
+    assert n_vox == rc.shape[0] and np.array_equal(cen, rc) and np.array_equal(col, rk)
 
 
 def _write_frames(path, w, h, frames, fx, fy):
