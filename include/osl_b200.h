@@ -86,13 +86,18 @@ osl_status osl_svo_reset(osl_svo* t);
 osl_status osl_svo_expand(osl_svo* t, int layers);
 int osl_svo_max_depth(const osl_svo* t);
 /* bit 0: 1 (default) reproduces reference quirk Q3 (svo.cu:123 `while (r_key >= 15)`); 0 = leaves are never split.
- * bit 1 (testing aid): always sort with the cooperative grid radix sort, never with the splitter-based bucket sort. */
+ * bit 1 (testing aid): always sort with the cooperative grid radix sort, never with the splitter-based bucket sort.
+ * bit 2 (measurement aid): osl_integrate_depth_host stages pinned colour planes too instead of reading them in place. */
 osl_status osl_svo_set_quirks(osl_svo* t, int ref_quirks);
 
 /* Pipelined mode for DEVICE-resident inputs (default 0).  With 1 the caller promises that the input buffers of every
  * osl_integrate_* call are complete when the call is made (not merely stream-ordered before it); the library then runs
  * back-projection + key sort of frame f+1 on an internal stream, overlapped with the tree update of frame f on the
- * caller's stream.  Results are identical.  osl_integrate_depth_host always pipelines (it owns the copies). */
+ * caller's stream.  Results are identical.  osl_integrate_depth_host always pipelines (it owns the copies).
+ * Readers and writers of the pool are ordered in BOTH directions: the library's raycast / extraction / download / view
+ * entry points wait for the frames enqueued before them (osl_svo_join), and every later frame's pool-writing stages
+ * wait for the raycasts enqueued before it -- integrate(f); raycast(stream R); integrate(f+1) renders the map after
+ * frame f, whole.  Foreign readers: see osl_svo_join. */
 osl_status osl_svo_set_pipeline(osl_svo* t, int enabled);
 
 /* Profiling aid: time k_emit / k_sort / k_structure / k_levels of every NON-pipelined integrate call with CUDA events
@@ -116,8 +121,10 @@ osl_status osl_integrate_depth_posed(osl_svo* t, const uint16_t* d_depth, const 
                                      float fy, const float* d_pose_colmajor, void* stream);
 /* Same from host buffers (what OpenNIDevice::readFrame + mainLoop do, openni_device.cpp:122,144).  The H2D copies run
  * on an internal copy stream into rotating device slots so the transfer of frame f+1 overlaps the kernels of frame f;
- * the call returns without waiting for the device.  Pinned source buffers must stay untouched until the frame has
- * completed (osl_svo_sync). */
+ * the call returns without waiting for the device.  Only the DEPTH plane is copied when the colour plane is pinned
+ * host memory: the device needs one colour per observed leaf (~5 % of the pixels) and reads those in place (zero-copy
+ * loads under UVA); a pageable colour plane is staged like the depth.  Pinned source buffers must stay untouched
+ * until the frame has completed (osl_svo_sync). */
 osl_status osl_integrate_depth_host(osl_svo* t, const uint16_t* h_depth, const uint8_t* h_rgb, int w, int h, float fx,
                                     float fy, const float pose[16], void* stream);
 /* Replaces svoFromPointCloud (svo.h:16, svo.cu:642): d_xyz = n glm::vec3 (12-byte stride), d_rgb = n Color256. */
@@ -128,7 +135,10 @@ osl_status osl_integrate_voxels(osl_svo* t, const float* d_centers4, const float
 /* Order `stream` after every integrate enqueued so far (device-side wait, the host does not block).  Strict-mode
  * frames are stream-ordered anyway; pipelined frames finish on an internal stream, and this library's own entry
  * points (raycast, extraction, download, view) join automatically -- call this before FOREIGN work on `stream` that
- * reads the pool, or before recording a timing event. */
+ * reads the pool, or before recording a timing event.  The reverse edge is taken care of as well: whatever is queued on
+ * `stream` up to the NEXT osl_integrate_* call on this tree is treated as a reader of the pool, and that frame's
+ * pool-writing stages wait for it (`stream` must still exist then).  Foreign readers on other streams, or queued later,
+ * are the caller's to order (join again). */
 osl_status osl_svo_join(osl_svo* t, void* stream);
 
 /* Wait for every integrate enqueued so far; returns a deferred error (e.g. OSL_ERR_POOL_OVERFLOW) if one occurred. */

@@ -45,6 +45,18 @@ __global__ void k_expand_root(u32* __restrict__ pool, int size) {
   }
 }
 
+// Structural check of an uploaded pool (osl_svo_upload / osl_svo_load): every child pointer must name an 8-aligned
+// tile inside the pool and beyond the root tile, or raycast / extraction / k_structure would read out of bounds.
+__global__ void k_validate_pool(const u32* __restrict__ pool, int n, int* bad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const u32 w0 = pool[2 * (size_t)i];
+  if (w0 & OSL_FLAG) {
+    const u32 c = w0 & OSL_MASK;
+    if ((c & 7u) || c < 8u || (unsigned long long)c + 8ull > (unsigned long long)n) atomicAdd(bad, 1);
+  }
+}
+
 extern "C" {
 
 const char* osl_version(void) { return "osl_b200 0.6 (sm_100a)"; }
@@ -154,6 +166,7 @@ void osl_svo_destroy(osl_svo* t) {
     if (t->stage_ev[i]) cudaEventDestroy(t->stage_ev[i]);
   if (t->pose_ev) cudaEventDestroy(t->pose_ev);
   if (t->pose_read_ev) cudaEventDestroy(t->pose_read_ev);
+  if (t->reader_ev) cudaEventDestroy(t->reader_ev);
   if (t->copy_stream) cudaStreamDestroy(t->copy_stream);
   if (t->h_ring) cudaFreeHost(t->h_ring);
   delete t;
@@ -231,6 +244,7 @@ osl_status osl_svo_set_quirks(osl_svo* t, int ref_quirks) {
   if (!t) return OSL_ERR_INVALID;
   t->tp.quirks = (ref_quirks & 1) ? 1 : 0;
   t->force_grid_sort = (ref_quirks & 2) ? 1 : 0;  // bit 1 (testing): never use the bucket sort
+  t->no_zero_copy = (ref_quirks & 4) ? 1 : 0;     // bit 2 (measurement): always stage host colour planes
   return OSL_OK;
 }
 
@@ -294,11 +308,27 @@ osl_status osl_integrate_depth_host(osl_svo* t, const uint16_t* h_depth, const u
   const int slot = (int)(t->stage_seq % OSL_STAGES);
   if (t->stage_seq >= OSL_STAGES) OSL_CUDA(cudaStreamWaitEvent(t->copy_stream, t->stage_free[slot], 0));
   OSL_CUDA(cudaMemcpyAsync(t->d_depth_stage[slot], h_depth, n * 2, cudaMemcpyHostToDevice, t->copy_stream));
-  OSL_CUDA(cudaMemcpyAsync(t->d_rgb_stage[slot], h_rgb, n * 3, cudaMemcpyHostToDevice, t->copy_stream));
+  // Colours: the device reads ONE pixel per observed leaf (the lowest pixel index that maps to it, ~5 % of the frame)
+  // and it knows which only after the sort.  When the caller's colour plane is pinned (cudaHostAlloc /
+  // cudaHostRegister: device-addressable under UVA) it is therefore not copied at all: k_levels gathers the winners'
+  // 3 bytes straight from host memory (zero-copy loads over PCIe, one 32-byte sector each), which takes 60 % of the
+  // frame's bytes off the link.  Pageable colour planes are staged through the copy stream as before.
+  const uint8_t* rgb_dev = nullptr;
+  if (!t->no_zero_copy) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, h_rgb) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
+      rgb_dev = static_cast<const uint8_t*>(attr.devicePointer);
+    else
+      cudaGetLastError();  // (pageable memory is reported as an error by older drivers)
+  }
+  if (!rgb_dev) {
+    OSL_CUDA(cudaMemcpyAsync(t->d_rgb_stage[slot], h_rgb, n * 3, cudaMemcpyHostToDevice, t->copy_stream));
+    rgb_dev = t->d_rgb_stage[slot];
+  }
   OSL_CUDA(cudaEventRecord(t->stage_copied[slot], t->copy_stream));  // k_emit (stream E) waits for it
   EmitParams ep;
   memset(&ep, 0, sizeof(ep));
-  ep.depth = t->d_depth_stage[slot]; ep.rgb = t->d_rgb_stage[slot]; ep.w = w; ep.h = h; ep.fx = fx; ep.fy = fy;
+  ep.depth = t->d_depth_stage[slot]; ep.rgb = rgb_dev; ep.w = w; ep.h = h; ep.fx = fx; ep.fy = fy;
   memcpy(ep.M, pose, sizeof(ep.M));
   ep.n = w * h; ep.mode = 0;
   rc = osl_run_integrate(t, ep, nullptr, st, true);  // always pipelined: the library owns the copies
@@ -329,7 +359,9 @@ osl_status osl_integrate_voxels(osl_svo* t, const float* d_centers4, const float
 osl_status osl_svo_join(osl_svo* t, void* stream) {
   if (!t) return OSL_ERR_INVALID;
   OSL_CUDA(cudaSetDevice(t->device));
-  return osl_join(t, (cudaStream_t)stream);
+  osl_status rc = osl_join(t, (cudaStream_t)stream);
+  if (rc) return rc;
+  return osl_note_foreign_reader(t, (cudaStream_t)stream);  // foreign readers on `stream` finish before later frames write
 }
 
 osl_status osl_svo_sync(osl_svo* t) {
@@ -380,7 +412,22 @@ osl_status osl_svo_upload(osl_svo* t, const uint32_t* h_pool, int n_nodes) {
   t->size = 0;
   osl_status rc = osl_grow_pool(t, (size_t)(n_nodes > 8 ? n_nodes : 8), 0);
   if (rc) return rc;
-  if (n_nodes > 0) OSL_CUDA(cudaMemcpy(t->d_pool, h_pool, (size_t)n_nodes * 8, cudaMemcpyHostToDevice));
+  if (n_nodes > 0) {
+    if (n_nodes < 8 || (n_nodes & 7)) return OSL_ERR_INVALID;  // whole 8-node tiles, the root's first
+    OSL_CUDA(cudaMemcpy(t->d_pool, h_pool, (size_t)n_nodes * 8, cudaMemcpyHostToDevice));
+    int* d_bad = reinterpret_cast<int*>(t->d_scan_totals + OSL_NCOUNT(OSL_MAXD) + 1);  // scratch word, zero at rest
+    int bad = 0;
+    k_validate_pool<<<(n_nodes + 255) / 256, 256>>>(t->d_pool, n_nodes, d_bad);
+    g_osl_launches++;
+    OSL_CUDA(cudaMemcpy(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost));
+    if (bad) {  // corrupt child pointers: leave an empty, valid tree behind
+      OSL_CUDA(cudaMemset(d_bad, 0, sizeof(int)));
+      OSL_CUDA(cudaMemset(t->d_pool, 0, (size_t)n_nodes * 8));
+      t->upload_count++;
+      set_device_size(t, 0);
+      return OSL_ERR_INVALID;
+    }
+  }
   t->sticky_error = OSL_OK;
   t->upload_count++;  // invalidates the cached extraction frontier
   return set_device_size(t, n_nodes);
@@ -435,6 +482,14 @@ osl_status osl_svo_load(osl_svo* t, const char* path) {
       h.center[0] != t->tp.cx || h.center[1] != t->tp.cy || h.center[2] != t->tp.cz || h.half_edge != t->tp.half) {
     fclose(f);
     return OSL_ERR_INVALID;
+  }
+  {  // the header must agree with the file before anything is allocated from it
+    long here = ftell(f), end = -1;
+    if (here >= 0 && fseek(f, 0, SEEK_END) == 0) end = ftell(f);
+    if (here < 0 || end < 0 || fseek(f, here, SEEK_SET) != 0 || (long long)(end - here) != 8ll * h.n_nodes) {
+      fclose(f);
+      return OSL_ERR_INVALID;
+    }
   }
   uint32_t* buf = (uint32_t*)malloc((size_t)(h.n_nodes > 0 ? h.n_nodes : 1) * 8);
   if (!buf) { fclose(f); return OSL_ERR_OOM; }
@@ -496,8 +551,10 @@ osl_status osl_raycast_rows(const osl_svo* t, uint8_t* d_out_rgba, int w, int h,
   const float c[3] = {t->tp.cx, t->tp.cy, t->tp.cz};
   osl_status jr = osl_join(const_cast<osl_svo*>(t), (cudaStream_t)stream);
   if (jr) return jr;
-  return raycast_rows_pool(t->d_pool, c, t->tp.half, d_out_rgba, w, h, row0, rows, rows > 0 ? rows : 1, 1, fov_deg,
-                           view, prm, h_stats, stream);
+  jr = raycast_rows_pool(t->d_pool, c, t->tp.half, d_out_rgba, w, h, row0, rows, rows > 0 ? rows : 1, 1, fov_deg,
+                         view, prm, h_stats, stream);
+  if (jr) return jr;
+  return osl_note_reader(const_cast<osl_svo*>(t), (cudaStream_t)stream);
 }
 
 // All rows one rank owns under the interleaved-band decomposition, in ONE launch: bands of band_h rows are dealt
@@ -515,8 +572,10 @@ osl_status osl_raycast_bands(const osl_svo* t, uint8_t* d_out_rgba, int w, int h
   const float c[3] = {t->tp.cx, t->tp.cy, t->tp.cz};
   osl_status jr = osl_join(const_cast<osl_svo*>(t), (cudaStream_t)stream);
   if (jr) return jr;
-  return raycast_rows_pool(t->d_pool, c, t->tp.half, d_out_rgba, w, h, rank * band_h, rows, band_h, n_ranks, fov_deg,
-                           view, prm, nullptr, stream);
+  jr = raycast_rows_pool(t->d_pool, c, t->tp.half, d_out_rgba, w, h, rank * band_h, rows, band_h, n_ranks, fov_deg,
+                         view, prm, nullptr, stream);
+  if (jr) return jr;
+  return osl_note_reader(const_cast<osl_svo*>(t), (cudaStream_t)stream);
 }
 
 // Stream-ordered after the integrates enqueued on the same stream (no host synchronisation needed).
@@ -527,7 +586,9 @@ osl_status osl_raycast(const osl_svo* t, uint8_t* d_out_rgba, int w, int h, floa
   const float c[3] = {t->tp.cx, t->tp.cy, t->tp.cz};
   osl_status jr = osl_join(const_cast<osl_svo*>(t), (cudaStream_t)stream);
   if (jr) return jr;
-  return osl_raycast_pool(t->d_pool, c, t->tp.half, d_out_rgba, w, h, fov_deg, view, prm, nullptr, stream);
+  jr = osl_raycast_pool(t->d_pool, c, t->tp.half, d_out_rgba, w, h, fov_deg, view, prm, nullptr, stream);
+  if (jr) return jr;
+  return osl_note_reader(const_cast<osl_svo*>(t), (cudaStream_t)stream);
 }
 
 osl_status osl_raycast_host(const osl_svo* t, uint8_t* h_out_rgba, int w, int h, float fov_deg, const float view[16],

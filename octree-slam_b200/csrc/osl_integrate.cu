@@ -1000,7 +1000,8 @@ k_structure(const u64* __restrict__ keys_sorted, const u64* __restrict__ keys_de
 #define LEVEL_SMEM (LEVEL_STAGE * (32 + 4 + 4 + 2 + 2) + 64)
 
 __device__ __forceinline__ void level_leaf(u32* pool, const LevelArrays& lv, int D, int idx, int mode,
-                                           const uint8_t* __restrict__ rgb, const float* __restrict__ colors4) {
+                                           const uint8_t* __restrict__ rgb, const float* __restrict__ colors4,
+                                           size_t rgb_bytes) {
   const size_t oD = lv.off[D];
   const u32 src = __ldg(&lv.src[idx]);
   const u32 node = __ldg(&lv.self[oD + idx]);
@@ -1011,8 +1012,22 @@ __device__ __forceinline__ void level_leaf(u32* pool, const LevelArrays& lv, int
     const float4 col = __ldg(reinterpret_cast<const float4*>(colors4) + src);
     nv = osl_blend_f4(cur, col.x, col.y, col.z);
   } else {
-    const uint8_t* q = rgb + 3 * (size_t)src;
-    nv = osl_blend_u8(cur, __ldg(q), __ldg(q + 1), __ldg(q + 2));
+    // the winner's 3 colour bytes: one or two aligned 32-bit loads (the plane may live in pinned HOST memory, where
+    // every load is a PCIe read -- osl_integrate_depth_host)
+    const size_t off = 3 * (size_t)src;
+    u32 r8, g8, b8;
+    if ((reinterpret_cast<uintptr_t>(rgb) & 3) == 0 && (off & ~(size_t)3) + 8 <= rgb_bytes) {
+      const u32* wp = reinterpret_cast<const u32*>(rgb + (off & ~(size_t)3));
+      const int sh = 8 * (int)(off & 3);
+      unsigned long long v = __ldg(wp);
+      if (sh > 8) v |= (unsigned long long)__ldg(wp + 1) << 32;
+      v >>= sh;
+      r8 = (u32)v & 0xFFu; g8 = (u32)(v >> 8) & 0xFFu; b8 = (u32)(v >> 16) & 0xFFu;
+    } else {
+      const uint8_t* q = rgb + off;
+      r8 = __ldg(q); g8 = __ldg(q + 1); b8 = __ldg(q + 2);
+    }
+    nv = osl_blend_u8(cur, r8, g8, b8);
   }
   w[1] = nv;
 }
@@ -1038,12 +1053,12 @@ k_levels(u32* pool, LevelArrays lv, const FrameState* fr, u32* done, int D, int 
   extern __shared__ __align__(16) unsigned char s_raw[];
   __shared__ int s_nl[OSL_MAXD + 2];   // n_level[d]
   __shared__ int s_pre[OSL_MAXD + 2];  // s_pre[d] = sum of n_level[1..d-1]
-  __shared__ int s_overflow;
+  __shared__ int s_overflow, s_nin;
   const int tid = threadIdx.x;
   const int gtid = blockIdx.x * LEVEL_THREADS + tid, gsz = gridDim.x * LEVEL_THREADS;
   // the frame's level counts: one parallel round trip, then a prefix over <= 20 values
   if (tid <= D && tid >= 1) s_nl[tid] = fr->n_level[tid];
-  if (tid == 0) s_overflow = fr->overflow;
+  if (tid == 0) { s_overflow = fr->overflow; s_nin = fr->n_in; }
   __syncthreads();
   if (s_overflow) return;
   if (tid == 0) {
@@ -1058,7 +1073,8 @@ k_levels(u32* pool, LevelArrays lv, const FrameState* fr, u32* done, int D, int 
   // phase 1: leaves
   {
     const int n_D = s_nl[D];
-    for (int idx = gtid; idx < n_D; idx += gsz) level_leaf(pool, lv, D, idx, mode, rgb, colors4);
+    const size_t rgb_bytes = 3 * (size_t)s_nin;
+    for (int idx = gtid; idx < n_D; idx += gsz) level_leaf(pool, lv, D, idx, mode, rgb, colors4, rgb_bytes);
   }
   PROF(35);
 
@@ -1373,6 +1389,8 @@ int g_osl_piped_trees = 0;  // trees of this process that have used pipelined mo
 // entry points call it; foreign work calls osl_svo_join).  Cooperative grids are capped at num_sms/3 CTAs in this mode (num_sms/(3*T) when T trees of the
 // process pipeline): at most three cooperative kernels per tree (grid sort, k_structure, k_levels) run concurrently,
 // <= num_sms CTAs in total, so a waiting CTA always finds an empty SM and no grid barrier can deadlock.
+static osl_status osl_order_after_readers(osl_svo* t, cudaStream_t st, bool piped, cudaStream_t sS, cudaStream_t sV);
+
 osl_status osl_run_integrate(osl_svo* t, EmitParams& ep, const void* colors, cudaStream_t st, bool inputs_on_front) {
   const int n = ep.n;
   const int D = t->tp.D;
@@ -1518,6 +1536,11 @@ osl_status osl_run_integrate(osl_svo* t, EmitParams& ep, const void* colors, cud
     }
   }
   // ---- S: structure plan + child pointers
+  {  // readers of the pool queued before this call (raycasts, foreign work on joined streams) finish first: the
+     // structure stage rewrites word0 / new tiles, the value stage rewrites word1
+    osl_status rr = osl_order_after_readers(t, st, piped, sS, sV);
+    if (rr) return rr;
+  }
   if (piped && f >= OSL_BACK)  // level lists + result block of this slot were last read by k_levels of frame f - 2
     OSL_CUDA(cudaStreamWaitEvent(sS, t->ring_ev[(f - OSL_BACK) % OSL_RING], 0));
   {
@@ -1566,6 +1589,47 @@ osl_status osl_run_integrate(osl_svo* t, EmitParams& ep, const void* colors, cud
   t->seq++;
   t->last_stream = st;
   t->last_piped = piped ? 1 : 0;
+  return OSL_OK;
+}
+
+// The pool's readers.  osl_note_reader: called by the library's own asynchronous readers right after they enqueue
+// their kernel on `st`.  osl_note_foreign_reader: `st` was handed to osl_svo_join, so foreign work that reads the pool
+// may be queued on it until the next integrate call; the event is recorded then.
+osl_status osl_note_reader(osl_svo* t, cudaStream_t st) {
+  if (!t->reader_ev) OSL_CUDA(cudaEventCreateWithFlags(&t->reader_ev, cudaEventDisableTiming));
+  if (t->reader_pending) OSL_CUDA(cudaStreamWaitEvent(st, t->reader_ev, 0));  // keep earlier readers covered
+  OSL_CUDA(cudaEventRecord(t->reader_ev, st));
+  t->reader_pending = 1;
+  return OSL_OK;
+}
+
+osl_status osl_note_foreign_reader(osl_svo* t, cudaStream_t st) {
+  for (int i = 0; i < t->foreign_n; i++)
+    if (t->foreign_reader[i] == st) return OSL_OK;
+  if (t->foreign_n == 8) {  // table full: cover what the oldest stream carries so far
+    osl_status rc = osl_note_reader(t, t->foreign_reader[0]);
+    if (rc) return rc;
+    for (int i = 1; i < 8; i++) t->foreign_reader[i - 1] = t->foreign_reader[i];
+    t->foreign_n = 7;
+  }
+  t->foreign_reader[t->foreign_n++] = st;
+  return OSL_OK;
+}
+
+// Called when a frame is enqueued: its pool-writing stages (streams sS, sV) wait for every reader noted so far.
+// Strict-mode frames on the stream the readers ran on are ordered already.
+static osl_status osl_order_after_readers(osl_svo* t, cudaStream_t st, bool piped, cudaStream_t sS, cudaStream_t sV) {
+  for (int i = 0; i < t->foreign_n; i++) {
+    if (!piped && t->foreign_reader[i] == st) continue;
+    osl_status rc = osl_note_reader(t, t->foreign_reader[i]);
+    if (rc) return rc;
+  }
+  t->foreign_n = 0;
+  if (t->reader_pending) {
+    OSL_CUDA(cudaStreamWaitEvent(sS, t->reader_ev, 0));
+    if (sV != sS) OSL_CUDA(cudaStreamWaitEvent(sV, t->reader_ev, 0));
+    t->reader_pending = 0;
+  }
   return OSL_OK;
 }
 

@@ -162,6 +162,7 @@ struct osl_svo {
   u64* d_keysC; u32* d_payC;   // k_sort_bucket slow-path scratch
   u64* d_split;                // [OSL_FRONT][BK_BUCKETS] splitters written by k_structure of frame f (set f % OSL_FRONT)
   int force_grid_sort;         // testing: always use the cooperative grid sort
+  int no_zero_copy;            // measurement: osl_integrate_depth_host always copies the colour plane
   uint8_t *d_m, *d_s;
   u32* d_start;       // per sorted key: node at the first depth it heads (k_structure phase A -> C)
   u32* d_flags;       // per virtual block: epoch of the frame whose count vector is published
@@ -186,6 +187,12 @@ struct osl_svo {
   int last_piped;
   int counted_piped;                     // this tree is counted in g_osl_piped_trees
   int join_pending;                      // pipelined frames are in flight that other streams have not been ordered after
+  // readers -> writers: work that READS the pool (the library's raycasts; foreign work on a stream handed to
+  // osl_svo_join) must finish before a later frame rewrites it.  reader_ev fires after every reader noted so far
+  // (each new reader's stream first waits for the previous state of the event, then re-records it); streams joined
+  // by osl_svo_join are recorded lazily, when the next integrate is enqueued (osl_order_after_readers).
+  cudaEvent_t reader_ev; int reader_pending;
+  cudaStream_t foreign_reader[8]; int foreign_n;
   int stage_timing, stage_valid;         // per-kernel CUDA-event timing of non-pipelined frames (bench / profiling)
   cudaEvent_t stage_ev[5];
   int pipeline;                          // 1: emit+sort run on the front stream (inputs are ready at call time)
@@ -235,6 +242,8 @@ osl_status osl_grow_pool(osl_svo* t, size_t want_nodes, cudaStream_t st);
 osl_status osl_reset_splitters(osl_svo* t);
 void osl_drop_workspace(osl_svo* t);
 osl_status osl_join(osl_svo* t, cudaStream_t st);
+osl_status osl_note_reader(osl_svo* t, cudaStream_t st);      // after enqueuing work on `st` that reads the pool
+osl_status osl_note_foreign_reader(osl_svo* t, cudaStream_t st);  // `st` may carry foreign readers until the next integrate
 osl_status osl_device_sort_pairs(u64* kA, u32* pA, u64* kB, u32* pB, int n, int key_bits, cudaStream_t st, int* in_B);
 
 // raycast / extraction / image kernels

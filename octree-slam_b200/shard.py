@@ -79,15 +79,21 @@ def replicate_tree(svo, src=0, group=None, device=None):
     return words // 2
 
 
-def gather_image(bands, tiles, h, w, dst=0, group=None):
-    """bands: this rank's [(row0, rows)], tiles: matching list of uint8 tensors [rows, w, 4].  Returns the h x w x 4
-    image on rank `dst` (None elsewhere)."""
+def gather_image(bands, tiles, h, w, dst=0, group=None, band=None):
+    """bands: this rank's [(row0, rows)], tiles: matching list of uint8 tensors [rows, w, 4]; `band` = the band height
+    EVERY rank used with row_bands (None = row_bands' default).  It is passed explicitly, never inferred from the local
+    bands: a rank that owns 0 or 1 bands cannot tell, and mismatched layouts hang the all-gather.  Returns the
+    h x w x 4 image on rank `dst` (None elsewhere)."""
     import torch
     dist = _dist()
     world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if band is None:
+        band = band_height(h, world)
+    assert [tuple(b) for b in bands] == row_bands(h, world, rank, band), "bands do not match the declared band height"
     dev = tiles[0].device if tiles else torch.device("cpu")
     mine = torch.cat([t.reshape(-1) for t in tiles]) if tiles else torch.empty(0, dtype=torch.uint8, device=dev)
-    sizes = [sum(r for _, r in row_bands_like(bands, h, world, k)) * w * 4 for k in range(world)]
+    layout = [row_bands(h, world, k, band) for k in range(world)]
+    sizes = [sum(r for _, r in layout[k]) * w * 4 for k in range(world)]
     cap = max(sizes)
     padded = torch.zeros(cap, dtype=torch.uint8, device=dev)
     padded[:mine.numel()] = mine
@@ -98,15 +104,7 @@ def gather_image(bands, tiles, h, w, dst=0, group=None):
     img = torch.empty((h, w, 4), dtype=torch.uint8, device=dev)
     for k in range(world):
         off = 0
-        for row0, rows in row_bands_like(bands, h, world, k):
+        for row0, rows in layout[k]:
             img[row0:row0 + rows] = gathered[k][off:off + rows * w * 4].reshape(rows, w, 4)
             off += rows * w * 4
     return img
-
-
-def row_bands_like(bands, h, world, rank):
-    """the band layout of `rank` given this rank's bands (all ranks use the same band height)"""
-    band = bands[0][1] if bands and len(bands) > 1 else None
-    if band is None:
-        return row_bands(h, world, rank)
-    return row_bands(h, world, rank, band)

@@ -6,6 +6,7 @@ Names, argument meaning and behaviour follow the reference classes so tests read
   rendering::coneTraceSVO (include/octree_slam/rendering/cone_tracing_kernels.h:16)
 torch is used only to hold device buffers; every computation happens in libosl_b200.so.
 """
+import collections
 import ctypes as C
 import math
 
@@ -34,7 +35,7 @@ class SVO:
     """One GPU-resident sparse voxel octree (the reference's OctreeNode::gpu_data_ / gpu_size_)."""
 
     def __init__(self, center=(0.0, 0.0, 0.0), half_edge=1.0, max_depth=8, reserve_nodes=0, device=0,
-                 quirks=True, force_grid_sort=False):
+                 quirks=True, force_grid_sort=False, zero_copy=True):
         self.center = tuple(float(c) for c in center)
         self.half_edge = float(np.float32(half_edge))
         self.max_depth = int(max_depth)
@@ -43,8 +44,13 @@ class SVO:
         _check(lib().osl_svo_create(C.byref(h), _f(self.center), self.half_edge, self.max_depth,
                                     int(reserve_nodes), device), "osl_svo_create")
         self._h = h
-        if not quirks or force_grid_sort:
-            _check(lib().osl_svo_set_quirks(self._h, int(bool(quirks)) | (2 if force_grid_sort else 0)),
+        # integrate calls are asynchronous and up to 8 frames (the library's result ring, OSL_RING) are in flight on the
+        # library's own streams: the input buffers of the last 2 * 8 calls stay referenced, so that torch's caching
+        # allocator cannot hand a block a queued kernel still reads to a later copy
+        self._keep = collections.deque(maxlen=16)
+        if not quirks or force_grid_sort or not zero_copy:
+            _check(lib().osl_svo_set_quirks(self._h, int(bool(quirks)) | (2 if force_grid_sort else 0) |
+                                            (0 if zero_copy else 4)),
                    "osl_svo_set_quirks")
 
     def set_pipeline(self, enabled=True):
@@ -81,7 +87,7 @@ class SVO:
         c = _dev(rgb, np.uint8, self.device)
         _check(lib().osl_integrate_depth(self._h, d.data_ptr(), c.data_ptr(), w, h, fx, fy,
                                          _f(mat_colmajor(pose)), stream), "osl_integrate_depth")
-        self._keep = (d, c)  # the call is asynchronous: keep the device buffers alive until the next call
+        self._keep.append((d, c))
         return self
 
     def integrate_depth_tracked(self, depth, rgb, fx, fy, camera, stream=None):
@@ -93,7 +99,7 @@ class SVO:
         _check(lib().osl_tracker_update(camera._h, d.data_ptr(), stream), "osl_tracker_update")
         _check(lib().osl_integrate_depth_posed(self._h, d.data_ptr(), c.data_ptr(), w, h, fx, fy,
                                                camera.pose_device(), stream), "osl_integrate_depth_posed")
-        self._keep = (d, c)
+        self._keep.append((d, c))
         return self
 
     def integrate_depth_host(self, depth, rgb, fx, fy, pose=IDENTITY, stream=None):
@@ -102,7 +108,7 @@ class SVO:
         h, w = depth.shape
         _check(lib().osl_integrate_depth_host(self._h, _hptr(depth), _hptr(rgb), w, h, fx, fy,
                                               _f(mat_colmajor(pose)), stream), "osl_integrate_depth_host")
-        self._keep = (depth, rgb)
+        self._keep.append((depth, rgb))
         return self
 
     def integrate_points(self, xyz, rgb, stream=None):
@@ -111,7 +117,7 @@ class SVO:
         n = p.shape[0]
         _check(lib().osl_integrate_points(self._h, p.data_ptr() if n else None, c.data_ptr() if n else None, n,
                                           stream), "osl_integrate_points")
-        self._keep = (p, c)
+        self._keep.append((p, c))
         return self
 
     def integrate_voxels(self, centers4, colors4, stream=None):
@@ -120,7 +126,7 @@ class SVO:
         n = p.shape[0]
         _check(lib().osl_integrate_voxels(self._h, p.data_ptr() if n else None, c.data_ptr() if n else None, n,
                                           stream), "osl_integrate_voxels")
-        self._keep = (p, c)
+        self._keep.append((p, c))
         return self
 
     # ---- views -----------------------------------------------------------------------------------------

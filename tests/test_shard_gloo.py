@@ -45,6 +45,13 @@ def _worker(rank, world, port, h, w, q):
         tiles = [torch.from_numpy(ref[r0:r0 + n].copy()) for r0, n in bands]
         img = S.gather_image(bands, tiles, h, w, dst=0)
         ok_img = True if rank != 0 else bool(np.array_equal(img.numpy(), ref))
+        # a non-default band height, chosen so that one rank owns a single band (or none): the layout must come from
+        # the declared height, not from what a rank can infer from its own bands
+        for bh in (h - 1, h // 2 + 1, 5):
+            b2 = S.row_bands(h, world, rank, bh)
+            t2 = [torch.from_numpy(ref[r0:r0 + n].copy()) for r0, n in b2]
+            i2 = S.gather_image(b2, t2, h, w, dst=0, band=bh)
+            ok_img = ok_img and (rank != 0 or bool(np.array_equal(i2.numpy(), ref)))
         # 2. pool replication: rank 0's tree reaches rank 1 bit for bit
         rng = np.random.default_rng(3)
         pool0 = rng.integers(0, 2 ** 32, size=2 * 1000, dtype=np.uint64).astype(np.uint32)
