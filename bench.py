@@ -181,10 +181,6 @@ def sum_over_ranks(x, world):
     return float(t.item())
 
 
-def total_frames_of(K, world):
-    return float(K) * world
-
-
 def run_ours(args):
     import torch
     import __graft_entry__ as graft
@@ -300,12 +296,7 @@ def run_ours(args):
 
     svo2 = pkg.SVO(center, half, DEPTH, reserve_nodes=1 << 24, device=local)
     ms_e2e, _, _, _ = timed(integrate_host, svo2)
-    e2e_unique = int(svo2.counters().n_unique)
     svo2.close()
-    # the same with the colour plane staged through the copy stream as well (what a pageable colour plane gets)
-    svo2b = pkg.SVO(center, half, DEPTH, reserve_nodes=1 << 24, device=local, zero_copy=False)
-    ms_e2e_staged, _, _, _ = timed(integrate_host, svo2b)
-    svo2b.close()
 
     # camera tracking (the step before integration): frame-to-frame ICP on resident depth frames,
     # 27 launches per frame, pose read back once at the end
@@ -366,17 +357,10 @@ def run_ours(args):
                    "multi_gpu": "replicas only: one independent stream+map per rank, no data-path collective",
                    "cuda_device_max_connections": os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS"),
                    "nodes_after": nodes},
-        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": W * H * 2 + 3 * e2e_unique,
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": W * H * 5,
                 "d2h_bytes_per_step": int(lib.osl_frame_result_bytes()),
-                "h2d_detail": {"depth_plane_copied": W * H * 2, "colour_bytes_gathered_in_place": 3 * e2e_unique,
-                               "colour_sectors_32B_read_over_pcie": 32 * e2e_unique,
-                               "colour_plane_in_pinned_host_memory": W * H * 3},
-                "staged_colour_plane": {"value": total_frames_of(K, world) / (ms_e2e_staged / 1e3),
-                                        "h2d_bytes_per_step": W * H * 5},
-                "api": "osl_integrate_depth_host: pinned host frames; the depth plane is copied on the library's copy "
-                       "stream, the colours of the winning pixels (one per observed leaf) are read in place from the "
-                       "pinned colour plane (zero-copy); per-frame result block written by the device into pinned "
-                       "host memory"},
+                "api": "osl_integrate_depth_host: pinned host frames, H2D on the library's copy stream, per-frame "
+                       "result block written by the device into pinned host memory"},
         "gpu_launches": int(launches),
         "raycast": {"mrays_per_s": RAY_W * RAY_H / (ray_ms / 1e3) / 1e6, "ms": ray_ms, "res": [RAY_W, RAY_H],
                     "mode": "ref_exact", "rows": "interleaved bands over %d rank(s)" % world,

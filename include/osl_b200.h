@@ -87,7 +87,8 @@ osl_status osl_svo_expand(osl_svo* t, int layers);
 int osl_svo_max_depth(const osl_svo* t);
 /* bit 0: 1 (default) reproduces reference quirk Q3 (svo.cu:123 `while (r_key >= 15)`); 0 = leaves are never split.
  * bit 1 (testing aid): always sort with the cooperative grid radix sort, never with the splitter-based bucket sort.
- * bit 2 (measurement aid): osl_integrate_depth_host stages pinned colour planes too instead of reading them in place. */
+ * bit 2 (measurement aid): osl_integrate_depth_host reads PINNED colour planes in place (zero-copy gather of the one
+ * colour per observed leaf) instead of staging them; measured slower than the DMA on B200, hence off by default. */
 osl_status osl_svo_set_quirks(osl_svo* t, int ref_quirks);
 
 /* Pipelined mode for DEVICE-resident inputs (default 0).  With 1 the caller promises that the input buffers of every
@@ -121,10 +122,8 @@ osl_status osl_integrate_depth_posed(osl_svo* t, const uint16_t* d_depth, const 
                                      float fy, const float* d_pose_colmajor, void* stream);
 /* Same from host buffers (what OpenNIDevice::readFrame + mainLoop do, openni_device.cpp:122,144).  The H2D copies run
  * on an internal copy stream into rotating device slots so the transfer of frame f+1 overlaps the kernels of frame f;
- * the call returns without waiting for the device.  Only the DEPTH plane is copied when the colour plane is pinned
- * host memory: the device needs one colour per observed leaf (~5 % of the pixels) and reads those in place (zero-copy
- * loads under UVA); a pageable colour plane is staged like the depth.  Pinned source buffers must stay untouched
- * until the frame has completed (osl_svo_sync). */
+ * the call returns without waiting for the device.  Pinned source buffers must stay untouched until the frame has
+ * completed (osl_svo_sync). */
 osl_status osl_integrate_depth_host(osl_svo* t, const uint16_t* h_depth, const uint8_t* h_rgb, int w, int h, float fx,
                                     float fy, const float pose[16], void* stream);
 /* Replaces svoFromPointCloud (svo.h:16, svo.cu:642): d_xyz = n glm::vec3 (12-byte stride), d_rgb = n Color256. */

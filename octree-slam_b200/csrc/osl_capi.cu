@@ -244,7 +244,7 @@ osl_status osl_svo_set_quirks(osl_svo* t, int ref_quirks) {
   if (!t) return OSL_ERR_INVALID;
   t->tp.quirks = (ref_quirks & 1) ? 1 : 0;
   t->force_grid_sort = (ref_quirks & 2) ? 1 : 0;  // bit 1 (testing): never use the bucket sort
-  t->no_zero_copy = (ref_quirks & 4) ? 1 : 0;     // bit 2 (measurement): always stage host colour planes
+  t->zero_copy_rgb = (ref_quirks & 4) ? 1 : 0;    // bit 2 (measurement): read pinned colour planes in place
   return OSL_OK;
 }
 
@@ -309,12 +309,13 @@ osl_status osl_integrate_depth_host(osl_svo* t, const uint16_t* h_depth, const u
   if (t->stage_seq >= OSL_STAGES) OSL_CUDA(cudaStreamWaitEvent(t->copy_stream, t->stage_free[slot], 0));
   OSL_CUDA(cudaMemcpyAsync(t->d_depth_stage[slot], h_depth, n * 2, cudaMemcpyHostToDevice, t->copy_stream));
   // Colours: the device reads ONE pixel per observed leaf (the lowest pixel index that maps to it, ~5 % of the frame)
-  // and it knows which only after the sort.  When the caller's colour plane is pinned (cudaHostAlloc /
-  // cudaHostRegister: device-addressable under UVA) it is therefore not copied at all: k_levels gathers the winners'
-  // 3 bytes straight from host memory (zero-copy loads over PCIe, one 32-byte sector each), which takes 60 % of the
-  // frame's bytes off the link.  Pageable colour planes are staged through the copy stream as before.
+  // and it knows which only after the sort.  Opt-in (osl_svo_set_quirks bit 2): a PINNED colour plane is not copied,
+  // k_levels gathers the winners' 3 bytes straight from host memory (zero-copy loads under UVA).  That takes 60 % of
+  // the frame's payload off the link, but measured on B200 / PCIe 5 it does not pay (profiles/r02_e2e_zero_copy.md):
+  // ~15 k scattered 32-byte PCIe reads per frame are bound by outstanding-request latency and stretch k_levels, so
+  // the default stages the colour plane with one DMA like the depth plane.
   const uint8_t* rgb_dev = nullptr;
-  if (!t->no_zero_copy) {
+  if (t->zero_copy_rgb) {
     cudaPointerAttributes attr;
     if (cudaPointerGetAttributes(&attr, h_rgb) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
       rgb_dev = static_cast<const uint8_t*>(attr.devicePointer);

@@ -162,7 +162,7 @@ struct osl_svo {
   u64* d_keysC; u32* d_payC;   // k_sort_bucket slow-path scratch
   u64* d_split;                // [OSL_FRONT][BK_BUCKETS] splitters written by k_structure of frame f (set f % OSL_FRONT)
   int force_grid_sort;         // testing: always use the cooperative grid sort
-  int no_zero_copy;            // measurement: osl_integrate_depth_host always copies the colour plane
+  int zero_copy_rgb;           // measurement: osl_integrate_depth_host reads pinned colour planes in place
   uint8_t *d_m, *d_s;
   u32* d_start;       // per sorted key: node at the first depth it heads (k_structure phase A -> C)
   u32* d_flags;       // per virtual block: epoch of the frame whose count vector is published

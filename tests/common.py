@@ -147,31 +147,37 @@ def check_frame_outcome(before, after, keys, rgb, D, canonical):
     group = np.cumsum(head) - 1                           # leaf group of every sorted input
     cur = bw1[leaf]
     got = aw1[leaf]
-    # leaves whose alpha may saturate under racing duplicates (boundary cells that swallow everything outside the
-    # cube): only their alpha range is checked in the non-canonical case
-    sat = (cur >> 24).astype(int) + 2 * counts > 255
+    ca, ga = (cur >> 24).astype(int), (got >> 24).astype(int)
     if canonical:
         want = blend_u8(cur, rgb[order[starts]])
         bad = np.flatnonzero(want != got)
         assert bad.size == 0, "%d leaves are not the blend of their lowest input" % bad.size
     else:
-        m = ((got >> 24).astype(int) - (cur >> 24).astype(int))
-        assert np.all(m[~sat] % 2 == 0) and np.all(m >= np.minimum(2, 255 - (cur >> 24).astype(int))) and \
-            np.all(m <= 2 * counts), "alpha outside {+2 .. +2k}"
+        # number of read-modify-writes that landed on the leaf: exact while alpha has not saturated at 255
+        sat = ga == 255
+        steps = (ga - ca) // 2
+        assert np.all((ga - ca)[~sat] % 2 == 0) and np.all(steps[~sat] >= 1) and np.all(steps <= counts), \
+            "alpha outside {+2 .. +2k}"
+        assert sat.mean() < 0.02, "too many saturated leaves for a meaningful check"
         one = blend_u8(cur[group], rgb[order]) == got[group]
         ok = np.zeros(ukeys.size, dtype=bool)
         np.logical_or.at(ok, group, one)
-        ok &= (m == 2)
-        assert sat.mean() < 0.02, "too many leaves near alpha saturation for a meaningful check"
-        for g in np.flatnonzero(~ok & ~sat):                     # serialised duplicates (rare): chains of m/2 blends
-            cols = rgb[order[starts[g]:starts[g] + counts[g]]]
-            states = {int(cur[g])}
-            for _ in range(m[g] // 2):
-                nxt = set()
-                for s in states:
-                    nxt.update(int(x) for x in blend_u8(np.full(cols.shape[0], s, dtype=np.uint32), cols))
-                states = nxt
-            assert int(got[g]) in states, "leaf %d: value %08x is no blend of its %d inputs" % (leaf[g], got[g], counts[g])
+        ok &= (steps == 1)
+        skipped = 0
+        for g in np.flatnonzero(~ok & ~sat):                  # serialised duplicates: chains of `steps` blends
+            cols = np.unique(rgb[order[starts[g]:starts[g] + counts[g]]], axis=0)
+            states = np.array([cur[g]], dtype=np.uint32)
+            for _ in range(int(steps[g])):
+                if states.size * cols.shape[0] > 2_000_000:
+                    states = None
+                    break
+                states = np.unique(blend_u8(np.repeat(states, cols.shape[0]), np.tile(cols, (states.size, 1))))
+            if states is None:
+                skipped += 1
+                continue
+            assert got[g] in states, "leaf %d: value %08x is no chain of %d blends of its %d inputs" % (
+                leaf[g], got[g], steps[g], counts[g])
+        assert skipped <= 0.01 * ukeys.size, "%d leaves too expensive to verify" % skipped
     # inner nodes on the touched paths: averageChildren of their tile; node 0's value word is Q6's
     touched = np.zeros(n_after, dtype=bool)
     touched[leaf] = True
