@@ -88,7 +88,9 @@ int osl_svo_max_depth(const osl_svo* t);
 /* bit 0: 1 (default) reproduces reference quirk Q3 (svo.cu:123 `while (r_key >= 15)`); 0 = leaves are never split.
  * bit 1 (testing aid): always sort with the cooperative grid radix sort, never with the splitter-based bucket sort.
  * bit 2 (measurement aid): osl_integrate_depth_host reads PINNED colour planes in place (zero-copy gather of the one
- * colour per observed leaf) instead of staging them; measured slower than the DMA on B200, hence off by default. */
+ * colour per observed leaf) instead of staging them; measured slower than the DMA on B200, hence off by default.
+ * bit 3 (testing / measurement aid): pipelined depth frames always run as four kernels on four streams, never as one
+ * k_frame launch per frame (the environment variable OSL_NO_FUSED does the same for every tree). */
 osl_status osl_svo_set_quirks(osl_svo* t, int ref_quirks);
 
 /* Pipelined mode for DEVICE-resident inputs (default 0).  With 1 the caller promises that the input buffers of every

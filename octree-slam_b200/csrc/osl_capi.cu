@@ -1,5 +1,6 @@
 // osl_capi.cu -- the C ABI of libosl_b200.so (include/osl_b200.h): object lifetime, memory, entry points.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "osl_internal.cuh"
@@ -111,6 +112,10 @@ osl_status osl_svo_create(osl_svo** out, const float center[3], float half_edge,
     if (cudaMemset(t->d_scan_totals, 0, (OSL_NCOUNT(OSL_MAXD) + 8) * sizeof(u32)) != cudaSuccess) { rc = OSL_ERR_CUDA; break; }
     if (cudaMallocHost(&t->h_ring, sizeof(FrameState) * OSL_RING) != cudaSuccess) { rc = OSL_ERR_OOM; break; }
     memset(t->h_ring, 0, sizeof(FrameState) * OSL_RING);
+    if (cudaMalloc(&t->d_ready, OSL_STAGES * sizeof(u32)) != cudaSuccess) { rc = OSL_ERR_OOM; break; }
+    if (cudaMemset(t->d_ready, 0, OSL_STAGES * sizeof(u32)) != cudaSuccess) { rc = OSL_ERR_CUDA; break; }
+    if (cudaMallocHost(&t->h_ready_vals, 64 * sizeof(u32)) != cudaSuccess) { rc = OSL_ERR_OOM; break; }
+    t->fused_enabled = getenv("OSL_NO_FUSED") ? 0 : 1;
     bool ok = true;
     for (int i = 0; i < OSL_RING && ok; i++)
       ok = cudaEventCreateWithFlags(&t->ring_ev[i], cudaEventDisableTiming) == cudaSuccess;
@@ -169,6 +174,8 @@ void osl_svo_destroy(osl_svo* t) {
   if (t->reader_ev) cudaEventDestroy(t->reader_ev);
   if (t->copy_stream) cudaStreamDestroy(t->copy_stream);
   if (t->h_ring) cudaFreeHost(t->h_ring);
+  if (t->h_ready_vals) cudaFreeHost(t->h_ready_vals);
+  cudaFree(t->d_ready);
   delete t;
 }
 
@@ -245,6 +252,7 @@ osl_status osl_svo_set_quirks(osl_svo* t, int ref_quirks) {
   t->tp.quirks = (ref_quirks & 1) ? 1 : 0;
   t->force_grid_sort = (ref_quirks & 2) ? 1 : 0;  // bit 1 (testing): never use the bucket sort
   t->zero_copy_rgb = (ref_quirks & 4) ? 1 : 0;    // bit 2 (measurement): read pinned colour planes in place
+  if (ref_quirks & 8) t->fused_enabled = 0;       // bit 3 (testing / measurement): pipelined frames as four kernels
   return OSL_OK;
 }
 
@@ -257,7 +265,7 @@ osl_status osl_integrate_depth(osl_svo* t, const uint16_t* d_depth, const uint8_
   ep.depth = d_depth; ep.rgb = d_rgb; ep.w = w; ep.h = h; ep.fx = fx; ep.fy = fy;
   memcpy(ep.M, pose, sizeof(ep.M));
   ep.n = w * h; ep.mode = 0;
-  return osl_run_integrate(t, ep, nullptr, (cudaStream_t)stream, false);
+  return osl_run_integrate(t, ep, nullptr, (cudaStream_t)stream, nullptr);
 }
 
 // The pose lives in device memory and is read when k_emit runs: lets a tracker's result drive the integration of
@@ -272,7 +280,7 @@ osl_status osl_integrate_depth_posed(osl_svo* t, const uint16_t* d_depth, const 
   ep.depth = d_depth; ep.rgb = d_rgb; ep.w = w; ep.h = h; ep.fx = fx; ep.fy = fy;
   ep.M_dev = d_pose;
   ep.n = w * h; ep.mode = 0;
-  return osl_run_integrate(t, ep, nullptr, (cudaStream_t)stream, false);
+  return osl_run_integrate(t, ep, nullptr, (cudaStream_t)stream, nullptr);
 }
 
 static osl_status ensure_stage(osl_svo* t, size_t n) {
@@ -289,6 +297,7 @@ static osl_status ensure_stage(osl_svo* t, size_t n) {
   }
   t->stage_cap = n;
   t->stage_seq = 0;
+  memset(t->stage_frame, 0, sizeof(t->stage_frame));
   return OSL_OK;
 }
 
@@ -304,39 +313,13 @@ osl_status osl_integrate_depth_host(osl_svo* t, const uint16_t* h_depth, const u
   const size_t n = (size_t)w * h;
   osl_status rc = ensure_stage(t, n);
   if (rc) return rc;
-  cudaStream_t st = (cudaStream_t)stream;
-  const int slot = (int)(t->stage_seq % OSL_STAGES);
-  if (t->stage_seq >= OSL_STAGES) OSL_CUDA(cudaStreamWaitEvent(t->copy_stream, t->stage_free[slot], 0));
-  OSL_CUDA(cudaMemcpyAsync(t->d_depth_stage[slot], h_depth, n * 2, cudaMemcpyHostToDevice, t->copy_stream));
-  // Colours: the device reads ONE pixel per observed leaf (the lowest pixel index that maps to it, ~5 % of the frame)
-  // and it knows which only after the sort.  Opt-in (osl_svo_set_quirks bit 2): a PINNED colour plane is not copied,
-  // k_levels gathers the winners' 3 bytes straight from host memory (zero-copy loads under UVA).  That takes 60 % of
-  // the frame's payload off the link, but measured on B200 / PCIe 5 it does not pay (profiles/r02_e2e_zero_copy.md):
-  // ~15 k scattered 32-byte PCIe reads per frame are bound by outstanding-request latency and stretch k_levels, so
-  // the default stages the colour plane with one DMA like the depth plane.
-  const uint8_t* rgb_dev = nullptr;
-  if (t->zero_copy_rgb) {
-    cudaPointerAttributes attr;
-    if (cudaPointerGetAttributes(&attr, h_rgb) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
-      rgb_dev = static_cast<const uint8_t*>(attr.devicePointer);
-    else
-      cudaGetLastError();  // (pageable memory is reported as an error by older drivers)
-  }
-  if (!rgb_dev) {
-    OSL_CUDA(cudaMemcpyAsync(t->d_rgb_stage[slot], h_rgb, n * 3, cudaMemcpyHostToDevice, t->copy_stream));
-    rgb_dev = t->d_rgb_stage[slot];
-  }
-  OSL_CUDA(cudaEventRecord(t->stage_copied[slot], t->copy_stream));  // k_emit (stream E) waits for it
   EmitParams ep;
   memset(&ep, 0, sizeof(ep));
-  ep.depth = t->d_depth_stage[slot]; ep.rgb = rgb_dev; ep.w = w; ep.h = h; ep.fx = fx; ep.fy = fy;
+  ep.w = w; ep.h = h; ep.fx = fx; ep.fy = fy;  // (depth / rgb: the staging slot osl_run_integrate picks)
   memcpy(ep.M, pose, sizeof(ep.M));
   ep.n = w * h; ep.mode = 0;
-  rc = osl_run_integrate(t, ep, nullptr, st, true);  // always pipelined: the library owns the copies
-  if (rc) return rc;
-  OSL_CUDA(cudaEventRecord(t->stage_free[slot], t->pipe[3]));  // the colours are last read by k_levels (stream V)
-  t->stage_seq++;
-  return OSL_OK;
+  const HostFrame hf = {h_depth, h_rgb};
+  return osl_run_integrate(t, ep, nullptr, (cudaStream_t)stream, &hf);  // always pipelined: the library owns the copies
 }
 
 osl_status osl_integrate_points(osl_svo* t, const float* d_xyz, const uint8_t* d_rgb, int n, void* stream) {
@@ -345,7 +328,7 @@ osl_status osl_integrate_points(osl_svo* t, const float* d_xyz, const uint8_t* d
   EmitParams ep;
   memset(&ep, 0, sizeof(ep));
   ep.pts = d_xyz; ep.stride = 3; ep.rgb = d_rgb; ep.n = n; ep.mode = 1;
-  return osl_run_integrate(t, ep, nullptr, (cudaStream_t)stream, false);
+  return osl_run_integrate(t, ep, nullptr, (cudaStream_t)stream, nullptr);
 }
 
 osl_status osl_integrate_voxels(osl_svo* t, const float* d_centers4, const float* d_colors4, int n, void* stream) {
@@ -354,7 +337,7 @@ osl_status osl_integrate_voxels(osl_svo* t, const float* d_centers4, const float
   EmitParams ep;
   memset(&ep, 0, sizeof(ep));
   ep.pts = d_centers4; ep.stride = 4; ep.n = n; ep.mode = 2;
-  return osl_run_integrate(t, ep, d_colors4, (cudaStream_t)stream, false);
+  return osl_run_integrate(t, ep, d_colors4, (cudaStream_t)stream, nullptr);
 }
 
 osl_status osl_svo_join(osl_svo* t, void* stream) {
@@ -416,7 +399,7 @@ osl_status osl_svo_upload(osl_svo* t, const uint32_t* h_pool, int n_nodes) {
   if (n_nodes > 0) {
     if (n_nodes < 8 || (n_nodes & 7)) return OSL_ERR_INVALID;  // whole 8-node tiles, the root's first
     OSL_CUDA(cudaMemcpy(t->d_pool, h_pool, (size_t)n_nodes * 8, cudaMemcpyHostToDevice));
-    int* d_bad = reinterpret_cast<int*>(t->d_scan_totals + OSL_NCOUNT(OSL_MAXD) + 1);  // scratch word, zero at rest
+    int* d_bad = reinterpret_cast<int*>(t->d_scan_totals + OSL_NCOUNT(OSL_MAXD) + 2);  // scratch word, zero at rest
     int bad = 0;
     k_validate_pool<<<(n_nodes + 255) / 256, 256>>>(t->d_pool, n_nodes, d_bad);
     g_osl_launches++;

@@ -17,6 +17,7 @@
 // streams (osl_run_integrate).  The host never waits for the device unless the pool has to grow, the caller asks for
 // sizes / counters, or it runs more than 3 frames ahead.
 #include <cooperative_groups.h>
+#include <string.h>
 
 #include "osl_internal.cuh"
 
@@ -26,7 +27,8 @@ namespace cg = cooperative_groups;
 
 // phase checkpoints (SM clock of CTA 0 / thread 0) for tools/phase_profile.py; one predicated store each
 __device__ unsigned long long g_osl_prof[64];
-#define PROF(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_osl_prof[i] = (unsigned long long)clock64(); } while (0)
+// (`bid` = the CTA's index inside its role: the bodies below run as kernels of their own and as roles of k_frame)
+#define PROF(i) do { if (bid == 0 && threadIdx.x == 0) g_osl_prof[i] = (unsigned long long)clock64(); } while (0)
 
 // ------------------------------------------------------------------------------------------------ k_emit
 // One CTA per 64x32-pixel tile (mode 0) or per 2048 consecutive inputs (modes 1, 2); 4 inputs per thread (16 warps per
@@ -44,16 +46,16 @@ __device__ unsigned long long g_osl_prof[64];
 #define EMIT_TH 32
 #define EMIT_SLOTS 4096
 #define EMIT_EMPTY 0xFFFFFFFFFFFFFFFFull
-#define EMIT_SMEM (EMIT_SLOTS * 8 + EMIT_SLOTS * 4 + EMIT_TILE * 2)
+#define EMIT_SMEM (EMIT_SLOTS * 8 + EMIT_SLOTS * 4 + EMIT_TILE * 2 + 16)
 
-__global__ void __launch_bounds__(EMIT_THREADS)
-k_emit(EmitParams p, TreeParams tp, int vec_ok, u64* __restrict__ keys, u32* __restrict__ pay,
-       u64* __restrict__ keys_dense, FrameState* fs, int parity) {
-  extern __shared__ __align__(16) unsigned char s_raw[];
+__device__ __forceinline__ void emit_body(const EmitParams& p, const TreeParams& tp, int vec_ok, u64* __restrict__ keys,
+                                          u32* __restrict__ pay, u64* __restrict__ keys_dense, FrameState* fs,
+                                          int parity, int bid, unsigned char* s_raw) {
   u64* s_key = reinterpret_cast<u64*>(s_raw);
   u32* s_pay = reinterpret_cast<u32*>(s_raw + EMIT_SLOTS * 8);
   unsigned short* s_list = reinterpret_cast<unsigned short*>(s_raw + EMIT_SLOTS * 12);
-  __shared__ u32 s_count, s_valid, s_base;
+  u32* s_misc = reinterpret_cast<u32*>(s_raw + EMIT_SLOTS * 12 + EMIT_TILE * 2);
+  u32 &s_count = s_misc[0], &s_valid = s_misc[1], &s_base = s_misc[2];
   const int tid = threadIdx.x, lane = tid & 31;
   const bool dedup = p.mode != 2;
   PROF(0);
@@ -70,7 +72,7 @@ k_emit(EmitParams p, TreeParams tp, int vec_ok, u64* __restrict__ keys, u32* __r
   u32 vmask = 0;
   int first;  // input index of this thread's first element (its 8 elements are consecutive)
   if (p.mode == 0) {
-    const int tx = blockIdx.x % p.tiles_x, ty = blockIdx.x / p.tiles_x;
+    const int tx = bid % p.tiles_x, ty = bid / p.tiles_x;
     const int y = ty * EMIT_TH + tid / (EMIT_TW / EMIT_PPT), x0 = tx * EMIT_TW + (tid % (EMIT_TW / EMIT_PPT)) * EMIT_PPT;
     first = y * p.w + x0;
     int dv[EMIT_PPT];
@@ -98,7 +100,7 @@ k_emit(EmitParams p, TreeParams tp, int vec_ok, u64* __restrict__ keys, u32* __r
       vmask |= (u32)ok << i;
     }
   } else {
-    first = blockIdx.x * EMIT_TILE + tid * EMIT_PPT;
+    first = bid * EMIT_TILE + tid * EMIT_PPT;
     bool bad = false;  // mode 2: an invalid input, or a key smaller than its predecessor's
 #pragma unroll
     for (int i = 0; i < EMIT_PPT; i++) {
@@ -171,6 +173,13 @@ k_emit(EmitParams p, TreeParams tp, int vec_ok, u64* __restrict__ keys, u32* __r
     pay[base + i] = s_pay[slot];
   }
   PROF(3);
+}
+
+__global__ void __launch_bounds__(EMIT_THREADS)
+k_emit(EmitParams p, TreeParams tp, int vec_ok, u64* __restrict__ keys, u32* __restrict__ pay,
+       u64* __restrict__ keys_dense, FrameState* fs, int parity) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  emit_body(p, tp, vec_ok, keys, pay, keys_dense, fs, parity, (int)blockIdx.x, s_raw);
 }
 
 // ------------------------------------------------------------------------------------------------ k_sort
@@ -397,7 +406,7 @@ k_sort(u64* kA, u32* pA, u64* kB, u32* pB, u32* cta_hist, const FrameState* fs, 
 #define BK_BUCKETS 64
 #define BK_THREADS SORT_THREADS
 #define BK_CAP SORT_TILE
-#define BK_SMEM (2 * BK_CAP * 8 + 2 * BK_CAP * 4)
+#define BK_SMEM (2 * BK_CAP * 8 + 2 * BK_CAP * 4 + (int)sizeof(BucketShared))
 
 struct BucketShared {
   u32 whist[SORT_WARPS][256];
@@ -493,17 +502,17 @@ __device__ void cta_sort_global(u64* k0, u32* p0, u64* k1, u32* p1, int c, int p
   }
 }
 
-__global__ void __launch_bounds__(BK_THREADS)
-k_sort_bucket(const u64* kin, const u32* pin, u64* kout, u32* pout, u64* kscr, u32* pscr, const FrameState* fs,
-              const u64* __restrict__ split, int passes, int parity) {
-  extern __shared__ __align__(16) unsigned char s_raw[];
-  __shared__ BucketShared S;
+// (runs on the first BK_THREADS threads of its CTA)
+__device__ __forceinline__ void bucket_body(const u64* kin, const u32* pin, u64* kout, u32* pout, u64* kscr, u32* pscr,
+                                            const FrameState* fs, const u64* __restrict__ split, int passes, int parity,
+                                            int bid, unsigned char* s_raw) {
+  BucketShared& S = *reinterpret_cast<BucketShared*>(s_raw + 2 * BK_CAP * 8 + 2 * BK_CAP * 4);
   u64* const s_key0 = reinterpret_cast<u64*>(s_raw);                    // [2][BK_CAP]
   u32* const s_pay0 = reinterpret_cast<u32*>(s_raw + 2 * BK_CAP * 8);   // [2][BK_CAP]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const u32 lt = lanemask_lt();
-  const int n = fs->acc_emit[parity];
-  const int b = blockIdx.x;
+  const int n = __ldcg(&fs->acc_emit[parity]);
+  const int b = bid;
   const u64 lo = (b == 0) ? 0ull : __ldg(&split[b - 1]);
   const u64 hi = (b == BK_BUCKETS - 1) ? ~0ull : __ldg(&split[b]);
   if (tid == 0) { S.cnt = 0; S.below = 0; S.or_lo = S.or_hi = 0u; S.and_lo = S.and_hi = ~0u; }
@@ -625,6 +634,13 @@ k_sort_bucket(const u64* kin, const u32* pin, u64* kout, u32* pout, u64* kscr, u
     pout[offset + i] = s_pay0[cur * BK_CAP + i];
   }
   PROF(11);
+}
+
+__global__ void __launch_bounds__(BK_THREADS)
+k_sort_bucket(const u64* kin, const u32* pin, u64* kout, u32* pout, u64* kscr, u32* pscr, const FrameState* fs,
+              const u64* __restrict__ split, int passes, int parity) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  bucket_body(kin, pin, kout, pout, kscr, pscr, fs, split, passes, parity, (int)blockIdx.x, s_raw);
 }
 
 // ------------------------------------------------------------------------------------------------ k_analyze
@@ -824,17 +840,27 @@ __device__ __forceinline__ void assign_block(int vb, int n, const u64* __restric
 
 __device__ __forceinline__ u32 ld_vol(const u32* p) { return *(const volatile u32*)p; }
 
-// (3 CTAs per SM: 40 registers, no spills; at 50 M keys the extra resident walks are worth 20 %)
-__global__ void __launch_bounds__(AN_THREADS, 3)
-k_structure(const u64* __restrict__ keys_sorted, const u64* __restrict__ keys_dense, u32* pay, u32* pool, TreeParams tp,
-            FrameState* fs, FrameState* fr, FrameState* hr, uint8_t* m8, uint8_t* s8, u32* start, u32* ctatot,
-            u32* flags, u32 epoch, LevelArrays lv, int mode, int capacity, int n_in, int parity, u64* split_out) {
-  __shared__ u32 s_w[AN_WARPS][NC_MAX];
-  __shared__ u32 s_plan[NC_MAX];
-  __shared__ u32 s_tot[NC_MAX];
-  __shared__ u32 s_base[NC_MAX];
-  __shared__ u32 s_ctot[NC_MAX];
-  __shared__ u32 s_scan[AN_WARPS];
+struct StructArgs {
+  const u64* keys_sorted; const u64* keys_dense; u32* pay; u32* pool; TreeParams tp;
+  FrameState* fs; FrameState* fr; FrameState* hr; uint8_t* m8; uint8_t* s8; u32* start; u32* ctatot;
+  u32* flags; u32 epoch; LevelArrays lv; int mode; int capacity; int n_in; int parity; u64* split_out;
+};
+#define STRUCT_SMEM ((AN_WARPS + 4) * NC_MAX * 4 + AN_WARPS * 4)
+
+__device__ __forceinline__ void structure_body(const StructArgs& A, int bid, int G, unsigned char* s_raw) {
+  const u64* __restrict__ keys_sorted = A.keys_sorted; const u64* __restrict__ keys_dense = A.keys_dense;
+  u32* pay = A.pay; u32* pool = A.pool; const TreeParams tp = A.tp;
+  FrameState* fs = A.fs; FrameState* fr = A.fr; FrameState* hr = A.hr;
+  uint8_t* m8 = A.m8; uint8_t* s8 = A.s8; u32* start = A.start; u32* ctatot = A.ctatot; u32* flags = A.flags;
+  const u32 epoch = A.epoch; const LevelArrays& lv = A.lv;
+  const int mode = A.mode, capacity = A.capacity, n_in = A.n_in, parity = A.parity;
+  u64* split_out = A.split_out;
+  u32 (*s_w)[NC_MAX] = reinterpret_cast<u32 (*)[NC_MAX]>(s_raw);
+  u32* s_plan = reinterpret_cast<u32*>(s_raw) + AN_WARPS * NC_MAX;
+  u32* s_tot = s_plan + NC_MAX;
+  u32* s_base = s_tot + NC_MAX;
+  u32* s_ctot = s_base + NC_MAX;
+  u32* s_scan = s_ctot + NC_MAX;
   const int D = tp.D, NC = OSL_NCOUNT(D);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = __ldcg(&fs->acc_emit[parity]);
@@ -845,15 +871,14 @@ k_structure(const u64* __restrict__ keys_sorted, const u64* __restrict__ keys_de
   const u64* __restrict__ keys = (mode == 2 && __ldcg(&fs->acc_unsorted[parity]) == 0) ? keys_dense : keys_sorted;
   const u32 size0 = (u32)(cur > 8 ? cur : 8);
   const int nvb = (n + AN_THREADS - 1) / AN_THREADS;
-  const int G = gridDim.x;
   // every CTA owns a CONTIGUOUS range of virtual blocks: the exclusive prefix of its first block is the sum of the
   // lower CTAs' totals, and the prefix of each further block follows by adding the previous block's counts
   const int per = (nvb + G - 1) / G;
-  const int vb0 = min(nvb, (int)blockIdx.x * per), vb1 = min(nvb, vb0 + per);
+  const int vb0 = min(nvb, bid * per), vb1 = min(nvb, vb0 + per);
 
   PROF(16);
   // splitters for k_sort_bucket of a later frame: BK_BUCKETS-quantiles of this frame's sorted keys
-  if (blockIdx.x == G - 1 && tid < BK_BUCKETS - 1 && n >= BK_BUCKETS)
+  if (bid == G - 1 && tid < BK_BUCKETS - 1 && n >= BK_BUCKETS)
     split_out[tid] = keys[(size_t)(((long long)(tid + 1) * n) / BK_BUCKETS)];
   for (int c = tid; c < NC; c += AN_THREADS) s_ctot[c] = 0;
   __syncthreads();
@@ -863,11 +888,11 @@ k_structure(const u64* __restrict__ keys_sorted, const u64* __restrict__ keys_de
   for (int vb = vb0; vb < vb1; vb++)
     analyze_block(vb, n, keys, pay, mode, pool, tp, m8, s8, start, s_ctot, &s_w[0][0]);
   // publish this CTA's counter vector behind an epoch flag (every CTA publishes, also one without blocks)
-  for (int c = tid; c < NC; c += AN_THREADS) ctatot[(size_t)blockIdx.x * NC + c] = s_ctot[c];
+  for (int c = tid; c < NC; c += AN_THREADS) ctatot[(size_t)bid * NC + c] = s_ctot[c];
   __syncthreads();
   if (tid == 0) {
     __threadfence();
-    *(volatile u32*)&flags[blockIdx.x] = epoch;
+    *(volatile u32*)&flags[bid] = epoch;
   }
   PROF(17);
 
@@ -885,7 +910,7 @@ k_structure(const u64* __restrict__ keys_sorted, const u64* __restrict__ keys_de
   PROF(18);
   for (int c = tid; c < NC; c += AN_THREADS) {
     u32 tot = 0, pre = 0;
-    const int mine = (int)blockIdx.x;
+    const int mine = bid;
     for (int b0 = 0; b0 < G; b0 += 16) {
       u32 v[16];
 #pragma unroll
@@ -943,7 +968,7 @@ k_structure(const u64* __restrict__ keys_sorted, const u64* __restrict__ keys_de
   // Book-keeping by the LAST CTA (the grid is sized with a margin, so it usually has no block of its own and this
   // stays off the critical path): the frame's result block, to the device copy k_levels reads and straight to the
   // pinned host ring (no cudaMemcpyAsync per frame; the host reads it after the event that follows k_levels).
-  if ((int)blockIdx.x == G - 1) {
+  if (bid == G - 1) {
     if (bs >= 1) {
       const int v = (int)(woff + incl - val);
       fr->base[bs * (D + 1) + bd] = v; hr->base[bs * (D + 1) + bd] = v;
@@ -976,11 +1001,17 @@ k_structure(const u64* __restrict__ keys_sorted, const u64* __restrict__ keys_de
       }
       // every CTA that has work read these before it published / passed the barrier; a CTA that starts later sees
       // 0 entries and idles
-      fs->acc_valid[parity] = 0; fs->acc_emit[parity] = 0; fs->acc_unsorted[parity] = 0;
+      fs->acc_valid[parity] = 0; fs->acc_emit[parity] = 0; fs->acc_unsorted[parity] = 0; fs->acc_tiles[parity] = 0;
       if (!overflow) fs->cur_size = (int)after;
       fs->frame_seq = seq;
     }
   }
+}
+
+// (3 CTAs per SM: 40 registers, no spills; at 50 M keys the extra resident walks are worth 20 %)
+__global__ void __launch_bounds__(AN_THREADS, 3) k_structure(StructArgs A) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  structure_body(A, (int)blockIdx.x, (int)gridDim.x, s_raw);
 }
 
 // ------------------------------------------------------------------------------------------------ k_levels
@@ -997,7 +1028,7 @@ k_structure(const u64* __restrict__ keys_sorted, const u64* __restrict__ keys_de
 #define LEVEL_THREADS 512
 #define LEVEL_NARROW 1024
 #define LEVEL_STAGE 2048
-#define LEVEL_SMEM (LEVEL_STAGE * (32 + 4 + 4 + 2 + 2) + 64)
+#define LEVEL_SMEM (LEVEL_STAGE * (32 + 4 + 4 + 2 + 2) + 64 + 256)
 
 __device__ __forceinline__ void level_leaf(u32* pool, const LevelArrays& lv, int D, int idx, int mode,
                                            const uint8_t* __restrict__ rgb, const float* __restrict__ colors4,
@@ -1046,21 +1077,46 @@ __device__ __forceinline__ void level_inner(u32* pool, const LevelArrays& lv, in
   pool[2 * (size_t)node + 1] = osl_average8(v);
 }
 
-__global__ void __launch_bounds__(LEVEL_THREADS)
-k_levels(u32* pool, LevelArrays lv, const FrameState* fr, u32* done, int D, int mode,
-         const uint8_t* __restrict__ rgb, const float* __restrict__ colors4) {
-  cg::grid_group grid = cg::this_grid();
-  extern __shared__ __align__(16) unsigned char s_raw[];
-  __shared__ int s_nl[OSL_MAXD + 2];   // n_level[d]
-  __shared__ int s_pre[OSL_MAXD + 2];  // s_pre[d] = sum of n_level[1..d-1]
-  __shared__ int s_overflow, s_nin;
+struct LevelArgs {
+  u32* pool; LevelArrays lv; const FrameState* fr; u32* done; int D; int mode;
+  const uint8_t* rgb; const float* colors4;
+  FrameState* hr; int done_tag;  // pinned result block of the frame; done_tag (frame number + 1) is stored into
+                                 // hr->done_flag when every value of the frame has been written
+};
+
+// barrier over the G co-resident CTAs of this role (k_levels is launched cooperatively; as a role of k_frame its CTAs
+// are the first of the grid): *ctr counts arrivals over the successive barriers of one launch, `phase` = 1, 2, ...
+__device__ __forceinline__ void role_barrier(u32* ctr, int G, int phase) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(ctr, 1u);
+    long long spin = 0;
+    while (*(volatile u32*)ctr < (u32)(G * phase))
+      if (++spin > (1ll << 31)) __trap();
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void levels_body(const LevelArgs& A, int bid, int G, unsigned char* s_raw) {
+  u32* pool = A.pool; const LevelArrays& lv = A.lv; const FrameState* fr = A.fr; u32* done = A.done;
+  const int D = A.D, mode = A.mode;
+  const uint8_t* __restrict__ rgb = A.rgb; const float* __restrict__ colors4 = A.colors4;
+  int* s_nl = reinterpret_cast<int*>(s_raw + LEVEL_STAGE * (32 + 4 + 4 + 2 + 2) + 64);  // n_level[d]
+  int* s_pre = s_nl + (OSL_MAXD + 2);  // s_pre[d] = sum of n_level[1..d-1]
+  int& s_overflow = s_pre[OSL_MAXD + 2];
+  int& s_nin = s_pre[OSL_MAXD + 3];
   const int tid = threadIdx.x;
-  const int gtid = blockIdx.x * LEVEL_THREADS + tid, gsz = gridDim.x * LEVEL_THREADS;
+  const int gtid = bid * LEVEL_THREADS + tid, gsz = G * LEVEL_THREADS;
   // the frame's level counts: one parallel round trip, then a prefix over <= 20 values
   if (tid <= D && tid >= 1) s_nl[tid] = fr->n_level[tid];
   if (tid == 0) { s_overflow = fr->overflow; s_nin = fr->n_in; }
   __syncthreads();
-  if (s_overflow) return;
+  if (s_overflow) {  // the frame was dropped by the structure stage: nothing to fold
+    if (bid == 0 && tid == 0 && A.hr) { __threadfence_system(); *(volatile int*)&A.hr->done_flag = A.done_tag; }
+    return;
+  }
   if (tid == 0) {
     int run = 0;
     s_nl[0] = 0; s_pre[0] = 0;
@@ -1080,10 +1136,10 @@ k_levels(u32* pool, LevelArrays lv, const FrameState* fr, u32* done, int D, int 
 
   // phase 2: wide levels with the whole grid
   int d = D - 1;
-  for (; d >= 1; d--) {
+  for (int phase = 1; d >= 1; d--, phase++) {
     const int n_d = s_nl[d];
     if (n_d <= LEVEL_NARROW) break;
-    grid.sync();
+    role_barrier(done + 1, G, phase);
     for (int idx = gtid; idx < n_d; idx += gsz) level_inner(pool, lv, d, idx);
   }
   PROF(36);
@@ -1093,12 +1149,13 @@ k_levels(u32* pool, LevelArrays lv, const FrameState* fr, u32* done, int D, int 
     __threadfence();
     atomicAdd(done, 1u);
   }
-  if (blockIdx.x != 0) return;
+  if (bid != 0) return;
   if (tid == 0) {
     long long spin = 0;
-    while (*(volatile u32*)done != gridDim.x)
+    while (*(volatile u32*)done != (u32)G)
       if (++spin > (1ll << 31)) __trap();  // bounded wait, see k_structure
     *(volatile u32*)done = 0u;  // the next launch starts from zero (launches of one tree are stream-ordered)
+    *(volatile u32*)(done + 1) = 0u;  // (every CTA passed its last role_barrier before it signalled `done`)
     __threadfence();
   }
   __syncthreads();
@@ -1160,6 +1217,8 @@ k_levels(u32* pool, LevelArrays lv, const FrameState* fr, u32* done, int D, int 
       if (tid == 0 && s_nl[1] > 0) pool[1] = osl_average8(s_w1[0]);  // phase 3 (Q6)
     }
     PROF(39);
+    __syncthreads();
+    if (tid == 0 && A.hr) { __threadfence_system(); *(volatile int*)&A.hr->done_flag = A.done_tag; }
     return;
   }
   // fallback: the narrow part does not fit the staging area -> one block barrier + one L2 round trip per level
@@ -1178,6 +1237,83 @@ k_levels(u32* pool, LevelArrays lv, const FrameState* fr, u32* done, int D, int 
     }
     pool[1] = osl_average8(v);
   }
+  __syncthreads();
+  if (tid == 0 && A.hr) { __threadfence_system(); *(volatile int*)&A.hr->done_flag = A.done_tag; }
+}
+
+__global__ void __launch_bounds__(LEVEL_THREADS) k_levels(LevelArgs A) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  levels_body(A, (int)blockIdx.x, (int)gridDim.x, s_raw);
+}
+
+// ------------------------------------------------------------------------------------------------ k_frame
+// ONE launch per frame for pipelined depth frames: the four stages run as ROLES of one grid, each on the frame that
+// has reached it --
+//     launch f = { emit(f) -> sort(f),  structure(f-1),  values(f-2) }
+// on ONE stream, so every dependency between frames is plain stream order (no events, no host round trips):
+// structure(f-1) needs sort(f-1) and structure(f-2), both in launch f-1; values(f-2) needs structure(f-2), in launch
+// f-1; the key-list slot emit(f) fills was last read by structure(f-3), the level lists structure(f-1) fills were
+// last read by values(f-3).  Launches are chained with programmatic dependent launch: the next grid's CTAs become
+// resident while this one drains and block in griddepcontrol.wait, so the stream never idles through a launch latency.
+// CTA ranges: [0, gS) structure, then gV values, then gE emit tiles, then BK_BUCKETS sort buckets.  The roles that
+// spin on flags of their own kind (structure: counter exchange; values: level barrier) come FIRST, the roles that
+// never wait on a later CTA (emit) before the one that waits for them (sort): with at most 2 * num_sms CTAs of
+// spinning roles per device (the host caps gS + gV + BK_BUCKETS) a spinning CTA can never keep the CTA it waits for
+// off the machine.  Inside the launch the sort role waits for the emit role through FrameState::acc_tiles.
+struct SortArgs {
+  const u64* kin; const u32* pin; u64* kout; u32* pout; u64* kscr; u32* pscr; const FrameState* fs;
+  const u64* split; int passes; int parity;
+};
+struct EmitArgs {
+  EmitParams p; TreeParams tp; int vec_ok; u64* keys; u32* pay; u64* keys_dense; FrameState* fs; int parity;
+};
+struct FrameArgs {
+  StructArgs S; LevelArgs V; EmitArgs E; SortArgs So;
+  int gS, gV, gE, gSo;
+};
+#define FRAME_THREADS 512
+#define FRAME_SMEM LEVEL_SMEM
+static_assert(FRAME_SMEM >= EMIT_SMEM && FRAME_SMEM >= BK_SMEM && FRAME_SMEM >= STRUCT_SMEM, "k_frame shared memory");
+static_assert(AN_THREADS == FRAME_THREADS && LEVEL_THREADS == FRAME_THREADS && EMIT_THREADS == FRAME_THREADS &&
+              BK_THREADS <= FRAME_THREADS, "k_frame role CTAs");
+
+__device__ __forceinline__ void spin_until_eq(const u32* p, u32 want) {
+  long long spin = 0;
+  while (*(const volatile u32*)p != want)
+    if (++spin > (1ll << 31)) __trap();  // bounded: an error to the host instead of a hung GPU
+  __threadfence();
+}
+
+__global__ void __launch_bounds__(FRAME_THREADS, 2) k_frame(const __grid_constant__ FrameArgs A) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  // programmatic dependent launch: let the next launch's CTAs take their places now (they wait below until this grid
+  // has completed), then wait for the previous launch ourselves
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  int b = (int)blockIdx.x;
+  if (b < A.gS) { structure_body(A.S, b, A.gS, s_raw); return; }
+  b -= A.gS;
+  if (b < A.gV) { levels_body(A.V, b, A.gV, s_raw); return; }
+  b -= A.gV;
+  if (b < A.gE) {
+    if (A.E.p.ready) {  // host frame: the staging copies of this frame (copy engine) have landed
+      if (threadIdx.x == 0) spin_until_eq(A.E.p.ready, A.E.p.ready_seq);
+      __syncthreads();
+    }
+    emit_body(A.E.p, A.E.tp, A.E.vec_ok, A.E.keys, A.E.pay, A.E.keys_dense, A.E.fs, A.E.parity, b, s_raw);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      atomicAdd(reinterpret_cast<u32*>(&A.E.fs->acc_tiles[A.E.parity]), 1u);
+    }
+    return;
+  }
+  b -= A.gE;
+  if (threadIdx.x >= BK_THREADS) return;  // whole warps leave: the barriers below count the remaining ones only
+  if (threadIdx.x == 0) spin_until_eq(reinterpret_cast<const u32*>(&A.So.fs->acc_tiles[A.So.parity]), (u32)A.gE);
+  __syncthreads();
+  bucket_body(A.So.kin, A.So.pin, A.So.kout, A.So.pout, A.So.kscr, A.So.pscr, A.So.fs, A.So.split, A.So.passes,
+              A.So.parity, b, s_raw);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -1251,6 +1387,7 @@ osl_status osl_ensure_workspace(osl_svo* t, size_t n) {
 osl_status osl_integrate_init(osl_svo* t) {
   OSL_CUDA(cudaFuncSetAttribute((const void*)k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, EMIT_SMEM));
   OSL_CUDA(cudaFuncSetAttribute((const void*)k_levels, cudaFuncAttributeMaxDynamicSharedMemorySize, LEVEL_SMEM));
+  OSL_CUDA(cudaFuncSetAttribute((const void*)k_structure, cudaFuncAttributeMaxDynamicSharedMemorySize, STRUCT_SMEM));
   OSL_CUDA(cudaFuncSetAttribute((const void*)k_sort_bucket, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM));
   OSL_CUDA(cudaMalloc(&t->d_split, OSL_FRONT * BK_BUCKETS * sizeof(u64)));
   return osl_reset_splitters(t);
@@ -1297,7 +1434,7 @@ osl_status osl_grow_pool(osl_svo* t, size_t want_nodes, cudaStream_t st) {
 
 int osl_structure_occupancy() {
   int occ = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)k_structure, AN_THREADS, 0);
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)k_structure, AN_THREADS, STRUCT_SMEM);
   if (e != cudaSuccess) { g_osl_last_cuda_error = (int)e; return 0; }
   return occ;
 }
@@ -1310,13 +1447,49 @@ int osl_levels_occupancy() {
 
 static inline int mode_of(const osl_svo* t, int slot) { return t->ring_mode[slot]; }
 
+static StructArgs make_struct_args(osl_svo* t, const u64* skeys, u32* spay, FrameState* fs, FrameState* fr,
+                                   unsigned long long f, const LevelArrays& lv, int mode, int n, int fslot) {
+  StructArgs A;
+  A.keys_sorted = skeys; A.keys_dense = t->d_keysB[fslot]; A.pay = spay; A.pool = t->d_pool; A.tp = t->tp;
+  A.fs = fs; A.fr = fr; A.hr = &t->h_ring[f % OSL_RING];  // pinned host memory, device-accessible (UVA)
+  A.m8 = t->d_m; A.s8 = t->d_s; A.start = t->d_start; A.ctatot = t->d_blockcnt; A.flags = t->d_flags;
+  A.epoch = (u32)(f + 1); A.lv = lv; A.mode = mode; A.capacity = (int)t->cap_nodes; A.n_in = n; A.parity = fslot;
+  A.split_out = t->d_split + fslot * BK_BUCKETS;
+  return A;
+}
+
+static LevelArgs make_level_args(osl_svo* t, const LevelArrays& lv, const FrameState* fr, unsigned long long f,
+                                 int mode, const uint8_t* rgb, const float* colors4) {
+  LevelArgs A;
+  A.pool = t->d_pool; A.lv = lv; A.fr = fr;
+  A.done = t->d_scan_totals + OSL_NCOUNT(OSL_MAXD);  // [0] one-sided barrier, [1] level barrier (zero at rest)
+  A.D = t->tp.D; A.mode = mode; A.rgb = rgb; A.colors4 = colors4;
+  A.hr = &t->h_ring[f % OSL_RING]; A.done_tag = (int)(f + 1);
+  return A;
+}
+
 // Consume the result blocks of frames that have completed (non-blocking unless `block`): exact node count, counters.
 osl_status osl_poll_results(osl_svo* t, bool block) {
   while (t->ring_tail != t->ring_head) {
     const int slot = (int)(t->ring_tail % OSL_RING);
-    cudaError_t e = block ? cudaEventSynchronize(t->ring_ev[slot]) : cudaEventQuery(t->ring_ev[slot]);
-    if (e == cudaErrorNotReady) break;
-    if (e != cudaSuccess) { g_osl_last_cuda_error = (int)e; return OSL_ERR_CUDA; }
+    if (t->ring_kind[slot] == 1) {  // k_frame path: completion is the tag the value stage stores in the pinned block
+      const int tag = (int)(t->ring_tail + 1);
+      if (block && *(volatile int*)&t->h_ring[slot].done_flag != tag) {
+        osl_status rc = osl_fused_flush(t);
+        if (rc) return rc;
+        cudaError_t e = cudaStreamSynchronize(t->pipe[2]);
+        if (e != cudaSuccess) { g_osl_last_cuda_error = (int)e; return OSL_ERR_CUDA; }
+      }
+      if (*(volatile int*)&t->h_ring[slot].done_flag != tag) {
+        if (block) return OSL_ERR_CUDA;  // (cannot happen: the stream has drained)
+        break;
+      }
+      __sync_synchronize();  // the block's other words were written before the tag
+    } else {
+      cudaError_t e = block ? cudaEventSynchronize(t->ring_ev[slot]) : cudaEventQuery(t->ring_ev[slot]);
+      if (e == cudaErrorNotReady) break;
+      if (e != cudaSuccess) { g_osl_last_cuda_error = (int)e; return OSL_ERR_CUDA; }
+    }
     const FrameState& F = t->h_ring[slot];
     t->inflight_headroom -= t->ring_headroom[slot];
     t->ring_tail++;
@@ -1356,6 +1529,23 @@ osl_status osl_poll_results(osl_svo* t, bool block) {
 static osl_status wait_oldest(osl_svo* t) {
   if (t->ring_tail == t->ring_head) return OSL_OK;
   const int slot = (int)(t->ring_tail % OSL_RING);
+  if (t->ring_kind[slot] == 1) {
+    // the oldest frame's last stage rides in the launch two frames later: issue it if it has not been issued
+    if (t->ring_head - t->ring_tail <= 2) {
+      osl_status rc = osl_fused_flush(t);
+      if (rc) return rc;
+    }
+    const int tag = (int)(t->ring_tail + 1);
+    for (long long spin = 0; *(volatile int*)&t->h_ring[slot].done_flag != tag; spin++) {
+      if ((spin & 0x3FF) == 0x3FF) {  // a kernel that trapped (or a lost launch) must not hang the host
+        cudaError_t e = cudaStreamQuery(t->pipe[2]);
+        if (e == cudaSuccess) break;  // drained: poll below sees the tag (or reports the inconsistency)
+        if (e != cudaErrorNotReady) { g_osl_last_cuda_error = (int)e; return OSL_ERR_CUDA; }
+      }
+    }
+    if (*(volatile int*)&t->h_ring[slot].done_flag != tag) return osl_poll_results(t, true);
+    return osl_poll_results(t, false);
+  }
   cudaError_t e = cudaEventSynchronize(t->ring_ev[slot]);
   if (e != cudaSuccess) { g_osl_last_cuda_error = (int)e; return OSL_ERR_CUDA; }
   return osl_poll_results(t, false);
@@ -1391,9 +1581,69 @@ int g_osl_piped_trees = 0;  // trees of this process that have used pipelined mo
 // <= num_sms CTAs in total, so a waiting CTA always finds an empty SM and no grid barrier can deadlock.
 static osl_status osl_order_after_readers(osl_svo* t, cudaStream_t st, bool piped, cudaStream_t sS, cudaStream_t sV);
 
-osl_status osl_run_integrate(osl_svo* t, EmitParams& ep, const void* colors, cudaStream_t st, bool inputs_on_front) {
+// One k_frame launch: the structure stage of frame fz_s, the value stage of frame fz_v and -- when `nw` is given --
+// emit + sort of the new frame.  nw == NULL drains the pipeline by one stage (osl_fused_flush).
+static osl_status fused_launch(osl_svo* t, const osl_svo::FzStage* nw, const EmitParams* ep) {
+  FrameArgs A;
+  memset(&A, 0, sizeof(A));
+  FrameState* fs = t->d_fs;
+  if (t->fz_s.valid) {
+    const osl_svo::FzStage& q = t->fz_s;
+    A.S = make_struct_args(t, t->d_keysB[q.fslot], t->d_payB[q.fslot], fs, t->d_fs + 1 + q.bslot, q.f, t->lv[q.bslot], 0,
+                           q.n, q.fslot);
+    A.gS = q.gS;
+  }
+  if (t->fz_v.valid) {
+    const osl_svo::FzStage& q = t->fz_v;
+    A.V = make_level_args(t, t->lv[q.bslot], t->d_fs + 1 + q.bslot, q.f, 0, q.rgb, nullptr);
+    A.gV = q.gV;
+  }
+  if (nw) {
+    A.E.p = *ep;
+    A.E.p.tiles_x = (ep->w + EMIT_TW - 1) / EMIT_TW;
+    A.E.p.tiles_y = (ep->h + EMIT_TH - 1) / EMIT_TH;
+    A.E.tp = t->tp;
+    A.E.vec_ok = ((reinterpret_cast<uintptr_t>(ep->depth) & 7) == 0) && (ep->w % 4 == 0);
+    A.E.keys = t->d_keysA[nw->fslot]; A.E.pay = t->d_payA[nw->fslot]; A.E.keys_dense = t->d_keysB[nw->fslot];
+    A.E.fs = fs; A.E.parity = nw->fslot;
+    A.gE = A.E.p.tiles_x * A.E.p.tiles_y;
+    A.So.kin = t->d_keysA[nw->fslot]; A.So.pin = t->d_payA[nw->fslot];
+    A.So.kout = t->d_keysB[nw->fslot]; A.So.pout = t->d_payB[nw->fslot];
+    A.So.kscr = t->d_keysC; A.So.pscr = t->d_payC; A.So.fs = fs;
+    A.So.split = t->d_split + nw->fslot * BK_BUCKETS; A.So.passes = (3 * t->tp.D + 7) / 8; A.So.parity = nw->fslot;
+    A.gSo = BK_BUCKETS;
+  }
+  const int grid = A.gS + A.gV + A.gE + A.gSo;
+  if (grid > 0) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(FRAME_THREADS); cfg.dynamicSmemBytes = FRAME_SMEM;
+    cfg.stream = t->pipe[2];
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    OSL_CUDA(cudaLaunchKernelEx(&cfg, k_frame, A));
+    OSL_LAUNCHED(1);
+  }
+  t->fz_v = t->fz_s;
+  if (nw) t->fz_s = *nw; else t->fz_s.valid = 0;
+  return OSL_OK;
+}
+
+// Issue the launches that carry the remaining stages of the frames enqueued so far (at most two).
+osl_status osl_fused_flush(osl_svo* t) {
+  while (t->fz_s.valid || t->fz_v.valid) {
+    osl_status rc = fused_launch(t, nullptr, nullptr);
+    if (rc) return rc;
+  }
+  return OSL_OK;
+}
+
+osl_status osl_run_integrate(osl_svo* t, EmitParams& ep, const void* colors, cudaStream_t st, const HostFrame* host) {
   const int n = ep.n;
   const int D = t->tp.D;
+  const bool inputs_on_front = host != nullptr;
   if (n < 0) return OSL_ERR_INVALID;
   if (t->sticky_error) return t->sticky_error;
   osl_status rc = OSL_OK;
@@ -1439,27 +1689,12 @@ osl_status osl_run_integrate(osl_svo* t, EmitParams& ep, const void* colors, cud
   const unsigned long long f = t->seq;
   const int fslot = (int)(f % OSL_FRONT), bslot = (int)(f % OSL_BACK);
   const bool piped = t->pipeline || inputs_on_front;
-  cudaStream_t sE = piped ? t->pipe[0] : st, sSo = piped ? t->pipe[1] : st, sS = piped ? t->pipe[2] : st,
-               sV = piped ? t->pipe[3] : st;
-  if (f > 0 && (piped != (t->last_piped != 0) || (!piped && st != t->last_stream))) {
-    // mode (or stream) switch: the previous frame must be complete before anything of this one starts
-    cudaEvent_t prev = t->ring_ev[(f - 1) % OSL_RING];
-    OSL_CUDA(cudaStreamWaitEvent(sE, prev, 0));
-    if (piped) {
-      OSL_CUDA(cudaStreamWaitEvent(sSo, prev, 0));
-      OSL_CUDA(cudaStreamWaitEvent(sS, prev, 0));
-      OSL_CUDA(cudaStreamWaitEvent(sV, prev, 0));
-    }
-  }
   if (piped && !t->counted_piped) {  // trees that pipeline share the device: the CTA budget is split between them
     t->counted_piped = 1;
     g_osl_piped_trees++;
   }
-  const int sharers = 3 * (g_osl_piped_trees > 0 ? g_osl_piped_trees : 1);
-  const int coop_cap = piped ? (t->num_sms / sharers > 0 ? t->num_sms / sharers : 1) : 0x7FFFFFFF;
+  const int trees = g_osl_piped_trees > 0 ? g_osl_piped_trees : 1;
   const int passes = (3 * D + 7) / 8;
-  u64* skeys = (passes & 1) ? t->d_keysB[fslot] : t->d_keysA[fslot];
-  u32* spay = (passes & 1) ? t->d_payB[fslot] : t->d_payA[fslot];
   bool use_bucket = false;
   // expected number of sorted entries / widest level, from the last completed frame (grid sizing only: every
   // kernel is grid-stride, a wrong guess costs time, not correctness)
@@ -1473,10 +1708,116 @@ osl_status osl_run_integrate(osl_svo* t, EmitParams& ep, const void* colors, cud
     // small key list and splitters of frame f - OSL_FRONT in place -> barrier-free bucket sort
     use_bucket = f >= OSL_FRONT && exp_emit <= (long long)BK_BUCKETS * BK_CAP / 2 && !t->force_grid_sort;
   }
+  // k_frame path (one launch per frame): pipelined depth frames with a host pose once the bucket sort applies.  Its
+  // spinning roles may hold at most 2 CTAs per SM in total over all pipelining trees of the process.
+  const int spin_cap = (2 * t->num_sms / trees - BK_BUCKETS) / 2;
+  const bool fused = piped && t->fused_enabled && ep.mode == 0 && !ep.M_dev && n > 0 && use_bucket && spin_cap >= 8;
+  if (f > 0 && fused != (t->last_fused != 0)) {
+    // Path switch (the first frames of a stream run as four kernels until splitters and size hints exist; a scene
+    // of another mode, a tracked frame): the two paths order their stages and recycle their slots differently, so the
+    // pipeline is drained in between.  Rare, and it makes every cross-path hazard vanish.
+    rc = osl_poll_results(t, true);
+    if (rc) return rc;
+    rc = drain_streams(t, st);
+    if (rc) return rc;
+  }
+  cudaStream_t sE = piped ? t->pipe[0] : st, sSo = piped ? t->pipe[1] : st, sS = piped ? t->pipe[2] : st,
+               sV = piped ? t->pipe[3] : st;
+  if (fused) sE = sSo = sV = sS;
+  if (f > 0 && !fused && (piped != (t->last_piped != 0) || (!piped && st != t->last_stream))) {
+    // mode (or stream) switch: the previous frame must be complete before anything of this one starts
+    cudaEvent_t prev = t->ring_ev[(f - 1) % OSL_RING];
+    OSL_CUDA(cudaStreamWaitEvent(sE, prev, 0));
+    if (piped) {
+      OSL_CUDA(cudaStreamWaitEvent(sSo, prev, 0));
+      OSL_CUDA(cudaStreamWaitEvent(sS, prev, 0));
+      OSL_CUDA(cudaStreamWaitEvent(sV, prev, 0));
+    }
+  }
+  const int sharers = 3 * trees;
+  const int coop_cap = piped ? (t->num_sms / sharers > 0 ? t->num_sms / sharers : 1) : 0x7FFFFFFF;
+  u64* skeys = (passes & 1) ? t->d_keysB[fslot] : t->d_keysA[fslot];
+  u32* spay = (passes & 1) ? t->d_payB[fslot] : t->d_payA[fslot];
   if (use_bucket) { skeys = t->d_keysB[fslot]; spay = t->d_payB[fslot]; }
   FrameState* fs = t->d_fs;              // persistent part
   FrameState* fr = t->d_fs + 1 + bslot;  // this frame's result block
   const LevelArrays& lv = t->lv[bslot];
+
+  // Host frames: the planes go through one of OSL_STAGES device slots on the copy stream, so that the transfer of
+  // frame f+1 overlaps the kernels of frame f.  Four-kernel path: events in both directions (slot free <- k_levels,
+  // k_emit <- copies).  k_frame path: no events at all -- the host recycles a slot once the frame that used it has
+  // reported completion in its pinned result block, and a 4-byte copy queued behind the planes carries a sequence
+  // number the emit role waits for.
+  const int sslot = (int)(t->stage_seq % OSL_STAGES);
+  if (host) {
+    const size_t np = (size_t)n;
+    if (fused) {
+      while (t->stage_frame[sslot] && t->ring_tail < t->stage_frame[sslot]) {
+        rc = wait_oldest(t);
+        if (rc) return rc;
+      }
+    } else if (t->stage_seq >= OSL_STAGES) {
+      OSL_CUDA(cudaStreamWaitEvent(t->copy_stream, t->stage_free[sslot], 0));
+    }
+    OSL_CUDA(cudaMemcpyAsync(t->d_depth_stage[sslot], host->h_depth, np * 2, cudaMemcpyHostToDevice, t->copy_stream));
+    // Colours: the device reads ONE pixel per observed leaf (the lowest pixel index that maps to it, ~5 % of the frame)
+    // and it knows which only after the sort.  Opt-in (osl_svo_set_quirks bit 2): a PINNED colour plane is not copied,
+    // k_levels gathers the winners' 3 bytes straight from host memory (zero-copy loads under UVA).  That takes 60 % of
+    // the frame's payload off the link, but measured on B200 / PCIe 5 it does not pay (profiles/r02_e2e_zero_copy.md):
+    // ~15 k scattered 32-byte PCIe reads per frame are bound by outstanding-request latency and stretch k_levels, so
+    // the default stages the colour plane with one DMA like the depth plane.
+    const uint8_t* rgb_dev = nullptr;
+    if (t->zero_copy_rgb) {
+      cudaPointerAttributes attr;
+      if (cudaPointerGetAttributes(&attr, host->h_rgb) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
+          attr.devicePointer)
+        rgb_dev = static_cast<const uint8_t*>(attr.devicePointer);
+      else
+        cudaGetLastError();  // (pageable memory is reported as an error by older drivers)
+    }
+    if (!rgb_dev) {
+      OSL_CUDA(cudaMemcpyAsync(t->d_rgb_stage[sslot], host->h_rgb, np * 3, cudaMemcpyHostToDevice, t->copy_stream));
+      rgb_dev = t->d_rgb_stage[sslot];
+    }
+    ep.depth = t->d_depth_stage[sslot]; ep.rgb = rgb_dev;
+    if (fused) {
+      const u32 val = (u32)(t->stage_seq + 1);
+      t->h_ready_vals[t->stage_seq % 64] = val;
+      OSL_CUDA(cudaMemcpyAsync(t->d_ready + sslot, &t->h_ready_vals[t->stage_seq % 64], sizeof(u32),
+                               cudaMemcpyHostToDevice, t->copy_stream));
+      ep.ready = t->d_ready + sslot; ep.ready_seq = val;
+      t->stage_frame[sslot] = f + 1;
+    } else {
+      OSL_CUDA(cudaEventRecord(t->stage_copied[sslot], t->copy_stream));  // k_emit (stream E) waits for it
+    }
+  }
+
+  if (fused) {
+    rc = osl_order_after_readers(t, st, true, sS, sS);
+    if (rc) return rc;
+    const int cap = spin_cap < t->structure_grid ? spin_cap : t->structure_grid;
+    osl_svo::FzStage nw;
+    nw.valid = 1; nw.f = f; nw.n = n; nw.fslot = fslot; nw.bslot = bslot; nw.rgb = ep.rgb;
+    nw.gS = grid_for(exp_emit, AN_THREADS, cap) + 1;  // (+1: the book-keeping CTA usually has no block of its own)
+    if (nw.gS > cap) nw.gS = cap;
+    nw.gV = grid_for(exp_level, LEVEL_THREADS, spin_cap < t->levels_grid ? spin_cap : t->levels_grid);
+    rc = fused_launch(t, &nw, &ep);
+    if (rc) return rc;
+    const int slot = (int)(f % OSL_RING);
+    t->ring_kind[slot] = 1;
+    t->fz_event_valid = 0;
+    t->join_pending = 1;
+    t->ring_headroom[slot] = headroom;
+    t->ring_mode[slot] = ep.mode;
+    t->inflight_headroom += headroom;
+    t->ring_head++;
+    t->seq++;
+    if (host) t->stage_seq++;
+    t->last_stream = st;
+    t->last_piped = 1;
+    t->last_fused = 1;
+    return OSL_OK;
+  }
 
   const bool timing = t->stage_timing && !piped && n > 0;
   if (timing) OSL_CUDA(cudaEventRecord(t->stage_ev[0], st));
@@ -1484,7 +1825,7 @@ osl_status osl_run_integrate(osl_svo* t, EmitParams& ep, const void* colors, cud
     // ---- E: back-projection, keys, tile-local de-duplication
     if (piped && f >= OSL_FRONT)  // the key-list slot was last read by k_structure of frame f - 3
       OSL_CUDA(cudaStreamWaitEvent(sE, t->struct_ev[(f - OSL_FRONT) % OSL_RING], 0));
-    if (inputs_on_front) OSL_CUDA(cudaStreamWaitEvent(sE, t->stage_copied[t->stage_seq % OSL_STAGES], 0));
+    if (inputs_on_front) OSL_CUDA(cudaStreamWaitEvent(sE, t->stage_copied[sslot], 0));
     if (piped && ep.mode == 0 && ep.M_dev) {  // the pose is produced by work queued on the caller's stream
       if (!t->pose_ev) OSL_CUDA(cudaEventCreateWithFlags(&t->pose_ev, cudaEventDisableTiming));
       OSL_CUDA(cudaEventRecord(t->pose_ev, st));
@@ -1545,19 +1886,11 @@ osl_status osl_run_integrate(osl_svo* t, EmitParams& ep, const void* colors, cud
     OSL_CUDA(cudaStreamWaitEvent(sS, t->ring_ev[(f - OSL_BACK) % OSL_RING], 0));
   {
     const int grid = grid_for(exp_emit, AN_THREADS, t->structure_grid < coop_cap ? t->structure_grid : coop_cap);
-    const u64* a0 = skeys; const u64* a0b = t->d_keysB[fslot]; u32* a1 = spay; u32* a2 = t->d_pool;
-    TreeParams a3 = t->tp; FrameState* a4 = fs;
-    FrameState* a4b = fr;
-    uint8_t* a5 = t->d_m; uint8_t* a6 = t->d_s; u32* a6b = t->d_start; u32* a7 = t->d_blockcnt;
-    u32* a8b = t->d_flags; u32 a8c = (u32)(f + 1);
-    LevelArrays a9 = lv; int a10 = ep.mode; int a11 = (int)t->cap_nodes; int a12 = n; int a13 = fslot;
-    u64* a14 = t->d_split + fslot * BK_BUCKETS;
-    FrameState* a4c = &t->h_ring[f % OSL_RING];  // pinned host memory, device-accessible (UVA)
-    void* args[] = {&a0, &a0b, &a1, &a2, &a3, &a4, &a4b, &a4c, &a5, &a6, &a6b, &a7, &a8b, &a8c, &a9, &a10, &a11, &a12,
-                    &a13, &a14};
+    StructArgs A = make_struct_args(t, skeys, spay, fs, fr, f, lv, ep.mode, n, fslot);
+    void* args[] = {&A};
     // (a plain launch was measured to be no faster than the cooperative one, which guarantees the co-residency the
     // flag exchange relies on)
-    OSL_CUDA(cudaLaunchCooperativeKernel((void*)k_structure, dim3(grid), dim3(AN_THREADS), args, 0, sS));
+    OSL_CUDA(cudaLaunchCooperativeKernel((void*)k_structure, dim3(grid), dim3(AN_THREADS), args, STRUCT_SMEM, sS));
     OSL_LAUNCHED(1);
     if (timing) OSL_CUDA(cudaEventRecord(t->stage_ev[3], st));
     if (piped) {
@@ -1568,11 +1901,8 @@ osl_status osl_run_integrate(osl_svo* t, EmitParams& ep, const void* colors, cud
   // ---- V: values, bottom-up
   if (n > 0) {
     const int grid = grid_for(exp_level, LEVEL_THREADS, t->levels_grid < coop_cap ? t->levels_grid : coop_cap);
-    u32* a0 = t->d_pool; LevelArrays a1 = lv; const FrameState* a2 = fr;
-    u32* a2b = t->d_scan_totals + OSL_NCOUNT(OSL_MAXD);  // arrival counter of the one-sided barrier (zero at rest)
-    int a3 = D; int a4 = ep.mode;
-    const uint8_t* a5 = ep.rgb; const float* a6 = (const float*)colors;
-    void* args[] = {&a0, &a1, &a2, &a2b, &a3, &a4, &a5, &a6};
+    LevelArgs A = make_level_args(t, lv, fr, f, ep.mode, ep.rgb, (const float*)colors);
+    void* args[] = {&A};
     OSL_CUDA(cudaLaunchCooperativeKernel((void*)k_levels, dim3(grid), dim3(LEVEL_THREADS), args, LEVEL_SMEM, sV));
     OSL_LAUNCHED(1);
   }
@@ -1581,6 +1911,11 @@ osl_status osl_run_integrate(osl_svo* t, EmitParams& ep, const void* colors, cud
   // after this event (the caller never waits for it unless it asks for sizes / counters)
   const int slot = (int)(f % OSL_RING);
   OSL_CUDA(cudaEventRecord(t->ring_ev[slot], sV));
+  if (host) {
+    OSL_CUDA(cudaEventRecord(t->stage_free[sslot], sV));  // the colours are last read by k_levels
+    t->stage_seq++;
+  }
+  t->ring_kind[slot] = 0;
   t->join_pending = piped ? 1 : 0;  // other streams are ordered after the pipeline by osl_svo_join (lazily)
   t->ring_headroom[slot] = headroom;
   t->ring_mode[slot] = ep.mode;
@@ -1589,6 +1924,7 @@ osl_status osl_run_integrate(osl_svo* t, EmitParams& ep, const void* colors, cud
   t->seq++;
   t->last_stream = st;
   t->last_piped = piped ? 1 : 0;
+  t->last_fused = 0;
   return OSL_OK;
 }
 
@@ -1637,6 +1973,12 @@ static osl_status osl_order_after_readers(osl_svo* t, cudaStream_t st, bool pipe
 // stream-ordered; pipelined frames complete on an internal stream.
 osl_status osl_join(osl_svo* t, cudaStream_t st) {
   if (t->seq == 0) return OSL_OK;
+  if (t->last_fused && !t->fz_event_valid) {  // k_frame path: issue the remaining stages, then mark the end of the frame
+    osl_status rc = osl_fused_flush(t);
+    if (rc) return rc;
+    OSL_CUDA(cudaEventRecord(t->ring_ev[(t->seq - 1) % OSL_RING], t->pipe[2]));
+    t->fz_event_valid = 1;
+  }
   if (t->join_pending || st != t->last_stream)
     OSL_CUDA(cudaStreamWaitEvent(st, t->ring_ev[(t->seq - 1) % OSL_RING], 0));
   return OSL_OK;

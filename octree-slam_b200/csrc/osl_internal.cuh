@@ -29,6 +29,7 @@ struct FrameState {
   int acc_valid[OSL_FRONT];  // [key-list slot] accumulated by k_emit (atomicAdd), consumed and zeroed by k_structure
   int acc_emit[OSL_FRONT];   // [key-list slot] entries k_emit appended to the key list
   int acc_unsorted[OSL_FRONT];  // [key-list slot] voxel path: the inputs are NOT (sorted and all valid)
+  int acc_tiles[OSL_FRONT];  // [key-list slot] k_frame: emit CTAs that have appended their entries (the sort role waits)
   int n_in;         // inputs
   int n_valid;      // V  (inputs with a valid key)
   int n_emit;       // entries sorted (modes 0/1: after the tile-local de-duplication; mode 2: == n_valid)
@@ -40,6 +41,7 @@ struct FrameState {
   int capacity;     // nodes
   int cur_size;     // nodes in the pool (persistent across frames; 0 = fresh tree)
   int frame_seq;    // frames processed
+  int done_flag;    // (pinned host copy only) frame number + 1, stored by the value stage when the frame is complete
   int n_level[OSL_MAXD + 2];                  // n_level[d] = distinct touched nodes at depth d (d = 1..D)
   int pass_count[OSL_MAXD + 1];               // |codes[i]| of reference pass i
   int base[(OSL_MAXD + 1) * (OSL_MAXD + 1)];  // base[s*(D+1)+d]: first global split rank of bucket (frontier s, depth d)
@@ -192,6 +194,14 @@ struct osl_svo {
   // (each new reader's stream first waits for the previous state of the event, then re-records it); streams joined
   // by osl_svo_join are recorded lazily, when the next integrate is enqueued (osl_order_after_readers).
   cudaEvent_t reader_ev; int reader_pending;
+  // k_frame pipeline (one launch per frame on pipe[2]): the frames whose structure / value stage the next launch
+  // carries; completion is read from the pinned result block (FrameState::done_flag), not from events
+  struct FzStage { int valid; unsigned long long f; int n, fslot, bslot, gS, gV; const uint8_t* rgb; } fz_s, fz_v;
+  int last_fused, fused_enabled;
+  int ring_kind[OSL_RING];               // 0: completion = ring_ev, 1: completion = done_flag of the pinned block
+  int fz_event_valid;                    // ring_ev of the last frame has been recorded behind the flushed pipeline
+  u32* d_ready; u32* h_ready_vals;       // host frames: per staging slot, the sequence number its copies carry
+  unsigned long long stage_frame[OSL_STAGES];  // frame number + 1 that last used the staging slot (k_frame path)
   cudaStream_t foreign_reader[8]; int foreign_n;
   int stage_timing, stage_valid;         // per-kernel CUDA-event timing of non-pipelined frames (bench / profiling)
   cudaEvent_t stage_ev[5];
@@ -230,8 +240,11 @@ struct EmitParams {
   int tiles_x, tiles_y;                                                             // mode 0: 64x32-pixel tiles
   const float* pts; int stride;                                                      // mode 1 (vec3) / 2 (vec4)
   int n; int mode;
+  const u32* ready; u32 ready_seq;  // k_frame, host frames: *ready == ready_seq once the staging copies have landed
 };
-osl_status osl_run_integrate(osl_svo* t, EmitParams& ep, const void* colors, cudaStream_t st, bool inputs_on_front);
+struct HostFrame { const uint16_t* h_depth; const uint8_t* h_rgb; };  // osl_integrate_depth_host: planes to stage
+osl_status osl_run_integrate(osl_svo* t, EmitParams& ep, const void* colors, cudaStream_t st, const HostFrame* host);
+osl_status osl_fused_flush(osl_svo* t);
 osl_status osl_integrate_init(osl_svo* t);
 osl_status osl_ensure_workspace(osl_svo* t, size_t n);
 int osl_sort_occupancy();  // co-resident k_sort CTAs per SM

@@ -35,7 +35,7 @@ class SVO:
     """One GPU-resident sparse voxel octree (the reference's OctreeNode::gpu_data_ / gpu_size_)."""
 
     def __init__(self, center=(0.0, 0.0, 0.0), half_edge=1.0, max_depth=8, reserve_nodes=0, device=0,
-                 quirks=True, force_grid_sort=False, zero_copy=False):
+                 quirks=True, force_grid_sort=False, zero_copy=False, fused=True):
         self.center = tuple(float(c) for c in center)
         self.half_edge = float(np.float32(half_edge))
         self.max_depth = int(max_depth)
@@ -48,9 +48,9 @@ class SVO:
         # library's own streams: the input buffers of the last 2 * 8 calls stay referenced, so that torch's caching
         # allocator cannot hand a block a queued kernel still reads to a later copy
         self._keep = collections.deque(maxlen=16)
-        if not quirks or force_grid_sort or zero_copy:
+        if not quirks or force_grid_sort or zero_copy or not fused:
             _check(lib().osl_svo_set_quirks(self._h, int(bool(quirks)) | (2 if force_grid_sort else 0) |
-                                            (4 if zero_copy else 0)),
+                                            (4 if zero_copy else 0) | (0 if fused else 8)),
                    "osl_svo_set_quirks")
 
     def set_pipeline(self, enabled=True):

@@ -83,7 +83,16 @@ def test_cfg1_frame_and_raycast_match_unmodified_reference(P):
             img = svo.raycast(W, H, 45.0, view)
             want, _ = ref.raycast(W, H, 45.0, view)
             assert np.array_equal(img, want), "%d pixels differ" % np.count_nonzero(np.any(img != want, axis=2))
-        assert np.count_nonzero(svo.raycast(W, H, 45.0, LOOK_PLUS_Z)[..., :3]) > W * H  # the scene is in view
+    # after two observations alpha is 131: no sample terminates a ray early (Q8) and the picture is nearly black.  A map
+    # observed 64 more times (alpha saturated) gives the renderer something to show; same comparison
+    svo.load(a2)
+    for _ in range(64):
+        svo.integrate_depth(depth, rgb, fx, fy)
+    ref.load(svo.pool())
+    img = svo.raycast(W, H, 45.0, LOOK_PLUS_Z)
+    want, _ = ref.raycast(W, H, 45.0, LOOK_PLUS_Z)
+    assert np.array_equal(img, want), "%d pixels differ" % np.count_nonzero(np.any(img != want, axis=2))
+    assert np.count_nonzero(img[..., :3].any(axis=2)) > W * H // 2  # the scene is in view
 
 
 def test_bench_map_raycast_matches_reference_at_bench_sizes(P):

@@ -138,3 +138,71 @@ def test_upload_rejects_corrupt_child_pointers(P):
         assert other.size == 0  # an empty, valid tree is left behind
     other.load(good)
     assert np.array_equal(other.raycast(64, 48), svo.raycast(64, 48))
+
+
+@pytest.mark.parametrize("host_frames", [False, True])
+@pytest.mark.parametrize("D", [8, 16])
+def test_one_launch_per_frame_pipeline_matches_oracle(P, D, host_frames):
+    """k_frame (one launch per frame: emit+sort of frame f, structure of f-1, values of f-2 as roles of one grid, chained
+    by programmatic dependent launch) against the oracle AND against the same frames run as four kernels: pools
+    bit-identical after every few frames, with a raycast, a size query and a scene cut in between (each of them drains
+    or flushes the pipeline at a different depth)."""
+    import torch
+    w, h, n = 320, 240, 24
+    center, half = P.synth.tree_params(D)
+    fx, fy = P.synth.focal(w, h)
+    fused = P.SVO(center, half, D, reserve_nodes=1 << 22).set_pipeline(True)
+    plain = P.SVO(center, half, D, reserve_nodes=1 << 22, fused=False).set_pipeline(True)
+    ref = orc.OracleSVO(center, half, D)
+    l0 = P.lib().osl_launch_count()
+    keep = []
+    for k in range(n):
+        pose = P.synth.orbit_pose(4 * k if k < 16 else 400 + 4 * k)  # scene cut at frame 16: the splitters go stale
+        depth, rgb = P.synth.make_frame(w, h, pose, seed=k)
+        ref.integrate_depth(depth, rgb, fx, fy, pose)
+        for svo in (fused, plain):
+            if host_frames:
+                hd, hc = torch.from_numpy(depth).pin_memory(), torch.from_numpy(rgb).pin_memory()
+                keep.append((hd, hc))
+                svo.integrate_depth_host(hd.numpy(), hc.numpy(), fx, fy, pose)
+            else:
+                dd, cc = torch.from_numpy(depth).cuda(), torch.from_numpy(rgb).cuda()
+                keep.append((dd, cc))
+                torch.cuda.synchronize()
+                svo.integrate_depth(dd, cc, fx, fy, pose)
+        if k in (5, 11, 12, 19):  # 12 right after 11: a flush with a single frame in the pipeline
+            want = ref.pool()
+            assert fused.size == ref.size and plain.size == ref.size
+            assert np.array_equal(fused.pool(), want), "k_frame pipeline differs from the oracle after frame %d" % k
+            assert np.array_equal(plain.pool(), want)
+        if k == 8:
+            img = fused.raycast(96, 72, 45.0, view_for_pose(pose))
+            assert np.array_equal(img, ref.raycast(96, 72, 45.0, view_for_pose(pose)))
+    assert np.array_equal(fused.pool(), ref.pool())
+    assert np.array_equal(plain.pool(), ref.pool())
+    c = fused.counters()
+    assert c.frames == n and c.n_nodes == ref.size
+    assert P.lib().osl_launch_count() > l0
+
+
+def test_one_launch_per_frame_is_really_one_launch(P):
+    """steady state of the pipelined path: one kernel launch per frame (+ two to drain)"""
+    import torch
+    D, w, h = 12, 320, 240
+    center, half = P.synth.tree_params(D)
+    fx, fy = P.synth.focal(w, h)
+    svo = P.SVO(center, half, D, reserve_nodes=1 << 22).set_pipeline(True)
+    frames = []
+    for k in range(40):
+        pose = P.synth.orbit_pose(2 * k)
+        depth, rgb = P.synth.make_frame(w, h, pose, seed=k)
+        frames.append((torch.from_numpy(depth).cuda(), torch.from_numpy(rgb).cuda(), pose))
+    torch.cuda.synchronize()
+    for d, c, pose in frames[:10]:
+        svo.integrate_depth(d, c, fx, fy, pose)
+    svo.sync()
+    l0 = P.lib().osl_launch_count()
+    for d, c, pose in frames[10:]:
+        svo.integrate_depth(d, c, fx, fy, pose)
+    svo.sync()
+    assert P.lib().osl_launch_count() - l0 == 30 + 2
