@@ -18,6 +18,7 @@ static osl_status drain(osl_svo* t) {
 static osl_status set_device_size(osl_svo* t, int size) {
   // FrameState::cur_size lives on the device (frames are planned there without a host round trip)
   OSL_CUDA(cudaMemcpy(&t->d_fs->cur_size, &size, sizeof(int), cudaMemcpyHostToDevice));
+  if (t->d_wcache) OSL_CUDA(cudaMemset(t->d_wcache, 0xFF, 4096 * sizeof(u64)));  // node indices / depths change meaning
   t->size = size;
   return OSL_OK;
 }
@@ -157,7 +158,7 @@ void osl_svo_destroy(osl_svo* t) {
   for (int i = 0; i < 4; i++)
     if (t->pipe[i]) cudaStreamDestroy(t->pipe[i]);
   cudaFree(t->d_m); cudaFree(t->d_s); cudaFree(t->d_blockcnt);
-  cudaFree(t->d_keysC); cudaFree(t->d_payC); cudaFree(t->d_split); cudaFree(t->d_start); cudaFree(t->d_flags);
+  cudaFree(t->d_keysC); cudaFree(t->d_payC); cudaFree(t->d_split); cudaFree(t->d_wcache); cudaFree(t->d_start); cudaFree(t->d_flags);
   cudaFree(t->d_scan_totals); cudaFree(t->d_fs);
   cudaFree(t->ex_kA); cudaFree(t->ex_kB); cudaFree(t->ex_nA); cudaFree(t->ex_nB); cudaFree(t->ex_status); cudaFree(t->ex_cnt);
   for (int i = 0; i < OSL_STAGES; i++) {
@@ -285,6 +286,10 @@ osl_status osl_integrate_depth_posed(osl_svo* t, const uint16_t* d_depth, const 
 
 static osl_status ensure_stage(osl_svo* t, size_t n) {
   if (n <= t->stage_cap) return OSL_OK;
+  {  // frames in flight read the slots (the k_frame path also has stages that are not even launched yet)
+    osl_status prc = osl_poll_results(t, true);
+    if (prc) return prc;
+  }
   OSL_CUDA(cudaDeviceSynchronize());
   for (int i = 0; i < OSL_STAGES; i++) {
     cudaFree(t->d_depth_stage[i]); cudaFree(t->d_rgb_stage[i]);

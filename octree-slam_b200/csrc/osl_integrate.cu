@@ -17,6 +17,7 @@
 // streams (osl_run_integrate).  The host never waits for the device unless the pool has to grow, the caller asks for
 // sizes / counters, or it runs more than 3 frames ahead.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "osl_internal.cuh"
@@ -653,10 +654,29 @@ __device__ __forceinline__ int key_digit(u64 key, int D, int d) { return (int)((
 // Walk the PRE-FRAME tree along `key` (splitKeys, svo.cu:108-142).  Returns the frontier depth s: the depth of the
 // first node on the path without the has-children flag, OSL_NONE if the path exists down to the leaf's parent.
 // Q3 (svo.cu:123 `>= 15`): when the last digit is 7 the reference also tests the LEAF and reports it for splitting.
+// Walk cache: a direct-mapped table (prefix of WC_H digits -> node at depth WC_H), one 64-bit word per entry
+// ((prefix << 30) | node: written and read atomically).  A node, once allocated, keeps its index and its ancestors
+// keep their has-children flags for the life of the tree, so an entry can never go stale (the host clears the table
+// when the pool is replaced: reset / upload / expand).  A hit replaces WC_H dependent loads from the root by one.
+#define WC_SLOTS 4096
+__device__ __forceinline__ int walk_cache_depth(int D) { const int h = D - 5 < 11 ? D - 5 : 11; return h >= 3 ? h : 0; }
+__device__ __forceinline__ u32 walk_cache_slot(u64 prefix) { return (u32)((prefix * 0x9E3779B97F4A7C15ull) >> 52); }
+
 __device__ __forceinline__ int walk_frontier(const u32* __restrict__ pool, u64 key, int D, int quirks, int m,
-                                             u32& start) {
+                                             u32& start, u64* wcache) {
   u32 node = (u32)key_digit(key, D, 1);
-  for (int t = 1; t <= D - 1; t++) {
+  int t = 1;
+  const int h = wcache ? walk_cache_depth(D) : 0;
+  u64 prefix = 0;
+  bool fill = false;
+  if (h && m + 1 >= h) {  // (the node at depth m+1, which phase C needs, lies at or below the cached depth)
+    prefix = key >> (3 * (D - h));
+    const u64 e = __ldcg(&wcache[walk_cache_slot(prefix)]);
+    if ((e >> 30) == prefix) { node = (u32)e & OSL_MASK; t = h; }
+    else fill = true;
+  }
+  for (; t <= D - 1; t++) {
+    if (fill && t == h) wcache[walk_cache_slot(prefix)] = (prefix << 30) | (u64)node;
     if (t == m + 1) start = node;  // the first node this key heads: where phase C resumes the walk
     const u32 w0 = pool[2 * (size_t)node];
     if (!(w0 & OSL_FLAG)) return t;
@@ -685,7 +705,7 @@ __device__ __forceinline__ int walk_frontier(const u32* __restrict__ pool, u64 k
 __device__ __forceinline__ void analyze_block(int vb, int n, const u64* __restrict__ keys, u32* pay, int mode,
                                               const u32* pool, const TreeParams& tp, uint8_t* __restrict__ m8,
                                               uint8_t* __restrict__ s8, u32* __restrict__ start,
-                                              u32* s_ctot, u32* s_cnt) {
+                                              u32* s_ctot, u32* s_cnt, u64* wcache) {
   const int D = tp.D, NC = OSL_NCOUNT(D);
   for (int c = threadIdx.x; c < NC; c += AN_THREADS) s_cnt[c] = 0;
   __syncthreads();
@@ -705,7 +725,7 @@ __device__ __forceinline__ void analyze_block(int vb, int n, const u64* __restri
         pay[j] = pm;
       }
       u32 st = 0;
-      s = walk_frontier(pool, k, D, tp.quirks, m, st);
+      s = walk_frontier(pool, k, D, tp.quirks, m, st, wcache);
       start[j] = st;
       atomicAdd(&s_cnt[OSL_CLVL(D, m + 1)], 1u);  // heads every level d > m
       if (s != OSL_NONE) {
@@ -756,13 +776,18 @@ __device__ __forceinline__ void assign_block(int vb, int n, const u64* __restric
   // pass 1: per-warp totals of every counter this block can touch
   for (int c = lane; c < NC; c += 32) s_w[warp][c] = 0;
   __syncwarp();
+  // (steady state: the whole path of every key exists -- no lane of the warp splits anything and the per-bucket
+  // collectives, three match_any per level, are skipped)
+  const bool any_split = __any_sync(FULL, unique && s != OSL_NONE);
   for (int d = d0; d <= D; d++) {
     const bool f = unique && m < d;
     const u32 bal = __ballot_sync(FULL, f);
     if (lane == 0) s_w[warp][OSL_CLVL(D, d)] = __popc(bal);
-    const bool sp = f && s != OSL_NONE && s <= d && (d <= D - 1 || s == D);
-    const u32 peers = __match_any_sync(FULL, sp ? s : 0);
-    if (sp && lane == __ffs(peers) - 1) s_w[warp][OSL_CBKT(D, s, d)] = __popc(peers);
+    if (any_split) {
+      const bool sp = f && s != OSL_NONE && s <= d && (d <= D - 1 || s == D);
+      const u32 peers = __match_any_sync(FULL, sp ? s : 0);
+      if (sp && lane == __ffs(peers) - 1) s_w[warp][OSL_CBKT(D, s, d)] = __popc(peers);
+    }
   }
   __syncthreads();
   // exclusive scan over the warps + the block's global base + the bucket's global rank base
@@ -795,11 +820,15 @@ __device__ __forceinline__ void assign_block(int vb, int n, const u64* __restric
   for (int d = d0; d <= D; d++) {
     const bool f = unique && m < d;
     const u32 bal = __ballot_sync(FULL, f);
-    const bool sp = f && s != OSL_NONE && s <= d && (d <= D - 1 || s == D);
-    const u32 peers = __match_any_sync(FULL, sp ? s : 0);
-    // same frontier depth among ALL unique keys of the warp (heads or not), for the parent-tile rank below
-    const u32 same_s = __match_any_sync(FULL, unique ? s : 0x100 + lane);
-    const u32 spmask = __ballot_sync(FULL, sp);
+    bool sp = false;
+    u32 peers = 0, same_s = 0, spmask = 0;
+    if (any_split) {
+      sp = f && s != OSL_NONE && s <= d && (d <= D - 1 || s == D);
+      peers = __match_any_sync(FULL, sp ? s : 0);
+      // same frontier depth among ALL unique keys of the warp (heads or not), for the parent-tile rank below
+      same_s = __match_any_sync(FULL, unique ? s : 0x100 + lane);
+      spmask = __ballot_sync(FULL, sp);
+    }
     u32 self = 0;
     if (f) self = (d == m + 1 && m < s_eff) ? node : path_tile + (u32)key_digit(k, D, d);
     u32 ct = 0xFFFFFFFFu;
@@ -844,6 +873,7 @@ struct StructArgs {
   const u64* keys_sorted; const u64* keys_dense; u32* pay; u32* pool; TreeParams tp;
   FrameState* fs; FrameState* fr; FrameState* hr; uint8_t* m8; uint8_t* s8; u32* start; u32* ctatot;
   u32* flags; u32 epoch; LevelArrays lv; int mode; int capacity; int n_in; int parity; u64* split_out;
+  u64* wcache;  // walk cache (NULL = off)
 };
 #define STRUCT_SMEM ((AN_WARPS + 4) * NC_MAX * 4 + AN_WARPS * 4)
 
@@ -886,7 +916,7 @@ __device__ __forceinline__ void structure_body(const StructArgs& A, int bid, int
   // leave its path -- was measured at 50 M keys: 3.5 ms against 3.2 ms for these independent walks; with 4 CTAs per
   // SM the walk latency is already hidden and the extra serial step only adds two block barriers per block.)
   for (int vb = vb0; vb < vb1; vb++)
-    analyze_block(vb, n, keys, pay, mode, pool, tp, m8, s8, start, s_ctot, &s_w[0][0]);
+    analyze_block(vb, n, keys, pay, mode, pool, tp, m8, s8, start, s_ctot, &s_w[0][0], A.wcache);
   // publish this CTA's counter vector behind an epoch flag (every CTA publishes, also one without blocks)
   for (int c = tid; c < NC; c += AN_THREADS) ctatot[(size_t)bid * NC + c] = s_ctot[c];
   __syncthreads();
@@ -1388,8 +1418,13 @@ osl_status osl_integrate_init(osl_svo* t) {
   OSL_CUDA(cudaFuncSetAttribute((const void*)k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, EMIT_SMEM));
   OSL_CUDA(cudaFuncSetAttribute((const void*)k_levels, cudaFuncAttributeMaxDynamicSharedMemorySize, LEVEL_SMEM));
   OSL_CUDA(cudaFuncSetAttribute((const void*)k_structure, cudaFuncAttributeMaxDynamicSharedMemorySize, STRUCT_SMEM));
+  OSL_CUDA(cudaFuncSetAttribute((const void*)k_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, FRAME_SMEM));
   OSL_CUDA(cudaFuncSetAttribute((const void*)k_sort_bucket, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM));
   OSL_CUDA(cudaMalloc(&t->d_split, OSL_FRONT * BK_BUCKETS * sizeof(u64)));
+  if (!getenv("OSL_NO_WALK_CACHE")) {
+    OSL_CUDA(cudaMalloc(&t->d_wcache, WC_SLOTS * sizeof(u64)));
+    OSL_CUDA(cudaMemset(t->d_wcache, 0xFF, WC_SLOTS * sizeof(u64)));
+  }
   return osl_reset_splitters(t);
 }
 
@@ -1455,6 +1490,7 @@ static StructArgs make_struct_args(osl_svo* t, const u64* skeys, u32* spay, Fram
   A.m8 = t->d_m; A.s8 = t->d_s; A.start = t->d_start; A.ctatot = t->d_blockcnt; A.flags = t->d_flags;
   A.epoch = (u32)(f + 1); A.lv = lv; A.mode = mode; A.capacity = (int)t->cap_nodes; A.n_in = n; A.parity = fslot;
   A.split_out = t->d_split + fslot * BK_BUCKETS;
+  A.wcache = t->d_wcache;
   return A;
 }
 

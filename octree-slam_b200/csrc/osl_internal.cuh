@@ -163,6 +163,7 @@ struct osl_svo {
   u32 *d_payA[OSL_FRONT], *d_payB[OSL_FRONT];
   u64* d_keysC; u32* d_payC;   // k_sort_bucket slow-path scratch
   u64* d_split;                // [OSL_FRONT][BK_BUCKETS] splitters written by k_structure of frame f (set f % OSL_FRONT)
+  u64* d_wcache;               // k_structure's walk cache (prefix -> node at a fixed depth); cleared when the pool is replaced
   int force_grid_sort;         // testing: always use the cooperative grid sort
   int zero_copy_rgb;           // measurement: osl_integrate_depth_host reads pinned colour planes in place
   uint8_t *d_m, *d_s;
