@@ -272,6 +272,10 @@ int osl_frame_result_bytes(void);
 /* Profiling aid: SM-clock checkpoints written by CTA 0 of the last k_emit / k_sort_bucket / k_structure / k_levels
  * launches (indices documented in tools/phase_profile.py).  Synchronizes the device. */
 osl_status osl_debug_profile(unsigned long long* out, int n);
+/* Profiling aid: enable = 1 clears the table and records, for the next k_frame launches of `t` (round-robin over 32
+ * slots), the [min start, max end] %globaltimer nanoseconds of each role: 0 structure, 1 values, 2 emit, 3 sort,
+ * 4 CTA arrival before the grid dependency wait.  out (may be NULL) receives 32 x 5 x 2 values.  Synchronizes. */
+osl_status osl_debug_trace(osl_svo* t, int enable, unsigned long long* out);
 /* number of kernels this library has launched in this process (for bench.py's gpu_launches) */
 int64_t osl_launch_count(void);
 

@@ -1056,8 +1056,10 @@ __global__ void __launch_bounds__(AN_THREADS, 3) k_structure(StructArgs A) {
 // of ALL remaining levels at once (independent loads) and folds them bottom-up in shared memory, block barriers
 // while a level is wider than a warp, warp barriers above that.
 #define LEVEL_THREADS 512
-#define LEVEL_NARROW 1024
-#define LEVEL_STAGE 2048
+#define LEVEL_NARROW 512
+#ifndef LEVEL_STAGE
+#define LEVEL_STAGE 1024
+#endif
 #define LEVEL_SMEM (LEVEL_STAGE * (32 + 4 + 4 + 2 + 2) + 64 + 256)
 
 __device__ __forceinline__ void level_leaf(u32* pool, const LevelArrays& lv, int D, int idx, int mode,
@@ -1300,9 +1302,26 @@ struct EmitArgs {
 struct FrameArgs {
   StructArgs S; LevelArgs V; EmitArgs E; SortArgs So;
   int gS, gV, gE, gSo;
+  int trace;  // >= 0: record the time span of every role of this launch in g_osl_span[trace] (tools/frame_timeline.py)
 };
+
+// tracing aid: [launch slot][0 structure, 1 values, 2 emit, 3 sort, 4 CTA arrival (before griddepcontrol.wait)][min
+// start, max end] in %globaltimer nanoseconds
+#define OSL_SPAN_SLOTS 32
+__device__ unsigned long long g_osl_span[OSL_SPAN_SLOTS][5][2];
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void span_mark(int slot, int role, bool end) {
+  if (slot < 0 || threadIdx.x != 0) return;
+  const unsigned long long t = global_ns();
+  if (end) atomicMax(&g_osl_span[slot][role][1], t); else atomicMin(&g_osl_span[slot][role][0], t);
+}
 #define FRAME_THREADS 512
-#define FRAME_SMEM LEVEL_SMEM
+constexpr int osl_max4(int a, int b, int c, int d) { return (a > b ? a : b) > (c > d ? c : d) ? (a > b ? a : b) : (c > d ? c : d); }
+#define FRAME_SMEM osl_max4(LEVEL_SMEM, EMIT_SMEM, BK_SMEM, STRUCT_SMEM)
 static_assert(FRAME_SMEM >= EMIT_SMEM && FRAME_SMEM >= BK_SMEM && FRAME_SMEM >= STRUCT_SMEM, "k_frame shared memory");
 static_assert(AN_THREADS == FRAME_THREADS && LEVEL_THREADS == FRAME_THREADS && EMIT_THREADS == FRAME_THREADS &&
               BK_THREADS <= FRAME_THREADS, "k_frame role CTAs");
@@ -1319,13 +1338,26 @@ __global__ void __launch_bounds__(FRAME_THREADS, 2) k_frame(const __grid_constan
   // programmatic dependent launch: let the next launch's CTAs take their places now (they wait below until this grid
   // has completed), then wait for the previous launch ourselves
   asm volatile("griddepcontrol.launch_dependents;");
+  span_mark(A.trace, 4, false);
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  span_mark(A.trace, 4, true);
   int b = (int)blockIdx.x;
-  if (b < A.gS) { structure_body(A.S, b, A.gS, s_raw); return; }
+  if (b < A.gS) {
+    span_mark(A.trace, 0, false);
+    structure_body(A.S, b, A.gS, s_raw);
+    span_mark(A.trace, 0, true);
+    return;
+  }
   b -= A.gS;
-  if (b < A.gV) { levels_body(A.V, b, A.gV, s_raw); return; }
+  if (b < A.gV) {
+    span_mark(A.trace, 1, false);
+    levels_body(A.V, b, A.gV, s_raw);
+    span_mark(A.trace, 1, true);
+    return;
+  }
   b -= A.gV;
   if (b < A.gE) {
+    span_mark(A.trace, 2, false);
     if (A.E.p.ready) {  // host frame: the staging copies of this frame (copy engine) have landed
       if (threadIdx.x == 0) spin_until_eq(A.E.p.ready, A.E.p.ready_seq);
       __syncthreads();
@@ -1336,14 +1368,17 @@ __global__ void __launch_bounds__(FRAME_THREADS, 2) k_frame(const __grid_constan
       __threadfence();
       atomicAdd(reinterpret_cast<u32*>(&A.E.fs->acc_tiles[A.E.parity]), 1u);
     }
+    span_mark(A.trace, 2, true);
     return;
   }
   b -= A.gE;
   if (threadIdx.x >= BK_THREADS) return;  // whole warps leave: the barriers below count the remaining ones only
+  span_mark(A.trace, 3, false);
   if (threadIdx.x == 0) spin_until_eq(reinterpret_cast<const u32*>(&A.So.fs->acc_tiles[A.So.parity]), (u32)A.gE);
   __syncthreads();
   bucket_body(A.So.kin, A.So.pin, A.So.kout, A.So.pout, A.So.kscr, A.So.pscr, A.So.fs, A.So.split, A.So.passes,
               A.So.parity, b, s_raw);
+  span_mark(A.trace, 3, true);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -1650,6 +1685,7 @@ static osl_status fused_launch(osl_svo* t, const osl_svo::FzStage* nw, const Emi
     A.gSo = BK_BUCKETS;
   }
   const int grid = A.gS + A.gV + A.gE + A.gSo;
+  A.trace = t->trace_on ? (int)(t->trace_seq++ % OSL_SPAN_SLOTS) : -1;
   if (grid > 0) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -2049,6 +2085,23 @@ osl_status osl_device_sort_pairs(u64* kA, u32* pA, u64* kB, u32* pB, int n, int 
   cudaFree(hist);
   cudaFree(fs);
   OSL_CUDA(e);
+  return OSL_OK;
+}
+
+// Tracing aid (tools/frame_timeline.py): enable = 1 clears the span table and records the role spans of the next
+// k_frame launches of `t` (round-robin over 32 slots); out (optional) receives the table, 32 x 5 x 2 nanosecond values.
+extern "C" osl_status osl_debug_trace(osl_svo* t, int enable, unsigned long long* out) {
+  if (!t) return OSL_ERR_INVALID;
+  OSL_CUDA(cudaDeviceSynchronize());
+  if (out) OSL_CUDA(cudaMemcpyFromSymbol(out, g_osl_span, sizeof(unsigned long long) * OSL_SPAN_SLOTS * 5 * 2));
+  if (enable) {
+    unsigned long long init[OSL_SPAN_SLOTS][5][2];
+    for (int i = 0; i < OSL_SPAN_SLOTS; i++)
+      for (int r = 0; r < 5; r++) { init[i][r][0] = ~0ull; init[i][r][1] = 0ull; }
+    OSL_CUDA(cudaMemcpyToSymbol(g_osl_span, init, sizeof(init)));
+    t->trace_seq = 0;
+  }
+  t->trace_on = enable ? 1 : 0;
   return OSL_OK;
 }
 

@@ -199,6 +199,7 @@ struct osl_svo {
   // carries; completion is read from the pinned result block (FrameState::done_flag), not from events
   struct FzStage { int valid; unsigned long long f; int n, fslot, bslot, gS, gV; const uint8_t* rgb; } fz_s, fz_v;
   int last_fused, fused_enabled;
+  int trace_on; unsigned long long trace_seq;  // osl_debug_trace
   int ring_kind[OSL_RING];               // 0: completion = ring_ev, 1: completion = done_flag of the pinned block
   int fz_event_valid;                    // ring_ev of the last frame has been recorded behind the flushed pipeline
   u32* d_ready; u32* h_ready_vals;       // host frames: per staging slot, the sequence number its copies carry

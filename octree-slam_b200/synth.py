@@ -117,9 +117,11 @@ def icosphere(subdiv=3, radius=0.8, center=(0.0, 0.0, 0.0)):
     return V, np.array(f, dtype=np.int32)
 
 
-def load_obj(path):
-    """Minimal Wavefront OBJ reader (v / f, polygons fan-triangulated like the reference's objUtil, obj.cpp:44-90)."""
-    vs, fs = [], []
+def load_obj(path, with_uv=False):
+    """Minimal Wavefront OBJ reader (v / vt / f, polygons fan-triangulated like the reference's objUtil,
+    obj.cpp:44-90).  with_uv: also returns float32 [nt, 2], the texture coordinate of each triangle's FIRST corner
+    (what the reference's ColorShader samples, voxelization.cu:113-126), or None when the file has none."""
+    vs, vts, fs, fuv = [], [], [], []
     with open(path) as fh:
         for line in fh:
             p = line.split()
@@ -127,9 +129,51 @@ def load_obj(path):
                 continue
             if p[0] == "v":
                 vs.append([float(x) for x in p[1:4]])
+            elif p[0] == "vt":
+                vts.append([float(x) for x in p[1:3]])
             elif p[0] == "f":
-                idx = [int(tok.split("/")[0]) for tok in p[1:]]
+                toks = [tok.split("/") for tok in p[1:]]
+                idx = [int(t[0]) for t in toks]
                 idx = [i - 1 if i > 0 else len(vs) + i for i in idx]
+                uv = [int(t[1]) if len(t) > 1 and t[1] else 0 for t in toks]
+                uv = [i - 1 if i > 0 else (len(vts) + i if i < 0 else -1) for i in uv]
                 for k in range(1, len(idx) - 1):
                     fs.append([idx[0], idx[k], idx[k + 1]])
-    return np.array(vs, dtype=np.float32), np.array(fs, dtype=np.int32)
+                    fuv.append(uv[0])
+    V, T = np.array(vs, dtype=np.float32), np.array(fs, dtype=np.int32)
+    if not with_uv:
+        return V, T
+    if not vts:
+        return V, T, None
+    vt = np.array(vts, dtype=np.float32)
+    fu = np.array(fuv, dtype=np.int64)
+    uv = np.where((fu >= 0)[:, None], vt[np.clip(fu, 0, len(vts) - 1)], 0.0).astype(np.float32)
+    return V, T, uv
+
+
+def load_bmp(path):
+    """24-bit BMP as the reference reads it (scene.cpp:38-62: 54-byte header, BGR bytes, rows as stored, no padding
+    handling) -> float32 [height, width, 3] RGB in [0, 1]."""
+    raw = open(path, "rb").read()
+    w = int.from_bytes(raw[18:22], "little", signed=True)
+    h = int.from_bytes(raw[22:26], "little", signed=True)
+    data = np.frombuffer(raw, dtype=np.uint8, count=3 * w * h, offset=54).reshape(h, w, 3)
+    return (data[..., ::-1].astype(np.float32) / np.float32(255.0))
+
+
+def triangle_colors(uv, tex):
+    """The reference's per-triangle flat colour (ColorShader, voxelization.cu:90-139 + createVoxelGrid :219-236): the
+    texel at the first corner's (u, v) -- int(u * width), int(v * height), clamped here where the reference indexes
+    unchecked -- quantised to 8 bits and returned as byte / 255; no texture coordinates: texel 0; no texture: green.
+    -> float32 [nt, 4] (alpha 0, as the reference leaves it)."""
+    nt = uv.shape[0] if uv is not None else 0
+    out = np.zeros((nt, 4), dtype=np.float32)
+    if tex is None:
+        out[:, 1] = 1.0
+        return out
+    h, w = tex.shape[:2]
+    tx = np.clip((uv[:, 0] * w).astype(np.int64), 0, w - 1)
+    ty = np.clip((uv[:, 1] * h).astype(np.int64), 0, h - 1)
+    c = np.clip(tex[ty, tx], 0.0, 1.0)
+    out[:, :3] = ((c * np.float32(255.0)).astype(np.int64) & 0xFF) / 255.0
+    return out

@@ -1,0 +1,69 @@
+#!/usr/bin/env python
+"""Timeline of the k_frame pipeline on the bench workload (640x480 -> depth 16, resident frames): for a run of
+consecutive launches, when each role's first CTA started and its last CTA ended (%globaltimer, osl_debug_trace).
+    python tools/frame_timeline.py [frames]"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as graft  # noqa: E402
+
+ROLES = ["structure", "values", "emit", "sort", "arrival"]
+
+
+def main():
+    import torch
+    frames = int(sys.argv[1]) if len(sys.argv) > 1 else 24
+    w, h, D = 640, 480, 16
+    pkg = graft.load_package()
+    lib = pkg.lib()
+    center, half = pkg.synth.tree_params(D)
+    fx, fy = pkg.synth.focal(w, h)
+    svo = pkg.SVO(center, half, D, reserve_nodes=1 << 24).set_pipeline(True)
+    keep = []
+    for k in range(40 + frames):
+        pose = pkg.synth.orbit_pose(k)
+        depth, rgb = pkg.synth.make_frame(w, h, pose, seed=k)
+        keep.append((torch.from_numpy(depth).cuda(), torch.from_numpy(rgb).cuda(), pose))
+    torch.cuda.synchronize()
+    for d, c, pose in keep[:40]:
+        svo.integrate_depth(d, c, fx, fy, pose)
+    svo.sync()
+    lib.osl_debug_trace(svo._h, 1, None)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for d, c, pose in keep[40:]:
+        svo.integrate_depth(d, c, fx, fy, pose)
+    svo.join(None)
+    e1.record()
+    svo.sync()
+    out = (C.c_uint64 * (32 * 5 * 2))()
+    lib.osl_debug_trace(svo._h, 0, out)
+    a = np.array(out, dtype=np.uint64).reshape(32, 5, 2).astype(np.float64)
+    n_launch = min(32, frames + 2)
+    t0 = a[:n_launch, :, 0][a[:n_launch, :, 0] < 1e19].min()
+    print("%d frames, %.2f us per frame by CUDA events; times in us since the first CTA" % (frames, e0.elapsed_time(e1) * 1e3 / frames))
+    print("launch  " + "  ".join("%-17s" % r for r in ROLES) + "  launch span   start-to-start")
+    prev = None
+    for i in range(n_launch):
+        cells = []
+        lo, hi = 1e30, 0.0
+        for r in range(5):
+            s, e = a[i, r]
+            if s > 1e19:
+                cells.append("%-17s" % "-")
+                continue
+            cells.append("%7.1f - %7.1f" % ((s - t0) / 1e3, (e - t0) / 1e3))
+            if r < 4:
+                lo, hi = min(lo, s), max(hi, e)
+        gap = "" if prev is None else "%6.1f" % ((lo - prev) / 1e3)
+        print("%4d    %s  %6.1f        %s" % (i, "  ".join(cells), (hi - lo) / 1e3, gap))
+        prev = lo
+
+
+if __name__ == "__main__":
+    main()
