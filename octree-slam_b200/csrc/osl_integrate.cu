@@ -705,8 +705,10 @@ __device__ __forceinline__ int walk_frontier(const u32* __restrict__ pool, u64 k
 __device__ __forceinline__ void analyze_block(int vb, int n, const u64* __restrict__ keys, u32* pay, int mode,
                                               const u32* pool, const TreeParams& tp, uint8_t* __restrict__ m8,
                                               uint8_t* __restrict__ s8, u32* __restrict__ start,
-                                              u32* s_ctot, u32* s_cnt, u64* wcache) {
+                                              u32* s_ctot, u32* s_cnt, u64* wcache, u64& k_out, int& m_out,
+                                              int& s_out, u32& st_out) {
   const int D = tp.D, NC = OSL_NCOUNT(D);
+  k_out = 0; m_out = D; s_out = OSL_NONE; st_out = 0;
   for (int c = threadIdx.x; c < NC; c += AN_THREADS) s_cnt[c] = 0;
   __syncthreads();
   const int j = vb * AN_THREADS + threadIdx.x;
@@ -727,6 +729,7 @@ __device__ __forceinline__ void analyze_block(int vb, int n, const u64* __restri
       u32 st = 0;
       s = walk_frontier(pool, k, D, tp.quirks, m, st, wcache);
       start[j] = st;
+      st_out = st;
       atomicAdd(&s_cnt[OSL_CLVL(D, m + 1)], 1u);  // heads every level d > m
       if (s != OSL_NONE) {
         const int lo = (s == D) ? D : max(m + 1, s);
@@ -735,6 +738,7 @@ __device__ __forceinline__ void analyze_block(int vb, int n, const u64* __restri
     }
     m8[j] = (uint8_t)m;
     s8[j] = (uint8_t)s;
+    k_out = k; m_out = m; s_out = s;
   }
   __syncthreads();
   // prefix over depth turns "first level headed" histograms into per-level / per-bucket counts
@@ -759,7 +763,8 @@ __device__ __forceinline__ void assign_block(int vb, int n, const u64* __restric
                                              const TreeParams& tp, const uint8_t* __restrict__ m8,
                                              const uint8_t* __restrict__ s8, const u32* __restrict__ start,
                                              u32* s_base, const LevelArrays& lv, int mode, u32 size0,
-                                             int n_invalid_front, const u32* s_plan, u32 (*s_w)[NC_MAX]) {
+                                             int n_invalid_front, const u32* s_plan, u32 (*s_w)[NC_MAX],
+                                             bool carried, u64 k_in, int m_in, int s_in, u32 st_in) {
   const int D = tp.D, NC = OSL_NCOUNT(D);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const u32 lt = lanemask_lt();
@@ -767,18 +772,21 @@ __device__ __forceinline__ void assign_block(int vb, int n, const u64* __restric
   u64 k = 0;
   int m = D, s = OSL_NONE;
   u32 node = 0;
-  if (j < n) { k = keys[j]; m = m8[j]; s = s8[j]; node = start[j]; }
+  if (carried) { k = k_in; m = m_in; s = s_in; node = st_in; }  // (a CTA that owns ONE block kept phase A's registers)
+  else if (j < n) { k = keys[j]; m = m8[j]; s = s8[j]; node = start[j]; }
   const bool unique = m < D;
 
   // No lane of this warp heads a level <= the warp's smallest m: the per-level collectives start one level above it
   // (one level early so that par_idx / path_tile of the first headed level come out of the loop itself).
   const int d0 = max(1, (int)__reduce_min_sync(FULL, (unsigned)m));
-  // pass 1: per-warp totals of every counter this block can touch
-  for (int c = lane; c < NC; c += 32) s_w[warp][c] = 0;
-  __syncwarp();
   // (steady state: the whole path of every key exists -- no lane of the warp splits anything and the per-bucket
-  // collectives, three match_any per level, are skipped)
+  // collectives, three match_any per level, are skipped; when no key of the BLOCK splits, only the D level counters
+  // are live and the bucket counters, (D+1)^2 of them, are not even touched)
   const bool any_split = __any_sync(FULL, unique && s != OSL_NONE);
+  const int NCu = __syncthreads_or(any_split ? 1 : 0) ? NC : D;
+  // pass 1: per-warp totals of every counter this block can touch
+  for (int c = lane; c < NCu; c += 32) s_w[warp][c] = 0;
+  __syncwarp();
   for (int d = d0; d <= D; d++) {
     const bool f = unique && m < d;
     const u32 bal = __ballot_sync(FULL, f);
@@ -791,7 +799,7 @@ __device__ __forceinline__ void assign_block(int vb, int n, const u64* __restric
   }
   __syncthreads();
   // exclusive scan over the warps + the block's global base + the bucket's global rank base
-  for (int c = tid; c < NC; c += AN_THREADS) {
+  for (int c = tid; c < NCu; c += AN_THREADS) {
     u32 run = s_base[c] + s_plan[c];
 #pragma unroll
     for (int w = 0; w < AN_WARPS; w++) {
@@ -875,7 +883,8 @@ struct StructArgs {
   u32* flags; u32 epoch; LevelArrays lv; int mode; int capacity; int n_in; int parity; u64* split_out;
   u64* wcache;  // walk cache (NULL = off)
 };
-#define STRUCT_SMEM ((AN_WARPS + 4) * NC_MAX * 4 + AN_WARPS * 4)
+#define STRUCT_MAXG 1024  // most CTAs a structure grid / role may have (s_has)
+#define STRUCT_SMEM ((AN_WARPS + 4) * NC_MAX * 4 + AN_WARPS * 4 + STRUCT_MAXG)
 
 __device__ __forceinline__ void structure_body(const StructArgs& A, int bid, int G, unsigned char* s_raw) {
   const u64* __restrict__ keys_sorted = A.keys_sorted; const u64* __restrict__ keys_dense = A.keys_dense;
@@ -915,40 +924,65 @@ __device__ __forceinline__ void structure_body(const StructArgs& A, int bid, int
   // (Sharing walks between the blocks of a CTA -- thread 0 walks the block's first key, the others resume where they
   // leave its path -- was measured at 50 M keys: 3.5 ms against 3.2 ms for these independent walks; with 4 CTAs per
   // SM the walk latency is already hidden and the extra serial step only adds two block barriers per block.)
+  u64 ck = 0; int cm = D, cs = OSL_NONE; u32 cst = 0;  // this thread's key state when the CTA owns a single block
   for (int vb = vb0; vb < vb1; vb++)
-    analyze_block(vb, n, keys, pay, mode, pool, tp, m8, s8, start, s_ctot, &s_w[0][0], A.wcache);
-  // publish this CTA's counter vector behind an epoch flag (every CTA publishes, also one without blocks)
-  for (int c = tid; c < NC; c += AN_THREADS) ctatot[(size_t)bid * NC + c] = s_ctot[c];
+    analyze_block(vb, n, keys, pay, mode, pool, tp, m8, s8, start, s_ctot, &s_w[0][0], A.wcache, ck, cm, cs, cst);
+  const bool carried = (vb1 - vb0 == 1);
+  // publish this CTA's counter vector behind an epoch flag (every CTA publishes, also one without blocks).  Compact
+  // form: the D per-level counters always; the (D+1)^2 bucket counters only when a key of this CTA splits a node --
+  // bit 31 of the flag says so -- which in steady state (the map already holds the surface) is no CTA at all.
+  u32 mine_split = 0;
+  for (int c = D + tid; c < NC; c += AN_THREADS) mine_split |= s_ctot[c];
+  const int has_split = __syncthreads_or(mine_split != 0u);
+  for (int c = tid; c < (has_split ? NC : D); c += AN_THREADS) ctatot[(size_t)bid * NC + c] = s_ctot[c];
   __syncthreads();
   if (tid == 0) {
     __threadfence();
-    *(volatile u32*)&flags[bid] = epoch;
+    *(volatile u32*)&flags[bid] = epoch | (has_split ? 0x80000000u : 0u);
   }
   PROF(17);
 
-  // wait for every CTA's vector (all CTAs are co-resident: cooperative launch), then sum them: totals for the plan,
-  // exclusive prefix for the own range -- one wait, no grid barrier
+  // wait for every CTA's vector (all CTAs are co-resident: cooperative launch / first roles of k_frame), then sum them:
+  // totals for the plan, exclusive prefix for the own range -- one wait, no grid barrier
+  uint8_t* s_has = reinterpret_cast<uint8_t*>(s_scan + AN_WARPS);  // [G] CTA b published bucket counters
   if (warp == 0) {
+    u32 any = 0;
     for (int b = lane; b < G; b += 32) {
       long long spin = 0;  // bounded: a vector that never arrives traps (error to the host) instead of hanging the GPU
-      while (ld_vol(&flags[b]) != epoch)
+      u32 v;
+      while (((v = ld_vol(&flags[b])) & 0x7FFFFFFFu) != epoch)
         if (++spin > (1ll << 31)) __trap();
+      s_has[b] = (uint8_t)(v >> 31);
+      any |= v >> 31;
     }
+    any = __any_sync(FULL, any != 0u);
+    if (lane == 0) s_scan[0] = any;
     __threadfence();
   }
+  __syncthreads();
+  const bool any_cta_split = s_scan[0] != 0u;
   __syncthreads();
   PROF(18);
   for (int c = tid; c < NC; c += AN_THREADS) {
     u32 tot = 0, pre = 0;
     const int mine = bid;
-    for (int b0 = 0; b0 < G; b0 += 16) {
-      u32 v[16];
+    if (c < D) {
+      for (int b0 = 0; b0 < G; b0 += 16) {
+        u32 v[16];
 #pragma unroll
-      for (int k = 0; k < 16; k++) v[k] = (b0 + k < G) ? __ldcg(&ctatot[(size_t)(b0 + k) * NC + c]) : 0u;
+        for (int k = 0; k < 16; k++) v[k] = (b0 + k < G) ? __ldcg(&ctatot[(size_t)(b0 + k) * NC + c]) : 0u;
 #pragma unroll
-      for (int k = 0; k < 16; k++) {
-        tot += v[k];
-        if (b0 + k < mine) pre += v[k];
+        for (int k = 0; k < 16; k++) {
+          tot += v[k];
+          if (b0 + k < mine) pre += v[k];
+        }
+      }
+    } else if (any_cta_split) {
+      for (int b = 0; b < G; b++) {
+        if (!s_has[b]) continue;
+        const u32 v = __ldcg(&ctatot[(size_t)b * NC + c]);
+        tot += v;
+        if (b < mine) pre += v;
       }
     }
     s_tot[c] = tot;
@@ -991,7 +1025,8 @@ __device__ __forceinline__ void structure_body(const StructArgs& A, int bid, int
   PROF(21);
   if (!overflow) {
     for (int vb = vb0; vb < vb1; vb++)
-      assign_block(vb, n, keys, pay, pool, tp, m8, s8, start, s_base, lv, mode, size0, n_invalid_front, s_plan, s_w);
+      assign_block(vb, n, keys, pay, pool, tp, m8, s8, start, s_base, lv, mode, size0, n_invalid_front, s_plan, s_w,
+                   carried, ck, cm, cs, cst);
   }
   PROF(22);
 
@@ -1281,17 +1316,18 @@ __global__ void __launch_bounds__(LEVEL_THREADS) k_levels(LevelArgs A) {
 // ------------------------------------------------------------------------------------------------ k_frame
 // ONE launch per frame for pipelined depth frames: the four stages run as ROLES of one grid, each on the frame that
 // has reached it --
-//     launch f = { emit(f) -> sort(f),  structure(f-1),  values(f-2) }
-// on ONE stream, so every dependency between frames is plain stream order (no events, no host round trips):
-// structure(f-1) needs sort(f-1) and structure(f-2), both in launch f-1; values(f-2) needs structure(f-2), in launch
-// f-1; the key-list slot emit(f) fills was last read by structure(f-3), the level lists structure(f-1) fills were
-// last read by values(f-3).  Launches are chained with programmatic dependent launch: the next grid's CTAs become
+//     launch f = { emit(f),  sort(f-1),  structure(f-2),  values(f-3) }
+// on ONE stream, so every dependency between frames is plain stream order (no events, no host round trips, no flags
+// inside a launch): sort(f-1) needs emit(f-1); structure(f-2) needs sort(f-2) and structure(f-3); values(f-3) needs
+// structure(f-3) -- all in launch f-1; the key-list slot emit(f) fills was last read by structure(f-3), the level
+// lists structure(f-2) fills were last read by values(f-4).  (A first version chained emit(f) -> sort(f) inside one
+// launch through a flag: the sort role, sharing its SMs with three other roles, then needs 18 us after the 13 us of
+// emit, and that chain -- 31 us -- set the period; profiles/r02_timeline_a.txt.)  Launches are chained with programmatic dependent launch: the next grid's CTAs become
 // resident while this one drains and block in griddepcontrol.wait, so the stream never idles through a launch latency.
 // CTA ranges: [0, gS) structure, then gV values, then gE emit tiles, then BK_BUCKETS sort buckets.  The roles that
 // spin on flags of their own kind (structure: counter exchange; values: level barrier) come FIRST, the roles that
-// never wait on a later CTA (emit) before the one that waits for them (sort): with at most 2 * num_sms CTAs of
-// spinning roles per device (the host caps gS + gV + BK_BUCKETS) a spinning CTA can never keep the CTA it waits for
-// off the machine.  Inside the launch the sort role waits for the emit role through FrameState::acc_tiles.
+// never wait (emit, sort) last: with at most 2 * num_sms CTAs of spinning roles per device (the host caps gS + gV) a
+// spinning CTA can never keep the CTA it waits for off the machine.
 struct SortArgs {
   const u64* kin; const u32* pin; u64* kout; u32* pout; u64* kscr; u32* pscr; const FrameState* fs;
   const u64* split; int passes; int parity;
@@ -1363,19 +1399,12 @@ __global__ void __launch_bounds__(FRAME_THREADS, 2) k_frame(const __grid_constan
       __syncthreads();
     }
     emit_body(A.E.p, A.E.tp, A.E.vec_ok, A.E.keys, A.E.pay, A.E.keys_dense, A.E.fs, A.E.parity, b, s_raw);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      __threadfence();
-      atomicAdd(reinterpret_cast<u32*>(&A.E.fs->acc_tiles[A.E.parity]), 1u);
-    }
     span_mark(A.trace, 2, true);
     return;
   }
   b -= A.gE;
   if (threadIdx.x >= BK_THREADS) return;  // whole warps leave: the barriers below count the remaining ones only
   span_mark(A.trace, 3, false);
-  if (threadIdx.x == 0) spin_until_eq(reinterpret_cast<const u32*>(&A.So.fs->acc_tiles[A.So.parity]), (u32)A.gE);
-  __syncthreads();
   bucket_body(A.So.kin, A.So.pin, A.So.kout, A.So.pout, A.So.kscr, A.So.pscr, A.So.fs, A.So.split, A.So.passes,
               A.So.parity, b, s_raw);
   span_mark(A.trace, 3, true);
@@ -1601,8 +1630,8 @@ static osl_status wait_oldest(osl_svo* t) {
   if (t->ring_tail == t->ring_head) return OSL_OK;
   const int slot = (int)(t->ring_tail % OSL_RING);
   if (t->ring_kind[slot] == 1) {
-    // the oldest frame's last stage rides in the launch two frames later: issue it if it has not been issued
-    if (t->ring_head - t->ring_tail <= 2) {
+    // the oldest frame's last stage rides in the launch three frames later: issue it if it has not been issued
+    if (t->ring_head - t->ring_tail <= 3) {
       osl_status rc = osl_fused_flush(t);
       if (rc) return rc;
     }
@@ -1669,6 +1698,14 @@ static osl_status fused_launch(osl_svo* t, const osl_svo::FzStage* nw, const Emi
     A.V = make_level_args(t, t->lv[q.bslot], t->d_fs + 1 + q.bslot, q.f, 0, q.rgb, nullptr);
     A.gV = q.gV;
   }
+  if (t->fz_so.valid) {
+    const osl_svo::FzStage& q = t->fz_so;
+    A.So.kin = t->d_keysA[q.fslot]; A.So.pin = t->d_payA[q.fslot];
+    A.So.kout = t->d_keysB[q.fslot]; A.So.pout = t->d_payB[q.fslot];
+    A.So.kscr = t->d_keysC; A.So.pscr = t->d_payC; A.So.fs = fs;
+    A.So.split = t->d_split + q.fslot * BK_BUCKETS; A.So.passes = (3 * t->tp.D + 7) / 8; A.So.parity = q.fslot;
+    A.gSo = BK_BUCKETS;
+  }
   if (nw) {
     A.E.p = *ep;
     A.E.p.tiles_x = (ep->w + EMIT_TW - 1) / EMIT_TW;
@@ -1678,11 +1715,6 @@ static osl_status fused_launch(osl_svo* t, const osl_svo::FzStage* nw, const Emi
     A.E.keys = t->d_keysA[nw->fslot]; A.E.pay = t->d_payA[nw->fslot]; A.E.keys_dense = t->d_keysB[nw->fslot];
     A.E.fs = fs; A.E.parity = nw->fslot;
     A.gE = A.E.p.tiles_x * A.E.p.tiles_y;
-    A.So.kin = t->d_keysA[nw->fslot]; A.So.pin = t->d_payA[nw->fslot];
-    A.So.kout = t->d_keysB[nw->fslot]; A.So.pout = t->d_payB[nw->fslot];
-    A.So.kscr = t->d_keysC; A.So.pscr = t->d_payC; A.So.fs = fs;
-    A.So.split = t->d_split + nw->fslot * BK_BUCKETS; A.So.passes = (3 * t->tp.D + 7) / 8; A.So.parity = nw->fslot;
-    A.gSo = BK_BUCKETS;
   }
   const int grid = A.gS + A.gV + A.gE + A.gSo;
   A.trace = t->trace_on ? (int)(t->trace_seq++ % OSL_SPAN_SLOTS) : -1;
@@ -1699,13 +1731,14 @@ static osl_status fused_launch(osl_svo* t, const osl_svo::FzStage* nw, const Emi
     OSL_LAUNCHED(1);
   }
   t->fz_v = t->fz_s;
-  if (nw) t->fz_s = *nw; else t->fz_s.valid = 0;
+  t->fz_s = t->fz_so;
+  if (nw) t->fz_so = *nw; else t->fz_so.valid = 0;
   return OSL_OK;
 }
 
-// Issue the launches that carry the remaining stages of the frames enqueued so far (at most two).
+// Issue the launches that carry the remaining stages of the frames enqueued so far (at most three).
 osl_status osl_fused_flush(osl_svo* t) {
-  while (t->fz_s.valid || t->fz_v.valid) {
+  while (t->fz_so.valid || t->fz_s.valid || t->fz_v.valid) {
     osl_status rc = fused_launch(t, nullptr, nullptr);
     if (rc) return rc;
   }
@@ -1782,7 +1815,7 @@ osl_status osl_run_integrate(osl_svo* t, EmitParams& ep, const void* colors, cud
   }
   // k_frame path (one launch per frame): pipelined depth frames with a host pose once the bucket sort applies.  Its
   // spinning roles may hold at most 2 CTAs per SM in total over all pipelining trees of the process.
-  const int spin_cap = (2 * t->num_sms / trees - BK_BUCKETS) / 2;
+  const int spin_cap = (2 * t->num_sms / trees) / 2;
   const bool fused = piped && t->fused_enabled && ep.mode == 0 && !ep.M_dev && n > 0 && use_bucket && spin_cap >= 8;
   if (f > 0 && fused != (t->last_fused != 0)) {
     // Path switch (the first frames of a stream run as four kernels until splitters and size hints exist; a scene

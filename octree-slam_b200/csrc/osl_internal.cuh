@@ -197,7 +197,7 @@ struct osl_svo {
   cudaEvent_t reader_ev; int reader_pending;
   // k_frame pipeline (one launch per frame on pipe[2]): the frames whose structure / value stage the next launch
   // carries; completion is read from the pinned result block (FrameState::done_flag), not from events
-  struct FzStage { int valid; unsigned long long f; int n, fslot, bslot, gS, gV; const uint8_t* rgb; } fz_s, fz_v;
+  struct FzStage { int valid; unsigned long long f; int n, fslot, bslot, gS, gV; const uint8_t* rgb; } fz_so, fz_s, fz_v;
   int last_fused, fused_enabled;
   int trace_on; unsigned long long trace_seq;  // osl_debug_trace
   int ring_kind[OSL_RING];               // 0: completion = ring_ev, 1: completion = done_flag of the pinned block

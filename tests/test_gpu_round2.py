@@ -143,7 +143,7 @@ def test_upload_rejects_corrupt_child_pointers(P):
 @pytest.mark.parametrize("host_frames", [False, True])
 @pytest.mark.parametrize("D", [8, 16])
 def test_one_launch_per_frame_pipeline_matches_oracle(P, D, host_frames):
-    """k_frame (one launch per frame: emit+sort of frame f, structure of f-1, values of f-2 as roles of one grid, chained
+    """k_frame (one launch per frame: emit of frame f, sort of f-1, structure of f-2, values of f-3 as roles of one grid, chained
     by programmatic dependent launch) against the oracle AND against the same frames run as four kernels: pools
     bit-identical after every few frames, with a raycast, a size query and a scene cut in between (each of them drains
     or flushes the pipeline at a different depth)."""
@@ -186,7 +186,7 @@ def test_one_launch_per_frame_pipeline_matches_oracle(P, D, host_frames):
 
 
 def test_one_launch_per_frame_is_really_one_launch(P):
-    """steady state of the pipelined path: one kernel launch per frame (+ two to drain)"""
+    """steady state of the pipelined path: one kernel launch per frame (+ three to drain)"""
     import torch
     D, w, h = 12, 320, 240
     center, half = P.synth.tree_params(D)
@@ -205,4 +205,4 @@ def test_one_launch_per_frame_is_really_one_launch(P):
     for d, c, pose in frames[10:]:
         svo.integrate_depth(d, c, fx, fy, pose)
     svo.sync()
-    assert P.lib().osl_launch_count() - l0 == 30 + 2
+    assert P.lib().osl_launch_count() - l0 == 30 + 3

@@ -10,6 +10,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
 import __graft_entry__ as graft  # noqa: E402
 
 ROLES = ["structure", "values", "emit", "sort", "arrival"]
@@ -44,7 +45,7 @@ def main():
     out = (C.c_uint64 * (32 * 5 * 2))()
     lib.osl_debug_trace(svo._h, 0, out)
     a = np.array(out, dtype=np.uint64).reshape(32, 5, 2).astype(np.float64)
-    n_launch = min(32, frames + 2)
+    n_launch = min(32, frames + 3)
     t0 = a[:n_launch, :, 0][a[:n_launch, :, 0] < 1e19].min()
     print("%d frames, %.2f us per frame by CUDA events; times in us since the first CTA" % (frames, e0.elapsed_time(e1) * 1e3 / frames))
     print("launch  " + "  ".join("%-17s" % r for r in ROLES) + "  launch span   start-to-start")
@@ -63,6 +64,15 @@ def main():
         gap = "" if prev is None else "%6.1f" % ((lo - prev) / 1e3)
         print("%4d    %s  %6.1f        %s" % (i, "  ".join(cells), (hi - lo) / 1e3, gap))
         prev = lo
+    # phases of CTA 0 of each role in the LAST launch that ran it (SM-clock checkpoints, osl_debug_profile)
+    from phase_profile import NAMES
+    prof = (C.c_uint64 * 64)()
+    lib.osl_debug_profile(prof, 64)
+    mhz = 1965.0
+    for kern, phases in NAMES.items():
+        print(kern)
+        for a_, b_, name in phases:
+            print("    %-44s %7.2f us" % (name, (prof[b_] - prof[a_]) / mhz))
 
 
 if __name__ == "__main__":
