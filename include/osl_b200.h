@@ -159,6 +159,25 @@ osl_status osl_get_counters(const osl_svo* t, osl_counters* out);
 osl_status osl_svo_save(const osl_svo* t, const char* path);
 osl_status osl_svo_load(osl_svo* t, const char* path);
 
+/* ---- replicas of one map on several GPUs (image rows shard, every rank holds the tree) ------------ */
+
+/* Everything stays in DEVICE memory; a collective library (NCCL) or a peer copy moves the bytes.
+ * Full copy: the receiver reserves room, exposes its pool, the collective writes the sender's flat 2*n uint32 array
+ * (the reference's wire format, octree.cpp:113-169) into it, osl_svo_adopt validates the child pointers and publishes
+ * it (OSL_ERR_INVALID, and an empty tree, when max_depth / centre / half edge differ from the source's or the array is
+ * corrupt).  osl_svo_pool_device waits for the pipeline; the pointer is valid until the pool next grows. */
+osl_status osl_svo_reserve(osl_svo* t, size_t n_nodes);
+osl_status osl_svo_pool_device(osl_svo* t, uint32_t** d_pool, size_t* cap_nodes);
+osl_status osl_svo_adopt(osl_svo* t, int n_nodes, int max_depth, const float center[3], float half_edge);
+/* Delta: what the LAST integrate call changed -- a 32-byte header, the (index, word0, word1) of every pre-existing or
+ * new node on a touched path (the frame's level lists) and the nodes the call appended (new tiles only ever go to the
+ * end of the pool).  ~0.3 MB for a 640x480 frame.  _bytes: size of the packed delta (waits for the frame); _pack writes
+ * it to d_buf (device memory, `cap` bytes); _apply on a replica that is in the state BEFORE that call brings it to the
+ * state after it (OSL_ERR_INVALID otherwise). */
+size_t osl_svo_delta_bytes(osl_svo* t);
+osl_status osl_svo_delta_pack(osl_svo* t, void* d_buf, size_t cap, size_t* bytes, void* stream);
+osl_status osl_svo_delta_apply(osl_svo* t, const void* d_buf, size_t bytes, void* stream);
+
 /* ---- raycast (cone_tracing_kernels.h:16) ------------------------------------------------------------------- */
 
 /* Replaces rendering::coneTraceSVO (cone_tracing_kernels.cu:157-198).  d_out: w*h uchar4 {R,G,B,A}.

@@ -15,7 +15,7 @@ static osl_status drain(osl_svo* t) {
   return t->sticky_error;
 }
 
-static osl_status set_device_size(osl_svo* t, int size) {
+osl_status osl_set_device_size(osl_svo* t, int size) {
   // FrameState::cur_size lives on the device (frames are planned there without a host round trip)
   OSL_CUDA(cudaMemcpy(&t->d_fs->cur_size, &size, sizeof(int), cudaMemcpyHostToDevice));
   if (t->d_wcache) OSL_CUDA(cudaMemset(t->d_wcache, 0xFF, 4096 * sizeof(u64)));  // node indices / depths change meaning
@@ -57,6 +57,24 @@ __global__ void k_validate_pool(const u32* __restrict__ pool, int n, int* bad) {
     const u32 c = w0 & OSL_MASK;
     if ((c & 7u) || c < 8u || (unsigned long long)c + 8ull > (unsigned long long)n) atomicAdd(bad, 1);
   }
+}
+
+// Runs k_validate_pool over the first n_nodes nodes; corrupt child pointers leave an EMPTY, valid tree behind.
+osl_status osl_validate_pool(osl_svo* t, int n_nodes) {
+  if (n_nodes <= 0) return OSL_OK;
+  int* d_bad = reinterpret_cast<int*>(t->d_scan_totals + OSL_NCOUNT(OSL_MAXD) + 2);  // scratch word, zero at rest
+  int bad = 0;
+  k_validate_pool<<<(n_nodes + 255) / 256, 256>>>(t->d_pool, n_nodes, d_bad);
+  g_osl_launches++;
+  OSL_CUDA(cudaMemcpy(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost));
+  if (bad) {
+    OSL_CUDA(cudaMemset(d_bad, 0, sizeof(int)));
+    OSL_CUDA(cudaMemset(t->d_pool, 0, (size_t)n_nodes * 8));
+    t->upload_count++;
+    osl_set_device_size(t, 0);
+    return OSL_ERR_INVALID;
+  }
+  return OSL_OK;
 }
 
 extern "C" {
@@ -189,7 +207,7 @@ osl_status osl_svo_reset(osl_svo* t) {
   t->sticky_error = OSL_OK;
   t->upload_count++;  // invalidates the cached extraction frontier
   memset(&t->counters, 0, sizeof(t->counters));
-  return set_device_size(t, 0);
+  return osl_set_device_size(t, 0);
 }
 
 osl_status osl_svo_expand(osl_svo* t, int layers) {
@@ -207,7 +225,7 @@ osl_status osl_svo_expand(osl_svo* t, int layers) {
       k_expand_root<<<1, 64>>>(t->d_pool, t->size);
       OSL_CUDA(cudaGetLastError());
       g_osl_launches++;
-      rc = set_device_size(t, t->size + 64);
+      rc = osl_set_device_size(t, t->size + 64);
       if (rc) return rc;
     }
     t->tp.half *= 2.0f;
@@ -404,22 +422,12 @@ osl_status osl_svo_upload(osl_svo* t, const uint32_t* h_pool, int n_nodes) {
   if (n_nodes > 0) {
     if (n_nodes < 8 || (n_nodes & 7)) return OSL_ERR_INVALID;  // whole 8-node tiles, the root's first
     OSL_CUDA(cudaMemcpy(t->d_pool, h_pool, (size_t)n_nodes * 8, cudaMemcpyHostToDevice));
-    int* d_bad = reinterpret_cast<int*>(t->d_scan_totals + OSL_NCOUNT(OSL_MAXD) + 2);  // scratch word, zero at rest
-    int bad = 0;
-    k_validate_pool<<<(n_nodes + 255) / 256, 256>>>(t->d_pool, n_nodes, d_bad);
-    g_osl_launches++;
-    OSL_CUDA(cudaMemcpy(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost));
-    if (bad) {  // corrupt child pointers: leave an empty, valid tree behind
-      OSL_CUDA(cudaMemset(d_bad, 0, sizeof(int)));
-      OSL_CUDA(cudaMemset(t->d_pool, 0, (size_t)n_nodes * 8));
-      t->upload_count++;
-      set_device_size(t, 0);
-      return OSL_ERR_INVALID;
-    }
+    osl_status vrc = osl_validate_pool(t, n_nodes);
+    if (vrc) return vrc;
   }
   t->sticky_error = OSL_OK;
   t->upload_count++;  // invalidates the cached extraction frontier
-  return set_device_size(t, n_nodes);
+  return osl_set_device_size(t, n_nodes);
 }
 
 // Checkpoint / resume (the reference has none; its de-facto wire format is the flat 2*n uint

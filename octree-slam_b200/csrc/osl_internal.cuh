@@ -257,6 +257,8 @@ osl_status osl_grow_pool(osl_svo* t, size_t want_nodes, cudaStream_t st);
 osl_status osl_reset_splitters(osl_svo* t);
 void osl_drop_workspace(osl_svo* t);
 osl_status osl_join(osl_svo* t, cudaStream_t st);
+osl_status osl_set_device_size(osl_svo* t, int size);  // FrameState::cur_size + host copy; clears the walk cache
+osl_status osl_validate_pool(osl_svo* t, int n_nodes);
 osl_status osl_note_reader(osl_svo* t, cudaStream_t st);      // after enqueuing work on `st` that reads the pool
 osl_status osl_note_foreign_reader(osl_svo* t, cudaStream_t st);  // `st` may carry foreign readers until the next integrate
 osl_status osl_device_sort_pairs(u64* kA, u32* pA, u64* kB, u32* pB, int n, int key_bits, cudaStream_t st, int* in_B);

@@ -14,9 +14,6 @@
 // mode 1 (fixed_accumulate) keeps the accumulator in registers across steps (what the code was meant to do).
 #include <math.h>
 
-#include <atomic>
-#include <mutex>
-
 #include "osl_internal.cuh"
 
 struct RayParams {
@@ -66,8 +63,6 @@ __device__ __forceinline__ float node_step(float size, int depth) {
 }
 
 #define RAY_THREADS 128
-#define OSL_MAX_DEVICES 64
-#define OSL_RAY_QUEUES 256
 
 // A cell of the tree a ray's descent went through, with the EXACT half-open bounds the root descent implies for it
 // (the centres compared on the way down): a sample inside them takes the same branches from the root, so the descent
@@ -89,215 +84,143 @@ __device__ __forceinline__ bool cell_has(const RayCell& c, int depth, float tx, 
 // the next samples: consecutive samples are half a leaf apart) and a shallow one 7 levels above (hit by nearly all
 // the others, which matters because one lane restarting at the root stalls its whole warp) -- and resumes the descent
 // at the deepest one that contains the new sample.  Identical results by construction.
-//
-// Scheduling (round 2): PERSISTENT warps with lane refill.  Rays of one 8x4-pixel patch take very different numbers of
-// steps (a ray that leaves through a window marches 10x longer than its neighbour that hits the wall), so with one
-// patch per warp two thirds of the lanes idled while the longest ray finished (ncu r01: 33 % of the warp slots
-// active).  Now a warp pulls patches from a global queue (one atomicAdd per patch, broadcast by shuffle) and, whenever
-// enough of its lanes have finished, hands the pixels of the next patch to exactly those lanes (rank among the idle
-// lanes by ballot / popc, k-th pending pixel by __fns).  Every ray is still computed by one thread with the same
-// operations in the same order -- pure scheduling, images bit-identical.
-struct RayState {
-  float rx, ry, rz, len;
-  RayCell A, B;  // deep, shallow
-  int last_lvl;
-  int idx;       // output pixel (local row * W + px)
-  u32 vx, vy, vz, vw;  // uchar4 accumulator (mod-256 arithmetic)
-};
-
-__device__ __forceinline__ void ray_begin(RayState& R, const RayParams& P, int px, int lr) {
-  const int py = P.row0 + (lr / P.band_h) * P.band_h * P.band_stride + lr % P.band_h;
-  // createRays (cone_tracing_kernels.cu:29-51)
-  const float magx = __fdiv_rn(__fmaf_rn(P.resx, -0.5f, (float)px), P.fx);
-  const float magy = __fdiv_rn(__fmaf_rn(P.resy, -0.5f, (float)py), P.fy);
-  const float dx = __fadd_rn(__fmaf_rn(magx, P.xdx, __fmul_rn(magy, P.ydx)), P.crx);
-  const float dy = __fadd_rn(__fmaf_rn(magx, P.xdy, __fmul_rn(magy, P.ydy)), P.cry);
-  const float dz = __fadd_rn(__fmaf_rn(magx, P.xdz, __fmul_rn(magy, P.ydz)), P.crz);
-  const float dot = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
-  const float inv = __frcp_rn(__fsqrt_rn(dot));
-  R.rx = __fmul_rn(__fmul_rn(dx, inv), P.start_dist);
-  R.ry = __fmul_rn(__fmul_rn(dy, inv), P.start_dist);
-  R.rz = __fmul_rn(__fmul_rn(dz, inv), P.start_dist);
-  R.len = ray_length(R.rx, R.ry, R.rz);
-  const float INF = __int_as_float(0x7f800000);
-  R.A.lvl = -1; R.B.lvl = -1;
-  R.A.child = R.A.self = R.B.child = R.B.self = 0u;
-  R.A.cx = R.A.cy = R.A.cz = R.A.e = R.B.cx = R.B.cy = R.B.cz = R.B.e = 0.f;
-  R.A.lox = R.A.loy = R.A.loz = R.B.lox = R.B.loy = R.B.loz = -INF;
-  R.A.hix = R.A.hiy = R.A.hiz = R.B.hix = R.B.hiy = R.B.hiz = INF;
-  R.last_lvl = 8;
-  R.idx = lr * P.W + px;
-  R.vx = R.vy = R.vz = R.vw = 0;
-}
-
-// One march step of the reference (coneTrace, cone_tracing_kernels.cu:53-146).  Returns true when the ray terminated;
-// `result` is then the pixel.
-__device__ __forceinline__ bool ray_step(RayState& R, const RayParams& P, const u32* __restrict__ pool,
-                                         const float* s_af, unsigned long long& visits, u32& result) {
-  const float INF = __int_as_float(0x7f800000);
-  RayCell& A = R.A;
-  RayCell& B = R.B;
-  const float tx = __fadd_rn(P.ox, R.rx), ty = __fadd_rn(P.oy, R.ry), tz = __fadd_rn(P.oz, R.rz);
-  const float pix = __fmul_rn(R.len, P.pix_scale);
-  int depth = lod_depth(P.size, pix);
-
-  // where the descent starts: deepest cached cell containing the sample, else the root
-  u32 node = 0, child = 0;
-  float cx = P.cx, cy = P.cy, cz = P.cz, e = P.size;
-  float blx = -INF, bhx = INF, bly = -INF, bhy = INF, blz = -INF, bhz = INF;  // bounds of the current cell
-  int i = 0;
-  if (cell_has(A, depth, tx, ty, tz)) {
-    i = A.lvl; node = A.self; child = A.child; cx = A.cx; cy = A.cy; cz = A.cz; e = A.e;
-    blx = A.lox; bhx = A.hix; bly = A.loy; bhy = A.hiy; blz = A.loz; bhz = A.hiz;
-  } else if (cell_has(B, depth, tx, ty, tz)) {
-    i = B.lvl; node = B.self; child = B.child; cx = B.cx; cy = B.cy; cz = B.cz; e = B.e;
-    blx = B.lox; bhx = B.hix; bly = B.loy; bhy = B.hiy; blz = B.loz; bhz = B.hiz;
-  }
-  visits += (unsigned long long)i;  // the word0 reads the root descent would have made down to here
-  bool open = true;                 // the descent has not met a node without children
-
-#define RAY_STEP_TRACKED()                                                         \
-  {                                                                                \
-    const bool bx = tx > cx, by = ty > cy, bz = tz > cz;                           \
-    node = child + (u32)((int)bx + 2 * (int)by + 4 * (int)bz);                     \
-    const u32 w0 = __ldg(pool + 2 * (size_t)node);                                 \
-    visits++;                                                                      \
-    if (!(w0 & OSL_FLAG)) { depth = i + 1; open = false; break; }                  \
-    child = w0 & OSL_MASK;                                                         \
-    if (bx) blx = fmaxf(blx, cx); else bhx = fminf(bhx, cx);                       \
-    if (by) bly = fmaxf(bly, cy); else bhy = fminf(bhy, cy);                       \
-    if (bz) blz = fmaxf(blz, cz); else bhz = fminf(bhz, cz);                       \
-    e = __fmul_rn(e, 0.5f);                                                        \
-    cx = __fadd_rn(cx, bx ? e : -e);                                               \
-    cy = __fadd_rn(cy, by ? e : -e);                                               \
-    cz = __fadd_rn(cz, bz ? e : -e);                                               \
-    i++;                                                                           \
-  }
-#define RAY_SNAPSHOT(C, L)                                                         \
-  {                                                                                \
-    C.lvl = (L); C.self = node; C.child = child; C.cx = cx; C.cy = cy; C.cz = cz; C.e = e; \
-    C.lox = blx; C.hix = bhx; C.loy = bly; C.hiy = bhy; C.loz = blz; C.hiz = bhz;          \
-  }
-
-  // tracked segments: down to the shallow target, snapshot, down to the deep target, snapshot
-  const int ltB = max(R.last_lvl - 7, 1), ltA = max(R.last_lvl - 3, ltB + 1);
-  if (i < ltB) {
-    for (; i < depth && i < ltB;) RAY_STEP_TRACKED()
-    if (open && i == ltB) RAY_SNAPSHOT(B, ltB)
-  }
-  if (open && i < ltA) {
-    for (; i < depth && i < ltA;) RAY_STEP_TRACKED()
-    if (open && i == ltA) RAY_SNAPSHOT(A, ltA)
-  }
-  if (open) {
-    for (; i < depth;) {
-      const bool bx = tx > cx, by = ty > cy, bz = tz > cz;
-      node = child + (u32)((int)bx + 2 * (int)by + 4 * (int)bz);
-      const u32 w0 = __ldg(pool + 2 * (size_t)node);
-      visits++;
-      if (!(w0 & OSL_FLAG)) { depth = i + 1; break; }
-      child = w0 & OSL_MASK;
-      e = __fmul_rn(e, 0.5f);
-      cx = __fadd_rn(cx, bx ? e : -e);
-      cy = __fadd_rn(cy, by ? e : -e);
-      cz = __fadd_rn(cz, bz ? e : -e);
-      i++;
-    }
-  }
-#undef RAY_STEP_TRACKED
-#undef RAY_SNAPSHOT
-  R.last_lvl = depth;
-
-  if (P.mode == 0) { R.vx = R.vy = R.vz = R.vw = 0; }  // Q8
-  const u32 ov = __ldg(pool + 2 * (size_t)node + 1);
-  const int alpha = (int)(ov >> 24) - 127;  // Q9: the reference's max(0, unsigned) is a no-op
-  const float af = s_af[ov >> 24];
-  R.vx = (R.vx + f2u8(__fmul_rn((float)(ov & 0xFFu), af))) & 0xFFu;
-  R.vy = (R.vy + f2u8(__fmul_rn((float)((ov >> 8) & 0xFFu), af))) & 0xFFu;
-  R.vz = (R.vz + f2u8(__fmul_rn((float)((ov >> 16) & 0xFFu), af))) & 0xFFu;
-  if ((int)R.vw + alpha < 127) {
-    R.vw = (R.vw + (u32)alpha) & 0xFFu;
-  } else {
-    result = R.vx | (R.vy << 8) | (R.vz << 16) | (255u << 24);
-    return true;
-  }
-  const float nd = node_step(P.size, depth);
-  const float sc = __fdiv_rn(__fadd_rn(R.len, nd), R.len);
-  R.rx = __fmul_rn(R.rx, sc); R.ry = __fmul_rn(R.ry, sc); R.rz = __fmul_rn(R.rz, sc);
-  R.len = ray_length(R.rx, R.ry, R.rz);  // also the next step's |ray| (the reference recomputes the same value)
-  if (R.len > P.max_range) {
-    const float f = __fdiv_rn(127.0f, (float)R.vw);
-    result = f2u8(__fmul_rn((float)R.vx, f)) | (f2u8(__fmul_rn((float)R.vy, f)) << 8) |
-             (f2u8(__fmul_rn((float)R.vz, f)) << 16) | (255u << 24);
-    return true;
-  }
-  return false;
-}
-
-// refill threshold: new rays are handed out when at least this many lanes of the warp idle (or all of them)
-#define RAY_REFILL 8
-
 __global__ void __launch_bounds__(RAY_THREADS)
-k_raycast(const u32* __restrict__ pool, RayParams P, uchar4* __restrict__ out, unsigned long long* stats,
-          unsigned int* queue, int n_patches) {
+k_raycast(const u32* __restrict__ pool, RayParams P, uchar4* __restrict__ out, unsigned long long* stats) {
   __shared__ float s_af[256];  // (A - 127) / 127.0f for every alpha byte (Q9: no clamp)
   for (int a = threadIdx.x; a < 256; a += RAY_THREADS) s_af[a] = __fdiv_rn((float)(a - 127), 127.0f);
   __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const u32 lt = lanemask_lt();
+  // a warp renders an 8x4-pixel patch (not 32 pixels of one row): neighbouring rays visit the same nodes and take
+  // similar numbers of steps, so fewer lanes idle while the longest ray of the warp finishes
+  const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int tiles_x = (P.W + 7) >> 3;
+  const int px = (gwarp % tiles_x) * 8 + (lane & 7);
+  const int lr = (gwarp / tiles_x) * 4 + (lane >> 3);
+  const int idx = lr * P.W + px;
   unsigned long long steps = 0, visits = 0;
-  RayState R;
-  R.idx = 0; R.last_lvl = 8; R.rx = R.ry = R.rz = R.len = 0.f; R.vx = R.vy = R.vz = R.vw = 0;
-  R.A.lvl = R.B.lvl = -1;
-  bool alive = false;
-  bool more = true;    // the queue may still hold patches (warp-uniform)
-  u32 pending = 0;     // pixels of the current patch not handed out yet (warp-uniform)
-  int patch = 0;       // (warp-uniform)
-  for (;;) {
-    const u32 idle = ~__ballot_sync(0xFFFFFFFFu, alive);
-    if ((pending || more) && (idle == 0xFFFFFFFFu || __popc(idle) >= RAY_REFILL)) {
-      u32 free_lanes = idle;
-      while (free_lanes) {
-        if (!pending) {
-          if (!more) break;
-          int pid = 0;
-          if (lane == 0) pid = (int)atomicAdd(queue, 1u);
-          pid = __shfl_sync(0xFFFFFFFFu, pid, 0);
-          if (pid >= n_patches) { more = false; break; }
-          patch = pid;
-          // valid pixels of the 8x4 patch (a warp renders a patch, not 32 pixels of one row: neighbouring rays visit
-          // the same nodes)
-          const int px = (patch % tiles_x) * 8 + (lane & 7), lr = (patch / tiles_x) * 4 + (lane >> 3);
-          pending = __ballot_sync(0xFFFFFFFFu, px < P.W && lr < P.rows);
-          if (!pending) continue;
-        }
-        // the k-th idle lane takes the k-th pending pixel
-        const bool is_free = (free_lanes >> lane) & 1u;
-        const int k = __popc(free_lanes & lt);
-        const int npend = __popc(pending);
-        if (is_free && k < npend) {
-          const int bit = (int)__fns(pending, 0, k + 1);
-          ray_begin(R, P, (patch % tiles_x) * 8 + (bit & 7), (patch / tiles_x) * 4 + (bit >> 3));
-          alive = true;
-        }
-        const int taken = min(__popc(free_lanes), npend);
-        // drop the `taken` lowest pending pixels and the `taken` lowest idle lanes
-        for (int q = 0; q < taken; q++) { pending &= pending - 1; free_lanes &= free_lanes - 1; }
-      }
-    }
-    if (!__any_sync(0xFFFFFFFFu, alive)) {
-      if (!pending && !more) break;
-      continue;
-    }
-    if (alive) {
+  if (px < P.W && lr < P.rows) {
+    const int py = P.row0 + (lr / P.band_h) * P.band_h * P.band_stride + lr % P.band_h;
+    // createRays (cone_tracing_kernels.cu:29-51)
+    const float magx = __fdiv_rn(__fmaf_rn(P.resx, -0.5f, (float)px), P.fx);
+    const float magy = __fdiv_rn(__fmaf_rn(P.resy, -0.5f, (float)py), P.fy);
+    const float dx = __fadd_rn(__fmaf_rn(magx, P.xdx, __fmul_rn(magy, P.ydx)), P.crx);
+    const float dy = __fadd_rn(__fmaf_rn(magx, P.xdy, __fmul_rn(magy, P.ydy)), P.cry);
+    const float dz = __fadd_rn(__fmaf_rn(magx, P.xdz, __fmul_rn(magy, P.ydz)), P.crz);
+    const float dot = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+    const float inv = __frcp_rn(__fsqrt_rn(dot));
+    float rx = __fmul_rn(__fmul_rn(dx, inv), P.start_dist);
+    float ry = __fmul_rn(__fmul_rn(dy, inv), P.start_dist);
+    float rz = __fmul_rn(__fmul_rn(dz, inv), P.start_dist);
+    float len = ray_length(rx, ry, rz);
+
+    const float INF = __int_as_float(0x7f800000);
+    RayCell A, B;  // deep, shallow
+    A.lvl = -1; B.lvl = -1;
+    A.child = A.self = B.child = B.self = 0u;
+    A.cx = A.cy = A.cz = A.e = B.cx = B.cy = B.cz = B.e = 0.f;
+    A.lox = A.loy = A.loz = B.lox = B.loy = B.loz = -INF;
+    A.hix = A.hiy = A.hiz = B.hix = B.hiy = B.hiz = INF;
+    int last_lvl = 8;
+
+    u32 vx = 0, vy = 0, vz = 0, vw = 0;  // uchar4 accumulator (mod-256 arithmetic)
+    u32 result = 0;
+    for (;;) {
       steps++;
-      u32 result;
-      if (ray_step(R, P, pool, s_af, visits, result)) {
-        out[R.idx] = make_uchar4(result & 0xFF, (result >> 8) & 0xFF, (result >> 16) & 0xFF, result >> 24);
-        alive = false;
+      const float tx = __fadd_rn(P.ox, rx), ty = __fadd_rn(P.oy, ry), tz = __fadd_rn(P.oz, rz);
+      const float pix = __fmul_rn(len, P.pix_scale);
+      int depth = lod_depth(P.size, pix);
+
+      // where the descent starts: deepest cached cell containing the sample, else the root
+      u32 node = 0, child = 0;
+      float cx = P.cx, cy = P.cy, cz = P.cz, e = P.size;
+      float blx = -INF, bhx = INF, bly = -INF, bhy = INF, blz = -INF, bhz = INF;  // bounds of the current cell
+      int i = 0;
+      if (cell_has(A, depth, tx, ty, tz)) {
+        i = A.lvl; node = A.self; child = A.child; cx = A.cx; cy = A.cy; cz = A.cz; e = A.e;
+        blx = A.lox; bhx = A.hix; bly = A.loy; bhy = A.hiy; blz = A.loz; bhz = A.hiz;
+      } else if (cell_has(B, depth, tx, ty, tz)) {
+        i = B.lvl; node = B.self; child = B.child; cx = B.cx; cy = B.cy; cz = B.cz; e = B.e;
+        blx = B.lox; bhx = B.hix; bly = B.loy; bhy = B.hiy; blz = B.loz; bhz = B.hiz;
+      }
+      visits += (unsigned long long)i;  // the word0 reads the root descent would have made down to here
+      bool open = true;                 // the descent has not met a node without children
+
+#define RAY_STEP_TRACKED()                                                         \
+      {                                                                            \
+        const bool bx = tx > cx, by = ty > cy, bz = tz > cz;                       \
+        node = child + (u32)((int)bx + 2 * (int)by + 4 * (int)bz);                 \
+        const u32 w0 = __ldg(pool + 2 * (size_t)node);                             \
+        visits++;                                                                  \
+        if (!(w0 & OSL_FLAG)) { depth = i + 1; open = false; break; }              \
+        child = w0 & OSL_MASK;                                                     \
+        if (bx) blx = fmaxf(blx, cx); else bhx = fminf(bhx, cx);                   \
+        if (by) bly = fmaxf(bly, cy); else bhy = fminf(bhy, cy);                   \
+        if (bz) blz = fmaxf(blz, cz); else bhz = fminf(bhz, cz);                   \
+        e = __fmul_rn(e, 0.5f);                                                    \
+        cx = __fadd_rn(cx, bx ? e : -e);                                           \
+        cy = __fadd_rn(cy, by ? e : -e);                                           \
+        cz = __fadd_rn(cz, bz ? e : -e);                                           \
+        i++;                                                                       \
+      }
+#define RAY_SNAPSHOT(C, L)                                                         \
+      {                                                                            \
+        C.lvl = (L); C.self = node; C.child = child; C.cx = cx; C.cy = cy; C.cz = cz; C.e = e; \
+        C.lox = blx; C.hix = bhx; C.loy = bly; C.hiy = bhy; C.loz = blz; C.hiz = bhz;          \
+      }
+
+      // tracked segments: down to the shallow target, snapshot, down to the deep target, snapshot
+      const int ltB = max(last_lvl - 7, 1), ltA = max(last_lvl - 3, ltB + 1);
+      if (i < ltB) {
+        for (; i < depth && i < ltB;) RAY_STEP_TRACKED()
+        if (open && i == ltB) RAY_SNAPSHOT(B, ltB)
+      }
+      if (open && i < ltA) {
+        for (; i < depth && i < ltA;) RAY_STEP_TRACKED()
+        if (open && i == ltA) RAY_SNAPSHOT(A, ltA)
+      }
+      if (open) {
+        for (; i < depth;) {
+          const bool bx = tx > cx, by = ty > cy, bz = tz > cz;
+          node = child + (u32)((int)bx + 2 * (int)by + 4 * (int)bz);
+          const u32 w0 = __ldg(pool + 2 * (size_t)node);
+          visits++;
+          if (!(w0 & OSL_FLAG)) { depth = i + 1; break; }
+          child = w0 & OSL_MASK;
+          e = __fmul_rn(e, 0.5f);
+          cx = __fadd_rn(cx, bx ? e : -e);
+          cy = __fadd_rn(cy, by ? e : -e);
+          cz = __fadd_rn(cz, bz ? e : -e);
+          i++;
+        }
+      }
+#undef RAY_STEP_TRACKED
+#undef RAY_SNAPSHOT
+      last_lvl = depth;
+
+      if (P.mode == 0) { vx = vy = vz = vw = 0; }  // Q8
+      const u32 ov = __ldg(pool + 2 * (size_t)node + 1);
+      const int alpha = (int)(ov >> 24) - 127;  // Q9: the reference's max(0, unsigned) is a no-op
+      const float af = s_af[ov >> 24];
+      vx = (vx + f2u8(__fmul_rn((float)(ov & 0xFFu), af))) & 0xFFu;
+      vy = (vy + f2u8(__fmul_rn((float)((ov >> 8) & 0xFFu), af))) & 0xFFu;
+      vz = (vz + f2u8(__fmul_rn((float)((ov >> 16) & 0xFFu), af))) & 0xFFu;
+      if ((int)vw + alpha < 127) {
+        vw = (vw + (u32)alpha) & 0xFFu;
+      } else {
+        result = vx | (vy << 8) | (vz << 16) | (255u << 24);
+        break;
+      }
+      const float nd = node_step(P.size, depth);
+      const float sc = __fdiv_rn(__fadd_rn(len, nd), len);
+      rx = __fmul_rn(rx, sc); ry = __fmul_rn(ry, sc); rz = __fmul_rn(rz, sc);
+      len = ray_length(rx, ry, rz);  // also the next step's |ray| (the reference recomputes the same value)
+      if (len > P.max_range) {
+        const float f = __fdiv_rn(127.0f, (float)vw);
+        result = f2u8(__fmul_rn((float)vx, f)) | (f2u8(__fmul_rn((float)vy, f)) << 8) |
+                 (f2u8(__fmul_rn((float)vz, f)) << 16) | (255u << 24);
+        break;
       }
     }
+    out[idx] = make_uchar4(result & 0xFF, (result >> 8) & 0xFF, (result >> 16) & 0xFF, result >> 24);
   }
   if (stats) {
 #pragma unroll
@@ -305,7 +228,7 @@ k_raycast(const u32* __restrict__ pool, RayParams P, uchar4* __restrict__ out, u
       steps += __shfl_xor_sync(0xFFFFFFFFu, steps, o);
       visits += __shfl_xor_sync(0xFFFFFFFFu, visits, o);
     }
-    if (lane == 0) {
+    if ((threadIdx.x & 31) == 0) {
       atomicAdd(&stats[0], steps);
       atomicAdd(&stats[1], visits);
     }
@@ -381,35 +304,10 @@ osl_status osl_launch_raycast(const u32* d_pool, const float center[3], float ha
   P.cx = center[0]; P.cy = center[1]; P.cz = center[2]; P.size = half_edge;
   P.fx = p.fx; P.fy = p.fy; P.start_dist = p.start_dist; P.max_range = p.max_range;
   P.mode = p.mode; P.W = w; P.H = h; P.row0 = row0; P.rows = rows; P.band_h = band_h; P.band_stride = band_stride;
-  const long long patches = (long long)((w + 7) / 8) * ((rows + 3) / 4);  // 8x4-pixel patches, pulled by persistent warps
-  if (patches > 0x7FFFFFFFll) return OSL_ERR_INVALID;
-  // per device: grid size for one resident wave, and a ring of patch-queue counters (each launch takes the next one
-  // and zeroes it in stream order, so launches on different streams never share a counter unless 256 are in flight)
-  static int s_ctas_per_sm[OSL_MAX_DEVICES], s_sms[OSL_MAX_DEVICES];
-  static unsigned int* s_queue[OSL_MAX_DEVICES];
-  static std::atomic<unsigned> s_launch{0};
-  int dev = 0;
-  OSL_CUDA(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= OSL_MAX_DEVICES) return OSL_ERR_UNSUPPORTED;
-  if (!s_queue[dev]) {
-    static std::mutex mu;
-    std::lock_guard<std::mutex> g(mu);
-    if (!s_queue[dev]) {
-      OSL_CUDA(cudaDeviceGetAttribute(&s_sms[dev], cudaDevAttrMultiProcessorCount, dev));
-      OSL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s_ctas_per_sm[dev], (const void*)k_raycast, RAY_THREADS, 0));
-      if (s_ctas_per_sm[dev] < 1) s_ctas_per_sm[dev] = 1;
-      unsigned int* q = nullptr;
-      OSL_CUDA(cudaMalloc(&q, OSL_RAY_QUEUES * sizeof(unsigned int)));
-      s_queue[dev] = q;
-    }
-  }
-  unsigned int* d_queue = s_queue[dev] + (s_launch.fetch_add(1) % OSL_RAY_QUEUES);
+  const long long warps = (long long)((w + 7) / 8) * ((rows + 3) / 4);  // one warp per 8x4-pixel patch
   const int wpb = RAY_THREADS / 32;
-  long long grid = (long long)s_sms[dev] * s_ctas_per_sm[dev];
-  if (grid * wpb > patches) grid = (patches + wpb - 1) / wpb;
-  OSL_CUDA(cudaMemsetAsync(d_queue, 0, sizeof(unsigned int), st));
-  k_raycast<<<(unsigned)grid, RAY_THREADS, 0, st>>>(d_pool, P, reinterpret_cast<uchar4*>(d_out), d_stats, d_queue,
-                                                   (int)patches);
+  k_raycast<<<(unsigned)((warps + wpb - 1) / wpb), RAY_THREADS, 0, st>>>(d_pool, P, reinterpret_cast<uchar4*>(d_out),
+                                                                         d_stats);
   OSL_LAUNCHED(1);
   OSL_CUDA(cudaGetLastError());
   return OSL_OK;
