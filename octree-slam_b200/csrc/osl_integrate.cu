@@ -712,6 +712,7 @@ __device__ __forceinline__ void analyze_block(int vb, int n, const u64* __restri
   for (int c = threadIdx.x; c < NC; c += AN_THREADS) s_cnt[c] = 0;
   __syncthreads();
   const int j = vb * AN_THREADS + threadIdx.x;
+  if (vb == 0 && threadIdx.x == 0) g_osl_prof[24] = (unsigned long long)clock64();
   if (j < n) {
     const u64 k = keys[j];
     int m = 0;
@@ -727,7 +728,9 @@ __device__ __forceinline__ void analyze_block(int vb, int n, const u64* __restri
         pay[j] = pm;
       }
       u32 st = 0;
+      if (vb == 0 && threadIdx.x == 0) g_osl_prof[25] = (unsigned long long)clock64();
       s = walk_frontier(pool, k, D, tp.quirks, m, st, wcache);
+      if (vb == 0 && threadIdx.x == 0) g_osl_prof[26] = (unsigned long long)clock64();
       start[j] = st;
       st_out = st;
       atomicAdd(&s_cnt[OSL_CLVL(D, m + 1)], 1u);  // heads every level d > m
@@ -798,6 +801,7 @@ __device__ __forceinline__ void assign_block(int vb, int n, const u64* __restric
     }
   }
   __syncthreads();
+  if (vb == 0 && tid == 0) g_osl_prof[27] = (unsigned long long)clock64();
   // exclusive scan over the warps + the block's global base + the bucket's global rank base
   for (int c = tid; c < NCu; c += AN_THREADS) {
     u32 run = s_base[c] + s_plan[c];
@@ -819,6 +823,7 @@ __device__ __forceinline__ void assign_block(int vb, int n, const u64* __restric
   // With it the head writes the child pointer of a node split this frame (svo.cu:269) right here, and k_levels
   // needs no dependent look-ups.  New tiles only get their value words initialised (svo.cu:272-275): the pool
   // beyond the live nodes is kept zero, so their word0 is already 0 and cannot race with the pointer writes.
+  if (vb == 0 && tid == 0) g_osl_prof[28] = (unsigned long long)clock64();
   const int s_eff = (s == OSL_NONE) ? D : s;
   const u32 le = lt | (1u << lane);
   // index (in level d-1) of the node on this key's path; below d0 the warp has no heads, so it is the last node

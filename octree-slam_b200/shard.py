@@ -57,26 +57,92 @@ def split_count_prefix(counts, group=None):
     return pass_base + lower, int(per_pass.sum().item())
 
 
+class _DeviceAlias:
+    """a raw device pointer as a torch tensor (no copy) through __cuda_array_interface__"""
+
+    def __init__(self, ptr, n_words):
+        self.__cuda_array_interface__ = {"shape": (int(n_words),), "typestr": "<i4", "data": (int(ptr), False),
+                                         "version": 2}
+
+
+def pool_tensor(svo, n_nodes):
+    """The first n_nodes nodes of `svo`'s pool as an int32 CUDA tensor ALIASING the pool (osl_svo_pool_device): a
+    collective can read from / write into the tree without a staging copy."""
+    import torch
+    ptr, cap = svo.pool_device()
+    assert n_nodes <= cap
+    return torch.as_tensor(_DeviceAlias(ptr, 2 * n_nodes), device="cuda:%d" % svo.device)
+
+
 def replicate_tree(svo, src=0, group=None, device=None):
-    """Broadcast the node pool of rank `src` to every rank and load it into `svo` (all ranks then hold the same tree).
-    `svo` needs .pool() -> uint32[2n] and .load(uint32[2n])."""
+    """Broadcast the node pool of rank `src` to every rank (all ranks then hold the same tree).
+
+    Trees on GPUs (objects with `pool_device`): the collective reads the source's pool and writes straight into the
+    receivers' pools -- device memory to device memory over NVLink, no host copy -- after a small header with the
+    geometry (max depth, centre, half edge: what a node index means) has been compared on every rank; the receiver
+    validates the child pointers before it publishes the tree (osl_svo_adopt).  Anything else (the CPU test doubles of
+    the gloo suite) goes through `.pool()` / `.load()` host arrays."""
     import torch
     dist = _dist()
     rank = dist.get_rank(group)
-    n = torch.zeros(1, dtype=torch.int64, device=device)
-    pool = None
+    on_gpu = hasattr(svo, "pool_device") and device is not None and str(device).startswith("cuda")
+    if not on_gpu:
+        n = torch.zeros(1, dtype=torch.int64, device=device)
+        pool = None
+        if rank == src:
+            pool = np.ascontiguousarray(svo.pool(), dtype=np.uint32)
+            n[0] = pool.size
+        dist.broadcast(n, src, group=group)
+        words = int(n.item())
+        buf = torch.empty(words, dtype=torch.int32, device=device)
+        if rank == src:
+            buf.copy_(torch.from_numpy(pool.view(np.int32)))
+        dist.broadcast(buf, src, group=group)
+        if rank != src:
+            svo.load(buf.cpu().numpy().view(np.uint32))
+        return words // 2
+    dev = "cuda:%d" % svo.device
+    hdr = torch.zeros(6, dtype=torch.float64, device=dev)
     if rank == src:
-        pool = np.ascontiguousarray(svo.pool(), dtype=np.uint32)
-        n[0] = pool.size
-    dist.broadcast(n, src, group=group)
-    words = int(n.item())
-    buf = torch.empty(words, dtype=torch.int32, device=device)
+        _, n_nodes, center, half = svo.view()
+        hdr[:] = torch.tensor([n_nodes, svo.max_depth, center[0], center[1], center[2], half], dtype=torch.float64)
+    dist.broadcast(hdr, src, group=group)
+    h = hdr.cpu().tolist()
+    n_nodes, depth, center, half = int(h[0]), int(h[1]), (h[2], h[3], h[4]), h[5]
+    if n_nodes == 0:
+        if rank != src:
+            svo.reset()
+        return 0
+    if rank != src:
+        svo.reserve(n_nodes)
+    dist.broadcast(pool_tensor(svo, n_nodes), src, group=group)  # NCCL: pool to pool
+    torch.cuda.synchronize()
+    if rank != src:
+        svo.adopt(n_nodes, depth, center, half)  # raises when the geometry differs or the pool is corrupt
+    return n_nodes
+
+
+def replicate_delta(svo, src=0, group=None):
+    """After ONE integrate call on rank `src` (and none on the others): ship what that call changed -- the touched
+    nodes' (index, word0, word1) and the appended tiles, osl_svo_delta_pack -- and apply it on every other rank.
+    Device to device; ~0.3 MB for a 640x480 frame instead of the whole pool.  Returns the delta's size in bytes."""
+    import torch
+    dist = _dist()
+    rank = dist.get_rank(group)
+    dev = "cuda:%d" % svo.device
+    nbytes = torch.zeros(1, dtype=torch.int64, device=dev)
     if rank == src:
-        buf.copy_(torch.from_numpy(pool.view(np.int32)))
+        nbytes[0] = svo.delta_bytes()
+    dist.broadcast(nbytes, src, group=group)
+    n = int(nbytes.item())
+    buf = torch.empty((n + 3) // 4, dtype=torch.int32, device=dev)
+    if rank == src:
+        svo.delta_pack(buf, n)
     dist.broadcast(buf, src, group=group)
     if rank != src:
-        svo.load(buf.cpu().numpy().view(np.uint32))
-    return words // 2
+        torch.cuda.synchronize()
+        svo.delta_apply(buf, n)
+    return n
 
 
 def gather_image(bands, tiles, h, w, dst=0, group=None, band=None):

@@ -145,6 +145,31 @@ class SVO:
         pool = np.ascontiguousarray(pool, dtype=np.uint32)
         _check(lib().osl_svo_upload(self._h, _hptr(pool), pool.size // 2), "osl_svo_upload")
 
+    # ---- replicas (shard.replicate_tree / replicate_delta) ------------------------------------------------
+    def reserve(self, n_nodes):
+        _check(lib().osl_svo_reserve(self._h, int(n_nodes)), "osl_svo_reserve")
+
+    def pool_device(self):
+        """(device pointer of the pool, capacity in nodes); waits for the pipeline"""
+        ptr, cap = C.c_void_p(), C.c_size_t()
+        _check(lib().osl_svo_pool_device(self._h, C.byref(ptr), C.byref(cap)), "osl_svo_pool_device")
+        return ptr.value, cap.value
+
+    def adopt(self, n_nodes, max_depth, center, half_edge):
+        """publish a pool a collective wrote into pool_device(): geometry must match, child pointers are validated"""
+        _check(lib().osl_svo_adopt(self._h, int(n_nodes), int(max_depth), _f(center), float(half_edge)), "osl_svo_adopt")
+
+    def delta_bytes(self):
+        return int(lib().osl_svo_delta_bytes(self._h))
+
+    def delta_pack(self, buf, cap_bytes, stream=None):
+        n = C.c_size_t()
+        _check(lib().osl_svo_delta_pack(self._h, buf.data_ptr(), int(cap_bytes), C.byref(n), stream), "osl_svo_delta_pack")
+        return n.value
+
+    def delta_apply(self, buf, nbytes, stream=None):
+        _check(lib().osl_svo_delta_apply(self._h, buf.data_ptr(), int(nbytes), stream), "osl_svo_delta_apply")
+
     def join(self, stream=None):
         """order `stream` after every frame enqueued so far (device-side)"""
         _check(lib().osl_svo_join(self._h, stream), "osl_svo_join")

@@ -19,6 +19,7 @@ ROLES = ["structure", "values", "emit", "sort", "arrival"]
 def main():
     import torch
     frames = int(sys.argv[1]) if len(sys.argv) > 1 else 24
+    host = len(sys.argv) > 2 and sys.argv[2] == "host"  # pinned host frames through osl_integrate_depth_host
     w, h, D = 640, 480, 16
     pkg = graft.load_package()
     lib = pkg.lib()
@@ -29,16 +30,20 @@ def main():
     for k in range(40 + frames):
         pose = pkg.synth.orbit_pose(k)
         depth, rgb = pkg.synth.make_frame(w, h, pose, seed=k)
-        keep.append((torch.from_numpy(depth).cuda(), torch.from_numpy(rgb).cuda(), pose))
+        if host:
+            keep.append((torch.from_numpy(depth).pin_memory().numpy(), torch.from_numpy(rgb).pin_memory().numpy(), pose))
+        else:
+            keep.append((torch.from_numpy(depth).cuda(), torch.from_numpy(rgb).cuda(), pose))
     torch.cuda.synchronize()
+    integrate = svo.integrate_depth_host if host else svo.integrate_depth
     for d, c, pose in keep[:40]:
-        svo.integrate_depth(d, c, fx, fy, pose)
+        integrate(d, c, fx, fy, pose)
     svo.sync()
     lib.osl_debug_trace(svo._h, 1, None)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for d, c, pose in keep[40:]:
-        svo.integrate_depth(d, c, fx, fy, pose)
+        integrate(d, c, fx, fy, pose)
     svo.join(None)
     e1.record()
     svo.sync()

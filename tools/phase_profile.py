@@ -17,7 +17,10 @@ NAMES = {
     "k_sort_bucket": [(8, 9, "scan list"), (9, 10, "smem radix sort"), (10, 11, "write")],
     "k_structure": [(16, 17, "A analyze (prefix, run-min, walk)"), (17, 18, "wait for all flags / barrier"),
                     (18, 19, "sum vectors / column scans"), (19, 20, "(barrier)"), (20, 21, "B2 plan"),
-                    (21, 22, "C assign (short walk, level lists, tile init)")],
+                    (21, 22, "C assign (short walk, level lists, tile init)"),
+                    (16, 24, "  A: prologue (n, cur, splitters)"), (24, 25, "  A: key + predecessor + run-min"),
+                    (25, 26, "  A: walk (thread 0)"), (26, 17, "  A: counts, block sync, publish"),
+                    (21, 27, "  C: pass 1 (ballots)"), (27, 28, "  C: warp scan"), (28, 22, "  C: pass 2 (walk, lists, tiles)")],
     "k_levels": [(32, 35, "leaves"), (35, 36, "wide levels (grid barrier each)"), (36, 37, "one-sided barrier"),
                  (37, 38, "stage narrow top"), (38, 39, "smem fold")],
 }
