@@ -889,7 +889,7 @@ struct StructArgs {
   u64* wcache;  // walk cache (NULL = off)
 };
 #define STRUCT_MAXG 1024  // most CTAs a structure grid / role may have (s_has)
-#define STRUCT_SMEM ((AN_WARPS + 4) * NC_MAX * 4 + AN_WARPS * 4 + STRUCT_MAXG)
+#define STRUCT_SMEM ((AN_WARPS + 4) * NC_MAX * 4 + AN_WARPS * 4 + 2 * STRUCT_MAXG)
 
 __device__ __forceinline__ void structure_body(const StructArgs& A, int bid, int G, unsigned char* s_raw) {
   const u64* __restrict__ keys_sorted = A.keys_sorted; const u64* __restrict__ keys_dense = A.keys_dense;
@@ -949,49 +949,77 @@ __device__ __forceinline__ void structure_body(const StructArgs& A, int bid, int
 
   // wait for every CTA's vector (all CTAs are co-resident: cooperative launch / first roles of k_frame), then sum them:
   // totals for the plan, exclusive prefix for the own range -- one wait, no grid barrier
-  uint8_t* s_has = reinterpret_cast<uint8_t*>(s_scan + AN_WARPS);  // [G] CTA b published bucket counters
+  unsigned short* s_list = reinterpret_cast<unsigned short*>(s_scan + AN_WARPS);  // CTAs that published bucket counters
   if (warp == 0) {
-    u32 any = 0;
-    for (int b = lane; b < G; b += 32) {
-      long long spin = 0;  // bounded: a vector that never arrives traps (error to the host) instead of hanging the GPU
-      u32 v;
-      while (((v = ld_vol(&flags[b])) & 0x7FFFFFFFu) != epoch)
-        if (++spin > (1ll << 31)) __trap();
-      s_has[b] = (uint8_t)(v >> 31);
-      any |= v >> 31;
+    u32 n_list = 0;
+    for (int b0 = 0; b0 < G; b0 += 32) {
+      const int b = b0 + lane;
+      u32 v = 0;
+      if (b < G) {
+        long long spin = 0;  // bounded: a vector that never arrives traps (error to the host) instead of hanging the GPU
+        while (((v = ld_vol(&flags[b])) & 0x7FFFFFFFu) != epoch)
+          if (++spin > (1ll << 31)) __trap();
+      }
+      const u32 has = __ballot_sync(FULL, (v >> 31) != 0u);
+      if (v >> 31) s_list[n_list + __popc(has & lanemask_lt())] = (unsigned short)b;
+      n_list += __popc(has);
     }
-    any = __any_sync(FULL, any != 0u);
-    if (lane == 0) s_scan[0] = any;
+    if (lane == 0) s_scan[0] = n_list;
     __threadfence();
   }
   __syncthreads();
-  const bool any_cta_split = s_scan[0] != 0u;
-  __syncthreads();
+  const int n_list = (int)s_scan[0];
   PROF(18);
-  for (int c = tid; c < NC; c += AN_THREADS) {
+  {
+    // per-level counters (always published): 16 groups of CTAs x 32 counter lanes, one batch of independent loads per
+    // thread, then a fold over the groups in shared memory -- one L2 round trip instead of one per 16 CTAs
+    u32* s_red = &s_w[0][0];  // [16][64]: totals, exclusive prefixes (phase A's scratch is free, phase C re-initialises it)
+    const int c = tid & 31, g = tid >> 5;
     u32 tot = 0, pre = 0;
-    const int mine = bid;
     if (c < D) {
-      for (int b0 = 0; b0 < G; b0 += 16) {
-        u32 v[16];
+      for (int b0 = g; b0 < G; b0 += 4 * AN_WARPS) {
+        u32 v[4];
 #pragma unroll
-        for (int k = 0; k < 16; k++) v[k] = (b0 + k < G) ? __ldcg(&ctatot[(size_t)(b0 + k) * NC + c]) : 0u;
+        for (int k = 0; k < 4; k++) {
+          const int b = b0 + k * AN_WARPS;
+          v[k] = (b < G) ? __ldcg(&ctatot[(size_t)b * NC + c]) : 0u;
+        }
 #pragma unroll
-        for (int k = 0; k < 16; k++) {
+        for (int k = 0; k < 4; k++) {
           tot += v[k];
-          if (b0 + k < mine) pre += v[k];
+          if (b0 + k * AN_WARPS < bid) pre += v[k];
         }
       }
-    } else if (any_cta_split) {
-      for (int b = 0; b < G; b++) {
-        if (!s_has[b]) continue;
-        const u32 v = __ldcg(&ctatot[(size_t)b * NC + c]);
-        tot += v;
-        if (b < mine) pre += v;
-      }
     }
-    s_tot[c] = tot;
-    s_base[c] = pre;
+    s_red[g * 64 + c] = tot;
+    s_red[g * 64 + 32 + c] = pre;
+    __syncthreads();
+    if (tid < D) {
+      u32 t2 = 0, p2 = 0;
+#pragma unroll
+      for (int q = 0; q < AN_WARPS; q++) { t2 += s_red[q * 64 + tid]; p2 += s_red[q * 64 + 32 + tid]; }
+      s_tot[tid] = t2;
+      s_base[tid] = p2;
+    }
+    // bucket counters: only the (few) CTAs that split something published them
+    for (int cc = D + tid; cc < NC; cc += AN_THREADS) {
+      u32 t2 = 0, p2 = 0;
+      for (int l0 = 0; l0 < n_list; l0 += 4) {
+        u32 v[4]; int bb[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          bb[k] = (l0 + k < n_list) ? (int)s_list[l0 + k] : -1;
+          v[k] = bb[k] >= 0 ? __ldcg(&ctatot[(size_t)bb[k] * NC + cc]) : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          t2 += v[k];
+          if (bb[k] >= 0 && bb[k] < bid) p2 += v[k];
+        }
+      }
+      s_tot[cc] = t2;
+      s_base[cc] = p2;
+    }
   }
   __syncthreads();
   PROF(19);
@@ -1891,11 +1919,17 @@ osl_status osl_run_integrate(osl_svo* t, EmitParams& ep, const void* colors, cud
     }
     ep.depth = t->d_depth_stage[sslot]; ep.rgb = rgb_dev;
     if (fused) {
-      const u32 val = (u32)(t->stage_seq + 1);
-      t->h_ready_vals[t->stage_seq % 64] = val;
-      OSL_CUDA(cudaMemcpyAsync(t->d_ready + sslot, &t->h_ready_vals[t->stage_seq % 64], sizeof(u32),
-                               cudaMemcpyHostToDevice, t->copy_stream));
-      ep.ready = t->d_ready + sslot; ep.ready_seq = val;
+      static const int host_event = getenv("OSL_FZ_HOST_EVENT") ? 1 : 0;  // (experiment: event edge instead of the flag)
+      if (host_event) {
+        OSL_CUDA(cudaEventRecord(t->stage_copied[sslot], t->copy_stream));
+        OSL_CUDA(cudaStreamWaitEvent(sS, t->stage_copied[sslot], 0));
+      } else {
+        const u32 val = (u32)(t->stage_seq + 1);
+        t->h_ready_vals[t->stage_seq % 64] = val;
+        OSL_CUDA(cudaMemcpyAsync(t->d_ready + sslot, &t->h_ready_vals[t->stage_seq % 64], sizeof(u32),
+                                 cudaMemcpyHostToDevice, t->copy_stream));
+        ep.ready = t->d_ready + sslot; ep.ready_seq = val;
+      }
       t->stage_frame[sslot] = f + 1;
     } else {
       OSL_CUDA(cudaEventRecord(t->stage_copied[sslot], t->copy_stream));  // k_emit (stream E) waits for it
