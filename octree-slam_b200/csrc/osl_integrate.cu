@@ -659,11 +659,12 @@ __device__ __forceinline__ int key_digit(u64 key, int D, int d) { return (int)((
 // keep their has-children flags for the life of the tree, so an entry can never go stale (the host clears the table
 // when the pool is replaced: reset / upload / expand).  A hit replaces WC_H dependent loads from the root by one.
 #define WC_SLOTS 4096
+#define PATH_KEEP 8
 __device__ __forceinline__ int walk_cache_depth(int D) { const int h = D - 5 < 11 ? D - 5 : 11; return h >= 3 ? h : 0; }
 __device__ __forceinline__ u32 walk_cache_slot(u64 prefix) { return (u32)((prefix * 0x9E3779B97F4A7C15ull) >> 52); }
 
 __device__ __forceinline__ int walk_frontier(const u32* __restrict__ pool, u64 key, int D, int quirks, int m,
-                                             u32& start, u64* wcache) {
+                                             u32& start, u64* wcache, u32* s_path) {
   u32 node = (u32)key_digit(key, D, 1);
   int t = 1;
   const int h = wcache ? walk_cache_depth(D) : 0;
@@ -680,6 +681,8 @@ __device__ __forceinline__ int walk_frontier(const u32* __restrict__ pool, u64 k
     if (t == m + 1) start = node;  // the first node this key heads: where phase C resumes the walk
     const u32 w0 = pool[2 * (size_t)node];
     if (!(w0 & OSL_FLAG)) return t;
+    // the child tiles along the last PATH_KEEP levels stay in shared memory: phase C walks the same nodes again
+    if (D - 1 - t < PATH_KEEP) s_path[(D - 1 - t) * AN_THREADS + threadIdx.x] = w0 & OSL_MASK;
     node = (w0 & OSL_MASK) + (u32)key_digit(key, D, t + 1);
   }
   if (m + 1 == D) start = node;  // the leaf itself (its whole path exists)
@@ -705,8 +708,8 @@ __device__ __forceinline__ int walk_frontier(const u32* __restrict__ pool, u64 k
 __device__ __forceinline__ void analyze_block(int vb, int n, const u64* __restrict__ keys, u32* pay, int mode,
                                               const u32* pool, const TreeParams& tp, uint8_t* __restrict__ m8,
                                               uint8_t* __restrict__ s8, u32* __restrict__ start,
-                                              u32* s_ctot, u32* s_cnt, u64* wcache, u64& k_out, int& m_out,
-                                              int& s_out, u32& st_out) {
+                                              u32* s_ctot, u32* s_cnt, u64* wcache, u32* s_path, u64& k_out,
+                                              int& m_out, int& s_out, u32& st_out) {
   const int D = tp.D, NC = OSL_NCOUNT(D);
   k_out = 0; m_out = D; s_out = OSL_NONE; st_out = 0;
   for (int c = threadIdx.x; c < NC; c += AN_THREADS) s_cnt[c] = 0;
@@ -729,7 +732,7 @@ __device__ __forceinline__ void analyze_block(int vb, int n, const u64* __restri
       }
       u32 st = 0;
       if (vb == 0 && threadIdx.x == 0) g_osl_prof[25] = (unsigned long long)clock64();
-      s = walk_frontier(pool, k, D, tp.quirks, m, st, wcache);
+      s = walk_frontier(pool, k, D, tp.quirks, m, st, wcache, s_path);
       if (vb == 0 && threadIdx.x == 0) g_osl_prof[26] = (unsigned long long)clock64();
       start[j] = st;
       st_out = st;
@@ -767,7 +770,8 @@ __device__ __forceinline__ void assign_block(int vb, int n, const u64* __restric
                                              const uint8_t* __restrict__ s8, const u32* __restrict__ start,
                                              u32* s_base, const LevelArrays& lv, int mode, u32 size0,
                                              int n_invalid_front, const u32* s_plan, u32 (*s_w)[NC_MAX],
-                                             bool carried, u64 k_in, int m_in, int s_in, u32 st_in) {
+                                             bool carried, u64 k_in, int m_in, int s_in, u32 st_in,
+                                             const u32* s_path) {
   const int D = tp.D, NC = OSL_NCOUNT(D);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const u32 lt = lanemask_lt();
@@ -778,6 +782,8 @@ __device__ __forceinline__ void assign_block(int vb, int n, const u64* __restric
   if (carried) { k = k_in; m = m_in; s = s_in; node = st_in; }  // (a CTA that owns ONE block kept phase A's registers)
   else if (j < n) { k = keys[j]; m = m8[j]; s = s8[j]; node = start[j]; }
   const bool unique = m < D;
+  // the winning input of the leaf (needed at the last level only): in flight while the levels above are laid out
+  const u32 paymin = (unique && mode != 2 && j < n) ? __ldcg(&pay[j]) : 0u;
 
   // No lane of this warp heads a level <= the warp's smallest m: the per-level collectives start one level above it
   // (one level early so that par_idx / path_tile of the first headed level come out of the loop itself).
@@ -847,7 +853,8 @@ __device__ __forceinline__ void assign_block(int vb, int n, const u64* __restric
     u32 ct = 0xFFFFFFFFu;
     if (f) {
       if (d < D && d < s_eff) {
-        ct = pool[2 * (size_t)node] & OSL_MASK;
+        // (a CTA that owns one block finds the child tile phase A read on the same path in shared memory)
+        ct = (carried && D - 1 - d < PATH_KEEP) ? s_path[(D - 1 - d) * AN_THREADS + tid] : (pool[2 * (size_t)node] & OSL_MASK);
         node = ct + (u32)key_digit(k, D, d + 1);
       } else if (sp) {
         const u32 rank = s_w[warp][OSL_CBKT(D, s, d)] + __popc(peers & lt);
@@ -872,7 +879,7 @@ __device__ __forceinline__ void assign_block(int vb, int n, const u64* __restric
       lv.digit[o] = (uint8_t)key_digit(k, D, d);
       lv.par[o] = par_idx;
       lv.self[o] = self;
-      if (d == D) lv.src[lbase + __popc(bal & lt)] = (mode == 2) ? (u32)(n_invalid_front + j) : __ldcg(&pay[j]);
+      if (d == D) lv.src[lbase + __popc(bal & lt)] = (mode == 2) ? (u32)(n_invalid_front + j) : paymin;
     }
     // the level-d node on this key's path: its own if it heads it, else the last one headed before it
     par_idx = lbase + __popc(bal & le) - 1u;
@@ -889,7 +896,7 @@ struct StructArgs {
   u64* wcache;  // walk cache (NULL = off)
 };
 #define STRUCT_MAXG 1024  // most CTAs a structure grid / role may have (s_has)
-#define STRUCT_SMEM ((AN_WARPS + 4) * NC_MAX * 4 + AN_WARPS * 4 + 2 * STRUCT_MAXG)
+#define STRUCT_SMEM ((AN_WARPS + 4) * NC_MAX * 4 + AN_WARPS * 4 + 2 * STRUCT_MAXG + 8 * 512 * 4)
 
 __device__ __forceinline__ void structure_body(const StructArgs& A, int bid, int G, unsigned char* s_raw) {
   const u64* __restrict__ keys_sorted = A.keys_sorted; const u64* __restrict__ keys_dense = A.keys_dense;
@@ -905,6 +912,7 @@ __device__ __forceinline__ void structure_body(const StructArgs& A, int bid, int
   u32* s_base = s_tot + NC_MAX;
   u32* s_ctot = s_base + NC_MAX;
   u32* s_scan = s_ctot + NC_MAX;
+  u32* s_path = reinterpret_cast<u32*>(s_raw + (AN_WARPS + 4) * NC_MAX * 4 + AN_WARPS * 4 + 2 * STRUCT_MAXG);  // [PATH_KEEP][512]
   const int D = tp.D, NC = OSL_NCOUNT(D);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = __ldcg(&fs->acc_emit[parity]);
@@ -931,7 +939,7 @@ __device__ __forceinline__ void structure_body(const StructArgs& A, int bid, int
   // SM the walk latency is already hidden and the extra serial step only adds two block barriers per block.)
   u64 ck = 0; int cm = D, cs = OSL_NONE; u32 cst = 0;  // this thread's key state when the CTA owns a single block
   for (int vb = vb0; vb < vb1; vb++)
-    analyze_block(vb, n, keys, pay, mode, pool, tp, m8, s8, start, s_ctot, &s_w[0][0], A.wcache, ck, cm, cs, cst);
+    analyze_block(vb, n, keys, pay, mode, pool, tp, m8, s8, start, s_ctot, &s_w[0][0], A.wcache, s_path, ck, cm, cs, cst);
   const bool carried = (vb1 - vb0 == 1);
   // publish this CTA's counter vector behind an epoch flag (every CTA publishes, also one without blocks).  Compact
   // form: the D per-level counters always; the (D+1)^2 bucket counters only when a key of this CTA splits a node --
@@ -1059,7 +1067,7 @@ __device__ __forceinline__ void structure_body(const StructArgs& A, int bid, int
   if (!overflow) {
     for (int vb = vb0; vb < vb1; vb++)
       assign_block(vb, n, keys, pay, pool, tp, m8, s8, start, s_base, lv, mode, size0, n_invalid_front, s_plan, s_w,
-                   carried, ck, cm, cs, cst);
+                   carried, ck, cm, cs, cst, s_path);
   }
   PROF(22);
 
@@ -1883,9 +1891,8 @@ osl_status osl_run_integrate(osl_svo* t, EmitParams& ep, const void* colors, cud
 
   // Host frames: the planes go through one of OSL_STAGES device slots on the copy stream, so that the transfer of
   // frame f+1 overlaps the kernels of frame f.  Four-kernel path: events in both directions (slot free <- k_levels,
-  // k_emit <- copies).  k_frame path: no events at all -- the host recycles a slot once the frame that used it has
-  // reported completion in its pinned result block, and a 4-byte copy queued behind the planes carries a sequence
-  // number the emit role waits for.
+  // k_emit <- copies).  k_frame path: the host recycles a slot once the frame that used it has reported completion in
+  // its pinned result block (no event), and the frame stream waits for the copies through one event.
   const int sslot = (int)(t->stage_seq % OSL_STAGES);
   if (host) {
     const size_t np = (size_t)n;
@@ -1919,8 +1926,12 @@ osl_status osl_run_integrate(osl_svo* t, EmitParams& ep, const void* colors, cud
     }
     ep.depth = t->d_depth_stage[sslot]; ep.rgb = rgb_dev;
     if (fused) {
-      static const int host_event = getenv("OSL_FZ_HOST_EVENT") ? 1 : 0;  // (experiment: event edge instead of the flag)
-      if (host_event) {
+      // copies -> emit role: one event edge per frame on the frame stream.  (The alternative, a 4-byte copy queued
+      // behind the planes that the emit CTAs spin on -- which would keep the frame stream free of anything but
+      // launches -- was measured slower, 47.4 vs 41.6 us per frame: 150 resident CTAs polling a flag for most of a
+      // 36 us transfer get in the way of the other three roles.  OSL_FZ_HOST_FLAG=1 selects it.)
+      static const int host_flag = getenv("OSL_FZ_HOST_FLAG") ? 1 : 0;
+      if (!host_flag) {
         OSL_CUDA(cudaEventRecord(t->stage_copied[sslot], t->copy_stream));
         OSL_CUDA(cudaStreamWaitEvent(sS, t->stage_copied[sslot], 0));
       } else {
@@ -1942,9 +1953,13 @@ osl_status osl_run_integrate(osl_svo* t, EmitParams& ep, const void* colors, cud
     const int cap = spin_cap < t->structure_grid ? spin_cap : t->structure_grid;
     osl_svo::FzStage nw;
     nw.valid = 1; nw.f = f; nw.n = n; nw.fslot = fslot; nw.bslot = bslot; nw.rgb = ep.rgb;
-    nw.gS = grid_for(exp_emit, AN_THREADS, cap) + 1;  // (+1: the book-keeping CTA usually has no block of its own)
+    // (the grids only cost time when they are too small -- every role loops -- so they follow the last frame closely:
+    // the four roles of a 640x480 frame then fit the machine in ONE wave of 2 CTAs per SM)
+    const long long fit_emit = (long long)(1.15 * t->hint_emit * (double)n / (double)t->hint_n_in) + 64;
+    const long long fit_level = (long long)(1.15 * t->hint_level * (double)n / (double)t->hint_n_in) + 64;
+    nw.gS = grid_for(fit_emit < exp_emit ? fit_emit : exp_emit, AN_THREADS, cap) + 1;  // (+1: the book-keeping CTA usually has no block of its own)
     if (nw.gS > cap) nw.gS = cap;
-    nw.gV = grid_for(exp_level, LEVEL_THREADS, spin_cap < t->levels_grid ? spin_cap : t->levels_grid);
+    nw.gV = grid_for(fit_level < exp_level ? fit_level : exp_level, LEVEL_THREADS, spin_cap < t->levels_grid ? spin_cap : t->levels_grid);
     rc = fused_launch(t, &nw, &ep);
     if (rc) return rc;
     const int slot = (int)(f % OSL_RING);
