@@ -166,7 +166,7 @@ void osl_svo_destroy(osl_svo* t) {
   cudaFree(t->d_pool);
   for (int f = 0; f < OSL_FRONT; f++) {
     cudaFree(t->d_keysA[f]); cudaFree(t->d_keysB[f]); cudaFree(t->d_payA[f]); cudaFree(t->d_payB[f]);
-    cudaFree(t->d_cta_hist[f]);
+    cudaFree(t->d_cta_hist[f]); cudaFree(t->d_bkeys[f]); cudaFree(t->d_bpay[f]);
     if (t->emit_done[f]) cudaEventDestroy(t->emit_done[f]);
     if (t->sort_done[f]) cudaEventDestroy(t->sort_done[f]);
   }

@@ -47,11 +47,14 @@ __device__ unsigned long long g_osl_prof[64];
 #define EMIT_TH 32
 #define EMIT_SLOTS 4096
 #define EMIT_EMPTY 0xFFFFFFFFFFFFFFFFull
-#define EMIT_SMEM (EMIT_SLOTS * 8 + EMIT_SLOTS * 4 + EMIT_TILE * 2 + 16)
+#define EMIT_SMEM (EMIT_SLOTS * 8 + EMIT_SLOTS * 4 + EMIT_TILE * 2 + 16 + EMIT_TILE * 2 + OSL_BUCKETS * 16)
 
+// `split` != NULL: the tile's entries are ALSO filed by splitter range (the OSL_BUCKETS key ranges of k_sort_bucket)
+// into bkeys / bpay[range][OSL_BUCKET_CAP], so that the sort reads its range directly instead of scanning the list.
 __device__ __forceinline__ void emit_body(const EmitParams& p, const TreeParams& tp, int vec_ok, u64* __restrict__ keys,
                                           u32* __restrict__ pay, u64* __restrict__ keys_dense, FrameState* fs,
-                                          int parity, int bid, unsigned char* s_raw) {
+                                          int parity, int bid, unsigned char* s_raw, const u64* __restrict__ split,
+                                          u64* __restrict__ bkeys, u32* __restrict__ bpay) {
   u64* s_key = reinterpret_cast<u64*>(s_raw);
   u32* s_pay = reinterpret_cast<u32*>(s_raw + EMIT_SLOTS * 8);
   unsigned short* s_list = reinterpret_cast<unsigned short*>(s_raw + EMIT_SLOTS * 12);
@@ -173,14 +176,49 @@ __device__ __forceinline__ void emit_body(const EmitParams& p, const TreeParams&
     keys[base + i] = s_key[slot];
     pay[base + i] = s_pay[slot];
   }
+  if (split && dedup) {
+    // file the entries by splitter range: range of a key = number of splitters <= key (k_sort_bucket's lo <= k < hi)
+    unsigned short* s_pos = reinterpret_cast<unsigned short*>(s_misc + 4);             // [EMIT_TILE] rank inside (tile, range)
+    u32* s_bcnt = reinterpret_cast<u32*>(s_pos + EMIT_TILE);                          // [OSL_BUCKETS]
+    u32* s_bbase = s_bcnt + OSL_BUCKETS;                                              // [OSL_BUCKETS]
+    u64* s_split = reinterpret_cast<u64*>(s_bbase + OSL_BUCKETS);                     // [OSL_BUCKETS - 1] (+1 pad)
+    if (tid < OSL_BUCKETS) { s_bcnt[tid] = 0; s_split[tid] = tid < OSL_BUCKETS - 1 ? __ldg(&split[tid]) : ~0ull; }
+    __syncthreads();
+    for (u32 i = tid; i < cnt; i += EMIT_THREADS) {
+      const u64 k = s_key[s_list[i]];
+      int b = 0;
+#pragma unroll
+      for (int step = OSL_BUCKETS / 2; step > 0; step >>= 1)
+        if (b + step - 1 < OSL_BUCKETS - 1 && s_split[b + step - 1] <= k) b += step;
+      s_pos[i] = (unsigned short)atomicAdd(&s_bcnt[b], 1u);
+    }
+    __syncthreads();
+    if (tid < OSL_BUCKETS && s_bcnt[tid])
+      s_bbase[tid] = atomicAdd(reinterpret_cast<u32*>(&fs->acc_bucket[parity][tid]), s_bcnt[tid]);
+    __syncthreads();
+    for (u32 i = tid; i < cnt; i += EMIT_THREADS) {
+      const u32 slot = (u32)s_list[i];
+      const u64 k = s_key[slot];
+      int b = 0;
+#pragma unroll
+      for (int step = OSL_BUCKETS / 2; step > 0; step >>= 1)
+        if (b + step - 1 < OSL_BUCKETS - 1 && s_split[b + step - 1] <= k) b += step;
+      const u32 at = s_bbase[b] + (u32)s_pos[i];
+      if (at < OSL_BUCKET_CAP) {  // (a range that overflows is counted in full and sorted the slow way, from the list)
+        bkeys[(size_t)b * OSL_BUCKET_CAP + at] = k;
+        bpay[(size_t)b * OSL_BUCKET_CAP + at] = s_pay[slot];
+      }
+    }
+  }
   PROF(3);
 }
 
 __global__ void __launch_bounds__(EMIT_THREADS)
 k_emit(EmitParams p, TreeParams tp, int vec_ok, u64* __restrict__ keys, u32* __restrict__ pay,
-       u64* __restrict__ keys_dense, FrameState* fs, int parity) {
+       u64* __restrict__ keys_dense, FrameState* fs, int parity, const u64* __restrict__ split, u64* __restrict__ bkeys,
+       u32* __restrict__ bpay) {
   extern __shared__ __align__(16) unsigned char s_raw[];
-  emit_body(p, tp, vec_ok, keys, pay, keys_dense, fs, parity, (int)blockIdx.x, s_raw);
+  emit_body(p, tp, vec_ok, keys, pay, keys_dense, fs, parity, (int)blockIdx.x, s_raw, split, bkeys, bpay);
 }
 
 // ------------------------------------------------------------------------------------------------ k_sort
@@ -404,9 +442,10 @@ k_sort(u64* kA, u32* pA, u64* kB, u32* pB, u32* cta_hist, const FrameState* fs, 
 // skips the digits on which all its keys agree (a contiguous key range shares its high digits), and writes them out.
 // A bucket that does not fit (scene cut, first frames) is sorted by the same CTA through global memory: slow but
 // correct, and the next frame gets fresh splitters.
-#define BK_BUCKETS 64
+#define BK_BUCKETS OSL_BUCKETS
 #define BK_THREADS SORT_THREADS
 #define BK_CAP SORT_TILE
+static_assert(BK_CAP == OSL_BUCKET_CAP, "bucket capacity");
 #define BK_SMEM (2 * BK_CAP * 8 + 2 * BK_CAP * 4 + (int)sizeof(BucketShared))
 
 struct BucketShared {
@@ -504,9 +543,11 @@ __device__ void cta_sort_global(u64* k0, u32* p0, u64* k1, u32* p1, int c, int p
 }
 
 // (runs on the first BK_THREADS threads of its CTA)
+// bkeys != NULL: k_emit filed the list by range -- a range that fits is read directly, the scan is skipped.
 __device__ __forceinline__ void bucket_body(const u64* kin, const u32* pin, u64* kout, u32* pout, u64* kscr, u32* pscr,
                                             const FrameState* fs, const u64* __restrict__ split, int passes, int parity,
-                                            int bid, unsigned char* s_raw) {
+                                            int bid, unsigned char* s_raw, const u64* __restrict__ bkeys,
+                                            const u32* __restrict__ bpay) {
   BucketShared& S = *reinterpret_cast<BucketShared*>(s_raw + 2 * BK_CAP * 8 + 2 * BK_CAP * 4);
   u64* const s_key0 = reinterpret_cast<u64*>(s_raw);                    // [2][BK_CAP]
   u32* const s_pay0 = reinterpret_cast<u32*>(s_raw + 2 * BK_CAP * 8);   // [2][BK_CAP]
@@ -520,13 +561,34 @@ __device__ __forceinline__ void bucket_body(const u64* kin, const u32* pin, u64*
   __syncthreads();
   PROF(8);
 
+  bool direct = false;
+  if (bkeys) {
+    // counts per range are final (k_emit ran in an earlier launch / kernel): own count, and the ranges below = offset
+    const int mine = __ldcg(&fs->acc_bucket[parity][b]);
+    if (tid < b) {
+      const u32 v = (u32)__ldcg(&fs->acc_bucket[parity][tid]);
+      if (v) atomicAdd(&S.below, v);
+    }
+    if (mine <= BK_CAP) {
+      direct = true;
+      for (int e = tid; e < mine; e += BK_THREADS) {
+        s_key0[e] = __ldcg(&bkeys[(size_t)b * BK_CAP + e]);
+        s_pay0[e] = __ldcg(&bpay[(size_t)b * BK_CAP + e]);
+      }
+      if (tid == 0) S.cnt = (u32)mine;
+    } else if (tid == 0) {
+      S.below = 0;  // (the scan below recounts)
+    }
+    __syncthreads();
+    if (!direct) { if (tid == 0) S.below = 0; __syncthreads(); }
+  }
   // scan the whole list: entries of lower buckets are counted, entries of this bucket are kept
   u32 below = 0;
   // (every CTA reads the same L2-resident lines: each starts at a different rotation of the list so that the 64 CTAs
   // spread over the L2 slices instead of queueing on the same line at the same time.  A TMA bulk-copy ring
   // (cp.async.bulk + mbarrier, 3 x 16 KB stages) was measured here too: 8.6 us vs 7.0 us for these register-staged
   // loads -- the limit is that contention, not load issue)
-  const int iters = (n + BK_THREADS * 16 - 1) / (BK_THREADS * 16);
+  const int iters = direct ? 0 : (n + BK_THREADS * 16 - 1) / (BK_THREADS * 16);
   const int rot = iters > 0 ? (int)(((long long)b * iters) / BK_BUCKETS) : 0;
   for (int it = 0; it < iters; it++) {  // 16 independent loads in flight per thread
     const int i0 = ((it + rot) % iters) * (BK_THREADS * 16);
@@ -555,7 +617,7 @@ __device__ __forceinline__ void bucket_body(const u64* kin, const u32* pin, u64*
   const int c = (int)S.cnt;
   const u32 offset = S.below;
   // payloads of the kept entries: one parallel round trip (a load inside the scan loop would stall it every time)
-  if (c <= BK_CAP)
+  if (c <= BK_CAP && !direct)
     for (int e = tid; e < c; e += BK_THREADS) s_pay0[e] = pin[s_pay0[e]];
   PROF(9);
   if (c == 0) return;
@@ -639,9 +701,10 @@ __device__ __forceinline__ void bucket_body(const u64* kin, const u32* pin, u64*
 
 __global__ void __launch_bounds__(BK_THREADS)
 k_sort_bucket(const u64* kin, const u32* pin, u64* kout, u32* pout, u64* kscr, u32* pscr, const FrameState* fs,
-              const u64* __restrict__ split, int passes, int parity) {
+              const u64* __restrict__ split, int passes, int parity, const u64* __restrict__ bkeys,
+              const u32* __restrict__ bpay) {
   extern __shared__ __align__(16) unsigned char s_raw[];
-  bucket_body(kin, pin, kout, pout, kscr, pscr, fs, split, passes, parity, (int)blockIdx.x, s_raw);
+  bucket_body(kin, pin, kout, pout, kscr, pscr, fs, split, passes, parity, (int)blockIdx.x, s_raw, bkeys, bpay);
 }
 
 // ------------------------------------------------------------------------------------------------ k_analyze
@@ -1075,6 +1138,7 @@ __device__ __forceinline__ void structure_body(const StructArgs& A, int bid, int
   // stays off the critical path): the frame's result block, to the device copy k_levels reads and straight to the
   // pinned host ring (no cudaMemcpyAsync per frame; the host reads it after the event that follows k_levels).
   if (bid == G - 1) {
+    if (tid < OSL_BUCKETS) fs->acc_bucket[parity][tid] = 0;
     if (bs >= 1) {
       const int v = (int)(woff + incl - val);
       fr->base[bs * (D + 1) + bd] = v; hr->base[bs * (D + 1) + bd] = v;
@@ -1371,10 +1435,11 @@ __global__ void __launch_bounds__(LEVEL_THREADS) k_levels(LevelArgs A) {
 // spinning CTA can never keep the CTA it waits for off the machine.
 struct SortArgs {
   const u64* kin; const u32* pin; u64* kout; u32* pout; u64* kscr; u32* pscr; const FrameState* fs;
-  const u64* split; int passes; int parity;
+  const u64* split; int passes; int parity; const u64* bkeys; const u32* bpay;
 };
 struct EmitArgs {
   EmitParams p; TreeParams tp; int vec_ok; u64* keys; u32* pay; u64* keys_dense; FrameState* fs; int parity;
+  const u64* split; u64* bkeys; u32* bpay;
 };
 struct FrameArgs {
   StructArgs S; LevelArgs V; EmitArgs E; SortArgs So;
@@ -1439,7 +1504,8 @@ __global__ void __launch_bounds__(FRAME_THREADS, 2) k_frame(const __grid_constan
       if (threadIdx.x == 0) spin_until_eq(A.E.p.ready, A.E.p.ready_seq);
       __syncthreads();
     }
-    emit_body(A.E.p, A.E.tp, A.E.vec_ok, A.E.keys, A.E.pay, A.E.keys_dense, A.E.fs, A.E.parity, b, s_raw);
+    emit_body(A.E.p, A.E.tp, A.E.vec_ok, A.E.keys, A.E.pay, A.E.keys_dense, A.E.fs, A.E.parity, b, s_raw, A.E.split,
+              A.E.bkeys, A.E.bpay);
     span_mark(A.trace, 2, true);
     return;
   }
@@ -1447,7 +1513,7 @@ __global__ void __launch_bounds__(FRAME_THREADS, 2) k_frame(const __grid_constan
   if (threadIdx.x >= BK_THREADS) return;  // whole warps leave: the barriers below count the remaining ones only
   span_mark(A.trace, 3, false);
   bucket_body(A.So.kin, A.So.pin, A.So.kout, A.So.pout, A.So.kscr, A.So.pscr, A.So.fs, A.So.split, A.So.passes,
-              A.So.parity, b, s_raw);
+              A.So.parity, b, s_raw, A.So.bkeys, A.So.bpay);
   span_mark(A.trace, 3, true);
 }
 
@@ -1526,6 +1592,10 @@ osl_status osl_integrate_init(osl_svo* t) {
   OSL_CUDA(cudaFuncSetAttribute((const void*)k_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, FRAME_SMEM));
   OSL_CUDA(cudaFuncSetAttribute((const void*)k_sort_bucket, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM));
   OSL_CUDA(cudaMalloc(&t->d_split, OSL_FRONT * BK_BUCKETS * sizeof(u64)));
+  for (int f = 0; f < OSL_FRONT; f++) {
+    OSL_CUDA(cudaMalloc(&t->d_bkeys[f], (size_t)OSL_BUCKETS * OSL_BUCKET_CAP * sizeof(u64)));
+    OSL_CUDA(cudaMalloc(&t->d_bpay[f], (size_t)OSL_BUCKETS * OSL_BUCKET_CAP * sizeof(u32)));
+  }
   if (!getenv("OSL_NO_WALK_CACHE")) {
     OSL_CUDA(cudaMalloc(&t->d_wcache, WC_SLOTS * sizeof(u64)));
     OSL_CUDA(cudaMemset(t->d_wcache, 0xFF, WC_SLOTS * sizeof(u64)));
@@ -1745,6 +1815,7 @@ static osl_status fused_launch(osl_svo* t, const osl_svo::FzStage* nw, const Emi
     A.So.kout = t->d_keysB[q.fslot]; A.So.pout = t->d_payB[q.fslot];
     A.So.kscr = t->d_keysC; A.So.pscr = t->d_payC; A.So.fs = fs;
     A.So.split = t->d_split + q.fslot * BK_BUCKETS; A.So.passes = (3 * t->tp.D + 7) / 8; A.So.parity = q.fslot;
+    A.So.bkeys = t->d_bkeys[q.fslot]; A.So.bpay = t->d_bpay[q.fslot];
     A.gSo = BK_BUCKETS;
   }
   if (nw) {
@@ -1755,6 +1826,7 @@ static osl_status fused_launch(osl_svo* t, const osl_svo::FzStage* nw, const Emi
     A.E.vec_ok = ((reinterpret_cast<uintptr_t>(ep->depth) & 7) == 0) && (ep->w % 4 == 0);
     A.E.keys = t->d_keysA[nw->fslot]; A.E.pay = t->d_payA[nw->fslot]; A.E.keys_dense = t->d_keysB[nw->fslot];
     A.E.fs = fs; A.E.parity = nw->fslot;
+    A.E.split = t->d_split + nw->fslot * BK_BUCKETS; A.E.bkeys = t->d_bkeys[nw->fslot]; A.E.bpay = t->d_bpay[nw->fslot];
     A.gE = A.E.p.tiles_x * A.E.p.tiles_y;
   }
   const int grid = A.gS + A.gV + A.gE + A.gSo;
@@ -2000,8 +2072,11 @@ osl_status osl_run_integrate(osl_svo* t, EmitParams& ep, const void* colors, cud
     } else {
       etiles = (n + EMIT_TILE - 1) / EMIT_TILE;
     }
+    const bool file_ranges = use_bucket && ep.mode != 2;
     k_emit<<<etiles, EMIT_THREADS, EMIT_SMEM, sE>>>(ep, t->tp, vec_ok, t->d_keysA[fslot], t->d_payA[fslot],
-                                                   t->d_keysB[fslot], fs, fslot);
+                                                   t->d_keysB[fslot], fs, fslot,
+                                                   file_ranges ? t->d_split + fslot * BK_BUCKETS : nullptr,
+                                                   t->d_bkeys[fslot], t->d_bpay[fslot]);
     OSL_LAUNCHED(1);
     if (piped && ep.mode == 0 && ep.M_dev) {
       // the producer of the pose (a tracker on the caller's stream) rewrites it for the next frame: order the
@@ -2019,7 +2094,8 @@ osl_status osl_run_integrate(osl_svo* t, EmitParams& ep, const void* colors, cud
     if (use_bucket) {
       k_sort_bucket<<<BK_BUCKETS, BK_THREADS, BK_SMEM, sSo>>>(t->d_keysA[fslot], t->d_payA[fslot], t->d_keysB[fslot],
                                                               t->d_payB[fslot], t->d_keysC, t->d_payC, fs,
-                                                              t->d_split + fslot * BK_BUCKETS, passes, fslot);
+                                                              t->d_split + fslot * BK_BUCKETS, passes, fslot,
+                                                              ep.mode != 2 ? t->d_bkeys[fslot] : nullptr, t->d_bpay[fslot]);
     } else {
       const int grid = grid_for(exp_emit, SORT_TILE, t->sort_grid < coop_cap ? t->sort_grid : coop_cap);
       u64* kA = t->d_keysA[fslot]; u32* pA = t->d_payA[fslot]; u64* kB = t->d_keysB[fslot]; u32* pB = t->d_payB[fslot];

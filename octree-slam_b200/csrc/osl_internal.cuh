@@ -20,6 +20,8 @@ typedef unsigned int u32;
 #define OSL_PIPE_DEPTH 3  // frames in flight the pool head-room is sized for
 #define OSL_FRONT 3   // key-list slots (k_emit / k_sort / k_structure of three consecutive frames overlap)
 #define OSL_BACK 2    // level-list + result-block slots (k_structure of frame f+1 overlaps k_levels of frame f)
+#define OSL_BUCKETS 64  // key ranges of the bucket sort (k_sort_bucket)
+#define OSL_BUCKET_CAP 2048  // entries a bucket holds in shared memory
 #define OSL_NCOUNT(D) ((D) + ((D) + 1) * ((D) + 1))
 #define OSL_CLVL(D, d) ((d)-1)
 #define OSL_CBKT(D, s, d) ((D) + (s) * ((D) + 1) + (d))
@@ -29,7 +31,8 @@ struct FrameState {
   int acc_valid[OSL_FRONT];  // [key-list slot] accumulated by k_emit (atomicAdd), consumed and zeroed by k_structure
   int acc_emit[OSL_FRONT];   // [key-list slot] entries k_emit appended to the key list
   int acc_unsorted[OSL_FRONT];  // [key-list slot] voxel path: the inputs are NOT (sorted and all valid)
-  int acc_tiles[OSL_FRONT];  // [key-list slot] k_frame: emit CTAs that have appended their entries (the sort role waits)
+  int acc_tiles[OSL_FRONT];  // (unused)
+  int acc_bucket[OSL_FRONT][OSL_BUCKETS];  // [key-list slot] entries k_emit filed under each splitter range
   int n_in;         // inputs
   int n_valid;      // V  (inputs with a valid key)
   int n_emit;       // entries sorted (modes 0/1: after the tile-local de-duplication; mode 2: == n_valid)
@@ -162,6 +165,7 @@ struct osl_svo {
   u64 *d_keysA[OSL_FRONT], *d_keysB[OSL_FRONT];  // sort ping/pong per front buffer
   u32 *d_payA[OSL_FRONT], *d_payB[OSL_FRONT];
   u64* d_keysC; u32* d_payC;   // k_sort_bucket slow-path scratch
+  u64* d_bkeys[OSL_FRONT]; u32* d_bpay[OSL_FRONT];  // [OSL_BUCKETS][OSL_BUCKET_CAP]: the key list as k_emit files it by splitter range
   u64* d_split;                // [OSL_FRONT][BK_BUCKETS] splitters written by k_structure of frame f (set f % OSL_FRONT)
   u64* d_wcache;               // k_structure's walk cache (prefix -> node at a fixed depth); cleared when the pool is replaced
   int force_grid_sort;         // testing: always use the cooperative grid sort

@@ -15,7 +15,7 @@ LIB = os.path.join(BUILD, "libosl_oracle.so")
 MAX_DEPTH = 20
 
 
-SOURCES = ["osl_oracle.c", "osl_oracle_track.c"]
+SOURCES = ["osl_oracle.c", "osl_oracle_track.c", "osl_oracle_thin.c"]
 
 
 def build(force=False):
@@ -252,6 +252,21 @@ def voxelize_mesh(vertices, triangles, center, half_edge, max_depth):
     lib().orc_voxelize_mesh(_ptr(V), V.shape[0], _ptr(T), T.shape[0], _f(center), float(half_edge),
                             int(max_depth), _ptr(keys), _ptr(tris), _ptr(cen), n)
     return keys, tris, cen
+
+
+def voxelize_thin(vertices, triangles, bbox0, bbox1, log_n=8):
+    """The reference's voxelisation rule (voxelpipe THIN_RASTER on the dense 2^log_n grid over the mesh bounding box,
+    voxelization.cu:24,281-285) -> (cells int32[n,3] (x, y, z) in ascending z,y,x order, tris int32[n] lowest triangle)"""
+    V = np.ascontiguousarray(vertices, dtype=np.float32)
+    T = np.ascontiguousarray(triangles, dtype=np.int32)
+    L = lib()
+    L.orc_voxelize_thin.restype = C.c_longlong
+    args = [_ptr(V), C.c_int(V.shape[0]), _ptr(T), C.c_int(T.shape[0]), _f(bbox0), _f(bbox1), C.c_int(int(log_n))]
+    n = L.orc_voxelize_thin(*args, None, None, C.c_longlong(0))
+    cells = np.empty((n, 3), dtype=np.int32)
+    tris = np.empty(n, dtype=np.int32)
+    L.orc_voxelize_thin(*args, _ptr(cells), _ptr(tris), C.c_longlong(n))
+    return cells, tris
 
 
 # ---------------------------------------------------------------------------------------------- camera tracking
