@@ -899,6 +899,7 @@ __device__ __forceinline__ void assign_block(int vb, int n, const u64* __restric
   // headed before this warp
   u32 par_idx = (d0 > 1) ? s_w[warp][OSL_CLVL(D, d0 - 1)] - 1u : 0u;
   u32 path_tile = 0; // tile holding the level-(d) nodes below this key's level-(d-1) node (root: tile 0)
+  size_t o_prev = 0;  // where this lane's level-(d-1) entry went (valid when it heads that level)
   for (int d = d0; d <= D; d++) {
     const bool f = unique && m < d;
     const u32 bal = __ballot_sync(FULL, f);
@@ -938,6 +939,9 @@ __device__ __forceinline__ void assign_block(int vb, int n, const u64* __restric
     const u32 lbase = s_w[warp][OSL_CLVL(D, d)];
     if (f) {
       const size_t o = lv.off[d] + lbase + __popc(bal & lt);
+      // the key that heads a node also heads that node's first (lowest-key) touched child: its own entry one level down
+      if (d >= 2 && m < d - 1) lv.fc[o_prev] = lbase + __popc(bal & lt);
+      o_prev = o;
       lv.ctile[o] = ct;
       lv.digit[o] = (uint8_t)key_digit(k, D, d);
       lv.par[o] = par_idx;
@@ -1200,7 +1204,7 @@ __global__ void __launch_bounds__(AN_THREADS, 3) k_structure(StructArgs A) {
 #ifndef LEVEL_STAGE
 #define LEVEL_STAGE 1024
 #endif
-#define LEVEL_SMEM (LEVEL_STAGE * (32 + 4 + 4 + 2 + 2) + 64 + 256)
+#define LEVEL_SMEM (LEVEL_STAGE * (32 + 4 + 4 + 2 + 2) + 64 + 512)
 
 __device__ __forceinline__ void level_leaf(u32* pool, const LevelArrays& lv, int D, int idx, int mode,
                                            const uint8_t* __restrict__ rgb, const float* __restrict__ colors4,
@@ -1234,6 +1238,8 @@ __device__ __forceinline__ void level_leaf(u32* pool, const LevelArrays& lv, int
   }
   w[1] = nv;
 }
+
+__device__ __forceinline__ size_t rgb_bytes_of(int n_in) { return 3 * (size_t)n_in; }
 
 __device__ __forceinline__ void level_inner(u32* pool, const LevelArrays& lv, int d, int idx) {
   const size_t od = lv.off[d];
@@ -1298,16 +1304,45 @@ __device__ __forceinline__ void levels_body(const LevelArgs& A, int bid, int G, 
   __syncthreads();
   PROF(32);
 
-  // phase 1: leaves
+  // Subtrees.  The deepest level that fits the narrow path (or is small enough to be shared out) is the CUT: every CTA
+  // takes a contiguous chunk of the cut level's nodes and folds their touched subtrees -- contiguous ranges of every
+  // deeper level list (lv.fc) -- bottom-up BY ITSELF, block barriers only.  (First version: one grid barrier per wide
+  // level, ~2 us each and three of them for a 640x480 frame.)  Levels above the cut that are still too wide for the
+  // narrow path (huge inputs only) take the grid-barrier route as before.
+  int cut = D - 1;
   {
+    const int roots_max = max(LEVEL_NARROW, 16 * G);
+    while (cut >= 1 && s_nl[cut] > roots_max) cut--;
+  }
+  if (D >= 2 && cut >= 1) {
+    int* s_lo = s_pre + (OSL_MAXD + 4);  // [D+2] first / one-past-last entry of this CTA at every level below the cut
+    int* s_hi = s_lo + (OSL_MAXD + 2);
+    const int n_c = s_nl[cut];
+    const int r0 = (int)(((long long)bid * n_c) / G), r1 = (int)(((long long)(bid + 1) * n_c) / G);
+    if (tid < 2) {  // two dependent chains of first-child look-ups, side by side
+      int a = tid == 0 ? r0 : r1;
+      int* dst = tid == 0 ? s_lo : s_hi;
+      dst[cut] = a;
+      for (int l = cut; l < D; l++) {
+        a = (a < s_nl[l]) ? (int)__ldcg(&lv.fc[lv.off[l] + a]) : s_nl[l + 1];
+        dst[l + 1] = a;
+      }
+    }
+    __syncthreads();
+    for (int idx = s_lo[D] + tid; idx < s_hi[D]; idx += LEVEL_THREADS) level_leaf(pool, lv, D, idx, mode, rgb, colors4, rgb_bytes_of(s_nin));
+    for (int l = D - 1; l >= cut; l--) {
+      __syncthreads();  // (this CTA wrote the children; level_inner reads them from L2)
+      for (int idx = s_lo[l] + tid; idx < s_hi[l]; idx += LEVEL_THREADS) level_inner(pool, lv, l, idx);
+    }
+  } else {
     const int n_D = s_nl[D];
-    const size_t rgb_bytes = 3 * (size_t)s_nin;
-    for (int idx = gtid; idx < n_D; idx += gsz) level_leaf(pool, lv, D, idx, mode, rgb, colors4, rgb_bytes);
+    for (int idx = gtid; idx < n_D; idx += gsz) level_leaf(pool, lv, D, idx, mode, rgb, colors4, rgb_bytes_of(s_nin));
+    cut = D;
   }
   PROF(35);
 
-  // phase 2: wide levels with the whole grid
-  int d = D - 1;
+  // levels above the cut that are too wide for one CTA: the whole grid, a barrier per level
+  int d = cut - 1;
   for (int phase = 1; d >= 1; d--, phase++) {
     const int n_d = s_nl[d];
     if (n_d <= LEVEL_NARROW) break;
@@ -1573,12 +1608,13 @@ osl_status osl_ensure_workspace(osl_svo* t, size_t n) {
     }
     // ctile(4) + par(4) + self(4) + digit(1) bytes per level entry, src(4) per leaf
     uint8_t* mem;
-    OSL_CUDA(cudaMalloc(&mem, total * 13 + cap * 4 + 64));
+    OSL_CUDA(cudaMalloc(&mem, total * 17 + cap * 4 + 64));
     t->d_level_mem[b] = mem;
     lv.ctile = reinterpret_cast<u32*>(mem);
     lv.par = lv.ctile + total;
     lv.self = lv.par + total;
-    lv.src = lv.self + total;
+    lv.fc = lv.self + total;
+    lv.src = lv.fc + total;
     lv.digit = reinterpret_cast<uint8_t*>(lv.src + cap);
   }
   t->ws_cap = cap;

@@ -54,6 +54,8 @@ struct LevelArrays {   // dense per-level lists of the nodes a frame touches, le
   u32* ctile;          // child tile index | OSL_NEWBIT ; 0xFFFFFFFF = none (unsplit leaf)
   u32* par;            // index (in level d-1) of the parent node
   u32* self;           // the node's own index in the pool
+  u32* fc;             // index (in level d+1) of the node's FIRST touched child: a node's touched children, and with them
+                       // its whole touched subtree, are contiguous ranges of the deeper level lists
   u32* src;            // leaves only: winning input (pixel index / sorted position), indexed by the level-D index
   uint8_t* digit;      // octant of the node inside its parent's tile
   size_t off[OSL_MAXD + 2];
