@@ -221,6 +221,18 @@ osl_status osl_voxelize_mesh(const float* d_vertices, int n_vertices, const int*
                              const float* d_tri_colors4, const float center[3], float half_edge, int max_depth,
                              float** d_centers4_out, float** d_colors4_out, int64_t** d_keys_out, int** d_tris_out,
                              int64_t* n_out, void* stream);
+/* The REFERENCE's voxelisation rule on the reference's grid: voxelization::meshToVoxelGrid (voxelization.cu:24,281-285)
+ * = voxelpipe THIN_RASTER / NO_BLENDING on the dense 2^log_n-per-axis grid over [bbox0, bbox1] (the mesh bounding box:
+ * anisotropic cells), restated from the vendored library's source (octree-slam_b200/csrc/osl_voxelize_thin.cu lists
+ * file:line) -- per column of the dominant-axis projection that the triangle's 2-D footprint touches, the one voxel
+ * that holds the plane's depth at the column centre; lowest triangle index where triangles collide.  Centres follow
+ * getCenterFromIndex (voxelization.cu:58-78).  cube_depth > 0: the voxels come out in the order of the Morton keys of
+ * their centres in that octree cube (what svoFromVoxelGrid sorts by), so quirk Q11 leaves the colours in place;
+ * cube_depth = 0: grid order (z, y, x).  d_cells_out: 3 ints (x, y, z) per voxel.  log_n in [3, 9]. */
+osl_status osl_voxelize_thin(const float* d_vertices, int n_vertices, const int* d_triangles, int n_triangles,
+                             const float* d_tri_colors4, const float bbox0[3], const float bbox1[3], int log_n,
+                             const float cube_center[3], float cube_half, int cube_depth, float** d_centers4_out,
+                             float** d_colors4_out, int** d_cells_out, int** d_tris_out, int64_t* n_out, void* stream);
 void osl_free_device(void* p);
 /* device-to-device copy (for bindings that must move a library-allocated result into a buffer they own) */
 osl_status osl_copy_device(void* d_dst, const void* d_src, size_t bytes);

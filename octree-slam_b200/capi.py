@@ -21,7 +21,7 @@ EXPORTS = [
     "osl_svo_create", "osl_svo_destroy", "osl_svo_reset", "osl_svo_expand", "osl_svo_max_depth", "osl_svo_set_quirks", "osl_svo_set_pipeline", "osl_svo_set_stage_timing", "osl_get_stage_times",
     "osl_integrate_depth", "osl_integrate_depth_posed", "osl_integrate_depth_host", "osl_integrate_points", "osl_integrate_voxels",
     "osl_svo_sync", "osl_svo_join", "osl_svo_view", "osl_svo_size", "osl_svo_download", "osl_svo_upload", "osl_get_counters", "osl_svo_save", "osl_svo_load",
-    "osl_raycast", "osl_raycast_host", "osl_raycast_pool", "osl_raycast_rows", "osl_raycast_bands", "osl_extract_voxels", "osl_voxelize_mesh", "osl_free_device", "osl_copy_device", "osl_debug_trace",
+    "osl_raycast", "osl_raycast_host", "osl_raycast_pool", "osl_raycast_rows", "osl_raycast_bands", "osl_extract_voxels", "osl_voxelize_mesh", "osl_voxelize_thin", "osl_free_device", "osl_copy_device", "osl_debug_trace",
     "osl_svo_reserve", "osl_svo_pool_device", "osl_svo_adopt", "osl_svo_delta_bytes", "osl_svo_delta_pack", "osl_svo_delta_apply",
     "osl_generate_vertex_map", "osl_transform_vertex_map", "osl_point_cloud_bbox", "osl_compute_keys",
     "osl_bilateral_filter", "osl_subsample_depth", "osl_subsample_f32", "osl_generate_normal_map", "osl_transform_normal_map",
@@ -106,6 +106,8 @@ def lib():
         "osl_extract_voxels": (i32, [vp, i32, vp, vp, vp, i64, C.POINTER(i64), vp]),
         "osl_voxelize_mesh": (i32, [vp, i32, vp, i32, vp, fp, f32, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp),
                                     C.POINTER(vp), C.POINTER(i64), vp]),
+        "osl_voxelize_thin": (i32, [vp, i32, vp, i32, vp, fp, fp, i32, fp, f32, i32, C.POINTER(vp), C.POINTER(vp),
+                                    C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), vp]),
         "osl_free_device": (None, [vp]),
         "osl_copy_device": (i32, [vp, vp, C.c_size_t]),
         "osl_debug_trace": (i32, [vp, i32, vp]),
