@@ -10,11 +10,12 @@ namespace voxelization {
 
 inline int log_N() { return 8; }  // voxelization.cu:24 GRID_RES
 
-// Reference signature.  The grid is the depth-log_N() leaf grid of the cube (centre = bbox mid-point, half edge =
-// bbox.bbox1.x) Scene::voxelizeMeshes builds its Octree on (scene.cpp:78), so every voxel centre is a leaf centre.
+// Reference signature = the reference's rule: voxelpipe THIN_RASTER on the dense 2^log_N() grid over the mesh bounding
+// box (voxelization.cu:281-285; restated in octree-slam_b200/csrc/osl_voxelize_thin.cu), voxels ordered by their Morton
+// keys in the cube Scene::voxelizeMeshes builds its Octree on (scene.cpp:78).
 // (`extern "C"` as in the reference, voxelization.h:21)
 extern "C" void meshToVoxelGrid(const Mesh& m_in, const bmp_texture* tex, VoxelGrid& grid_out);
-// same on an explicit cube / depth (new; C++ linkage -- an extern "C" name cannot be overloaded)
+// the sparse CONSERVATIVE voxeliser on an explicit cube / depth: every leaf cell the triangle overlaps (new; C++ linkage -- an extern "C" name cannot be overloaded)
 void meshToVoxelGridAt(const Mesh& m_in, const bmp_texture* tex, const glm::vec3& center, float half_edge, int depth,
                        VoxelGrid& grid_out);
 

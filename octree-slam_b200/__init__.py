@@ -6,7 +6,7 @@ The directory name contains a hyphen (the layout the task prescribes); import it
 from . import capi  # noqa: F401
 from .capi import Counters, OslError, RaycastParams, RaycastStats, lib  # noqa: F401
 from .world import (SVO, BoundingBox, Octree, Scene, computeKeys, computePointCloudBoundingBox,  # noqa: F401
-                    coneTraceSVO, generateVertexMap, meshToVoxelGrid, transformVertexMap)
+                    coneTraceSVO, generateVertexMap, meshToVoxelGrid, meshToVoxelGridThin, transformVertexMap)
 from . import sensor  # noqa: F401
 from .sensor import RGBDCamera  # noqa: F401
 from . import synth  # noqa: F401

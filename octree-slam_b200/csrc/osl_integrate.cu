@@ -723,11 +723,12 @@ __device__ __forceinline__ int key_digit(u64 key, int D, int d) { return (int)((
 // when the pool is replaced: reset / upload / expand).  A hit replaces WC_H dependent loads from the root by one.
 #define WC_SLOTS 4096
 #define PATH_KEEP 8
+#define SHALLOW_SLOTS 32  // keys per CTA whose shallow path (levels above the last PATH_KEEP) is kept as well
 __device__ __forceinline__ int walk_cache_depth(int D) { const int h = D - 5 < 11 ? D - 5 : 11; return h >= 3 ? h : 0; }
 __device__ __forceinline__ u32 walk_cache_slot(u64 prefix) { return (u32)((prefix * 0x9E3779B97F4A7C15ull) >> 52); }
 
 __device__ __forceinline__ int walk_frontier(const u32* __restrict__ pool, u64 key, int D, int quirks, int m,
-                                             u32& start, u64* wcache, u32* s_path) {
+                                             u32& start, u64* wcache, u32* s_path, u32* s_shallow, int slot) {
   u32 node = (u32)key_digit(key, D, 1);
   int t = 1;
   const int h = wcache ? walk_cache_depth(D) : 0;
@@ -746,6 +747,7 @@ __device__ __forceinline__ int walk_frontier(const u32* __restrict__ pool, u64 k
     if (!(w0 & OSL_FLAG)) return t;
     // the child tiles along the last PATH_KEEP levels stay in shared memory: phase C walks the same nodes again
     if (D - 1 - t < PATH_KEEP) s_path[(D - 1 - t) * AN_THREADS + threadIdx.x] = w0 & OSL_MASK;
+    else if (slot >= 0) s_shallow[t * SHALLOW_SLOTS + slot] = w0 & OSL_MASK;  // (the few keys that head shallow levels)
     node = (w0 & OSL_MASK) + (u32)key_digit(key, D, t + 1);
   }
   if (m + 1 == D) start = node;  // the leaf itself (its whole path exists)
@@ -771,11 +773,12 @@ __device__ __forceinline__ int walk_frontier(const u32* __restrict__ pool, u64 k
 __device__ __forceinline__ void analyze_block(int vb, int n, const u64* __restrict__ keys, u32* pay, int mode,
                                               const u32* pool, const TreeParams& tp, uint8_t* __restrict__ m8,
                                               uint8_t* __restrict__ s8, u32* __restrict__ start,
-                                              u32* s_ctot, u32* s_cnt, u64* wcache, u32* s_path, u64& k_out,
-                                              int& m_out, int& s_out, u32& st_out) {
+                                              u32* s_ctot, u32* s_cnt, u64* wcache, u32* s_path, u32* s_shallow,
+                                              u64& k_out, int& m_out, int& s_out, u32& st_out, int& slot_out) {
   const int D = tp.D, NC = OSL_NCOUNT(D);
-  k_out = 0; m_out = D; s_out = OSL_NONE; st_out = 0;
+  k_out = 0; m_out = D; s_out = OSL_NONE; st_out = 0; slot_out = -1;
   for (int c = threadIdx.x; c < NC; c += AN_THREADS) s_cnt[c] = 0;
+  if (threadIdx.x == 0) s_shallow[OSL_MAXD * SHALLOW_SLOTS] = 0u;  // slots handed out
   __syncthreads();
   const int j = vb * AN_THREADS + threadIdx.x;
   if (vb == 0 && threadIdx.x == 0) g_osl_prof[24] = (unsigned long long)clock64();
@@ -795,7 +798,15 @@ __device__ __forceinline__ void analyze_block(int vb, int n, const u64* __restri
       }
       u32 st = 0;
       if (vb == 0 && threadIdx.x == 0) g_osl_prof[25] = (unsigned long long)clock64();
-      s = walk_frontier(pool, k, D, tp.quirks, m, st, wcache, s_path);
+      // a key that heads levels above the last PATH_KEEP (the first key of a frame, of a far-away sub-tree) takes one
+      // of the CTA's few shallow-path slots: phase C then finds every child tile of its path in shared memory
+      int slot = -1;
+      if (m + 1 < D - PATH_KEEP) {
+        slot = (int)atomicAdd(&s_shallow[OSL_MAXD * SHALLOW_SLOTS], 1u);
+        if (slot >= SHALLOW_SLOTS) slot = -1;
+      }
+      slot_out = slot;
+      s = walk_frontier(pool, k, D, tp.quirks, m, st, wcache, s_path, s_shallow, slot);
       if (vb == 0 && threadIdx.x == 0) g_osl_prof[26] = (unsigned long long)clock64();
       start[j] = st;
       st_out = st;
@@ -834,7 +845,7 @@ __device__ __forceinline__ void assign_block(int vb, int n, const u64* __restric
                                              u32* s_base, const LevelArrays& lv, int mode, u32 size0,
                                              int n_invalid_front, const u32* s_plan, u32 (*s_w)[NC_MAX],
                                              bool carried, u64 k_in, int m_in, int s_in, u32 st_in,
-                                             const u32* s_path) {
+                                             const u32* s_path, const u32* s_shallow, int slot) {
   const int D = tp.D, NC = OSL_NCOUNT(D);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const u32 lt = lanemask_lt();
@@ -918,7 +929,9 @@ __device__ __forceinline__ void assign_block(int vb, int n, const u64* __restric
     if (f) {
       if (d < D && d < s_eff) {
         // (a CTA that owns one block finds the child tile phase A read on the same path in shared memory)
-        ct = (carried && D - 1 - d < PATH_KEEP) ? s_path[(D - 1 - d) * AN_THREADS + tid] : (pool[2 * (size_t)node] & OSL_MASK);
+        ct = (carried && D - 1 - d < PATH_KEEP) ? s_path[(D - 1 - d) * AN_THREADS + tid]
+             : (carried && slot >= 0)         ? s_shallow[d * SHALLOW_SLOTS + slot]
+                                               : (pool[2 * (size_t)node] & OSL_MASK);
         node = ct + (u32)key_digit(k, D, d + 1);
       } else if (sp) {
         const u32 rank = s_w[warp][OSL_CBKT(D, s, d)] + __popc(peers & lt);
@@ -963,7 +976,7 @@ struct StructArgs {
   u64* wcache;  // walk cache (NULL = off)
 };
 #define STRUCT_MAXG 1024  // most CTAs a structure grid / role may have (s_has)
-#define STRUCT_SMEM ((AN_WARPS + 4) * NC_MAX * 4 + AN_WARPS * 4 + 2 * STRUCT_MAXG + 8 * 512 * 4)
+#define STRUCT_SMEM ((AN_WARPS + 4) * NC_MAX * 4 + AN_WARPS * 4 + 2 * STRUCT_MAXG + 8 * 512 * 4 + (OSL_MAXD * 32 + 4) * 4)
 
 __device__ __forceinline__ void structure_body(const StructArgs& A, int bid, int G, unsigned char* s_raw) {
   const u64* __restrict__ keys_sorted = A.keys_sorted; const u64* __restrict__ keys_dense = A.keys_dense;
@@ -980,6 +993,7 @@ __device__ __forceinline__ void structure_body(const StructArgs& A, int bid, int
   u32* s_ctot = s_base + NC_MAX;
   u32* s_scan = s_ctot + NC_MAX;
   u32* s_path = reinterpret_cast<u32*>(s_raw + (AN_WARPS + 4) * NC_MAX * 4 + AN_WARPS * 4 + 2 * STRUCT_MAXG);  // [PATH_KEEP][512]
+  u32* s_shallow = s_path + PATH_KEEP * AN_THREADS;  // [OSL_MAXD][SHALLOW_SLOTS] + 1 counter
   const int D = tp.D, NC = OSL_NCOUNT(D);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = __ldcg(&fs->acc_emit[parity]);
@@ -1004,9 +1018,10 @@ __device__ __forceinline__ void structure_body(const StructArgs& A, int bid, int
   // (Sharing walks between the blocks of a CTA -- thread 0 walks the block's first key, the others resume where they
   // leave its path -- was measured at 50 M keys: 3.5 ms against 3.2 ms for these independent walks; with 4 CTAs per
   // SM the walk latency is already hidden and the extra serial step only adds two block barriers per block.)
-  u64 ck = 0; int cm = D, cs = OSL_NONE; u32 cst = 0;  // this thread's key state when the CTA owns a single block
+  u64 ck = 0; int cm = D, cs = OSL_NONE, cslot = -1; u32 cst = 0;  // this thread's key state when the CTA owns a single block
   for (int vb = vb0; vb < vb1; vb++)
-    analyze_block(vb, n, keys, pay, mode, pool, tp, m8, s8, start, s_ctot, &s_w[0][0], A.wcache, s_path, ck, cm, cs, cst);
+    analyze_block(vb, n, keys, pay, mode, pool, tp, m8, s8, start, s_ctot, &s_w[0][0], A.wcache, s_path, s_shallow, ck, cm,
+                  cs, cst, cslot);
   const bool carried = (vb1 - vb0 == 1);
   // publish this CTA's counter vector behind an epoch flag (every CTA publishes, also one without blocks).  Compact
   // form: the D per-level counters always; the (D+1)^2 bucket counters only when a key of this CTA splits a node --
@@ -1134,7 +1149,7 @@ __device__ __forceinline__ void structure_body(const StructArgs& A, int bid, int
   if (!overflow) {
     for (int vb = vb0; vb < vb1; vb++)
       assign_block(vb, n, keys, pay, pool, tp, m8, s8, start, s_base, lv, mode, size0, n_invalid_front, s_plan, s_w,
-                   carried, ck, cm, cs, cst, s_path);
+                   carried, ck, cm, cs, cst, s_path, s_shallow, cslot);
   }
   PROF(22);
 

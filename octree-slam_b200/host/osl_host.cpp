@@ -181,13 +181,12 @@ namespace voxelization {
 
 static inline float clamp01(float v) { return v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v); }
 
-void meshToVoxelGridAt(const Mesh& m_in, const bmp_texture* tex, const glm::vec3& center, float half_edge, int depth,
-                       VoxelGrid& grid_out) {
-  const int n_tri = m_in.ibosize / 3, n_vert = m_in.vbosize / 3;
-  // per-triangle flat colour, the reference's ColorShader: no texture -> green; no texture coordinates -> texel 0;
-  // else the texel at the FIRST corner ("TODO: interpolate", voxelization.cu:125-126); quantised to 8 bits and
-  // returned as byte / 255.0 (createVoxelGrid)
-  std::vector<float> tri_col((size_t)n_tri * 4, 0.0f);
+// per-triangle flat colour, the reference's ColorShader (voxelization.cu:90-139): no texture -> green; no texture
+// coordinates -> texel 0; else the texel at the FIRST corner ("TODO: interpolate", voxelization.cu:125-126); quantised
+// to 8 bits and returned as byte / 255.0 (createVoxelGrid, voxelization.cu:219-236)
+static void triangleColors(const Mesh& m_in, const bmp_texture* tex, std::vector<float>& tri_col) {
+  const int n_tri = m_in.ibosize / 3;
+  tri_col.assign((size_t)n_tri * 4, 0.0f);
   for (int t = 0; t < n_tri; t++) {
     int r = 0, g = 255, b = 0;
     if (tex && tex->width > 0 && tex->data) {
@@ -205,6 +204,13 @@ void meshToVoxelGridAt(const Mesh& m_in, const bmp_texture* tex, const glm::vec3
     tri_col[4 * t] = (float)((r & 0xFF) / 255.0); tri_col[4 * t + 1] = (float)((g & 0xFF) / 255.0);
     tri_col[4 * t + 2] = (float)((b & 0xFF) / 255.0);
   }
+}
+
+void meshToVoxelGridAt(const Mesh& m_in, const bmp_texture* tex, const glm::vec3& center, float half_edge, int depth,
+                       VoxelGrid& grid_out) {
+  const int n_tri = m_in.ibosize / 3, n_vert = m_in.vbosize / 3;
+  std::vector<float> tri_col;
+  triangleColors(m_in, tex, tri_col);
   float *d_v = nullptr, *d_c = nullptr;
   int* d_i = nullptr;
   cudaMalloc((void**)&d_v, sizeof(float) * 3 * (size_t)(n_vert > 0 ? n_vert : 1));
@@ -227,8 +233,37 @@ void meshToVoxelGridAt(const Mesh& m_in, const bmp_texture* tex, const glm::vec3
   grid_out.bbox = m_in.bbox;
 }
 
+// The reference signature = the reference's rule (voxelization.cu:381-405): voxelpipe THIN_RASTER on the dense
+// 2^log_N grid over the MESH bounding box; scale and bbox as the reference sets them (voxelization.cu:401-405).  The
+// voxels come out ordered by their Morton keys in the cube Scene::voxelizeMeshes builds its Octree on (scene.cpp:78),
+// so that svoFromVoxelGrid's colour quirk Q11 is harmless.
 void meshToVoxelGrid(const Mesh& m_in, const bmp_texture* tex, VoxelGrid& grid_out) {
-  meshToVoxelGridAt(m_in, tex, (m_in.bbox.bbox1 + m_in.bbox.bbox0) / 2.0f, m_in.bbox.bbox1.x, log_N(), grid_out);
+  const int n_tri = m_in.ibosize / 3, n_vert = m_in.vbosize / 3;
+  std::vector<float> tri_col;
+  triangleColors(m_in, tex, tri_col);
+  float *d_v = nullptr, *d_c = nullptr;
+  int* d_i = nullptr;
+  cudaMalloc((void**)&d_v, sizeof(float) * 3 * (size_t)(n_vert > 0 ? n_vert : 1));
+  cudaMalloc((void**)&d_i, sizeof(int) * 3 * (size_t)(n_tri > 0 ? n_tri : 1));
+  cudaMalloc((void**)&d_c, sizeof(float) * 4 * (size_t)(n_tri > 0 ? n_tri : 1));
+  cudaMemcpy(d_v, m_in.vbo, sizeof(float) * 3 * (size_t)n_vert, cudaMemcpyHostToDevice);
+  cudaMemcpy(d_i, m_in.ibo, sizeof(int) * 3 * (size_t)n_tri, cudaMemcpyHostToDevice);
+  cudaMemcpy(d_c, tri_col.data(), sizeof(float) * 4 * (size_t)n_tri, cudaMemcpyHostToDevice);
+  if (grid_out.size > 0) { cudaFree(grid_out.centers); cudaFree(grid_out.colors); grid_out.size = 0; }
+  float *centers = nullptr, *colors = nullptr;
+  int64_t n = 0;
+  const float b0[3] = {m_in.bbox.bbox0.x, m_in.bbox.bbox0.y, m_in.bbox.bbox0.z};
+  const float b1[3] = {m_in.bbox.bbox1.x, m_in.bbox.bbox1.y, m_in.bbox.bbox1.z};
+  const glm::vec3 mid = (m_in.bbox.bbox1 + m_in.bbox.bbox0) / 2.0f;
+  const float c3[3] = {mid.x, mid.y, mid.z};
+  report(osl_voxelize_thin(d_v, n_vert, d_i, n_tri, d_c, b0, b1, log_N(), c3, m_in.bbox.bbox1.x, log_N(), &centers,
+                           &colors, nullptr, nullptr, &n, nullptr), "osl_voxelize_thin");
+  cudaFree(d_v); cudaFree(d_i); cudaFree(d_c);
+  grid_out.centers = reinterpret_cast<glm::vec4*>(centers);
+  grid_out.colors = reinterpret_cast<glm::vec4*>(colors);
+  grid_out.size = (int)n;
+  grid_out.scale = (m_in.bbox.bbox1.x - m_in.bbox.bbox0.x) / (float)(1 << log_N()) / 2.0f;  // computeScale, voxelization.cu:80-82
+  grid_out.bbox = m_in.bbox;
 }
 
 }  // namespace voxelization

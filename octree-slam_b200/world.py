@@ -320,6 +320,35 @@ def meshToVoxelGrid(vertices, triangles, tri_colors4, center, half_edge, max_dep
     return (centers, colors, keys, tris) if want_keys else (centers, colors)
 
 
+def meshToVoxelGridThin(vertices, triangles, tri_colors4, bbox0, bbox1, log_n=8, cube=None, device=0):
+    """voxelization::meshToVoxelGrid with the REFERENCE's rule (voxelpipe THIN_RASTER on the dense 2^log_n grid over the
+    mesh bounding box, voxelization.cu:24,281-285; osl_voxelize_thin).  cube = (center, half_edge, depth) of the octree
+    the grid is meant for orders the voxels by their Morton keys there.  -> (centers4, colors4, cells int32[n,3],
+    tris int32[n]) CUDA tensors."""
+    torch = _torch()
+    V = _dev(np.asarray(vertices, dtype=np.float32), np.float32, device)
+    T = _dev(np.asarray(triangles, dtype=np.int32), np.int32, device)
+    Cc = _dev(np.asarray(tri_colors4, dtype=np.float32), np.float32, device) if tri_colors4 is not None else None
+    pc, pk, pcell, ptri, n = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_int64()
+    center, half, depth = cube if cube is not None else ((0.0, 0.0, 0.0), 1.0, 0)
+    _check(lib().osl_voxelize_thin(V.data_ptr(), V.shape[0], T.data_ptr(), T.shape[0],
+                                   Cc.data_ptr() if Cc is not None else None, _f(bbox0), _f(bbox1), int(log_n),
+                                   _f(center), float(half), int(depth), C.byref(pc), C.byref(pk), C.byref(pcell),
+                                   C.byref(ptri), C.byref(n), None), "osl_voxelize_thin")
+    cnt = n.value
+    dev = "cuda:%d" % device
+    outs = [(pc, torch.empty((cnt, 4), dtype=torch.float32, device=dev)),
+            (pk, torch.empty((cnt, 4), dtype=torch.float32, device=dev)),
+            (pcell, torch.empty((cnt, 3), dtype=torch.int32, device=dev)),
+            (ptri, torch.empty((cnt,), dtype=torch.int32, device=dev))]
+    for ptr, dst in outs:
+        if cnt and ptr.value:
+            _check(lib().osl_copy_device(dst.data_ptr(), ptr, dst.numel() * dst.element_size()), "osl_copy_device")
+        if ptr.value:
+            lib().osl_free_device(ptr)
+    return tuple(t for _, t in outs)
+
+
 # ---- reference-shaped classes ------------------------------------------------------------------------------
 
 class BoundingBox:
