@@ -376,8 +376,11 @@ def run_ours(args):
                      # capture (profiles/r01_ncu_full_summary_v07.csv; cold caches: ncu flushes L2 between kernels)
                      "traffic": 2269184, "traffic_source": "profiles/r01_ncu_full_summary_v07.csv",
                      "peak_source": peak_src,
-                     "kernel": "integrate pipeline per frame (k_emit+k_sort+k_structure+k_levels), "
-                               "B_int = 5N+8U+68S+68*sum(P_l) per frame",
+                     "kernel": "k_frame: ONE launch per frame whose four roles (emit / sort / structure / values) each "
+                               "work on the frame that has reached them; achieved = B_int of one frame / average "
+                               "launch period over the timed region (CUDA events around the PDL-chained launches), "
+                               "B_int = 5N+8U+68S+68*sum(P_l)",
+                     "launches_in_timed_region": int(launches),
                      "bytes_per_frame": bytes_alg / float(K),
                      "counters_last_frame": {"N": int(last.n_points), "V": int(last.n_valid), "U": int(last.n_unique),
                                              "S": int(last.n_split),
@@ -388,6 +391,23 @@ def run_ours(args):
                              "DESIGN.md section 3"},
         "clocks": clocks,
     }
+    # BASELINE configs 2 and 5 on their named inputs (tools/cfg_mesh_bench.py; the meshes are staged into
+    # baseline/_assets by __graft_entry__.build()): voxelise -> svoFromVoxelGrid -> raycast, every rank its own replica
+    # of the map, the image in interleaved row bands over the ranks
+    if not args.no_mesh_configs:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import cfg_mesh_bench
+        for name in ("cfg2", "cfg5"):
+            try:
+                res, rms = cfg_mesh_bench.run(name, None, 3, rank, world, local)
+                rms = max_over_ranks(rms, world)
+                Wm_, Hm_ = res["raycast"]["res"]
+                res["raycast"]["ms_max_over_ranks"] = rms
+                res["raycast"]["mrays_per_s"] = Wm_ * Hm_ / (rms / 1e3) / 1e6
+                line[name] = res
+            except Exception as exc:  # (a missing asset or an out-of-memory box must not cost the headline line)
+                line[name] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+                max_over_ranks(0.0, world)
     if rank == 0:
         line["cpu_baseline"] = cpu_baseline_port(pkg, depths, rgbs, poses, fx, fy, center, half)
         print(json.dumps(line))
@@ -507,6 +527,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-mesh-configs", action="store_true", help="skip the cfg2 / cfg5 mesh objects of the line")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -27,7 +27,7 @@ namespace cg = cooperative_groups;
 #define FULL 0xFFFFFFFFu
 
 // phase checkpoints (SM clock of CTA 0 / thread 0) for tools/phase_profile.py; one predicated store each
-__device__ unsigned long long g_osl_prof[64];
+__device__ unsigned long long g_osl_prof[128];
 // (`bid` = the CTA's index inside its role: the bodies below run as kernels of their own and as roles of k_frame)
 #define PROF(i) do { if (bid == 0 && threadIdx.x == 0) g_osl_prof[i] = (unsigned long long)clock64(); } while (0)
 
@@ -963,6 +963,10 @@ __device__ __forceinline__ void assign_block(int vb, int n, const u64* __restric
     }
     // the level-d node on this key's path: its own if it heads it, else the last one headed before it
     par_idx = lbase + __popc(bal & le) - 1u;
+  }
+  if (vb == 0 && lane == 0) {  // (profiling: when each warp of CTA 0's first block left the loop, and its first level)
+    g_osl_prof[64 + warp] = (unsigned long long)clock64();
+    g_osl_prof[80 + warp] = (unsigned long long)d0 | ((unsigned long long)any_split << 8);
   }
   __syncthreads();
 }
@@ -2320,7 +2324,7 @@ extern "C" osl_status osl_debug_trace(osl_svo* t, int enable, unsigned long long
 }
 
 extern "C" osl_status osl_debug_profile(unsigned long long* out, int n) {
-  if (!out || n < 0 || n > 64) return OSL_ERR_INVALID;
+  if (!out || n < 0 || n > 128) return OSL_ERR_INVALID;
   OSL_CUDA(cudaDeviceSynchronize());
   OSL_CUDA(cudaMemcpyFromSymbol(out, g_osl_prof, sizeof(unsigned long long) * (size_t)n));
   return OSL_OK;

@@ -38,14 +38,22 @@ static inline float ccw(int axis, f3 n) {
   if (axis == 1) return n.y < 0.0f ? 1.0f : -1.0f;
   return n.z > 0.0f ? 1.0f : -1.0f;
 }
+/* float -> int as the GPU converts (F2I.TRUNC saturates: NaN -> 0, out of range -> INT_MIN / INT_MAX); a host cast is
+ * undefined there, and degenerate triangles (zero-area: n = 0, 1/n = inf) do produce such values */
+static inline int f2i(float f) {
+  if (f != f) return 0;
+  if (f >= 2147483648.0f) return 2147483647;
+  if (f <= -2147483648.0f) return (-2147483647 - 1);
+  return (int)f;
+}
 static inline int imin(int a, int b) { return a < b ? a : b; }
 static inline int imax(int a, int b) { return a > b ? a : b; }
 
 /* fine.h:130-152 */
 static void scanline_bounds(const float b[3], const float ndu[3], const float inv[3], int* min_u, int* max_u) {
   for (int i = 0; i < 3; i++) {
-    if (ndu[i] > 0.0f) *min_u = imax(*min_u, (int)ceilf(-b[i] * inv[i]));
-    else if (ndu[i] < 0.0f) *max_u = imin(*max_u, (int)(-b[i] * inv[i]));
+    if (ndu[i] > 0.0f) *min_u = imax(*min_u, f2i(ceilf(-b[i] * inv[i])));
+    else if (ndu[i] < 0.0f) *max_u = imin(*max_u, f2i(-b[i] * inv[i]));
     else if (b[i] < 0.0f) *min_u = *max_u + 1;
   }
 }
@@ -82,8 +90,8 @@ long long orc_voxelize_thin(const float* verts, int n_verts, const int* tris_in,
     }
     int b0[3], b1[3];
     for (int i = 0; i < 3; i++) {
-      b0[i] = imin(imax((int)lo[i], 0), N - 1);
-      b1[i] = imin(imax((int)ceilf(hi[i]), 0), N - 1);
+      b0[i] = imin(imax(f2i(lo[i]), 0), N - 1);
+      b1[i] = imin(imax(f2i(ceilf(hi[i])), 0), N - 1);
     }
     const f3 e0 = {v1.x - v0.x, v1.y - v0.y, v1.z - v0.z};
     const f3 e1 = {v2.x - v1.x, v2.y - v1.y, v2.z - v1.z};
@@ -153,7 +161,7 @@ long long orc_voxelize_thin(const float* verts, int n_verts, const int* tris_in,
               const float q1 = pex * uf;
               const float q2 = pey * vf;
               const float wf = pez - (q1 + q2);
-              const int w = (int)(wf * sel_w(axis, inv_delta));
+              const int w = f2i(wf * sel_w(axis, inv_delta));
               if (w >= isel_w(axis, tile) && w < isel_w(axis, tile) + T) {
                 int x, y, z;
                 if (axis == 0) { x = w; y = u; z = v; }

@@ -122,6 +122,11 @@ def run(name, depth=None, reps=3, rank=0, world=1, device=0, verbose=False):
     same_structure = svo_s.size == nodes
     svo_s.close()
     del cen_s, col_s
+    # the reference's renderer only shows nodes whose occupancy counter has saturated (a sample terminates a ray when
+    # alpha >= 254, cone_tracing_kernels.cu:115-121; a once-observed surface is transparent): observe the grid 64 times
+    for _ in range(max(0, 64 - (reps + 1))):
+        svo.integrate_voxels(cen, col)
+    svo.sync()
     # ---- raycast: camera outside the cube for the bunny (2.5 half edges from the centre), inside the
     # atrium for sponza; interleaved row bands over the ranks
     c = np.asarray(center, dtype=np.float64)

@@ -71,13 +71,16 @@ def main():
         prev = lo
     # phases of CTA 0 of each role in the LAST launch that ran it (SM-clock checkpoints, osl_debug_profile)
     from phase_profile import NAMES
-    prof = (C.c_uint64 * 64)()
-    lib.osl_debug_profile(prof, 64)
+    prof = (C.c_uint64 * 128)()
+    lib.osl_debug_profile(prof, 128)
     mhz = 1965.0
     for kern, phases in NAMES.items():
         print(kern)
         for a_, b_, name in phases:
             print("    %-44s %7.2f us" % (name, (prof[b_] - prof[a_]) / mhz))
+    print("assign pass 2 of CTA 0, per warp: us after the pass began / first level d0 / any split")
+    print("   " + "  ".join("%.1f/%d/%d" % ((prof[64 + w] - prof[28]) / mhz, prof[80 + w] & 0xFF, prof[80 + w] >> 8)
+                           for w in range(16)))
 
 
 if __name__ == "__main__":
