@@ -161,7 +161,7 @@ def load_bmp(path):
     return (data[..., ::-1].astype(np.float32) / np.float32(255.0))
 
 
-def triangle_colors(uv, tex):
+def triangle_colors(uv, tex, wrap=False):
     """The reference's per-triangle flat colour (ColorShader, voxelization.cu:90-139 + createVoxelGrid :219-236): the
     texel at the first corner's (u, v) -- int(u * width), int(v * height), clamped here where the reference indexes
     unchecked -- quantised to 8 bits and returned as byte / 255; no texture coordinates: texel 0; no texture: green.
@@ -172,6 +172,8 @@ def triangle_colors(uv, tex):
         out[:, 1] = 1.0
         return out
     h, w = tex.shape[:2]
+    if wrap:  # tiling texture coordinates (sponza): the fractional part, as a renderer would sample them
+        uv = uv - np.floor(uv)
     tx = np.clip((uv[:, 0] * w).astype(np.int64), 0, w - 1)
     ty = np.clip((uv[:, 1] * h).astype(np.int64), 0, h - 1)
     c = np.clip(tex[ty, tx], 0.0, 1.0)

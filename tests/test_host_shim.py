@@ -205,8 +205,21 @@ def test_scene_voxelize_meshes_replay_matches_oracle(tmp_path):
     size = float(b1[0])
     assert (np.float32(cx), np.float32(cy), np.float32(cz)) == tuple(np.float32(c) for c in center)
     assert np.float32(half) == np.float32(size)
-    keys, tris, cen = orc.voxelize_mesh(V, T, tuple(center), size, 8)
-    colors = np.zeros((keys.size, 4), dtype=np.float32)
+    # meshToVoxelGrid with the reference's signature = the reference's rule: voxelpipe THIN_RASTER on the dense 256^3
+    # grid over the mesh BOUNDING BOX (oracle/osl_oracle_thin.c), centres per getCenterFromIndex (voxelization.cu:58-78),
+    # handed to svoFromVoxelGrid in ascending order of their keys in the octree cube (ties by grid index)
+    cells, tris = orc.voxelize_thin(V, T, b0, b1, 8)
+    f32 = np.float32
+    td = (b1 - b0).astype(f32) / f32(32)
+    pd = td / f32(8)
+    cen = np.ones((cells.shape[0], 4), dtype=f32)
+    cen[:, :3] = (b0[None, :] + (cells // 8).astype(f32) * td[None, :] + (cells % 8).astype(f32) * pd[None, :] +
+                  (pd / f32(2.0))[None, :]).astype(f32)
+    keys = orc.compute_keys(cen[:, :3], tuple(center), size, 8)
+    lin = (cells[:, 2].astype(np.int64) * 256 + cells[:, 1]) * 256 + cells[:, 0]
+    order = np.lexsort((lin, keys))
+    cen = np.ascontiguousarray(cen[order])
+    colors = np.zeros((cen.shape[0], 4), dtype=np.float32)
     colors[:, 1] = np.float32(255 / 255.0)  # no texture: green
     ref = orc.OracleSVO(tuple(center), size, 8)
     ref.integrate_voxels(cen, colors)

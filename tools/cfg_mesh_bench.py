@@ -62,7 +62,8 @@ def run(name, depth=None, reps=3, rank=0, world=1, device=0, verbose=False):
         V = (V * np.float32(scale)).astype(np.float32)
         tex_path = graft.asset("texture1.bmp")
         tex = pkg.synth.load_bmp(tex_path) if tex_path else None
-        colors = pkg.synth.triangle_colors(uv if uv is not None else np.zeros((T.shape[0], 2), np.float32), tex)
+        colors = pkg.synth.triangle_colors(uv if uv is not None else np.zeros((T.shape[0], 2), np.float32), tex,
+                                           wrap=(name == "cfg5"))
     lo, hi = V.min(axis=0), V.max(axis=0)
     center = tuple(float(x) for x in (np.float32(0.5) * (lo + hi)))
     half = float(hi[0])  # scene.cpp:78: bbox.bbox1.x (quirk Q10), not an extent
