@@ -911,7 +911,47 @@ __device__ __forceinline__ void assign_block(int vb, int n, const u64* __restric
   u32 par_idx = (d0 > 1) ? s_w[warp][OSL_CLVL(D, d0 - 1)] - 1u : 0u;
   u32 path_tile = 0; // tile holding the level-(d) nodes below this key's level-(d-1) node (root: tile 0)
   size_t o_prev = 0;  // where this lane's level-(d-1) entry went (valid when it heads that level)
-  for (int d = d0; d <= D; d++) {
+  // Solo prefix.  The warp's collectives start at its smallest m, but the levels between the smallest and the
+  // second-smallest m are headed by ONE lane (typically: the first key of a frame or of a far sub-tree heads a dozen
+  // levels on its own, the other 31 lanes only the last three or four).  That lane lays those levels out by itself,
+  // rank 0 of the warp at each of them, without a single vote; the warp-wide loop starts where company begins.
+  int d_main = d0;
+  if (!any_split) {
+    const unsigned um = unique ? (unsigned)m : (unsigned)D;
+    const unsigned m_min = __reduce_min_sync(FULL, um);
+    const u32 who = __ballot_sync(FULL, um == m_min);
+    if (__popc(who) == 1) {
+      const int solo = __ffs(who) - 1;
+      const int m_2nd = (int)__reduce_min_sync(FULL, lane == solo ? (unsigned)D : um);
+      if (m_2nd > d0) {
+        if (lane == solo) {
+          for (int d = d0; d < m_2nd; d++) {
+            const u32 lbase = s_w[warp][OSL_CLVL(D, d)];
+            if (m < d) {
+              const u32 self = (d == m + 1) ? node : path_tile + (u32)key_digit(k, D, d);
+              const u32 ct = (carried && D - 1 - d < PATH_KEEP) ? s_path[(D - 1 - d) * AN_THREADS + tid]
+                             : (carried && slot >= 0)         ? s_shallow[d * SHALLOW_SLOTS + slot]
+                                                               : (pool[2 * (size_t)node] & OSL_MASK);
+              node = ct + (u32)key_digit(k, D, d + 1);
+              path_tile = ct;
+              const size_t o = lv.off[d] + lbase;
+              if (d >= 2 && m < d - 1) lv.fc[o_prev] = lbase;
+              o_prev = o;
+              lv.ctile[o] = ct;
+              lv.digit[o] = (uint8_t)key_digit(k, D, d);
+              lv.par[o] = par_idx;
+              lv.self[o] = self;
+              par_idx = lbase;
+            } else {
+              par_idx = lbase - 1u;
+            }
+          }
+        }
+        d_main = m_2nd;
+      }
+    }
+  }
+  for (int d = d_main; d <= D; d++) {
     const bool f = unique && m < d;
     const u32 bal = __ballot_sync(FULL, f);
     bool sp = false;
