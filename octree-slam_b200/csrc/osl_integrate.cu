@@ -951,6 +951,7 @@ __device__ __forceinline__ void assign_block(int vb, int n, const u64* __restric
       }
     }
   }
+  if (vb == 0 && tid == 0) { g_osl_prof[96] = (unsigned long long)clock64(); g_osl_prof[97] = (unsigned long long)d_main; }
   for (int d = d_main; d <= D; d++) {
     const bool f = unique && m < d;
     const u32 bal = __ballot_sync(FULL, f);

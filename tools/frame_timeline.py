@@ -78,6 +78,7 @@ def main():
         print(kern)
         for a_, b_, name in phases:
             print("    %-44s %7.2f us" % (name, (prof[b_] - prof[a_]) / mhz))
+    print("warp 0 of CTA 0: solo prefix %.2f us, warp-wide loop from level %d" % ((prof[96] - prof[28]) / mhz, prof[97]))
     print("assign pass 2 of CTA 0, per warp: us after the pass began / first level d0 / any split")
     print("   " + "  ".join("%.1f/%d/%d" % ((prof[64 + w] - prof[28]) / mhz, prof[80 + w] & 0xFF, prof[80 + w] >> 8)
                            for w in range(16)))
