@@ -87,7 +87,6 @@ __device__ __forceinline__ bool cell_has(const RayCell& c, int depth, float tx, 
 __global__ void __launch_bounds__(RAY_THREADS)
 k_raycast(const u32* __restrict__ pool, RayParams P, uchar4* __restrict__ out, unsigned long long* stats) {
   __shared__ float s_af[256];  // (A - 127) / 127.0f for every alpha byte (Q9: no clamp)
-  __shared__ RayCell s_cellB[RAY_THREADS];
   for (int a = threadIdx.x; a < 256; a += RAY_THREADS) s_af[a] = __fdiv_rn((float)(a - 127), 127.0f);
   __syncthreads();
   // a warp renders an 8x4-pixel patch (not 32 pixels of one row): neighbouring rays visit the same nodes and take
@@ -114,10 +113,7 @@ k_raycast(const u32* __restrict__ pool, RayParams P, uchar4* __restrict__ out, u
     float len = ray_length(rx, ry, rz);
 
     const float INF = __int_as_float(0x7f800000);
-    // deep cell in registers; the shallow one, consulted on ~15 % of the steps, in shared memory (13 words per thread,
-    // an odd stride: conflict-free), which takes the kernel from 70 to under 64 registers -- 8 instead of 7 CTAs per SM
-    RayCell A;
-    RayCell& B = s_cellB[threadIdx.x];
+    RayCell A, B;  // deep, shallow
     A.lvl = -1; B.lvl = -1;
     A.child = A.self = B.child = B.self = 0u;
     A.cx = A.cy = A.cz = A.e = B.cx = B.cy = B.cz = B.e = 0.f;
