@@ -38,7 +38,12 @@ RAY_W, RAY_H = 640, 480
 FOV = 45.0
 METRIC = "depth_frames_per_sec_640x480_into_depth16_svo"
 # one `ncu --set full` capture of k_raycast on the bench map (profiles/r02_ncu_full_summary_raycast.csv)
-RAY_NCU = {"dram_bytes": None, "issue": None, "source": "profiles/r02_ncu_full_summary_raycast.csv"}
+RAY_NCU = {"dram_bytes": 414976,
+           "issue": {"issue_slots_active_pct": 72.6, "inst_per_cycle_per_sm": 2.38, "peak_inst_per_cycle_per_sm": 4.0,
+                     "active_threads_per_warp_inst": 22.45, "l1_hit_pct": 97.1, "warps_active_pct": 32.9,
+                     "top_stalls": "wait 29 %, not selected 17 %, selected 15 %, long scoreboard 11 % "
+                                   "(profiles/r02_ncu_raycast_stalls.csv)"},
+           "source": "profiles/r02_ncu_full_summary_raycast.csv (640x480, 25-frame bench map, 198 us under ncu)"}
 
 
 def make_ring(synth, n_frames, seed0=0):
@@ -385,7 +390,7 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      # dram__bytes_read.sum + dram__bytes_write.sum of the four kernels of one frame, one ncu --set full
                      # capture (profiles/r01_ncu_full_summary_v07.csv; cold caches: ncu flushes L2 between kernels)
-                     "traffic": 2269184, "traffic_source": "profiles/r01_ncu_full_summary_v07.csv",
+                     "traffic": 2164992, "traffic_source": "profiles/r02_ncu_full_summary_kframe.csv (one k_frame launch)",
                      "peak_source": peak_src,
                      "kernel": "k_frame: ONE launch per frame whose four roles (emit / sort / structure / values) each "
                                "work on the frame that has reached them; achieved = B_int of one frame / average "

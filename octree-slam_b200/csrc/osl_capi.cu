@@ -176,7 +176,7 @@ void osl_svo_destroy(osl_svo* t) {
   for (int i = 0; i < 4; i++)
     if (t->pipe[i]) cudaStreamDestroy(t->pipe[i]);
   cudaFree(t->d_m); cudaFree(t->d_s); cudaFree(t->d_blockcnt);
-  cudaFree(t->d_keysC); cudaFree(t->d_payC); cudaFree(t->d_split); cudaFree(t->d_wcache); cudaFree(t->d_start); cudaFree(t->d_flags);
+  cudaFree(t->d_keysC); cudaFree(t->d_payC); cudaFree(t->d_split); cudaFree(t->d_wcache); cudaFree(t->d_blockcnt_tot); cudaFree(t->d_start); cudaFree(t->d_flags);
   cudaFree(t->d_scan_totals); cudaFree(t->d_fs);
   cudaFree(t->ex_kA); cudaFree(t->ex_kB); cudaFree(t->ex_nA); cudaFree(t->ex_nB); cudaFree(t->ex_status); cudaFree(t->ex_cnt);
   for (int i = 0; i < OSL_STAGES; i++) {

@@ -774,7 +774,8 @@ __device__ __forceinline__ void analyze_block(int vb, int n, const u64* __restri
                                               const u32* pool, const TreeParams& tp, uint8_t* __restrict__ m8,
                                               uint8_t* __restrict__ s8, u32* __restrict__ start,
                                               u32* s_ctot, u32* s_cnt, u64* wcache, u32* s_path, u32* s_shallow,
-                                              u64& k_out, int& m_out, int& s_out, u32& st_out, int& slot_out) {
+                                              u64& k_out, int& m_out, int& s_out, u32& st_out, int& slot_out,
+                                              int has_prev, u64 prev_key) {
   const int D = tp.D, NC = OSL_NCOUNT(D);
   k_out = 0; m_out = D; s_out = OSL_NONE; st_out = 0; slot_out = -1;
   for (int c = threadIdx.x; c < NC; c += AN_THREADS) s_cnt[c] = 0;
@@ -785,8 +786,8 @@ __device__ __forceinline__ void analyze_block(int vb, int n, const u64* __restri
   if (j < n) {
     const u64 k = keys[j];
     int m = 0;
-    if (j > 0) {
-      const u64 x = k ^ keys[j - 1];
+    if (j > 0 || has_prev) {
+      const u64 x = k ^ (j > 0 ? keys[j - 1] : prev_key);
       m = x ? (D - 1 - (63 - __clzll((long long)x)) / 3) : D;
     }
     int s = OSL_NONE;
@@ -1019,6 +1020,12 @@ struct StructArgs {
   FrameState* fs; FrameState* fr; FrameState* hr; uint8_t* m8; uint8_t* s8; u32* start; u32* ctatot;
   u32* flags; u32 epoch; LevelArrays lv; int mode; int capacity; int n_in; int parity; u64* split_out;
   u64* wcache;  // walk cache (NULL = off)
+  // one map built by several GPUs (osl_shard_*): this rank's keys are a contiguous slice of the globally sorted list
+  int shard;          // 0 normal; 1 analyse only: publish the counters, write this rank's totals, stop; 2 assign only
+  int has_prev; u64 prev_key;  // the key before the slice (last key of the lower rank): the first key's predecessor
+  const u32* ext;     // shard 2: [2][NC] bucket counters -- exclusive prefix over the lower ranks, totals over all ranks
+  u32* rank_tot;      // shard 1: [NC] this rank's totals
+  u32 src_base;       // voxel grids: global sorted position of the slice's first key (colour index, Q11)
 };
 #define STRUCT_MAXG 1024  // most CTAs a structure grid / role may have (s_has)
 #define STRUCT_SMEM ((AN_WARPS + 4) * NC_MAX * 4 + AN_WARPS * 4 + 2 * STRUCT_MAXG + 8 * 512 * 4 + (OSL_MAXD * 32 + 4) * 4)
@@ -1043,7 +1050,7 @@ __device__ __forceinline__ void structure_body(const StructArgs& A, int bid, int
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = __ldcg(&fs->acc_emit[parity]);
   const int n_valid = __ldcg(&fs->acc_valid[parity]);
-  const int n_invalid_front = n_in - n_valid;
+  const int n_invalid_front = n_in - n_valid + (int)A.src_base;
   const int cur = __ldcg(&fs->cur_size);
   // voxel grids that arrived sorted and gap-free were not sorted again: read k_emit's dense copy
   const u64* __restrict__ keys = (mode == 2 && __ldcg(&fs->acc_unsorted[parity]) == 0) ? keys_dense : keys_sorted;
@@ -1065,20 +1072,23 @@ __device__ __forceinline__ void structure_body(const StructArgs& A, int bid, int
   // SM the walk latency is already hidden and the extra serial step only adds two block barriers per block.)
   u64 ck = 0; int cm = D, cs = OSL_NONE, cslot = -1; u32 cst = 0;  // this thread's key state when the CTA owns a single block
   for (int vb = vb0; vb < vb1; vb++)
-    analyze_block(vb, n, keys, pay, mode, pool, tp, m8, s8, start, s_ctot, &s_w[0][0], A.wcache, s_path, s_shallow, ck, cm,
-                  cs, cst, cslot);
-  const bool carried = (vb1 - vb0 == 1);
+    if (A.shard != 2)
+      analyze_block(vb, n, keys, pay, mode, pool, tp, m8, s8, start, s_ctot, &s_w[0][0], A.wcache, s_path, s_shallow, ck,
+                    cm, cs, cst, cslot, A.shard ? A.has_prev : 0, A.prev_key);
+  const bool carried = (vb1 - vb0 == 1) && A.shard != 2;
   // publish this CTA's counter vector behind an epoch flag (every CTA publishes, also one without blocks).  Compact
   // form: the D per-level counters always; the (D+1)^2 bucket counters only when a key of this CTA splits a node --
   // bit 31 of the flag says so -- which in steady state (the map already holds the surface) is no CTA at all.
   u32 mine_split = 0;
   for (int c = D + tid; c < NC; c += AN_THREADS) mine_split |= s_ctot[c];
   const int has_split = __syncthreads_or(mine_split != 0u);
-  for (int c = tid; c < (has_split ? NC : D); c += AN_THREADS) ctatot[(size_t)bid * NC + c] = s_ctot[c];
-  __syncthreads();
-  if (tid == 0) {
-    __threadfence();
-    *(volatile u32*)&flags[bid] = epoch | (has_split ? 0x80000000u : 0u);
+  if (A.shard != 2) {  // (an assign-only launch finds the vectors and flags its analyse-only launch published)
+    for (int c = tid; c < (has_split ? NC : D); c += AN_THREADS) ctatot[(size_t)bid * NC + c] = s_ctot[c];
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      *(volatile u32*)&flags[bid] = epoch | (has_split ? 0x80000000u : 0u);
+    }
   }
   PROF(17);
 
@@ -1159,6 +1169,20 @@ __device__ __forceinline__ void structure_body(const StructArgs& A, int bid, int
   __syncthreads();
   PROF(19);
   PROF(20);
+  if (A.shard == 1) {  // sharded build, first half: this rank's totals go to the host, which sums them over the ranks
+    if (bid == G - 1)
+      for (int c = tid; c < NC; c += AN_THREADS) A.rank_tot[c] = s_tot[c];
+    return;
+  }
+  if (A.shard == 2) {
+    // second half: the bucket counters become global (totals over all ranks for the plan, the lower ranks' counts in
+    // front of this rank's for the tile ranks); the per-level counters stay local -- the level lists are this rank's own
+    for (int c = D + tid; c < NC; c += AN_THREADS) {
+      s_base[c] += __ldg(&A.ext[c]);
+      s_tot[c] = __ldg(&A.ext[NC + c]);
+    }
+    __syncthreads();
+  }
 
   // phase B2: the allocation plan.  Entry e = i*D + (d-1) in the reference's order (pass i, then depth d):
   // bucket (s = d - i, d).  Exclusive scan over the <= D*D entries gives each bucket's first global rank.
@@ -1318,6 +1342,7 @@ __device__ __forceinline__ void level_inner(u32* pool, const LevelArrays& lv, in
 struct LevelArgs {
   u32* pool; LevelArrays lv; const FrameState* fr; u32* done; int D; int mode;
   const uint8_t* rgb; const float* colors4;
+  int no_root;                   // sharded build: the root average (Q6) is written by osl_shard_fixup, not here
   FrameState* hr; int done_tag;  // pinned result block of the frame; done_tag (frame number + 1) is stored into
                                  // hr->done_flag when every value of the frame has been written
 };
@@ -1447,7 +1472,8 @@ __device__ __forceinline__ void levels_body(const LevelArgs& A, int bid, int G, 
         ct = __ldg(&lv.ctile[ol + idx]);
         dig = (u32)__ldg(&lv.digit[ol + idx]);
         node = __ldg(&lv.self[ol + idx]);
-        par = (l == 1) ? 0u : (u32)(1 + s_pre[l - 1]) + __ldg(&lv.par[ol + idx]);
+        const u32 pr = __ldg(&lv.par[ol + idx]);  // 0xFFFFFFFF: the parent is in another rank's lists (sharded build)
+        par = (l == 1) ? 0u : (pr == 0xFFFFFFFFu ? 0xFFFFu : (u32)(1 + s_pre[l - 1]) + pr);
       }
       const uint4* tile = reinterpret_cast<const uint4*>(pool + 2 * (size_t)(ct & OSL_MASK));
 #pragma unroll
@@ -1466,7 +1492,7 @@ __device__ __forceinline__ void levels_body(const LevelArgs& A, int bid, int G, 
         const int e = base + idx;
         const u32 avg = osl_average8(s_w1[e]);
         pool[2 * (size_t)s_node[e] + 1] = avg;
-        s_w1[s_par[e]][s_dig[e]] = avg;
+        if (s_par[e] != 0xFFFFu) s_w1[s_par[e]][s_dig[e]] = avg;
       }
       __syncthreads();
     }
@@ -1477,11 +1503,11 @@ __device__ __forceinline__ void levels_body(const LevelArgs& A, int bid, int G, 
           const int e = base + tid;
           const u32 avg = osl_average8(s_w1[e]);
           pool[2 * (size_t)s_node[e] + 1] = avg;
-          s_w1[s_par[e]][s_dig[e]] = avg;
+          if (s_par[e] != 0xFFFFu) s_w1[s_par[e]][s_dig[e]] = avg;
         }
         __syncwarp();
       }
-      if (tid == 0 && s_nl[1] > 0) pool[1] = osl_average8(s_w1[0]);  // phase 3 (Q6)
+      if (tid == 0 && s_nl[1] > 0 && !A.no_root) pool[1] = osl_average8(s_w1[0]);  // phase 3 (Q6)
     }
     PROF(39);
     __syncthreads();
@@ -1494,7 +1520,7 @@ __device__ __forceinline__ void levels_body(const LevelArgs& A, int bid, int G, 
     for (int idx = tid; idx < n_d; idx += LEVEL_THREADS) level_inner(pool, lv, d, idx);
     __syncthreads();
   }
-  if (tid == 0 && s_nl[1] > 0) {  // phase 3 (Q6)
+  if (tid == 0 && s_nl[1] > 0 && !A.no_root) {  // phase 3 (Q6)
     const uint4* tile = reinterpret_cast<const uint4*>(pool);
     u32 v[8];
 #pragma unroll
@@ -1688,6 +1714,7 @@ osl_status osl_integrate_init(osl_svo* t) {
   OSL_CUDA(cudaFuncSetAttribute((const void*)k_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, FRAME_SMEM));
   OSL_CUDA(cudaFuncSetAttribute((const void*)k_sort_bucket, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM));
   OSL_CUDA(cudaMalloc(&t->d_split, OSL_FRONT * BK_BUCKETS * sizeof(u64)));
+  OSL_CUDA(cudaMalloc(&t->d_blockcnt_tot, 3 * NC_MAX * sizeof(u32)));
   for (int f = 0; f < OSL_FRONT; f++) {
     OSL_CUDA(cudaMalloc(&t->d_bkeys[f], (size_t)OSL_BUCKETS * OSL_BUCKET_CAP * sizeof(u64)));
     OSL_CUDA(cudaMalloc(&t->d_bpay[f], (size_t)OSL_BUCKETS * OSL_BUCKET_CAP * sizeof(u32)));
@@ -1756,6 +1783,7 @@ static inline int mode_of(const osl_svo* t, int slot) { return t->ring_mode[slot
 static StructArgs make_struct_args(osl_svo* t, const u64* skeys, u32* spay, FrameState* fs, FrameState* fr,
                                    unsigned long long f, const LevelArrays& lv, int mode, int n, int fslot) {
   StructArgs A;
+  memset(&A, 0, sizeof(A));
   A.keys_sorted = skeys; A.keys_dense = t->d_keysB[fslot]; A.pay = spay; A.pool = t->d_pool; A.tp = t->tp;
   A.fs = fs; A.fr = fr; A.hr = &t->h_ring[f % OSL_RING];  // pinned host memory, device-accessible (UVA)
   A.m8 = t->d_m; A.s8 = t->d_s; A.start = t->d_start; A.ctatot = t->d_blockcnt; A.flags = t->d_flags;
@@ -1768,6 +1796,7 @@ static StructArgs make_struct_args(osl_svo* t, const u64* skeys, u32* spay, Fram
 static LevelArgs make_level_args(osl_svo* t, const LevelArrays& lv, const FrameState* fr, unsigned long long f,
                                  int mode, const uint8_t* rgb, const float* colors4) {
   LevelArgs A;
+  memset(&A, 0, sizeof(A));
   A.pool = t->d_pool; A.lv = lv; A.fr = fr;
   A.done = t->d_scan_totals + OSL_NCOUNT(OSL_MAXD);  // [0] one-sided barrier, [1] level barrier (zero at rest)
   A.D = t->tp.D; A.mode = mode; A.rgb = rgb; A.colors4 = colors4;
@@ -2362,6 +2391,155 @@ extern "C" osl_status osl_debug_trace(osl_svo* t, int enable, unsigned long long
   }
   t->trace_on = enable ? 1 : 0;
   return OSL_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ sharded build
+// ONE map built by several GPUs ("partition the key space by contiguous Morton ranges ... each GPU
+// all-gathers its per-pass split counts -> exclusive prefix over GPUs -> local ranks become global indices").  Input: a
+// voxel grid in Morton order without invalid entries (what the voxelisers and the extraction emit), present on every
+// rank; rank r takes the contiguous slice [lo, hi).  Three calls per rank, the exchange between them is the caller's
+// (shard.integrate_voxels_sharded: one all-gather of NC counters, one of the deltas):
+//   osl_shard_analyze   keys of the slice, phase A of k_structure with the lower rank's last key as the predecessor of
+//                       the slice's first key -> this rank's counter totals
+//   osl_shard_assign    phase B2 + C with the bucket counters made global (totals of all ranks for the plan, the lower
+//                       ranks' counts in front of this rank's), then the value fold of this rank's sub-trees
+//   osl_shard_fixup     (osl_replica.cu) after the ranks exchanged what they changed: the nodes on the paths of the
+//                       slices' first keys -- the only ones with children in two ranks -- are re-averaged bottom-up, and
+//                       the root average (Q6) is written
+// Node indices, child pointers and values come out bit-identical with a single-GPU osl_integrate_voxels of the whole
+// grid (tests/test_gpu_multirank.py).
+__global__ void k_key_of(const float* __restrict__ pts, int stride, long long idx, TreeParams tp, u64* out, int* valid) {
+  const float* q = pts + (size_t)stride * idx;
+  u64 k;
+  const bool ok = osl_key(q[0], q[1], q[2], tp, k);
+  *out = k;
+  *valid = ok ? 1 : 0;
+}
+
+extern "C" osl_status osl_shard_analyze(osl_svo* t, const float* d_centers4, int n_total, int lo, int hi,
+                                        uint32_t* h_totals, int* n_counters, void* stream) {
+  if (!t || !d_centers4 || n_total <= 0 || lo < 0 || hi < lo || hi > n_total || !h_totals) return OSL_ERR_INVALID;
+  OSL_CUDA(cudaSetDevice(t->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = hi - lo, D = t->tp.D, NC = OSL_NCOUNT(D);
+  if (n_counters) *n_counters = NC;
+  osl_status rc = osl_poll_results(t, true);  // exact size, idle pipeline: the three calls run in stream order on `st`
+  if (rc) return rc;
+  rc = drain_streams(t, st);
+  if (rc) return rc;
+  if (t->sticky_error) return t->sticky_error;
+  rc = osl_ensure_workspace(t, (size_t)(n > 0 ? n : 1));
+  if (rc) return rc;
+  const unsigned long long f = t->seq;
+  const int fslot = (int)(f % OSL_FRONT), bslot = (int)(f % OSL_BACK);
+  FrameState* fs = t->d_fs;
+  // the predecessor of the slice's first key (the grid is on every rank: no exchange needed)
+  u64 prev_key = 0;
+  int has_prev = 0;
+  u64* d_tmp = reinterpret_cast<u64*>(t->d_scan_totals);  // scratch (idle pipeline)
+  if (lo > 0) {
+    k_key_of<<<1, 1, 0, st>>>(d_centers4, 4, (long long)lo - 1, t->tp, d_tmp, reinterpret_cast<int*>(d_tmp + 1));
+    OSL_LAUNCHED(1);
+    u64 h[2];
+    OSL_CUDA(cudaMemcpyAsync(h, d_tmp, sizeof(h), cudaMemcpyDeviceToHost, st));
+    OSL_CUDA(cudaStreamSynchronize(st));
+    OSL_CUDA(cudaMemsetAsync(d_tmp, 0, sizeof(h), st));
+    if (!(int)h[1]) return OSL_ERR_UNSUPPORTED;  // invalid voxels sort to the front in the reference: not a slice-able grid
+    prev_key = h[0];
+    has_prev = 1;
+  }
+  EmitParams ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.pts = d_centers4 + 4 * (size_t)lo; ep.stride = 4; ep.n = n; ep.mode = 2;
+  t->shard_n = n; t->shard_lo = lo; t->shard_f = f;
+  if (n > 0) {
+    const int etiles = (n + EMIT_TILE - 1) / EMIT_TILE;
+    k_emit<<<etiles, EMIT_THREADS, EMIT_SMEM, st>>>(ep, t->tp, 0, t->d_keysA[fslot], t->d_payA[fslot], t->d_keysB[fslot], fs,
+                                                   fslot, nullptr, nullptr, nullptr);
+    OSL_LAUNCHED(1);
+  }
+  // phase A + counter exchange among this rank's CTAs; the totals come back to the host
+  u32* d_tot = t->d_blockcnt_tot;
+  {
+    const int grid = grid_for(n, AN_THREADS, t->structure_grid);
+    StructArgs A = make_struct_args(t, t->d_keysA[fslot], t->d_payA[fslot], fs, t->d_fs + 1 + bslot, f, t->lv[bslot], 2, n, fslot);
+    A.shard = 1; A.has_prev = has_prev; A.prev_key = prev_key; A.rank_tot = d_tot; A.src_base = (u32)lo;
+    void* args[] = {&A};
+    OSL_CUDA(cudaLaunchCooperativeKernel((void*)k_structure, dim3(grid), dim3(AN_THREADS), args, STRUCT_SMEM, st));
+    OSL_LAUNCHED(1);
+    t->shard_grid = grid;
+  }
+  int h_flags[2] = {0, 0};
+  OSL_CUDA(cudaMemcpyAsync(h_totals, d_tot, NC * sizeof(u32), cudaMemcpyDeviceToHost, st));
+  OSL_CUDA(cudaMemcpyAsync(&h_flags[0], &fs->acc_unsorted[fslot], sizeof(int), cudaMemcpyDeviceToHost, st));
+  OSL_CUDA(cudaMemcpyAsync(&h_flags[1], &fs->acc_valid[fslot], sizeof(int), cudaMemcpyDeviceToHost, st));
+  OSL_CUDA(cudaStreamSynchronize(st));
+  if (n > 0 && (h_flags[0] != 0 || h_flags[1] != n)) {  // unsorted, or invalid voxels: the slices would not be key ranges
+    int zero[3] = {0, 0, 0};
+    cudaMemcpy(&fs->acc_unsorted[fslot], &zero[0], sizeof(int), cudaMemcpyHostToDevice);
+    cudaMemcpy(&fs->acc_valid[fslot], &zero[0], sizeof(int), cudaMemcpyHostToDevice);
+    cudaMemcpy(&fs->acc_emit[fslot], &zero[0], sizeof(int), cudaMemcpyHostToDevice);
+    return OSL_ERR_UNSUPPORTED;
+  }
+  if (has_prev && n > 0) {  // the slices must be key ranges in rank order
+    u64 first = 0;
+    OSL_CUDA(cudaMemcpy(&first, t->d_keysB[fslot], sizeof(u64), cudaMemcpyDeviceToHost));
+    if (first < prev_key) return OSL_ERR_UNSUPPORTED;
+  }
+  return OSL_OK;
+}
+
+extern "C" osl_status osl_shard_assign(osl_svo* t, const float* d_colors4, const uint32_t* h_base, const uint32_t* h_totals,
+                                       void* stream) {
+  if (!t || !h_base || !h_totals || !d_colors4) return OSL_ERR_INVALID;
+  OSL_CUDA(cudaSetDevice(t->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int D = t->tp.D, NC = OSL_NCOUNT(D), n = t->shard_n;
+  const unsigned long long f = t->shard_f;
+  if (f != t->seq) return OSL_ERR_INVALID;  // no osl_shard_analyze pending
+  const int fslot = (int)(f % OSL_FRONT), bslot = (int)(f % OSL_BACK);
+  FrameState* fs = t->d_fs;
+  // the pool must hold what ALL ranks append: 8 nodes per split, over every bucket
+  unsigned long long splits = 0;
+  for (int c = D; c < NC; c++) splits += h_totals[c];
+  {
+    const size_t want = (size_t)(t->size > 8 ? t->size : 8) + 8ull * splits;
+    if (want > ((size_t)1 << 30)) return OSL_ERR_POOL_OVERFLOW;
+    if (want > t->cap_nodes) {
+      osl_status rc = osl_grow_pool(t, want, st);
+      if (rc) return rc;
+    }
+  }
+  u32* d_ext = t->d_blockcnt_tot + NC_MAX;  // [2][NC]
+  OSL_CUDA(cudaMemcpyAsync(d_ext, h_base, NC * sizeof(u32), cudaMemcpyHostToDevice, st));
+  OSL_CUDA(cudaMemcpyAsync(d_ext + NC, h_totals, NC * sizeof(u32), cudaMemcpyHostToDevice, st));
+  {
+    StructArgs A = make_struct_args(t, t->d_keysA[fslot], t->d_payA[fslot], fs, t->d_fs + 1 + bslot, f, t->lv[bslot], 2, n, fslot);
+    A.shard = 2; A.ext = d_ext; A.src_base = (u32)t->shard_lo;
+    void* args[] = {&A};
+    OSL_CUDA(cudaLaunchCooperativeKernel((void*)k_structure, dim3(t->shard_grid), dim3(AN_THREADS), args, STRUCT_SMEM, st));
+    OSL_LAUNCHED(1);
+  }
+  if (n > 0) {
+    const int grid = grid_for(n, LEVEL_THREADS, t->levels_grid);
+    LevelArgs A = make_level_args(t, t->lv[bslot], t->d_fs + 1 + bslot, f, 2, nullptr, d_colors4);
+    A.no_root = 1;
+    void* args[] = {&A};
+    OSL_CUDA(cudaLaunchCooperativeKernel((void*)k_levels, dim3(grid), dim3(LEVEL_THREADS), args, LEVEL_SMEM, st));
+    OSL_LAUNCHED(1);
+  }
+  const int slot = (int)(f % OSL_RING);
+  OSL_CUDA(cudaEventRecord(t->ring_ev[slot], st));
+  t->ring_kind[slot] = 0;
+  t->join_pending = 0;
+  t->ring_headroom[slot] = 0;
+  t->ring_mode[slot] = 2;
+  t->ring_head++;
+  t->seq++;
+  t->last_stream = st;
+  t->last_piped = 0;
+  t->last_fused = 0;
+  return osl_poll_results(t, true);
 }
 
 extern "C" osl_status osl_debug_profile(unsigned long long* out, int n) {

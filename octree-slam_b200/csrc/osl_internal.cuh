@@ -176,6 +176,8 @@ struct osl_svo {
   u32* d_start;       // per sorted key: node at the first depth it heads (k_structure phase A -> C)
   u32* d_flags;       // per virtual block: epoch of the frame whose count vector is published
   u32* d_blockcnt;    // [k_structure CTAs][NC] per-CTA counter vectors
+  u32* d_blockcnt_tot;  // sharded build: [3][NC_MAX] this rank's totals, then the external base / totals
+  int shard_n, shard_lo, shard_grid; unsigned long long shard_f;  // between osl_shard_analyze and osl_shard_assign
   u32* d_cta_hist[OSL_FRONT];  // sort: [grid][256]
   u32* d_scan_totals; // [NC_MAX + 8] scratch words; word NC_MAX = arrival counter of k_levels' one-sided barrier
   LevelArrays lv[OSL_BACK];
