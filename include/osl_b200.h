@@ -178,6 +178,29 @@ size_t osl_svo_delta_bytes(osl_svo* t);
 osl_status osl_svo_delta_pack(osl_svo* t, void* d_buf, size_t cap, size_t* bytes, void* stream);
 osl_status osl_svo_delta_apply(osl_svo* t, const void* d_buf, size_t bytes, void* stream);
 
+/* ---- ONE map built by several GPUs (Morton-range shards + the per-pass split-count prefix) ------------ */
+
+/* Input: a voxel grid in Morton order without invalid entries (what osl_voxelize_* and osl_extract_voxels emit), present
+ * on every rank, all ranks' trees in the same state.  Rank r takes the contiguous slice [lo, hi) of the grid.  Between
+ * the calls the CALLER exchanges two things with the other ranks (shard.integrate_voxels_sharded: NCCL all-gathers):
+ *   1. osl_shard_analyze  -> h_totals[*n_counters]: this rank's counters (levels, then (frontier, depth) buckets)
+ *      exchange: h_base[c] = sum of the LOWER ranks' totals, h_totals_all[c] = sum over ALL ranks
+ *   2. osl_shard_assign   allocates tiles at the global ranks (pass = depth - frontier depth, then numeric key, over all
+ *      ranks: svo.cu:220,284), writes this rank's nodes, folds the values of this rank's sub-trees
+ *      exchange: osl_shard_delta_pack on every rank, all-gather, osl_shard_delta_apply of every OTHER rank's delta
+ *   3. osl_shard_fixup    re-averages the nodes on the paths of the slices' first keys (children in two ranks) and writes
+ *      the root average (Q6)
+ * The pool is then bit-identical on every rank with a single-GPU osl_integrate_voxels of the whole grid.
+ * OSL_ERR_UNSUPPORTED: the slice is not sorted / contains invalid voxels. */
+osl_status osl_shard_analyze(osl_svo* t, const float* d_centers4, int n_total, int lo, int hi, uint32_t* h_totals,
+                             int* n_counters, void* stream);
+osl_status osl_shard_assign(osl_svo* t, const float* d_colors4, const uint32_t* h_base, const uint32_t* h_totals_all,
+                            void* stream);
+size_t osl_shard_delta_bytes(osl_svo* t);
+osl_status osl_shard_delta_pack(osl_svo* t, void* d_buf, size_t cap, size_t* bytes, void* stream);
+osl_status osl_shard_delta_apply(osl_svo* t, const void* d_buf, size_t bytes, void* stream);
+osl_status osl_shard_fixup(osl_svo* t, const float* d_centers4, int n_total, const int* h_starts, int n_bounds, void* stream);
+
 /* ---- raycast (cone_tracing_kernels.h:16) ------------------------------------------------------------------- */
 
 /* Replaces rendering::coneTraceSVO (cone_tracing_kernels.cu:157-198).  d_out: w*h uchar4 {R,G,B,A}.

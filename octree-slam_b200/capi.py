@@ -23,6 +23,7 @@ EXPORTS = [
     "osl_svo_sync", "osl_svo_join", "osl_svo_view", "osl_svo_size", "osl_svo_download", "osl_svo_upload", "osl_get_counters", "osl_svo_save", "osl_svo_load",
     "osl_raycast", "osl_raycast_host", "osl_raycast_pool", "osl_raycast_rows", "osl_raycast_bands", "osl_extract_voxels", "osl_voxelize_mesh", "osl_voxelize_thin", "osl_free_device", "osl_copy_device", "osl_debug_trace",
     "osl_svo_reserve", "osl_svo_pool_device", "osl_svo_adopt", "osl_svo_delta_bytes", "osl_svo_delta_pack", "osl_svo_delta_apply",
+    "osl_shard_analyze", "osl_shard_assign", "osl_shard_delta_bytes", "osl_shard_delta_pack", "osl_shard_delta_apply", "osl_shard_fixup",
     "osl_generate_vertex_map", "osl_transform_vertex_map", "osl_point_cloud_bbox", "osl_compute_keys",
     "osl_bilateral_filter", "osl_subsample_depth", "osl_subsample_f32", "osl_generate_normal_map", "osl_transform_normal_map",
     "osl_color_to_intensity", "osl_icp_cost",
@@ -117,6 +118,12 @@ def lib():
         "osl_svo_delta_bytes": (C.c_size_t, [vp]),
         "osl_svo_delta_pack": (i32, [vp, vp, C.c_size_t, C.POINTER(C.c_size_t), vp]),
         "osl_svo_delta_apply": (i32, [vp, vp, C.c_size_t, vp]),
+        "osl_shard_analyze": (i32, [vp, vp, i32, i32, i32, vp, C.POINTER(i32), vp]),
+        "osl_shard_assign": (i32, [vp, vp, vp, vp, vp]),
+        "osl_shard_delta_bytes": (C.c_size_t, [vp]),
+        "osl_shard_delta_pack": (i32, [vp, vp, C.c_size_t, C.POINTER(C.c_size_t), vp]),
+        "osl_shard_delta_apply": (i32, [vp, vp, C.c_size_t, vp]),
+        "osl_shard_fixup": (i32, [vp, vp, i32, vp, i32, vp]),
         "osl_generate_vertex_map": (i32, [vp, vp, i32, i32, f32, f32, i32, i32, vp]),
         "osl_transform_vertex_map": (i32, [vp, fp, i32, vp]),
         "osl_point_cloud_bbox": (i32, [vp, i32, fp, vp]),

@@ -191,3 +191,192 @@ osl_status osl_svo_delta_apply(osl_svo* t, const void* d_buf, size_t bytes, void
 }
 
 }  // extern "C"
+
+// ---- sharded build (osl_shard_analyze / osl_shard_assign in osl_integrate.cu) ------------------------------------------
+// What a rank changed in a sharded build: the nodes of its level lists only.  The tiles it allocated are scattered
+// through the appended range (every pass interleaves the ranks), so the receiver re-creates them from the child
+// pointers: a triple whose word0 points at or beyond `size_before` names a tile that did not exist -- its 8 value words
+// become "empty" (svo.cu:272-275) before the triples of the touched children are written.
+__global__ void k_delta_init_tiles(u32* __restrict__ pool, const uint3* __restrict__ in, int n, u32 size_before, int limit, int* bad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint3 e = in[i];
+  if (!(e.y & OSL_FLAG)) return;
+  const u32 tile = e.y & OSL_MASK;
+  if (tile < size_before) return;
+  if ((tile & 7u) || (long long)tile + 8 > (long long)limit) { atomicAdd(bad, 1); return; }
+#pragma unroll
+  for (int c = 0; c < 8; c++) pool[2 * (size_t)(tile + c) + 1] = OSL_EMPTY;
+}
+
+// The nodes on the paths of the slices' first keys are the only ones with touched children in two ranks.  One CTA: thread b
+// walks key b down the FINAL tree (every rank has applied every delta), then the paths are re-averaged level by level,
+// deepest first (averageChildren, svo.cu:384-441; shared ancestors get the same value from every thread that owns them);
+// thread 0 finally writes the root average into node 0's value word (quirk Q6) exactly as k_levels does on one GPU.
+#define FIX_MAX 64
+__global__ void k_shard_fixup(u32* __restrict__ pool, const u64* __restrict__ keys, int n_keys, int D, int any_touched) {
+  __shared__ u32 s_path[FIX_MAX][OSL_MAXD + 1];
+  const int b = threadIdx.x;
+  if (b < n_keys) {
+    const u64 key = keys[b];
+    u32 node = (u32)((key >> (3 * (D - 1))) & 7ull);
+    for (int d = 1; d <= D; d++) {
+      s_path[b][d] = node;
+      const u32 w0 = pool[2 * (size_t)node];
+      if (d == D || !(w0 & OSL_FLAG)) {
+        for (int q = d + 1; q <= D; q++) s_path[b][q] = 0xFFFFFFFFu;
+        break;
+      }
+      node = (w0 & OSL_MASK) + (u32)((key >> (3 * (D - d - 1))) & 7ull);
+    }
+  }
+  __syncthreads();
+  for (int d = D - 1; d >= 1; d--) {
+    if (b < n_keys) {
+      const u32 node = s_path[b][d];
+      if (node != 0xFFFFFFFFu) {
+        const u32 w0 = pool[2 * (size_t)node];
+        if (w0 & OSL_FLAG) {
+          const u32* tile = pool + 2 * (size_t)(w0 & OSL_MASK);
+          u32 v[8];
+#pragma unroll
+          for (int c = 0; c < 8; c++) v[c] = ((volatile const u32*)tile)[2 * c + 1];
+          ((volatile u32*)pool)[2 * (size_t)node + 1] = osl_average8(v);
+        }
+      }
+    }
+    __threadfence_block();
+    __syncthreads();
+  }
+  if (b == 0 && any_touched) {
+    u32 v[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) v[c] = ((volatile const u32*)pool)[2 * c + 1];
+    ((volatile u32*)pool)[1] = osl_average8(v);
+  }
+}
+
+__global__ void k_keys_of(const float* __restrict__ pts, const int* __restrict__ idx, int n, TreeParams tp, u64* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* q = pts + 4 * (size_t)idx[i];
+  u64 k;
+  osl_key(q[0], q[1], q[2], tp, k);
+  out[i] = k;
+}
+
+extern "C" {
+
+size_t osl_shard_delta_bytes(osl_svo* t) {
+  if (!t) return 0;
+  cudaSetDevice(t->device);
+  if (osl_poll_results(t, true) != OSL_OK || t->seq == 0) return 0;
+  const FrameState& F = t->h_ring[(t->seq - 1) % OSL_RING];
+  size_t touched = 0;
+  for (int d = 1; d <= t->tp.D; d++) touched += (size_t)F.n_level[d];
+  return sizeof(DeltaHeader) + touched * sizeof(uint3);
+}
+
+// this rank's changes of the last osl_shard_assign: header + (index, word0, word1) of its level-list nodes
+osl_status osl_shard_delta_pack(osl_svo* t, void* d_buf, size_t cap, size_t* bytes, void* stream) {
+  if (!t || !d_buf || !bytes) return OSL_ERR_INVALID;
+  OSL_CUDA(cudaSetDevice(t->device));
+  osl_status rc = osl_poll_results(t, true);
+  if (rc) return rc;
+  if (t->seq == 0) return OSL_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned long long f = t->seq - 1;
+  const FrameState& F = t->h_ring[f % OSL_RING];
+  const LevelArrays& lv = t->lv[f % OSL_BACK];
+  const int D = t->tp.D;
+  if (F.overflow) return OSL_ERR_POOL_OVERFLOW;
+  DeltaHeader h;
+  memset(&h, 0, sizeof(h));
+  h.magic = 0x534C534Fu;  // 'OSLS': sparse
+  h.max_depth = D; h.size_before = F.size_before; h.size_after = F.size_after;
+  size_t touched = 0;
+  for (int d = 1; d <= D; d++) touched += (size_t)F.n_level[d];
+  h.n_touched = (int)touched;
+  const size_t need = sizeof(h) + touched * sizeof(uint3);
+  *bytes = need;
+  if (need > cap) return OSL_ERR_INVALID;
+  unsigned char* p = static_cast<unsigned char*>(d_buf);
+  OSL_CUDA(cudaMemcpyAsync(p, &h, sizeof(h), cudaMemcpyHostToDevice, st));
+  size_t done = 0;
+  for (int d = 1; d <= D; d++) {
+    const int n = F.n_level[d];
+    if (n <= 0) continue;
+    k_delta_pack<<<(n + 255) / 256, 256, 0, st>>>(t->d_pool, lv.self + lv.off[d], n,
+                                                  reinterpret_cast<uint3*>(p + sizeof(h)) + done);
+    OSL_LAUNCHED(1);
+    done += (size_t)n;
+  }
+  OSL_CUDA(cudaStreamSynchronize(st));
+  return OSL_OK;
+}
+
+// another rank's changes of the same sharded build (this rank has run its own osl_shard_assign: same sizes)
+osl_status osl_shard_delta_apply(osl_svo* t, const void* d_buf, size_t bytes, void* stream) {
+  if (!t || !d_buf || bytes < sizeof(DeltaHeader)) return OSL_ERR_INVALID;
+  OSL_CUDA(cudaSetDevice(t->device));
+  osl_status rc = osl_poll_results(t, true);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  DeltaHeader h;
+  OSL_CUDA(cudaMemcpyAsync(&h, d_buf, sizeof(h), cudaMemcpyDeviceToHost, st));
+  OSL_CUDA(cudaStreamSynchronize(st));
+  if (h.magic != 0x534C534Fu || h.max_depth != t->tp.D || h.size_after != t->size || h.n_touched < 0 ||
+      bytes != sizeof(h) + (size_t)h.n_touched * sizeof(uint3))
+    return OSL_ERR_INVALID;
+  if (h.n_touched == 0) return OSL_OK;
+  const uint3* tri = reinterpret_cast<const uint3*>(static_cast<const unsigned char*>(d_buf) + sizeof(h));
+  int* d_bad = reinterpret_cast<int*>(t->d_scan_totals + OSL_NCOUNT(OSL_MAXD) + 2);  // scratch word, zero at rest
+  const int blocks = (h.n_touched + 255) / 256;
+  k_delta_init_tiles<<<blocks, 256, 0, st>>>(t->d_pool, tri, h.n_touched, (u32)(h.size_before > 8 ? h.size_before : 8),
+                                             h.size_after, d_bad);
+  k_delta_apply<<<blocks, 256, 0, st>>>(t->d_pool, tri, h.n_touched, h.size_after, d_bad);
+  OSL_LAUNCHED(2);
+  int bad = 0;
+  OSL_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+  OSL_CUDA(cudaStreamSynchronize(st));
+  if (bad) {
+    OSL_CUDA(cudaMemset(d_bad, 0, sizeof(int)));
+    return OSL_ERR_INVALID;
+  }
+  t->upload_count++;
+  return OSL_OK;
+}
+
+// h_starts: grid index of the first voxel of ranks 1 .. n_ranks-1 (the slices' boundaries); the grid is on every rank
+osl_status osl_shard_fixup(osl_svo* t, const float* d_centers4, int n_total, const int* h_starts, int n_bounds, void* stream) {
+  if (!t || !d_centers4 || n_total < 0 || n_bounds < 0 || n_bounds > FIX_MAX || (n_bounds > 0 && !h_starts)) return OSL_ERR_INVALID;
+  OSL_CUDA(cudaSetDevice(t->device));
+  osl_status rc = osl_poll_results(t, true);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  int* d_idx = nullptr;
+  u64* d_keys = nullptr;
+  int starts[FIX_MAX];
+  int nb = 0;
+  for (int i = 0; i < n_bounds; i++)
+    if (h_starts[i] > 0 && h_starts[i] < n_total) starts[nb++] = h_starts[i];  // (an empty slice has no first key)
+  OSL_CUDA(cudaMalloc(&d_idx, sizeof(int) * FIX_MAX));
+  cudaError_t e = cudaMalloc(&d_keys, sizeof(u64) * FIX_MAX);
+  if (e == cudaSuccess && nb) e = cudaMemcpyAsync(d_idx, starts, sizeof(int) * nb, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && nb) {
+    k_keys_of<<<1, FIX_MAX, 0, st>>>(d_centers4, d_idx, nb, t->tp, d_keys);
+    OSL_LAUNCHED(1);
+  }
+  if (e == cudaSuccess) {
+    k_shard_fixup<<<1, FIX_MAX, 0, st>>>(t->d_pool, d_keys, nb, t->tp.D, n_total > 0 ? 1 : 0);
+    OSL_LAUNCHED(1);
+    e = cudaStreamSynchronize(st);
+  }
+  cudaFree(d_idx);
+  cudaFree(d_keys);
+  OSL_CUDA(e);
+  t->upload_count++;
+  return OSL_OK;
+}
+
+}  // extern "C"

@@ -145,6 +145,46 @@ def replicate_delta(svo, src=0, group=None):
     return n
 
 
+def integrate_voxels_sharded(svo, centers4, colors4, group=None):
+    """svoFromVoxelGrid of ONE grid into ONE map by all ranks.  `centers4` / `colors4`: the whole grid
+    as CUDA tensors [n, 4] on every rank, in Morton order without invalid voxels (the voxelisers' output order); every
+    rank's `svo` in the same state.  Rank r analyses the slice [r n / R, (r+1) n / R); ONE all-gather of the per-pass
+    split counters (the north-star's "NCCL only for the per-level node-count prefix") turns local tile ranks into the
+    reference's global node indices (pass = depth - frontier depth, then numeric key, svo.cu:220,284); a second
+    all-gather ships what every rank changed, so that all replicas end up bit-identical with a single-GPU
+    osl_integrate_voxels of the whole grid.  Returns (n_counters, delta bytes of this rank)."""
+    import torch
+    dist = _dist()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = centers4.device
+    n = int(centers4.shape[0])
+    lo, hi = (rank * n) // world, ((rank + 1) * n) // world
+    tot = svo.shard_analyze(centers4, n, lo, hi)
+    t_dev = torch.from_numpy(tot.astype(np.int64)).to(dev)
+    gathered = [torch.empty_like(t_dev) for _ in range(world)]
+    dist.all_gather(gathered, t_dev, group=group)
+    allc = torch.stack(gathered).cpu().numpy()                     # [world, NC]
+    base = allc[:rank].sum(axis=0).astype(np.uint32) if rank else np.zeros(allc.shape[1], dtype=np.uint32)
+    svo.shard_assign(colors4, base, allc.sum(axis=0).astype(np.uint32))
+    # what every rank changed: (index, word0, word1) triples of its level lists
+    mine = svo.shard_delta_bytes()
+    sz = torch.tensor([mine], dtype=torch.int64, device=dev)
+    sizes = [torch.empty_like(sz) for _ in range(world)]
+    dist.all_gather(sizes, sz, group=group)
+    sizes = [int(x.item()) for x in sizes]
+    cap = (max(sizes) + 3) // 4
+    buf = torch.zeros(cap, dtype=torch.int32, device=dev)
+    svo.shard_delta_pack(buf, cap * 4)
+    bufs = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(bufs, buf, group=group)
+    torch.cuda.synchronize(dev)
+    for q in range(world):
+        if q != rank:
+            svo.shard_delta_apply(bufs[q].data_ptr(), sizes[q])
+    svo.shard_fixup(centers4, n, [(q * n) // world for q in range(1, world)])
+    return allc.shape[1], mine
+
+
 def gather_image(bands, tiles, h, w, dst=0, group=None, band=None):
     """bands: this rank's [(row0, rows)], tiles: matching list of uint8 tensors [rows, w, 4]; `band` = the band height
     EVERY rank used with row_bands (None = row_bands' default).  It is passed explicitly, never inferred from the local

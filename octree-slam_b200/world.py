@@ -16,6 +16,9 @@ from . import capi
 from .capi import IDENTITY, Counters, RaycastParams, RaycastStats, _check, _f, _hptr, lib, mat_colmajor
 
 
+OSL_NCOUNT_MAX = 20 + 21 * 21  # OSL_NCOUNT(OSL_MAX_DEPTH): level counters + (frontier, depth) bucket counters
+
+
 def _torch():
     import torch
     return torch
@@ -169,6 +172,35 @@ class SVO:
 
     def delta_apply(self, buf, nbytes, stream=None):
         _check(lib().osl_svo_delta_apply(self._h, buf.data_ptr(), int(nbytes), stream), "osl_svo_delta_apply")
+
+    # ---- one map built by several GPUs (shard.integrate_voxels_sharded) -----------------------------------
+    def shard_analyze(self, centers4, n_total, lo, hi, stream=None):
+        tot = np.zeros(OSL_NCOUNT_MAX, dtype=np.uint32)
+        nc = C.c_int()
+        _check(lib().osl_shard_analyze(self._h, centers4.data_ptr(), int(n_total), int(lo), int(hi), _hptr(tot),
+                                       C.byref(nc), stream), "osl_shard_analyze")
+        return tot[:nc.value].copy()
+
+    def shard_assign(self, colors4, base, totals, stream=None):
+        base = np.ascontiguousarray(base, dtype=np.uint32)
+        totals = np.ascontiguousarray(totals, dtype=np.uint32)
+        _check(lib().osl_shard_assign(self._h, colors4.data_ptr(), _hptr(base), _hptr(totals), stream), "osl_shard_assign")
+
+    def shard_delta_bytes(self):
+        return int(lib().osl_shard_delta_bytes(self._h))
+
+    def shard_delta_pack(self, buf, cap_bytes, stream=None):
+        n = C.c_size_t()
+        _check(lib().osl_shard_delta_pack(self._h, buf.data_ptr(), int(cap_bytes), C.byref(n), stream), "osl_shard_delta_pack")
+        return n.value
+
+    def shard_delta_apply(self, ptr, nbytes, stream=None):
+        _check(lib().osl_shard_delta_apply(self._h, ptr, int(nbytes), stream), "osl_shard_delta_apply")
+
+    def shard_fixup(self, centers4, n_total, starts, stream=None):
+        st = np.ascontiguousarray(starts, dtype=np.int32)
+        _check(lib().osl_shard_fixup(self._h, centers4.data_ptr(), int(n_total), _hptr(st) if st.size else None, int(st.size),
+                                     stream), "osl_shard_fixup")
 
     def join(self, stream=None):
         """order `stream` after every frame enqueued so far (device-side)"""

@@ -89,6 +89,28 @@ def main():
         except P.OslError:
             refused = True
     out["geometry_mismatch_refused"] = refused
+    # 5. ONE map built by all ranks from ONE voxel grid (Morton-range shards, split-count prefix over the ranks): pools
+    #    bit-identical on every rank with the single-GPU build, also for the second observation (Q3 leaf splits, blends
+    #    with non-empty leaves) and for a second, overlapping grid
+    Dm = 9
+    V, T = P.synth.icosphere(4, 0.8, (0.05, -0.02, 0.1))
+    rng = np.random.default_rng(5)
+    colors = rng.uniform(0.1, 1.0, size=(T.shape[0], 4)).astype(np.float32)
+    cen, col = P.meshToVoxelGrid(V, T, colors, (0.0, 0.0, 0.0), 1.0, Dm, device=local)
+    V2, T2 = P.synth.icosphere(3, 0.55, (-0.2, 0.1, 0.0))
+    cen2, col2 = P.meshToVoxelGrid(V2, T2, colors[:T2.shape[0]], (0.0, 0.0, 0.0), 1.0, Dm, device=local)
+    single = P.SVO((0.0, 0.0, 0.0), 1.0, Dm, device=local)
+    sharded = P.SVO((0.0, 0.0, 0.0), 1.0, Dm, device=local)
+    ok_shard, sizes_shard = True, []
+    for c4, k4 in ((cen, col), (cen, col), (cen2, col2), (cen, col)):
+        single.integrate_voxels(c4, k4)
+        S.integrate_voxels_sharded(sharded, c4, k4)
+        a, b = single.pool(), sharded.pool()
+        ok_shard = ok_shard and a.size == b.size and bool(np.array_equal(a, b))
+        sizes_shard.append(int(a.size // 2))
+    out["sharded_build_equal"] = ok_shard
+    out["sharded_build_nodes"] = sizes_shard
+    out["sharded_voxels"] = [int(cen.shape[0]), int(cen2.shape[0])]
     gathered = [None] * world
     dist.all_gather_object(gathered, out)
     if rank == 0:

@@ -1,6 +1,7 @@
 """GPU, world size >= 2 (skipped on a single-GPU box; run with `gpurun --gpus 2`): the multi-GPU decomposition on real
 devices over NCCL -- device-to-device tree replication (full copy and per-frame deltas), every rank's pool equal to
-rank 0's, the gathered row-band image equal to the single-GPU image.  ("nothing asserts the gathered image
+rank 0's, the gathered row-band image equal to the single-GPU image; and ONE map built by all ranks from one voxel grid
+(Morton-range shards, all-gather of the per-pass split counters) bit-identical with the single-GPU build.  ("nothing asserts the gathered image
 equals the 1-GPU image or that replicate_tree round-trips a real SVO".)"""
 import json
 import os
@@ -48,4 +49,6 @@ def test_replicas_and_band_raycast_over_nccl(world):
         assert r["pool_equal_after_local_frame"], r
         assert r["geometry_mismatch_refused"], r
         assert all(0 < b < 4_000_000 for b in r["delta_bytes"]), r  # deltas, not pools
+        assert r["sharded_build_equal"], r  # one map built by all ranks == the single-GPU build, on every rank
+        assert r["sharded_voxels"][0] > 100_000 and r["sharded_build_nodes"][1] > r["sharded_build_nodes"][0]
     assert res[0]["image_equal"] and res[0]["full_copy_nodes"] > 8
