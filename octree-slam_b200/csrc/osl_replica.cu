@@ -205,8 +205,11 @@ __global__ void k_delta_init_tiles(u32* __restrict__ pool, const uint3* __restri
   const u32 tile = e.y & OSL_MASK;
   if (tile < size_before) return;
   if ((tile & 7u) || (long long)tile + 8 > (long long)limit) { atomicAdd(bad, 1); return; }
+  // (only words that are still zero: this rank may already have written a child of its own into the other rank's
+  // tile -- the first key of a slice continues below nodes the lower rank split -- and no initialised value is 0)
 #pragma unroll
-  for (int c = 0; c < 8; c++) pool[2 * (size_t)(tile + c) + 1] = OSL_EMPTY;
+  for (int c = 0; c < 8; c++)
+    if (pool[2 * (size_t)(tile + c) + 1] == 0u) pool[2 * (size_t)(tile + c) + 1] = OSL_EMPTY;
 }
 
 // The nodes on the paths of the slices' first keys are the only ones with touched children in two ranks.  One CTA: thread b
