@@ -1410,7 +1410,9 @@ __device__ __forceinline__ void levels_body(const LevelArgs& A, int bid, int G, 
       dst[cut] = a;
       for (int l = cut; l < D; l++) {
         a = (a < s_nl[l]) ? (int)__ldcg(&lv.fc[lv.off[l] + a]) : s_nl[l + 1];
-        dst[l + 1] = a;
+        // (sharded build: the first key of a slice may head only levels below the cut -- those entries, at the front
+        // of their lists, descend from no node of this rank's cut level; the first CTA takes them along)
+        dst[l + 1] = (tid == 0 && bid == 0) ? 0 : a;
       }
     }
     __syncthreads();
