@@ -846,7 +846,7 @@ __device__ __forceinline__ void assign_block(int vb, int n, const u64* __restric
                                              u32* s_base, const LevelArrays& lv, int mode, u32 size0,
                                              int n_invalid_front, const u32* s_plan, u32 (*s_w)[NC_MAX],
                                              bool carried, u64 k_in, int m_in, int s_in, u32 st_in,
-                                             const u32* s_path, const u32* s_shallow, int slot) {
+                                             const u32* s_path, const u32* s_shallow, int slot, bool shard) {
   const int D = tp.D, NC = OSL_NCOUNT(D);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const u32 lt = lanemask_lt();
@@ -1001,6 +1001,9 @@ __device__ __forceinline__ void assign_block(int vb, int n, const u64* __restric
       lv.digit[o] = (uint8_t)key_digit(k, D, d);
       lv.par[o] = par_idx;
       lv.self[o] = self;
+      // sharded build: a node of this rank may live in a tile the LOWER rank allocates (the slice's first key continues
+      // below nodes that rank splits); its value word must be "empty" before this rank's value fold blends into it
+      if (shard && self >= size0) pool[2 * (size_t)self + 1] = OSL_EMPTY;
       if (d == D) lv.src[lbase + __popc(bal & lt)] = (mode == 2) ? (u32)(n_invalid_front + j) : paymin;
     }
     // the level-d node on this key's path: its own if it heads it, else the last one headed before it
@@ -1218,7 +1221,7 @@ __device__ __forceinline__ void structure_body(const StructArgs& A, int bid, int
   if (!overflow) {
     for (int vb = vb0; vb < vb1; vb++)
       assign_block(vb, n, keys, pay, pool, tp, m8, s8, start, s_base, lv, mode, size0, n_invalid_front, s_plan, s_w,
-                   carried, ck, cm, cs, cst, s_path, s_shallow, cslot);
+                   carried, ck, cm, cs, cst, s_path, s_shallow, cslot, A.shard != 0);
   }
   PROF(22);
 

@@ -123,6 +123,33 @@ def run(name, depth=None, reps=3, rank=0, world=1, device=0, verbose=False):
     same_structure = svo_s.size == nodes
     svo_s.close()
     del cen_s, col_s
+    # ONE map built by ALL ranks from this grid (shard.integrate_voxels_sharded: Morton-range slices, one all-gather of the
+    # per-pass split counters, one of the changes): strong scaling of svoFromVoxelGrid, pool identical to the one above
+    sharded = None
+    if world > 1:
+        import torch.distributed as dist
+        svo_sh = pkg.SVO(center, half, D, reserve_nodes=max(1 << 20, int(2.7 * n)), device=device)
+        times = []
+        for k in range(reps + 1):
+            sync()
+            dist.barrier()
+            t0 = time.perf_counter()
+            pkg.shard.integrate_voxels_sharded(svo_sh, cen, col)
+            sync()
+            dist.barrier()
+            times.append((time.perf_counter() - t0) * 1e3)
+        same = svo_sh.size == nodes
+        if same and n <= 80_000_000:  # (compare on the device: both pools after reps + 1 observations)
+            pa, na, _, _ = svo.view()
+            pb, nb, _, _ = svo_sh.view()
+            ta = torch.as_tensor(pkg.shard._DeviceAlias(pa, 2 * na), device="cuda:%d" % device)
+            tb = torch.as_tensor(pkg.shard._DeviceAlias(pb, 2 * nb), device="cuda:%d" % device)
+            same = bool(torch.equal(ta, tb))
+        sharded = {"ranks": world, "first_ms": times[0], "steady_ms": float(np.median(times[1:])),
+                   "single_gpu_first_ms": ms[0], "single_gpu_steady_ms": steady_ms,
+                   "pool_identical_to_single_gpu_build": bool(same),
+                   "timing": "host wall clock between barriers (device synchronised), all ranks"}
+        svo_sh.close()
     # the reference's renderer only shows nodes whose occupancy counter has saturated (a sample terminates a ray when
     # alpha >= 254, cone_tracing_kernels.cu:115-121; a once-observed surface is transparent): observe the grid 64 times
     for _ in range(max(0, 64 - (reps + 1))):
@@ -173,6 +200,7 @@ def run(name, depth=None, reps=3, rank=0, world=1, device=0, verbose=False):
                                             "k_levels": stage_s[3]},
                                "same_node_count_as_ordered": bool(same_structure)},
             "U": int(cn.n_unique), "peak_GBps": peak},
+        "sharded_build": sharded,
         "raycast": {"res": [W, H], "ranks": world, "ms_this_rank": ray_ms, "rows_this_rank": rows,
                     "mrays_per_s_this_rank": W * rows / (ray_ms / 1e3) / 1e6,
                     "steps_per_ray": (st.steps / float(st.rays)) if st.rays else None, "lit_pixels": lit},
