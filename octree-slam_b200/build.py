@@ -10,7 +10,7 @@ LIB = os.path.join(HERE, "libosl_b200.so")
 HOST = os.path.join(HERE, "host")
 HOST_LIB = os.path.join(HERE, "libosl_host.so")
 HOST_MAIN = os.path.join(HERE, "osl_main")
-SOURCES = ["osl_capi.cu", "osl_integrate.cu", "osl_raycast.cu", "osl_extract.cu", "osl_image.cu", "osl_voxelize.cu", "osl_track.cu", "osl_replica.cu", "osl_voxelize_thin.cu"]
+SOURCES = ["osl_capi.cu", "osl_integrate.cu", "osl_raycast.cu", "osl_extract.cu", "osl_image.cu", "osl_voxelize.cu", "osl_track.cu", "osl_replica.cu", "osl_voxelize_thin.cu", "osl_sort.cu"]
 # the voxeliser is checked bit-exactly against a plain-C restatement: no FMA contraction there
 EXTRA_FLAGS = {"osl_voxelize.cu": ["-fmad=false"], "osl_voxelize_thin.cu": ["-fmad=false"]}
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

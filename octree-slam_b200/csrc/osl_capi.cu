@@ -118,6 +118,7 @@ osl_status osl_svo_create(osl_svo** out, const float center[3], float half_edge,
   t->sort_grid = (occ_sort > 4 ? 4 : occ_sort) * t->num_sms;
   t->structure_grid = (occ_str > 4 ? 4 : occ_str) * t->num_sms;
   t->levels_grid = (occ_lvl > 4 ? 4 : occ_lvl) * t->num_sms;
+  { const int ob = osl_structure_big_occupancy(); t->structure_big_grid = (ob > 2 ? 2 : ob) * t->num_sms; }
   osl_status rc = OSL_OK;
   t->hint_emit = t->hint_level = -1;
   do {
@@ -178,6 +179,7 @@ void osl_svo_destroy(osl_svo* t) {
   cudaFree(t->d_m); cudaFree(t->d_s); cudaFree(t->d_blockcnt);
   cudaFree(t->d_keysC); cudaFree(t->d_payC); cudaFree(t->d_split); cudaFree(t->d_wcache); cudaFree(t->d_blockcnt_tot); cudaFree(t->d_start); cudaFree(t->d_flags);
   cudaFree(t->d_scan_totals); cudaFree(t->d_fs);
+  for (int f = 0; f < OSL_FRONT; f++) osl_sort_big_free(&t->sort_ws[f]);
   cudaFree(t->ex_kA); cudaFree(t->ex_kB); cudaFree(t->ex_nA); cudaFree(t->ex_nB); cudaFree(t->ex_status); cudaFree(t->ex_cnt);
   for (int i = 0; i < OSL_STAGES; i++) {
     cudaFree(t->d_depth_stage[i]); cudaFree(t->d_rgb_stage[i]);

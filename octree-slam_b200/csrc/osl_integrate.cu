@@ -839,6 +839,159 @@ __device__ __forceinline__ void analyze_block(int vb, int n, const u64* __restri
   __syncthreads();
 }
 
+// Phase A for a CTA that owns MANY blocks (voxel grids of millions of keys): the per-block counts only matter as the
+// CTA's total -- phase C recomputes every block's prefix on the way -- so the range is streamed without a single block
+// barrier, AN_R keys per thread, and the AN_R tree walks of a thread advance in lockstep: AN_R independent loads in
+// flight per thread instead of one (the walk is a chain of dependent L2 round trips; at 57 M keys phase A took 1.4 ms
+// of which the chain was most).  Keys that miss the walk cache or head levels above it take the scalar walk.
+#define AN_R 4
+__device__ __forceinline__ void analyze_stream(int j0, int j1, int n, const u64* __restrict__ keys, u32* pay, int mode,
+                                               const u32* pool, const TreeParams& tp, uint8_t* __restrict__ m8,
+                                               uint8_t* __restrict__ s8, u32* __restrict__ start, u32* s_ctot,
+                                               u32* s_cnt, u64* wcache, u32* s_path, u32* s_shallow, int has_prev,
+                                               u64 prev_key) {
+  const int D = tp.D, NC = OSL_NCOUNT(D);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int h = wcache ? walk_cache_depth(D) : 0;
+  for (int c = tid; c < NC; c += AN_THREADS) s_cnt[c] = 0;
+  __syncthreads();
+  for (int base = j0; base < j1; base += AN_THREADS * AN_R) {  // (uniform trip count: the votes below are warp-wide)
+    u64 k[AN_R], e[AN_R];
+    int m[AN_R], s[AN_R];
+    u32 node[AN_R], st[AN_R];
+    unsigned act = 0, slow = 0;
+#pragma unroll
+    for (int r = 0; r < AN_R; r++) {
+      const int j = base + r * AN_THREADS + tid;
+      k[r] = 0; m[r] = D; s[r] = OSL_NONE; st[r] = 0; node[r] = 0; e[r] = ~0ull;
+      if (j < j1) {
+        k[r] = keys[j];
+        if (j > 0 || has_prev) {
+          const u64 x = k[r] ^ (j > 0 ? keys[j - 1] : prev_key);
+          m[r] = x ? (D - 1 - (63 - __clzll((long long)x)) / 3) : D;
+        } else {
+          m[r] = 0;
+        }
+        if (m[r] < D) {
+          if (h && m[r] + 1 >= h) e[r] = __ldcg(&wcache[walk_cache_slot(k[r] >> (3 * (D - h)))]);
+          else slow |= 1u << r;
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < AN_R; r++) {
+      // A prefix that is not in the table yet is missed by EVERY key below it in this batch -- they all looked it up at
+      // the same time (on average 1 000 keys per depth-h prefix for the cfg2 surface).  One of the lanes that miss the
+      // same prefix walks from the root to depth h, enters it, and hands the node to the others.
+      const u64 prefix = k[r] >> (3 * (D - h));
+      const bool cand = m[r] < D && !((slow >> r) & 1u);
+      const bool hit = cand && (e[r] >> 30) == prefix;
+      if (hit) { node[r] = (u32)e[r] & OSL_MASK; act |= 1u << r; }
+      const bool miss = cand && !hit;
+      const u32 missers = __ballot_sync(FULL, miss);
+      if (missers) {
+        int leader = lane;
+        u32 nh = 0xFFFFFFFFu;
+        if (miss) {
+          leader = __ffs(__match_any_sync(missers, prefix)) - 1;
+          if (lane == leader) {
+            u32 nd = (u32)key_digit(k[r], D, 1);
+            int t = 1;
+            for (; t < h; t++) {
+              const u32 w0 = pool[2 * (size_t)nd];
+              if (!(w0 & OSL_FLAG)) break;
+              nd = (w0 & OSL_MASK) + (u32)key_digit(k[r], D, t + 1);
+            }
+            if (t == h) {
+              nh = nd;
+              wcache[walk_cache_slot(prefix)] = (prefix << 30) | (u64)nd;
+            }
+          }
+        }
+        nh = __shfl_sync(FULL, nh, leader);
+        if (miss) {
+          if (nh != 0xFFFFFFFFu) { node[r] = nh; act |= 1u << r; }
+          else slow |= 1u << r;  // (the tree ends above depth h on this path)
+        }
+      }
+    }
+    if (mode != 2) {  // canonical Q7: the lowest input index of the run of equal keys wins
+#pragma unroll
+      for (int r = 0; r < AN_R; r++) {
+        const int j = base + r * AN_THREADS + tid;
+        if (m[r] < D) {
+          u32 pm = pay[j];
+          for (int jj = j + 1; jj < n && keys[jj] == k[r]; jj++) pm = min(pm, pay[jj]);
+          pay[j] = pm;
+        }
+      }
+    }
+    for (int t = h; t <= D && act; t++) {
+      u32 w0[AN_R];
+#pragma unroll
+      for (int r = 0; r < AN_R; r++) {
+        w0[r] = 0;
+        if ((act >> r) & 1u) {
+          if (t == m[r] + 1) st[r] = node[r];
+          if (t < D || (tp.quirks && key_digit(k[r], D, D) == 7)) w0[r] = pool[2 * (size_t)node[r]];
+          else act &= ~(1u << r);  // the whole path exists
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < AN_R; r++) {
+        if ((act >> r) & 1u) {
+          if (!(w0[r] & OSL_FLAG)) { s[r] = t; act &= ~(1u << r); }
+          else if (t == D) act &= ~(1u << r);  // (Q3 leaf that already has children)
+          else node[r] = (w0[r] & OSL_MASK) + (u32)key_digit(k[r], D, t + 1);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < AN_R; r++)
+      if ((slow >> r) & 1u) s[r] = walk_frontier(pool, k[r], D, tp.quirks, m[r], st[r], wcache, s_path, s_shallow, -1);
+#pragma unroll
+    for (int r = 0; r < AN_R; r++) {
+      const int j = base + r * AN_THREADS + tid;
+      const bool uniq = m[r] < D;
+      if (j < j1) {
+        m8[j] = (uint8_t)m[r];
+        s8[j] = (uint8_t)s[r];
+        if (uniq) start[j] = st[r];
+      }
+      // counters: warp-aggregated for the three deepest first-headed levels (nearly every key of a surface), shared
+      // atomics for the rest
+#pragma unroll
+      for (int q = 1; q <= 3; q++) {
+        const u32 bal = __ballot_sync(FULL, uniq && m[r] == D - q);
+        if (lane == 0 && bal && D - q >= 0) atomicAdd(&s_cnt[OSL_CLVL(D, D - q + 1)], (u32)__popc(bal));
+      }
+      if (uniq && m[r] < D - 3) atomicAdd(&s_cnt[OSL_CLVL(D, m[r] + 1)], 1u);
+      const bool sp = uniq && s[r] != OSL_NONE;
+      if (__any_sync(FULL, sp)) {
+        const int lo = (s[r] == D) ? D : max(m[r] + 1, s[r]);
+        const bool cnt = sp && (s[r] == D || lo <= D - 1);
+        const u32 peers = __match_any_sync(FULL, cnt ? (s[r] << 8) | lo : 0xFFFF);
+        if (cnt && lane == __ffs(peers) - 1) atomicAdd(&s_cnt[OSL_CBKT(D, s[r], lo)], (u32)__popc(peers));
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    u32 run = 0;
+    for (int d = 1; d <= D; d++) { run += s_cnt[OSL_CLVL(D, d)]; s_cnt[OSL_CLVL(D, d)] = run; }
+  } else if ((int)threadIdx.x <= D) {
+    const int sd = threadIdx.x;
+    u32 run = 0;
+    for (int d = sd; d <= D; d++) {
+      run += s_cnt[OSL_CBKT(D, sd, d)];
+      s_cnt[OSL_CBKT(D, sd, d)] = (d == D && sd != D) ? 0u : run;
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < NC; c += AN_THREADS) s_ctot[c] += s_cnt[c];
+  __syncthreads();
+}
+
 // s_base: this block's exclusive prefix of every counter (shared memory)
 __device__ __forceinline__ void assign_block(int vb, int n, const u64* __restrict__ keys, const u32* pay, u32* pool,
                                              const TreeParams& tp, const uint8_t* __restrict__ m8,
@@ -846,7 +999,8 @@ __device__ __forceinline__ void assign_block(int vb, int n, const u64* __restric
                                              u32* s_base, const LevelArrays& lv, int mode, u32 size0,
                                              int n_invalid_front, const u32* s_plan, u32 (*s_w)[NC_MAX],
                                              bool carried, u64 k_in, int m_in, int s_in, u32 st_in,
-                                             const u32* s_path, const u32* s_shallow, int slot, bool shard) {
+                                             const u32* s_path, const u32* s_shallow, int slot, bool shard,
+                                             bool preloaded = false, u32 pay_in = 0u) {
   const int D = tp.D, NC = OSL_NCOUNT(D);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const u32 lt = lanemask_lt();
@@ -854,11 +1008,11 @@ __device__ __forceinline__ void assign_block(int vb, int n, const u64* __restric
   u64 k = 0;
   int m = D, s = OSL_NONE;
   u32 node = 0;
-  if (carried) { k = k_in; m = m_in; s = s_in; node = st_in; }  // (a CTA that owns ONE block kept phase A's registers)
-  else if (j < n) { k = keys[j]; m = m8[j]; s = s8[j]; node = start[j]; }
+  if (carried || preloaded) { k = k_in; m = m_in; s = s_in; node = st_in; }  // (a CTA that owns ONE block kept phase A's
+  else if (j < n) { k = keys[j]; m = m8[j]; s = s8[j]; node = start[j]; }    // registers; big inputs: loaded one block ahead)
   const bool unique = m < D;
   // the winning input of the leaf (needed at the last level only): in flight while the levels above are laid out
-  const u32 paymin = (unique && mode != 2 && j < n) ? __ldcg(&pay[j]) : 0u;
+  const u32 paymin = preloaded ? pay_in : (unique && mode != 2 && j < n) ? __ldcg(&pay[j]) : 0u;
 
   // No lane of this warp heads a level <= the warp's smallest m: the per-level collectives start one level above it
   // (one level early so that par_idx / path_tile of the first headed level come out of the loop itself).
@@ -1033,6 +1187,7 @@ struct StructArgs {
 #define STRUCT_MAXG 1024  // most CTAs a structure grid / role may have (s_has)
 #define STRUCT_SMEM ((AN_WARPS + 4) * NC_MAX * 4 + AN_WARPS * 4 + 2 * STRUCT_MAXG + 8 * 512 * 4 + (OSL_MAXD * 32 + 4) * 4)
 
+template <bool BIG>
 __device__ __forceinline__ void structure_body(const StructArgs& A, int bid, int G, unsigned char* s_raw) {
   const u64* __restrict__ keys_sorted = A.keys_sorted; const u64* __restrict__ keys_dense = A.keys_dense;
   u32* pay = A.pay; u32* pool = A.pool; const TreeParams tp = A.tp;
@@ -1074,10 +1229,15 @@ __device__ __forceinline__ void structure_body(const StructArgs& A, int bid, int
   // leave its path -- was measured at 50 M keys: 3.5 ms against 3.2 ms for these independent walks; with 4 CTAs per
   // SM the walk latency is already hidden and the extra serial step only adds two block barriers per block.)
   u64 ck = 0; int cm = D, cs = OSL_NONE, cslot = -1; u32 cst = 0;  // this thread's key state when the CTA owns a single block
-  for (int vb = vb0; vb < vb1; vb++)
-    if (A.shard != 2)
-      analyze_block(vb, n, keys, pay, mode, pool, tp, m8, s8, start, s_ctot, &s_w[0][0], A.wcache, s_path, s_shallow, ck,
-                    cm, cs, cst, cslot, A.shard ? A.has_prev : 0, A.prev_key);
+  if (BIG && vb1 - vb0 >= 2 && A.shard != 2) {
+    analyze_stream(vb0 * AN_THREADS, min(n, vb1 * AN_THREADS), n, keys, pay, mode, pool, tp, m8, s8, start, s_ctot,
+                   &s_w[0][0], A.wcache, s_path, s_shallow, A.shard ? A.has_prev : 0, A.prev_key);
+  } else {
+    for (int vb = vb0; vb < vb1; vb++)
+      if (A.shard != 2)
+        analyze_block(vb, n, keys, pay, mode, pool, tp, m8, s8, start, s_ctot, &s_w[0][0], A.wcache, s_path, s_shallow,
+                      ck, cm, cs, cst, cslot, A.shard ? A.has_prev : 0, A.prev_key);
+  }
   const bool carried = (vb1 - vb0 == 1) && A.shard != 2;
   // publish this CTA's counter vector behind an epoch flag (every CTA publishes, also one without blocks).  Compact
   // form: the D per-level counters always; the (D+1)^2 bucket counters only when a key of this CTA splits a node --
@@ -1219,9 +1379,33 @@ __device__ __forceinline__ void structure_body(const StructArgs& A, int bid, int
   const bool overflow = after > (long long)capacity;
   PROF(21);
   if (!overflow) {
-    for (int vb = vb0; vb < vb1; vb++)
-      assign_block(vb, n, keys, pay, pool, tp, m8, s8, start, s_base, lv, mode, size0, n_invalid_front, s_plan, s_w,
-                   carried, ck, cm, cs, cst, s_path, s_shallow, cslot, A.shard != 0);
+    if (BIG && !carried) {
+      // many blocks per CTA: the next block's inputs are loaded while this one is laid out (each block otherwise starts
+      // with a full DRAM round trip before its first vote)
+      u64 nk = 0; int nm = D, ns = OSL_NONE; u32 nst = 0, npay = 0;
+      {
+        const int j = vb0 * AN_THREADS + tid;
+        if (vb0 < vb1 && j < n) {
+          nk = keys[j]; nm = m8[j]; ns = s8[j]; nst = start[j];
+          if (mode != 2) npay = __ldcg(&pay[j]);
+        }
+      }
+      for (int vb = vb0; vb < vb1; vb++) {
+        const u64 k0 = nk; const int m0 = nm, s0 = ns; const u32 st0 = nst, pay0 = npay;
+        nk = 0; nm = D; ns = OSL_NONE; nst = 0; npay = 0;
+        const int j = (vb + 1) * AN_THREADS + tid;
+        if (vb + 1 < vb1 && j < n) {
+          nk = keys[j]; nm = m8[j]; ns = s8[j]; nst = start[j];
+          if (mode != 2) npay = __ldcg(&pay[j]);
+        }
+        assign_block(vb, n, keys, pay, pool, tp, m8, s8, start, s_base, lv, mode, size0, n_invalid_front, s_plan, s_w,
+                     false, k0, m0, s0, st0, s_path, s_shallow, -1, A.shard != 0, true, pay0);
+      }
+    } else {
+      for (int vb = vb0; vb < vb1; vb++)
+        assign_block(vb, n, keys, pay, pool, tp, m8, s8, start, s_base, lv, mode, size0, n_invalid_front, s_plan, s_w,
+                     carried, ck, cm, cs, cst, s_path, s_shallow, cslot, A.shard != 0);
+    }
   }
   PROF(22);
 
@@ -1272,7 +1456,14 @@ __device__ __forceinline__ void structure_body(const StructArgs& A, int bid, int
 // (3 CTAs per SM: 40 registers, no spills; at 50 M keys the extra resident walks are worth 20 %)
 __global__ void __launch_bounds__(AN_THREADS, 3) k_structure(StructArgs A) {
   extern __shared__ __align__(16) unsigned char s_raw[];
-  structure_body(A, (int)blockIdx.x, (int)gridDim.x, s_raw);
+  structure_body<false>(A, (int)blockIdx.x, (int)gridDim.x, s_raw);
+}
+
+// Voxel grids / clouds of millions of keys: 2 CTAs per SM with 64 registers -- four walks in flight per thread in phase A
+// and the next block's inputs prefetched in phase C hide more latency than a third resident CTA does.
+__global__ void __launch_bounds__(AN_THREADS, 2) k_structure_big(StructArgs A) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  structure_body<true>(A, (int)blockIdx.x, (int)gridDim.x, s_raw);
 }
 
 // ------------------------------------------------------------------------------------------------ k_levels
@@ -1398,17 +1589,30 @@ __device__ __forceinline__ void levels_body(const LevelArgs& A, int bid, int G, 
   // level, ~2 us each and three of them for a 640x480 frame.)  Levels above the cut that are still too wide for the
   // narrow path (huge inputs only) take the grid-barrier route as before.
   int cut = D - 1;
+  const bool big = !A.no_root && s_nl[D] >= (1 << 20);
   {
-    const int roots_max = max(LEVEL_NARROW, 16 * G);
+    // (huge inputs: a deeper cut -- more, smaller subtrees -- so that the shares below can be balanced closely)
+    const int roots_max = max(LEVEL_NARROW, (big ? 256 : 16) * G);
     while (cut >= 1 && s_nl[cut] > roots_max) cut--;
   }
   if (D >= 2 && cut >= 1) {
     int* s_lo = s_pre + (OSL_MAXD + 4);  // [D+2] first / one-past-last entry of this CTA at every level below the cut
     int* s_hi = s_lo + (OSL_MAXD + 2);
     const int n_c = s_nl[cut];
-    const int r0 = (int)(((long long)bid * n_c) / G), r1 = (int)(((long long)(bid + 1) * n_c) / G);
     if (tid < 2) {  // two dependent chains of first-child look-ups, side by side
-      int a = tid == 0 ? r0 : r1;
+      // This CTA's share of the cut level.  Frames: equal node counts.  Huge inputs: equal LEAF counts -- the subtrees of
+      // a surface differ by an order of magnitude in size -- so the share starts at the cut-level ancestor (parent
+      // chain) of leaf bid * n_D / G.
+      const int b = bid + tid;
+      int a = (int)(((long long)b * n_c) / G);
+      if (big) {
+        if (b == 0) a = 0;
+        else if (b >= G) a = n_c;
+        else {
+          a = (int)(((long long)b * s_nl[D]) / G);
+          for (int l = D; l > cut; l--) a = (int)__ldcg(&lv.par[lv.off[l] + a]);
+        }
+      }
       int* dst = tid == 0 ? s_lo : s_hi;
       dst[cut] = a;
       for (int l = cut; l < D; l++) {
@@ -1612,7 +1816,7 @@ __global__ void __launch_bounds__(FRAME_THREADS, 2) k_frame(const __grid_constan
   int b = (int)blockIdx.x;
   if (b < A.gS) {
     span_mark(A.trace, 0, false);
-    structure_body(A.S, b, A.gS, s_raw);
+    structure_body<false>(A.S, b, A.gS, s_raw);
     span_mark(A.trace, 0, true);
     return;
   }
@@ -1716,6 +1920,7 @@ osl_status osl_integrate_init(osl_svo* t) {
   OSL_CUDA(cudaFuncSetAttribute((const void*)k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, EMIT_SMEM));
   OSL_CUDA(cudaFuncSetAttribute((const void*)k_levels, cudaFuncAttributeMaxDynamicSharedMemorySize, LEVEL_SMEM));
   OSL_CUDA(cudaFuncSetAttribute((const void*)k_structure, cudaFuncAttributeMaxDynamicSharedMemorySize, STRUCT_SMEM));
+  OSL_CUDA(cudaFuncSetAttribute((const void*)k_structure_big, cudaFuncAttributeMaxDynamicSharedMemorySize, STRUCT_SMEM));
   OSL_CUDA(cudaFuncSetAttribute((const void*)k_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, FRAME_SMEM));
   OSL_CUDA(cudaFuncSetAttribute((const void*)k_sort_bucket, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM));
   OSL_CUDA(cudaMalloc(&t->d_split, OSL_FRONT * BK_BUCKETS * sizeof(u64)));
@@ -1776,6 +1981,12 @@ int osl_structure_occupancy() {
   if (e != cudaSuccess) { g_osl_last_cuda_error = (int)e; return 0; }
   return occ;
 }
+int osl_structure_big_occupancy() {
+  int occ = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)k_structure_big, AN_THREADS, STRUCT_SMEM);
+  return e == cudaSuccess ? occ : 0;
+}
+
 int osl_levels_occupancy() {
   int occ = 0;
   cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)k_levels, LEVEL_THREADS, LEVEL_SMEM);
@@ -2087,6 +2298,17 @@ osl_status osl_run_integrate(osl_svo* t, EmitParams& ep, const void* colors, cud
   u64* skeys = (passes & 1) ? t->d_keysB[fslot] : t->d_keysA[fslot];
   u32* spay = (passes & 1) ? t->d_payB[fslot] : t->d_payA[fslot];
   if (use_bucket) { skeys = t->d_keysB[fslot]; spay = t->d_payB[fslot]; }
+  static const int no_big_sort = getenv("OSL_NO_BIG_SORT") ? 1 : 0;
+  const bool big_sort = !use_bucket && exp_emit >= (1ll << 19) && !no_big_sort;
+  if (big_sort) {
+    for (int q = 0; q < OSL_FRONT; q++) {  // (all slots at once: an allocation in a later frame would stall the stream)
+      rc = osl_sort_big_reserve(&t->sort_ws[q]);
+      if (rc) return rc;
+    }
+    const int pb = osl_sort_big_passes(3 * D, nullptr);
+    skeys = (pb & 1) ? t->d_keysB[fslot] : t->d_keysA[fslot];
+    spay = (pb & 1) ? t->d_payB[fslot] : t->d_payA[fslot];
+  }
   FrameState* fs = t->d_fs;              // persistent part
   FrameState* fr = t->d_fs + 1 + bslot;  // this frame's result block
   const LevelArrays& lv = t->lv[bslot];
@@ -2226,6 +2448,14 @@ osl_status osl_run_integrate(osl_svo* t, EmitParams& ep, const void* colors, cud
                                                               t->d_payB[fslot], t->d_keysC, t->d_payC, fs,
                                                               t->d_split + fslot * BK_BUCKETS, passes, fslot,
                                                               ep.mode != 2 ? t->d_bkeys[fslot] : nullptr, t->d_bpay[fslot]);
+    } else if (big_sort) {
+      // big inputs: osl_sort.cu (9-bit digits, prefetched tiles, keys only for voxel grids -- Q11: their colour index
+      // is the sorted position)
+      rc = osl_sort_big(&t->sort_ws[fslot], t->d_keysA[fslot], t->d_payA[fslot], t->d_keysB[fslot], t->d_payB[fslot],
+                        &fs->acc_emit[fslot], ep.mode == 2 ? &fs->acc_unsorted[fslot] : nullptr, exp_emit, 3 * D,
+                        ep.mode != 2, piped ? coop_cap : 0, sSo);
+      if (rc) return rc;
+      OSL_LAUNCHED(-1);  // (counted below)
     } else {
       const int grid = grid_for(exp_emit, SORT_TILE, t->sort_grid < coop_cap ? t->sort_grid : coop_cap);
       u64* kA = t->d_keysA[fslot]; u32* pA = t->d_payA[fslot]; u64* kB = t->d_keysB[fslot]; u32* pB = t->d_payB[fslot];
@@ -2250,12 +2480,16 @@ osl_status osl_run_integrate(osl_svo* t, EmitParams& ep, const void* colors, cud
   if (piped && f >= OSL_BACK)  // level lists + result block of this slot were last read by k_levels of frame f - 2
     OSL_CUDA(cudaStreamWaitEvent(sS, t->ring_ev[(f - OSL_BACK) % OSL_RING], 0));
   {
-    const int grid = grid_for(exp_emit, AN_THREADS, t->structure_grid < coop_cap ? t->structure_grid : coop_cap);
+    static const int no_big = getenv("OSL_NO_BIG") ? 1 : 0;
+    const bool big = exp_emit >= (1ll << 20) && t->structure_big_grid > 0 && !no_big;
+    const int gmax = big ? t->structure_big_grid : t->structure_grid;
+    const int grid = grid_for(exp_emit, AN_THREADS, gmax < coop_cap ? gmax : coop_cap);
     StructArgs A = make_struct_args(t, skeys, spay, fs, fr, f, lv, ep.mode, n, fslot);
     void* args[] = {&A};
     // (a plain launch was measured to be no faster than the cooperative one, which guarantees the co-residency the
     // flag exchange relies on)
-    OSL_CUDA(cudaLaunchCooperativeKernel((void*)k_structure, dim3(grid), dim3(AN_THREADS), args, STRUCT_SMEM, sS));
+    OSL_CUDA(cudaLaunchCooperativeKernel(big ? (void*)k_structure_big : (void*)k_structure, dim3(grid), dim3(AN_THREADS),
+                                         args, STRUCT_SMEM, sS));
     OSL_LAUNCHED(1);
     if (timing) OSL_CUDA(cudaEventRecord(t->stage_ev[3], st));
     if (piped) {
@@ -2355,6 +2589,20 @@ osl_status osl_device_sort_pairs(u64* kA, u32* pA, u64* kB, u32* pB, int n, int 
   const int passes = (key_bits + 7) / 8;
   *in_B = passes & 1;
   if (n <= 0) return OSL_OK;
+  if (n >= (1 << 19) && !getenv("OSL_NO_BIG_SORT")) {  // big inputs: osl_sort.cu
+    OslSortWs ws;
+    int* d_n = nullptr;
+    *in_B = osl_sort_big_passes(key_bits, nullptr) & 1;
+    OSL_CUDA(cudaMalloc(&d_n, sizeof(int)));
+    cudaError_t e1 = cudaMemcpyAsync(d_n, &n, sizeof(int), cudaMemcpyHostToDevice, st);
+    osl_status rc = e1 == cudaSuccess ? osl_sort_big(&ws, kA, pA, kB, pB, d_n, nullptr, n, key_bits, true, 0, st) : OSL_ERR_CUDA;
+    cudaError_t e2 = cudaStreamSynchronize(st);
+    osl_sort_big_free(&ws);
+    cudaFree(d_n);
+    if (rc) return rc;
+    OSL_CUDA(e2);
+    return OSL_OK;
+  }
   int dev = 0, sms = 0;
   OSL_CUDA(cudaGetDevice(&dev));
   OSL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

@@ -153,6 +153,17 @@ __device__ __forceinline__ u32 lanemask_lt() {
 }
 
 // ---- host-side internals ------------------------------------------------------------------------------------
+// workspace of the big-input radix sort (osl_sort.cu)
+struct OslSortWs {
+  u32* hist = nullptr;  // [grid + 1][512] per-CTA digit counts / totals
+  int grid = 0;
+};
+int osl_sort_big_passes(int key_bits, int* bits_out);
+osl_status osl_sort_big(OslSortWs* ws, u64* kA, u32* pA, u64* kB, u32* pB, const int* d_n, const int* d_run_flag,
+                        long long n_upper, int key_bits, bool with_pay, int grid_cap, cudaStream_t st);
+void osl_sort_big_free(OslSortWs* ws);
+osl_status osl_sort_big_reserve(OslSortWs* ws);
+
 struct osl_svo {
   int device;
   TreeParams tp;
@@ -221,7 +232,8 @@ struct osl_svo {
   int hint_n_in;
   cudaEvent_t stage_copied[OSL_STAGES], stage_free[OSL_STAGES];
   uint16_t* d_depth_stage[OSL_STAGES]; uint8_t* d_rgb_stage[OSL_STAGES]; size_t stage_cap; unsigned long long stage_seq;
-  int structure_grid, levels_grid;
+  int structure_grid, levels_grid, structure_big_grid;
+  OslSortWs sort_ws[OSL_FRONT];  // one per key-list slot: the sorts of consecutive pipelined frames may overlap
   osl_counters counters;
   // extraction scratch + the frontier of the last call (count / fill call pairs)
   long long *ex_kA, *ex_kB, *ex_res_k; u32 *ex_nA, *ex_nB, *ex_res_n; unsigned long long* ex_status; int* ex_cnt;
@@ -259,6 +271,7 @@ osl_status osl_integrate_init(osl_svo* t);
 osl_status osl_ensure_workspace(osl_svo* t, size_t n);
 int osl_sort_occupancy();  // co-resident k_sort CTAs per SM
 int osl_structure_occupancy();
+int osl_structure_big_occupancy();
 int osl_levels_occupancy();
 osl_status osl_poll_results(osl_svo* t, bool block);
 osl_status osl_grow_pool(osl_svo* t, size_t want_nodes, cudaStream_t st);

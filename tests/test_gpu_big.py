@@ -1,0 +1,79 @@
+"""GPU: inputs of MILLIONS of keys (the cfg2 / cfg5 size class) against the CPU oracle, bit for bit.  From 2^20 expected
+keys on, svoFromVoxelGrid / svoFromPointCloud take the big-input variants of the kernels (k_structure_big: streamed
+phase A with four walks per thread, prefetched phase C; k_levels: leaf-balanced subtree shares; the grid radix sort),
+which the frame-sized tests never reach."""
+import numpy as np
+import pytest
+
+from common import pkg
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def P():
+    return pkg()
+
+
+@pytest.fixture(scope="module")
+def sphere_grid(P):
+    """a sphere voxelised at depth 10: ~1.9 M voxels in Morton order (device tensors)"""
+    D = 10
+    V, T = P.synth.icosphere(5, 0.8, (0.05, -0.02, 0.03))
+    colors = np.random.default_rng(3).uniform(0.0, 1.0, size=(T.shape[0], 4)).astype(np.float32)
+    cen, col = P.meshToVoxelGrid(V, T, colors, (0.0, 0.0, 0.0), 1.0, D)
+    assert cen.shape[0] > (1 << 20)
+    return D, cen, col
+
+
+@pytest.mark.parametrize("order", ["morton", "shuffled", "morton_with_duplicates_and_invalid"])
+def test_big_voxel_grid_matches_oracle(P, sphere_grid, order):
+    import torch
+    D, cen, col = sphere_grid
+    n = cen.shape[0]
+    if order == "shuffled":
+        perm = torch.from_numpy(np.random.default_rng(9).permutation(n)).cuda()
+        cen, col = cen[perm].contiguous(), col[perm].contiguous()
+    elif order == "morton_with_duplicates_and_invalid":
+        cen, col = cen.clone(), col.clone()
+        cen[5000:5003] = cen[5000]          # runs of equal keys (Q11: colours go by sorted position)
+        cen[n // 2] = cen[n // 2 - 1]
+        cen[n - 1] = cen[n - 2]
+        cen[123457, 1] = float("inf")       # an invalid voxel: the grid is no longer gap-free, the sort runs
+    svo = P.SVO((0, 0, 0), 1.0, D, reserve_nodes=int(3.0 * n))
+    ref = orc.OracleSVO((0, 0, 0), 1.0, D)
+    cen_h, col_h = cen.cpu().numpy(), col.cpu().numpy()
+    for k in range(3):  # build, re-observe with Q3 splits, steady state
+        svo.integrate_voxels(cen, col)
+        ref.integrate_voxels(cen_h, col_h)
+        assert svo.size == ref.size, "observation %d" % k
+    a, b = svo.pool(), ref.pool()
+    assert np.array_equal(a[0::2], b[0::2]), "child pointers differ"
+    assert np.array_equal(a, b), "%d values differ" % np.count_nonzero(a[1::2] != b[1::2])
+    # a second, overlapping grid (shifted by a few cells): new sub-trees next to existing ones
+    cen2 = cen.clone()
+    cen2[:, 0] += 7.0 * 2.0 / (1 << D)
+    svo.integrate_voxels(cen2, col)
+    ref.integrate_voxels(cen2.cpu().numpy(), col_h)
+    assert np.array_equal(svo.pool(), ref.pool())
+
+
+def test_big_point_cloud_matches_oracle(P):
+    """2.5 M points with many duplicates per leaf (depth 9): the de-duplicating emit, the grid sort on (key, index)
+    pairs and the canonical lowest-index rule at this size"""
+    rng = np.random.default_rng(11)
+    D, n = 9, 2_500_000
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    pts = (0.75 * d + rng.normal(scale=0.002, size=(n, 3))).astype(np.float32)
+    pts[::100003, 2] = np.nan
+    rgb = rng.integers(0, 256, size=(n, 3)).astype(np.uint8)
+    svo = P.SVO((0, 0, 0), 1.0, D, reserve_nodes=1 << 23)
+    ref = orc.OracleSVO((0, 0, 0), 1.0, D)
+    for k in range(3):
+        svo.integrate_points(pts, rgb)
+        ref.integrate_points(pts, rgb)
+        assert svo.size == ref.size, "observation %d" % k
+    assert svo.counters().n_unique > (1 << 19)
+    assert np.array_equal(svo.pool(), ref.pool())
