@@ -39,7 +39,7 @@ __device__ unsigned long long g_osl_prof[128];
 // 640x480 frame, so ~2048 pixels collapse to ~150 (key, lowest pixel) entries before anything is sorted.  Tiles
 // append their entries to the key list with one atomicAdd; the order of the list is irrelevant because the sort is by
 // key and k_structure takes the MINIMUM payload of every run of equal keys (canonical Q7: lowest pixel wins).
-// Mode 2 (voxel grid, Q11: colour j goes to the j-th smallest key) must keep duplicates and only compacts.
+// Mode 2 (voxel grid, Q11: colour j goes to the j-th smallest key) keeps its duplicates: k_emit_grid below.
 #define EMIT_THREADS 512
 #define EMIT_PPT 4
 #define EMIT_TILE (EMIT_THREADS * EMIT_PPT)
@@ -104,8 +104,7 @@ __device__ __forceinline__ void emit_body(const EmitParams& p, const TreeParams&
       vmask |= (u32)ok << i;
     }
   } else {
-    first = bid * EMIT_TILE + tid * EMIT_PPT;
-    bool bad = false;  // mode 2: an invalid input, or a key smaller than its predecessor's
+    first = bid * EMIT_TILE + tid * EMIT_PPT;  // (mode 1: point clouds; voxel grids have their own kernel, k_emit_grid)
 #pragma unroll
     for (int i = 0; i < EMIT_PPT; i++) {
       const int idx = first + i;
@@ -114,24 +113,8 @@ __device__ __forceinline__ void emit_body(const EmitParams& p, const TreeParams&
       if (idx < p.n) {
         const float* q = p.pts + (size_t)p.stride * idx;
         ok = osl_key(__ldg(q), __ldg(q + 1), __ldg(q + 2), tp, k[i]);
-        bad |= !ok || (i > 0 && k[i] < k[i - 1]);
       }
       vmask |= (u32)ok << i;
-    }
-    if (p.mode == 2) {
-      // Voxel grids usually arrive in Morton order already (the voxeliser and the extraction emit them that way):
-      // keep a dense copy in input order and tell k_sort / k_structure when it is sorted and gap-free, so the whole
-      // radix sort is skipped (svoFromVoxelGrid's own sort, svo.cu:602, is then the identity as well).
-      if (first < p.n && first > 0) {  // the predecessor of this thread's first input
-        const float* q = p.pts + (size_t)p.stride * (first - 1);
-        u64 kp;
-        const bool okp = osl_key(__ldg(q), __ldg(q + 1), __ldg(q + 2), tp, kp);
-        bad |= okp && (vmask & 1u) && k[0] < kp;
-      }
-#pragma unroll
-      for (int i = 0; i < EMIT_PPT; i++)
-        if (first + i < p.n) keys_dense[first + i] = k[i];
-      if (__any_sync(FULL, bad) && lane == 0) atomicOr(reinterpret_cast<u32*>(&fs->acc_unsorted[parity]), 1u);
     }
   }
   __syncthreads();
@@ -222,6 +205,96 @@ k_emit(EmitParams p, TreeParams tp, int vec_ok, u64* __restrict__ keys, u32* __r
 }
 
 // ------------------------------------------------------------------------------------------------ k_sort
+// ------------------------------------------------------------------------------------------------ voxel grids (mode 2)
+// svoFromVoxelGrid's inputs keep their duplicates (Q11: colour j goes to the j-th smallest key), so there is nothing to
+// de-duplicate: the keys go straight to the key list IN INPUT ORDER, 8 bytes per voxel, and the kernel only notes whether
+// the list needs sorting at all (the voxelisers and the extraction emit Morton order; svo.cu:602 is then the identity).
+// An invalid voxel (outside the cube, non-finite) leaves a gap marker; the rare grid that has one is compacted by
+// k_grid_compact / k_grid_copy_back before the sort.  (The first version staged every tile through the shared-memory
+// append of the point-cloud path and wrote a dense copy, the list and a payload nobody reads: 20 bytes per voxel and
+// 0.8 ms for the 57.5 M voxels of cfg2.)
+#define GRID_THREADS 256
+#define GRID_PPT 4
+#define GRID_GAP 0xFFFFFFFFFFFFFFFFull
+__global__ void __launch_bounds__(GRID_THREADS)
+k_emit_grid(const float* __restrict__ pts, int stride, int n, TreeParams tp, u64* __restrict__ keys, FrameState* fs, int parity) {
+  const int lane = threadIdx.x & 31;
+  const long long first = ((long long)blockIdx.x * GRID_THREADS + threadIdx.x) * GRID_PPT;
+  u64 k[GRID_PPT];
+  bool bad = false;
+  int valid = 0;
+  if (first < n) {
+    const bool vec = stride == 4 && (reinterpret_cast<uintptr_t>(pts) & 15) == 0;
+#pragma unroll
+    for (int i = 0; i < GRID_PPT; i++) {
+      k[i] = GRID_GAP;
+      if (first + i < n) {
+        float x, y, z;
+        if (vec) {
+          const float4 q = __ldg(reinterpret_cast<const float4*>(pts) + first + i);
+          x = q.x; y = q.y; z = q.z;
+        } else {
+          const float* q = pts + (size_t)stride * (size_t)(first + i);
+          x = __ldg(q); y = __ldg(q + 1); z = __ldg(q + 2);
+        }
+        u64 kk;
+        const bool ok = osl_key(x, y, z, tp, kk);
+        if (ok) { k[i] = kk; valid++; }
+        bad |= !ok || (i > 0 && k[i - 1] != GRID_GAP && kk < k[i - 1]);
+      }
+    }
+    if (first > 0 && k[0] != GRID_GAP) {  // the predecessor of this thread's first voxel
+      const float* q = pts + (size_t)stride * (size_t)(first - 1);
+      u64 kp;
+      if (osl_key(__ldg(q), __ldg(q + 1), __ldg(q + 2), tp, kp)) bad |= k[0] < kp;
+    }
+    if (first + GRID_PPT <= n && (reinterpret_cast<uintptr_t>(keys) & 15) == 0) {
+      ulonglong2* o = reinterpret_cast<ulonglong2*>(keys + first);
+      o[0] = make_ulonglong2(k[0], k[1]);
+      o[1] = make_ulonglong2(k[2], k[3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < GRID_PPT; i++)
+        if (first + i < n) keys[first + i] = k[i];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) valid += __shfl_xor_sync(FULL, valid, o);
+  __shared__ int s_valid;
+  if (threadIdx.x == 0) s_valid = 0;
+  __syncthreads();
+  if (lane == 0 && valid) atomicAdd(&s_valid, valid);
+  if (__any_sync(FULL, bad) && lane == 0) atomicOr(reinterpret_cast<u32*>(&fs->acc_unsorted[parity]), 1u);
+  __syncthreads();
+  if (threadIdx.x == 0 && s_valid) {
+    atomicAdd(&fs->acc_valid[parity], s_valid);
+    atomicAdd(&fs->acc_emit[parity], s_valid);
+  }
+}
+
+// the rare grid with invalid voxels: drop the gap markers (the order of the list does not matter, it is sorted next)
+__global__ void __launch_bounds__(GRID_THREADS)
+k_grid_compact(const u64* __restrict__ keys, u64* __restrict__ tmp, int n, FrameState* fs, int parity) {
+  if (fs->acc_valid[parity] == n) return;
+  const int lane = threadIdx.x & 31;
+  for (long long j = (long long)blockIdx.x * GRID_THREADS + threadIdx.x; j < (long long)((n + 31) / 32) * 32;
+       j += (long long)gridDim.x * GRID_THREADS) {
+    const u64 k = j < n ? keys[j] : GRID_GAP;
+    const u32 bal = __ballot_sync(FULL, k != GRID_GAP);
+    int base = 0;
+    if (lane == 0 && bal) base = atomicAdd(&fs->acc_tiles[parity], __popc(bal));
+    base = __shfl_sync(FULL, base, 0);
+    if (k != GRID_GAP) tmp[base + __popc(bal & lanemask_lt())] = k;
+  }
+}
+__global__ void __launch_bounds__(GRID_THREADS)
+k_grid_copy_back(u64* __restrict__ keys, const u64* __restrict__ tmp, int n, const FrameState* fs, int parity) {
+  const int v = fs->acc_valid[parity];
+  if (v == n) return;
+  for (long long j = (long long)blockIdx.x * GRID_THREADS + threadIdx.x; j < v; j += (long long)gridDim.x * GRID_THREADS)
+    keys[j] = tmp[j];
+}
+
 #define SORT_THREADS 256
 #define SORT_ITEMS 8
 #define SORT_TILE (SORT_THREADS * SORT_ITEMS)
@@ -273,7 +346,7 @@ __device__ __forceinline__ void sort_rank(SortTile& t, u32* whist, int base, int
 __global__ void __launch_bounds__(SORT_THREADS, 3)
 k_sort(u64* kA, u32* pA, u64* kB, u32* pB, u32* cta_hist, const FrameState* fs, int passes, int parity, int mode) {
   cg::grid_group grid = cg::this_grid();
-  if (mode == 2 && fs->acc_unsorted[parity] == 0) return;  // k_emit's dense copy is already sorted (uniform exit)
+  if (mode == 2 && fs->acc_unsorted[parity] == 0) return;  // the key list is already sorted (uniform exit)
   __shared__ u32 s_hist[256];
   __shared__ u32 s_whist[SORT_WARPS][256];
   __shared__ u32 s_run[256];
@@ -2000,7 +2073,7 @@ static StructArgs make_struct_args(osl_svo* t, const u64* skeys, u32* spay, Fram
                                    unsigned long long f, const LevelArrays& lv, int mode, int n, int fslot) {
   StructArgs A;
   memset(&A, 0, sizeof(A));
-  A.keys_sorted = skeys; A.keys_dense = t->d_keysB[fslot]; A.pay = spay; A.pool = t->d_pool; A.tp = t->tp;
+  A.keys_sorted = skeys; A.keys_dense = t->d_keysA[fslot]; A.pay = spay; A.pool = t->d_pool; A.tp = t->tp;  // (dense: voxel grids in Morton order, the key list as emitted)
   A.fs = fs; A.fr = fr; A.hr = &t->h_ring[f % OSL_RING];  // pinned host memory, device-accessible (UVA)
   A.m8 = t->d_m; A.s8 = t->d_s; A.start = t->d_start; A.ctatot = t->d_blockcnt; A.flags = t->d_flags;
   A.epoch = (u32)(f + 1); A.lv = lv; A.mode = mode; A.capacity = (int)t->cap_nodes; A.n_in = n; A.parity = fslot;
@@ -2425,10 +2498,19 @@ osl_status osl_run_integrate(osl_svo* t, EmitParams& ep, const void* colors, cud
       etiles = (n + EMIT_TILE - 1) / EMIT_TILE;
     }
     const bool file_ranges = use_bucket && ep.mode != 2;
-    k_emit<<<etiles, EMIT_THREADS, EMIT_SMEM, sE>>>(ep, t->tp, vec_ok, t->d_keysA[fslot], t->d_payA[fslot],
-                                                   t->d_keysB[fslot], fs, fslot,
-                                                   file_ranges ? t->d_split + fslot * BK_BUCKETS : nullptr,
-                                                   t->d_bkeys[fslot], t->d_bpay[fslot]);
+    if (ep.mode == 2) {
+      const int per = GRID_THREADS * GRID_PPT;
+      k_emit_grid<<<(n + per - 1) / per, GRID_THREADS, 0, sE>>>(ep.pts, ep.stride, n, t->tp, t->d_keysA[fslot], fs, fslot);
+      const int cg2 = 4 * t->num_sms;
+      k_grid_compact<<<cg2, GRID_THREADS, 0, sE>>>(t->d_keysA[fslot], t->d_keysB[fslot], n, fs, fslot);
+      k_grid_copy_back<<<cg2, GRID_THREADS, 0, sE>>>(t->d_keysA[fslot], t->d_keysB[fslot], n, fs, fslot);
+      OSL_LAUNCHED(2);
+    } else {
+      k_emit<<<etiles, EMIT_THREADS, EMIT_SMEM, sE>>>(ep, t->tp, vec_ok, t->d_keysA[fslot], t->d_payA[fslot],
+                                                     t->d_keysB[fslot], fs, fslot,
+                                                     file_ranges ? t->d_split + fslot * BK_BUCKETS : nullptr,
+                                                     t->d_bkeys[fslot], t->d_bpay[fslot]);
+    }
     OSL_LAUNCHED(1);
     if (piped && ep.mode == 0 && ep.M_dev) {
       // the producer of the pose (a tracker on the caller's stream) rewrites it for the next frame: order the
@@ -2706,19 +2788,20 @@ extern "C" osl_status osl_shard_analyze(osl_svo* t, const float* d_centers4, int
   ep.pts = d_centers4 + 4 * (size_t)lo; ep.stride = 4; ep.n = n; ep.mode = 2;
   t->shard_n = n; t->shard_lo = lo; t->shard_f = f;
   if (n > 0) {
-    const int etiles = (n + EMIT_TILE - 1) / EMIT_TILE;
-    k_emit<<<etiles, EMIT_THREADS, EMIT_SMEM, st>>>(ep, t->tp, 0, t->d_keysA[fslot], t->d_payA[fslot], t->d_keysB[fslot], fs,
-                                                   fslot, nullptr, nullptr, nullptr);
+    const int per = GRID_THREADS * GRID_PPT;
+    k_emit_grid<<<(n + per - 1) / per, GRID_THREADS, 0, st>>>(ep.pts, ep.stride, n, t->tp, t->d_keysA[fslot], fs, fslot);
     OSL_LAUNCHED(1);
   }
   // phase A + counter exchange among this rank's CTAs; the totals come back to the host
   u32* d_tot = t->d_blockcnt_tot;
   {
-    const int grid = grid_for(n, AN_THREADS, t->structure_grid);
+    const bool big = n >= (1 << 20) && t->structure_big_grid > 0;  // (osl_shard_assign takes the same kernel and grid)
+    const int grid = grid_for(n, AN_THREADS, big ? t->structure_big_grid : t->structure_grid);
     StructArgs A = make_struct_args(t, t->d_keysA[fslot], t->d_payA[fslot], fs, t->d_fs + 1 + bslot, f, t->lv[bslot], 2, n, fslot);
     A.shard = 1; A.has_prev = has_prev; A.prev_key = prev_key; A.rank_tot = d_tot; A.src_base = (u32)lo;
     void* args[] = {&A};
-    OSL_CUDA(cudaLaunchCooperativeKernel((void*)k_structure, dim3(grid), dim3(AN_THREADS), args, STRUCT_SMEM, st));
+    OSL_CUDA(cudaLaunchCooperativeKernel(big ? (void*)k_structure_big : (void*)k_structure, dim3(grid), dim3(AN_THREADS), args,
+                                         STRUCT_SMEM, st));
     OSL_LAUNCHED(1);
     t->shard_grid = grid;
   }
@@ -2736,7 +2819,7 @@ extern "C" osl_status osl_shard_analyze(osl_svo* t, const float* d_centers4, int
   }
   if (has_prev && n > 0) {  // the slices must be key ranges in rank order
     u64 first = 0;
-    OSL_CUDA(cudaMemcpy(&first, t->d_keysB[fslot], sizeof(u64), cudaMemcpyDeviceToHost));
+    OSL_CUDA(cudaMemcpy(&first, t->d_keysA[fslot], sizeof(u64), cudaMemcpyDeviceToHost));
     if (first < prev_key) return OSL_ERR_UNSUPPORTED;
   }
   return OSL_OK;
@@ -2770,7 +2853,9 @@ extern "C" osl_status osl_shard_assign(osl_svo* t, const float* d_colors4, const
     StructArgs A = make_struct_args(t, t->d_keysA[fslot], t->d_payA[fslot], fs, t->d_fs + 1 + bslot, f, t->lv[bslot], 2, n, fslot);
     A.shard = 2; A.ext = d_ext; A.src_base = (u32)t->shard_lo;
     void* args[] = {&A};
-    OSL_CUDA(cudaLaunchCooperativeKernel((void*)k_structure, dim3(t->shard_grid), dim3(AN_THREADS), args, STRUCT_SMEM, st));
+    const bool big = n >= (1 << 20) && t->structure_big_grid > 0;
+    OSL_CUDA(cudaLaunchCooperativeKernel(big ? (void*)k_structure_big : (void*)k_structure, dim3(t->shard_grid), dim3(AN_THREADS),
+                                         args, STRUCT_SMEM, st));
     OSL_LAUNCHED(1);
   }
   if (n > 0) {
