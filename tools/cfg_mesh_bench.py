@@ -121,6 +121,13 @@ def run(name, depth=None, reps=3, rank=0, world=1, device=0, verbose=False):
     svo_s.set_stage_timing(False)
     cn_s = svo_s.counters()
     same_structure = svo_s.size == nodes
+    # full-size property check: the node indices / child pointers do not depend on the input order (word0 of every node;
+    # the colours do, by the reference's rule that colour j goes to the j-th smallest key, quirk Q11)
+    same_word0 = False
+    if same_structure:
+        pa, pb = pkg.shard.pool_tensor(svo, nodes), pkg.shard.pool_tensor(svo_s, nodes)
+        same_word0 = bool(torch.equal(pa[0::2], pb[0::2]))
+        del pa, pb
     svo_s.close()
     del cen_s, col_s
     # ONE map built by ALL ranks from this grid (shard.integrate_voxels_sharded: Morton-range slices, one all-gather of the
@@ -198,7 +205,8 @@ def run(name, depth=None, reps=3, rank=0, world=1, device=0, verbose=False):
                                "frac_of_hbm_peak": cn_s.algorithmic_bytes / (float(np.median(ms_s[1:])) / 1e3) / 1e9 / peak,
                                "stage_ms": {"k_emit": stage_s[0], "k_sort": stage_s[1], "k_structure": stage_s[2],
                                             "k_levels": stage_s[3]},
-                               "same_node_count_as_ordered": bool(same_structure)},
+                               "same_node_count_as_ordered": bool(same_structure),
+                               "same_child_pointers_as_ordered": same_word0},
             "U": int(cn.n_unique), "peak_GBps": peak},
         "sharded_build": sharded,
         "raycast": {"res": [W, H], "ranks": world, "ms_this_rank": ray_ms, "rows_this_rank": rows,
