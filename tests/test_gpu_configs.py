@@ -165,3 +165,50 @@ def test_cfg3_1000_frame_orbit_matches_patched_reference(P):
     assert np.all(aa <= ab)
     assert np.array_equal(aa > 127, ab > 127), "the sets of observed nodes differ"
     assert done == n, "the reference integrated only %d of %d frames inside its time budget (pools equal so far)" % (done, n)
+
+
+@pytest.mark.parametrize("D", [10, 12])
+def test_cfg2_voxel_grid_matches_reference(P, D):
+    """SURVEY.md 8d cfg2, the mesh path main.cpp runs once per scene (Scene::voxelizeMeshes -> svoFromVoxelGrid,
+    scene.cpp:64-85, svo.cu:584-640): bunny_tex.obj voxelised on the cfg2 cube, the whole grid (3.6 M voxels at depth 10,
+    57.5 M at depth 12 -- the size bench.py's cfg2 object times) through OUR big-input kernels and through the
+    reference's own svoFromVoxelGrid: depth 10 against the UNMODIFIED reference, depth 12 against ref + 64-bit patch
+    (keys beyond depth 10 are truncated in the original, Q2).  Build + re-observation (Q3 leaf splits) + steady state,
+    in Morton order and shuffled.  The voxeliser emits distinct cells, so nothing races: every word is compared (node 0's
+    value apart, Q6)."""
+    import sys
+    import torch
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import __graft_entry__ as graft
+    if D > 10 and not R.available(True):
+        pytest.skip("libosl_ref64.so not built")
+    path = graft.asset("bunny_tex.obj")
+    if path:
+        V, T = P.synth.load_obj(path)
+    else:  # (assets not staged: a mesh of the same size class)
+        V, T = P.synth.icosphere(4, 1.35)
+    colors = np.random.default_rng(2).uniform(0.0, 1.0, size=(T.shape[0], 4)).astype(np.float32)
+    lo, hi = V.min(axis=0), V.max(axis=0)
+    center = tuple(float(x) for x in (np.float32(0.5) * (lo + hi)))
+    half = float(hi[0])  # scene.cpp:78
+    cen, col = P.meshToVoxelGrid(V, T, colors, center, half, D)
+    n = cen.shape[0]
+    assert n > (1 << 20)
+    for order in ("morton", "shuffled"):
+        if order == "shuffled":
+            perm = torch.from_numpy(np.random.default_rng(4).permutation(n)).cuda()
+            cen, col = cen[perm].contiguous(), col[perm].contiguous()
+            del perm
+        cen_h, col_h = cen.cpu().numpy(), col.cpu().numpy()
+        svo = P.SVO(center, half, D, reserve_nodes=int(3.8 * n))
+        ref = R.RefSVO(center, half, D, patched64=D > 10)
+        for k in range(3):
+            svo.integrate_voxels(cen, col)
+            ref.integrate_voxels(cen_h, col_h)
+            assert svo.size == ref.size, (order, k, svo.size, ref.size)
+        a, b = svo.pool(), ref.pool()
+        assert np.array_equal(a[0::2], b[0::2]), "%s: child pointers differ" % order
+        a[1] = b[1] = 0
+        assert np.array_equal(a, b), "%s: %d values differ" % (order, np.count_nonzero(a != b))
+        svo.close()
+        del ref, a, b
