@@ -57,5 +57,25 @@ s = P.sensor.subsampleDepth(f)
 vm = P.generateVertexMap(f, fx, fy)
 nm = P.sensor.generateNormalMap(vm, w, h)
 A, b_, pairs = P.sensor.computeICPCost2(vm, nm, vm, nm)
-print("sanitize run ok:", a.size, img.shape, keys.size, v.size, pairs)
+# inputs of > 2^20 keys: k_emit_grid, k_sort_big (keys only and with payload), k_structure_big, leaf-balanced k_levels
+rng = np.random.default_rng(1)
+Db = 8
+cells = np.unique(rng.integers(0, 8 ** Db, size=1_400_000))
+ix, iy, iz = cells % 256, (cells // 256) % 256, cells // 65536
+big = np.ones((cells.size, 4), dtype=np.float32)
+big[:, 0], big[:, 1], big[:, 2] = (ix + 0.5) / 128.0 - 1.0, (iy + 0.5) / 128.0 - 1.0, (iz + 0.5) / 128.0 - 1.0
+bigcol = rng.uniform(0, 1, size=big.shape).astype(np.float32)
+g1, g2 = P.SVO((0, 0, 0), 1.0, Db, reserve_nodes=1 << 23), P.SVO((0, 0, 0), 1.0, Db, reserve_nodes=1 << 23)
+gb, gc = torch.from_numpy(big).cuda(), torch.from_numpy(bigcol).cuda()
+order = torch.from_numpy(np.argsort(P.computeKeys(big[:, :3], (0, 0, 0), 1.0, Db), kind="stable")).cuda()
+for _ in range(3):
+    g1.integrate_voxels(gb, gc)                  # shuffled: the sort runs
+    g2.integrate_voxels(gb[order].contiguous(), gc[order].contiguous())  # Morton order: skipped
+assert g1.size == g2.size and np.array_equal(g1.pool()[0::2], g2.pool()[0::2])
+g3 = P.SVO((0, 0, 0), 1.0, Db, reserve_nodes=1 << 23)
+g4 = P.SVO((0, 0, 0), 1.0, Db, reserve_nodes=1 << 23)
+g3.integrate_points(big[:, :3], np.zeros((big.shape[0], 3), dtype=np.uint8))   # big point cloud: pair sort
+g4.integrate_voxels(gb, gc)
+assert g3.size == g4.size and np.array_equal(g3.pool()[0::2], g4.pool()[0::2])
+print("sanitize run ok:", a.size, img.shape, keys.size, v.size, pairs, g1.size)
 PY
