@@ -77,3 +77,22 @@ def test_big_point_cloud_matches_oracle(P):
         assert svo.size == ref.size, "observation %d" % k
     assert svo.counters().n_unique > (1 << 19)
     assert np.array_equal(svo.pool(), ref.pool())
+
+
+def test_big_voxel_grid_pipelined_matches_strict(P, sphere_grid):
+    """the big-input kernels under the frame pipeline (internal streams, cooperative grids capped so that the stages of
+    consecutive calls can be co-resident): same pool as the strict, stream-ordered calls"""
+    import torch
+    D, cen, col = sphere_grid
+    n = cen.shape[0]
+    perm = torch.from_numpy(np.random.default_rng(10).permutation(n)).cuda()
+    cen_s, col_s = cen[perm].contiguous(), col[perm].contiguous()
+    torch.cuda.synchronize()
+    strict = P.SVO((0, 0, 0), 1.0, D, reserve_nodes=int(3.0 * n))
+    piped = P.SVO((0, 0, 0), 1.0, D, reserve_nodes=int(3.0 * n)).set_pipeline(True)
+    for a, b in ((cen, col), (cen_s, col_s), (cen, col), (cen_s, col_s)):
+        strict.integrate_voxels(a, b)
+        piped.integrate_voxels(a, b)
+    piped.sync()
+    assert strict.size == piped.size
+    assert np.array_equal(strict.pool(), piped.pool())
