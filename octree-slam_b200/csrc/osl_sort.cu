@@ -350,18 +350,21 @@ int osl_sort_big_passes(int key_bits, int* bits_out) {
 osl_status osl_sort_big(OslSortWs* ws, u64* kA, u32* pA, u64* kB, u32* pB, const int* d_n, const int* d_run_flag,
                         long long n_upper, int key_bits, bool with_pay, int grid_cap, cudaStream_t st) {
   if (n_upper <= 0) return OSL_OK;
-  static int occ_pay = -1, occ_keys = -1, sms = 0;
-  if (occ_pay < 0) {
-    int dev = 0;
-    OSL_CUDA(cudaGetDevice(&dev));
-    OSL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  // (function attributes and occupancy are per device; one process may drive several)
+  static int s_occ_pay[64], s_occ_keys[64], s_sms[64];
+  static bool s_have[64] = {false};
+  int dev = 0;
+  OSL_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return OSL_ERR_INVALID;
+  if (!s_have[dev]) {
+    OSL_CUDA(cudaDeviceGetAttribute(&s_sms[dev], cudaDevAttrMultiProcessorCount, dev));
     OSL_CUDA(cudaFuncSetAttribute((const void*)k_sort_big<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb_smem<true>()));
     OSL_CUDA(cudaFuncSetAttribute((const void*)k_sort_big<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb_smem<false>()));
-    int a = 0, b = 0;
-    OSL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, (const void*)k_sort_big<true>, SB_THREADS, sb_smem<true>()));
-    OSL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, (const void*)k_sort_big<false>, SB_THREADS, sb_smem<false>()));
-    occ_keys = b; occ_pay = a;
+    OSL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s_occ_pay[dev], (const void*)k_sort_big<true>, SB_THREADS, sb_smem<true>()));
+    OSL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s_occ_keys[dev], (const void*)k_sort_big<false>, SB_THREADS, sb_smem<false>()));
+    s_have[dev] = true;
   }
+  const int occ_pay = s_occ_pay[dev], occ_keys = s_occ_keys[dev], sms = s_sms[dev];
   const int occ = with_pay ? occ_pay : occ_keys;
   if (occ < 1) return OSL_ERR_CUDA;
   long long grid = (long long)occ * sms;
