@@ -3,7 +3,7 @@
 // k_sort (osl_integrate.cu), which stays the sort of mid-sized inputs; what differs at this size:
 //   * 8- or 9-bit digits, whichever needs fewer passes for the key width (36-bit keys of a depth-12 tree: 4 passes);
 //   * keys only for voxel grids -- their colour index is the SORTED POSITION of the key (quirk Q11), no payload moves;
-//   * every CTA owns a contiguous range of 2048-key tiles; the count phase keeps 8 loads per thread in flight, the
+//   * every CTA owns a contiguous range of tiles (4096 keys, or 2048 pairs); the count phase keeps 8 loads per thread in flight, the
 //     scatter phase prefetches the next tile into shared memory (cp.async) while the current one is ranked (warp
 //     match-any), staged in digit order and written out as runs of equal digits;
 //   * the cross-CTA prefix is a column scan of the [CTA][digit] count matrix done once (one CTA per digit, one L2 round
@@ -25,9 +25,12 @@ namespace cg = cooperative_groups;
 namespace {
 
 constexpr int SB_THREADS = 256;
-constexpr int SB_ITEMS = 8;
+// keys per thread and tile: 16 when only keys move (4096-key tiles, 2 CTAs per SM), 8 with a payload (2048, 3 CTAs)
+template <bool PAY> struct SbCfg {
+  static constexpr int ITEMS = PAY ? 8 : 16;
+  static constexpr int TILE = SB_THREADS * ITEMS;
+};
 constexpr int SB_WARPS = SB_THREADS / 32;
-constexpr int SB_TILE = SB_THREADS * SB_ITEMS;
 constexpr int SB_RADIX = 512;   // most digit values (9-bit digits)
 constexpr int SB_MAXG = 768;    // most CTAs (3 rows of the column scan per thread)
 
@@ -41,7 +44,7 @@ struct SortBigArgs {
 
 template <bool PAY>
 constexpr int sb_smem() {
-  return SB_TILE * 8 * 2 + (PAY ? SB_TILE * 4 * 2 : 0) + SB_WARPS * SB_RADIX * 4 + 3 * SB_RADIX * 4 + 64;
+  return SbCfg<PAY>::TILE * 8 * 2 + (PAY ? SbCfg<PAY>::TILE * 4 * 2 : 0) + SB_WARPS * SB_RADIX * 4 + 3 * SB_RADIX * 4 + 64;
 }
 
 // exclusive scan of one value per thread over the block (8 warps); total = sum over the block
@@ -73,6 +76,7 @@ __device__ __forceinline__ void sb_cp16(void* smem, const void* gmem, int bytes)
 
 template <bool PAY>
 __device__ __forceinline__ void sb_prefetch(u64* s_in_k, u32* s_in_p, const u64* kin, const u32* pin, int tile, int n, int tid) {
+  constexpr int SB_TILE = SbCfg<PAY>::TILE;
   const long long g0 = (long long)tile * SB_TILE;
 #pragma unroll
   for (int i = 0; i < SB_TILE * 8 / 16 / SB_THREADS; i++) {  // 4 chunks of two keys
@@ -94,7 +98,8 @@ __device__ __forceinline__ void sb_prefetch(u64* s_in_k, u32* s_in_p, const u64*
 }
 
 template <bool PAY>
-__global__ void __launch_bounds__(SB_THREADS, PAY ? 3 : 4) k_sort_big(SortBigArgs A) {
+__global__ void __launch_bounds__(SB_THREADS, PAY ? 3 : 2) k_sort_big(SortBigArgs A) {
+  constexpr int SB_ITEMS = SbCfg<PAY>::ITEMS, SB_TILE = SbCfg<PAY>::TILE;
   cg::grid_group grid = cg::this_grid();
   if (A.run_flag && *A.run_flag == 0) return;  // (uniform over the grid)
   extern __shared__ __align__(16) unsigned char s_raw[];
@@ -370,7 +375,8 @@ osl_status osl_sort_big(OslSortWs* ws, u64* kA, u32* pA, u64* kB, u32* pB, const
   long long grid = (long long)occ * sms;
   if (grid > SB_MAXG) grid = SB_MAXG;
   if (grid_cap > 0 && grid > grid_cap) grid = grid_cap;
-  const long long tiles = (n_upper + SB_TILE - 1) / SB_TILE;
+  const int tile_keys = with_pay ? SbCfg<true>::TILE : SbCfg<false>::TILE;
+  const long long tiles = (n_upper + tile_keys - 1) / tile_keys;
   if (grid > tiles) grid = tiles;
   if (grid < 1) grid = 1;
   osl_status rr = osl_sort_big_reserve(ws);
