@@ -326,6 +326,9 @@ int osl_frame_result_bytes(void);
 /* Profiling aid: SM-clock checkpoints written by CTA 0 of the last k_emit / k_sort_bucket / k_structure / k_levels
  * launches (indices documented in tools/phase_profile.py).  Synchronizes the device. */
 osl_status osl_debug_profile(unsigned long long* out, int n);
+/* Tracing aid (tools/large_profile.py): SM clock of every CTA of the last big-input structure launch at the start / end
+ * of its analysis phase and the start / end of its assignment phase; out[4][1024]. */
+osl_status osl_debug_cta_profile(unsigned long long* out);
 /* Profiling aid: enable = 1 clears the table and records, for the next k_frame launches of `t` (round-robin over 32
  * slots), the [min start, max end] %globaltimer nanoseconds of each role: 0 structure, 1 values, 2 emit, 3 sort,
  * 4 CTA arrival before the grid dependency wait.  out (may be NULL) receives 32 x 5 x 2 values.  Synchronizes. */

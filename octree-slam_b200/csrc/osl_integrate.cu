@@ -28,6 +28,7 @@ namespace cg = cooperative_groups;
 
 // phase checkpoints (SM clock of CTA 0 / thread 0) for tools/phase_profile.py; one predicated store each
 __device__ unsigned long long g_osl_prof[128];
+__device__ unsigned long long g_osl_ctaprof[4][1024];  // per CTA of the big-input structure stage: SM clock at the start / end of A, start / end of C
 // (`bid` = the CTA's index inside its role: the bodies below run as kernels of their own and as roles of k_frame)
 #define PROF(i) do { if (bid == 0 && threadIdx.x == 0) g_osl_prof[i] = (unsigned long long)clock64(); } while (0)
 
@@ -1293,6 +1294,7 @@ __device__ __forceinline__ void structure_body(const StructArgs& A, int bid, int
   const int vb0 = min(nvb, bid * per), vb1 = min(nvb, vb0 + per);
 
   PROF(16);
+  if (BIG && threadIdx.x == 0 && bid < 1024) g_osl_ctaprof[0][bid] = (unsigned long long)clock64();
   // splitters for k_sort_bucket of a later frame: BK_BUCKETS-quantiles of this frame's sorted keys
   if (bid == G - 1 && tid < BK_BUCKETS - 1 && n >= BK_BUCKETS)
     split_out[tid] = keys[(size_t)(((long long)(tid + 1) * n) / BK_BUCKETS)];
@@ -1327,6 +1329,7 @@ __device__ __forceinline__ void structure_body(const StructArgs& A, int bid, int
     }
   }
   PROF(17);
+  if (BIG && threadIdx.x == 0 && bid < 1024) g_osl_ctaprof[1][bid] = (unsigned long long)clock64();
 
   // wait for every CTA's vector (all CTAs are co-resident: cooperative launch / first roles of k_frame), then sum them:
   // totals for the plan, exclusive prefix for the own range -- one wait, no grid barrier
@@ -1451,6 +1454,7 @@ __device__ __forceinline__ void structure_body(const StructArgs& A, int bid, int
   const long long after = (long long)size0 + 8ll * n_split;
   const bool overflow = after > (long long)capacity;
   PROF(21);
+  if (BIG && threadIdx.x == 0 && bid < 1024) g_osl_ctaprof[2][bid] = (unsigned long long)clock64();
   if (!overflow) {
     if (BIG && !carried) {
       // many blocks per CTA: the next block's inputs are loaded while this one is laid out (each block otherwise starts
@@ -1481,6 +1485,7 @@ __device__ __forceinline__ void structure_body(const StructArgs& A, int bid, int
     }
   }
   PROF(22);
+  if (BIG && threadIdx.x == 0 && bid < 1024) g_osl_ctaprof[3][bid] = (unsigned long long)clock64();
 
   // Book-keeping by the LAST CTA (the grid is sized with a margin, so it usually has no block of its own and this
   // stays off the critical path): the frame's result block, to the device copy k_levels reads and straight to the
@@ -2878,6 +2883,14 @@ extern "C" osl_status osl_shard_assign(osl_svo* t, const float* d_colors4, const
   t->last_piped = 0;
   t->last_fused = 0;
   return osl_poll_results(t, true);
+}
+
+// per-CTA phase clocks of the last k_structure_big launch: out[4][1024]
+extern "C" osl_status osl_debug_cta_profile(unsigned long long* out) {
+  if (!out) return OSL_ERR_INVALID;
+  OSL_CUDA(cudaDeviceSynchronize());
+  OSL_CUDA(cudaMemcpyFromSymbol(out, g_osl_ctaprof, sizeof(unsigned long long) * 4 * 1024));
+  return OSL_OK;
 }
 
 extern "C" osl_status osl_debug_profile(unsigned long long* out, int n) {

@@ -55,6 +55,18 @@ def main():
             print("%s call %d: n=%d unique=%d split=%d nodes=%d | emit %.0f sort %.0f structure %.0f levels %.0f us (sum %.0f)"
                   % (label, k, n, cn.n_unique, cn.n_split, svo.size, st[0], st[1], st[2], st[3], st.sum()))
             if k in (0, reps):
+                cp = (C.c_uint64 * 4096)()
+                lib.osl_debug_cta_profile(cp)
+                a = np.array(cp[:], dtype=np.float64).reshape(4, 1024)
+                live = a[0] > 0
+                if live.any():
+                    q = lambda v: "min %.0f median %.0f max %.0f" % (v.min() / mhz, np.median(v) / mhz, v.max() / mhz)
+                    print("      per CTA (%d): A took %s us | C took %s us" %
+                          (int(live.sum()), q(a[1][live] - a[0][live]), q(a[3][live] - a[2][live])))
+                    idx = np.nonzero(live)[0]
+                    parts = np.array_split(idx[:-1], 12)
+                    print("      by CTA index (12 groups): A " + " ".join("%.0f" % ((a[1][g] - a[0][g]).mean() / mhz) for g in parts) +
+                          " | C " + " ".join("%.0f" % ((a[3][g] - a[2][g]).mean() / mhz) for g in parts))
                 for kern, ph in PHASES:
                     for a, b, name in ph:
                         print("      %-12s %-36s %9.1f us" % (kern, name, (prof[b] - prof[a]) / mhz))
