@@ -53,7 +53,7 @@ __device__ unsigned long long g_osl_ctaprof[4][1024];  // per CTA of the big-inp
 // `split` != NULL: the tile's entries are ALSO filed by splitter range (the OSL_BUCKETS key ranges of k_sort_bucket)
 // into bkeys / bpay[range][OSL_BUCKET_CAP], so that the sort reads its range directly instead of scanning the list.
 __device__ __forceinline__ void emit_body(const EmitParams& p, const TreeParams& tp, int vec_ok, u64* __restrict__ keys,
-                                          u32* __restrict__ pay, u64* __restrict__ keys_dense, FrameState* fs,
+                                          u32* __restrict__ pay, FrameState* fs,
                                           int parity, int bid, unsigned char* s_raw, const u64* __restrict__ split,
                                           u64* __restrict__ bkeys, u32* __restrict__ bpay) {
   u64* s_key = reinterpret_cast<u64*>(s_raw);
@@ -62,10 +62,9 @@ __device__ __forceinline__ void emit_body(const EmitParams& p, const TreeParams&
   u32* s_misc = reinterpret_cast<u32*>(s_raw + EMIT_SLOTS * 12 + EMIT_TILE * 2);
   u32 &s_count = s_misc[0], &s_valid = s_misc[1], &s_base = s_misc[2];
   const int tid = threadIdx.x, lane = tid & 31;
-  const bool dedup = p.mode != 2;
   PROF(0);
 
-  if (dedup) {
+  {
     uint4* k4 = reinterpret_cast<uint4*>(s_key);
     for (int i = tid; i < EMIT_SLOTS / 2; i += EMIT_THREADS) k4[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
     uint4* p4 = reinterpret_cast<uint4*>(s_pay);
@@ -131,19 +130,13 @@ __device__ __forceinline__ void emit_body(const EmitParams& p, const TreeParams&
   for (int i = 0; i < EMIT_PPT; i++) {
     if (!((vmask >> i) & 1u)) continue;
     const u32 src = (u32)(first + i);
-    if (dedup) {
-      if (i > 0 && ((vmask >> (i - 1)) & 1u) && k[i] == k[i - 1]) continue;  // the earlier element already won
-      u32 slot = (u32)((k[i] * 0x9E3779B97F4A7C15ull) >> 52);
-      for (;;) {
-        const u64 prev = atomicCAS(reinterpret_cast<unsigned long long*>(&s_key[slot]), EMIT_EMPTY, k[i]);
-        if (prev == EMIT_EMPTY) s_list[atomicAdd(&s_count, 1u)] = (unsigned short)slot;
-        if (prev == EMIT_EMPTY || prev == k[i]) { atomicMin(&s_pay[slot], src); break; }
-        slot = (slot + 1) & (EMIT_SLOTS - 1);
-      }
-    } else {
-      const u32 pos = atomicAdd(&s_count, 1u);
-      s_key[pos] = k[i];
-      s_pay[pos] = src;
+    if (i > 0 && ((vmask >> (i - 1)) & 1u) && k[i] == k[i - 1]) continue;  // the earlier element already won
+    u32 slot = (u32)((k[i] * 0x9E3779B97F4A7C15ull) >> 52);
+    for (;;) {
+      const u64 prev = atomicCAS(reinterpret_cast<unsigned long long*>(&s_key[slot]), EMIT_EMPTY, k[i]);
+      if (prev == EMIT_EMPTY) s_list[atomicAdd(&s_count, 1u)] = (unsigned short)slot;
+      if (prev == EMIT_EMPTY || prev == k[i]) { atomicMin(&s_pay[slot], src); break; }
+      slot = (slot + 1) & (EMIT_SLOTS - 1);
     }
   }
   __syncthreads();
@@ -156,11 +149,11 @@ __device__ __forceinline__ void emit_body(const EmitParams& p, const TreeParams&
   __syncthreads();
   const u32 base = s_base;
   for (u32 i = tid; i < cnt; i += EMIT_THREADS) {
-    const u32 slot = dedup ? (u32)s_list[i] : i;
+    const u32 slot = (u32)s_list[i];
     keys[base + i] = s_key[slot];
     pay[base + i] = s_pay[slot];
   }
-  if (split && dedup) {
+  if (split) {
     // file the entries by splitter range: range of a key = number of splitters <= key (k_sort_bucket's lo <= k < hi)
     unsigned short* s_pos = reinterpret_cast<unsigned short*>(s_misc + 4);             // [EMIT_TILE] rank inside (tile, range)
     u32* s_bcnt = reinterpret_cast<u32*>(s_pos + EMIT_TILE);                          // [OSL_BUCKETS]
@@ -199,10 +192,10 @@ __device__ __forceinline__ void emit_body(const EmitParams& p, const TreeParams&
 
 __global__ void __launch_bounds__(EMIT_THREADS)
 k_emit(EmitParams p, TreeParams tp, int vec_ok, u64* __restrict__ keys, u32* __restrict__ pay,
-       u64* __restrict__ keys_dense, FrameState* fs, int parity, const u64* __restrict__ split, u64* __restrict__ bkeys,
+       FrameState* fs, int parity, const u64* __restrict__ split, u64* __restrict__ bkeys,
        u32* __restrict__ bpay) {
   extern __shared__ __align__(16) unsigned char s_raw[];
-  emit_body(p, tp, vec_ok, keys, pay, keys_dense, fs, parity, (int)blockIdx.x, s_raw, split, bkeys, bpay);
+  emit_body(p, tp, vec_ok, keys, pay, fs, parity, (int)blockIdx.x, s_raw, split, bkeys, bpay);
 }
 
 // ------------------------------------------------------------------------------------------------ k_sort
@@ -1284,7 +1277,7 @@ __device__ __forceinline__ void structure_body(const StructArgs& A, int bid, int
   const int n_valid = __ldcg(&fs->acc_valid[parity]);
   const int n_invalid_front = n_in - n_valid + (int)A.src_base;
   const int cur = __ldcg(&fs->cur_size);
-  // voxel grids that arrived sorted and gap-free were not sorted again: read k_emit's dense copy
+  // voxel grids that arrived sorted and gap-free were not sorted again: the key list as k_emit_grid wrote it
   const u64* __restrict__ keys = (mode == 2 && __ldcg(&fs->acc_unsorted[parity]) == 0) ? keys_dense : keys_sorted;
   const u32 size0 = (u32)(cur > 8 ? cur : 8);
   const int nvb = (n + AN_THREADS - 1) / AN_THREADS;
@@ -1846,7 +1839,7 @@ struct SortArgs {
   const u64* split; int passes; int parity; const u64* bkeys; const u32* bpay;
 };
 struct EmitArgs {
-  EmitParams p; TreeParams tp; int vec_ok; u64* keys; u32* pay; u64* keys_dense; FrameState* fs; int parity;
+  EmitParams p; TreeParams tp; int vec_ok; u64* keys; u32* pay; FrameState* fs; int parity;
   const u64* split; u64* bkeys; u32* bpay;
 };
 struct FrameArgs {
@@ -1912,7 +1905,7 @@ __global__ void __launch_bounds__(FRAME_THREADS, 2) k_frame(const __grid_constan
       if (threadIdx.x == 0) spin_until_eq(A.E.p.ready, A.E.p.ready_seq);
       __syncthreads();
     }
-    emit_body(A.E.p, A.E.tp, A.E.vec_ok, A.E.keys, A.E.pay, A.E.keys_dense, A.E.fs, A.E.parity, b, s_raw, A.E.split,
+    emit_body(A.E.p, A.E.tp, A.E.vec_ok, A.E.keys, A.E.pay, A.E.fs, A.E.parity, b, s_raw, A.E.split,
               A.E.bkeys, A.E.bpay);
     span_mark(A.trace, 2, true);
     return;
@@ -2243,7 +2236,7 @@ static osl_status fused_launch(osl_svo* t, const osl_svo::FzStage* nw, const Emi
     A.E.p.tiles_y = (ep->h + EMIT_TH - 1) / EMIT_TH;
     A.E.tp = t->tp;
     A.E.vec_ok = ((reinterpret_cast<uintptr_t>(ep->depth) & 7) == 0) && (ep->w % 4 == 0);
-    A.E.keys = t->d_keysA[nw->fslot]; A.E.pay = t->d_payA[nw->fslot]; A.E.keys_dense = t->d_keysB[nw->fslot];
+    A.E.keys = t->d_keysA[nw->fslot]; A.E.pay = t->d_payA[nw->fslot];
     A.E.fs = fs; A.E.parity = nw->fslot;
     A.E.split = t->d_split + nw->fslot * BK_BUCKETS; A.E.bkeys = t->d_bkeys[nw->fslot]; A.E.bpay = t->d_bpay[nw->fslot];
     A.gE = A.E.p.tiles_x * A.E.p.tiles_y;
@@ -2511,8 +2504,7 @@ osl_status osl_run_integrate(osl_svo* t, EmitParams& ep, const void* colors, cud
       k_grid_copy_back<<<cg2, GRID_THREADS, 0, sE>>>(t->d_keysA[fslot], t->d_keysB[fslot], n, fs, fslot);
       OSL_LAUNCHED(2);
     } else {
-      k_emit<<<etiles, EMIT_THREADS, EMIT_SMEM, sE>>>(ep, t->tp, vec_ok, t->d_keysA[fslot], t->d_payA[fslot],
-                                                     t->d_keysB[fslot], fs, fslot,
+      k_emit<<<etiles, EMIT_THREADS, EMIT_SMEM, sE>>>(ep, t->tp, vec_ok, t->d_keysA[fslot], t->d_payA[fslot], fs, fslot,
                                                      file_ranges ? t->d_split + fslot * BK_BUCKETS : nullptr,
                                                      t->d_bkeys[fslot], t->d_bpay[fslot]);
     }
