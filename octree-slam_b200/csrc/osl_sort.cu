@@ -4,8 +4,9 @@
 //   * 8- or 9-bit digits, whichever needs fewer passes for the key width (36-bit keys of a depth-12 tree: 4 passes);
 //   * keys only for voxel grids -- their colour index is the SORTED POSITION of the key (quirk Q11), no payload moves;
 //   * every CTA owns a contiguous range of tiles (4096 keys, or 2048 pairs); the count phase keeps 8 loads per thread in flight, the
-//     scatter phase prefetches the next tile into shared memory (cp.async) while the current one is ranked (warp
-//     match-any), staged in digit order and written out as runs of equal digits;
+//     scatter phase prefetches the next tile into shared memory (one TMA bulk copy, cp.async.bulk + mbarrier, issued by
+//     one thread; cp.async for the ragged last tile) while the current one is ranked, staged in digit order and written
+//     out as runs of equal digits;
 //   * the cross-CTA prefix is a column scan of the [CTA][digit] count matrix done once (one CTA per digit, one L2 round
 //     trip) instead of every CTA summing every other CTA's counts.
 // A chained-scan ("one-sweep") variant with per-tile look-back was built first and measured on B200: with 14 k tiles per
@@ -74,10 +75,45 @@ __device__ __forceinline__ void sb_cp16(void* smem, const void* gmem, int bytes)
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(bytes));
 }
 
+// TMA bulk copy (cp.async.bulk, 1-D) of a whole tile into shared memory: ONE thread issues it, the bytes arrive on an
+// mbarrier the CTA waits on -- instead of 4 (+2) cp.async per thread with their address arithmetic.
+__device__ __forceinline__ unsigned sb_saddr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sb_bar_init(u64* bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(sb_saddr(bar)));
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::);
+}
+__device__ __forceinline__ void sb_bar_expect(u64* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(sb_saddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sb_bulk(void* dst, const void* src, unsigned bytes, u64* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(sb_saddr(dst)),
+               "l"(src), "r"(bytes), "r"(sb_saddr(bar))
+               : "memory");
+}
+__device__ __forceinline__ void sb_bar_wait(u64* bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok)
+                 : "r"(sb_saddr(bar)), "r"(parity)
+                 : "memory");
+  } while (!ok);
+}
+
 template <bool PAY>
-__device__ __forceinline__ void sb_prefetch(u64* s_in_k, u32* s_in_p, const u64* kin, const u32* pin, int tile, int n, int tid) {
+__device__ __forceinline__ void sb_prefetch(u64* s_in_k, u32* s_in_p, const u64* kin, const u32* pin, int tile, int n, int tid,
+                                            bool bulk, u64* bar) {
   constexpr int SB_TILE = SbCfg<PAY>::TILE;
   const long long g0 = (long long)tile * SB_TILE;
+  if (bulk) {  // (a full tile at 16-byte aligned addresses; uniform over the CTA)
+    if (tid == 0) {
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // the CTA's reads of the previous tile come first
+      sb_bar_expect(bar, SB_TILE * 8 + (PAY ? SB_TILE * 4 : 0));
+      sb_bulk(s_in_k, kin + g0, SB_TILE * 8, bar);
+      if (PAY) sb_bulk(s_in_p, pin + g0, SB_TILE * 4, bar);
+    }
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < SB_TILE * 8 / 16 / SB_THREADS; i++) {  // 4 chunks of two keys
     const int c = i * SB_THREADS + tid;
@@ -113,6 +149,10 @@ __global__ void __launch_bounds__(SB_THREADS, PAY ? 3 : 2) k_sort_big(SortBigArg
   u32* s_base = s_run + SB_RADIX;
   u32* s_goff = s_base + SB_RADIX;
   u32* s_wsum = s_goff + SB_RADIX;
+  u64* s_bar = reinterpret_cast<u64*>(s_wsum + 8);  // mbarrier of the tile copies
+  unsigned bar_phase = 0;
+  if (threadIdx.x == 0) sb_bar_init(s_bar);
+  __syncthreads();
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, bid = blockIdx.x;
   const int n = *A.n_ptr;
@@ -215,13 +255,20 @@ __global__ void __launch_bounds__(SB_THREADS, PAY ? 3 : 2) k_sort_big(SortBigArg
     __syncthreads();
 
     // ---- scatter, tile by tile; the next tile is on its way into shared memory while this one is processed
-    if (t0 < t1) sb_prefetch<PAY>(s_in_k, s_in_p, kin, pin, t0, n, tid);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(kin) | reinterpret_cast<uintptr_t>(pin)) & 15) == 0;
+    auto full_tile = [&](int tl) { return aligned && (long long)(tl + 1) * SB_TILE <= n; };
+    if (t0 < t1) sb_prefetch<PAY>(s_in_k, s_in_p, kin, pin, t0, n, tid, full_tile(t0), s_bar);
     for (int tile = t0; tile < t1; tile++) {
       const int base = tile * SB_TILE + warp * (32 * SB_ITEMS);
 #ifdef SB_PROFILE
       d0 = clock64();
 #endif
-      asm volatile("cp.async.wait_group 0;\n" ::);
+      if (full_tile(tile)) {
+        sb_bar_wait(s_bar, bar_phase);
+        bar_phase ^= 1u;
+      } else {
+        asm volatile("cp.async.wait_group 0;\n" ::);
+      }
       __syncthreads();
       SBD(d_wait);
       u64 key[SB_ITEMS];
@@ -233,7 +280,7 @@ __global__ void __launch_bounds__(SB_THREADS, PAY ? 3 : 2) k_sort_big(SortBigArg
       }
       for (int d = lane; d < RB; d += 32) s_whist[warp][d] = 0;
       __syncthreads();
-      if (tile + 1 < t1) sb_prefetch<PAY>(s_in_k, s_in_p, kin, pin, tile + 1, n, tid);
+      if (tile + 1 < t1) sb_prefetch<PAY>(s_in_k, s_in_p, kin, pin, tile + 1, n, tid, full_tile(tile + 1), s_bar);
 #pragma unroll
       for (int i = 0; i < SB_ITEMS; i++) {
         const bool ok = (base + i * 32 + lane) < n;
