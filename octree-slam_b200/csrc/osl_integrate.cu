@@ -2669,17 +2669,21 @@ osl_status osl_device_sort_pairs(u64* kA, u32* pA, u64* kB, u32* pB, int n, int 
   *in_B = passes & 1;
   if (n <= 0) return OSL_OK;
   if (n >= (1 << 19) && !getenv("OSL_NO_BIG_SORT")) {  // big inputs: osl_sort.cu
-    OslSortWs ws;
-    int* d_n = nullptr;
+    // (a process-wide workspace per device, kept for the next call; the sort is stream-ordered and the callers --
+    // the voxelisers -- run one at a time per device)
+    static OslSortWs s_ws[64];
+    static int* s_dn[64] = {nullptr};
+    int dev = 0;
+    OSL_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return OSL_ERR_INVALID;
     *in_B = osl_sort_big_passes(key_bits, nullptr) & 1;
-    OSL_CUDA(cudaMalloc(&d_n, sizeof(int)));
-    cudaError_t e1 = cudaMemcpyAsync(d_n, &n, sizeof(int), cudaMemcpyHostToDevice, st);
-    osl_status rc = e1 == cudaSuccess ? osl_sort_big(&ws, kA, pA, kB, pB, d_n, nullptr, n, key_bits, true, 0, st) : OSL_ERR_CUDA;
-    cudaError_t e2 = cudaStreamSynchronize(st);
-    osl_sort_big_free(&ws);
-    cudaFree(d_n);
+    if (!s_dn[dev]) OSL_CUDA(cudaMalloc(&s_dn[dev], sizeof(int)));
+    static int s_n[64];
+    s_n[dev] = n;
+    OSL_CUDA(cudaMemcpyAsync(s_dn[dev], &s_n[dev], sizeof(int), cudaMemcpyHostToDevice, st));
+    osl_status rc = osl_sort_big(&s_ws[dev], kA, pA, kB, pB, s_dn[dev], nullptr, n, key_bits, true, 0, st);
     if (rc) return rc;
-    OSL_CUDA(e2);
+    OSL_CUDA(cudaStreamSynchronize(st));  // (s_n is pageable: the copy above has been staged by now; callers expect completion)
     return OSL_OK;
   }
   int dev = 0, sms = 0;

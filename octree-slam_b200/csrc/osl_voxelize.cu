@@ -14,9 +14,15 @@
 //   k_vox_setup   per triangle: cell bounding box, dominant axis, number of 1024-column chunks of its projection
 //   k_vox_items   work items (triangle, chunk), appended with one atomicAdd per triangle
 //   k_vox_raster  one warp per item: for every column of the chunk the cell range the triangle's plane crosses, SAT
-//                 on those cells; pass 1 counts hits, pass 2 inserts (cell, triangle) into a global hash set
-//                 (64-bit CAS on the cell code, atomicMin on the triangle index)
-//   k_vox_compact hash table -> (Morton key, triangle) list;  k_sort;  k_vox_finish -> centres + colours
+//                 on those cells; pass 1 counts the hits of every item, pass 2 appends (Morton key, triangle) pairs to
+//                 a list -- one atomicAdd per item reserves its stretch, a shared-memory counter places the hits in it
+//   k_sort_big    the pairs by key (osl_sort.cu)
+//   k_vox_heads / k_vox_scan / k_vox_unique   one entry per cell: lowest triangle of each run of equal keys,
+//                 order-preserving compaction (per-block head counts, their scan, placement)
+//   k_vox_finish  centres + colours
+// (First version: the hits went into a global hash set -- 64-bit CAS on the cell, atomicMin on the triangle -- which was
+// then compacted and sorted.  At 57.5 M voxels the random atomics cost 8.9 ms and the table scan 3.3 ms of 18 ms; a
+// locality-preserving slot function made it 40x worse: neighbouring cells then queue on the same L2 atomic units.)
 // Compiled with -fmad=false: every product and sum below rounds exactly as in the CPU restatement.
 #include "osl_internal.cuh"
 
@@ -137,15 +143,33 @@ __device__ __forceinline__ unsigned long long vx_code(int ix, int iy, int iz) {
   return ((unsigned long long)iz << 42) | ((unsigned long long)iy << 21) | (unsigned long long)ix;
 }
 
-// INSERT = false: count overlapping cells; true: insert them into the hash set
+// leading-1 Morton key of a cell, digit = x + 2y + 4z per level, most significant level first (svo.cu:33-66)
+__device__ __forceinline__ u64 vx_morton(int ix, int iy, int iz, int D) {
+  u64 k = 1;
+  for (int l = D - 1; l >= 0; l--)
+    k = (k << 3) | (u64)(((ix >> l) & 1) | (((iy >> l) & 1) << 1) | (((iz >> l) & 1) << 2));
+  return k;
+}
+
+// INSERT = false: count the cells every item overlaps; true: append them, as (Morton key, triangle) pairs, to the list
 template <bool INSERT>
 __global__ void __launch_bounds__(256)
 k_vox_raster(const float* __restrict__ V, const int* __restrict__ T, const VoxTri* __restrict__ tri,
              const uint2* __restrict__ items, unsigned long long n_items, VoxGrid g, unsigned long long* hits,
-             unsigned long long* table_key, u32* table_tri, unsigned long long table_mask) {
+             u32* item_hits, u64* out_keys, u32* out_tris) {
   const unsigned long long item = (unsigned long long)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   unsigned long long local = 0;
+  __shared__ unsigned s_cur[8];            // INSERT: hits placed so far in this warp's stretch
+  __shared__ unsigned long long s_base[8]; // INSERT: where the stretch starts
+  if (INSERT) {
+    if (lane == 0) {
+      s_cur[threadIdx.x >> 5] = 0;
+      const u32 cnt = item < n_items ? item_hits[item] : 0u;
+      s_base[threadIdx.x >> 5] = cnt ? atomicAdd(hits, (unsigned long long)cnt) : 0ull;
+    }
+    __syncwarp();
+  }
   if (item < n_items) {
     const uint2 it = items[item];
     const int t = (int)it.x;
@@ -190,13 +214,9 @@ k_vox_raster(const float* __restrict__ V, const int* __restrict__ T, const VoxTr
         if (!INSERT) {
           local++;
         } else {
-          const unsigned long long code = vx_code(idx[0], idx[1], idx[2]);
-          unsigned long long slot = (code * 0x9E3779B97F4A7C15ull) >> 20 & table_mask;
-          for (;;) {
-            const unsigned long long prev = atomicCAS(&table_key[slot], VX_EMPTY, code);
-            if (prev == VX_EMPTY || prev == code) { atomicMin(&table_tri[slot], (u32)t); break; }
-            slot = (slot + 1) & table_mask;
-          }
+          const unsigned long long pos = s_base[threadIdx.x >> 5] + atomicAdd(&s_cur[threadIdx.x >> 5], 1u);
+          out_keys[pos] = vx_morton(idx[0], idx[1], idx[2], g.D);
+          out_tris[pos] = (u32)t;
         }
       }
     }
@@ -204,35 +224,98 @@ k_vox_raster(const float* __restrict__ V, const int* __restrict__ T, const VoxTr
   if (!INSERT) {
 #pragma unroll
     for (int o2 = 16; o2 > 0; o2 >>= 1) local += __shfl_xor_sync(0xFFFFFFFFu, local, o2);
+    if (lane == 0 && item < n_items) item_hits[item] = (u32)local;
     if (lane == 0 && local) atomicAdd(hits, local);
   }
 }
 
-// leading-1 Morton key of a cell, digit = x + 2y + 4z per level, most significant level first (svo.cu:33-66)
-__device__ __forceinline__ u64 vx_morton(int ix, int iy, int iz, int D) {
-  u64 k = 1;
-  for (int l = D - 1; l >= 0; l--)
-    k = (k << 3) | (u64)(((ix >> l) & 1) | (((iy >> l) & 1) << 1) | (((iz >> l) & 1) << 2));
-  return k;
+// One entry per cell from the sorted pair list (runs of equal keys = the triangles that overlap the cell).
+#define VX_UBLOCK 2048
+__global__ void __launch_bounds__(256)
+k_vox_heads(const u64* __restrict__ keys, long long n, u32* blockcnt) {
+  const long long b0 = (long long)blockIdx.x * VX_UBLOCK;
+  int c = 0;
+  for (int i = threadIdx.x; i < VX_UBLOCK; i += 256) {
+    const long long j = b0 + i;
+    if (j < n && (j == 0 || keys[j] != keys[j - 1])) c++;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+  __shared__ int s_c[8];
+  if ((threadIdx.x & 31) == 0) s_c[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < 8; w++) t += s_c[w];
+    blockcnt[blockIdx.x] = (u32)t;
+  }
+}
+
+// exclusive scan of the block counts (one CTA; a few ten thousand values), total -> *count
+__global__ void __launch_bounds__(1024)
+k_vox_scan(u32* blockcnt, int nb, unsigned long long* count) {
+  __shared__ unsigned long long s_w[32];
+  __shared__ unsigned long long s_run;
+  if (threadIdx.x == 0) s_run = 0;
+  __syncthreads();
+  for (int b0 = 0; b0 < nb; b0 += 1024) {
+    const int b = b0 + threadIdx.x;
+    const u32 v = b < nb ? blockcnt[b] : 0u;
+    unsigned long long incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if ((threadIdx.x & 31) >= o) incl += t;
+    }
+    if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    unsigned long long woff = 0, tot = 0;
+    for (int w = 0; w < 32; w++) {
+      if (w < (int)(threadIdx.x >> 5)) woff += s_w[w];
+      tot += s_w[w];
+    }
+    const unsigned long long base = s_run;
+    if (b < nb) blockcnt[b] = (u32)(base + woff + incl - v);
+    __syncthreads();
+    if (threadIdx.x == 0) s_run = base + tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *count = s_run;
 }
 
 __global__ void __launch_bounds__(256)
-k_vox_compact(const unsigned long long* __restrict__ table_key, const u32* __restrict__ table_tri,
-              unsigned long long table_size, int D, u64* keys, u32* tris, unsigned long long* count) {
-  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const unsigned long long code = (i < table_size) ? table_key[i] : VX_EMPTY;
-  const bool hit = code != VX_EMPTY;
-  // one atomicAdd per warp, not per voxel (50 M atomics on one address cost 3 ms)
-  const u32 bal = __ballot_sync(0xFFFFFFFFu, hit);
-  if (!bal) return;
-  const int lane = threadIdx.x & 31, leader = __ffs(bal) - 1;
-  unsigned long long base = 0;
-  if (lane == leader) base = atomicAdd(count, (unsigned long long)__popc(bal));
-  base = __shfl_sync(0xFFFFFFFFu, base, leader);
-  if (!hit) return;
-  const unsigned long long pos = base + (unsigned long long)__popc(bal & ((1u << lane) - 1u));
-  keys[pos] = vx_morton((int)(code & 0x1FFFFF), (int)((code >> 21) & 0x1FFFFF), (int)((code >> 42) & 0x1FFFFF), D);
-  tris[pos] = table_tri[i];
+k_vox_unique(const u64* __restrict__ keys, const u32* __restrict__ tris, long long n, const u32* __restrict__ blockbase,
+             u64* okeys, u32* otris) {
+  const long long b0 = (long long)blockIdx.x * VX_UBLOCK;
+  __shared__ int s_w[8];
+  __shared__ int s_run;
+  if (threadIdx.x == 0) s_run = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i0 = 0; i0 < VX_UBLOCK; i0 += 256) {  // (consecutive threads take consecutive entries: the order is kept)
+    const long long j = b0 + i0 + threadIdx.x;
+    const bool head = j < n && (j == 0 || keys[j] != keys[j - 1]);
+    const u32 bal = __ballot_sync(0xFFFFFFFFu, head);
+    if (lane == 0) s_w[warp] = __popc(bal);
+    __syncthreads();
+    int woff = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+      if (w < warp) woff += s_w[w];
+      tot += s_w[w];
+    }
+    if (head) {
+      const u64 k = keys[j];
+      u32 tm = tris[j];
+      for (long long jj = j + 1; jj < n && keys[jj] == k; jj++) tm = min(tm, tris[jj]);  // lowest triangle of the cell
+      const long long pos = (long long)blockbase[blockIdx.x] + s_run + woff + __popc(bal & ((1u << lane) - 1u));
+      okeys[pos] = k;
+      otris[pos] = tm;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_run += tot;
+    __syncthreads();
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -298,8 +381,8 @@ extern "C" osl_status osl_voxelize_mesh(const float* d_vertices, int n_vertices,
   VoxTri* tri = nullptr;
   unsigned long long* d_ctr = nullptr;  // [0] chunks, [1] cursor, [2] hits, [3] unique
   uint2* items = nullptr;
-  unsigned long long* tkey = nullptr;
-  u32* ttri = nullptr;
+  u32* item_hits = nullptr;
+  u32* blockcnt = nullptr;
   u64 *kA = nullptr, *kB = nullptr;
   u32 *pA = nullptr, *pB = nullptr;
   float4 *centers = nullptr, *colors = nullptr;
@@ -308,8 +391,8 @@ extern "C" osl_status osl_voxelize_mesh(const float* d_vertices, int n_vertices,
   osl_status rc = OSL_OK;
   cudaError_t e = cudaSuccess;
   unsigned long long h_ctr[4] = {0, 0, 0, 0};
-  unsigned long long tsize = 0;
   long long n = 0;
+  unsigned long long H = 0;  // hits = (cell, triangle) pairs
 #define VX_CHECK(x) do { e = (x); if (e != cudaSuccess) { g_osl_last_cuda_error = (int)e; rc = (e == cudaErrorMemoryAllocation) ? OSL_ERR_OOM : OSL_ERR_CUDA; goto done; } } while (0)
   VX_CHECK(cudaMallocAsync(&tri, sizeof(VoxTri) * (size_t)n_triangles, st));
   VX_CHECK(cudaMallocAsync(&d_ctr, 4 * sizeof(unsigned long long), st));
@@ -325,40 +408,46 @@ extern "C" osl_status osl_voxelize_mesh(const float* d_vertices, int n_vertices,
   OSL_LAUNCHED(1);
   {
     const unsigned long long blocks = (h_ctr[0] + 7) / 8;
+    VX_CHECK(cudaMallocAsync(&item_hits, sizeof(u32) * h_ctr[0], st));
     k_vox_raster<false><<<(unsigned)blocks, 256, 0, st>>>(d_vertices, d_triangles, tri, items, h_ctr[0], g, d_ctr + 2,
-                                                          nullptr, nullptr, 0);
+                                                          item_hits, nullptr, nullptr);
     OSL_LAUNCHED(1);
     VX_CHECK(cudaMemcpyAsync(h_ctr, d_ctr, sizeof(h_ctr), cudaMemcpyDeviceToHost, st));
     VX_CHECK(cudaStreamSynchronize(st));
-    if (h_ctr[2] == 0) goto done;
-    if (h_ctr[2] >= (1ull << 31)) { rc = OSL_ERR_POOL_OVERFLOW; goto done; }
-    tsize = 1024;
-    while (tsize < 2 * h_ctr[2]) tsize <<= 1;
-    VX_CHECK(cudaMallocAsync(&tkey, tsize * 8, st));
-    VX_CHECK(cudaMallocAsync(&ttri, tsize * 4, st));
-    VX_CHECK(cudaMemsetAsync(tkey, 0xFF, tsize * 8, st));
-    VX_CHECK(cudaMemsetAsync(ttri, 0xFF, tsize * 4, st));
+    H = h_ctr[2];
+    if (H == 0) goto done;
+    if (H >= (1ull << 31)) { rc = OSL_ERR_POOL_OVERFLOW; goto done; }
+    VX_CHECK(cudaMallocAsync(&kA, H * 8, st)); VX_CHECK(cudaMallocAsync(&kB, H * 8, st));
+    VX_CHECK(cudaMallocAsync(&pA, H * 4, st)); VX_CHECK(cudaMallocAsync(&pB, H * 4, st));
+    VX_CHECK(cudaMemsetAsync(d_ctr + 2, 0, sizeof(unsigned long long), st));  // now the append cursor
     k_vox_raster<true><<<(unsigned)blocks, 256, 0, st>>>(d_vertices, d_triangles, tri, items, h_ctr[0], g, d_ctr + 2,
-                                                         tkey, ttri, tsize - 1);
+                                                         item_hits, kA, pA);
     OSL_LAUNCHED(1);
   }
-  VX_CHECK(cudaMallocAsync(&kA, h_ctr[2] * 8, st)); VX_CHECK(cudaMallocAsync(&kB, h_ctr[2] * 8, st));
-  VX_CHECK(cudaMallocAsync(&pA, h_ctr[2] * 4, st)); VX_CHECK(cudaMallocAsync(&pB, h_ctr[2] * 4, st));
-  k_vox_compact<<<(unsigned)((tsize + 255) / 256), 256, 0, st>>>(tkey, ttri, tsize, max_depth, kA, pA, d_ctr + 3);
-  OSL_LAUNCHED(1);
-  VX_CHECK(cudaMemcpyAsync(h_ctr, d_ctr, sizeof(h_ctr), cudaMemcpyDeviceToHost, st));
-  VX_CHECK(cudaStreamSynchronize(st));
-  n = (long long)h_ctr[3];
   {
     int in_B = 0;
-    rc = osl_device_sort_pairs(kA, pA, kB, pB, (int)n, 3 * max_depth + 1, st, &in_B);
+    rc = osl_device_sort_pairs(kA, pA, kB, pB, (int)H, 3 * max_depth, st, &in_B);  // (the leading 1 at bit 3D is common to all keys)
     if (rc) goto done;
     const u64* sk = in_B ? kB : kA;
     const u32* sp = in_B ? pB : pA;
-    VX_CHECK(cudaMalloc(&centers, sizeof(float4) * (size_t)n));
-    VX_CHECK(cudaMalloc(&colors, sizeof(float4) * (size_t)n));
-    if (d_keys_out) VX_CHECK(cudaMalloc(&keys_out, sizeof(long long) * (size_t)n));
-    if (d_tris_out) VX_CHECK(cudaMalloc(&tris_out, sizeof(int) * (size_t)n));
+    u64* uk = in_B ? kA : kB;  // the other pair of buffers takes the one-entry-per-cell list
+    u32* up = in_B ? pA : pB;
+    const int nb = (int)((H + VX_UBLOCK - 1) / VX_UBLOCK);
+    VX_CHECK(cudaMallocAsync(&blockcnt, sizeof(u32) * (size_t)nb, st));
+    k_vox_heads<<<nb, 256, 0, st>>>(sk, (long long)H, blockcnt);
+    k_vox_scan<<<1, 1024, 0, st>>>(blockcnt, nb, d_ctr + 3);
+    k_vox_unique<<<nb, 256, 0, st>>>(sk, sp, (long long)H, blockcnt, uk, up);
+    OSL_LAUNCHED(3);
+    VX_CHECK(cudaMemcpyAsync(h_ctr, d_ctr, sizeof(h_ctr), cudaMemcpyDeviceToHost, st));
+    VX_CHECK(cudaStreamSynchronize(st));
+    n = (long long)h_ctr[3];
+    sk = uk; sp = up;
+    // (stream-ordered pool allocations as well: a fresh gigabyte from cudaMalloc costs milliseconds of page mapping;
+    // the caller releases them with osl_free_device = cudaFree, which hands them back to the pool)
+    VX_CHECK(cudaMallocAsync(&centers, sizeof(float4) * (size_t)n, st));
+    VX_CHECK(cudaMallocAsync(&colors, sizeof(float4) * (size_t)n, st));
+    if (d_keys_out) VX_CHECK(cudaMallocAsync(&keys_out, sizeof(long long) * (size_t)n, st));
+    if (d_tris_out) VX_CHECK(cudaMallocAsync(&tris_out, sizeof(int) * (size_t)n, st));
     k_vox_finish<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sk, sp, n, g, reinterpret_cast<const float4*>(d_tri_colors4),
                                                               centers, colors, keys_out, tris_out);
     OSL_LAUNCHED(1);
@@ -373,7 +462,7 @@ done:
   // scratch comes from the stream-ordered pool (cudaMallocAsync): after the first call these are pool hits, not
   // multi-gigabyte driver allocations; the outputs are plain cudaMalloc (the caller frees them with cudaFree)
   {
-    void* scratch[] = {tri, d_ctr, items, tkey, ttri, kA, kB, pA, pB};
+    void* scratch[] = {tri, d_ctr, items, item_hits, blockcnt, kA, kB, pA, pB};
     for (void* q : scratch)
       if (q) cudaFreeAsync(q, st);
   }
