@@ -20,6 +20,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <cmath>
 #include "osl_internal.cuh"
 
 namespace cg = cooperative_groups;
@@ -210,46 +211,127 @@ k_emit(EmitParams p, TreeParams tp, int vec_ok, u64* __restrict__ keys, u32* __r
 #define GRID_THREADS 256
 #define GRID_PPT 4
 #define GRID_GAP 0xFFFFFFFFFFFFFFFFull
+
+// Closed form of computeKey (svo.cu:33-66) with a certificate.  The reference's key is D rounds of "compare with the
+// centre, step the centre by +-e" in FP32; every centre it compares against is lo + (integer) * cell, computed with at
+// most D roundings of half an ulp(|centre| + half) each.  So when a coordinate is farther than that from every cell
+// boundary, all D comparisons of the float descent agree with exact arithmetic and the cell index is
+// floor((p - lo) / cell).  That quotient is evaluated in FP32 fixed point here (one subtract, one multiply, one
+// conversion per axis); its own rounding errors and the rounding of lo widen the band (make_grid_fast).  Coordinates
+// inside the band (a few per cent of a surface's voxels at depth 12; all of them when the tree is too deep for FP32) are
+// not decided here: their voxel goes on a list and k_grid_fix runs the reference's descent for it.  [The descent costs
+// ~18 instructions per level and voxel and made k_emit_grid issue-bound: 0.75 ms for 57.5 M voxels.]
+struct GridFast {
+  float lox, loy, loz;  // fl(centre - half)
+  float scale;          // 2^sh / cell: one multiply gives the cell index and sh fraction bits in fixed point
+  u32 tol;              // the band around every cell boundary, in 2^-sh cells
+  int sh;               // 31 - D
+  int G;                // cells per axis
+  int on;
+};
+__device__ __forceinline__ bool grid_fast_axis(float p, float lo, const GridFast& gf, int& idx) {
+  const float s = (p - lo) * gf.scale;
+  idx = 0;
+  if (!(s >= 0.0f)) return true;  // below the cube, or NaN (y only, Q1): every comparison of the descent is false
+  if (s >= 2147483648.0f) { idx = gf.G - 1; return true; }  // above the cube (or +INF): every comparison true
+  const u32 u = __float2uint_rz(s);
+  const u32 fr = u & ((1u << gf.sh) - 1u);
+  idx = (int)(u >> gf.sh);
+  return fr > gf.tol && fr < (1u << gf.sh) - gf.tol;
+}
+__device__ __forceinline__ u32 grid_spread10(u32 v) {
+  v &= 0x3FFu;
+  v = (v | (v << 16)) & 0x030000FFu;
+  v = (v | (v << 8)) & 0x0300F00Fu;
+  v = (v | (v << 4)) & 0x030C30C3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+// digit = x + 2y + 4z, most significant level first; sp = the 1024-entry table of grid_spread10 in shared memory (six
+// look-ups instead of six 10-instruction bit spreads per voxel)
+__device__ __forceinline__ u64 grid_morton(int ix, int iy, int iz, const u32* sp) {
+  const u32 lo30 = sp[ix & 1023] | (sp[iy & 1023] << 1) | (sp[iz & 1023] << 2);
+  const u32 hi30 = sp[((u32)ix >> 10) & 1023] | (sp[((u32)iy >> 10) & 1023] << 1) | (sp[((u32)iz >> 10) & 1023] << 2);
+  return ((u64)hi30 << 30) | (u64)lo30;
+}
+// key of one voxel: true = decided (valid or a gap), false = valid but inside the uncertainty band (key provisional)
+__device__ __forceinline__ bool grid_key(float x, float y, float z, const TreeParams& tp, const GridFast& gf, u64& key,
+                                         bool& ok, const u32* sp) {
+  if (!gf.on) { ok = osl_key(x, y, z, tp, key); return true; }
+  ok = isfinite(x) && isfinite(z);
+  int ix, iy, iz;
+  const bool cx = grid_fast_axis(x, gf.lox, gf, ix);
+  const bool cy = grid_fast_axis(y, gf.loy, gf, iy);
+  const bool cz = grid_fast_axis(z, gf.loz, gf, iz);
+  key = grid_morton(ix, iy, iz, sp);
+  return !ok || (cx && cy && cz);
+}
+
 __global__ void __launch_bounds__(GRID_THREADS)
-k_emit_grid(const float* __restrict__ pts, int stride, int n, TreeParams tp, u64* __restrict__ keys, FrameState* fs, int parity) {
+k_emit_grid(const float* __restrict__ pts, int stride, int n, TreeParams tp, GridFast gf, u64* __restrict__ keys,
+            u32* __restrict__ fixlist, FrameState* fs, int parity) {
+  // a warp takes 128 consecutive voxels, lane l the voxels w0 + 32 i + l: loads and stores are contiguous over the warp,
+  // the predecessor of a voxel is the neighbouring lane's (one shuffle), and only the warp's very first voxel needs the
+  // key of a voxel the warp does not own
+  __shared__ u32 s_sp[1024];
+  for (int v = threadIdx.x; v < 1024; v += GRID_THREADS) s_sp[v] = grid_spread10((u32)v);
+  __syncthreads();
   const int lane = threadIdx.x & 31;
-  const long long first = ((long long)blockIdx.x * GRID_THREADS + threadIdx.x) * GRID_PPT;
-  u64 k[GRID_PPT];
+  const long long w0 = ((long long)blockIdx.x * (GRID_THREADS / 32) + (threadIdx.x >> 5)) * (32 * GRID_PPT);
+  const bool vec = stride == 4 && (reinterpret_cast<uintptr_t>(pts) & 15) == 0;
   bool bad = false;
   int valid = 0;
-  if (first < n) {
-    const bool vec = stride == 4 && (reinterpret_cast<uintptr_t>(pts) & 15) == 0;
+  u64 pk = 0;           // key / state of the voxel before this lane's current one
+  bool pok = false, pdec = false;
+  if (lane == 0 && w0 > 0 && w0 < n) {
+    const float* q = pts + (size_t)stride * (size_t)(w0 - 1);
+    pdec = grid_key(__ldg(q), __ldg(q + 1), __ldg(q + 2), tp, gf, pk, pok, s_sp);
+  }
+  u32 und_bal[GRID_PPT];
 #pragma unroll
-    for (int i = 0; i < GRID_PPT; i++) {
-      k[i] = GRID_GAP;
-      if (first + i < n) {
-        float x, y, z;
-        if (vec) {
-          const float4 q = __ldg(reinterpret_cast<const float4*>(pts) + first + i);
-          x = q.x; y = q.y; z = q.z;
-        } else {
-          const float* q = pts + (size_t)stride * (size_t)(first + i);
-          x = __ldg(q); y = __ldg(q + 1); z = __ldg(q + 2);
-        }
-        u64 kk;
-        const bool ok = osl_key(x, y, z, tp, kk);
-        if (ok) { k[i] = kk; valid++; }
-        bad |= !ok || (i > 0 && k[i - 1] != GRID_GAP && kk < k[i - 1]);
+  for (int i = 0; i < GRID_PPT; i++) {
+    const long long idx = w0 + 32 * i + lane;
+    u64 kk = GRID_GAP;
+    bool ok = false, dec = true;
+    if (idx < n) {
+      float x, y, z;
+      if (vec) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(pts) + idx);
+        x = q.x; y = q.y; z = q.z;
+      } else {
+        const float* q = pts + (size_t)stride * (size_t)idx;
+        x = __ldg(q); y = __ldg(q + 1); z = __ldg(q + 2);
       }
+      dec = grid_key(x, y, z, tp, gf, kk, ok, s_sp);
+      if (!ok) { kk = GRID_GAP; bad = true; }  // an invalid voxel: the list has a gap, it is compacted and sorted
+      keys[idx] = kk;
     }
-    if (first > 0 && k[0] != GRID_GAP) {  // the predecessor of this thread's first voxel
-      const float* q = pts + (size_t)stride * (size_t)(first - 1);
-      u64 kp;
-      if (osl_key(__ldg(q), __ldg(q + 1), __ldg(q + 2), tp, kp)) bad |= k[0] < kp;
-    }
-    if (first + GRID_PPT <= n && (reinterpret_cast<uintptr_t>(keys) & 15) == 0) {
-      ulonglong2* o = reinterpret_cast<ulonglong2*>(keys + first);
-      o[0] = make_ulonglong2(k[0], k[1]);
-      o[1] = make_ulonglong2(k[2], k[3]);
-    } else {
+    // the predecessor: the lane below; lane 0 takes lane 31's previous voxel (or the one before the warp's range)
+    const u64 nk = __shfl_up_sync(FULL, kk, 1);
+    const bool nok = __shfl_up_sync(FULL, (int)ok, 1) != 0, ndec = __shfl_up_sync(FULL, (int)dec, 1) != 0;
+    if (lane > 0) { pk = nk; pok = nok; pdec = ndec; }
+    // (order is checked here between decided neighbours only; k_grid_fix_check looks at the others)
+    if (idx < n && ok && dec && pok && pdec && kk < pk) bad = true;
+    valid += ok ? 1 : 0;
+    und_bal[i] = __ballot_sync(FULL, idx < n && ok && !dec);
+    // lane 0's predecessor for the next round: this round's lane 31
+    const u64 lk = __shfl_sync(FULL, kk, 31);
+    const bool lok = __shfl_sync(FULL, (int)ok, 31) != 0, ldec = __shfl_sync(FULL, (int)dec, 31) != 0;
+    if (lane == 0) { pk = lk; pok = lok; pdec = ldec; }
+  }
+  {  // undecided voxels -> the list (one atomicAdd per warp)
+    int tot = 0;
 #pragma unroll
-      for (int i = 0; i < GRID_PPT; i++)
-        if (first + i < n) keys[first + i] = k[i];
+    for (int i = 0; i < GRID_PPT; i++) tot += __popc(und_bal[i]);
+    if (tot) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&fs->acc_bucket[parity][0], tot);
+      base = __shfl_sync(FULL, base, 0);
+#pragma unroll
+      for (int i = 0; i < GRID_PPT; i++) {
+        if ((und_bal[i] >> lane) & 1u) fixlist[base + __popc(und_bal[i] & lanemask_lt())] = (u32)(w0 + 32 * i + lane);
+        base += __popc(und_bal[i]);
+      }
     }
   }
 #pragma unroll
@@ -264,6 +346,31 @@ k_emit_grid(const float* __restrict__ pts, int stride, int n, TreeParams tp, u64
     atomicAdd(&fs->acc_valid[parity], s_valid);
     atomicAdd(&fs->acc_emit[parity], s_valid);
   }
+}
+
+// the voxels k_emit_grid could not decide: the reference's float descent, then the order against both neighbours
+__global__ void __launch_bounds__(GRID_THREADS)
+k_grid_fix(const float* __restrict__ pts, int stride, TreeParams tp, u64* __restrict__ keys, const u32* __restrict__ fixlist,
+           const FrameState* fs, int parity) {
+  const int m = fs->acc_bucket[parity][0];
+  for (int i = blockIdx.x * GRID_THREADS + threadIdx.x; i < m; i += gridDim.x * GRID_THREADS) {
+    const u32 j = fixlist[i];
+    const float* q = pts + (size_t)stride * (size_t)j;
+    u64 kk;
+    if (osl_key(__ldg(q), __ldg(q + 1), __ldg(q + 2), tp, kk)) keys[j] = kk;
+  }
+}
+__global__ void __launch_bounds__(GRID_THREADS)
+k_grid_fix_check(const u64* __restrict__ keys, int n, const u32* __restrict__ fixlist, FrameState* fs, int parity) {
+  const int m = fs->acc_bucket[parity][0];
+  bool bad = false;
+  for (int i = blockIdx.x * GRID_THREADS + threadIdx.x; i < m; i += gridDim.x * GRID_THREADS) {
+    const u32 j = fixlist[i];
+    const u64 k = keys[j];
+    if (j > 0) { const u64 kp = keys[j - 1]; bad |= kp != GRID_GAP && k < kp; }
+    if ((int)j + 1 < n) { const u64 kn = keys[j + 1]; bad |= kn != GRID_GAP && kn < k; }
+  }
+  if (bad) atomicOr(reinterpret_cast<u32*>(&fs->acc_unsorted[parity]), 1u);
 }
 
 // the rare grid with invalid voxels: drop the gap markers (the order of the list does not matter, it is sorted next)
@@ -2270,6 +2377,29 @@ osl_status osl_fused_flush(osl_svo* t) {
   return OSL_OK;
 }
 
+// parameters of the certified closed-form key (k_emit_grid); off when FP32 leaves no margin inside a cell
+static GridFast make_grid_fast(const TreeParams& tp) {
+  GridFast g;
+  memset(&g, 0, sizeof(g));
+  static const int no_fast = getenv("OSL_NO_FAST_KEYS") ? 1 : 0;
+  const double half = (double)tp.half;
+  if (no_fast || !(half > 0.0) || tp.D < 1 || tp.D > 20) return g;
+  g.G = 1 << tp.D;
+  g.sh = 31 - tp.D;
+  const double inv_cs = (double)g.G / (2.0 * half);
+  g.lox = (float)((double)tp.cx - half); g.loy = (float)((double)tp.cy - half); g.loz = (float)((double)tp.cz - half);
+  g.scale = (float)(inv_cs * ldexp(1.0, g.sh));
+  const double M = fmax(fmax(fabs((double)tp.cx), fabs((double)tp.cy)), fabs((double)tp.cz)) + half;
+  const double ulpM = ldexp(1.0, ilogb(M) + 1 - 23);  // ulp of the binade above M
+  // band, in cells: the descent's D <= 20 roundings of half an ulp (16 ulp taken), the rounding of lo (half an ulp), the
+  // three roundings of (p - lo) * scale (3 * 2^-24 relative to a quotient of at most G: G * 2^-22 taken)
+  const double tol = 16.5 * ulpM * inv_cs + (double)g.G * ldexp(1.0, -22);
+  if (!(tol < 0.25)) return g;
+  g.tol = (u32)ceil(tol * ldexp(1.0, g.sh)) + 1u;
+  g.on = 1;
+  return g;
+}
+
 osl_status osl_run_integrate(osl_svo* t, EmitParams& ep, const void* colors, cudaStream_t st, const HostFrame* host) {
   const int n = ep.n;
   const int D = t->tp.D;
@@ -2498,8 +2628,15 @@ osl_status osl_run_integrate(osl_svo* t, EmitParams& ep, const void* colors, cud
     const bool file_ranges = use_bucket && ep.mode != 2;
     if (ep.mode == 2) {
       const int per = GRID_THREADS * GRID_PPT;
-      k_emit_grid<<<(n + per - 1) / per, GRID_THREADS, 0, sE>>>(ep.pts, ep.stride, n, t->tp, t->d_keysA[fslot], fs, fslot);
+      const GridFast gf = make_grid_fast(t->tp);
       const int cg2 = 4 * t->num_sms;
+      k_emit_grid<<<(n + per - 1) / per, GRID_THREADS, 0, sE>>>(ep.pts, ep.stride, n, t->tp, gf, t->d_keysA[fslot],
+                                                                t->d_payA[fslot], fs, fslot);
+      if (gf.on) {  // (the undecided voxels; the list lives in the payload buffer, which voxel grids do not use)
+        k_grid_fix<<<cg2, GRID_THREADS, 0, sE>>>(ep.pts, ep.stride, t->tp, t->d_keysA[fslot], t->d_payA[fslot], fs, fslot);
+        k_grid_fix_check<<<cg2, GRID_THREADS, 0, sE>>>(t->d_keysA[fslot], n, t->d_payA[fslot], fs, fslot);
+        OSL_LAUNCHED(2);
+      }
       k_grid_compact<<<cg2, GRID_THREADS, 0, sE>>>(t->d_keysA[fslot], t->d_keysB[fslot], n, fs, fslot);
       k_grid_copy_back<<<cg2, GRID_THREADS, 0, sE>>>(t->d_keysA[fslot], t->d_keysB[fslot], n, fs, fslot);
       OSL_LAUNCHED(2);
@@ -2790,7 +2927,10 @@ extern "C" osl_status osl_shard_analyze(osl_svo* t, const float* d_centers4, int
   t->shard_n = n; t->shard_lo = lo; t->shard_f = f;
   if (n > 0) {
     const int per = GRID_THREADS * GRID_PPT;
-    k_emit_grid<<<(n + per - 1) / per, GRID_THREADS, 0, st>>>(ep.pts, ep.stride, n, t->tp, t->d_keysA[fslot], fs, fslot);
+    GridFast gf0;
+    memset(&gf0, 0, sizeof(gf0));  // (slices of a sharded build: the plain descent)
+    k_emit_grid<<<(n + per - 1) / per, GRID_THREADS, 0, st>>>(ep.pts, ep.stride, n, t->tp, gf0, t->d_keysA[fslot],
+                                                              t->d_payA[fslot], fs, fslot);
     OSL_LAUNCHED(1);
   }
   // phase A + counter exchange among this rank's CTAs; the totals come back to the host

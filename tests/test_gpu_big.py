@@ -96,3 +96,56 @@ def test_big_voxel_grid_pipelined_matches_strict(P, sphere_grid):
     piped.sync()
     assert strict.size == piped.size
     assert np.array_equal(strict.pool(), piped.pool())
+
+
+@pytest.mark.parametrize("center,half,D", [((0.0, 0.0, 0.0), 1.0, 12), ((0.0123, -0.0456, 0.789), 1.3493741, 12),
+                                           ((3.3, -7.7, 12.1), 0.7, 9), ((0.0, 0.0, 0.0), 655.36, 16),
+                                           ((1000.5, 2000.25, -3000.125), 10.0, 20), ((0.1, 0.2, 0.3), 5.0, 3)])
+def test_voxel_keys_on_cell_boundaries(P, center, half, D):
+    """k_emit_grid decides most keys in closed form and certifies them; coordinates within a few ulp of a cell boundary go
+    to the reference's float descent instead.  Adversarial inputs: coordinates exactly ON boundaries of every level, one
+    ulp to either side, a few ulp away, NaN / INF in y (Q1: still a valid key), INF in x (invalid), points outside the
+    cube -- through svoFromVoxelGrid on the GPU and in the oracle (which only knows the descent): equal pools."""
+    rng = np.random.default_rng(D * 7 + 1)
+    n = 120_000
+    c = np.asarray(center, dtype=np.float64)
+    lo = c - half
+    pts = np.empty((n, 3), dtype=np.float32)
+    for a in range(3):
+        lvl = rng.integers(1, D + 1, size=n)
+        k = (rng.random(n) * (2.0 ** lvl)).astype(np.int64)
+        b = (lo[a] + k * (2.0 * half) / (2.0 ** lvl)).astype(np.float32)      # a cell boundary of level lvl, as a float
+        kind = rng.integers(0, 8, size=n)
+        up = np.nextafter(b, np.float32(np.inf))
+        dn = np.nextafter(b, np.float32(-np.inf))
+        far = b
+        for _ in range(5):
+            far = np.nextafter(far, np.float32(np.inf))
+        rnd = (lo[a] + rng.random(n) * 2.0 * half).astype(np.float32)
+        outside = (lo[a] + (rng.random(n) * 4.0 - 1.0) * 2.0 * half).astype(np.float32)
+        pts[:, a] = np.select([kind == 0, kind == 1, kind == 2, kind == 3, kind == 4], [b, up, dn, far, outside], rnd)
+    pts[::997, 1] = np.nan
+    pts[5::997, 1] = np.inf
+    pts[7::997, 1] = -np.inf
+    pts[11::997, 0] = np.inf       # invalid voxels
+    pts[13::997, 2] = np.nan
+    centers = np.ones((n, 4), dtype=np.float32)
+    centers[:, :3] = pts
+    colors = rng.uniform(0, 1, size=(n, 4)).astype(np.float32)
+    svo = P.SVO(center, half, D, reserve_nodes=1 << 22)
+    ref = orc.OracleSVO(center, half, D)
+    for _ in range(2):
+        svo.integrate_voxels(centers, colors)
+        ref.integrate_voxels(centers, colors)
+    assert svo.size == ref.size
+    assert np.array_equal(svo.pool(), ref.pool())
+    # the same points pre-sorted by key (no invalid ones): the "already in Morton order" decision must survive the fix-ups
+    good = np.isfinite(pts[:, 0]) & np.isfinite(pts[:, 2])
+    keys = orc.compute_keys(pts[good], center, half, D)
+    order = np.argsort(keys, kind="stable")
+    cs, ks = centers[good][order], colors[good][order]
+    svo2 = P.SVO(center, half, D, reserve_nodes=1 << 22)
+    ref2 = orc.OracleSVO(center, half, D)
+    svo2.integrate_voxels(cs, ks)
+    ref2.integrate_voxels(cs, ks)
+    assert np.array_equal(svo2.pool(), ref2.pool())
