@@ -153,6 +153,8 @@ def dist_setup(n_gpus):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     bind_to_gpu_numa_node(local)
+    import __graft_entry__ as graft
+    graft.wait_for_cuda(device=local)  # (a fresh box sometimes refuses the first CUDA initialisation for a few seconds)
     torch.cuda.set_device(local)
     if world > 1:
         import torch.distributed as dist
