@@ -77,5 +77,16 @@ g4 = P.SVO((0, 0, 0), 1.0, Db, reserve_nodes=1 << 23)
 g3.integrate_points(big[:, :3], np.zeros((big.shape[0], 3), dtype=np.uint8))   # big point cloud: pair sort
 g4.integrate_voxels(gb, gc)
 assert g3.size == g4.size and np.array_equal(g3.pool()[0::2], g4.pool()[0::2])
-print("sanitize run ok:", a.size, img.shape, keys.size, v.size, pairs, g1.size)
+# voxel keys on / next to cell boundaries (k_grid_fix, k_grid_fix_check) and an invalid voxel (k_grid_compact)
+edge = big[:200000].copy()
+edge[::3, 0] = np.float32(-1.0) + np.float32(2.0 / 256) * np.arange(edge[::3].shape[0], dtype=np.float32) % np.float32(2.0)
+edge[1::3, 1] = np.nextafter(edge[1::3, 1] - np.float32(1.0 / 256), np.float32(9))
+edge[77, 2] = np.inf
+g5 = P.SVO((0, 0, 0), 1.0, Db, reserve_nodes=1 << 22)
+g5.integrate_voxels(edge, bigcol[:200000])
+# the sparse mesh voxeliser (append + sort + unique) and the reference's thin rule
+Vm, Tm = P.synth.icosphere(3, 0.7, (0.05, 0.0, -0.03))
+cm, km = P.meshToVoxelGrid(Vm, Tm, None, (0, 0, 0), 1.0, 8)
+_, _, cells, tris = P.meshToVoxelGridThin(Vm, Tm, None, Vm.min(axis=0), Vm.max(axis=0), 6)
+print("sanitize run ok:", a.size, img.shape, keys.size, v.size, pairs, g1.size, g5.size, cm.shape[0], cells.shape[0])
 PY
