@@ -26,9 +26,9 @@ namespace cg = cooperative_groups;
 namespace {
 
 constexpr int SB_THREADS = 256;
-// keys per thread and tile: 16 when only keys move (4096-key tiles, 2 CTAs per SM), 8 with a payload (2048, 3 CTAs)
+// keys per thread and tile: 16 when only keys move (4096-key tiles), 12 with a payload (3072 pairs); 2 CTAs per SM
 template <bool PAY> struct SbCfg {
-  static constexpr int ITEMS = PAY ? 8 : 16;
+  static constexpr int ITEMS = PAY ? 12 : 16;
   static constexpr int TILE = SB_THREADS * ITEMS;
 };
 constexpr int SB_WARPS = SB_THREADS / 32;
@@ -134,7 +134,7 @@ __device__ __forceinline__ void sb_prefetch(u64* s_in_k, u32* s_in_p, const u64*
 }
 
 template <bool PAY>
-__global__ void __launch_bounds__(SB_THREADS, PAY ? 3 : 2) k_sort_big(SortBigArgs A) {
+__global__ void __launch_bounds__(SB_THREADS, 2) k_sort_big(SortBigArgs A) {
   constexpr int SB_ITEMS = SbCfg<PAY>::ITEMS, SB_TILE = SbCfg<PAY>::TILE;
   cg::grid_group grid = cg::this_grid();
   if (A.run_flag && *A.run_flag == 0) return;  // (uniform over the grid)
