@@ -1013,86 +1013,102 @@ __device__ __forceinline__ void analyze_block(int vb, int n, const u64* __restri
   __syncthreads();
 }
 
+// Walk the pre-frame tree along `key` down to the leaf's PARENT (depth D-1).  Returns the frontier depth (1..D-1), or
+// OSL_NONE when the path exists that far; then ptile is the parent's child tile.  st = the node at depth m+1 when the
+// walk gets there (m+1 <= D-1).  The leaf test of Q3 is the caller's.
+__device__ __forceinline__ int walk_parent(const u32* __restrict__ pool, u64 key, int D, int m, u64* wcache, u32& st,
+                                           u32& ptile) {
+  u32 node = (u32)key_digit(key, D, 1);
+  int t = 1;
+  const int h = wcache ? walk_cache_depth(D) : 0;
+  u64 prefix = 0;
+  bool fill = false;
+  if (h && m + 1 >= h) {
+    prefix = key >> (3 * (D - h));
+    const u64 e = __ldcg(&wcache[walk_cache_slot(prefix)]);
+    if ((e >> 30) == prefix) { node = (u32)e & OSL_MASK; t = h; }
+    else fill = true;
+  }
+  for (; t <= D - 1; t++) {
+    if (fill && t == h) wcache[walk_cache_slot(prefix)] = (prefix << 30) | (u64)node;
+    if (t == m + 1) st = node;
+    const u32 w0 = pool[2 * (size_t)node];
+    if (!(w0 & OSL_FLAG)) return t;
+    if (t == D - 1) { ptile = w0 & OSL_MASK; break; }
+    node = (w0 & OSL_MASK) + (u32)key_digit(key, D, t + 1);
+  }
+  return OSL_NONE;
+}
+
 // Phase A for a CTA that owns MANY blocks (voxel grids of millions of keys): the per-block counts only matter as the
 // CTA's total -- phase C recomputes every block's prefix on the way -- so the range is streamed without a single block
-// barrier, AN_R keys per thread, and the AN_R tree walks of a thread advance in lockstep: AN_R independent loads in
-// flight per thread instead of one (the walk is a chain of dependent L2 round trips; at 57 M keys phase A took 1.4 ms
-// of which the chain was most).  Keys that miss the walk cache or head levels above it take the scalar walk.
+// barrier.  A warp takes AN_R * 32 CONSECUTIVE sorted keys, and only the keys that open a new parent (common prefix
+// with the predecessor shorter than D-1 digits; the batch's first key always) walk the tree: they are compacted into a
+// per-warp list (a surface fills about four of a parent's eight cells, so 128 keys are ~35 walks instead of 128), a lane
+// walks one list entry from the walk cache down to the parent, and every key then takes frontier and parent tile from
+// the entry of the last opener at or before it.  What is left per key is the leaf test of Q3 (last digit 7 only).
+// Openers that miss the walk cache share one walk from the root per prefix; the few that head levels above the cached
+// depth take the scalar walk.
 #define AN_R 4
+#define AN_HEAD_BYTES (AN_WARPS * AN_R * 32 * 9)  // per warp: AN_R*32 entries of 8 bytes (key -> st:ptile) + 1 byte (m -> s)
 __device__ __forceinline__ void analyze_stream(int j0, int j1, int n, const u64* __restrict__ keys, u32* pay, int mode,
                                                const u32* pool, const TreeParams& tp, uint8_t* __restrict__ m8,
                                                uint8_t* __restrict__ s8, u32* __restrict__ start, u32* s_ctot,
-                                               u32* s_cnt, u64* wcache, u32* s_path, u32* s_shallow, int has_prev,
+                                               u32* s_cnt, unsigned char* s_heads, u64* wcache, int has_prev,
                                                u64 prev_key) {
   const int D = tp.D, NC = OSL_NCOUNT(D);
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int h = wcache ? walk_cache_depth(D) : 0;
+  const u32 lt = lanemask_lt(), le = lt | (1u << lane);
+  u64* s_hk = reinterpret_cast<u64*>(s_heads) + warp * (AN_R * 32);
+  uint8_t* s_hm = s_heads + AN_WARPS * AN_R * 32 * 8 + warp * (AN_R * 32);
   for (int c = tid; c < NC; c += AN_THREADS) s_cnt[c] = 0;
   __syncthreads();
-  for (int base = j0; base < j1; base += AN_THREADS * AN_R) {  // (uniform trip count: the votes below are warp-wide)
-    u64 k[AN_R], e[AN_R];
-    int m[AN_R], s[AN_R];
-    u32 node[AN_R], st[AN_R];
-    unsigned act = 0, slow = 0;
+  for (int base = j0; base < j1; base += AN_THREADS * AN_R) {
+    const int wb = base + warp * (AN_R * 32);  // this warp's keys: [wb, wb + 128)
+    u64 k[AN_R];
+    int m[AN_R], s[AN_R], hidx[AN_R];
+    u32 st[AN_R];
+    int nh = 0;  // openers of this batch
+    u64 before = 0;  // the key in front of the batch
+    bool has_before = false;
+    if (lane == 0 && wb < j1) {
+      if (wb > 0) { before = keys[wb - 1]; has_before = true; }
+      else if (has_prev) { before = prev_key; has_before = true; }
+    }
 #pragma unroll
     for (int r = 0; r < AN_R; r++) {
-      const int j = base + r * AN_THREADS + tid;
-      k[r] = 0; m[r] = D; s[r] = OSL_NONE; st[r] = 0; node[r] = 0; e[r] = ~0ull;
+      const int j = wb + r * 32 + lane;
+      k[r] = j < j1 ? keys[j] : 0ull;
+    }
+#pragma unroll
+    for (int r = 0; r < AN_R; r++) {
+      const int j = wb + r * 32 + lane;
+      u64 pk = __shfl_up_sync(FULL, k[r], 1);
+      bool hp = true;
+      if (lane == 0) {
+        if (r == 0) { pk = before; hp = has_before; }
+      }
+      if (r > 0) {
+        const u64 last = __shfl_sync(FULL, k[r - 1], 31);
+        if (lane == 0) pk = last;
+      }
+      m[r] = D; s[r] = OSL_NONE; st[r] = 0;
       if (j < j1) {
-        k[r] = keys[j];
-        if (j > 0 || has_prev) {
-          const u64 x = k[r] ^ (j > 0 ? keys[j - 1] : prev_key);
-          m[r] = x ? (D - 1 - (63 - __clzll((long long)x)) / 3) : D;
-        } else {
-          m[r] = 0;
-        }
-        if (m[r] < D) {
-          if (h && m[r] + 1 >= h) e[r] = __ldcg(&wcache[walk_cache_slot(k[r] >> (3 * (D - h)))]);
-          else slow |= 1u << r;
-        }
+        const u64 x = k[r] ^ pk;
+        m[r] = !hp ? 0 : (x ? (D - 1 - (63 - __clzll((long long)x)) / 3) : D);
       }
+      const bool opener = j < j1 && (m[r] < D - 1 || (r == 0 && lane == 0));
+      const u32 bal = __ballot_sync(FULL, opener);
+      hidx[r] = nh + __popc(bal & le) - 1;
+      if (opener) { s_hk[hidx[r]] = k[r]; s_hm[hidx[r]] = (uint8_t)m[r]; }
+      nh += __popc(bal);
     }
-#pragma unroll
-    for (int r = 0; r < AN_R; r++) {
-      // A prefix that is not in the table yet is missed by EVERY key below it in this batch -- they all looked it up at
-      // the same time (on average 1 000 keys per depth-h prefix for the cfg2 surface).  One of the lanes that miss the
-      // same prefix walks from the root to depth h, enters it, and hands the node to the others.
-      const u64 prefix = k[r] >> (3 * (D - h));
-      const bool cand = m[r] < D && !((slow >> r) & 1u);
-      const bool hit = cand && (e[r] >> 30) == prefix;
-      if (hit) { node[r] = (u32)e[r] & OSL_MASK; act |= 1u << r; }
-      const bool miss = cand && !hit;
-      const u32 missers = __ballot_sync(FULL, miss);
-      if (missers) {
-        int leader = lane;
-        u32 nh = 0xFFFFFFFFu;
-        if (miss) {
-          leader = __ffs(__match_any_sync(missers, prefix)) - 1;
-          if (lane == leader) {
-            u32 nd = (u32)key_digit(k[r], D, 1);
-            int t = 1;
-            for (; t < h; t++) {
-              const u32 w0 = pool[2 * (size_t)nd];
-              if (!(w0 & OSL_FLAG)) break;
-              nd = (w0 & OSL_MASK) + (u32)key_digit(k[r], D, t + 1);
-            }
-            if (t == h) {
-              nh = nd;
-              wcache[walk_cache_slot(prefix)] = (prefix << 30) | (u64)nd;
-            }
-          }
-        }
-        nh = __shfl_sync(FULL, nh, leader);
-        if (miss) {
-          if (nh != 0xFFFFFFFFu) { node[r] = nh; act |= 1u << r; }
-          else slow |= 1u << r;  // (the tree ends above depth h on this path)
-        }
-      }
-    }
+    __syncwarp();
     if (mode != 2) {  // canonical Q7: the lowest input index of the run of equal keys wins
 #pragma unroll
       for (int r = 0; r < AN_R; r++) {
-        const int j = base + r * AN_THREADS + tid;
+        const int j = wb + r * 32 + lane;
         if (m[r] < D) {
           u32 pm = pay[j];
           for (int jj = j + 1; jj < n && keys[jj] == k[r]; jj++) pm = min(pm, pay[jj]);
@@ -1100,32 +1116,89 @@ __device__ __forceinline__ void analyze_stream(int j0, int j1, int n, const u64*
         }
       }
     }
-    for (int t = h; t <= D && act; t++) {
-      u32 w0[AN_R];
-#pragma unroll
-      for (int r = 0; r < AN_R; r++) {
-        w0[r] = 0;
-        if ((act >> r) & 1u) {
-          if (t == m[r] + 1) st[r] = node[r];
-          if (t < D || (tp.quirks && key_digit(k[r], D, D) == 7)) w0[r] = pool[2 * (size_t)node[r]];
-          else act &= ~(1u << r);  // the whole path exists
+    // ---- the openers' walks, 32 at a time
+    for (int q0 = 0; q0 < nh; q0 += 32) {
+      const int idx = q0 + lane;
+      const bool active = idx < nh;
+      const u64 hk = active ? s_hk[idx] : 0ull;
+      const int hm = active ? (int)s_hm[idx] : D;
+      const u64 prefix = h ? hk >> (3 * (D - h)) : 0ull;
+      const bool cand = active && h && hm + 1 >= h;
+      bool slow = active && !cand;
+      u64 e = ~0ull;
+      if (cand) e = __ldcg(&wcache[walk_cache_slot(prefix)]);
+      const bool hit = cand && (e >> 30) == prefix;
+      u32 node = hit ? ((u32)e & OSL_MASK) : 0u;
+      bool act = hit;
+      // A prefix that is not in the table yet is missed by EVERY opener below it in this row (they are neighbours in key
+      // order).  One of the lanes that miss the same prefix walks from the root to depth h, enters it, and hands the
+      // node to the others.
+      const bool miss = cand && !hit;
+      const u32 missers = __ballot_sync(FULL, miss);
+      if (missers) {
+        int leader = lane;
+        u32 ndh = 0xFFFFFFFFu;
+        if (miss) {
+          leader = __ffs(__match_any_sync(missers, prefix)) - 1;
+          if (lane == leader) {
+            u32 nd = (u32)key_digit(hk, D, 1);
+            int t = 1;
+            for (; t < h; t++) {
+              const u32 w0 = pool[2 * (size_t)nd];
+              if (!(w0 & OSL_FLAG)) break;
+              nd = (w0 & OSL_MASK) + (u32)key_digit(hk, D, t + 1);
+            }
+            if (t == h) {
+              ndh = nd;
+              wcache[walk_cache_slot(prefix)] = (prefix << 30) | (u64)nd;
+            }
+          }
+        }
+        ndh = __shfl_sync(FULL, ndh, leader);
+        if (miss) {
+          if (ndh != 0xFFFFFFFFu) { node = ndh; act = true; }
+          else slow = true;  // (the tree ends above depth h on this path)
         }
       }
+      int fs = OSL_NONE;
+      u32 hst = 0, ptile = 0;
+      for (int t = h; t <= D - 1 && act; t++) {
+        if (t == hm + 1) hst = node;
+        const u32 w0 = pool[2 * (size_t)node];
+        if (!(w0 & OSL_FLAG)) { fs = t; act = false; }
+        else if (t == D - 1) { ptile = w0 & OSL_MASK; act = false; }
+        else node = (w0 & OSL_MASK) + (u32)key_digit(hk, D, t + 1);
+      }
+      if (slow) fs = walk_parent(pool, hk, D, hm, wcache, hst, ptile);
+      if (active) { s_hk[idx] = ((u64)hst << 32) | (u64)ptile; s_hm[idx] = (uint8_t)fs; }
+    }
+    __syncwarp();
+    // ---- every key: frontier and parent tile of its opener; the leaf test of Q3
+    u32 leaf[AN_R], lw[AN_R];
 #pragma unroll
-      for (int r = 0; r < AN_R; r++) {
-        if ((act >> r) & 1u) {
-          if (!(w0[r] & OSL_FLAG)) { s[r] = t; act &= ~(1u << r); }
-          else if (t == D) act &= ~(1u << r);  // (Q3 leaf that already has children)
-          else node[r] = (w0[r] & OSL_MASK) + (u32)key_digit(k[r], D, t + 1);
+    for (int r = 0; r < AN_R; r++) {
+      leaf[r] = 0; lw[r] = OSL_FLAG;
+      if (m[r] < D) {
+        const u64 res = s_hk[hidx[r]];
+        const int fs = (int)s_hm[hidx[r]];
+        const bool own = m[r] < D - 1;  // this key's own entry: st is the node at its depth m+1
+        if (fs != (int)OSL_NONE) {
+          s[r] = fs;
+          st[r] = own ? (u32)(res >> 32) : 0u;
+        } else {
+          leaf[r] = ((u32)res & OSL_MASK) + (u32)key_digit(k[r], D, D);
+          st[r] = own ? (u32)(res >> 32) : leaf[r];
+          if (tp.quirks && key_digit(k[r], D, D) == 7) lw[r] = pool[2 * (size_t)leaf[r]];
         }
       }
     }
 #pragma unroll
     for (int r = 0; r < AN_R; r++)
-      if ((slow >> r) & 1u) s[r] = walk_frontier(pool, k[r], D, tp.quirks, m[r], st[r], wcache, s_path, s_shallow, -1);
+      if (!(lw[r] & OSL_FLAG)) s[r] = D;
+    __syncwarp();  // (the list is rewritten by the next batch)
 #pragma unroll
     for (int r = 0; r < AN_R; r++) {
-      const int j = base + r * AN_THREADS + tid;
+      const int j = wb + r * 32 + lane;
       const bool uniq = m[r] < D;
       if (j < j1) {
         m8[j] = (uint8_t)m[r];
@@ -1405,8 +1478,10 @@ __device__ __forceinline__ void structure_body(const StructArgs& A, int bid, int
   // SM the walk latency is already hidden and the extra serial step only adds two block barriers per block.)
   u64 ck = 0; int cm = D, cs = OSL_NONE, cslot = -1; u32 cst = 0;  // this thread's key state when the CTA owns a single block
   if (BIG && vb1 - vb0 >= 2 && A.shard != 2) {
+    // (phase A's counters take the first row of s_w; the openers' list the rows behind it)
+    static_assert(((NC_MAX * 4 + 7) & ~7) + AN_HEAD_BYTES <= AN_WARPS * NC_MAX * 4, "the openers' list must fit s_w");
     analyze_stream(vb0 * AN_THREADS, min(n, vb1 * AN_THREADS), n, keys, pay, mode, pool, tp, m8, s8, start, s_ctot,
-                   &s_w[0][0], A.wcache, s_path, s_shallow, A.shard ? A.has_prev : 0, A.prev_key);
+                   &s_w[0][0], s_raw + ((NC_MAX * 4 + 7) & ~7), A.wcache, A.shard ? A.has_prev : 0, A.prev_key);
   } else {
     for (int vb = vb0; vb < vb1; vb++)
       if (A.shard != 2)
