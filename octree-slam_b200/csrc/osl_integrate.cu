@@ -901,34 +901,114 @@ __device__ __forceinline__ int key_digit(u64 key, int D, int d) { return (int)((
 __device__ __forceinline__ int walk_cache_depth(int D) { const int h = D - 5 < 11 ? D - 5 : 11; return h >= 3 ? h : 0; }
 __device__ __forceinline__ u32 walk_cache_slot(u64 prefix) { return (u32)((prefix * 0x9E3779B97F4A7C15ull) >> 52); }
 
-__device__ __forceinline__ int walk_frontier(const u32* __restrict__ pool, u64 key, int D, int quirks, int m,
-                                             u32& start, u64* wcache, u32* s_path, u32* s_shallow, int slot) {
+// Hint table: (prefix of t digits, t) -> the node index an earlier walk found there; hashed, direct-mapped, NOT tagged.
+// A walk from the root is a chain of D-1 dependent steps (node -> child tile -> node ...) executed by ONE lane -- 15 L2
+// round trips plus their address arithmetic, 5 us for a depth-16 tree -- and every frame has a few dozen keys that need
+// it: the first key, the first key of every far-away sub-tree (they head levels above the walk cache), keys below a prefix
+// the walk cache does not hold yet.  The slowest key sets the length of phase A.  With the hints the WARP walks such a
+// key: lane t-1 takes level t, loads the hinted node of its level and that node's pool word (two round trips for the
+// whole path), and the links are checked against each other with one shuffle -- level t+1's hint must EQUAL the child the
+// verified level t points to.  A hint is therefore only ever a guess: a wrong, stale or torn one ends the verified part
+// of the path there, the owner walks the rest the ordinary way and refreshes the hints; no result depends on the table
+// (it needs no clearing, no tags, no ordering between writers).
+#define WH_BITS 18
+#define WH_SLOTS (1u << WH_BITS)
+#define WALK_COOP_MAX 4
+__device__ __forceinline__ u32 walk_hint_slot(u64 key, int D, int t) {
+  const u64 p = (key >> (3 * (D - t))) + (u64)t * 0xD6E8FEB86659FD93ull;
+  return (u32)((p * 0x9E3779B97F4A7C15ull) >> (64 - WH_BITS));
+}
+
+// Called by ALL lanes of a warp (active = this lane has a key to walk).  limit: nodes of the pre-frame pool (a hint at or
+// beyond it is not followed).
+__device__ __forceinline__ int walk_frontier(const u32* __restrict__ pool, u64 key, int D, int quirks, int m, bool active,
+                                             u32& start, u64* wcache, u32* s_path, u32* s_shallow, int slot, u32 limit) {
+  const int lane = threadIdx.x & 31;
   u32 node = (u32)key_digit(key, D, 1);
   int t = 1;
   const int h = wcache ? walk_cache_depth(D) : 0;
+  u32* hints = reinterpret_cast<u32*>(wcache + WC_SLOTS);  // (used when h > 0 only)
   u64 prefix = 0;
   bool fill = false;
-  if (h && m + 1 >= h) {  // (the node at depth m+1, which phase C needs, lies at or below the cached depth)
+  if (active && h && m + 1 >= h) {  // (the node at depth m+1, which phase C needs, lies at or below the cached depth)
     prefix = key >> (3 * (D - h));
     const u64 e = __ldcg(&wcache[walk_cache_slot(prefix)]);
     if ((e >> 30) == prefix) { node = (u32)e & OSL_MASK; t = h; }
     else fill = true;
   }
-  for (; t <= D - 1; t++) {
-    if (fill && t == h) wcache[walk_cache_slot(prefix)] = (prefix << 30) | (u64)node;
-    if (t == m + 1) start = node;  // the first node this key heads: where phase C resumes the walk
-    const u32 w0 = pool[2 * (size_t)node];
-    if (!(w0 & OSL_FLAG)) return t;
-    // the child tiles along the last PATH_KEEP levels stay in shared memory: phase C walks the same nodes again
-    if (D - 1 - t < PATH_KEEP) s_path[(D - 1 - t) * AN_THREADS + threadIdx.x] = w0 & OSL_MASK;
-    else if (slot >= 0) s_shallow[t * SHALLOW_SLOTS + slot] = w0 & OSL_MASK;  // (the few keys that head shallow levels)
-    node = (w0 & OSL_MASK) + (u32)key_digit(key, D, t + 1);
+  // Q3: when the last digit is 7 the LEAF is tested as well
+  const bool q3 = quirks && key_digit(key, D, D) == 7;
+  int result = OSL_NONE;
+  bool done = !active;
+  const bool from_root = active && h && t == 1;
+  u32 todo = __ballot_sync(FULL, from_root);
+  // (a prefix that is new to the walk cache is missed by all of its keys at once: when many lanes start at the root they
+  // walk side by side as before -- and leave the hints behind -- rather than queue for the warp)
+  if (__popc(todo) > WALK_COOP_MAX) todo = 0;
+  while (todo) {  // ---- the warp walks the keys that start at the root, one at a time
+    const int src = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const u64 ks = __shfl_sync(FULL, key, src);
+    const int ms = __shfl_sync(FULL, m, src);
+    const int ls = __shfl_sync(FULL, q3 ? 1 : 0, src) ? D : D - 1;  // deepest level tested
+    const int slot_s = __shfl_sync(FULL, slot, src);
+    const int fill_s = __shfl_sync(FULL, fill ? 1 : 0, src);
+    const int tl = lane + 1;  // this lane's level
+    const bool valid = tl <= ls;
+    u32 nd = 0xFFFFFFFFu;
+    if (valid) nd = (tl == 1) ? (u32)key_digit(ks, D, 1) : __ldcg(&hints[walk_hint_slot(ks, D, tl)]);
+    const bool okh = valid && nd < limit;
+    const u32 w = okh ? pool[2 * (size_t)nd] : 0u;
+    const u32 nxt = __shfl_down_sync(FULL, nd, 1);
+    const u32 child = (w & OSL_MASK) + (u32)key_digit(ks, D, tl < D ? tl + 1 : D);
+    const bool link = okh && tl < ls && (w & OSL_FLAG) && child == nxt;
+    const u32 linked = __ballot_sync(FULL, link);
+    const int c = __ffs(~linked) - 1;  // lanes 0..c-1 are linked: the nodes of levels 1..c+1 are the real ones
+    const int tv = c + 1;              // deepest verified level (its pool word is valid: a real node lies below `limit`)
+    const u32 wc = __shfl_sync(FULL, w, c);
+    const u32 child_c = __shfl_sync(FULL, child, c);
+    const bool flag_c = (wc & OSL_FLAG) != 0u;
+    // what the sequential walk does at the levels 1..tv
+    if (tl <= tv && tl <= D - 1 && (tl < tv || flag_c)) {
+      if (D - 1 - tl < PATH_KEEP) s_path[(D - 1 - tl) * AN_THREADS + (threadIdx.x & ~31) + src] = w & OSL_MASK;
+      else if (slot_s >= 0) s_shallow[tl * SHALLOW_SLOTS + slot_s] = w & OSL_MASK;
+    }
+    if (fill_s && tl == h && tl <= tv) {
+      const u64 ph = ks >> (3 * (D - h));
+      wcache[walk_cache_slot(ph)] = (ph << 30) | (u64)nd;
+    }
+    const u32 st_s = __shfl_sync(FULL, nd, ms < 31 ? ms : 31);  // node of level ms+1 (when ms+1 <= tv)
+    if (lane == src) {
+      if (ms + 1 <= tv) start = st_s;
+      if (!flag_c) { result = tv; done = true; }          // frontier (for tv == D: the leaf of Q3 without children)
+      else if (tv == ls) {                                 // the whole path exists
+        if (ms + 1 == D && tv == D - 1) start = child_c;   // (the leaf itself)
+        done = true;
+      } else {                                             // no (or a wrong) hint below level tv: go on from there
+        node = child_c;
+        t = tv + 1;
+      }
+    }
   }
-  if (m + 1 == D) start = node;  // the leaf itself (its whole path exists)
-  if (quirks && key_digit(key, D, D) == 7) {
-    if (!(pool[2 * (size_t)node] & OSL_FLAG)) return D;
+  if (!done) {
+    for (; t <= D - 1; t++) {
+      if (from_root && t >= 2) hints[walk_hint_slot(key, D, t)] = node;
+      if (fill && t == h) wcache[walk_cache_slot(prefix)] = (prefix << 30) | (u64)node;
+      if (t == m + 1) start = node;  // the first node this key heads: where phase C resumes the walk
+      const u32 w0 = pool[2 * (size_t)node];
+      if (!(w0 & OSL_FLAG)) return t;
+      // the child tiles along the last PATH_KEEP levels stay in shared memory: phase C walks the same nodes again
+      if (D - 1 - t < PATH_KEEP) s_path[(D - 1 - t) * AN_THREADS + threadIdx.x] = w0 & OSL_MASK;
+      else if (slot >= 0) s_shallow[t * SHALLOW_SLOTS + slot] = w0 & OSL_MASK;  // (the few keys that head shallow levels)
+      node = (w0 & OSL_MASK) + (u32)key_digit(key, D, t + 1);
+    }
+    if (m + 1 == D) start = node;  // the leaf itself (its whole path exists)
+    if (q3) {
+      if (from_root) hints[walk_hint_slot(key, D, D)] = node;
+      if (!(pool[2 * (size_t)node] & OSL_FLAG)) return D;
+    }
   }
-  return OSL_NONE;
+  return result;
 }
 
 // ------------------------------------------------------------------------------------------------ k_structure
@@ -949,7 +1029,7 @@ __device__ __forceinline__ void analyze_block(int vb, int n, const u64* __restri
                                               uint8_t* __restrict__ s8, u32* __restrict__ start,
                                               u32* s_ctot, u32* s_cnt, u64* wcache, u32* s_path, u32* s_shallow,
                                               u64& k_out, int& m_out, int& s_out, u32& st_out, int& slot_out,
-                                              int has_prev, u64 prev_key) {
+                                              int has_prev, u64 prev_key, u32 limit) {
   const int D = tp.D, NC = OSL_NCOUNT(D);
   k_out = 0; m_out = D; s_out = OSL_NONE; st_out = 0; slot_out = -1;
   for (int c = threadIdx.x; c < NC; c += AN_THREADS) s_cnt[c] = 0;
@@ -957,40 +1037,45 @@ __device__ __forceinline__ void analyze_block(int vb, int n, const u64* __restri
   __syncthreads();
   const int j = vb * AN_THREADS + threadIdx.x;
   if (vb == 0 && threadIdx.x == 0) g_osl_prof[24] = (unsigned long long)clock64();
+  u64 k = 0;
+  int m = D, slot = -1;
   if (j < n) {
-    const u64 k = keys[j];
-    int m = 0;
+    k = keys[j];
+    m = 0;
     if (j > 0 || has_prev) {
       const u64 x = k ^ (j > 0 ? keys[j - 1] : prev_key);
       m = x ? (D - 1 - (63 - __clzll((long long)x)) / 3) : D;
     }
-    int s = OSL_NONE;
     if (m < D) {
       if (mode != 2) {  // canonical Q7: the lowest input index of the run of equal keys wins (runs are short:
         u32 pm = pay[j];  // one entry per 64x32-pixel tile that saw the leaf)
         for (int jj = j + 1; jj < n && keys[jj] == k; jj++) pm = min(pm, pay[jj]);
         pay[j] = pm;
       }
-      u32 st = 0;
-      if (vb == 0 && threadIdx.x == 0) g_osl_prof[25] = (unsigned long long)clock64();
       // a key that heads levels above the last PATH_KEEP (the first key of a frame, of a far-away sub-tree) takes one
       // of the CTA's few shallow-path slots: phase C then finds every child tile of its path in shared memory
-      int slot = -1;
       if (m + 1 < D - PATH_KEEP) {
         slot = (int)atomicAdd(&s_shallow[OSL_MAXD * SHALLOW_SLOTS], 1u);
         if (slot >= SHALLOW_SLOTS) slot = -1;
       }
-      slot_out = slot;
-      s = walk_frontier(pool, k, D, tp.quirks, m, st, wcache, s_path, s_shallow, slot);
-      if (vb == 0 && threadIdx.x == 0) g_osl_prof[26] = (unsigned long long)clock64();
-      start[j] = st;
-      st_out = st;
-      atomicAdd(&s_cnt[OSL_CLVL(D, m + 1)], 1u);  // heads every level d > m
-      if (s != OSL_NONE) {
-        const int lo = (s == D) ? D : max(m + 1, s);
-        if (s == D || lo <= D - 1) atomicAdd(&s_cnt[OSL_CBKT(D, s, lo)], 1u);
-      }
     }
+  }
+  const bool uniq = m < D;  // (j < n)
+  if (vb == 0 && threadIdx.x == 0) g_osl_prof[25] = (unsigned long long)clock64();
+  u32 st = 0;
+  const int s = walk_frontier(pool, k, D, tp.quirks, m, uniq, st, wcache, s_path, s_shallow, slot, limit);  // (whole warps)
+  if (vb == 0 && threadIdx.x == 0) g_osl_prof[26] = (unsigned long long)clock64();
+  if (uniq) {
+    slot_out = slot;
+    start[j] = st;
+    st_out = st;
+    atomicAdd(&s_cnt[OSL_CLVL(D, m + 1)], 1u);  // heads every level d > m
+    if (s != OSL_NONE) {
+      const int lo = (s == D) ? D : max(m + 1, s);
+      if (s == D || lo <= D - 1) atomicAdd(&s_cnt[OSL_CBKT(D, s, lo)], 1u);
+    }
+  }
+  if (j < n) {
     m8[j] = (uint8_t)m;
     s8[j] = (uint8_t)s;
     k_out = k; m_out = m; s_out = s;
@@ -1486,7 +1571,7 @@ __device__ __forceinline__ void structure_body(const StructArgs& A, int bid, int
     for (int vb = vb0; vb < vb1; vb++)
       if (A.shard != 2)
         analyze_block(vb, n, keys, pay, mode, pool, tp, m8, s8, start, s_ctot, &s_w[0][0], A.wcache, s_path, s_shallow,
-                      ck, cm, cs, cst, cslot, A.shard ? A.has_prev : 0, A.prev_key);
+                      ck, cm, cs, cst, cslot, A.shard ? A.has_prev : 0, A.prev_key, size0);
   }
   const bool carried = (vb1 - vb0 == 1) && A.shard != 2;
   // publish this CTA's counter vector behind an epoch flag (every CTA publishes, also one without blocks).  Compact
@@ -2183,8 +2268,9 @@ osl_status osl_integrate_init(osl_svo* t) {
     OSL_CUDA(cudaMalloc(&t->d_bpay[f], (size_t)OSL_BUCKETS * OSL_BUCKET_CAP * sizeof(u32)));
   }
   if (!getenv("OSL_NO_WALK_CACHE")) {
-    OSL_CUDA(cudaMalloc(&t->d_wcache, WC_SLOTS * sizeof(u64)));
-    OSL_CUDA(cudaMemset(t->d_wcache, 0xFF, WC_SLOTS * sizeof(u64)));
+    // (the walk cache, and behind it the hint table of walk_frontier)
+    OSL_CUDA(cudaMalloc(&t->d_wcache, WC_SLOTS * sizeof(u64) + WH_SLOTS * sizeof(u32)));
+    OSL_CUDA(cudaMemset(t->d_wcache, 0xFF, WC_SLOTS * sizeof(u64) + WH_SLOTS * sizeof(u32)));
   }
   return osl_reset_splitters(t);
 }
