@@ -1410,7 +1410,49 @@ __device__ __forceinline__ void assign_block(int vb, int n, const u64* __restric
     if (__popc(who) == 1) {
       const int solo = __ffs(who) - 1;
       const int m_2nd = (int)__reduce_min_sync(FULL, lane == solo ? (unsigned)D : um);
-      if (m_2nd > d0) {
+      // With the path's child tiles in shared memory (a CTA that owns one block) the levels do not depend on each other:
+      // lane i lays out level d0 + i (the first key of a frame heads a dozen levels: 2 us for one lane)
+      const int slot_s = __shfl_sync(FULL, slot, solo);
+      const bool spread = carried && (slot_s >= 0 || D - 1 - d0 < PATH_KEEP);
+      if (m_2nd > d0 && spread) {
+        const u64 ks = __shfl_sync(FULL, k, solo);
+        const u32 node_s = __shfl_sync(FULL, node, solo);
+        const u32 par0 = __shfl_sync(FULL, par_idx, solo);
+        const int ms = (int)m_min, tid_s = (tid & ~31) + solo;
+        auto tile_of = [&](int dd) -> u32 {
+          return (D - 1 - dd < PATH_KEEP) ? s_path[(D - 1 - dd) * AN_THREADS + tid_s] : s_shallow[dd * SHALLOW_SLOTS + slot_s];
+        };
+        const int d = d0 + lane;
+        if (d < m_2nd && ms < d) {
+          const u32 lbase = s_w[warp][OSL_CLVL(D, d)];
+          const u32 ct = tile_of(d);
+          const u32 self = (d == ms + 1) ? node_s : tile_of(d - 1) + (u32)key_digit(ks, D, d);
+          u32 par = par0;
+          if (d > d0) {
+            const u32 lb1 = s_w[warp][OSL_CLVL(D, d - 1)];
+            par = (ms < d - 1) ? lb1 : lb1 - 1u;
+            if (ms < d - 1) lv.fc[lv.off[d - 1] + lb1] = lbase;
+          }
+          const size_t o = lv.off[d] + lbase;
+          lv.ctile[o] = ct;
+          lv.digit[o] = (uint8_t)key_digit(ks, D, d);
+          lv.par[o] = par;
+          lv.self[o] = self;
+        }
+        if (lane == solo) {  // where the warp-wide loop finds this key
+          const int last = m_2nd - 1;
+          const u32 lbl = s_w[warp][OSL_CLVL(D, last)];
+          if (ms < last) {
+            path_tile = tile_of(last);
+            node = path_tile + (u32)key_digit(k, D, last + 1);
+            o_prev = lv.off[last] + lbl;
+            par_idx = lbl;
+          } else {
+            par_idx = lbl - 1u;
+          }
+        }
+        d_main = m_2nd;
+      } else if (m_2nd > d0) {
         if (lane == solo) {
           for (int d = d0; d < m_2nd; d++) {
             const u32 lbase = s_w[warp][OSL_CLVL(D, d)];
