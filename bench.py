@@ -392,7 +392,7 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      # dram__bytes_read.sum + dram__bytes_write.sum of the four kernels of one frame, one ncu --set full
                      # capture (profiles/r01_ncu_full_summary_v07.csv; cold caches: ncu flushes L2 between kernels)
-                     "traffic": 2164992, "traffic_source": "profiles/r02_ncu_full_summary_kframe.csv (one k_frame launch)",
+                     "traffic": 2055168, "traffic_source": "profiles/r02_ncu_full_summary_kframe_v2.csv (one k_frame launch)",
                      "peak_source": peak_src,
                      "kernel": "k_frame: ONE launch per frame whose four roles (emit / sort / structure / values) each "
                                "work on the frame that has reached them; achieved = B_int of one frame / average "

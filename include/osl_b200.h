@@ -333,6 +333,9 @@ osl_status osl_debug_cta_profile(unsigned long long* out);
  * slots), the [min start, max end] %globaltimer nanoseconds of each role: 0 structure, 1 values, 2 emit, 3 sort,
  * 4 CTA arrival before the grid dependency wait.  out (may be NULL) receives 32 x 5 x 2 values.  Synchronizes. */
 osl_status osl_debug_trace(osl_svo* t, int enable, unsigned long long* out);
+/* Test aid: fills the hint table of the structure stage's tree walks (node-index guesses that are verified against the
+ * pool before use) with pseudo-random words; results must not change.  Synchronizes. */
+osl_status osl_debug_scramble_hints(osl_svo* t, unsigned seed);
 /* number of kernels this library has launched in this process (for bench.py's gpu_launches) */
 int64_t osl_launch_count(void);
 

@@ -29,7 +29,7 @@ EXPORTS = [
     "osl_color_to_intensity", "osl_icp_cost",
     "osl_tracker_create", "osl_tracker_destroy", "osl_tracker_reset", "osl_tracker_update", "osl_tracker_update_host",
     "osl_tracker_get_pose", "osl_tracker_pose_device", "osl_tracker_view",
-    "osl_status_string", "osl_last_cuda_error", "osl_version", "osl_frame_result_bytes", "osl_launch_count", "osl_debug_profile", "osl_debug_cta_profile",
+    "osl_status_string", "osl_last_cuda_error", "osl_version", "osl_frame_result_bytes", "osl_launch_count", "osl_debug_profile", "osl_debug_cta_profile", "osl_debug_scramble_hints",
 ]
 
 
@@ -150,6 +150,7 @@ def lib():
         "osl_launch_count": (i64, []),
         "osl_debug_profile": (i32, [vp, i32]),
         "osl_debug_cta_profile": (i32, [vp]),
+        "osl_debug_scramble_hints": (i32, [vp, C.c_uint]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

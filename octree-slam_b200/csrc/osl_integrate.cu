@@ -3069,6 +3069,26 @@ extern "C" osl_status osl_debug_trace(osl_svo* t, int enable, unsigned long long
   return OSL_OK;
 }
 
+// Test aid: overwrites the hint table of the tree walks (walk_frontier) with pseudo-random words -- node indices inside
+// the pool, beyond it, and 0xFFFFFFFF -- to show that no result depends on it.  Synchronizes.
+__global__ void k_scramble_hints(u32* hints, u32 n, u32 seed, u32 size) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  u32 x = (i + 1u) * 0x9E3779B1u ^ seed;
+  x ^= x >> 15; x *= 0x85EBCA77u; x ^= x >> 13; x *= 0xC2B2AE3Du; x ^= x >> 16;
+  const u32 kind = x & 3u;
+  hints[i] = kind == 0 ? 0xFFFFFFFFu : kind == 1 ? x : (x >> 2) % (size ? size : 1u);
+}
+extern "C" osl_status osl_debug_scramble_hints(osl_svo* t, unsigned seed) {
+  if (!t) return OSL_ERR_INVALID;
+  OSL_CUDA(cudaDeviceSynchronize());
+  if (!t->d_wcache) return OSL_OK;
+  k_scramble_hints<<<(WH_SLOTS + 255) / 256, 256>>>(reinterpret_cast<u32*>(t->d_wcache + WC_SLOTS), WH_SLOTS, seed, (u32)t->size);
+  OSL_CUDA(cudaGetLastError());
+  OSL_CUDA(cudaDeviceSynchronize());
+  return OSL_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ sharded build
 // ONE map built by several GPUs ("partition the key space by contiguous Morton ranges ... each GPU
 // all-gathers its per-pass split counts -> exclusive prefix over GPUs -> local ranks become global indices").  Input: a

@@ -206,3 +206,34 @@ def test_one_launch_per_frame_is_really_one_launch(P):
         svo.integrate_depth(d, c, fx, fy, pose)
     svo.sync()
     assert P.lib().osl_launch_count() - l0 == 30 + 3
+
+
+@pytest.mark.parametrize("D", [10, 16, 20])
+def test_walk_hints_are_only_guesses(P, D):
+    """The structure stage walks keys that start at the root with the whole warp: one level per lane, nodes taken from a
+    hint table and the links between the levels verified against the pool (walk_frontier).  A hint may be anything --
+    here the table is overwritten with random words (valid node indices of OTHER nodes, indices beyond the pool,
+    0xFFFFFFFF) before every frame, pipelined and strict: the pools stay equal to the oracle's, word for word."""
+    import torch
+    w, h, n = 320, 240, 12
+    center, half = P.synth.tree_params(D)
+    fx, fy = P.synth.focal(w, h)
+    piped = P.SVO(center, half, D, reserve_nodes=1 << 22).set_pipeline(True)
+    strict = P.SVO(center, half, D, reserve_nodes=1 << 22)
+    ref = orc.OracleSVO(center, half, D)
+    keep = []
+    for k in range(n):
+        pose = P.synth.orbit_pose(3 * k if k < 8 else 300 + 3 * k)
+        depth, rgb = P.synth.make_frame(w, h, pose, seed=k)
+        ref.integrate_depth(depth, rgb, fx, fy, pose)
+        dd, cc = torch.from_numpy(depth).cuda(), torch.from_numpy(rgb).cuda()
+        keep.append((dd, cc))
+        torch.cuda.synchronize()
+        for svo in (piped, strict):
+            if k % 2 == 1 or svo is strict:  # (the scramble synchronizes: every other frame the pipeline stays full)
+                assert P.lib().osl_debug_scramble_hints(svo._h, 1000 * k + D) == 0
+            svo.integrate_depth(dd, cc, fx, fy, pose)
+    want = ref.pool()
+    assert piped.size == ref.size and strict.size == ref.size
+    assert np.array_equal(piped.pool(), want)
+    assert np.array_equal(strict.pool(), want)
