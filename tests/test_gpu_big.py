@@ -1,6 +1,6 @@
 """GPU: inputs of MILLIONS of keys (the cfg2 / cfg5 size class) against the CPU oracle, bit for bit.  From 2^20 expected
 keys on, svoFromVoxelGrid / svoFromPointCloud take the big-input variants of the kernels (k_structure_big: streamed
-phase A with four walks per thread, prefetched phase C; k_levels: leaf-balanced subtree shares; the grid radix sort),
+phase A in which only the keys that open a new parent walk the tree, prefetched phase C; k_levels: leaf-balanced subtree shares; the grid radix sort),
 which the frame-sized tests never reach."""
 import numpy as np
 import pytest
