@@ -1551,6 +1551,7 @@ struct StructArgs {
   FrameState* fs; FrameState* fr; FrameState* hr; uint8_t* m8; uint8_t* s8; u32* start; u32* ctatot;
   u32* flags; u32 epoch; LevelArrays lv; int mode; int capacity; int n_in; int parity; u64* split_out;
   u64* wcache;  // walk cache (NULL = off)
+  u64* lvltag;  // [CTA][OSL_MAXD] per-level counters of the frame-sized exchange, each word tagged with the epoch
   // one map built by several GPUs (osl_shard_*): this rank's keys are a contiguous slice of the globally sorted list
   int shard;          // 0 normal; 1 analyse only: publish the counters, write this rank's totals, stop; 2 assign only
   int has_prev; u64 prev_key;  // the key before the slice (last key of the lower rank): the first key's predecessor
@@ -1594,7 +1595,7 @@ __device__ __forceinline__ void structure_body(const StructArgs& A, int bid, int
   const int vb0 = min(nvb, bid * per), vb1 = min(nvb, vb0 + per);
 
   PROF(16);
-  if (BIG && threadIdx.x == 0 && bid < 1024) g_osl_ctaprof[0][bid] = (unsigned long long)clock64();
+  if (threadIdx.x == 0 && bid < 1024) g_osl_ctaprof[0][bid] = (unsigned long long)clock64();
   // splitters for k_sort_bucket of a later frame: BK_BUCKETS-quantiles of this frame's sorted keys
   if (bid == G - 1 && tid < BK_BUCKETS - 1 && n >= BK_BUCKETS)
     split_out[tid] = keys[(size_t)(((long long)(tid + 1) * n) / BK_BUCKETS)];
@@ -1622,7 +1623,23 @@ __device__ __forceinline__ void structure_body(const StructArgs& A, int bid, int
   u32 mine_split = 0;
   for (int c = D + tid; c < NC; c += AN_THREADS) mine_split |= s_ctot[c];
   const int has_split = __syncthreads_or(mine_split != 0u);
-  if (A.shard != 2) {  // (an assign-only launch finds the vectors and flags its analyse-only launch published)
+  // Frame-sized inputs publish the D per-level counters as SELF-TAGGED 64-bit words, (epoch << 32) | count, bit 31 of
+  // word 0 = "this CTA also published bucket counters": a word is valid the moment it carries this frame's epoch, so the
+  // steady state needs no fence, no flag and no second round trip -- the readers' loads of the counters ARE the wait.
+  // (The flag protocol cost ~2.7 us per frame: the writers' fence, the flag's way to L2, a poll, then the loads of the
+  // counters; tools/frame_timeline.py prints the exchange time of every CTA.)  Counts of this path stay below 2^31.
+  const bool tagged = !BIG && A.shard == 0 && A.lvltag != nullptr;
+  if (tagged) {
+    if (has_split) {  // (rare: the bucket counters go first, fenced)
+      for (int c = D + tid; c < NC; c += AN_THREADS) ctatot[(size_t)bid * NC + c] = s_ctot[c];
+      __syncthreads();
+    }
+    if (tid < D) {
+      if (has_split) __threadfence();
+      const u64 wv = ((u64)epoch << 32) | (u64)s_ctot[tid] | ((tid == 0 && has_split) ? 0x80000000ull : 0ull);
+      *(volatile u64*)&A.lvltag[(size_t)bid * OSL_MAXD + tid] = wv;
+    }
+  } else if (A.shard != 2) {  // (an assign-only launch finds the vectors and flags its analyse-only launch published)
     for (int c = tid; c < (has_split ? NC : D); c += AN_THREADS) ctatot[(size_t)bid * NC + c] = s_ctot[c];
     __syncthreads();
     if (tid == 0) {
@@ -1631,12 +1648,14 @@ __device__ __forceinline__ void structure_body(const StructArgs& A, int bid, int
     }
   }
   PROF(17);
-  if (BIG && threadIdx.x == 0 && bid < 1024) g_osl_ctaprof[1][bid] = (unsigned long long)clock64();
+  if (threadIdx.x == 0 && bid < 1024) g_osl_ctaprof[1][bid] = (unsigned long long)clock64();
 
   // wait for every CTA's vector (all CTAs are co-resident: cooperative launch / first roles of k_frame), then sum them:
   // totals for the plan, exclusive prefix for the own range -- one wait, no grid barrier
   unsigned short* s_list = reinterpret_cast<unsigned short*>(s_scan + AN_WARPS);  // CTAs that published bucket counters
-  if (warp == 0) {
+  if (tagged) {
+    if (tid == 0) s_scan[0] = 0u;
+  } else if (warp == 0) {
     u32 n_list = 0;
     for (int b0 = 0; b0 < G; b0 += 32) {
       const int b = b0 + lane;
@@ -1654,7 +1673,6 @@ __device__ __forceinline__ void structure_body(const StructArgs& A, int bid, int
     __threadfence();
   }
   __syncthreads();
-  const int n_list = (int)s_scan[0];
   PROF(18);
   {
     // per-level counters (always published): 16 groups of CTAs x 32 counter lanes, one batch of independent loads per
@@ -1665,10 +1683,33 @@ __device__ __forceinline__ void structure_body(const StructArgs& A, int bid, int
     if (c < D) {
       for (int b0 = g; b0 < G; b0 += 4 * AN_WARPS) {
         u32 v[4];
+        if (tagged) {
+          u64 tv[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-          const int b = b0 + k * AN_WARPS;
-          v[k] = (b < G) ? __ldcg(&ctatot[(size_t)b * NC + c]) : 0u;
+          for (int k = 0; k < 4; k++) {
+            const int b = b0 + k * AN_WARPS;
+            tv[k] = (b < G) ? *(const volatile u64*)&A.lvltag[(size_t)b * OSL_MAXD + c] : ((u64)epoch << 32);
+          }
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const int b = b0 + k * AN_WARPS;
+            long long spin = 0;  // bounded: a vector that never arrives traps (error to the host) instead of hanging the GPU
+            while ((u32)(tv[k] >> 32) != epoch) {
+              tv[k] = *(const volatile u64*)&A.lvltag[(size_t)b * OSL_MAXD + c];
+              if (++spin > (1ll << 31)) __trap();
+            }
+            v[k] = (u32)tv[k];
+            if (c == 0 && (v[k] & 0x80000000u)) {  // this CTA published bucket counters as well
+              v[k] &= 0x7FFFFFFFu;
+              s_list[atomicAdd(&s_scan[0], 1u)] = (unsigned short)b;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const int b = b0 + k * AN_WARPS;
+            v[k] = (b < G) ? __ldcg(&ctatot[(size_t)b * NC + c]) : 0u;
+          }
         }
 #pragma unroll
         for (int k = 0; k < 4; k++) {
@@ -1680,6 +1721,8 @@ __device__ __forceinline__ void structure_body(const StructArgs& A, int bid, int
     s_red[g * 64 + c] = tot;
     s_red[g * 64 + 32 + c] = pre;
     __syncthreads();
+    const int n_list = (int)s_scan[0];
+    if (tagged && n_list > 0) __threadfence();  // (the bucket counters were written before the tagged words)
     if (tid < D) {
       u32 t2 = 0, p2 = 0;
 #pragma unroll
@@ -1756,7 +1799,7 @@ __device__ __forceinline__ void structure_body(const StructArgs& A, int bid, int
   const long long after = (long long)size0 + 8ll * n_split;
   const bool overflow = after > (long long)capacity;
   PROF(21);
-  if (BIG && threadIdx.x == 0 && bid < 1024) g_osl_ctaprof[2][bid] = (unsigned long long)clock64();
+  if (threadIdx.x == 0 && bid < 1024) g_osl_ctaprof[2][bid] = (unsigned long long)clock64();
   if (!overflow) {
     if (BIG && !carried) {
       // many blocks per CTA: the next block's inputs are loaded while this one is laid out (each block otherwise starts
@@ -1787,7 +1830,7 @@ __device__ __forceinline__ void structure_body(const StructArgs& A, int bid, int
     }
   }
   PROF(22);
-  if (BIG && threadIdx.x == 0 && bid < 1024) g_osl_ctaprof[3][bid] = (unsigned long long)clock64();
+  if (threadIdx.x == 0 && bid < 1024) g_osl_ctaprof[3][bid] = (unsigned long long)clock64();
 
   // Book-keeping by the LAST CTA (the grid is sized with a margin, so it usually has no block of its own and this
   // stays off the critical path): the frame's result block, to the device copy k_levels reads and straight to the
@@ -2254,7 +2297,7 @@ osl_status osl_ensure_workspace(osl_svo* t, size_t n) {
   cudaFree(t->d_m); cudaFree(t->d_s); cudaFree(t->d_blockcnt);
   for (int b = 0; b < OSL_BACK; b++) { cudaFree(t->d_level_mem[b]); t->d_level_mem[b] = nullptr; }
   cudaFree(t->d_keysC); cudaFree(t->d_payC); cudaFree(t->d_start); cudaFree(t->d_flags);
-  t->d_keysC = nullptr; t->d_payC = nullptr; t->d_start = nullptr; t->d_flags = nullptr;
+  t->d_keysC = nullptr; t->d_payC = nullptr; t->d_start = nullptr; t->d_flags = nullptr; t->d_lvltag = nullptr;
   t->d_m = t->d_s = nullptr;
   t->d_blockcnt = nullptr;
   t->ws_cap = 0;
@@ -2272,8 +2315,11 @@ osl_status osl_ensure_workspace(osl_svo* t, size_t n) {
   const size_t nctas = (size_t)(t->structure_grid > 0 ? t->structure_grid : 1);
   OSL_CUDA(cudaMalloc(&t->d_blockcnt, nctas * OSL_NCOUNT(D) * sizeof(u32)));  // one counter vector per CTA
   OSL_CUDA(cudaMalloc(&t->d_start, cap * sizeof(u32)));
-  OSL_CUDA(cudaMalloc(&t->d_flags, nctas * sizeof(u32)));
-  OSL_CUDA(cudaMemset(t->d_flags, 0, nctas * sizeof(u32)));  // epoch-tagged (frame number + 1), never reset
+  // (flags, then -- 8-byte aligned -- the tagged per-level counter words of the frame-sized exchange)
+  const size_t flag_bytes = (nctas * sizeof(u32) + 7) & ~(size_t)7;
+  OSL_CUDA(cudaMalloc(&t->d_flags, flag_bytes + nctas * OSL_MAXD * sizeof(u64)));
+  OSL_CUDA(cudaMemset(t->d_flags, 0, flag_bytes + nctas * OSL_MAXD * sizeof(u64)));  // epoch-tagged (frame number + 1), never reset
+  t->d_lvltag = reinterpret_cast<u64*>(reinterpret_cast<unsigned char*>(t->d_flags) + flag_bytes);
   for (int b = 0; b < OSL_BACK; b++) {
     LevelArrays& lv = t->lv[b];
     size_t total = 0;
@@ -2387,6 +2433,7 @@ static StructArgs make_struct_args(osl_svo* t, const u64* skeys, u32* spay, Fram
   A.epoch = (u32)(f + 1); A.lv = lv; A.mode = mode; A.capacity = (int)t->cap_nodes; A.n_in = n; A.parity = fslot;
   A.split_out = t->d_split + fslot * BK_BUCKETS;
   A.wcache = t->d_wcache;
+  A.lvltag = t->d_lvltag;
   return A;
 }
 

@@ -186,6 +186,7 @@ struct osl_svo {
   uint8_t *d_m, *d_s;
   u32* d_start;       // per sorted key: node at the first depth it heads (k_structure phase A -> C)
   u32* d_flags;       // per virtual block: epoch of the frame whose count vector is published
+  u64* d_lvltag;      // inside the d_flags allocation: [CTA][OSL_MAXD] epoch-tagged per-level counters (frame-sized exchange)
   u32* d_blockcnt;    // [k_structure CTAs][NC] per-CTA counter vectors
   u32* d_blockcnt_tot;  // sharded build: [3][NC_MAX] this rank's totals, then the external base / totals
   int shard_n, shard_lo, shard_grid; unsigned long long shard_f;  // between osl_shard_analyze and osl_shard_assign

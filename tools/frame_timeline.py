@@ -74,6 +74,16 @@ def main():
     prof = (C.c_uint64 * 128)()
     lib.osl_debug_profile(prof, 128)
     mhz = 1965.0
+    # per-CTA phase lengths of the LAST structure launch (SM clocks: only differences inside one CTA are meaningful)
+    cp = (C.c_uint64 * 4096)()
+    lib.osl_debug_cta_profile(cp)
+    q = np.array(cp[:], dtype=np.float64).reshape(4, 1024)
+    live = (q[0] > 0) & (q[3] > q[2]) & (q[1] > q[0])
+    if live.any():
+        idx = np.nonzero(live)[0]
+        print("structure role, last launch, per CTA: analyze / exchange+plan / assign [us]")
+        print("   " + "  ".join("%d:%.1f/%.1f/%.1f" % (i, (q[1][i] - q[0][i]) / mhz, (q[2][i] - q[1][i]) / mhz, (q[3][i] - q[2][i]) / mhz)
+                              for i in idx))
     for kern, phases in NAMES.items():
         print(kern)
         for a_, b_, name in phases:
