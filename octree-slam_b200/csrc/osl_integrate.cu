@@ -1684,6 +1684,7 @@ __device__ __forceinline__ void structure_body(const StructArgs& A, int bid, int
       for (int b0 = g; b0 < G; b0 += 4 * AN_WARPS) {
         u32 v[4];
         if (tagged) {
+          bool saw_split = false;
           u64 tv[4];
 #pragma unroll
           for (int k = 0; k < 4; k++) {
@@ -1702,8 +1703,12 @@ __device__ __forceinline__ void structure_body(const StructArgs& A, int bid, int
             if (c == 0 && (v[k] & 0x80000000u)) {  // this CTA published bucket counters as well
               v[k] &= 0x7FFFFFFFu;
               s_list[atomicAdd(&s_scan[0], 1u)] = (unsigned short)b;
+              saw_split = true;
             }
           }
+          // acquire side of the bucket counters: the thread that observed the mark fences BEFORE the block barrier
+          // behind which the other threads read them (the flag protocol's order: poll, fence, barrier, loads)
+          if (saw_split) __threadfence();
         } else {
 #pragma unroll
           for (int k = 0; k < 4; k++) {
@@ -1722,7 +1727,6 @@ __device__ __forceinline__ void structure_body(const StructArgs& A, int bid, int
     s_red[g * 64 + 32 + c] = pre;
     __syncthreads();
     const int n_list = (int)s_scan[0];
-    if (tagged && n_list > 0) __threadfence();  // (the bucket counters were written before the tagged words)
     if (tid < D) {
       u32 t2 = 0, p2 = 0;
 #pragma unroll
